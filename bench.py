@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- Biot-Savart pair-interactions/s on the synthetic multirotor wake (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference OpenMP path
+
+One "step" = one wake-convection stage of the hot path at the named size: re-pack the filament set from
+the device-resident wake lattices, sweep every convected wake node (targets) against every filament
+(sources) with the sm_100a kernel, convect the nodes, and (N > 1) all-gather the updated node slices
+over NCCL and scatter them back into the lattices.  Work is fixed as N grows (targets are sharded):
+strong scaling.  `value` = total pair interactions of all ranks / max-over-ranks device time.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOPS_PER_PAIR = 76        # algorithmic flops of vf_vind as written + gam scale/accumulate
+PIPE_INSTR_PER_PAIR = 44   # FP64-pipe instructions per pair in bs_sweep_kernel (SASS count)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--filaments", type=int, default=1_000_000)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--T", type=int, default=0, help="targets per thread (0 = auto)")
+    ap.add_argument("--nsplit", type=int, default=0, help="source splits (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload(args):
+    from volcanor_b200 import synth
+    lats = synth.multirotor(args.filaments, seed=args.seed)
+    n_src = sum(l.n_filaments() for l in lats)
+    m = sum(l.targets().shape[0] for l in lats)
+    name = (f"synthetic 4-rotor(2 blades)+wing wake, {n_src} filaments x {m} wake-node targets, "
+            f"seed {args.seed} (BASELINE.json configs[4] at ~1e{int(round(np.log10(max(n_src, 1))))})")
+    return lats, n_src, m, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(args, p1, p2, rvc, gam, flag, P, seconds: float):
+    """C restatement of the reference OpenMP path (oracle, 'port') on the host cores, bounded sample."""
+    from oracle import pyoracle
+    pyoracle.build()
+    lib = None
+    tmp = tempfile.mkdtemp(prefix="vlc_native_")
+    nat = pyoracle.build_native(Path(tmp))
+    flags = "-O2 -march=native -fopenmp"
+    if nat is not None:
+        try:
+            lib = pyoracle.load(path=nat)
+        except OSError:
+            lib = None
+    if lib is None:
+        lib = pyoracle.load("omp")
+        flags = "-O2 -march=x86-64-v3 -fopenmp (prebuilt)"
+    os.environ.setdefault("OMP_SCHEDULE", "dynamic,16")
+    cores = lib.orc_num_threads()
+    n = rvc.size
+    probe = min(P.shape[0], max(cores * 4, 64))
+    t0 = time.perf_counter()
+    pyoracle.vind_flat(p1, p2, rvc, gam, flag, P[:probe], lib=lib)
+    dt = time.perf_counter() - t0
+    rate = probe * n / max(dt, 1e-9)
+    m_s = int(min(P.shape[0], max(probe, rate * seconds / n)))
+    idx = np.linspace(0, P.shape[0] - 1, m_s).astype(np.int64)
+    Ps = np.ascontiguousarray(P[idx])
+    t0 = time.perf_counter()
+    pyoracle.vind_flat(p1, p2, rvc, gam, flag, Ps, lib=lib)
+    dt = time.perf_counter() - t0
+    return {"value": m_s * n / dt, "unit": "pair-interactions/s", "cores": int(cores), "kind": "port",
+            "sample": f"{m_s} evenly spaced targets x all {n} filaments of the same workload, "
+                      f"{dt:.1f} s, gcc {flags}, OMP_SCHEDULE={os.environ.get('OMP_SCHEDULE')}",
+            "lib": lib, "m_sample": m_s}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path (C restatement; no Fortran compiler exists here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from volcanor_b200 import synth
+    lats, n_src, m, name = workload(args)
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    P = synth.targets_all(lats)
+    base = cpu_baseline(args, p1, p2, rvc, gam, flag, P, seconds=3.0)
+    lib, m_s = base.pop("lib"), base.pop("m_sample")
+    from oracle import pyoracle
+    idx = np.linspace(0, P.shape[0] - 1, m_s).astype(np.int64)
+    Ps = np.ascontiguousarray(P[idx])
+    for _ in range(args.warmup):
+        pyoracle.vind_flat(p1, p2, rvc, gam, flag, Ps, lib=lib)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pyoracle.vind_flat(p1, p2, rvc, gam, flag, Ps, lib=lib)
+    dt = time.perf_counter() - t0
+    val = args.steps * m_s * n_src / dt
+    base["value"] = val
+    base["sample"] = (f"each step = {m_s} evenly spaced targets x all {n_src} filaments (bounded sample of the "
+                      f"workload), C restatement of the reference OpenMP loops (libCommon.f90:132-146)")
+    out = {"impl": "reference", "metric": "biot_savart_pair_interactions_per_s", "value": val,
+           "unit": "pair-interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": {"workload": name, "filaments": n_src, "targets": m},
+           "cpu_baseline": base,
+           "e2e": {"value": val, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import volcanor_b200 as vb
+    from volcanor_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (volcanor_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lats, n_src, m, name = workload(args)
+    ctx = vb.Context(local)
+    ctx.set_tuning(args.T, args.nsplit)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- device-resident wake state (node-indexed SoA per lattice) ----
+    d = []
+    for l in lats:
+        d.append({"R": l.R, "S": l.S, "F": l.F,
+                  "nodes": torch.from_numpy(l.nodes).to(dev), "gam": torch.from_numpy(l.gam).to(dev),
+                  "rvc4": torch.from_numpy(l.rvc4).to(dev),
+                  "far": torch.from_numpy(l.far_nodes).to(dev) if l.F > 0 else None,
+                  "gamF": torch.from_numpy(l.gamF).to(dev) if l.F > 0 else None,
+                  "rvcF": torch.from_numpy(l.rvcF).to(dev) if l.F > 0 else None})
+    # target list = convected nodes of every lattice (+ far-chain nodes), padded to world * per
+    per = (m + world - 1) // world
+    P_all = torch.zeros(world * per, 3, dtype=torch.float64, device=dev)
+    lo, hi = rank * per, min((rank + 1) * per, m)
+    m_loc = max(0, hi - lo)
+    V_loc = torch.zeros(per, 3, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dt_step = 1e-9
+
+    def gather_targets():
+        off = 0
+        for L in d:
+            k = L["R"] * (L["S"] + 1)
+            ctx.lattice_targets_dev(L["R"], L["S"], L["nodes"], P_all[off:off + k])
+            off += k
+            if L["F"] > 0:
+                P_all[off:off + L["F"]].copy_(L["far"][1:])
+                off += L["F"]
+
+    def scatter_targets():
+        off = 0
+        for L in d:
+            k = L["R"] * (L["S"] + 1)
+            ctx.lattice_scatter_dev(L["R"], L["S"], L["nodes"], P_all[off:off + k])
+            off += k
+            if L["F"] > 0:
+                L["far"][1:].copy_(P_all[off:off + L["F"]])
+                off += L["F"]
+
+    def pack():
+        for i, L in enumerate(d):
+            ctx.pack_lattice_dev(0, i > 0, L["R"], L["S"], L["nodes"], L["gam"], L["rvc4"], L["F"], L["far"],
+                                 L["gamF"], L["rvcF"])
+
+    ev_k0, ev_k1 = [], []
+
+    def step(record=False):
+        flush.zero_()                                  # L2 flush (inside the timed region, ~0.05 ms)
+        pack()                                         # filament records from the current lattices
+        gather_targets()
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        if m_loc > 0:
+            ctx.vind_dev(0, m_loc, P_all[lo:hi], V_loc)    # THE sweep: m_loc targets x n_src filaments
+        if record:
+            e1.record(stream)
+            ev_k0.append(e0)
+            ev_k1.append(e1)
+        if m_loc > 0:
+            ctx.convect_dev(m_loc, P_all[lo:hi], V_loc, dt_step)
+        if world > 1:
+            dist.all_gather_into_tensor(P_all, P_all[rank * per:(rank + 1) * per].clone())
+        scatter_targets()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pack()
+    assert ctx.num_sources(0) == n_src, (ctx.num_sources(0), n_src)
+    fp64_peak, _ = ctx.measure_fp64_peak(20000)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for _ in range(args.steps):
+        step(record=True)
+    t1.record(stream)
+    barrier()
+    elapsed_ms = t0.elapsed_time(t1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)])) if ev_k0 else 0.0
+    tt = torch.tensor([elapsed_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    elapsed_ms, kern_ms_max = float(tt[0]), float(tt[1])
+    pairs_step = float(m) * float(n_src)
+    value = pairs_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+        P_host = synth.targets_all(lats)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hp1, hp2, hr, hg, hf = pin(p1), pin(p2), pin(rvc), pin(gam), pin(flag)
+        hP = pin(P_host[lo:hi]) if m_loc > 0 else None
+        hV = torch.empty(max(m_loc, 1), 3, dtype=torch.float64).pin_memory()
+        lib, h = ctx.lib, ctx.h
+
+        def e2e_step():
+            ctx._ck(lib.vlc_set_sources(h, 1, n_src, hp1.data_ptr(), hp2.data_ptr(), hr.data_ptr(), hg.data_ptr(),
+                                        hf.data_ptr()))
+            if m_loc > 0:
+                ctx._ck(lib.vlc_vind(h, 1, m_loc, hP.data_ptr(), hV.data_ptr()))
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        w = time.perf_counter() - w0
+        tw = torch.tensor([w], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e = {"value": pairs_step * args.steps / float(tw[0]), "unit": "pair-interactions/s",
+               "h2d_bytes_per_step": int(8 * 8 * n_src + n_src + 24 * m_loc), "d2h_bytes_per_step": int(24 * m_loc),
+               "call": "vlc_set_sources + vlc_vind (host buffers, pinned), per rank: all sources, its target slice",
+               "ms_per_step": 1e3 * float(tw[0]) / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (bs_sweep_kernel), measured live with CUDA events ----
+    pairs_launch = float(m_loc) * float(n_src)
+    achieved = pairs_launch * FLOPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12 if kern_ms_max > 0 else 0.0
+    peak = fp64_peak / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "kernel": "bs_sweep_kernel", "kernel_ms": kern_ms_max, "pairs_per_launch": pairs_launch,
+                "flops_per_pair": FLOPS_PER_PAIR,
+                "pipe_frac": pairs_launch * PIPE_INSTR_PER_PAIR * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
+                "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); "
+                               "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
+                "note": "compute-bound pairwise N-body on the FP64 pipe (no tensor cores by construction); "
+                        "frac = algorithmic 76 flop/pair, pipe_frac = issued 44 FP64 instr/pair"}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+        cpu = cpu_baseline(args, p1, p2, rvc, gam, flag, synth.targets_all(lats), args.cpu_seconds)
+        cpu.pop("lib")
+        cpu.pop("m_sample")
+
+    out = {"metric": "biot_savart_pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
+           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": name, "filaments": n_src, "targets": m, "targets_per_rank": per,
+                      "step": "pack lattices -> sweep (targets slice x all filaments) -> convect -> all-gather -> scatter",
+                      "l2": "flushed every step by a 256 MiB memset inside the timed region",
+                      "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather/stage",
+                      "tuning": {"T": args.T, "nsplit": args.nsplit}},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "stages_per_s": args.steps / (elapsed_ms * 1e-3),
+           "fp64_peak_measured_tflops": peak}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/*
+ * volcanor_b200.h -- C ABI of the B200-native Biot-Savart hot path of VOLCANOR.
+ *
+ * This is the drop-in boundary.  The reference (cibinjoseph/VOLCANOR, Fortran 2008 + OpenMP,
+ * one statically linked program) has no FFI of its own; the entry points below are what an
+ * `iso_c_binding` shim (fortran/libGPU.f90) binds so that the driver's
+ * call sites stay unchanged.  Each entry point names the reference procedure it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns 0 on success, non-zero on failure; vlc_last_error(ctx) gives the
+ *     message (the Fortran shim turns it into `error stop`, like the reference's own
+ *     `error stop` sites, e.g. libCommon.f90:168, libMath.f90:73).
+ *   - arrays are column-major exactly as Fortran passes them: a `real(dp) :: P(3, m)` is
+ *     `const double P[3*m]` with xyz fastest.
+ *   - "records" are the reference's derived types viewed as arrays of doubles
+ *     (`transfer(blade%waN, buf)`): vr_class = 50 doubles (classdef.f90:81-104), Fwake_class = 13
+ *     doubles (:198-220), wingpanel_class = 104 doubles (:106-179).  See VLC_*_DOUBLES.
+ *   - host-pointer entry points copy in and out synchronously; `_dev` entry points take device
+ *     pointers and are asynchronous on the context's stream (vlc_set_stream / vlc_sync).
+ *   - there is no CPU fallback: without a CUDA device vlc_create fails.
+ *   - the caller is single-threaded per context (the reference calls these sites from the
+ *     master thread, outside OpenMP regions).
+ */
+#ifndef VOLCANOR_B200_H
+#define VOLCANOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vlc_ctx vlc_ctx;
+
+#define VLC_VF_DOUBLES 12         /* vf_class        classdef.f90:57-79   */
+#define VLC_VR_DOUBLES 50         /* vr_class        classdef.f90:81-104  */
+#define VLC_FWAKE_DOUBLES 13      /* Fwake_class     classdef.f90:198-220 */
+#define VLC_WINGPANEL_DOUBLES 104 /* wingpanel_class classdef.f90:106-179 */
+#define VLC_NPFWAKE 240           /* pFwake_class    classdef.f90:225     */
+#define VLC_MAX_SETS 8
+
+enum {
+  VLC_OK = 0,
+  VLC_ERR_CUDA = 1,     /* CUDA runtime / cuSOLVER failure */
+  VLC_ERR_ARG = 2,      /* bad argument */
+  VLC_ERR_STATE = 3,    /* call order (e.g. solve before calcAIC) */
+  VLC_ERR_SINGULAR = 4, /* 'Matrix is numerically singular!' libMath.f90:73 */
+  VLC_ERR_NODEVICE = 5
+};
+
+/* ---- context ---------------------------------------------------------------------------- */
+int vlc_create(int device, vlc_ctx** out);
+int vlc_destroy(vlc_ctx* ctx);
+const char* vlc_last_error(const vlc_ctx* ctx); /* ctx may be NULL: error of the last failed vlc_create */
+const char* vlc_version(void);
+int vlc_set_stream(vlc_ctx* ctx, void* cuda_stream); /* NULL -> the context's own stream */
+int vlc_sync(vlc_ctx* ctx);
+/* sm_count, compute capability major/minor, bytes of device memory */
+int vlc_device_info(vlc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes);
+/* Launch shape of the sweep kernel: targets_per_thread in {1,2,3,4} (0 = auto),
+ * nsplit = source splits (0 = auto).  Only affects speed and summation order, never the pair formula. */
+int vlc_set_tuning(vlc_ctx* ctx, int targets_per_thread, int nsplit);
+/* Kernels launched by this context since creation (for bench.py's gpu_launches). */
+int64_t vlc_launch_count(const vlc_ctx* ctx);
+
+/* ---- tier 1: flat filament sets --------------------------------------------------------- */
+/*
+ * Load source set `set` (0 <= set < VLC_MAX_SETS) with n straight vortex filaments.
+ * p1, p2: (3, n) end points = vf%fc(:,1), vf%fc(:,2); rvc: core radius vf%rVc; gam: circulation of
+ * the ring / far-wake element that owns the filament (negative for the horseshoe correction,
+ * classdef.f90:1461).  wake_flag (may be NULL = all 0): non-zero applies the wake rule
+ * `abs(gam) > eps` (classdef.f90:1452, :1466, :1472); wing filaments are never skipped (:1350-1355).
+ */
+int vlc_set_sources(vlc_ctx* ctx, int set, int64_t n, const double* p1, const double* p2, const double* rvc,
+                    const double* gam, const uint8_t* wake_flag);
+int vlc_set_sources_dev(vlc_ctx* ctx, int set, int64_t n, const double* d_p1, const double* d_p2,
+                        const double* d_rvc, const double* d_gam, const uint8_t* d_wake_flag);
+int64_t vlc_num_sources(const vlc_ctx* ctx, int set);
+/*
+ * V(:, t) = sum_k gam_k * vf_vind(filament_k, P(:, t))   -- vf_vind = classdef.f90:476-503.
+ * One call replaces one OpenMP target loop (libCommon.f90:132-146, :190-195; main.f90:528-573).
+ * P, V: (3, m).  V is overwritten.
+ */
+int vlc_vind(vlc_ctx* ctx, int set, int64_t m, const double* P, double* V);
+int vlc_vind_dev(vlc_ctx* ctx, int set, int64_t m, const double* d_P, double* d_V);
+/* Only sources [first, first+count) of the set; first must be a multiple of vlc_source_tile(). */
+int vlc_vind_range_dev(vlc_ctx* ctx, int set, int64_t first, int64_t count, int64_t m, const double* d_P,
+                       double* d_V);
+int vlc_source_tile(void);
+
+/* ---- tier 2: the reference's rotor-level call sites ---------------------------------------- */
+/* Declare rotor ir (0-based) -- sizes as rotor_class (classdef.f90:363): nb blades, nc x ns wing
+ * panels, nNwake near-wake rows, nFwake far-wake rows; surfaceType as rotor%surfaceType (+-1 lifting,
+ * +-2 non-lifting: vind_bywing returns 0, classdef.f90:4437-4441 + :544-554). */
+int vlc_rotor_define(vlc_ctx* ctx, int ir, int nb, int nc, int ns, int nNwake, int nFwake, int surfaceType);
+/* rotor%rowNear, rotor%rowFar (1-based, as in the reference, main.f90:412-417). */
+int vlc_rotor_set_rows(vlc_ctx* ctx, int ir, int rowNear, int rowFar);
+/* Upload blade ib (0-based) state in reference record layout. predicted != 0 -> waNPredicted etc. */
+int vlc_rotor_put_wing(vlc_ctx* ctx, int ir, int ib, const double* wiP /* nc*ns x 104 */);
+int vlc_rotor_put_nwake(vlc_ctx* ctx, int ir, int ib, int predicted, const double* waN /* nNwake*ns x 50 */);
+int vlc_rotor_put_fwake(vlc_ctx* ctx, int ir, int ib, int predicted, const double* waF /* nFwake x 13 */);
+int vlc_rotor_put_pfwake(vlc_ctx* ctx, int ir, int ib, int predicted, const double* wapF /* 240 x 13 */);
+/* Only the circulations of the wing rings: gam (nc*ns) for blade ib = rotor_map_gam (classdef.f90:4181). */
+int vlc_rotor_put_wing_gam(vlc_ctx* ctx, int ir, int ib, const double* gam);
+
+/* = rotor%vind_bywing(P) classdef.f90:4424, batched over m points */
+int vlc_rotor_vind_bywing(vlc_ctx* ctx, int ir, int64_t m, const double* P, double* V);
+/* = rotor%vind_bywake(P [, 'P']) classdef.f90:4459 */
+int vlc_rotor_vind_bywake(vlc_ctx* ctx, int ir, int predicted, int64_t m, const double* P, double* V);
+/* = rotor%vind_bywing_boundVortices(P) classdef.f90:4445 */
+int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* ctx, int ir, int64_t m, const double* P, double* V);
+/* = vind_bywing(P) + vind_bywake(P[, 'P']) of rotor ir in one sweep */
+int vlc_rotor_vind(vlc_ctx* ctx, int ir, int predicted, int64_t m, const double* P, double* V);
+/*
+ * = vind_onNwake_byRotor(rotor(ir), Nwake[, 'P'])  libCommon.f90:114-171.
+ * Nwake: slice of Nwake_class records, element (i, j) at Nwake + 50*((i-1) + ld*(j-1)),
+ * rows x cols; vindArray: (3, rows, cols+1).
+ */
+int vlc_vind_onNwake_byRotor(vlc_ctx* ctx, int ir, const double* Nwake, int rows, int cols, int ld, int predicted,
+                             double* vindArray);
+/* = vind_onFwake_byRotor(rotor(ir), Fwake[, 'P'])  libCommon.f90:173-211; vindArray (3, rows). */
+int vlc_vind_onFwake_byRotor(vlc_ctx* ctx, int ir, const double* Fwake, int rows, int predicted,
+                             double* vindArray);
+
+/* = rotor%calcAIC() classdef.f90:4151-4179: assembles AIC on the device from the uploaded wing
+ * (CP, nCap, vortex rings) and LU-factors it (cuSOLVER getrf; the reference's explicit inverse
+ * inv2 = DGETRF+DGETRI, libMath.f90:48-83, is replaced by factor-once / getrs-per-step).
+ * AIC_out (N x N column-major, N = nc*ns*nb) may be NULL. */
+int vlc_rotor_calcAIC(vlc_ctx* ctx, int ir, double* AIC_out);
+/* gamVec = AIC^-1 * RHS, replaces matmulAX(AIC_inv, RHS) (main.f90:190, :596). */
+int vlc_rotor_solve(vlc_ctx* ctx, int ir, const double* RHS, double* gamVec);
+/* AIC_inv (N x N) if the caller wants the explicit inverse the reference stores. */
+int vlc_rotor_get_AIC_inv(vlc_ctx* ctx, int ir, double* AIC_inv);
+
+/* ---- tier 3: device-resident wake state (node-indexed SoA) -------------------------------- */
+/*
+ * A "lattice" is one blade's near wake kept on the device as TE nodes: nodes(3, nrows+1, ns+1)
+ * where node row r (0-based) is the leading edge of ring row r and the trailing edge of row r-1;
+ * ring (r, j) has corners 1=(r,j) 2=(r+1,j) 3=(r+1,j+1) 4=(r,j+1) (vr_assignP, classdef.f90:569-592),
+ * so the re-stitch of blade_wake_continuity (classdef.f90:1609-1702) is implicit.
+ * Declared in wake_state section of DESIGN.md; entry points below operate on flat device arrays so
+ * that bench.py / the multi-GPU driver can shard targets and all-gather node slices.
+ */
+/* x(3,n) += v(3,n) * dt   -- vr_shiftdP / Fwake_shiftdP with U*dt (classdef.f90:1531, :1545) */
+int vlc_convect_dev(vlc_ctx* ctx, int64_t n, double* d_x, const double* d_v, double dt);
+/* Adams-Bashforth predictor velocity: out = 0.5*(3 v - v1)  (main.f90:1032-1034) */
+int vlc_ab2_dev(vlc_ctx* ctx, int64_t n, const double* d_v, const double* d_v1, double* d_out);
+/* Adams-Moulton corrector velocity: out = (vp + vs) * 0.5   (main.f90:1094-1096) */
+int vlc_am2_dev(vlc_ctx* ctx, int64_t n, const double* d_vp, const double* d_vs, double* d_out);
+/* rVc <- sqrt(rVc^2 + 4*1.2564*apparentViscCoeff*nu*dt); gam <- gam*exp(-decayCoeff*dt)
+ * (rotor_dissipate_wake classdef.f90:4356-4408, vr_decay :662-668).  Either pointer may be NULL. */
+int vlc_dissipate_dev(vlc_ctx* ctx, int64_t n_rvc, double* d_rvc, int64_t n_gam, double* d_gam,
+                      double apparentViscCoeff, double kinematicVisc, double decayCoeff, double dt);
+/* far-wake strain: lc = |p1-p2|, rVc = rVc0*sqrt(l0/lc)  (classdef.f90:4410-4422, :505-521) */
+int vlc_strain_dev(vlc_ctx* ctx, int64_t n, const double* d_p1, const double* d_p2, const double* d_l0,
+                   const double* d_rvc0, double* d_rvc);
+/*
+ * Build the packed source set `set` from a near-wake lattice + far-wake chain on the device, in the
+ * reference's enumeration order (blade_vind_bywake, classdef.f90:1450-1469): rings (j, i) x 4 filaments,
+ * then (if nfar > 0) the horseshoe correction -vf2 of the last row, then the far filaments.
+ *   nodes (3, nrows+1, ns+1); gam (nrows, ns); rvc4 (4, nrows, ns) = vf(1..4)%rVc of every ring (kept per
+ *   ring, not per edge, because the reference lets the two copies of a shared edge differ);
+ *   far: p(3, nfar+1) chain with filament i = fc(:,2)=p(:,i) -> fc(:,1)=p(:,i+1), gamF(nfar), rvcF(nfar).
+ *   append != 0 adds to the set instead of replacing it (several blades / rotors).
+ */
+int vlc_pack_lattice_dev(vlc_ctx* ctx, int set, int append, int nrows, int ns, const double* d_nodes,
+                         const double* d_gam, const double* d_rvc4, int nfar, const double* d_far_nodes,
+                         const double* d_gamF, const double* d_rvcF);
+/* rotor_dissipate_wake on a lattice (classdef.f90:4364-4393): vf1 grows, vf3 <- vf1, gam decays, vf2 grows,
+ * vf4(i) <- vf2(i-1) for i > first row. */
+int vlc_dissipate_lattice_dev(vlc_ctx* ctx, int nrows, int ns, double* d_rvc4, double* d_gam,
+                              double apparentViscCoeff, double kinematicVisc, double decayCoeff, double dt);
+
+/* Convected nodes of a lattice <-> contiguous target list, in the order of vind_onNwake_byRotor
+ * (libCommon.f90:133-145: column-major over (row, col) incl. the extra last column):
+ *   gather : P(3, nrows, ns+1) = nodes(:, 2:nrows+1, :)        scatter : the inverse copy. */
+int vlc_lattice_targets_dev(vlc_ctx* ctx, int nrows, int ns, const double* d_nodes, double* d_P);
+int vlc_lattice_scatter_dev(vlc_ctx* ctx, int nrows, int ns, double* d_nodes, const double* d_P);
+
+/* ---- measurement helper ------------------------------------------------------------------ */
+/* Register-resident DFMA chains on every SM: returns sustained FP64 FMA rate in flop/s (DFMA = 2)
+ * and the elapsed milliseconds; used by bench.py as the measured FP64 roofline denominator
+ * (MEASURED_PEAKS.json has no FP64 entry). */
+int vlc_measure_fp64_peak(vlc_ctx* ctx, int iters, double* flops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLCANOR_B200_H */

@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerance (north-star): per-call induced velocities within 1e-12 relative.  Because a target sums up to
+millions of signed terms with heavy cancellation, "relative" is measured against the velocity scale of the
+batch, sum|terms|: err = max|V_gpu - V_oracle| / max sum_k |gam_k vf_vind_k|.
+"""
+import numpy as np
+import pytest
+
+from tests import refgeom
+from tests.helpers import lattice_to_rotor, scaled_err
+from volcanor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _check_flat(ctx, oracle, p1, p2, rvc, gam, flag, P, tol=TOL):
+    ctx.set_sources(0, p1, p2, rvc, gam, flag)
+    V = ctx.vind(0, P)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, P)
+    Vl, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, P)
+    e = scaled_err(V, Vo, Vabs)
+    assert np.all(np.isfinite(V))
+    assert e < tol, e
+    return V, Vo, Vl, Vabs
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (7, 3), (127, 129), (128, 512), (129, 513), (1000, 77), (5000, 2049)])
+def test_flat_random_vs_oracle(ctx, oracle, n, m):
+    ctx.set_tuning(0, 0)
+    _check_flat(ctx, oracle, *synth.random_filaments(n, m, seed=n + m))
+
+
+def test_empty_inputs(ctx):
+    z3, z1 = np.zeros((0, 3)), np.zeros(0)
+    ctx.set_sources(1, z3, z3, z1, z1, None)
+    assert ctx.num_sources(1) == 0
+    V = ctx.vind(1, np.ones((5, 3)))
+    assert V.shape == (5, 3) and np.all(V == 0.0)       # no sources -> zero velocity
+    p1, p2, rvc, gam, flag, _ = synth.random_filaments(10, 4, seed=1)
+    ctx.set_sources(1, p1, p2, rvc, gam, flag)
+    assert ctx.vind(1, np.zeros((0, 3))).shape == (0, 3)  # no targets
+
+
+def test_targets_on_filament_nodes_are_skipped_exactly(ctx, oracle):
+    """classdef.f90:498: a wake node lying on the end points / axis of a filament gets exactly 0 from it."""
+    p1 = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]])
+    p2 = np.array([[1.0, 0.0, 0.0], [1.0, 2.0, 0.0]])
+    rvc = np.array([0.0, 0.01])
+    gam = np.array([1.0, 1.0])
+    P = np.array([[0.0, 0, 0], [1.0, 0, 0], [0.5, 0, 0], [1.0, 2.0, 0], [1.0, 1.0, 0.0], [7.0, 0.0, 0.0]])
+    ctx.set_sources(0, p1, p2, rvc, gam, None)
+    V = ctx.vind(0, P)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, None, P)
+    assert np.all(np.isfinite(V))
+    assert np.max(np.abs(V - Vo)) < 1e-15
+    assert np.all(V[1] == 0.0)   # the shared node sees neither filament
+
+
+def test_gamma_skip_rule(ctx, oracle):
+    """|gam| <= eps wake filaments contribute exactly 0; wing filaments are never skipped (classdef.f90:1452 vs :1350)."""
+    p1, p2, rvc, gam, flag, P = synth.random_filaments(64, 32, seed=5)
+    gam[:] = 1e-17
+    flag[:] = 1
+    ctx.set_sources(0, p1, p2, rvc, gam, flag)
+    assert np.all(ctx.vind(0, P) == 0.0)
+    flag[:] = 0
+    ctx.set_sources(0, p1, p2, rvc, gam, flag)
+    V = ctx.vind(0, P)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, P)
+    assert np.any(V != 0.0) and np.max(np.abs(V - Vo)) < 1e-12 * np.max(np.abs(Vo))
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+@pytest.mark.parametrize("nsplit", [1, 3, 16])
+def test_launch_shapes_agree(ctx, oracle, T, nsplit):
+    """targets-per-thread and source splits only change speed and summation order."""
+    p1, p2, rvc, gam, flag, P = synth.random_filaments(3000, 1500, seed=11)
+    ctx.set_tuning(T, nsplit)
+    try:
+        _check_flat(ctx, oracle, p1, p2, rvc, gam, flag, P)
+    finally:
+        ctx.set_tuning(0, 0)
+
+
+def test_linearity_in_gamma(ctx):
+    p1, p2, rvc, gam, flag, P = synth.random_filaments(2000, 300, seed=2)
+    flag[:] = 0
+    ctx.set_sources(0, p1, p2, rvc, gam, flag)
+    V1 = ctx.vind(0, P)
+    ctx.set_sources(0, p1, p2, rvc, 2.0 * gam, flag)
+    V2 = ctx.vind(0, P)
+    assert np.array_equal(V2, 2.0 * V1)   # scaling by 2 is exact in binary floating point
+
+
+def test_synthetic_multirotor_vs_oracle(ctx, oracle):
+    """BASELINE.json configs[4] shape at 2e4 filaments: every wake node against every filament."""
+    lats = synth.multirotor(20000, seed=12345)
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    P = synth.targets_all(lats)
+    V, Vo, Vl, Vabs = _check_flat(ctx, oracle, p1, p2, rvc, gam, flag, P)
+    # both are equally far from the long-double evaluation (the GPU path is not less accurate)
+    assert scaled_err(V, Vl, Vabs) < 5 * max(scaled_err(Vo, Vl, Vabs), 1e-15)
+
+
+def test_device_pointer_path_and_range(ctx, oracle):
+    import torch
+    p1, p2, rvc, gam, flag, P = synth.random_filaments(1000, 700, seed=9)
+    ctx.set_sources(2, p1, p2, rvc, gam, flag)
+    dP = torch.from_numpy(P).cuda()
+    dV = torch.empty_like(dP)
+    ctx.vind_dev(2, P.shape[0], dP, dV)
+    ctx.sync()
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, P)
+    _, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, P)
+    assert scaled_err(dV.cpu().numpy(), Vo, Vabs) < TOL
+    # source ranges: [0,512) + [512, 1000) == all
+    a, b = torch.empty_like(dP), torch.empty_like(dP)
+    ctx.vind_range_dev(2, 0, 512, P.shape[0], dP, a)
+    ctx.vind_range_dev(2, 512, 488, P.shape[0], dP, b)
+    ctx.sync()
+    assert scaled_err((a + b).cpu().numpy(), Vo, Vabs) < TOL
+
+
+# ------------------------------------------------------------------ tier 2: rotor-level call sites
+
+def _make_rotor_pair(ctx, oracle, seed=0, nb=2, nc=3, ns=5, nNwake=7, nFwake=4, rowNear=2, rowFar=2):
+    rng = np.random.default_rng(seed)
+    ro = oracle.Rotor(nb, nc, ns, nNwake, nFwake)
+    ro.set_params()
+    ro.set_rows(rowNear, rowFar)
+    ctx.rotor_define(0, nb, nc, ns, nNwake, nFwake, 1)
+    ctx.rotor_set_rows(0, rowNear, rowFar)
+    for ib in range(nb):
+        wing = refgeom.flat_wing_records(nc, ns, 1.0, 4.0, 0.1, [-10.0, 0, 0], 0.01, 0.04)
+        dz = 0.3 * ib  # stack the blades' wings so that collocation points differ
+        for f in range(4):
+            wing[:, :, 12 * f + 2] += dz
+            wing[:, :, 12 * f + 5] += dz
+        wing[:, :, 54:64:3] += dz   # PC z
+        wing[:, :, 66] += dz        # CP z
+        wing[:, :, 48] = rng.uniform(-1, 1, size=(ns, nc))
+        ro.wiP(ib)[...] = wing
+        ctx.rotor_put_wing(0, ib, ro.wiP(ib))
+        lat = synth._helix_lattice(rng, np.array([0.0, 0.0, -0.2 - ib]), 1.0, 0.1, ns, nNwake, nFwake,
+                                   psi0=ib * np.pi, sense=1.0)
+        lat.gam[0, 3] = 0.0          # a skipped ring
+        lat.gam[1, 4] = 1e-17
+        for pred in (False, True):
+            if pred:
+                lat.nodes[:, 1:] += 1e-3 * rng.normal(size=lat.nodes[:, 1:].shape)
+            lattice_to_rotor(lat, ro, ib, pred)
+            ctx.rotor_put_nwake(0, ib, ro.waN(ib, pred), pred)
+            ctx.rotor_put_fwake(0, ib, ro.waF(ib, pred), pred)
+    return ro
+
+
+def _tol_scale(ro, P):
+    return max(np.max(np.abs(ro.vind_points(2, P))), 1e-300)
+
+
+@pytest.mark.parametrize("rows", [(2, 2), (1, 1), (7, 5), (5, 4)])
+def test_rotor_source_loops_vs_oracle(ctx, oracle, rows):
+    """vind_bywing / vind_bywake[,'P'] / vind_bywing_boundVortices (classdef.f90:4424-4479)."""
+    ro = _make_rotor_pair(ctx, oracle, seed=4, rowNear=rows[0], rowFar=rows[1])
+    P = np.random.default_rng(7).uniform(-1.5, 1.5, size=(200, 3))
+    s = _tol_scale(ro, P) * 50
+    assert np.max(np.abs(ctx.rotor_vind_bywing(0, P) - ro.vind_points(0, P))) < TOL * s
+    assert np.max(np.abs(ctx.rotor_vind_bywake(0, P) - ro.vind_points(1, P))) < TOL * s
+    assert np.max(np.abs(ctx.rotor_vind_bywake(0, P, True) - ro.vind_points(1, P, True))) < TOL * s
+    assert np.max(np.abs(ctx.rotor_vind_bywing_boundVortices(0, P) - ro.vind_points(3, P))) < TOL * s
+
+
+def test_vind_onNwake_onFwake_byRotor_vs_oracle(ctx, oracle):
+    """libCommon.f90:114-211 on the active slices waN(rowNear:nNwake,:) / waF(rowFar:nFwake), C and P."""
+    ro = _make_rotor_pair(ctx, oracle, seed=8, rowNear=3, rowFar=2)
+    P = np.random.default_rng(7).uniform(-1.5, 1.5, size=(50, 3))
+    s = _tol_scale(ro, P) * 50
+    for pred in (False, True):
+        for ib in range(ro.nb):
+            ref = ro.vind_onNwake_byRotor(ro, ib, 3, pred)
+            got = ctx.vind_onNwake_byRotor(0, ro.waN(ib, pred), ro.nNwake - 2, ro.ns, ro.nNwake, pred,
+                                           offset_records=2)
+            assert got.shape == ref.shape and np.max(np.abs(got - ref)) < TOL * s
+            reff = ro.vind_onFwake_byRotor(ro, ib, 2, pred)
+            gotf = ctx.vind_onFwake_byRotor(0, ro.waF(ib, pred), ro.nFwake - 1, pred, offset_records=1)
+            assert np.max(np.abs(gotf - reff)) < TOL * s
+
+
+def test_no_far_wake_means_no_horseshoe_correction(ctx, oracle):
+    """classdef.f90:1458: correction and far filaments only when rowFar <= nFwake."""
+    ro = _make_rotor_pair(ctx, oracle, seed=3, nFwake=4, rowNear=1, rowFar=5)
+    P = np.random.default_rng(1).uniform(-1.5, 1.5, size=(64, 3))
+    s = _tol_scale(ro, P) * 50
+    assert np.max(np.abs(ctx.rotor_vind_bywake(0, P) - ro.vind_points(1, P))) < TOL * s
+
+
+@pytest.mark.parametrize("name", ["wing1x3", "wing1x2"])
+def test_aic_kat_on_gpu(ctx, oracle, name):
+    """rotor%calcAIC (classdef.f90:4151-4179) against the reference's golden AIC and the oracle."""
+    rec = getattr(refgeom, name)()
+    ns, nc, _ = rec.shape
+    golden = refgeom.AIC_WING1X3 if name == "wing1x3" else refgeom.AIC_WING1X2
+    ctx.rotor_define(1, 1, nc, ns, 2, 0, 1)
+    ctx.rotor_put_wing(1, 0, rec)
+    A = ctx.rotor_calcAIC(1, nc * ns)
+    assert np.max(np.abs(A - golden)) < 1e-6     # the reference test's own tolerance
+    ro = oracle.Rotor(1, nc, ns, 2, 0)
+    ro.wiP(0)[...] = rec
+    ro.calcAIC()
+    assert np.max(np.abs(A - ro.AIC())) < 1e-13 * np.max(np.abs(A))
+    rhs = np.arange(1.0, nc * ns + 1.0)
+    g = ctx.rotor_solve(1, rhs)
+    assert np.max(np.abs(g - ro.AIC(inverse=True) @ rhs)) < 1e-12 * np.max(np.abs(g))
+    assert np.max(np.abs(ctx.rotor_get_AIC_inv(1, nc * ns) - ro.AIC(inverse=True))) < 1e-12 * np.max(np.abs(ro.AIC(True)))
+
+
+def test_aic_larger_rotor_and_solve(ctx, oracle):
+    ro = _make_rotor_pair(ctx, oracle, seed=21, nb=2, nc=4, ns=13)
+    assert ro.calcAIC() == 0
+    A = ctx.rotor_calcAIC(0, ro.N)
+    assert np.max(np.abs(A - ro.AIC())) < 1e-12 * np.max(np.abs(A))
+    rhs = np.random.default_rng(2).normal(size=ro.N)
+    g = ctx.rotor_solve(0, rhs)
+    gref = ro.AIC(inverse=True) @ rhs
+    assert np.max(np.abs(g - gref)) < 1e-10 * np.max(np.abs(gref))
+
+
+def test_solve_before_calcAIC_is_an_error(ctx):
+    import volcanor_b200 as vb
+    ctx.rotor_define(2, 1, 1, 2, 2, 0, 1)
+    with pytest.raises(vb.VlcError):
+        ctx.rotor_solve(2, np.ones(2))
+
+
+def test_singular_aic_reports_like_reference(ctx):
+    """libMath.f90:73 'Matrix is numerically singular!' (all-zero geometry)."""
+    import volcanor_b200 as vb
+    ctx.rotor_define(2, 1, 1, 2, 2, 0, 1)
+    ctx.rotor_put_wing(2, 0, np.zeros((2, 1, 104)))
+    with pytest.raises(vb.VlcError, match="singular"):
+        ctx.rotor_calcAIC(2, 2)

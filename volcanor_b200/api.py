@@ -1,0 +1,341 @@
+"""ctypes binding of include/volcanor_b200.h plus a small object wrapper.
+
+Names and argument meaning follow the reference's procedures (src/libCommon.f90:114-211,
+src/classdef.f90:4151-4479) so that the parity tests read like the reference's own tests.
+Every failure of the library raises :class:`VlcError` (the reference `error stop`s).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_ROOT = _HERE.parent
+_LIB = None
+
+VR_DOUBLES = 50
+FWAKE_DOUBLES = 13
+WINGPANEL_DOUBLES = 104
+NPFWAKE = 240
+
+
+class VlcError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _HERE / "libvolcanor_b200.so"
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc -> volcanor_b200/libvolcanor_b200.so (sm_100a only, in-tree so it travels with gpurun)."""
+    out = lib_path()
+    srcs = [_HERE / "csrc" / "capi.cu"]
+    deps = list((_HERE / "csrc").glob("*.cu*")) + [_ROOT / "include" / "volcanor_b200.h"]
+    if out.exists() and not force and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++",
+           "-shared", "-o", str(out)] + [str(s) for s in srcs] + ["-lcusolver"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise VlcError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr, file=sys.stderr)
+    return out
+
+
+def _declared_symbols() -> list[str]:
+    hdr = (_ROOT / "include" / "volcanor_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(vlc_[a-zA-Z0-9_]+)\s*\(", hdr)))
+
+
+DECLARED_SYMBOLS = _declared_symbols()
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library.  Fails loudly if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not p.exists():
+        raise VlcError(f"{p} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(volcanor_b200 has no CPU fallback)")
+    lib = C.CDLL(str(p))
+    i64, i32 = C.c_int64, C.c_int
+    sig = {
+        "vlc_create": (i32, [i32, C.POINTER(_vp)]),
+        "vlc_destroy": (i32, [_vp]),
+        "vlc_last_error": (C.c_char_p, [_vp]),
+        "vlc_version": (C.c_char_p, []),
+        "vlc_set_stream": (i32, [_vp, _vp]),
+        "vlc_sync": (i32, [_vp]),
+        "vlc_device_info": (i32, [_vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
+        "vlc_set_tuning": (i32, [_vp, i32, i32]),
+        "vlc_launch_count": (i64, [_vp]),
+        "vlc_set_sources": (i32, [_vp, i32, i64, _vp, _vp, _vp, _vp, _vp]),
+        "vlc_set_sources_dev": (i32, [_vp, i32, i64, _vp, _vp, _vp, _vp, _vp]),
+        "vlc_num_sources": (i64, [_vp, i32]),
+        "vlc_vind": (i32, [_vp, i32, i64, _vp, _vp]),
+        "vlc_vind_dev": (i32, [_vp, i32, i64, _vp, _vp]),
+        "vlc_vind_range_dev": (i32, [_vp, i32, i64, i64, i64, _vp, _vp]),
+        "vlc_source_tile": (i32, []),
+        "vlc_rotor_define": (i32, [_vp, i32, i32, i32, i32, i32, i32, i32]),
+        "vlc_rotor_set_rows": (i32, [_vp, i32, i32, i32]),
+        "vlc_rotor_put_wing": (i32, [_vp, i32, i32, _vp]),
+        "vlc_rotor_put_nwake": (i32, [_vp, i32, i32, i32, _vp]),
+        "vlc_rotor_put_fwake": (i32, [_vp, i32, i32, i32, _vp]),
+        "vlc_rotor_put_pfwake": (i32, [_vp, i32, i32, i32, _vp]),
+        "vlc_rotor_put_wing_gam": (i32, [_vp, i32, i32, _vp]),
+        "vlc_rotor_vind_bywing": (i32, [_vp, i32, i64, _vp, _vp]),
+        "vlc_rotor_vind_bywake": (i32, [_vp, i32, i32, i64, _vp, _vp]),
+        "vlc_rotor_vind_bywing_boundVortices": (i32, [_vp, i32, i64, _vp, _vp]),
+        "vlc_rotor_vind": (i32, [_vp, i32, i32, i64, _vp, _vp]),
+        "vlc_vind_onNwake_byRotor": (i32, [_vp, i32, _vp, i32, i32, i32, i32, _vp]),
+        "vlc_vind_onFwake_byRotor": (i32, [_vp, i32, _vp, i32, i32, _vp]),
+        "vlc_rotor_calcAIC": (i32, [_vp, i32, _vp]),
+        "vlc_rotor_solve": (i32, [_vp, i32, _vp, _vp]),
+        "vlc_rotor_get_AIC_inv": (i32, [_vp, i32, _vp]),
+        "vlc_convect_dev": (i32, [_vp, i64, _vp, _vp, C.c_double]),
+        "vlc_ab2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
+        "vlc_am2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
+        "vlc_dissipate_dev": (i32, [_vp, i64, _vp, i64, _vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+        "vlc_dissipate_lattice_dev": (i32, [_vp, i32, i32, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+        "vlc_strain_dev": (i32, [_vp, i64, _vp, _vp, _vp, _vp, _vp]),
+        "vlc_pack_lattice_dev": (i32, [_vp, i32, i32, i32, i32, _vp, _vp, _vp, i32, _vp, _vp, _vp]),
+        "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
+        "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
+        "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._vlc_signatures = sig
+    _LIB = lib
+    return lib
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.size == int(np.prod(shape)), (a.shape, shape)
+    return a
+
+
+def _ptr(a) -> int | None:
+    """Raw address of a numpy array, torch tensor (host or device) or int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Context:
+    """One library context = one GPU.  Mirrors the reference call sites (see the header)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.vlc_create(device, C.byref(h))
+        if rc != 0:
+            raise VlcError(f"vlc_create failed ({rc}): {self.lib.vlc_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise VlcError(f"[{rc}] {self.lib.vlc_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vlc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr: int | None):
+        self._ck(self.lib.vlc_set_stream(self.h, stream_ptr))
+
+    def sync(self):
+        self._ck(self.lib.vlc_sync(self.h))
+
+    def set_tuning(self, targets_per_thread: int = 0, nsplit: int = 0):
+        self._ck(self.lib.vlc_set_tuning(self.h, targets_per_thread, nsplit))
+
+    def device_info(self) -> dict:
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self._ck(self.lib.vlc_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "mem_bytes": mem.value}
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.vlc_launch_count(self.h))
+
+    def measure_fp64_peak(self, iters: int = 20000) -> tuple[float, float]:
+        f, ms = C.c_double(), C.c_double()
+        self._ck(self.lib.vlc_measure_fp64_peak(self.h, iters, C.byref(f), C.byref(ms)))
+        return f.value, ms.value
+
+    # -- tier 1 -----------------------------------------------------------------------------
+    def set_sources(self, set_: int, p1, p2, rvc, gam, wake_flag=None):
+        """Host arrays: p1, p2 (n,3) [= Fortran (3,n)], rvc (n), gam (n), wake_flag (n) uint8 or None."""
+        p1, p2, rvc, gam = _f64(p1), _f64(p2), _f64(rvc), _f64(gam)
+        n = rvc.size
+        assert p1.size == 3 * n and p2.size == 3 * n and gam.size == n
+        fl = None if wake_flag is None else np.ascontiguousarray(wake_flag, dtype=np.uint8)
+        self._ck(self.lib.vlc_set_sources(self.h, set_, n, _ptr(p1), _ptr(p2), _ptr(rvc), _ptr(gam), _ptr(fl)))
+
+    def set_sources_dev(self, set_: int, n: int, p1, p2, rvc, gam, wake_flag=None):
+        self._ck(self.lib.vlc_set_sources_dev(self.h, set_, n, _ptr(p1), _ptr(p2), _ptr(rvc), _ptr(gam),
+                                              _ptr(wake_flag)))
+
+    def num_sources(self, set_: int) -> int:
+        return int(self.lib.vlc_num_sources(self.h, set_))
+
+    def vind(self, set_: int, P) -> np.ndarray:
+        """V (m,3) at host points P (m,3)."""
+        P = _f64(P)
+        m = P.size // 3
+        V = np.empty((m, 3), dtype=np.float64)
+        self._ck(self.lib.vlc_vind(self.h, set_, m, _ptr(P), _ptr(V)))
+        return V
+
+    def vind_into(self, set_: int, m: int, P, V):
+        """Host buffers (numpy or pinned torch tensors) without allocation."""
+        self._ck(self.lib.vlc_vind(self.h, set_, m, _ptr(P), _ptr(V)))
+
+    def vind_dev(self, set_: int, m: int, dP, dV):
+        self._ck(self.lib.vlc_vind_dev(self.h, set_, m, _ptr(dP), _ptr(dV)))
+
+    def vind_range_dev(self, set_: int, first: int, count: int, m: int, dP, dV):
+        self._ck(self.lib.vlc_vind_range_dev(self.h, set_, first, count, m, _ptr(dP), _ptr(dV)))
+
+    # -- tier 2 -----------------------------------------------------------------------------
+    def rotor_define(self, ir, nb, nc, ns, nNwake, nFwake, surfaceType=1):
+        self._ck(self.lib.vlc_rotor_define(self.h, ir, nb, nc, ns, nNwake, nFwake, surfaceType))
+
+    def rotor_set_rows(self, ir, rowNear, rowFar):
+        self._ck(self.lib.vlc_rotor_set_rows(self.h, ir, rowNear, rowFar))
+
+    def rotor_put_wing(self, ir, ib, wiP):
+        self._ck(self.lib.vlc_rotor_put_wing(self.h, ir, ib, _ptr(_f64(wiP))))
+
+    def rotor_put_wing_gam(self, ir, ib, gam):
+        self._ck(self.lib.vlc_rotor_put_wing_gam(self.h, ir, ib, _ptr(_f64(gam))))
+
+    def rotor_put_nwake(self, ir, ib, waN, predicted=False):
+        self._ck(self.lib.vlc_rotor_put_nwake(self.h, ir, ib, int(predicted), _ptr(_f64(waN))))
+
+    def rotor_put_fwake(self, ir, ib, waF, predicted=False):
+        self._ck(self.lib.vlc_rotor_put_fwake(self.h, ir, ib, int(predicted), _ptr(_f64(waF))))
+
+    def rotor_put_pfwake(self, ir, ib, wapF, predicted=False):
+        self._ck(self.lib.vlc_rotor_put_pfwake(self.h, ir, ib, int(predicted), _ptr(_f64(wapF))))
+
+    def _points(self, fn, P, *pre):
+        P = _f64(P)
+        m = P.size // 3
+        V = np.empty((m, 3), dtype=np.float64)
+        self._ck(fn(self.h, *pre, m, _ptr(P), _ptr(V)))
+        return V
+
+    def rotor_vind_bywing(self, ir, P):
+        return self._points(self.lib.vlc_rotor_vind_bywing, P, ir)
+
+    def rotor_vind_bywake(self, ir, P, predicted=False):
+        return self._points(self.lib.vlc_rotor_vind_bywake, P, ir, int(predicted))
+
+    def rotor_vind_bywing_boundVortices(self, ir, P):
+        return self._points(self.lib.vlc_rotor_vind_bywing_boundVortices, P, ir)
+
+    def rotor_vind(self, ir, P, predicted=False):
+        return self._points(self.lib.vlc_rotor_vind, P, ir, int(predicted))
+
+    def vind_onNwake_byRotor(self, ir, Nwake, rows, cols, ld, predicted=False, offset_records=0):
+        """Nwake: the parent record array (ld*cols*50 doubles); slice starts `offset_records` records in.
+        Returns (cols+1, rows, 3) = Fortran (3, rows, cols+1)."""
+        Nwake = _f64(Nwake)
+        out = np.empty((cols + 1, rows, 3), dtype=np.float64)
+        self._ck(self.lib.vlc_vind_onNwake_byRotor(self.h, ir, Nwake.ctypes.data + 8 * VR_DOUBLES * offset_records,
+                                                   rows, cols, ld, int(predicted), _ptr(out)))
+        return out
+
+    def vind_onFwake_byRotor(self, ir, Fwake, rows, predicted=False, offset_records=0):
+        Fwake = _f64(Fwake)
+        out = np.empty((rows, 3), dtype=np.float64)
+        self._ck(self.lib.vlc_vind_onFwake_byRotor(self.h, ir, Fwake.ctypes.data + 8 * FWAKE_DOUBLES * offset_records,
+                                                   rows, int(predicted), _ptr(out)))
+        return out
+
+    def rotor_calcAIC(self, ir, N, want_matrix=True):
+        A = np.empty((N, N), dtype=np.float64, order="F") if want_matrix else None
+        self._ck(self.lib.vlc_rotor_calcAIC(self.h, ir, _ptr(A)))
+        return A
+
+    def rotor_solve(self, ir, RHS):
+        RHS = _f64(RHS)
+        g = np.empty_like(RHS)
+        self._ck(self.lib.vlc_rotor_solve(self.h, ir, _ptr(RHS), _ptr(g)))
+        return g
+
+    def rotor_get_AIC_inv(self, ir, N):
+        A = np.empty((N, N), dtype=np.float64, order="F")
+        self._ck(self.lib.vlc_rotor_get_AIC_inv(self.h, ir, _ptr(A)))
+        return A
+
+    # -- tier 3 (device pointers: torch tensors or ints) --------------------------------------
+    def convect_dev(self, n, x, v, dt):
+        self._ck(self.lib.vlc_convect_dev(self.h, n, _ptr(x), _ptr(v), dt))
+
+    def ab2_dev(self, n, v, v1, out):
+        self._ck(self.lib.vlc_ab2_dev(self.h, n, _ptr(v), _ptr(v1), _ptr(out)))
+
+    def am2_dev(self, n, vp, vs, out):
+        self._ck(self.lib.vlc_am2_dev(self.h, n, _ptr(vp), _ptr(vs), _ptr(out)))
+
+    def dissipate_dev(self, n_rvc, rvc, n_gam, gam, apparentViscCoeff, kinematicVisc, decayCoeff, dt):
+        self._ck(self.lib.vlc_dissipate_dev(self.h, n_rvc, _ptr(rvc), n_gam, _ptr(gam), apparentViscCoeff,
+                                            kinematicVisc, decayCoeff, dt))
+
+    def dissipate_lattice_dev(self, nrows, ns, rvc4, gam, apparentViscCoeff, kinematicVisc, decayCoeff, dt):
+        self._ck(self.lib.vlc_dissipate_lattice_dev(self.h, nrows, ns, _ptr(rvc4), _ptr(gam), apparentViscCoeff,
+                                                    kinematicVisc, decayCoeff, dt))
+
+    def strain_dev(self, n, p1, p2, l0, rvc0, rvc):
+        self._ck(self.lib.vlc_strain_dev(self.h, n, _ptr(p1), _ptr(p2), _ptr(l0), _ptr(rvc0), _ptr(rvc)))
+
+    def pack_lattice_dev(self, set_, append, nrows, ns, nodes, gam, rvc4, nfar=0, far_nodes=None, gamF=None,
+                         rvcF=None):
+        self._ck(self.lib.vlc_pack_lattice_dev(self.h, set_, int(append), nrows, ns, _ptr(nodes), _ptr(gam),
+                                               _ptr(rvc4), nfar, _ptr(far_nodes), _ptr(gamF), _ptr(rvcF)))
+
+    def lattice_targets_dev(self, nrows, ns, nodes, P):
+        self._ck(self.lib.vlc_lattice_targets_dev(self.h, nrows, ns, _ptr(nodes), _ptr(P)))
+
+    def lattice_scatter_dev(self, nrows, ns, nodes, P):
+        self._ck(self.lib.vlc_lattice_scatter_dev(self.h, nrows, ns, _ptr(nodes), _ptr(P)))

@@ -1,0 +1,107 @@
+// bs_sweep.cuh -- the targets x sources Biot-Savart sweep kernel (K1/K2/K3/K5/K9 of SURVEY 2.1).
+//
+// Replaces the OpenMP target loops of src/libCommon.f90:132-146, :190-195 and the RHS / force loops
+// of src/main.f90:528-573, :632-656: every target sums gam * vf_vind over a packed source set.
+//
+// Decomposition: blockIdx.x = tile of THREADS*T targets (T targets per thread, held in registers),
+// blockIdx.y = contiguous chunk of the source list (source split, used when targets are few).
+// Each CTA streams its chunk through shared memory in TILE-filament tiles with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier, STAGES-deep ring); all lanes read the same filament -> LDS.128 broadcast.
+// Partial sums of the source splits go to part[split][3m]; a fixed-order reduce kernel adds them, so
+// results are deterministic for a given (m, n, nsplit).
+#pragma once
+#include "vlc_device.cuh"
+
+namespace vlc {
+
+template <int T, int THREADS, int TILE, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a multiple of TILE
+                long long chunk,                  // sources per split (multiple of TILE)
+                long long n_src_padded,           // total padded sources (multiple of TILE)
+                const double* __restrict__ P,     // targets (3, m) interleaved
+                long long m,
+                double* __restrict__ out)         // [gridDim.y][3 m]
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* buf = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * kSrcBytes);
+
+  const int tid = threadIdx.x;
+  const long long s_begin = (long long)blockIdx.y * chunk;
+  long long s_end = s_begin + chunk;
+  if (s_end > n_src_padded) s_end = n_src_padded;
+  const int ntiles = (s_end > s_begin) ? (int)((s_end - s_begin) / TILE) : 0;
+  const double* gsrc = src + s_begin * kSrcDoubles;
+  constexpr uint32_t kTileBytes = TILE * kSrcBytes;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s)
+      if (s < ntiles) {
+        mbar_expect_tx(&bars[s], kTileBytes);
+        tma_bulk_g2s(buf + (size_t)s * TILE * kSrcDoubles, gsrc + (size_t)s * TILE * kSrcDoubles, kTileBytes,
+                     &bars[s]);
+      }
+  }
+
+  // T targets per thread, strided by THREADS so global loads/stores of a warp stay close together.
+  const long long t0 = (long long)blockIdx.x * (THREADS * T) + tid;
+  double px[T], py[T], pz[T], vx[T], vy[T], vz[T];
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const long long t = t0 + (long long)k * THREADS;
+    const bool ok = t < m;
+    px[k] = ok ? P[3 * t + 0] : 0.0;
+    py[k] = ok ? P[3 * t + 1] : 0.0;
+    pz[k] = ok ? P[3 * t + 2] : 0.0;
+    vx[k] = vy[k] = vz[k] = 0.0;
+  }
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int stage = tile % STAGES;
+    const uint32_t phase = (uint32_t)(tile / STAGES) & 1u;
+    mbar_wait(&bars[stage], phase);
+    const double* sb = buf + (size_t)stage * TILE * kSrcDoubles;
+#pragma unroll 2
+    for (int j = 0; j < TILE; ++j) {
+      const Src s = load_src(sb + j * kSrcDoubles);
+#pragma unroll
+      for (int k = 0; k < T; ++k) pair_accumulate(s, px[k], py[k], pz[k], vx[k], vy[k], vz[k]);
+    }
+    __syncthreads();  // every warp is done with this stage before it is refilled
+    if (tid == 0 && tile + STAGES < ntiles) {
+      mbar_expect_tx(&bars[stage], kTileBytes);
+      tma_bulk_g2s(buf + (size_t)stage * TILE * kSrcDoubles, gsrc + (size_t)(tile + STAGES) * TILE * kSrcDoubles,
+                   kTileBytes, &bars[stage]);
+    }
+  }
+
+  double* o = out + (size_t)blockIdx.y * 3 * (size_t)m;
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const long long t = t0 + (long long)k * THREADS;
+    if (t < m) {
+      o[3 * t + 0] = vx[k];
+      o[3 * t + 1] = vy[k];
+      o[3 * t + 2] = vz[k];
+    }
+  }
+}
+
+// Fixed-order sum of the source-split partials: V[i] = ((part[0][i] + part[1][i]) + ...).
+__global__ void bs_reduce_kernel(const double* __restrict__ part, int nsplit, long long len, double* __restrict__ V) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double a = part[i];
+  for (int s = 1; s < nsplit; ++s) a += part[(size_t)s * len + i];
+  V[i] = a;
+}
+
+}  // namespace vlc

@@ -1,0 +1,1061 @@
+// capi.cu -- implementation of the C ABI in include/volcanor_b200.h.
+//
+// Owns: device buffers (packed source sets, reference-layout rotor copies, LU factors), the CUDA
+// stream, the cuSOLVER handle.  The caller owns every host array.  No CPU compute path exists
+// here: every entry point either launches sm_100a kernels or fails with an error.
+#include "../../include/volcanor_b200.h"
+
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bs_sweep.cuh"
+#include "pack.cuh"
+#include "wake_state.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;  // threads per sweep CTA
+constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
+constexpr int kStages = 3;     // TMA ring depth
+
+std::string g_create_error;
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t cap = 0;  // doubles
+};
+
+struct SourceSet {
+  DevBuf rec;
+  long long n = 0;      // logical filaments
+  long long n_pad = 0;  // padded to kTile
+};
+
+struct Rotor {
+  bool defined = false;
+  int nb = 0, nc = 0, ns = 0, nNwake = 0, nFwake = 0, surfaceType = 1;
+  int rowNear = 1, rowFar = 1;
+  // reference-layout copies (all blades, blade-major)
+  DevBuf wiP, waN[2], waF[2], wapF[2];
+  bool have_pf[2] = {false, false};
+  // packed: [wing | wake] per set (C, P), and bound-vortex set
+  SourceSet comb[2];
+  long long wing_pad[2] = {0, 0};  // padded wing segment length inside comb[s]
+  long long wing_n = 0;
+  SourceSet bound;
+  bool dirty[2] = {true, true};
+  bool bound_dirty = true;
+  // AIC
+  int N = 0;
+  DevBuf LU;
+  int* d_ipiv = nullptr;
+  int* d_info = nullptr;
+  bool factored = false;
+};
+
+}  // namespace
+
+struct vlc_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  long long mem_bytes = 0;
+  int tune_T = 0, tune_nsplit = 0;
+  long long launches = 0;
+  SourceSet sets[VLC_MAX_SETS];
+  DevBuf part;     // source-split partials
+  DevBuf stage_P;  // host-API staging
+  DevBuf stage_V;
+  DevBuf scratch;  // packing inputs for host-API set_sources
+  unsigned char* d_flag = nullptr;
+  size_t flag_cap = 0;
+  std::vector<Rotor> rotors;
+  cusolverDnHandle_t solver = nullptr;
+  DevBuf solver_work;
+  int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
+};
+
+namespace {
+
+int fail(vlc_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CUDA_OK(c, expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail((c), VLC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+#define CHECK_CTX(c) \
+  if (!(c)) return VLC_ERR_ARG
+
+int bind_device(vlc_ctx* c) {
+  CUDA_OK(c, cudaSetDevice(c->device));
+  return VLC_OK;
+}
+
+int reserve(vlc_ctx* c, DevBuf& b, size_t doubles) {
+  if (doubles <= b.cap) return VLC_OK;
+  if (b.p) {
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    CUDA_OK(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = doubles + doubles / 8 + 1024;
+  CUDA_OK(c, cudaMalloc(&b.p, want * sizeof(double)));
+  b.cap = want;
+  return VLC_OK;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+inline long long pad_tile(long long n) { return (n + kTile - 1) / kTile * kTile; }
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+constexpr size_t kSweepSmem = (size_t)kStages * kTile * vlc::kSrcBytes + kStages * sizeof(uint64_t);
+
+template <int T, int MINB>
+int launch_sweep_T(vlc_ctx* c, const double* src, long long n_pad, long long chunk, int nsplit, long long m,
+                   const double* dP, double* out) {
+  auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB>;
+  static bool attr_set[64] = {false};
+  if (c->device < 64 && !attr_set[c->device]) {
+    CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
+    attr_set[c->device] = true;
+  }
+  dim3 grid(blocks_for(m, kThreads * T), (unsigned)nsplit, 1);
+  kern<<<grid, kThreads, kSweepSmem, c->stream>>>(src, chunk, n_pad, dP, m, out);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  return VLC_OK;
+}
+
+template <int T, int MINB>
+int query_occ(vlc_ctx* c, int* out) {
+  auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB>;
+  CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
+  CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, kThreads, kSweepSmem));
+  return VLC_OK;
+}
+
+// Launch shape: T targets per thread and nsplit source splits.
+void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, int* nsplit_out) {
+  const long long src_tiles = n_pad / kTile;
+  int T = c->tune_T;
+  if (T < 1 || T > 4) {
+    // enough target tiles to fill the machine at T=4?  otherwise fewer targets per thread
+    const long long slots4 = (long long)c->sm_count * (c->occ[4] > 0 ? c->occ[4] : 3);
+    const long long tiles4 = (m + kThreads * 4 - 1) / (kThreads * 4);
+    T = (tiles4 * src_tiles >= 4 * slots4 || tiles4 >= slots4) ? 4 : 2;
+    if (m <= kThreads) T = 1;
+  }
+  int nsplit = c->tune_nsplit;
+  if (nsplit < 1) {
+    const long long slots = (long long)c->sm_count * (c->occ[T] > 0 ? c->occ[T] : 3);
+    const long long tiles = (m + (long long)kThreads * T - 1) / ((long long)kThreads * T);
+    // candidates: keep chunks >= 4 tiles when possible, cap the partial buffer
+    long long max_split = src_tiles / 4;
+    if (max_split < 1) max_split = 1;
+    if (max_split > 256) max_split = 256;
+    const long long cap_by_mem = (long long)((size_t)1 << 31) / (3 * (m > 0 ? m : 1) * 8) + 1;  // <= 2 GiB partials
+    if (max_split > cap_by_mem) max_split = cap_by_mem;
+    double best = -1.0;
+    int best_s = 1;
+    for (long long s = 1; s <= max_split; ++s) {
+      const long long chunk_tiles = (src_tiles + s - 1) / s;
+      const long long real_s = (src_tiles + chunk_tiles - 1) / chunk_tiles;
+      const double ctas = (double)tiles * (double)real_s;
+      const double waves = ctas / (double)slots;
+      const double eff = waves / (double)(long long)(waves + 0.999999);
+      // mild preference for more, smaller CTAs once efficiency saturates (better tail), and for fewer splits
+      const double score = eff - 1e-4 * (double)s;
+      if (waves >= 1.0 ? (score > best + 1e-9) : (eff > best + 1e-9)) {
+        best = (waves >= 1.0) ? score : eff;
+        best_s = (int)s;
+      }
+      if (waves >= 8.0 && eff > 0.97) break;
+    }
+    nsplit = best_s;
+  }
+  if (nsplit > src_tiles) nsplit = (int)(src_tiles > 0 ? src_tiles : 1);
+  *T_out = T;
+  *nsplit_out = nsplit;
+}
+
+int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* dP, double* dV) {
+  if (m <= 0) return VLC_OK;
+  if (n_pad <= 0) {
+    CUDA_OK(c, cudaMemsetAsync(dV, 0, sizeof(double) * 3 * (size_t)m, c->stream));
+    return VLC_OK;
+  }
+  int T, nsplit;
+  choose_shape(c, m, n_pad, &T, &nsplit);
+  const long long src_tiles = n_pad / kTile;
+  const long long chunk_tiles = (src_tiles + nsplit - 1) / nsplit;
+  nsplit = (int)((src_tiles + chunk_tiles - 1) / chunk_tiles);
+  const long long chunk = chunk_tiles * kTile;
+  double* out = dV;
+  if (nsplit > 1) {
+    int rc = reserve(c, c->part, (size_t)nsplit * 3 * (size_t)m);
+    if (rc) return rc;
+    out = c->part.p;
+  }
+  int rc;
+  switch (T) {
+    case 1: rc = launch_sweep_T<1, 5>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
+    case 2: rc = launch_sweep_T<2, 4>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
+    case 3: rc = launch_sweep_T<3, 4>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
+    default: rc = launch_sweep_T<4, 3>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
+  }
+  if (rc) return rc;
+  if (nsplit > 1) {
+    const long long len = 3 * m;
+    vlc::bs_reduce_kernel<<<blocks_for(len, 256), 256, 0, c->stream>>>(c->part.p, nsplit, len, dV);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  return VLC_OK;
+}
+
+// host-buffer sweep: H2D targets, sweep, D2H velocities (synchronous)
+int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* P, double* V) {
+  if (m <= 0) return VLC_OK;
+  if (!P || !V) return fail(c, VLC_ERR_ARG, "null target / output pointer");
+  int rc = reserve(c, c->stage_P, 3 * (size_t)m);
+  if (rc) return rc;
+  rc = reserve(c, c->stage_V, 3 * (size_t)m);
+  if (rc) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(c->stage_P.p, P, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+  rc = sweep(c, src, n_pad, m, c->stage_P.p, c->stage_V.p);
+  if (rc) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(V, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+int check_set(vlc_ctx* c, int set) {
+  if (set < 0 || set >= VLC_MAX_SETS) return fail(c, VLC_ERR_ARG, "source set index out of range");
+  return VLC_OK;
+}
+
+Rotor* get_rotor(vlc_ctx* c, int ir) {
+  if (ir < 0 || ir >= (int)c->rotors.size() || !c->rotors[ir].defined) {
+    c->err = "rotor not defined";
+    return nullptr;
+  }
+  return &c->rotors[ir];
+}
+
+// (Re)build the packed [wing | wake] set of a rotor in the reference's enumeration order.
+int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
+  if (!r.dirty[s]) return VLC_OK;
+  const int nrows = r.nNwake > 0 ? (r.nNwake - r.rowNear + 1) : 0;
+  const bool has_far = (r.nNwake > 0) && (r.rowFar <= r.nFwake);  // classdef.f90:1458
+  const int nfar = has_far ? (r.nFwake - r.rowFar + 1) : 0;
+  const bool lifting = (abs(r.surfaceType) == 1);  // classdef.f90:4432
+  const long long wing_n = lifting ? 4LL * r.nc * r.ns * r.nb : 0;
+  const long long wing_pad = pad_tile(wing_n);
+  long long wake_per_blade = 4LL * nrows * r.ns;
+  if (has_far) wake_per_blade += r.ns + nfar + (r.have_pf[s] ? VLC_NPFWAKE : 0);
+  const long long wake_n = wake_per_blade * r.nb;
+  const long long total_pad = wing_pad + pad_tile(wake_n);
+  int rc = reserve(c, r.comb[s].rec, (size_t)total_pad * vlc::kSrcDoubles);
+  if (rc) return rc;
+  double* rec = r.comb[s].rec.p;
+  cudaStream_t st = c->stream;
+  if (wing_n > 0) {
+    for (int ib = 0; ib < r.nb; ++ib) {
+      const long long cnt = 4LL * r.nc * r.ns;
+      vlc::pack_rings_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(
+          r.wiP.p + (size_t)ib * r.nc * r.ns * vlc::kWp, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0,
+          rec + (size_t)ib * cnt * vlc::kSrcDoubles);
+      c->launches++;
+    }
+  }
+  if (wing_pad > wing_n) {
+    vlc::pack_null_kernel<<<blocks_for(wing_pad - wing_n, 256), 256, 0, st>>>(wing_pad - wing_n,
+                                                                               rec + (size_t)wing_n * vlc::kSrcDoubles);
+    c->launches++;
+  }
+  double* wrec = rec + (size_t)wing_pad * vlc::kSrcDoubles;
+  long long off = 0;
+  for (int ib = 0; ib < r.nb && r.nNwake > 0; ++ib) {
+    const double* waN = r.waN[s].p + (size_t)ib * r.nNwake * r.ns * vlc::kVr;
+    if (nrows > 0) {
+      const long long cnt = 4LL * nrows * r.ns;
+      vlc::pack_rings_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows,
+                                                                    r.ns, 0xF, 4, 1.0, 1,
+                                                                    wrec + (size_t)off * vlc::kSrcDoubles);
+      c->launches++;
+      off += cnt;
+    }
+    if (has_far) {
+      // horseshoe correction: -vf(2) of the last near row, no gam rule (classdef.f90:1460-1463)
+      vlc::pack_rings_kernel<<<blocks_for(r.ns, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns,
+                                                                     0x2, 1, -1.0, 0,
+                                                                     wrec + (size_t)off * vlc::kSrcDoubles);
+      c->launches++;
+      off += r.ns;
+      vlc::pack_fwake_kernel<<<blocks_for(nfar, 128), 128, 0, st>>>(
+          r.waF[s].p + (size_t)ib * r.nFwake * vlc::kFw, r.rowFar - 1, nfar, wrec + (size_t)off * vlc::kSrcDoubles);
+      c->launches++;
+      off += nfar;
+      if (r.have_pf[s]) {
+        vlc::pack_fwake_kernel<<<blocks_for(VLC_NPFWAKE, 128), 128, 0, st>>>(
+            r.wapF[s].p + (size_t)ib * VLC_NPFWAKE * vlc::kFw, 0, VLC_NPFWAKE, wrec + (size_t)off * vlc::kSrcDoubles);
+        c->launches++;
+        off += VLC_NPFWAKE;
+      }
+    }
+  }
+  const long long wake_pad = pad_tile(wake_n);
+  if (wake_pad > off) {
+    vlc::pack_null_kernel<<<blocks_for(wake_pad - off, 256), 256, 0, st>>>(wake_pad - off,
+                                                                            wrec + (size_t)off * vlc::kSrcDoubles);
+    c->launches++;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  r.comb[s].n = wing_n + wake_n;
+  r.comb[s].n_pad = total_pad;
+  r.wing_pad[s] = wing_pad;
+  r.wing_n = wing_n;
+  r.dirty[s] = false;
+  return VLC_OK;
+}
+
+// bound-vortex set (classdef.f90:1376-1396): (vf2 + vf4)*gam of every ring, minus vf2*gam of row nc.
+int pack_bound(vlc_ctx* c, Rotor& r) {
+  if (!r.bound_dirty) return VLC_OK;
+  const long long per_blade = 2LL * r.nc * r.ns + r.ns;
+  const long long n = per_blade * r.nb;
+  const long long n_pad = pad_tile(n);
+  int rc = reserve(c, r.bound.rec, (size_t)n_pad * vlc::kSrcDoubles);
+  if (rc) return rc;
+  double* rec = r.bound.rec.p;
+  long long off = 0;
+  for (int ib = 0; ib < r.nb; ++ib) {
+    const double* wiP = r.wiP.p + (size_t)ib * r.nc * r.ns * vlc::kWp;
+    const long long cnt = 2LL * r.nc * r.ns;
+    vlc::pack_rings_kernel<<<blocks_for(cnt, 256), 256, 0, c->stream>>>(wiP, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xA, 2,
+                                                                         1.0, 0, rec + (size_t)off * vlc::kSrcDoubles);
+    off += cnt;
+    vlc::pack_rings_kernel<<<blocks_for(r.ns, 128), 128, 0, c->stream>>>(wiP, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2,
+                                                                          1, -1.0, 0,
+                                                                          rec + (size_t)off * vlc::kSrcDoubles);
+    off += r.ns;
+    c->launches += 2;
+  }
+  if (n_pad > n) {
+    vlc::pack_null_kernel<<<blocks_for(n_pad - n, 256), 256, 0, c->stream>>>(n_pad - n,
+                                                                              rec + (size_t)n * vlc::kSrcDoubles);
+    c->launches++;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  r.bound.n = n;
+  r.bound.n_pad = n_pad;
+  r.bound_dirty = false;
+  return VLC_OK;
+}
+
+int upload(vlc_ctx* c, DevBuf& b, size_t total, size_t offset, const double* host, size_t count) {
+  int rc = reserve(c, b, total);
+  if (rc) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(b.p + offset, host, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer right away
+  return VLC_OK;
+}
+
+}  // namespace
+
+// ============================================================================ context
+
+extern "C" const char* vlc_version(void) { return "volcanor_b200 0.1 (sm_100a, FP64)"; }
+
+extern "C" int vlc_create(int device, vlc_ctx** out) {
+  if (!out) return VLC_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                     " (volcanor_b200 has no CPU fallback)";
+    return VLC_ERR_NODEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return VLC_ERR_ARG;
+  }
+  vlc_ctx* c = new vlc_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice / cudaGetDeviceProperties failed";
+    delete c;
+    return VLC_ERR_CUDA;
+  }
+  if (prop.major < 10) {
+    g_create_error = std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only";
+    delete c;
+    return VLC_ERR_NODEVICE;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->mem_bytes = (long long)prop.totalGlobalMem;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaStreamCreate failed";
+    delete c;
+    return VLC_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  int rc = 0;
+  rc |= query_occ<1, 5>(c, &c->occ[1]);
+  rc |= query_occ<2, 4>(c, &c->occ[2]);
+  rc |= query_occ<3, 4>(c, &c->occ[3]);
+  rc |= query_occ<4, 3>(c, &c->occ[4]);
+  if (rc) {
+    g_create_error = "sweep kernel not loadable on this device: " + c->err;
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return VLC_ERR_CUDA;
+  }
+  *out = c;
+  return VLC_OK;
+}
+
+extern "C" int vlc_destroy(vlc_ctx* c) {
+  if (!c) return VLC_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->sets) release(s.rec);
+  release(c->part);
+  release(c->stage_P);
+  release(c->stage_V);
+  release(c->scratch);
+  release(c->solver_work);
+  if (c->d_flag) cudaFree(c->d_flag);
+  for (auto& r : c->rotors) {
+    release(r.wiP);
+    for (int s = 0; s < 2; ++s) {
+      release(r.waN[s]);
+      release(r.waF[s]);
+      release(r.wapF[s]);
+      release(r.comb[s].rec);
+    }
+    release(r.bound.rec);
+    release(r.LU);
+    if (r.d_ipiv) cudaFree(r.d_ipiv);
+    if (r.d_info) cudaFree(r.d_info);
+  }
+  if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return VLC_OK;
+}
+
+extern "C" const char* vlc_last_error(const vlc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int vlc_set_stream(vlc_ctx* c, void* s) {
+  CHECK_CTX(c);
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  if (c->solver) cusolverDnSetStream(c->solver, c->stream);
+  return VLC_OK;
+}
+
+extern "C" int vlc_sync(vlc_ctx* c) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_device_info(vlc_ctx* c, int* sm, int* maj, int* min, int64_t* mem) {
+  CHECK_CTX(c);
+  if (sm) *sm = c->sm_count;
+  if (maj) *maj = c->cc_major;
+  if (min) *min = c->cc_minor;
+  if (mem) *mem = c->mem_bytes;
+  return VLC_OK;
+}
+
+extern "C" int vlc_set_tuning(vlc_ctx* c, int T, int nsplit) {
+  CHECK_CTX(c);
+  if (T < 0 || T > 4 || nsplit < 0) return fail(c, VLC_ERR_ARG, "targets_per_thread in 0..4, nsplit >= 0");
+  c->tune_T = T;
+  c->tune_nsplit = nsplit;
+  return VLC_OK;
+}
+
+extern "C" int64_t vlc_launch_count(const vlc_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int vlc_source_tile(void) { return kTile; }
+
+// ============================================================================ tier 1
+
+extern "C" int vlc_set_sources_dev(vlc_ctx* c, int set, int64_t n, const double* p1, const double* p2,
+                                   const double* rvc, const double* gam, const uint8_t* flag) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  if (n < 0) return fail(c, VLC_ERR_ARG, "n < 0");
+  if (n > 0 && (!p1 || !p2 || !rvc || !gam)) return fail(c, VLC_ERR_ARG, "null source array");
+  SourceSet& s = c->sets[set];
+  const long long n_pad = pad_tile(n);
+  if ((rc = reserve(c, s.rec, (size_t)n_pad * vlc::kSrcDoubles))) return rc;
+  if (n_pad > 0) {
+    vlc::pack_flat_kernel<<<blocks_for(n_pad, 256), 256, 0, c->stream>>>(n, n_pad, p1, p2, rvc, gam, flag, s.rec.p);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  s.n = n;
+  s.n_pad = n_pad;
+  return VLC_OK;
+}
+
+extern "C" int vlc_set_sources(vlc_ctx* c, int set, int64_t n, const double* p1, const double* p2, const double* rvc,
+                               const double* gam, const uint8_t* flag) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  if (n < 0) return fail(c, VLC_ERR_ARG, "n < 0");
+  if (n == 0) return vlc_set_sources_dev(c, set, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (!p1 || !p2 || !rvc || !gam) return fail(c, VLC_ERR_ARG, "null source array");
+  if ((rc = reserve(c, c->scratch, 8 * (size_t)n))) return rc;
+  double* d = c->scratch.p;
+  cudaStream_t st = c->stream;
+  CUDA_OK(c, cudaMemcpyAsync(d, p1, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(c, cudaMemcpyAsync(d + 3 * n, p2, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(c, cudaMemcpyAsync(d + 6 * n, rvc, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(c, cudaMemcpyAsync(d + 7 * n, gam, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  const uint8_t* dflag = nullptr;
+  if (flag) {
+    if (c->flag_cap < (size_t)n) {
+      if (c->d_flag) {
+        CUDA_OK(c, cudaStreamSynchronize(st));
+        CUDA_OK(c, cudaFree(c->d_flag));
+        c->d_flag = nullptr;
+      }
+      CUDA_OK(c, cudaMalloc(&c->d_flag, (size_t)n + 1024));
+      c->flag_cap = (size_t)n + 1024;
+    }
+    CUDA_OK(c, cudaMemcpyAsync(c->d_flag, flag, (size_t)n, cudaMemcpyHostToDevice, st));
+    dflag = c->d_flag;
+  }
+  rc = vlc_set_sources_dev(c, set, n, d, d + 3 * n, d + 6 * n, d + 7 * n, dflag);
+  if (rc) return rc;
+  CUDA_OK(c, cudaStreamSynchronize(st));
+  return VLC_OK;
+}
+
+extern "C" int64_t vlc_num_sources(const vlc_ctx* c, int set) {
+  if (!c || set < 0 || set >= VLC_MAX_SETS) return -1;
+  return c->sets[set].n;
+}
+
+extern "C" int vlc_vind_dev(vlc_ctx* c, int set, int64_t m, const double* dP, double* dV) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  if (m < 0) return fail(c, VLC_ERR_ARG, "m < 0");
+  if (m > 0 && (!dP || !dV)) return fail(c, VLC_ERR_ARG, "null target / output pointer");
+  return sweep(c, c->sets[set].rec.p, c->sets[set].n_pad, m, dP, dV);
+}
+
+extern "C" int vlc_vind_range_dev(vlc_ctx* c, int set, int64_t first, int64_t count, int64_t m, const double* dP,
+                                  double* dV) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  const SourceSet& s = c->sets[set];
+  if (first < 0 || count < 0 || first % kTile != 0 || first + count > s.n_pad)
+    return fail(c, VLC_ERR_ARG, "source range must start on a tile boundary and lie inside the set");
+  if (m > 0 && (!dP || !dV)) return fail(c, VLC_ERR_ARG, "null target / output pointer");
+  long long cnt_pad = pad_tile(count);
+  if (first + cnt_pad > s.n_pad) cnt_pad = s.n_pad - first;
+  if (cnt_pad != count && first + count < s.n)
+    return fail(c, VLC_ERR_ARG, "an interior source range must be a whole number of tiles");
+  return sweep(c, s.rec.p + (size_t)first * vlc::kSrcDoubles, cnt_pad, m, dP, dV);
+}
+
+extern "C" int vlc_vind(vlc_ctx* c, int set, int64_t m, const double* P, double* V) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  if (m < 0) return fail(c, VLC_ERR_ARG, "m < 0");
+  return sweep_host(c, c->sets[set].rec.p, c->sets[set].n_pad, m, P, V);
+}
+
+// ============================================================================ tier 2
+
+extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int nNwake, int nFwake, int surfaceType) {
+  CHECK_CTX(c);
+  if (ir < 0 || ir > 1023) return fail(c, VLC_ERR_ARG, "rotor index out of range");
+  if (nb < 1 || nc < 1 || ns < 1 || nNwake < 0 || nFwake < 0) return fail(c, VLC_ERR_ARG, "bad rotor sizes");
+  if ((int)c->rotors.size() <= ir) c->rotors.resize(ir + 1);
+  Rotor& r = c->rotors[ir];
+  r.defined = true;
+  r.nb = nb;
+  r.nc = nc;
+  r.ns = ns;
+  r.nNwake = nNwake;
+  r.nFwake = nFwake;
+  r.surfaceType = surfaceType == 0 ? 1 : surfaceType;  // classdef.f90:3023
+  r.rowNear = nNwake + 1;                              // main.f90:228-230
+  r.rowFar = nFwake + 1;
+  r.N = nc * ns * nb;
+  r.dirty[0] = r.dirty[1] = r.bound_dirty = true;
+  r.factored = false;
+  r.have_pf[0] = r.have_pf[1] = false;
+  int rc = bind_device(c);
+  if (rc) return rc;
+  // zero-initialised device copies so that never-uploaded rows hold gam = 0 like rotor_init (:3835-3836)
+  if ((rc = reserve(c, r.wiP, (size_t)nb * nc * ns * vlc::kWp))) return rc;
+  CUDA_OK(c, cudaMemsetAsync(r.wiP.p, 0, r.wiP.cap * sizeof(double), c->stream));
+  for (int s = 0; s < 2; ++s) {
+    if ((rc = reserve(c, r.waN[s], (size_t)nb * nNwake * ns * vlc::kVr + 1))) return rc;
+    if ((rc = reserve(c, r.waF[s], (size_t)nb * nFwake * vlc::kFw + 1))) return rc;
+    if ((rc = reserve(c, r.wapF[s], (size_t)nb * VLC_NPFWAKE * vlc::kFw))) return rc;
+    CUDA_OK(c, cudaMemsetAsync(r.waN[s].p, 0, r.waN[s].cap * sizeof(double), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(r.waF[s].p, 0, r.waF[s].cap * sizeof(double), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(r.wapF[s].p, 0, r.wapF[s].cap * sizeof(double), c->stream));
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_set_rows(vlc_ctx* c, int ir, int rowNear, int rowFar) {
+  CHECK_CTX(c);
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (rowNear < 1 || rowNear > r->nNwake + 1 || rowFar < 1 || rowFar > r->nFwake + 1)
+    return fail(c, VLC_ERR_ARG, "rowNear / rowFar out of range");
+  if (rowNear != r->rowNear || rowFar != r->rowFar) r->dirty[0] = r->dirty[1] = true;
+  r->rowNear = rowNear;
+  r->rowFar = rowFar;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_put_wing(vlc_ctx* c, int ir, int ib, const double* wiP) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !wiP) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const size_t per = (size_t)r->nc * r->ns * vlc::kWp;
+  r->dirty[0] = r->dirty[1] = r->bound_dirty = true;
+  r->factored = false;
+  return upload(c, r->wiP, per * r->nb, per * ib, wiP, per);
+}
+
+extern "C" int vlc_rotor_put_wing_gam(vlc_ctx* c, int ir, int ib, const double* gam) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !gam) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const size_t np = (size_t)r->nc * r->ns;
+  CUDA_OK(c, cudaMemcpy2DAsync(r->wiP.p + (size_t)ib * np * vlc::kWp + vlc::kVrGam, vlc::kWp * sizeof(double), gam,
+                               sizeof(double), sizeof(double), np, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  r->dirty[0] = r->dirty[1] = r->bound_dirty = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_put_nwake(vlc_ctx* c, int ir, int ib, int predicted, const double* waN) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !waN) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const int s = predicted ? 1 : 0;
+  const size_t per = (size_t)r->nNwake * r->ns * vlc::kVr;
+  r->dirty[s] = true;
+  if (per == 0) return VLC_OK;
+  return upload(c, r->waN[s], per * r->nb, per * ib, waN, per);
+}
+
+extern "C" int vlc_rotor_put_fwake(vlc_ctx* c, int ir, int ib, int predicted, const double* waF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb) return fail(c, VLC_ERR_ARG, "bad blade index");
+  const int s = predicted ? 1 : 0;
+  const size_t per = (size_t)r->nFwake * vlc::kFw;
+  r->dirty[s] = true;
+  if (per == 0) return VLC_OK;
+  if (!waF) return fail(c, VLC_ERR_ARG, "null pointer");
+  return upload(c, r->waF[s], per * r->nb, per * ib, waF, per);
+}
+
+extern "C" int vlc_rotor_put_pfwake(vlc_ctx* c, int ir, int ib, int predicted, const double* wapF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !wapF) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const int s = predicted ? 1 : 0;
+  const size_t per = (size_t)VLC_NPFWAKE * vlc::kFw;
+  r->dirty[s] = true;
+  r->have_pf[s] = true;
+  return upload(c, r->wapF[s], per * r->nb, per * ib, wapF, per);
+}
+
+extern "C" int vlc_rotor_vind_bywing(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if ((rc = pack_rotor(c, *r, 0))) return rc;
+  return sweep_host(c, r->comb[0].rec.p, r->wing_pad[0], m, P, V);
+}
+
+extern "C" int vlc_rotor_vind_bywake(vlc_ctx* c, int ir, int predicted, int64_t m, const double* P, double* V) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const int s = predicted ? 1 : 0;
+  if ((rc = pack_rotor(c, *r, s))) return rc;
+  return sweep_host(c, r->comb[s].rec.p + (size_t)r->wing_pad[s] * vlc::kSrcDoubles,
+                    r->comb[s].n_pad - r->wing_pad[s], m, P, V);
+}
+
+extern "C" int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if ((rc = pack_bound(c, *r))) return rc;
+  return sweep_host(c, r->bound.rec.p, r->bound.n_pad, m, P, V);
+}
+
+extern "C" int vlc_rotor_vind(vlc_ctx* c, int ir, int predicted, int64_t m, const double* P, double* V) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const int s = predicted ? 1 : 0;
+  if ((rc = pack_rotor(c, *r, s))) return rc;
+  return sweep_host(c, r->comb[s].rec.p, r->comb[s].n_pad, m, P, V);
+}
+
+extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake, int rows, int cols, int ld,
+                                        int predicted, double* vindArray) {
+  CHECK_CTX(c);
+  if (rows < 0 || cols < 1 || ld < rows) return fail(c, VLC_ERR_ARG, "bad Nwake slice shape");
+  if (rows == 0) return VLC_OK;
+  if (!Nwake || !vindArray) return fail(c, VLC_ERR_ARG, "null pointer");
+  // targets in the reference's order (libCommon.f90:133-145): corner 2 of ring (i,j) = vf(2)%fc(:,1),
+  // then corner 3 of the last column = vf(3)%fc(:,1)
+  std::vector<double> P((size_t)3 * rows * (cols + 1));
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) {
+      const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * j);
+      std::memcpy(&P[3 * ((size_t)i + (size_t)rows * j)], rec + VLC_VF_DOUBLES * 1, 3 * sizeof(double));
+    }
+  for (int i = 0; i < rows; ++i) {
+    const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * (cols - 1));
+    std::memcpy(&P[3 * ((size_t)i + (size_t)rows * cols)], rec + VLC_VF_DOUBLES * 2, 3 * sizeof(double));
+  }
+  return vlc_rotor_vind(c, ir, predicted, (int64_t)rows * (cols + 1), P.data(), vindArray);
+}
+
+extern "C" int vlc_vind_onFwake_byRotor(vlc_ctx* c, int ir, const double* Fwake, int rows, int predicted,
+                                        double* vindArray) {
+  CHECK_CTX(c);
+  if (rows < 0) return fail(c, VLC_ERR_ARG, "rows < 0");
+  if (rows == 0) return VLC_OK;
+  if (!Fwake || !vindArray) return fail(c, VLC_ERR_ARG, "null pointer");
+  std::vector<double> P((size_t)3 * rows);
+  for (int i = 0; i < rows; ++i) std::memcpy(&P[3 * (size_t)i], Fwake + (size_t)VLC_FWAKE_DOUBLES * i, 3 * sizeof(double));
+  return vlc_rotor_vind(c, ir, predicted, rows, P.data(), vindArray);
+}
+
+// ---------------------------------------------------------------------------- AIC
+
+namespace {
+int ensure_solver(vlc_ctx* c) {
+  if (c->solver) return VLC_OK;
+  cusolverStatus_t st = cusolverDnCreate(&c->solver);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(c, VLC_ERR_CUDA, "cusolverDnCreate failed: " + std::to_string((int)st));
+  cusolverDnSetStream(c->solver, c->stream);
+  return VLC_OK;
+}
+}  // namespace
+
+extern "C" int vlc_rotor_calcAIC(vlc_ctx* c, int ir, double* AIC_out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if ((rc = ensure_solver(c))) return rc;
+  const int N = r->N;
+  if ((rc = reserve(c, r->LU, (size_t)N * N))) return rc;
+  if (!r->d_ipiv) CUDA_OK(c, cudaMalloc(&r->d_ipiv, sizeof(int) * (size_t)N));
+  if (!r->d_info) CUDA_OK(c, cudaMalloc(&r->d_info, sizeof(int)));
+  dim3 grid(blocks_for(N, 128), N, 1);
+  vlc::aic_assemble_kernel<<<grid, 128, 0, c->stream>>>(r->wiP.p, N, r->LU.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  if (AIC_out) {
+    CUDA_OK(c, cudaMemcpyAsync(AIC_out, r->LU.p, sizeof(double) * (size_t)N * N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  int lwork = 0;
+  cusolverStatus_t st = cusolverDnDgetrf_bufferSize(c->solver, N, N, r->LU.p, N, &lwork);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(c, VLC_ERR_CUDA, "cusolverDnDgetrf_bufferSize failed");
+  if ((rc = reserve(c, c->solver_work, (size_t)lwork + 1))) return rc;
+  st = cusolverDnDgetrf(c->solver, N, N, r->LU.p, N, c->solver_work.p, r->d_ipiv, r->d_info);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(c, VLC_ERR_CUDA, "cusolverDnDgetrf failed: " + std::to_string((int)st));
+  int info = 0;
+  CUDA_OK(c, cudaMemcpyAsync(&info, r->d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->launches++;
+  if (info != 0) return fail(c, VLC_ERR_SINGULAR, "Matrix is numerically singular!");  // libMath.f90:73
+  r->factored = true;
+  return VLC_OK;
+}
+
+namespace {
+int solve_dev(vlc_ctx* c, Rotor* r, double* dB, int nrhs) {
+  cusolverStatus_t st = cusolverDnDgetrs(c->solver, CUBLAS_OP_N, r->N, nrhs, r->LU.p, r->N, r->d_ipiv, dB, r->N, r->d_info);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(c, VLC_ERR_CUDA, "cusolverDnDgetrs failed: " + std::to_string((int)st));
+  c->launches++;
+  return VLC_OK;
+}
+}  // namespace
+
+extern "C" int vlc_rotor_solve(vlc_ctx* c, int ir, const double* RHS, double* gamVec) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (!r->factored) return fail(c, VLC_ERR_STATE, "vlc_rotor_solve before vlc_rotor_calcAIC");
+  if (!RHS || !gamVec) return fail(c, VLC_ERR_ARG, "null pointer");
+  if ((rc = reserve(c, c->stage_V, (size_t)r->N))) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(c->stage_V.p, RHS, sizeof(double) * r->N, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = solve_dev(c, r, c->stage_V.p, 1))) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(gamVec, c->stage_V.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_AIC_inv(vlc_ctx* c, int ir, double* AIC_inv) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (!r->factored) return fail(c, VLC_ERR_STATE, "vlc_rotor_get_AIC_inv before vlc_rotor_calcAIC");
+  if (!AIC_inv) return fail(c, VLC_ERR_ARG, "null pointer");
+  const size_t NN = (size_t)r->N * r->N;
+  if ((rc = reserve(c, c->scratch, NN))) return rc;
+  vlc::identity_kernel<<<blocks_for((long long)NN, 256), 256, 0, c->stream>>>(r->N, c->scratch.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  if ((rc = solve_dev(c, r, c->scratch.p, r->N))) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(AIC_inv, c->scratch.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+// ============================================================================ tier 3
+
+#define LAUNCH1D(c, kern, n, ...)                                                      \
+  do {                                                                                 \
+    if ((n) > 0) {                                                                     \
+      kern<<<blocks_for((n), 256), 256, 0, (c)->stream>>>(__VA_ARGS__);                \
+      CUDA_OK((c), cudaGetLastError());                                                \
+      (c)->launches++;                                                                 \
+    }                                                                                  \
+  } while (0)
+
+extern "C" int vlc_convect_dev(vlc_ctx* c, int64_t n, double* x, const double* v, double dt) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!x || !v))) return fail(c, VLC_ERR_ARG, "bad arguments");
+  LAUNCH1D(c, vlc::convect_kernel, 3 * n, 3 * n, x, v, dt);
+  return VLC_OK;
+}
+
+extern "C" int vlc_ab2_dev(vlc_ctx* c, int64_t n, const double* v, const double* v1, double* out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!v || !v1 || !out))) return fail(c, VLC_ERR_ARG, "bad arguments");
+  LAUNCH1D(c, vlc::ab2_kernel, 3 * n, 3 * n, v, v1, out);
+  return VLC_OK;
+}
+
+extern "C" int vlc_am2_dev(vlc_ctx* c, int64_t n, const double* vp, const double* vs, double* out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!vp || !vs || !out))) return fail(c, VLC_ERR_ARG, "bad arguments");
+  LAUNCH1D(c, vlc::am2_kernel, 3 * n, 3 * n, vp, vs, out);
+  return VLC_OK;
+}
+
+extern "C" int vlc_dissipate_dev(vlc_ctx* c, int64_t n_rvc, double* rvc, int64_t n_gam, double* gam,
+                                 double apparentViscCoeff, double nu, double decayCoeff, double dt) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (n_rvc < 0 || n_gam < 0) return fail(c, VLC_ERR_ARG, "bad arguments");
+  if (rvc) LAUNCH1D(c, vlc::core_growth_kernel, n_rvc, n_rvc, rvc, apparentViscCoeff, nu, dt);
+  if (gam) LAUNCH1D(c, vlc::decay_kernel, n_gam, n_gam, gam, decayCoeff, dt);
+  return VLC_OK;
+}
+
+extern "C" int vlc_dissipate_lattice_dev(vlc_ctx* c, int nrows, int ns, double* rvc4, double* gam,
+                                         double apparentViscCoeff, double nu, double decayCoeff, double dt) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (nrows < 0 || ns < 0 || !rvc4 || !gam) return fail(c, VLC_ERR_ARG, "bad arguments");
+  const long long n = (long long)nrows * ns;
+  LAUNCH1D(c, vlc::dissipate_lattice_kernel, n, nrows, ns, rvc4, gam, apparentViscCoeff, nu, decayCoeff, dt);
+  LAUNCH1D(c, vlc::dissipate_lattice_vf4_kernel, n, nrows, ns, rvc4);
+  return VLC_OK;
+}
+
+extern "C" int vlc_strain_dev(vlc_ctx* c, int64_t n, const double* p1, const double* p2, const double* l0,
+                              const double* rvc0, double* rvc) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!p1 || !p2 || !l0 || !rvc0 || !rvc))) return fail(c, VLC_ERR_ARG, "bad arguments");
+  LAUNCH1D(c, vlc::strain_kernel, n, n, p1, p2, l0, rvc0, rvc);
+  return VLC_OK;
+}
+
+extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, int ns, const double* nodes,
+                                    const double* gam, const double* rvc4, int nfar, const double* far_nodes,
+                                    const double* gamF, const double* rvcF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  if (nrows < 0 || ns < 1 || nfar < 0) return fail(c, VLC_ERR_ARG, "bad lattice shape");
+  if (nrows > 0 && (!nodes || !gam || !rvc4)) return fail(c, VLC_ERR_ARG, "null lattice array");
+  if (nfar > 0 && (!far_nodes || !gamF || !rvcF || nrows == 0)) return fail(c, VLC_ERR_ARG, "bad far-wake arguments");
+  SourceSet& s = c->sets[set];
+  const long long base = append ? s.n : 0;
+  const long long add = 4LL * nrows * ns + (nfar > 0 ? ns + nfar : 0);
+  const long long n_new = base + add;
+  const long long n_pad = pad_tile(n_new);
+  if ((size_t)n_pad * vlc::kSrcDoubles > s.rec.cap) {
+    // grow, preserving what is already packed
+    DevBuf nb;
+    if ((rc = reserve(c, nb, (size_t)n_pad * vlc::kSrcDoubles * 2))) return rc;
+    if (base > 0)
+      CUDA_OK(c, cudaMemcpyAsync(nb.p, s.rec.p, sizeof(double) * (size_t)base * vlc::kSrcDoubles,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    release(s.rec);
+    s.rec = nb;
+  }
+  double* rec = s.rec.p + (size_t)base * vlc::kSrcDoubles;
+  long long off = 0;
+  if (nrows > 0) {
+    const long long cnt = 4LL * nrows * ns;
+    LAUNCH1D(c, vlc::pack_lattice_kernel, cnt, nrows, ns, nodes, gam, rvc4, rec);
+    off += cnt;
+  }
+  if (nfar > 0) {
+    LAUNCH1D(c, vlc::pack_horseshoe_kernel, (long long)ns, nrows, ns, nodes, gam, rvc4,
+             rec + (size_t)off * vlc::kSrcDoubles);
+    off += ns;
+    LAUNCH1D(c, vlc::pack_chain_kernel, (long long)nfar, nfar, far_nodes, gamF, rvcF,
+             rec + (size_t)off * vlc::kSrcDoubles);
+    off += nfar;
+  }
+  if (n_pad > n_new)
+    LAUNCH1D(c, vlc::pack_null_kernel, n_pad - n_new, n_pad - n_new, s.rec.p + (size_t)n_new * vlc::kSrcDoubles);
+  s.n = n_new;
+  s.n_pad = n_pad;
+  return VLC_OK;
+}
+
+extern "C" int vlc_lattice_targets_dev(vlc_ctx* c, int nrows, int ns, const double* nodes, double* P) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (nrows < 0 || ns < 0 || !nodes || !P) return fail(c, VLC_ERR_ARG, "bad arguments");
+  const long long n = 3LL * nrows * (ns + 1);
+  LAUNCH1D(c, vlc::lattice_gather_kernel, n, nrows, ns, nodes, P);
+  return VLC_OK;
+}
+
+extern "C" int vlc_lattice_scatter_dev(vlc_ctx* c, int nrows, int ns, double* nodes, const double* P) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (nrows < 0 || ns < 0 || !nodes || !P) return fail(c, VLC_ERR_ARG, "bad arguments");
+  const long long n = 3LL * nrows * (ns + 1);
+  LAUNCH1D(c, vlc::lattice_scatter_kernel, n, nrows, ns, nodes, P);
+  return VLC_OK;
+}
+
+// ============================================================================ measurement
+
+extern "C" int vlc_measure_fp64_peak(vlc_ctx* c, int iters, double* flops_per_s, double* ms_out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (iters < 1) iters = 1;
+  const int blocks = c->sm_count * 8, threads = 256;
+  if ((rc = reserve(c, c->scratch, (size_t)blocks * threads))) return rc;
+  cudaEvent_t e0, e1;
+  CUDA_OK(c, cudaEventCreate(&e0));
+  CUDA_OK(c, cudaEventCreate(&e1));
+  vlc::dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(iters / 4 + 1, c->scratch.p);  // warm-up
+  CUDA_OK(c, cudaEventRecord(e0, c->stream));
+  vlc::dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(iters, c->scratch.p);
+  CUDA_OK(c, cudaEventRecord(e1, c->stream));
+  CUDA_OK(c, cudaEventSynchronize(e1));
+  CUDA_OK(c, cudaGetLastError());
+  c->launches += 2;
+  float ms = 0.f;
+  CUDA_OK(c, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = (double)blocks * threads * (double)iters * vlc::kPeakChains * vlc::kPeakUnroll * 2.0;
+  if (flops_per_s) *flops_per_s = flops / (ms * 1e-3);
+  if (ms_out) *ms_out = ms;
+  return VLC_OK;
+}

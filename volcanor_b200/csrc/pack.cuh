@@ -1,0 +1,178 @@
+// pack.cuh -- device kernels that turn the caller's filament descriptions into packed 96-byte
+// source records (vlc_device.cuh: p1, p2, r0, L2, K, G), in the REFERENCE's enumeration order
+// (src/classdef.f90:1342-1357 wing rings; :1437-1513 wake rings, horseshoe correction, far and
+// prescribed filaments), and the AIC assembly kernel (classdef.f90:4151-4176).
+#pragma once
+#include "vlc_device.cuh"
+
+namespace vlc {
+
+#define VLC_INV4PI 0.07957747154594767 /* 0.25/pi, classdef.f90:13 */
+
+// Record layout offsets (doubles) of the reference derived types, see include/volcanor_b200.h.
+constexpr int kVf = 12, kVr = 50, kFw = 13, kWp = 104;
+constexpr int kVfRvc = 9;      // vf%rVc
+constexpr int kVrGam = 48;     // vr%gam
+constexpr int kFwGam = 12;     // Fwake%gam
+constexpr int kWpCP = 64;      // wingpanel%CP   (vr 50 + gamPrev,gamTrapz 2 + PC 12)
+constexpr int kWpNcap = 67;    // wingpanel%nCap
+
+__device__ __forceinline__ void write_rec(double* __restrict__ rec, double p1x, double p1y, double p1z, double p2x,
+                                          double p2y, double p2z, double rvc, double G) {
+  const double r0x = p2x - p1x, r0y = p2y - p1y, r0z = p2z - p1z;
+  const double L2 = fma(r0z, r0z, fma(r0y, r0y, r0x * r0x));
+  const double q = rvc * rvc * L2;  // (rVc*|r0|)^2 ; reference: (rVc*norm2(r0))**4 (classdef.f90:501)
+  double2* o = reinterpret_cast<double2*>(rec);
+  o[0] = make_double2(p1x, p1y);
+  o[1] = make_double2(p1z, p2x);
+  o[2] = make_double2(p2y, p2z);
+  o[3] = make_double2(r0x, r0y);
+  o[4] = make_double2(r0z, L2);
+  o[5] = make_double2(q * q, G);
+}
+
+__device__ __forceinline__ void write_null_rec(double* __restrict__ rec) {
+  double2* o = reinterpret_cast<double2*>(rec);
+  const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o[k] = z;
+}
+
+// gam -> G with the reference's wake rule `abs(gam) > eps` (classdef.f90:1452) when wake != 0.
+__device__ __forceinline__ double strength(double gam, bool wake) {
+  if (wake && !(fabs(gam) > 2.220446049250313e-16)) return 0.0;
+  return gam * VLC_INV4PI;
+}
+
+// Flat filament arrays (tier 1). Records [n, n_pad) become null filaments.
+__global__ void pack_flat_kernel(long long n, long long n_pad, const double* __restrict__ p1,
+                                 const double* __restrict__ p2, const double* __restrict__ rvc,
+                                 const double* __restrict__ gam, const unsigned char* __restrict__ flag,
+                                 double* __restrict__ rec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  double* r = rec + i * kSrcDoubles;
+  if (i >= n) {
+    write_null_rec(r);
+    return;
+  }
+  const bool wake = flag ? (flag[i] != 0) : false;
+  write_rec(r, p1[3 * i], p1[3 * i + 1], p1[3 * i + 2], p2[3 * i], p2[3 * i + 1], p2[3 * i + 2], rvc[i],
+            strength(gam[i], wake));
+}
+
+__global__ void pack_null_kernel(long long count, double* __restrict__ rec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) write_null_rec(rec + i * kSrcDoubles);
+}
+
+// Filaments of vortex rings stored as reference records.
+//   ring(i, j) at base + stride*(i + ld*j) doubles, i in [i0, i0+ni), j in [0, nj); 4 filaments each.
+//   Output order: j outer, i inner, filament innermost  (classdef.f90:1350-1355, :1450-1456).
+//   fil_mask selects filaments (bit f), sign scales gam.
+__global__ void pack_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int ni, int nj,
+                                  int fil_mask, int nfil, double sign, int wake, double* __restrict__ rec) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)ni * nj * nfil;
+  if (q >= total) return;
+  const int fsel = (int)(q % nfil);
+  const long long ring = q / nfil;
+  const int i = (int)(ring % ni) + i0;
+  const int j = (int)(ring / ni);
+  // fsel-th set bit of fil_mask
+  int f = 0, seen = -1;
+  for (int b = 0; b < 4; ++b)
+    if (fil_mask & (1 << b)) {
+      ++seen;
+      if (seen == fsel) f = b;
+    }
+  const double* vr = base + (size_t)stride * ((size_t)i + (size_t)ld * j);
+  const double* vf = vr + kVf * f;
+  write_rec(rec + q * kSrcDoubles, vf[0], vf[1], vf[2], vf[3], vf[4], vf[5], vf[kVfRvc],
+            strength(sign * vr[kVrGam], wake != 0));
+}
+
+// Far-wake / prescribed-wake filaments stored as Fwake_class records (13 doubles), i in [i0, i0+ni).
+__global__ void pack_fwake_kernel(const double* __restrict__ base, int i0, int ni, double* __restrict__ rec) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ni) return;
+  const double* fw = base + (size_t)kFw * (i0 + q);
+  write_rec(rec + (size_t)q * kSrcDoubles, fw[0], fw[1], fw[2], fw[3], fw[4], fw[5], fw[kVfRvc],
+            strength(fw[kFwGam], true));
+}
+
+// AIC(row, col) = vr(col)%vind(CP(row)) . nCap(row)   classdef.f90:4159-4176 (serial 6-deep loop there).
+// One thread per entry; the 4 filaments of a ring are summed in order like vr_vind (:537-540).
+// wiP: all blades' wingpanel records, blade-major: panel (ic, is) of blade ib at (ib*nc*ns + ic + nc*is)*104.
+__global__ void aic_assemble_kernel(const double* __restrict__ wiP, int N, double* __restrict__ A) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.y;
+  if (row >= N) return;
+  const double* pr = wiP + (size_t)kWp * row;
+  const double* pc = wiP + (size_t)kWp * col;
+  const double px = pr[kWpCP], py = pr[kWpCP + 1], pz = pr[kWpCP + 2];
+  double vx = 0.0, vy = 0.0, vz = 0.0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const double* vf = pc + kVf * f;
+    Src s;
+    s.p1x = vf[0]; s.p1y = vf[1]; s.p1z = vf[2]; s.p2x = vf[3]; s.p2y = vf[4]; s.p2z = vf[5];
+    s.r0x = s.p2x - s.p1x; s.r0y = s.p2y - s.p1y; s.r0z = s.p2z - s.p1z;
+    s.L2 = fma(s.r0z, s.r0z, fma(s.r0y, s.r0y, s.r0x * s.r0x));
+    const double q = vf[kVfRvc] * vf[kVfRvc] * s.L2;
+    s.K = q * q;
+    s.G = VLC_INV4PI;
+    pair_accumulate(s, px, py, pz, vx, vy, vz);
+  }
+  A[(size_t)row + (size_t)N * col] = vx * pr[kWpNcap] + vy * pr[kWpNcap + 1] + vz * pr[kWpNcap + 2];
+}
+
+// ---- tier 3: node-indexed lattice -> packed records ------------------------------------------
+// nodes(3, nrows+1, ns+1): node (r, c) at 3*(r + (nrows+1)*c).  Ring (r, j): corners
+// 1=(r,j) 2=(r+1,j) 3=(r+1,j+1) 4=(r,j+1); filament k runs corner k -> k+1 (classdef.f90:569-592).
+// Output order: j outer, r inner, filament innermost (classdef.f90:1450-1456).
+__global__ void pack_lattice_kernel(int nrows, int ns, const double* __restrict__ nodes,
+                                    const double* __restrict__ gam, const double* __restrict__ rvc4,
+                                    double* __restrict__ rec) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nrows * ns * 4;
+  if (q >= total) return;
+  const int f = (int)(q & 3);
+  const long long ring = q >> 2;
+  const int r = (int)(ring % nrows), j = (int)(ring / nrows);
+  const int nr1 = nrows + 1;
+  // corner (row, col) of filament start / end
+  const int cr[5] = {r, r + 1, r + 1, r, r};
+  const int cc[5] = {j, j, j + 1, j + 1, j};
+  const double* a = nodes + 3 * ((size_t)cr[f] + (size_t)nr1 * cc[f]);
+  const double* b = nodes + 3 * ((size_t)cr[f + 1] + (size_t)nr1 * cc[f + 1]);
+  write_rec(rec + q * kSrcDoubles, a[0], a[1], a[2], b[0], b[1], b[2], rvc4[q],
+            strength(gam[(size_t)r + (size_t)nrows * j], true));
+}
+
+// Horseshoe correction: -vf2 of the last near row (classdef.f90:1460-1463), one per column.
+__global__ void pack_horseshoe_kernel(int nrows, int ns, const double* __restrict__ nodes,
+                                      const double* __restrict__ gam, const double* __restrict__ rvc4,
+                                      double* __restrict__ rec) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns) return;
+  const int nr1 = nrows + 1;
+  const size_t ring = (size_t)(nrows - 1) + (size_t)nrows * j;
+  const double* a = nodes + 3 * ((size_t)nrows + (size_t)nr1 * j);
+  const double* b = nodes + 3 * ((size_t)nrows + (size_t)nr1 * (j + 1));
+  write_rec(rec + (size_t)j * kSrcDoubles, a[0], a[1], a[2], b[0], b[1], b[2], rvc4[4 * ring + 1],
+            strength(-gam[ring], false));
+}
+
+// Far-wake chain: filament i has fc(:,1) = p(:, i+1) (downstream / TE end) and fc(:,2) = p(:, i)
+// (classdef.f90:198-211: endpoint 1 is the trailing end, 2 the leading end).
+__global__ void pack_chain_kernel(int nfar, const double* __restrict__ p, const double* __restrict__ gamF,
+                                  const double* __restrict__ rvcF, double* __restrict__ rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfar) return;
+  const double* a = p + 3 * (size_t)(i + 1);
+  const double* b = p + 3 * (size_t)i;
+  write_rec(rec + (size_t)i * kSrcDoubles, a[0], a[1], a[2], b[0], b[1], b[2], rvcF[i], strength(gamF[i], true));
+}
+
+}  // namespace vlc

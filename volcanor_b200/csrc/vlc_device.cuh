@@ -1,0 +1,120 @@
+// vlc_device.cuh -- device-side building blocks of the Biot-Savart hot path (sm_100a, FP64).
+//
+// The pair interaction restates vf_vind (reference src/classdef.f90:476-503) in a form
+// that keeps the FP64 pipe busy:
+//   reference : v = (c * inv4pi * r0.(r1/|r1| - r2/|r2|)) / sqrt((rVc |r0|)^4 + |c|^4),  c = r1 x r2,
+//               0 when |c|^2 <= eps^2
+//   here      : v = c * [ G * ( (r0.r1) * w1 - (r0.r2) * w2 ) ],
+//               w_k = rsqrt(|r_k|^2 * (K + |c|^4)),  K = (rVc^2 |r0|^2)^2,  G = gam/(4 pi)
+// r0, |r0|^2, K and G are per-SOURCE quantities computed once by the pack kernels, so a pair
+// costs 2 reciprocal square roots instead of 3 square roots + 9 divides.  r1 = P - p1 and
+// r2 = P - p2 are formed exactly as the reference does, so a target that coincides bitwise
+// with a filament end point still gives c == 0 exactly and is skipped by the same guard
+// (this is how wake nodes skip the filaments they belong to).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vlc {
+
+// libMath.f90:11 eps = epsilon(1._dp); classdef.f90:498 guard is c2 > eps*eps = 2^-104.
+__device__ __constant__ const double kEps = 2.220446049250313e-16;
+#define VLC_EPS2 4.930380657631324e-32 /* 2^-104 exactly */
+
+// A packed source filament: 12 doubles = 96 B = 6 x 16 B (LDS.128 broadcast friendly).
+//   [0..2] p1   [3..5] p2   [6..8] r0 = p2 - p1   [9] L2 = |r0|^2   [10] K = (rVc^2 L2)^2   [11] G = gam/4pi
+constexpr int kSrcDoubles = 12;
+constexpr int kSrcBytes = kSrcDoubles * 8;
+
+// MUFU.RSQ64H seed (rel. err ~2^-21) + one third-order Newton step: same sequence CUDA's own
+// rsqrt() uses on its fast path, minus the special-case branch (inputs here are finite > 0
+// whenever the result is used; the c2 guard selects 0 otherwise).
+__device__ __forceinline__ double rsqrt_fp64(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double t = y * y;
+  double e = fma(-x, t, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double q = e * y;
+  return fma(p, q, y);
+}
+
+struct Src {
+  double p1x, p1y, p1z, p2x, p2y, p2z, r0x, r0y, r0z, L2, K, G;
+};
+
+__device__ __forceinline__ Src load_src(const double* __restrict__ s) {
+  // 6 x 16-byte shared loads; every lane reads the same address -> broadcast.
+  const double2* s2 = reinterpret_cast<const double2*>(s);
+  double2 a = s2[0], b = s2[1], c = s2[2], d = s2[3], e = s2[4], f = s2[5];
+  Src r;
+  r.p1x = a.x; r.p1y = a.y; r.p1z = b.x; r.p2x = b.y; r.p2y = c.x; r.p2z = c.y;
+  r.r0x = d.x; r.r0y = d.y; r.r0z = e.x; r.L2 = e.y; r.K = f.x; r.G = f.y;
+  return r;
+}
+
+// One pair interaction, accumulated into (vx,vy,vz).  ~44 FP64-pipe instructions.
+__device__ __forceinline__ void pair_accumulate(const Src& s, double px, double py, double pz,
+                                                double& vx, double& vy, double& vz) {
+  const double r1x = px - s.p1x, r1y = py - s.p1y, r1z = pz - s.p1z;
+  const double r2x = px - s.p2x, r2y = py - s.p2y, r2z = pz - s.p2z;
+  const double cx = fma(r1y, r2z, -(r1z * r2y));
+  const double cy = fma(r1z, r2x, -(r1x * r2z));
+  const double cz = fma(r1x, r2y, -(r1y * r2x));
+  const double c2 = fma(cz, cz, fma(cy, cy, cx * cx));
+  const double d1 = fma(r1z, r1z, fma(r1y, r1y, r1x * r1x));
+  const double d2 = fma(r2z, r2z, fma(r2y, r2y, r2x * r2x));
+  const double a1 = fma(s.r0z, r1z, fma(s.r0y, r1y, s.r0x * r1x));
+  const double a2 = a1 - s.L2;  // r0.r2 = r0.r1 - |r0|^2
+  const double den = fma(c2, c2, s.K);
+  const double w1 = rsqrt_fp64(d1 * den);
+  const double w2 = rsqrt_fp64(d2 * den);
+  double sc = (a1 * w1 - a2 * w2) * s.G;
+  // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`; integer compare keeps it off the FP64 pipe.
+  // c2 >= 0 always; threshold 2^-104 has a zero low word.
+  const int hi = __double2hiint(c2);
+  const int lo = __double2loint(c2);
+  const bool on = (hi > 0x39700000) || (hi == 0x39700000 && lo != 0);
+  sc = on ? sc : 0.0;
+  vx = fma(cx, sc, vx);
+  vy = fma(cy, sc, vy);
+  vz = fma(cz, sc, vz);
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace vlc

@@ -1,0 +1,120 @@
+// wake_state.cuh -- O(N) state-update kernels of the wake (K6-K8 of SURVEY 2.1) and small helpers.
+// HBM-bound elementwise maps; each cites the reference statement it restates.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace vlc {
+
+// vr_shiftdP / Fwake_shiftdP with dshift = vel*dt (classdef.f90:1531, :1538, :1545; :611-616, :946)
+__global__ void convect_kernel(long long n, double* __restrict__ x, const double* __restrict__ v, double dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = __dadd_rn(x[i], __dmul_rn(v[i], dt));  // no FMA contraction: bit-parity with the reference arithmetic
+}
+
+// main.f90:1032-1034  velNwake = 0.5*(3*velNwake - velNwake1)   (Adams-Bashforth predictor velocity)
+__global__ void ab2_kernel(long long n, const double* __restrict__ v, const double* __restrict__ v1,
+                           double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __dmul_rn(0.5, __dadd_rn(__dmul_rn(3.0, v[i]), -v1[i]));
+}
+
+// main.f90:1094-1096  velNwake = (velNwakePredicted + velNwakeStep)*0.5   (Adams-Moulton corrector)
+__global__ void am2_kernel(long long n, const double* __restrict__ vp, const double* __restrict__ vs,
+                           double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (vp[i] + vs[i]) * 0.5;
+}
+
+// classdef.f90:4368-4370 / :4398-4401  rVc = sqrt(rVc**2 + 4*oseenParameter*apparentViscCoeff*nu*dt)
+__device__ __forceinline__ double grow(double rvc, double a, double nu, double dt) {
+  return sqrt(__dadd_rn(__dmul_rn(rvc, rvc), 4.0 * 1.2564 * a * nu * dt));
+}
+
+__global__ void core_growth_kernel(long long n, double* __restrict__ rvc, double a, double nu, double dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rvc[i] = grow(rvc[i], a, nu, dt);
+}
+
+// classdef.f90:662-668, :975-980  gam = gam*exp(-decayCoeff*dt)
+__global__ void decay_kernel(long long n, double* __restrict__ gam, double decayCoeff, double dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gam[i] = gam[i] * exp(-decayCoeff * dt);
+}
+
+// classdef.f90:4364-4384 on rvc4 (4, nrows, ns): vf1 grows, vf3 <- vf1 (quirk C2), gam decays, vf2 grows.
+__global__ void dissipate_lattice_kernel(int nrows, int ns, double* __restrict__ rvc4, double* __restrict__ gam,
+                                         double a, double nu, double decayCoeff, double dt) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)nrows * ns) return;
+  double* r = rvc4 + 4 * q;
+  const double r1 = grow(r[0], a, nu, dt);
+  r[0] = r1;
+  r[2] = r1;
+  gam[q] = gam[q] * exp(-decayCoeff * dt);
+  r[1] = grow(r[1], a, nu, dt);
+}
+
+// classdef.f90:4386-4392  vf4(i) <- vf2(i-1) for i > first row (second pass: needs the updated vf2).
+__global__ void dissipate_lattice_vf4_kernel(int nrows, int ns, double* __restrict__ rvc4) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)nrows * ns) return;
+  const int r = (int)(q % nrows);
+  if (r > 0) rvc4[4 * q + 3] = rvc4[4 * (q - 1) + 1];
+}
+
+// classdef.f90:4414-4421 + :505-521  lc = |fc1 - fc2|; rVc = rVc0*sqrt(l0/lc)
+__global__ void strain_kernel(long long n, const double* __restrict__ p1, const double* __restrict__ p2,
+                              const double* __restrict__ l0, const double* __restrict__ rvc0,
+                              double* __restrict__ rvc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double dx = p1[3 * i] - p2[3 * i], dy = p1[3 * i + 1] - p2[3 * i + 1], dz = p1[3 * i + 2] - p2[3 * i + 2];
+  const double lc = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+  rvc[i] = rvc0[i] * sqrt(l0[i] / lc);
+}
+
+// nodes(3, nrows+1, ns+1) rows 1..nrows <-> P(3, nrows, ns+1)  (targets of libCommon.f90:133-145)
+__global__ void lattice_gather_kernel(int nrows, int ns, const double* __restrict__ nodes, double* __restrict__ P) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 3LL * nrows * (ns + 1)) return;
+  const int d = (int)(q % 3);
+  const long long t = q / 3;
+  const int r = (int)(t % nrows), c = (int)(t / nrows);
+  P[q] = nodes[3 * ((size_t)(r + 1) + (size_t)(nrows + 1) * c) + d];
+}
+__global__ void lattice_scatter_kernel(int nrows, int ns, double* __restrict__ nodes, const double* __restrict__ P) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 3LL * nrows * (ns + 1)) return;
+  const int d = (int)(q % 3);
+  const long long t = q / 3;
+  const int r = (int)(t % nrows), c = (int)(t / nrows);
+  nodes[3 * ((size_t)(r + 1) + (size_t)(nrows + 1) * c) + d] = P[q];
+}
+
+__global__ void identity_kernel(int N, double* __restrict__ A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * N) return;
+  A[i] = ((i % N) == (i / N)) ? 1.0 : 0.0;
+}
+
+// FP64 roofline denominator: kPeakChains independent register-resident DFMA chains per thread.
+constexpr int kPeakChains = 8;
+constexpr int kPeakUnroll = 16;
+__global__ void dfma_peak_kernel(int iters, double* __restrict__ out) {
+  double a[kPeakChains];
+  const double b = 1.0000001, c = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k) a[k] = 1.0 + k * 1e-3 + threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < kPeakUnroll; ++u)
+#pragma unroll
+      for (int k = 0; k < kPeakChains; ++k) a[k] = fma(a[k], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k) s += a[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace vlc
