@@ -29,7 +29,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FLOPS_PER_PAIR = 76        # algorithmic flops of vf_vind as written + gam scale/accumulate
-PIPE_INSTR_PER_PAIR = 44   # FP64-pipe instructions per pair in bs_sweep_kernel (SASS count)
+PIPE_INSTR_PER_PAIR = {0: 43, 1: 41}   # FP64-pipe instructions per pair in bs_sweep_kernel (SASS count; full / fast)
 
 
 def parse():
@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--T", type=int, default=0, help="targets per thread (0 = auto)")
     ap.add_argument("--nsplit", type=int, default=0, help="source splits (0 = auto)")
+    ap.add_argument("--precision", type=int, default=0, choices=[0, 1],
+                    help="0 = full (third-order rsqrt), 1 = fast (second order, pair error <= ~4e-14)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -206,6 +208,7 @@ def main():
     lats, n_src, m, name = workload(args)
     ctx = vb.Context(local)
     ctx.set_tuning(args.T, args.nsplit)
+    ctx.set_precision(args.precision)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -353,11 +356,11 @@ def main():
                 "traffic": None,
                 "kernel": "bs_sweep_kernel", "kernel_ms": kern_ms_max, "pairs_per_launch": pairs_launch,
                 "flops_per_pair": FLOPS_PER_PAIR,
-                "pipe_frac": pairs_launch * PIPE_INSTR_PER_PAIR * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
+                "pipe_frac": pairs_launch * PIPE_INSTR_PER_PAIR[args.precision] * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
                 "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); "
                                "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
                 "note": "compute-bound pairwise N-body on the FP64 pipe (no tensor cores by construction); "
-                        "frac = algorithmic 76 flop/pair, pipe_frac = issued 44 FP64 instr/pair"}
+                        "frac = algorithmic 76 flop/pair, pipe_frac = issued FP64 instr/pair (43 full, 41 fast)"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         p1, p2, rvc, gam, flag = synth.flatten_all(lats)
@@ -372,7 +375,9 @@ def main():
                       "step": "pack lattices -> sweep (targets slice x all filaments) -> convect -> all-gather -> scatter",
                       "l2": "flushed every step by a 256 MiB memset inside the timed region",
                       "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather/stage",
-                      "tuning": {"T": args.T, "nsplit": args.nsplit}},
+                      "tuning": {"T": args.T, "nsplit": args.nsplit},
+                      "precision": ["full: third-order rsqrt refinement, pair error ~1e-16",
+                                    "fast: second-order rsqrt refinement, pair error <= ~4e-14"][args.precision]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
            "stages_per_s": args.steps / (elapsed_ms * 1e-3),
            "fp64_peak_measured_tflops": peak}

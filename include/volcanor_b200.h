@@ -54,13 +54,21 @@ int vlc_create(int device, vlc_ctx** out);
 int vlc_destroy(vlc_ctx* ctx);
 const char* vlc_last_error(const vlc_ctx* ctx); /* ctx may be NULL: error of the last failed vlc_create */
 const char* vlc_version(void);
-int vlc_set_stream(vlc_ctx* ctx, void* cuda_stream); /* NULL -> the context's own stream */
+/* Run on the caller's cudaStream_t (cuda_stream == NULL is the legacy default stream, which is what
+ * torch.cuda.current_stream().cuda_stream returns for the default stream); use_own != 0 switches back to
+ * the context's own non-blocking stream (the default after vlc_create). */
+int vlc_set_stream(vlc_ctx* ctx, void* cuda_stream, int use_own);
 int vlc_sync(vlc_ctx* ctx);
 /* sm_count, compute capability major/minor, bytes of device memory */
 int vlc_device_info(vlc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes);
 /* Launch shape of the sweep kernel: targets_per_thread in {1,2,3,4} (0 = auto),
  * nsplit = source splits (0 = auto).  Only affects speed and summation order, never the pair formula. */
 int vlc_set_tuning(vlc_ctx* ctx, int targets_per_thread, int nsplit);
+/* Arithmetic of the two reciprocal square roots per pair (everything else is identical):
+ *   0 = full: MUFU.RSQ64H seed + third-order Newton step, pair error ~1e-16 (default);
+ *   1 = fast: second-order step, relative error of a pair <= ~4e-14 (2 FP64 instructions fewer per pair),
+ *       inside the 1e-12 per-call tolerance with > 20x margin (DESIGN.md "Precision modes"). */
+int vlc_set_precision(vlc_ctx* ctx, int mode);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 int64_t vlc_launch_count(const vlc_ctx* ctx);
 
@@ -183,6 +191,9 @@ int vlc_lattice_scatter_dev(vlc_ctx* ctx, int nrows, int ns, double* d_nodes, co
  * and the elapsed milliseconds; used by bench.py as the measured FP64 roofline denominator
  * (MEASURED_PEAKS.json has no FP64 entry). */
 int vlc_measure_fp64_peak(vlc_ctx* ctx, int iters, double* flops_per_s, double* ms);
+/* Evaluate the raw MUFU.RSQ64H seed and the full / fast refined reciprocal square roots of x[0..n)
+ * (host arrays) -- lets the tests measure the error bounds the precision modes rely on. */
+int vlc_probe_rsqrt(vlc_ctx* ctx, int64_t n, const double* x, double* seed, double* full, double* fast);
 
 #ifdef __cplusplus
 }

@@ -28,4 +28,4 @@ def lattice_to_rotor(lat, rotor, ib, predicted=False):
 
 def scaled_err(V, Vref, Vabs):
     """max |V - Vref| / max(sum |terms|): the per-call parity measure."""
-    return float(np.max(np.abs(V - Vref)) / np.max(Vabs))
+    return float(np.max(np.abs(V - Vref)) / max(np.max(Vabs), 1e-300))

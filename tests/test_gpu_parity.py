@@ -241,3 +241,38 @@ def test_singular_aic_reports_like_reference(ctx):
     ctx.rotor_put_wing(2, 0, np.zeros((2, 1, 104)))
     with pytest.raises(vb.VlcError, match="singular"):
         ctx.rotor_calcAIC(2, 2)
+
+
+# ------------------------------------------------------------------ precision modes
+
+def test_rsqrt_seed_accuracy(ctx):
+    """The FAST mode relies on the MUFU.RSQ64H seed error d <= 2^-22 (vlc_device.cuh kSeedRelErr):
+    second-order Newton leaves a relative error <= 1.5 d^2 ~ 8.5e-14 before centring, <= 4.3e-14 after."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-60), np.log(1e60), size=1 << 20)),
+                        1.0 + rng.uniform(0, 3, size=1 << 20)])
+    seed, full, fast = ctx.probe_rsqrt(x)
+    ref = 1.0 / np.sqrt(x.astype(np.longdouble))
+    d = np.max(np.abs(seed / ref - 1.0))
+    efull = np.max(np.abs(full / ref - 1.0))
+    efast = np.max(np.abs(fast / ref - 1.0))
+    print(f"seed rel err {float(d):.3e} (2^{np.log2(float(d)):.2f}), full {float(efull):.3e}, fast {float(efast):.3e}")
+    assert d <= 2.0 ** -22
+    assert efull < 4e-16
+    assert efast <= 1.5 * 2.0 ** -44 * 1.01 + 3e-16
+    assert np.all(fast <= ref * (1 + 3e-16))     # the second-order result is never high
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 1e-12), (1, 1e-12)])
+def test_precision_modes_hold_tolerance(ctx, oracle, mode, tol):
+    lats = synth.multirotor(20000, seed=7)
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    P = synth.targets_all(lats)
+    ctx.set_precision(mode)
+    try:
+        V, Vo, Vl, Vabs = _check_flat(ctx, oracle, p1, p2, rvc, gam, flag, P, tol)
+        e = scaled_err(V, Vl, Vabs)
+        print(f"mode {mode}: scaled error vs long double {e:.3e}")
+        assert e < (2e-13 if mode == 1 else 2e-14)
+    finally:
+        ctx.set_precision(0)

@@ -82,10 +82,11 @@ def load_library() -> C.CDLL:
         "vlc_destroy": (i32, [_vp]),
         "vlc_last_error": (C.c_char_p, [_vp]),
         "vlc_version": (C.c_char_p, []),
-        "vlc_set_stream": (i32, [_vp, _vp]),
+        "vlc_set_stream": (i32, [_vp, _vp, i32]),
         "vlc_sync": (i32, [_vp]),
         "vlc_device_info": (i32, [_vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "vlc_set_tuning": (i32, [_vp, i32, i32]),
+        "vlc_set_precision": (i32, [_vp, i32]),
         "vlc_launch_count": (i64, [_vp]),
         "vlc_set_sources": (i32, [_vp, i32, i64, _vp, _vp, _vp, _vp, _vp]),
         "vlc_set_sources_dev": (i32, [_vp, i32, i64, _vp, _vp, _vp, _vp, _vp]),
@@ -120,6 +121,7 @@ def load_library() -> C.CDLL:
         "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
+        "vlc_probe_rsqrt": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -178,14 +180,19 @@ class Context:
         except Exception:
             pass
 
-    def set_stream(self, stream_ptr: int | None):
-        self._ck(self.lib.vlc_set_stream(self.h, stream_ptr))
+    def set_stream(self, stream_ptr: int | None, use_own: bool = False):
+        """stream_ptr = torch.cuda.current_stream().cuda_stream (0/None = legacy default stream)."""
+        self._ck(self.lib.vlc_set_stream(self.h, stream_ptr or None, int(use_own)))
 
     def sync(self):
         self._ck(self.lib.vlc_sync(self.h))
 
     def set_tuning(self, targets_per_thread: int = 0, nsplit: int = 0):
         self._ck(self.lib.vlc_set_tuning(self.h, targets_per_thread, nsplit))
+
+    def set_precision(self, mode: int):
+        """0 = full (third-order rsqrt refinement), 1 = fast (second order, pair error <= ~4e-14)."""
+        self._ck(self.lib.vlc_set_precision(self.h, mode))
 
     def device_info(self) -> dict:
         sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
@@ -200,6 +207,12 @@ class Context:
         f, ms = C.c_double(), C.c_double()
         self._ck(self.lib.vlc_measure_fp64_peak(self.h, iters, C.byref(f), C.byref(ms)))
         return f.value, ms.value
+
+    def probe_rsqrt(self, x):
+        x = _f64(x).ravel()
+        seed, full, fast = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        self._ck(self.lib.vlc_probe_rsqrt(self.h, x.size, _ptr(x), _ptr(seed), _ptr(full), _ptr(fast)))
+        return seed, full, fast
 
     # -- tier 1 -----------------------------------------------------------------------------
     def set_sources(self, set_: int, p1, p2, rvc, gam, wake_flag=None):

@@ -14,7 +14,7 @@
 
 namespace vlc {
 
-template <int T, int THREADS, int TILE, int STAGES, int MINB>
+template <int T, int THREADS, int TILE, int STAGES, int MINB, bool FAST>
 __global__ void __launch_bounds__(THREADS, MINB)
 bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a multiple of TILE
                 long long chunk,                  // sources per split (multiple of TILE)
@@ -73,7 +73,7 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
     for (int j = 0; j < TILE; ++j) {
       const Src s = load_src(sb + j * kSrcDoubles);
 #pragma unroll
-      for (int k = 0; k < T; ++k) pair_accumulate(s, px[k], py[k], pz[k], vx[k], vy[k], vz[k]);
+      for (int k = 0; k < T; ++k) pair_accumulate<FAST>(s, px[k], py[k], pz[k], vx[k], vy[k], vz[k]);
     }
     __syncthreads();  // every warp is done with this stage before it is refilled
     if (tid == 0 && tile + STAGES < ntiles) {
@@ -83,14 +83,17 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
     }
   }
 
+  // FAST mode: the second-order Newton step leaves every rsqrt low by a factor in [1 - 1.5 d^2, 1]
+  // (d = seed error <= kSeedRelErr); centre that bias once per target.
+  constexpr double kCentre = FAST ? (1.0 + 0.75 * kSeedRelErr * kSeedRelErr) : 1.0;
   double* o = out + (size_t)blockIdx.y * 3 * (size_t)m;
 #pragma unroll
   for (int k = 0; k < T; ++k) {
     const long long t = t0 + (long long)k * THREADS;
     if (t < m) {
-      o[3 * t + 0] = vx[k];
-      o[3 * t + 1] = vy[k];
-      o[3 * t + 2] = vz[k];
+      o[3 * t + 0] = FAST ? vx[k] * kCentre : vx[k];
+      o[3 * t + 1] = FAST ? vy[k] * kCentre : vy[k];
+      o[3 * t + 2] = FAST ? vz[k] * kCentre : vz[k];
     }
   }
 }

@@ -69,6 +69,7 @@ struct vlc_ctx {
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   long long mem_bytes = 0;
   int tune_T = 0, tune_nsplit = 0;
+  bool fast = false;  // rsqrt refinement: false = third order (~1e-16), true = second order (~4e-14)
   long long launches = 0;
   SourceSet sets[VLC_MAX_SETS];
   DevBuf part;     // source-split partials
@@ -130,15 +131,10 @@ inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) /
 
 constexpr size_t kSweepSmem = (size_t)kStages * kTile * vlc::kSrcBytes + kStages * sizeof(uint64_t);
 
-template <int T, int MINB>
+template <int T, int MINB, bool FAST>
 int launch_sweep_T(vlc_ctx* c, const double* src, long long n_pad, long long chunk, int nsplit, long long m,
                    const double* dP, double* out) {
-  auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB>;
-  static bool attr_set[64] = {false};
-  if (c->device < 64 && !attr_set[c->device]) {
-    CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
-    attr_set[c->device] = true;
-  }
+  auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB, FAST>;
   dim3 grid(blocks_for(m, kThreads * T), (unsigned)nsplit, 1);
   kern<<<grid, kThreads, kSweepSmem, c->stream>>>(src, chunk, n_pad, dP, m, out);
   CUDA_OK(c, cudaGetLastError());
@@ -148,7 +144,7 @@ int launch_sweep_T(vlc_ctx* c, const double* src, long long n_pad, long long chu
 
 template <int T, int MINB>
 int query_occ(vlc_ctx* c, int* out) {
-  auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB>;
+  auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB, false>;
   CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
   CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, kThreads, kSweepSmem));
   return VLC_OK;
@@ -217,12 +213,16 @@ int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const dou
     out = c->part.p;
   }
   int rc;
+#define VLC_SWEEP(TT, MB)                                                                        \
+  rc = c->fast ? launch_sweep_T<TT, MB, true>(c, src, n_pad, chunk, nsplit, m, dP, out)          \
+               : launch_sweep_T<TT, MB, false>(c, src, n_pad, chunk, nsplit, m, dP, out)
   switch (T) {
-    case 1: rc = launch_sweep_T<1, 5>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
-    case 2: rc = launch_sweep_T<2, 4>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
-    case 3: rc = launch_sweep_T<3, 4>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
-    default: rc = launch_sweep_T<4, 3>(c, src, n_pad, chunk, nsplit, m, dP, out); break;
+    case 1: VLC_SWEEP(1, 5); break;
+    case 2: VLC_SWEEP(2, 4); break;
+    case 3: VLC_SWEEP(3, 3); break;
+    default: VLC_SWEEP(4, 3); break;
   }
+#undef VLC_SWEEP
   if (rc) return rc;
   if (nsplit > 1) {
     const long long len = 3 * m;
@@ -427,7 +427,7 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
   int rc = 0;
   rc |= query_occ<1, 5>(c, &c->occ[1]);
   rc |= query_occ<2, 4>(c, &c->occ[2]);
-  rc |= query_occ<3, 4>(c, &c->occ[3]);
+  rc |= query_occ<3, 3>(c, &c->occ[3]);
   rc |= query_occ<4, 3>(c, &c->occ[4]);
   if (rc) {
     g_create_error = "sweep kernel not loadable on this device: " + c->err;
@@ -471,9 +471,9 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
 
 extern "C" const char* vlc_last_error(const vlc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
-extern "C" int vlc_set_stream(vlc_ctx* c, void* s) {
+extern "C" int vlc_set_stream(vlc_ctx* c, void* s, int use_own) {
   CHECK_CTX(c);
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->stream = use_own ? c->own_stream : (cudaStream_t)s;  // s == NULL is the legacy default stream
   if (c->solver) cusolverDnSetStream(c->solver, c->stream);
   return VLC_OK;
 }
@@ -500,6 +500,13 @@ extern "C" int vlc_set_tuning(vlc_ctx* c, int T, int nsplit) {
   if (T < 0 || T > 4 || nsplit < 0) return fail(c, VLC_ERR_ARG, "targets_per_thread in 0..4, nsplit >= 0");
   c->tune_T = T;
   c->tune_nsplit = nsplit;
+  return VLC_OK;
+}
+
+extern "C" int vlc_set_precision(vlc_ctx* c, int mode) {
+  CHECK_CTX(c);
+  if (mode != 0 && mode != 1) return fail(c, VLC_ERR_ARG, "precision mode must be 0 (full) or 1 (fast)");
+  c->fast = (mode == 1);
   return VLC_OK;
 }
 
@@ -1057,5 +1064,21 @@ extern "C" int vlc_measure_fp64_peak(vlc_ctx* c, int iters, double* flops_per_s,
   const double flops = (double)blocks * threads * (double)iters * vlc::kPeakChains * vlc::kPeakUnroll * 2.0;
   if (flops_per_s) *flops_per_s = flops / (ms * 1e-3);
   if (ms_out) *ms_out = ms;
+  return VLC_OK;
+}
+
+extern "C" int vlc_probe_rsqrt(vlc_ctx* c, int64_t n, const double* x, double* seed, double* full, double* fast) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (n <= 0 || !x || !seed || !full || !fast) return fail(c, VLC_ERR_ARG, "bad arguments");
+  if ((rc = reserve(c, c->scratch, 4 * (size_t)n))) return rc;
+  double* d = c->scratch.p;
+  CUDA_OK(c, cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH1D(c, vlc::rsqrt_probe_kernel, n, n, d, d + n, d + 2 * n, d + 3 * n);
+  CUDA_OK(c, cudaMemcpyAsync(seed, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(full, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(fast, d + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }

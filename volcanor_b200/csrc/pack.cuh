@@ -26,8 +26,8 @@ __device__ __forceinline__ void write_rec(double* __restrict__ rec, double p1x, 
   o[0] = make_double2(p1x, p1y);
   o[1] = make_double2(p1z, p2x);
   o[2] = make_double2(p2y, p2z);
-  o[3] = make_double2(r0x, r0y);
-  o[4] = make_double2(r0z, L2);
+  o[3] = make_double2(G * r0x, G * r0y);
+  o[4] = make_double2(G * r0z, G * L2);
   o[5] = make_double2(q * q, G);
 }
 
@@ -117,12 +117,14 @@ __global__ void aic_assemble_kernel(const double* __restrict__ wiP, int N, doubl
     const double* vf = pc + kVf * f;
     Src s;
     s.p1x = vf[0]; s.p1y = vf[1]; s.p1z = vf[2]; s.p2x = vf[3]; s.p2y = vf[4]; s.p2z = vf[5];
-    s.r0x = s.p2x - s.p1x; s.r0y = s.p2y - s.p1y; s.r0z = s.p2z - s.p1z;
-    s.L2 = fma(s.r0z, s.r0z, fma(s.r0y, s.r0y, s.r0x * s.r0x));
-    const double q = vf[kVfRvc] * vf[kVfRvc] * s.L2;
+    const double r0x = s.p2x - s.p1x, r0y = s.p2y - s.p1y, r0z = s.p2z - s.p1z;
+    const double L2 = fma(r0z, r0z, fma(r0y, r0y, r0x * r0x));
+    const double q = vf[kVfRvc] * vf[kVfRvc] * L2;
     s.K = q * q;
-    s.G = VLC_INV4PI;
-    pair_accumulate(s, px, py, pz, vx, vy, vz);
+    s.r0gx = VLC_INV4PI * r0x; s.r0gy = VLC_INV4PI * r0y; s.r0gz = VLC_INV4PI * r0z;
+    s.L2g = VLC_INV4PI * L2;
+    s.spare = VLC_INV4PI;
+    pair_accumulate<false>(s, px, py, pz, vx, vy, vz);
   }
   A[(size_t)row + (size_t)N * col] = vx * pr[kWpNcap] + vy * pr[kWpNcap + 1] + vz * pr[kWpNcap + 2];
 }

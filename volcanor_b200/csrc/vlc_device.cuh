@@ -4,9 +4,9 @@
 // that keeps the FP64 pipe busy:
 //   reference : v = (c * inv4pi * r0.(r1/|r1| - r2/|r2|)) / sqrt((rVc |r0|)^4 + |c|^4),  c = r1 x r2,
 //               0 when |c|^2 <= eps^2
-//   here      : v = c * [ G * ( (r0.r1) * w1 - (r0.r2) * w2 ) ],
+//   here      : v = c * [ (G r0.r1) * w1 - (G r0.r2) * w2 ],
 //               w_k = rsqrt(|r_k|^2 * (K + |c|^4)),  K = (rVc^2 |r0|^2)^2,  G = gam/(4 pi)
-// r0, |r0|^2, K and G are per-SOURCE quantities computed once by the pack kernels, so a pair
+// G r0, G |r0|^2 and K are per-SOURCE quantities computed once by the pack kernels, so a pair
 // costs 2 reciprocal square roots instead of 3 square roots + 9 divides.  r1 = P - p1 and
 // r2 = P - p2 are formed exactly as the reference does, so a target that coincides bitwise
 // with a filament end point still gives c == 0 exactly and is skipped by the same guard
@@ -22,25 +22,34 @@ __device__ __constant__ const double kEps = 2.220446049250313e-16;
 #define VLC_EPS2 4.930380657631324e-32 /* 2^-104 exactly */
 
 // A packed source filament: 12 doubles = 96 B = 6 x 16 B (LDS.128 broadcast friendly).
-//   [0..2] p1   [3..5] p2   [6..8] r0 = p2 - p1   [9] L2 = |r0|^2   [10] K = (rVc^2 L2)^2   [11] G = gam/4pi
+//   [0..2] p1   [3..5] p2   [6..8] G*r0, r0 = p2 - p1   [9] G*|r0|^2   [10] K = (rVc^2 |r0|^2)^2   [11] G = gam/4pi
 constexpr int kSrcDoubles = 12;
 constexpr int kSrcBytes = kSrcDoubles * 8;
 
-// MUFU.RSQ64H seed (rel. err ~2^-21) + one third-order Newton step: same sequence CUDA's own
-// rsqrt() uses on its fast path, minus the special-case branch (inputs here are finite > 0
-// whenever the result is used; the c2 guard selects 0 otherwise).
+// Reciprocal square root on the FP64 pipe: MUFU.RSQ64H seed y0 (relative error d <= ~2^-22, measured by
+// tests/test_gpu_parity.py::test_rsqrt_seed_accuracy) refined by Newton.
+//   FULL (third order, the sequence CUDA's own rsqrt() uses on its fast path): 5 FP64 instr, error ~2.5 d^3
+//   FAST (second order): 4 FP64 instr, y1 = y0 (1 - 1.5 d^2 + ...): relative error <= 1.5 d^2 ~ 4e-14,
+//        always low; bs_sweep_kernel centres it with one multiply by (1 + 0.75 d_max^2) per target.
+// No special-case branch: inputs are finite > 0 whenever the result is used (the c2 guard predicates
+// the accumulation otherwise).
+constexpr double kSeedRelErr = 2.384185791015625e-07;  // 2^-22 (measured max is below, see profiles/)
+template <bool FAST>
 __device__ __forceinline__ double rsqrt_fp64(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double t = y * y;
-  double e = fma(-x, t, 1.0);
-  double p = fma(0.375, e, 0.5);
-  double q = e * y;
+  const double t = y * y;
+  const double e = fma(-x, t, 1.0);
+  const double q = e * y;
+  if (FAST) return fma(0.5, q, y);
+  const double p = fma(0.375, e, 0.5);
   return fma(p, q, y);
 }
 
 struct Src {
-  double p1x, p1y, p1z, p2x, p2y, p2z, r0x, r0y, r0z, L2, K, G;
+  // r0g = G*(p2 - p1), L2g = G*|p2 - p1|^2 with G = gam/(4 pi): the strength is folded into the two
+  // per-source quantities that enter the result linearly, which saves one FP64 multiply per pair.
+  double p1x, p1y, p1z, p2x, p2y, p2z, r0gx, r0gy, r0gz, L2g, K, spare;
 };
 
 __device__ __forceinline__ Src load_src(const double* __restrict__ s) {
@@ -49,11 +58,14 @@ __device__ __forceinline__ Src load_src(const double* __restrict__ s) {
   double2 a = s2[0], b = s2[1], c = s2[2], d = s2[3], e = s2[4], f = s2[5];
   Src r;
   r.p1x = a.x; r.p1y = a.y; r.p1z = b.x; r.p2x = b.y; r.p2y = c.x; r.p2z = c.y;
-  r.r0x = d.x; r.r0y = d.y; r.r0z = e.x; r.L2 = e.y; r.K = f.x; r.G = f.y;
+  r.r0gx = d.x; r.r0gy = d.y; r.r0gz = e.x; r.L2g = e.y; r.K = f.x; r.spare = f.y;
   return r;
 }
 
-// One pair interaction, accumulated into (vx,vy,vz).  ~44 FP64-pipe instructions.
+// One pair interaction, accumulated into (vx,vy,vz).  43 (FULL) / 41 (FAST) FP64-pipe instructions:
+// 6 sub, 6 cross, 3+3+3 squared norms, 3 dot, 1 a2, 1 den, 2 products, 2 rsqrt (5|4 each), 2 combine,
+// 3 accumulate.
+template <bool FAST>
 __device__ __forceinline__ void pair_accumulate(const Src& s, double px, double py, double pz,
                                                 double& vx, double& vy, double& vz) {
   const double r1x = px - s.p1x, r1y = py - s.p1y, r1z = pz - s.p1z;
@@ -64,18 +76,22 @@ __device__ __forceinline__ void pair_accumulate(const Src& s, double px, double 
   const double c2 = fma(cz, cz, fma(cy, cy, cx * cx));
   const double d1 = fma(r1z, r1z, fma(r1y, r1y, r1x * r1x));
   const double d2 = fma(r2z, r2z, fma(r2y, r2y, r2x * r2x));
-  const double a1 = fma(s.r0z, r1z, fma(s.r0y, r1y, s.r0x * r1x));
-  const double a2 = a1 - s.L2;  // r0.r2 = r0.r1 - |r0|^2
+  const double a1 = fma(s.r0gz, r1z, fma(s.r0gy, r1y, s.r0gx * r1x));  // G * r0.r1
+  const double a2 = a1 - s.L2g;                                         // G * r0.r2 = G*(r0.r1 - |r0|^2)
   const double den = fma(c2, c2, s.K);
-  const double w1 = rsqrt_fp64(d1 * den);
-  const double w2 = rsqrt_fp64(d2 * den);
-  double sc = (a1 * w1 - a2 * w2) * s.G;
-  // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`; integer compare keeps it off the FP64 pipe.
-  // c2 >= 0 always; threshold 2^-104 has a zero low word.
-  const int hi = __double2hiint(c2);
-  const int lo = __double2loint(c2);
-  const bool on = (hi > 0x39700000) || (hi == 0x39700000 && lo != 0);
-  sc = on ? sc : 0.0;
+  const double w1 = rsqrt_fp64<FAST>(d1 * den);
+  const double w2 = rsqrt_fp64<FAST>(d2 * den);
+  double sc = fma(a1, w1, -(a2 * w2));
+  // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`: c2 >= 0, so its bit pattern orders like an integer;
+  // eps^2 = 2^-104 = 0x3970000000000000.  One 64-bit integer compare + one select keep the guard off
+  // the FP64 pipe (each FP64 instruction costs two issue cycles, an integer one costs one).
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.gt.s64 p, %1, 0x3970000000000000;\n\t"
+      "selp.f64 %0, %0, 0d0000000000000000, p;\n\t"
+      "}"
+      : "+d"(sc)
+      : "l"(__double_as_longlong(c2)));
   vx = fma(cx, sc, vx);
   vy = fma(cy, sc, vy);
   vz = fma(cz, sc, vz);

@@ -118,3 +118,18 @@ __global__ void dfma_peak_kernel(int iters, double* __restrict__ out) {
 }
 
 }  // namespace vlc
+
+// ---- probe: raw MUFU.RSQ64H seed and both Newton refinements (tests measure the seed error bound) ----
+#include "vlc_device.cuh"
+namespace vlc {
+__global__ void rsqrt_probe_kernel(long long n, const double* __restrict__ x, double* __restrict__ seed,
+                                   double* __restrict__ full, double* __restrict__ fast) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x[i]));
+  seed[i] = y;
+  full[i] = rsqrt_fp64<false>(x[i]);
+  fast[i] = rsqrt_fp64<true>(x[i]);
+}
+}  // namespace vlc
