@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--T", type=int, default=0, help="targets per thread (0 = auto)")
     ap.add_argument("--nsplit", type=int, default=0, help="source splits (0 = auto)")
     ap.add_argument("--precision", type=int, default=0, choices=[0, 1],
-                    help="0 = full (third-order rsqrt), 1 = fast (second order, pair error <= ~4e-14)")
+                    help="0 = full (third-order rsqrt, default), 1 = fast (second order, pair error <= 6.4e-13)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -377,7 +377,7 @@ def main():
                       "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather/stage",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
                       "precision": ["full: third-order rsqrt refinement, pair error ~1e-16",
-                                    "fast: second-order rsqrt refinement, pair error <= ~4e-14"][args.precision]},
+                                    "fast: second-order rsqrt refinement, pair error <= 6.4e-13"][args.precision]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
            "stages_per_s": args.steps / (elapsed_ms * 1e-3),
            "fp64_peak_measured_tflops": peak}

@@ -66,8 +66,9 @@ int vlc_device_info(vlc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, i
 int vlc_set_tuning(vlc_ctx* ctx, int targets_per_thread, int nsplit);
 /* Arithmetic of the two reciprocal square roots per pair (everything else is identical):
  *   0 = full: MUFU.RSQ64H seed + third-order Newton step, pair error ~1e-16 (default);
- *   1 = fast: second-order step, relative error of a pair <= ~4e-14 (2 FP64 instructions fewer per pair),
- *       inside the 1e-12 per-call tolerance with > 20x margin (DESIGN.md "Precision modes"). */
+ *   1 = fast: second-order step, relative error of a pair <= 6.4e-13 (2 FP64 instructions fewer per pair,
+ *       ~6 % faster): inside the 1e-12 per-call tolerance but with little margin -> opt-in only
+ *       (DESIGN.md "Precision modes"). */
 int vlc_set_precision(vlc_ctx* ctx, int mode);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 int64_t vlc_launch_count(const vlc_ctx* ctx);

@@ -246,8 +246,8 @@ def test_singular_aic_reports_like_reference(ctx):
 # ------------------------------------------------------------------ precision modes
 
 def test_rsqrt_seed_accuracy(ctx):
-    """The FAST mode relies on the MUFU.RSQ64H seed error d <= 2^-22 (vlc_device.cuh kSeedRelErr):
-    second-order Newton leaves a relative error <= 1.5 d^2 ~ 8.5e-14 before centring, <= 4.3e-14 after."""
+    """Seed error bound used by vlc_device.cuh (kSeedRelErr = 2^-20): FULL mode ends at rounding level,
+    FAST mode (second-order Newton) at <= 1.5 d^2 = 1.4e-12 before centring."""
     rng = np.random.default_rng(0)
     x = np.concatenate([np.exp(rng.uniform(np.log(1e-60), np.log(1e60), size=1 << 20)),
                         1.0 + rng.uniform(0, 3, size=1 << 20)])
@@ -257,9 +257,9 @@ def test_rsqrt_seed_accuracy(ctx):
     efull = np.max(np.abs(full / ref - 1.0))
     efast = np.max(np.abs(fast / ref - 1.0))
     print(f"seed rel err {float(d):.3e} (2^{np.log2(float(d)):.2f}), full {float(efull):.3e}, fast {float(efast):.3e}")
-    assert d <= 2.0 ** -22
+    assert d <= 2.0 ** -20
     assert efull < 4e-16
-    assert efast <= 1.5 * 2.0 ** -44 * 1.01 + 3e-16
+    assert efast <= 1.5 * 2.0 ** -40 * 1.01 + 3e-16
     assert np.all(fast <= ref * (1 + 3e-16))     # the second-order result is never high
 
 
@@ -273,6 +273,6 @@ def test_precision_modes_hold_tolerance(ctx, oracle, mode, tol):
         V, Vo, Vl, Vabs = _check_flat(ctx, oracle, p1, p2, rvc, gam, flag, P, tol)
         e = scaled_err(V, Vl, Vabs)
         print(f"mode {mode}: scaled error vs long double {e:.3e}")
-        assert e < (2e-13 if mode == 1 else 2e-14)
+        assert e < (7e-13 if mode == 1 else 2e-14)
     finally:
         ctx.set_precision(0)

@@ -26,14 +26,18 @@ __device__ __constant__ const double kEps = 2.220446049250313e-16;
 constexpr int kSrcDoubles = 12;
 constexpr int kSrcBytes = kSrcDoubles * 8;
 
-// Reciprocal square root on the FP64 pipe: MUFU.RSQ64H seed y0 (relative error d <= ~2^-22, measured by
-// tests/test_gpu_parity.py::test_rsqrt_seed_accuracy) refined by Newton.
+// Reciprocal square root on the FP64 pipe: MUFU.RSQ64H seed y0 (only the high word of x is used: measured
+// relative error d <= 9.2e-7 = 2^-20.06 on B200, tests/test_gpu_parity.py::test_rsqrt_seed_accuracy)
+// refined by Newton.
 //   FULL (third order, the sequence CUDA's own rsqrt() uses on its fast path): 5 FP64 instr, error ~2.5 d^3
-//   FAST (second order): 4 FP64 instr, y1 = y0 (1 - 1.5 d^2 + ...): relative error <= 1.5 d^2 ~ 4e-14,
-//        always low; bs_sweep_kernel centres it with one multiply by (1 + 0.75 d_max^2) per target.
+//        ~ 2e-18 -> results limited by rounding (measured 1.1e-16).  DEFAULT.
+//   FAST (second order): 4 FP64 instr, y1 = y0 (1 - 1.5 d^2 + ...): relative error <= 1.5 d^2 = 1.3e-12,
+//        always low; bs_sweep_kernel centres it with one multiply by (1 + 0.75 d_max^2) per target, leaving
+//        <= 6.4e-13 per pair (1.5e-13 measured on a whole sweep).  Inside the 1e-12 tolerance but with
+//        little margin, hence opt-in only (vlc_set_precision).
 // No special-case branch: inputs are finite > 0 whenever the result is used (the c2 guard predicates
 // the accumulation otherwise).
-constexpr double kSeedRelErr = 2.384185791015625e-07;  // 2^-22 (measured max is below, see profiles/)
+constexpr double kSeedRelErr = 9.5367431640625e-07;  // 2^-20 >= measured max 9.18e-7
 template <bool FAST>
 __device__ __forceinline__ double rsqrt_fp64(double x) {
   double y;
