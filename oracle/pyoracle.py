@@ -80,6 +80,26 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_rotor_rollup": (None, [_vp]),
         "orc_vel_order2_Nwake": (None, [_vp, _vp, i32, i32, _vp]),
         "orc_vel_order2_Fwake": (None, [_vp, _vp, i32, _vp]),
+        "orc_rotor_dims": (None, [_vp, _vp]),
+        # case driver (vlc_case.c)
+        "orc_case_new": (_vp, [i32]),
+        "orc_case_free": (None, [_vp]),
+        "orc_case_set_config": (i32, [_vp, C.c_char_p, d]),
+        "orc_case_set_geom": (i32, [_vp, i32, C.c_char_p, i32, _vp]),
+        "orc_case_set_hooks": (None, [_vp, _vp]),
+        "orc_case_init": (i32, [_vp]),
+        "orc_case_init_rotors": (i32, [_vp]),
+        "orc_case_step": (i32, [_vp]),
+        "orc_case_iter": (i32, [_vp]),
+        "orc_case_config": (_vp, [_vp]),
+        "orc_case_rotor": (_vp, [_vp, i32]),
+        "orc_case_error": (C.c_char_p, [_vp]),
+        "orc_case_force_nondim": (None, [_vp, i32, _vp]),
+        "orc_case_pairs_last_step": (d, [_vp]),
+        "orc_rotor_dirLiftDrag": (None, [_vp]),
+        "orc_rotor_calc_secAlpha": (None, [_vp]),
+        "orc_rotor_calc_force": (None, [_vp, d, d]),
+        "orc_blade_sec": (_vp, [_vp, i32, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         if hasattr(lib, name):
@@ -152,10 +172,35 @@ class Rotor:
         self.nb, self.nc, self.ns, self.nNwake, self.nFwake = nb, nc, ns, nNwake, nFwake
         self.h = self.lib.orc_rotor_new(nb, nc, ns, nNwake, nFwake)
         self.N = nc * ns * nb
+        self.owner = True
+
+    @classmethod
+    def from_handle(cls, lib, h):
+        """Non-owning wrapper of a rotor that lives inside an orc_case_t."""
+        self = cls.__new__(cls)
+        self.lib, self.h, self.owner = lib, h, False
+        dims = (C.c_int * 10)()
+        lib.orc_rotor_dims(h, dims)
+        self.nb, self.nc, self.ns, self.nNwake, self.nFwake = dims[0:5]
+        self.N = self.nc * self.ns * self.nb
+        return self
+
+    def dims(self) -> dict:
+        d = (C.c_int * 10)()
+        self.lib.orc_rotor_dims(self.h, d)
+        return dict(zip(["nb", "nc", "ns", "nNwake", "nFwake", "rowNear", "rowFar", "nbConvect", "nNwakeEnd",
+                         "nFwakeEnd"], list(d)))
+
+    def sec(self, ib, name, width=1):
+        """Sectional array of blade ib by name (vlc_case.c orc_blade_sec): (ns,) or (ns, 3)."""
+        p = self.lib.orc_blade_sec(self.h, ib, name.encode())
+        if not p:
+            raise KeyError(name)
+        return self._view(p, (self.ns, 3) if width == 3 else (self.ns,))
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.owner:
                 self.lib.orc_rotor_free(self.h)
                 self.h = None
         except Exception:
@@ -232,3 +277,92 @@ class Rotor:
 
     def calcAIC(self):
         return self.lib.orc_rotor_calcAIC(self.h)
+
+
+class OrcConfig(C.Structure):
+    """orc_config_t (vlc_case.h)"""
+    _fields_ = [("nt", C.c_int), ("nr", C.c_int), ("dt", C.c_double), ("density", C.c_double),
+                ("velSound", C.c_double), ("kinematicVisc", C.c_double), ("ntSub", C.c_int), ("ntSubInit", C.c_int),
+                ("rotorForcePlot", C.c_int), ("wakeDissipation", C.c_int), ("wakeStrain", C.c_int),
+                ("wakeBurst", C.c_int), ("wakeSuppress", C.c_int), ("slowStart", C.c_int), ("slowStartNt", C.c_int),
+                ("fdScheme", C.c_int), ("initWakeVelNt", C.c_int)]
+
+
+class OrcHooks(C.Structure):
+    """orc_hooks_t (vlc_case.h): the five hot-path call sites of the driver."""
+    VIND_POINTS = C.CFUNCTYPE(C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_long, _vp, _vp)
+    VIND_ONN = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp)
+    VIND_ONF = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp)
+    CALC_AIC = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, _vp)
+    SOLVE = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, _vp)
+    _fields_ = [("user", _vp), ("vind_points", VIND_POINTS), ("vind_onNwake", VIND_ONN), ("vind_onFwake", VIND_ONF),
+                ("calcAIC", CALC_AIC), ("solve", SOLVE)]
+
+
+class Case:
+    """The oracle's restatement of `program main` (vlc_case.c).  `params` = {"config": {...}, "geom": [{...}, ...]}
+    with the namelist variable names of config.nml / geomXX.nml (tests/golden/*.json hold the reference's cases)."""
+
+    def __init__(self, params: dict, variant="strict"):
+        self.lib = load(variant)
+        geoms = params["geom"]
+        self.nr = len(geoms)
+        self.h = self.lib.orc_case_new(self.nr)
+        self.ignored = []
+        for k, v in params["config"].items():
+            if self.lib.orc_case_set_config(self.h, k.encode(), float(v)) != 0:
+                self.ignored.append(k)
+        for ir, g in enumerate(geoms):
+            for k, v in g.items():
+                if isinstance(v, str):
+                    self.ignored.append(k)
+                    continue
+                a = _f64(np.atleast_1d(v)).ravel()
+                if self.lib.orc_case_set_geom(self.h, ir, k.encode(), a.size, a.ctypes.data) != 0:
+                    self.ignored.append(k)
+        self._hooks = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.orc_case_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"oracle case driver failed ({rc}): {self.lib.orc_case_error(self.h).decode()}")
+
+    def set_hooks(self, hooks: "OrcHooks | None"):
+        self._hooks = hooks  # keep the callbacks alive
+        self.lib.orc_case_set_hooks(self.h, C.byref(hooks) if hooks is not None else None)
+
+    def init_rotors(self):
+        self._ck(self.lib.orc_case_init_rotors(self.h))
+
+    def init(self):
+        self._ck(self.lib.orc_case_init(self.h))
+
+    def step(self):
+        self._ck(self.lib.orc_case_step(self.h))
+
+    @property
+    def iter(self) -> int:
+        return self.lib.orc_case_iter(self.h)
+
+    @property
+    def config(self) -> OrcConfig:
+        return OrcConfig.from_address(self.lib.orc_case_config(self.h))
+
+    def rotor(self, ir) -> Rotor:
+        return Rotor.from_handle(self.lib, self.lib.orc_case_rotor(self.h, ir))
+
+    def force_nondim(self, ir=0) -> np.ndarray:
+        out = np.empty(9)
+        self.lib.orc_case_force_nondim(self.h, ir, out.ctypes.data)
+        return out
+
+    @property
+    def pairs_last_step(self) -> float:
+        return self.lib.orc_case_pairs_last_step(self.h)

@@ -1,0 +1,93 @@
+/*
+ * vlc_case.h -- CPU ORACLE, case driver (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the reference's program flow (src/main.f90) and of the subset of
+ * rotor_init / kinematics / loads (src/classdef.f90) that the reference's own golden results
+ * exercise, so that the oracle's wake sweeps, convection, core growth and roll-up are pinned
+ * END TO END by the reference's CT/CL histories
+ * (tests/katzNplotkin-AR04.case/referenceResults/r01ForceNonDim.csv.ref) and by the force KATs of
+ * tests/rotor1x2_test.f90 / wing1x2_test.f90 / wing1x3_test.f90.
+ *
+ * The five hot-path call sites of the driver go through a table of function pointers
+ * (orc_hooks_t).  The default table is the CPU oracle itself; the GPU parity tests install a
+ * table that forwards to the C ABI of include/volcanor_b200.h -- i.e. the same driver, with its
+ * OpenMP vind loops replaced by the library, which is exactly the substitution the Fortran shim
+ * performs.
+ *
+ * Scope: surfaceType 1 (lifting) rotors and wings, geometryFile '0' or a PLOT3D grid passed in
+ * memory, forceCalcSwitch 0, fdScheme 0/1/3, slowStart 0-3, wake dissipation / strain,
+ * axisymmetry, far-wake roll-up and truncation.  Not restated (unused by every shipped case):
+ * image surfaces, non-lifting STL bodies, camber files, C81 tables, blade/body dynamics, custom
+ * trajectories, wake burst, prescribed far wake generation, fdScheme 2/4/5.
+ */
+#ifndef VLC_CASE_H
+#define VLC_CASE_H
+
+#include "vlc_oracle.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* config.nml (libCommon.f90:51-108); missing keys are 0. */
+typedef struct {
+  int nt, nr;
+  double dt, density, velSound, kinematicVisc;
+  int ntSub, ntSubInit, rotorForcePlot, wakeDissipation, wakeStrain, wakeBurst, wakeSuppress;
+  int slowStart, slowStartNt, fdScheme, initWakeVelNt;
+} orc_config_t;
+
+/* Hot-path call sites of the driver.  Every function returns 0 on success. */
+typedef struct orc_hooks {
+  void *user;
+  /* rotor(jr)%vind_bywing (what 0) / %vind_bywake[,'P'] (1) / both (2) / %vind_bywing_boundVortices (3),
+   * batched over m points: replaces the per-point calls inside the OpenMP loops main.f90:124-167,
+   * :247-271, :528-573, :632-656. */
+  int (*vind_points)(void *user, int jr, int what, int predicted, long m, const double *P, double *V);
+  /* vind_onNwake_byRotor / vind_onFwake_byRotor (libCommon.f90:114-211) */
+  int (*vind_onNwake)(void *user, int jr, const double *Nwake, int rows, int cols, int ld, int predicted,
+                      double *out);
+  int (*vind_onFwake)(void *user, int jr, const double *Fwake, int rows, int predicted, double *out);
+  /* rotor%calcAIC() (classdef.f90:4151): fill AIC (N x N); AIC_inv may be left untouched if solve is set */
+  int (*calcAIC)(void *user, int ir, double *AIC, double *AIC_inv);
+  /* gamVec = matmulAX(AIC_inv, RHS) (main.f90:190, :596) */
+  int (*solve)(void *user, int ir, const double *RHS, double *gamVec);
+} orc_hooks_t;
+
+typedef struct orc_case orc_case_t;
+
+orc_case_t *orc_case_new(int nr);
+void orc_case_free(orc_case_t *c);
+/* key = namelist variable name of config.nml; returns 0 if the key is known */
+int orc_case_set_config(orc_case_t *c, const char *key, double value);
+/* key = namelist variable name of geomXX.nml (ir 0-based); vectors take n values.
+ * "grid" passes a PLOT3D grid (3, nc+1, ns+1) as read by rotor_plot3dtoblade (classdef.f90:3957). */
+int orc_case_set_geom(orc_case_t *c, int ir, const char *key, int n, const double *values);
+void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *hooks); /* NULL = CPU oracle */
+/* main.f90:1-382: init rotors, pitch, AIC, initial solution, initial forces.  Returns 0 / error code. */
+int orc_case_init(orc_case_t *c);
+/* one pass of the time loop main.f90:400-1452 (iter = 1..nt) */
+int orc_case_step(orc_case_t *c);
+int orc_case_iter(const orc_case_t *c);
+const orc_config_t *orc_case_config(const orc_case_t *c);
+orc_rotor_t *orc_case_rotor(orc_case_t *c, int ir);
+const char *orc_case_error(const orc_case_t *c);
+/* the columns force2file writes to rNNForceNonDim.csv (libPostprocess.f90:824-837):
+ * out[0..8] = CL/CT, CD/CQ, CLu, CDi, CD0, CDu, CFx, CFy, CFz */
+void orc_case_force_nondim(orc_case_t *c, int ir, double out[9]);
+/* pair interactions (vf_vind evaluations in the reference's enumeration) of the last step */
+double orc_case_pairs_last_step(const orc_case_t *c);
+
+/* pieces exposed for the KAT tests */
+int orc_case_init_rotors(orc_case_t *c); /* main.f90:31-58 only: rotor%init + initial pitch */
+void orc_blade_rot_pitch(orc_blade_t *b, double theta);
+double orc_rotor_gettheta(const orc_rotor_t *r, double psi, int ib);
+void orc_rotor_dirLiftDrag(orc_rotor_t *r);
+void orc_rotor_calc_secAlpha(orc_rotor_t *r);
+void orc_rotor_calc_force(orc_rotor_t *r, double density, double dt);
+double *orc_blade_sec(orc_rotor_t *r, int ib, const char *name); /* sectional arrays by name */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -879,7 +879,14 @@ orc_rotor_t *orc_rotor_new(int nb, int nc, int ns, int nNwake, int nFwake) {
     b->velFwake1 = (double *)calloc(vf, sizeof(double));
     b->velFwakePredicted = (double *)calloc(vf, sizeof(double));
     b->velFwakeStep = (double *)calloc(vf, sizeof(double));
+    /* sectional arrays of the case driver (vlc_case.c; classdef.f90:3091-3122) */
+    double **s1[] = {&b->secChord, &b->secArea, &b->secAlpha, &b->secCL, &b->secCLu, &b->secCD, &b->secMflapArm};
+    double **s3[] = {&b->secForceInertial, &b->secLift, &b->secDrag, &b->secLiftDir, &b->secDragDir, &b->secLiftUnsteady,
+                     &b->secTauCapChord, &b->secTauCapSpan, &b->secNormalVec, &b->secCP, &b->secChordwiseResVel};
+    for (size_t k = 0; k < sizeof(s1) / sizeof(s1[0]); ++k) *s1[k] = (double *)calloc((size_t)ns + 1, sizeof(double));
+    for (size_t k = 0; k < sizeof(s3) / sizeof(s3[0]); ++k) *s3[k] = (double *)calloc(3 * (size_t)ns + 3, sizeof(double));
   }
+  r->streamwiseCoreVec = (double *)calloc((size_t)ns + 2, sizeof(double));
   return r;
 }
 
@@ -900,7 +907,12 @@ void orc_rotor_free(orc_rotor_t *r) {
     free(b->velFwake1);
     free(b->velFwakePredicted);
     free(b->velFwakeStep);
+    double *s[] = {b->secChord, b->secArea, b->secAlpha, b->secCL, b->secCLu, b->secCD, b->secMflapArm,
+                   b->secForceInertial, b->secLift, b->secDrag, b->secLiftDir, b->secDragDir, b->secLiftUnsteady,
+                   b->secTauCapChord, b->secTauCapSpan, b->secNormalVec, b->secCP, b->secChordwiseResVel};
+    for (size_t k = 0; k < sizeof(s) / sizeof(s[0]); ++k) free(s[k]);
   }
+  free(r->streamwiseCoreVec);
   free(r->blade);
   free(r->AIC);
   free(r->AIC_inv);
@@ -930,6 +942,11 @@ double *orc_rotor_vel(orc_rotor_t *r, int ib, int which) {
 }
 double *orc_rotor_AIC(orc_rotor_t *r, int inverse) { return inverse ? r->AIC_inv : r->AIC; }
 double *orc_rotor_vec(orc_rotor_t *r, int which) { return which == 0 ? r->gamVec : (which == 1 ? r->RHS : r->gamVecPrev); }
+/* out[0..9] = nb nc ns nNwake nFwake rowNear rowFar nbConvect nNwakeEnd nFwakeEnd */
+void orc_rotor_dims(const orc_rotor_t *r, int *out) {
+  out[0] = r->nb; out[1] = r->nc; out[2] = r->ns; out[3] = r->nNwake; out[4] = r->nFwake;
+  out[5] = r->rowNear; out[6] = r->rowFar; out[7] = r->nbConvect; out[8] = r->nNwakeEnd; out[9] = r->nFwakeEnd;
+}
 void orc_rotor_set_rows(orc_rotor_t *r, int rowNear, int rowFar) {
   r->rowNear = rowNear;
   r->rowFar = rowFar;

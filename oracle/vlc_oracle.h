@@ -70,6 +70,17 @@ typedef struct {
   orc_fwake_t wapF[ORC_NPFWAKE], wapFPredicted[ORC_NPFWAKE];
   double *velNwake, *velNwake1, *velNwakePredicted, *velNwakeStep; /* (3,nNwake,ns+1) */
   double *velFwake, *velFwake1, *velFwakePredicted, *velFwakeStep; /* (3,nFwake) */
+  /* ---- case-driver state (vlc_case.c; classdef.f90:238-312) ---- */
+  double theta, psi, pivotLE, preconeAngle, flap, dflap;
+  double flapOrigin[3];
+  double forceInertial[3], lift[3], drag[3], liftUnsteady[3];
+  double xAxis[3], yAxis[3], zAxis[3];
+  double xAxisAzi[3], yAxisAzi[3], zAxisAzi[3];
+  double xAxisAziFlap[3], yAxisAziFlap[3], zAxisAziFlap[3];
+  double *secChord, *secArea, *secAlpha, *secCL, *secCLu, *secCD, *secMflapArm; /* (ns) */
+  double *secForceInertial, *secLift, *secDrag, *secLiftDir, *secDragDir, *secLiftUnsteady; /* (3,ns) */
+  double *secTauCapChord, *secTauCapSpan, *secNormalVec, *secCP, *secChordwiseResVel;       /* (3,ns) */
+  int spanwiseLiftSwitch;
 } orc_blade_t;
 
 /* The hot-path subset of rotor_class (classdef.f90:360-467). */
@@ -86,6 +97,17 @@ typedef struct {
   orc_blade_t *blade;
   double *AIC, *AIC_inv; /* (N,N) column-major, N = nc*ns*nb */
   double *gamVec, *gamVecPrev, *RHS;
+  /* ---- case-driver state (vlc_case.c; classdef.f90:360-416) ---- */
+  int propConvention, spanSpacing, chordSpacing, spanwiseLiftSwitch, symmetricTau, forceCalcSwitch;
+  int wakeTruncateNt, prescWakeAfterTruncNt, prescWakeGenNt;
+  double radius, root_cut, chord, preconeAngle, thetaTwist, pivotLE, flapHinge, psi, psiStart;
+  double pts[3], cgCoords[3], fromCoords[3], velBody[3], omegaBody[3];
+  double xAxisBody[3], yAxisBody[3], zAxisBody[3];
+  double dragUnitVec[3], sideUnitVec[3], liftUnitVec[3];
+  double spanwiseCore, *streamwiseCoreVec; /* (ns+1) */
+  double rollupStartRadius, rollupEndRadius, initWakeVel, skewLimit;
+  double nonDimforceDenominator;
+  double forceInertial[3], lift[3], liftPrev[3], drag[3], liftUnsteady[3];
 } orc_rotor_t;
 
 /* ---- libMath.f90 ---- */
@@ -161,6 +183,7 @@ double *orc_rotor_wapF(orc_rotor_t *r, int ib, int predicted);
 double *orc_rotor_vel(orc_rotor_t *r, int ib, int which);
 double *orc_rotor_AIC(orc_rotor_t *r, int inverse);
 double *orc_rotor_vec(orc_rotor_t *r, int which);
+void orc_rotor_dims(const orc_rotor_t *r, int *out);
 void orc_rotor_set_rows(orc_rotor_t *r, int rowNear, int rowFar);
 void orc_rotor_set_params(orc_rotor_t *r, int surfaceType, int axisymmetrySwitch, int nbConvect, double Omega,
                           double omegaSlow, const double *shaftAxis, const double *hubCoords, double theta0,
