@@ -356,7 +356,10 @@ class Case:
         return OrcConfig.from_address(self.lib.orc_case_config(self.h))
 
     def rotor(self, ir) -> Rotor:
-        return Rotor.from_handle(self.lib, self.lib.orc_case_rotor(self.h, ir))
+        h = self.lib.orc_case_rotor(self.h, ir)
+        if not h:
+            raise RuntimeError("rotor does not exist yet: call init_rotors() / init() first")
+        return Rotor.from_handle(self.lib, h)
 
     def force_nondim(self, ir=0) -> np.ndarray:
         out = np.empty(9)

@@ -221,3 +221,44 @@ def test_pair_count_matches_survey_table(oracle):
     n_wing, n_wake, m_cp, m_wake = 4 * 4 * 26, 4 * rows * 26, 4 * 26, rows * 27
     expect = m_cp * n_wake + m_cp * ((2 * 4 * 26 + 26) + n_wing) + 2 * m_wake * (n_wing + n_wake)
     assert c.pairs_last_step == expect
+
+
+def test_hook_table_roundtrip_is_bitwise_identical(oracle):
+    """The hook plumbing used by the GPU case test (tests/case_hooks.py) changes nothing by itself: the same
+    oracle arithmetic reached through Python callbacks reproduces the default history bit for bit."""
+    from tests.case_hooks import loopback_hooks
+    fx = json.loads((GOLDEN / "simplewing.json").read_text())
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    h = loopback_hooks(b)
+    b.set_hooks(h)
+    a.init()
+    b.init()
+    for _ in range(12):
+        a.step()
+        b.step()
+        assert not h.errors, h.errors
+        assert np.array_equal(a.force_nondim(0), b.force_nondim(0))
+        assert np.array_equal(a.rotor(0).vec(0), b.rotor(0).vec(0))
+    assert a.config.nt == 40 and abs(a.config.dt - 0.025) < 1e-15     # SURVEY D: simplewing dt = chord/nc/V, nt = 10 chords
+
+
+@pytest.mark.parametrize("name,nsteps", [("simplewing", 10), ("elevateTest", 34)])
+def test_shim_logic_of_gpu_hooks_with_oracle_backed_context(oracle, name, nsteps):
+    """tests/case_hooks.py:gpu_hooks (the upload-then-call sequence of the iso_c_binding shim) driven against a
+    stand-in context that computes from the uploaded copies only: histories must be bitwise identical, i.e. every
+    piece of state a sweep reads has been uploaded (C and 'P' wakes, wing circulations, row counters)."""
+    from tests.case_hooks import OracleBackedContext, gpu_hooks
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    h = gpu_hooks(b, OracleBackedContext())
+    b.set_hooks(h)
+    a.init()
+    b.init()
+    assert not h.errors, h.errors
+    for _ in range(nsteps):
+        a.step()
+        b.step()
+        assert not h.errors, h.errors
+        assert np.array_equal(a.force_nondim(0), b.force_nondim(0))
+        assert np.array_equal(a.rotor(0).vec(0), b.rotor(0).vec(0))
+    assert np.array_equal(a.rotor(0).waN(0), b.rotor(0).waN(0))

@@ -305,6 +305,17 @@ class Context:
                                                    rows, int(predicted), _ptr(out)))
         return out
 
+    def vind_onNwake_byRotor_ptr(self, ir, Nwake_ptr: int, rows, cols, ld, predicted=False):
+        """Same, from the raw address of element (1,1) of the slice (what the Fortran shim passes)."""
+        out = np.empty((cols + 1, rows, 3), dtype=np.float64)
+        self._ck(self.lib.vlc_vind_onNwake_byRotor(self.h, ir, Nwake_ptr, rows, cols, ld, int(predicted), _ptr(out)))
+        return out
+
+    def vind_onFwake_byRotor_ptr(self, ir, Fwake_ptr: int, rows, predicted=False):
+        out = np.empty((rows, 3), dtype=np.float64)
+        self._ck(self.lib.vlc_vind_onFwake_byRotor(self.h, ir, Fwake_ptr, rows, int(predicted), _ptr(out)))
+        return out
+
     def rotor_calcAIC(self, ir, N, want_matrix=True):
         A = np.empty((N, N), dtype=np.float64, order="F") if want_matrix else None
         self._ck(self.lib.vlc_rotor_calcAIC(self.h, ir, _ptr(A)))

@@ -631,6 +631,11 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
   r.surfaceType = surfaceType == 0 ? 1 : surfaceType;  // classdef.f90:3023
   r.rowNear = nNwake + 1;                              // main.f90:228-230
   r.rowFar = nFwake + 1;
+  if (r.d_ipiv && r.N != nc * ns * nb) {  // re-definition with another size: the pivot array is sized by N
+    cudaStreamSynchronize(c->stream);
+    cudaFree(r.d_ipiv);
+    r.d_ipiv = nullptr;
+  }
   r.N = nc * ns * nb;
   r.dirty[0] = r.dirty[1] = r.bound_dirty = true;
   r.factored = false;
@@ -672,7 +677,8 @@ extern "C" int vlc_rotor_put_wing(vlc_ctx* c, int ir, int ib, const double* wiP)
   if (ib < 0 || ib >= r->nb || !wiP) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
   const size_t per = (size_t)r->nc * r->ns * vlc::kWp;
   r->dirty[0] = r->dirty[1] = r->bound_dirty = true;
-  r->factored = false;
+  // The LU factors stay valid: the reference computes AIC once, before the time loop, and keeps using it while the
+  // wing moves rigidly (main.f90:65-81); only vlc_rotor_calcAIC replaces them.
   return upload(c, r->wiP, per * r->nb, per * ib, wiP, per);
 }
 
