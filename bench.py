@@ -222,10 +222,10 @@ def main():
                   "gamF": torch.from_numpy(l.gamF).to(dev) if l.F > 0 else None,
                   "rvcF": torch.from_numpy(l.rvcF).to(dev) if l.F > 0 else None})
     # target list = convected nodes of every lattice (+ far-chain nodes), padded to world * per
-    per = (m + world - 1) // world
-    P_all = torch.zeros(world * per, 3, dtype=torch.float64, device=dev)
-    lo, hi = rank * per, min((rank + 1) * per, m)
-    m_loc = max(0, hi - lo)
+    from volcanor_b200.sharding import TargetShard, allgather_slices
+    shard = TargetShard(m, world, rank)
+    per, lo, hi, m_loc = shard.per, shard.lo, shard.hi, shard.count
+    P_all = torch.zeros(shard.padded, 3, dtype=torch.float64, device=dev)
     V_loc = torch.zeros(per, 3, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     dt_step = 1e-9
@@ -272,8 +272,7 @@ def main():
             ev_k1.append(e1)
         if m_loc > 0:
             ctx.convect_dev(m_loc, P_all[lo:hi], V_loc, dt_step)
-        if world > 1:
-            dist.all_gather_into_tensor(P_all, P_all[rank * per:(rank + 1) * per].clone())
+        allgather_slices(P_all, shard)                 # the one exchange step of a convection stage (NCCL)
         scatter_targets()
 
     def barrier():

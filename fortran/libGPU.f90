@@ -1,0 +1,304 @@
+!! libGPU -- iso_c_binding shim between VOLCANOR's Fortran driver and libvolcanor_b200.so
+!!
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (DESIGN.md, "Boundary").
+!! The call sequence below is the one tests/case_hooks.py:gpu_hooks drives against the same C ABI from the
+!! C restatement of `program main` (oracle/vlc_case.c), where it is tested on a B200 (tests/test_gpu_case.py).
+!!
+!! Build (reference tree, with a Fortran compiler):
+!!   gfortran -c libGPU.f90   (after classdef.f90; add to CMakeLists.txt next to libCommon.f90)
+!!   link: -L<repo>/volcanor_b200 -lvolcanor_b200 -lcudart -lcusolver
+!!
+!! What changes in the driver (INTEGRATION.md has the full diff):
+!!   libCommon.f90: `use libGPU`, and the bodies of vind_onNwake_byRotor / vind_onFwake_byRotor become one call each
+!!   main.f90     : the three OpenMP CP loops (RHS :528-573, initial :124-167, forces :632-656) call
+!!                  gpu_vind_points on the array of collocation points instead of rotor%vind_* per point;
+!!                  calcAIC / matmulAX(AIC_inv, RHS) become gpu_calcAIC / gpu_solve
+!! Nothing else (case files, derived types, time integration, loads, output) is touched.
+module libGPU
+  use, intrinsic :: iso_c_binding
+  use classdef, only: rotor_class, Nwake_class, Fwake_class, dp
+  implicit none
+  private
+  public :: gpu_init, gpu_finalize, gpu_sync_rotor, gpu_vind_onNwake_byRotor, gpu_vind_onFwake_byRotor
+  public :: gpu_vind_points, gpu_calcAIC, gpu_solve
+
+  type(c_ptr), save :: ctx = c_null_ptr
+
+  ! what for gpu_vind_points
+  integer, parameter, public :: GPU_BYWING = 0, GPU_BYWAKE = 1, GPU_BOTH = 2, GPU_BOUNDVORTICES = 3
+
+  interface
+    integer(c_int) function vlc_create(device, out) bind(C, name='vlc_create')
+      import :: c_int, c_ptr
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: out
+    end function
+    integer(c_int) function vlc_destroy(c) bind(C, name='vlc_destroy')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+    end function
+    type(c_ptr) function vlc_last_error(c) bind(C, name='vlc_last_error')
+      import :: c_ptr
+      type(c_ptr), value :: c
+    end function
+    integer(c_int) function vlc_rotor_define(c, ir, nb, nc, ns, nNwake, nFwake, surfaceType) &
+        & bind(C, name='vlc_rotor_define')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, nb, nc, ns, nNwake, nFwake, surfaceType
+    end function
+    integer(c_int) function vlc_rotor_set_rows(c, ir, rowNear, rowFar) bind(C, name='vlc_rotor_set_rows')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, rowNear, rowFar
+    end function
+    integer(c_int) function vlc_rotor_put_wing(c, ir, ib, wiP) bind(C, name='vlc_rotor_put_wing')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib
+      real(c_double), intent(in) :: wiP(*)
+    end function
+    integer(c_int) function vlc_rotor_put_nwake(c, ir, ib, predicted, waN) bind(C, name='vlc_rotor_put_nwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(in) :: waN(*)
+    end function
+    integer(c_int) function vlc_rotor_put_fwake(c, ir, ib, predicted, waF) bind(C, name='vlc_rotor_put_fwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(in) :: waF(*)
+    end function
+    integer(c_int) function vlc_rotor_put_pfwake(c, ir, ib, predicted, wapF) bind(C, name='vlc_rotor_put_pfwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(in) :: wapF(*)
+    end function
+    integer(c_int) function vlc_rotor_vind_bywing(c, ir, m, P, V) bind(C, name='vlc_rotor_vind_bywing')
+      import :: c_int, c_int64_t, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      integer(c_int64_t), value :: m
+      real(c_double), intent(in) :: P(3, *)
+      real(c_double), intent(out) :: V(3, *)
+    end function
+    integer(c_int) function vlc_rotor_vind_bywake(c, ir, predicted, m, P, V) bind(C, name='vlc_rotor_vind_bywake')
+      import :: c_int, c_int64_t, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, predicted
+      integer(c_int64_t), value :: m
+      real(c_double), intent(in) :: P(3, *)
+      real(c_double), intent(out) :: V(3, *)
+    end function
+    integer(c_int) function vlc_rotor_vind(c, ir, predicted, m, P, V) bind(C, name='vlc_rotor_vind')
+      import :: c_int, c_int64_t, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, predicted
+      integer(c_int64_t), value :: m
+      real(c_double), intent(in) :: P(3, *)
+      real(c_double), intent(out) :: V(3, *)
+    end function
+    integer(c_int) function vlc_rotor_vind_bywing_boundVortices(c, ir, m, P, V) &
+        & bind(C, name='vlc_rotor_vind_bywing_boundVortices')
+      import :: c_int, c_int64_t, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      integer(c_int64_t), value :: m
+      real(c_double), intent(in) :: P(3, *)
+      real(c_double), intent(out) :: V(3, *)
+    end function
+    integer(c_int) function vlc_vind_onNwake_byRotor(c, ir, Nwake, rows, cols, ld, predicted, vindArray) &
+        & bind(C, name='vlc_vind_onNwake_byRotor')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, rows, cols, ld, predicted
+      real(c_double), intent(in) :: Nwake(*)
+      real(c_double), intent(out) :: vindArray(3, rows, cols + 1)
+    end function
+    integer(c_int) function vlc_vind_onFwake_byRotor(c, ir, Fwake, rows, predicted, vindArray) &
+        & bind(C, name='vlc_vind_onFwake_byRotor')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, rows, predicted
+      real(c_double), intent(in) :: Fwake(*)
+      real(c_double), intent(out) :: vindArray(3, rows)
+    end function
+    integer(c_int) function vlc_rotor_calcAIC(c, ir, AIC_out) bind(C, name='vlc_rotor_calcAIC')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), intent(out) :: AIC_out(*)
+    end function
+    integer(c_int) function vlc_rotor_solve(c, ir, RHS, gamVec) bind(C, name='vlc_rotor_solve')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), intent(in) :: RHS(*)
+      real(c_double), intent(out) :: gamVec(*)
+    end function
+  end interface
+
+contains
+
+  subroutine check(rc)
+    !! The library returns a status; the reference aborts with `error stop` (e.g. libMath.f90:73).
+    integer(c_int), intent(in) :: rc
+    character(kind=c_char), pointer :: msg(:)
+    integer :: n
+    if (rc /= 0) then
+      call c_f_pointer(vlc_last_error(ctx), msg, [512])
+      n = 1
+      do while (n < 512 .and. msg(n) /= c_null_char)
+        n = n + 1
+      enddo
+      print *, 'volcanor_b200: ', msg(1:n - 1)
+      error stop 'ERROR: GPU library call failed'
+    endif
+  end subroutine check
+
+  subroutine gpu_init(rotor, device)
+    !! Once, after rotor%init (main.f90:31-40): declare every rotor's sizes.
+    type(rotor_class), intent(in) :: rotor(:)
+    integer, intent(in) :: device
+    integer :: ir
+    call check(vlc_create(int(device, c_int), ctx))
+    do ir = 1, size(rotor)
+      call check(vlc_rotor_define(ctx, ir - 1, rotor(ir)%nb, rotor(ir)%nc, rotor(ir)%ns, &
+        & rotor(ir)%nNwake, rotor(ir)%nFwake, rotor(ir)%surfaceType))
+    enddo
+  end subroutine gpu_init
+
+  subroutine gpu_finalize()
+    if (c_associated(ctx)) call check(vlc_destroy(ctx))
+    ctx = c_null_ptr
+  end subroutine gpu_finalize
+
+  subroutine gpu_sync_rotor(rotor, ir, predicted)
+    !! Flatten the non-interoperable derived types into arrays of doubles and upload them.
+    !! vr_class = 50, Fwake_class = 13, wingpanel_class = 104 doubles (sequence of default reals(dp));
+    !! `transfer` keeps the component order of classdef.f90:57-220.
+    type(rotor_class), intent(in) :: rotor
+    integer, intent(in) :: ir
+    logical, intent(in) :: predicted
+    integer :: ib
+    integer(c_int) :: p
+    real(c_double), allocatable :: buf(:)
+    p = merge(1_c_int, 0_c_int, predicted)
+    call check(vlc_rotor_set_rows(ctx, ir - 1, rotor%rowNear, rotor%rowFar))
+    do ib = 1, rotor%nb
+      buf = transfer(rotor%blade(ib)%wiP, buf)
+      call check(vlc_rotor_put_wing(ctx, ir - 1, ib - 1, buf))
+      if (rotor%nNwake > 0) then
+        if (predicted) then
+          buf = transfer(rotor%blade(ib)%waNPredicted, buf)
+        else
+          buf = transfer(rotor%blade(ib)%waN, buf)
+        endif
+        call check(vlc_rotor_put_nwake(ctx, ir - 1, ib - 1, p, buf))
+        if (rotor%nFwake > 0) then
+          if (predicted) then
+            buf = transfer(rotor%blade(ib)%waFPredicted, buf)
+          else
+            buf = transfer(rotor%blade(ib)%waF, buf)
+          endif
+          call check(vlc_rotor_put_fwake(ctx, ir - 1, ib - 1, p, buf))
+        endif
+        if (rotor%prescWakeNt > 0) then
+          if (predicted) then
+            buf = transfer(rotor%blade(ib)%wapFPredicted%waF, buf)
+          else
+            buf = transfer(rotor%blade(ib)%wapF%waF, buf)
+          endif
+          call check(vlc_rotor_put_pfwake(ctx, ir - 1, ib - 1, p, buf))
+        endif
+      endif
+    enddo
+  end subroutine gpu_sync_rotor
+
+  function gpu_vind_onNwake_byRotor(rotor, ir, Nwake, optionalChar) result(vindArray)
+    !! Drop-in body of libCommon.f90:114-171 (ir = index of `rotor` in the global rotor array).
+    type(rotor_class), intent(in) :: rotor
+    integer, intent(in) :: ir
+    type(Nwake_class), intent(in), dimension(:, :) :: Nwake
+    character(len=1), optional :: optionalChar
+    real(dp), dimension(3, size(Nwake, 1), size(Nwake, 2) + 1) :: vindArray
+    real(c_double), allocatable :: buf(:)
+    logical :: pred
+    pred = .false.
+    if (present(optionalChar)) then
+      if (optionalChar /= 'P') error stop 'ERROR: Wrong character flag for vind_onNwake_byRotor()'
+      pred = .true.
+    endif
+    call gpu_sync_rotor(rotor, ir, pred)
+    buf = transfer(Nwake, buf)           ! contiguous copy of the slice: ld = rows
+    call check(vlc_vind_onNwake_byRotor(ctx, ir - 1, buf, size(Nwake, 1), size(Nwake, 2), size(Nwake, 1), &
+      & merge(1_c_int, 0_c_int, pred), vindArray))
+  end function gpu_vind_onNwake_byRotor
+
+  function gpu_vind_onFwake_byRotor(rotor, ir, Fwake, optionalChar) result(vindArray)
+    !! Drop-in body of libCommon.f90:173-211
+    type(rotor_class), intent(in) :: rotor
+    integer, intent(in) :: ir
+    type(Fwake_class), intent(in), dimension(:) :: Fwake
+    character(len=1), optional :: optionalChar
+    real(dp), dimension(3, size(Fwake)) :: vindArray
+    real(c_double), allocatable :: buf(:)
+    logical :: pred
+    pred = .false.
+    if (present(optionalChar)) then
+      if (optionalChar /= 'P') error stop 'ERROR: Wrong character flag for vind_onFwake_byRotor()'
+      pred = .true.
+    endif
+    if (size(Fwake) == 0) return
+    call gpu_sync_rotor(rotor, ir, pred)
+    buf = transfer(Fwake, buf)
+    call check(vlc_vind_onFwake_byRotor(ctx, ir - 1, buf, size(Fwake), merge(1_c_int, 0_c_int, pred), vindArray))
+  end function gpu_vind_onFwake_byRotor
+
+  function gpu_vind_points(rotor, ir, what, P, predicted) result(V)
+    !! rotor%vind_bywing / %vind_bywake / both / %vind_bywing_boundVortices at all points of P(3, m) in one call:
+    !! replaces the per-point calls inside the OpenMP loops of main.f90:124-167, :247-271, :528-573, :632-656.
+    type(rotor_class), intent(in) :: rotor
+    integer, intent(in) :: ir, what
+    real(dp), intent(in) :: P(:, :)
+    logical, intent(in) :: predicted
+    real(dp) :: V(3, size(P, 2))
+    integer(c_int64_t) :: m
+    integer(c_int) :: pr
+    m = size(P, 2, kind=c_int64_t)
+    pr = merge(1_c_int, 0_c_int, predicted)
+    call gpu_sync_rotor(rotor, ir, predicted)
+    select case (what)
+    case (GPU_BYWING)
+      call check(vlc_rotor_vind_bywing(ctx, ir - 1, m, P, V))
+    case (GPU_BYWAKE)
+      call check(vlc_rotor_vind_bywake(ctx, ir - 1, pr, m, P, V))
+    case (GPU_BOTH)
+      call check(vlc_rotor_vind(ctx, ir - 1, pr, m, P, V))
+    case (GPU_BOUNDVORTICES)
+      call check(vlc_rotor_vind_bywing_boundVortices(ctx, ir - 1, m, P, V))
+    case default
+      error stop 'ERROR: gpu_vind_points: wrong selector'
+    end select
+  end function gpu_vind_points
+
+  subroutine gpu_calcAIC(rotor, ir)
+    !! rotor%calcAIC() (classdef.f90:4151-4179): assemble on the device, LU-factor once (cuSOLVER getrf).
+    !! rotor%AIC is filled for output / isInverse-style checks; AIC_inv is not needed any more.
+    type(rotor_class), intent(inout) :: rotor
+    integer, intent(in) :: ir
+    call gpu_sync_rotor(rotor, ir, .false.)
+    call check(vlc_rotor_calcAIC(ctx, ir - 1, rotor%AIC))
+  end subroutine gpu_calcAIC
+
+  function gpu_solve(rotor, ir) result(gamVec)
+    !! gamVec = matmulAX(AIC_inv, RHS) (main.f90:190, :596) -> getrs with the stored factors
+    type(rotor_class), intent(in) :: rotor
+    integer, intent(in) :: ir
+    real(dp) :: gamVec(size(rotor%RHS))
+    call check(vlc_rotor_solve(ctx, ir - 1, rotor%RHS, gamVec))
+  end function gpu_solve
+
+end module libGPU
