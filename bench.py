@@ -30,6 +30,7 @@ sys.path.insert(0, str(ROOT))
 
 FLOPS_PER_PAIR = 76        # algorithmic flops of vf_vind as written + gam scale/accumulate
 PIPE_INSTR_PER_PAIR = {0: 43, 1: 41}   # FP64-pipe instructions per pair in bs_sweep_kernel (SASS count; full / fast)
+PIPE_INSTR_PER_RECORD = 72             # ... per (target, ring-step record) in bs_lattice_kernel = 4 reference pairs
 
 
 def parse():
@@ -44,6 +45,8 @@ def parse():
     ap.add_argument("--nsplit", type=int, default=0, help="source splits (0 = auto)")
     ap.add_argument("--precision", type=int, default=0, choices=[0, 1],
                     help="0 = full (third-order rsqrt, default), 1 = fast (second order, pair error <= 6.4e-13)")
+    ap.add_argument("--flat", action="store_true",
+                    help="force the flat kernel on the reference's enumeration (default: shared-node lattice kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -209,6 +212,7 @@ def main():
     ctx = vb.Context(local)
     ctx.set_tuning(args.T, args.nsplit)
     ctx.set_precision(args.precision)
+    ctx.set_shared_nodes(not args.flat)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -282,6 +286,8 @@ def main():
 
     pack()
     assert ctx.num_sources(0) == n_src, (ctx.num_sources(0), n_src)
+    info = ctx.set_info(0)
+    shared = info["shared_active"] == 1
     fp64_peak, _ = ctx.measure_fp64_peak(20000)
 
     for _ in range(max(args.warmup, 3)):
@@ -301,30 +307,37 @@ def main():
     elapsed_ms = t0.elapsed_time(t1)
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)])) if ev_k0 else 0.0
-    tt = torch.tensor([elapsed_ms, kern_ms], dtype=torch.float64, device=dev)
+    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)])) if ev_k0 else 0.0
+    # dominant kernel alone (CUDA events recorded by the library on the launching stream around that launch, last step)
+    main_ms, total_ms = ctx.last_sweep_ms() if m_loc > 0 else (0.0, 0.0)
+    kern_ms = sweep_ms * (main_ms / total_ms) if total_ms > 0 else sweep_ms
+    tt = torch.tensor([elapsed_ms, kern_ms, sweep_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed_ms, kern_ms_max = float(tt[0]), float(tt[1])
+    elapsed_ms, kern_ms_max, sweep_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
     pairs_step = float(m) * float(n_src)
     value = pairs_step * args.steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D + D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e:
-        p1, p2, rvc, gam, flag = synth.flatten_all(lats)
         P_host = synth.targets_all(lats)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        hp1, hp2, hr, hg, hf = pin(p1), pin(p2), pin(rvc), pin(gam), pin(flag)
+        hl = [{"R": l.R, "S": l.S, "F": l.F, "nodes": pin(l.nodes), "gam": pin(l.gam), "rvc4": pin(l.rvc4),
+               "far": pin(l.far_nodes) if l.F > 0 else None, "gamF": pin(l.gamF) if l.F > 0 else None,
+               "rvcF": pin(l.rvcF) if l.F > 0 else None} for l in lats]
+        h2d = sum(8 * (L["nodes"].numel() + L["gam"].numel() + L["rvc4"].numel()
+                       + (L["far"].numel() + 2 * L["F"] if L["F"] > 0 else 0)) for L in hl)
         hP = pin(P_host[lo:hi]) if m_loc > 0 else None
         hV = torch.empty(max(m_loc, 1), 3, dtype=torch.float64).pin_memory()
-        lib, h = ctx.lib, ctx.h
 
         def e2e_step():
-            ctx._ck(lib.vlc_set_sources(h, 1, n_src, hp1.data_ptr(), hp2.data_ptr(), hr.data_ptr(), hg.data_ptr(),
-                                        hf.data_ptr()))
+            # the caller-facing C-ABI calls with HOST buffers: wake lattices in, velocities of this rank's targets out
+            for i, L in enumerate(hl):
+                ctx.pack_lattice(1, i > 0, L["R"], L["S"], L["nodes"], L["gam"], L["rvc4"], L["F"], L["far"],
+                                 L["gamF"], L["rvcF"])
             if m_loc > 0:
-                ctx._ck(lib.vlc_vind(h, 1, m_loc, hP.data_ptr(), hV.data_ptr()))
+                ctx.vind_into(1, m_loc, hP, hV)
 
         for _ in range(2):
             e2e_step()
@@ -338,8 +351,9 @@ def main():
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {"value": pairs_step * args.steps / float(tw[0]), "unit": "pair-interactions/s",
-               "h2d_bytes_per_step": int(8 * 8 * n_src + n_src + 24 * m_loc), "d2h_bytes_per_step": int(24 * m_loc),
-               "call": "vlc_set_sources + vlc_vind (host buffers, pinned), per rank: all sources, its target slice",
+               "h2d_bytes_per_step": int(h2d + 24 * m_loc), "d2h_bytes_per_step": int(24 * m_loc),
+               "call": "vlc_pack_lattice (host wake lattices of all blades) + vlc_vind (host targets -> host velocities), "
+                       "pinned buffers, per rank: all sources, its target slice",
                "ms_per_step": 1e3 * float(tw[0]) / args.steps}
 
     if rank != 0:
@@ -347,19 +361,31 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (bs_sweep_kernel), measured live with CUDA events ----
-    pairs_launch = float(m_loc) * float(n_src)
-    achieved = pairs_launch * FLOPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12 if kern_ms_max > 0 else 0.0
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
     peak = fp64_peak / 1e12
+    if shared:
+        # bs_lattice_kernel covers the 4 ring filaments of every near-wake ring; the remainder kernel the rest
+        kernel = "bs_lattice_kernel"
+        pairs_launch = float(m_loc) * 4.0 * float(sum(l.R * l.S for l in lats))
+        issued = float(m_loc) * float(info["lattice_records"]) * PIPE_INSTR_PER_RECORD
+        note = ("shared-node lattice kernel: every lattice node evaluated once per target and every interior edge once "
+                "with the merged strength of its two rings -- the reference's ring-by-ring sum regrouped, so frac counts "
+                "the reference's 76 flop x 4 filaments per ring while the kernel issues 72 FP64 instructions per "
+                "(target, ring): frac may exceed 1; pipe_frac = issued FP64 instructions vs the pipe's peak")
+    else:
+        kernel = "bs_sweep_kernel"
+        pairs_launch = float(m_loc) * float(n_src)
+        issued = pairs_launch * PIPE_INSTR_PER_PAIR[args.precision]
+        note = ("flat kernel on the reference's enumeration: frac = algorithmic 76 flop/pair, pipe_frac = issued FP64 "
+                "instr/pair (43 full, 41 fast)")
+    achieved = pairs_launch * FLOPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12 if kern_ms_max > 0 else 0.0
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
-                "kernel": "bs_sweep_kernel", "kernel_ms": kern_ms_max, "pairs_per_launch": pairs_launch,
-                "flops_per_pair": FLOPS_PER_PAIR,
-                "pipe_frac": pairs_launch * PIPE_INSTR_PER_PAIR[args.precision] * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
+                "traffic": None, "kernel": kernel, "kernel_ms": kern_ms_max, "sweep_ms": sweep_ms_max,
+                "pairs_per_launch": pairs_launch, "flops_per_pair": FLOPS_PER_PAIR,
+                "pipe_frac": issued * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
                 "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); "
                                "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
-                "note": "compute-bound pairwise N-body on the FP64 pipe (no tensor cores by construction); "
-                        "frac = algorithmic 76 flop/pair, pipe_frac = issued FP64 instr/pair (43 full, 41 fast)"}
+                "note": "compute-bound pairwise N-body on the FP64 pipe (no tensor cores by construction); " + note}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         p1, p2, rvc, gam, flag = synth.flatten_all(lats)
@@ -375,6 +401,9 @@ def main():
                       "l2": "flushed every step by a 256 MiB memset inside the timed region",
                       "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather/stage",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
+                      "sources": ({"form": "shared-node lattice", "ring_step_records": int(info["lattice_records"]),
+                                   "remainder_filaments": int(info["remainder_filaments"])} if shared
+                                  else {"form": "flat reference enumeration"}),
                       "precision": ["full: third-order rsqrt refinement, pair error ~1e-16",
                                     "fast: second-order rsqrt refinement, pair error <= 6.4e-13"][args.precision]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

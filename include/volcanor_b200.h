@@ -176,6 +176,19 @@ int vlc_strain_dev(vlc_ctx* ctx, int64_t n, const double* d_p1, const double* d_
 int vlc_pack_lattice_dev(vlc_ctx* ctx, int set, int append, int nrows, int ns, const double* d_nodes,
                          const double* d_gam, const double* d_rvc4, int nfar, const double* d_far_nodes,
                          const double* d_gamF, const double* d_rvcF);
+/* Same with HOST arrays (copied in synchronously): the caller-facing form of the lattice path. */
+int vlc_pack_lattice(vlc_ctx* ctx, int set, int append, int nrows, int ns, const double* nodes, const double* gam,
+                     const double* rvc4, int nfar, const double* far_nodes, const double* gamF, const double* rvcF);
+/* Sets built by vlc_pack_lattice_dev also hold a SHARED-NODE form: every lattice node is evaluated once
+ * per target instead of once per adjacent ring filament and every interior edge once with the merged strength of the
+ * two rings that share it -- the same sum as the reference's ring-by-ring enumeration (classdef.f90:1450-1456), 18
+ * instead of 43 FP64 instructions per reference pair.  If the two copies of a shared edge carry different core radii
+ * the device falls back to the flat enumeration by itself.  on = 0 forces the flat enumeration (default on = 1). */
+int vlc_set_shared_nodes(vlc_ctx* ctx, int on);
+/* out[0] = filaments in the reference's enumeration, out[1] = ring-step records and out[2] = remainder filaments of
+ * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel, 0 if
+ * the flat one (reads the device flag: synchronises), -1 for a flat-only set. */
+int vlc_set_info(vlc_ctx* ctx, int set, int64_t* out);
 /* rotor_dissipate_wake on a lattice (classdef.f90:4364-4393): vf1 grows, vf3 <- vf1, gam decays, vf2 grows,
  * vf4(i) <- vf2(i-1) for i > first row. */
 int vlc_dissipate_lattice_dev(vlc_ctx* ctx, int nrows, int ns, double* d_rvc4, double* d_gam,
@@ -192,6 +205,10 @@ int vlc_lattice_scatter_dev(vlc_ctx* ctx, int nrows, int ns, double* d_nodes, co
  * and the elapsed milliseconds; used by bench.py as the measured FP64 roofline denominator
  * (MEASURED_PEAKS.json has no FP64 entry). */
 int vlc_measure_fp64_peak(vlc_ctx* ctx, int iters, double* flops_per_s, double* ms);
+/* Device time of the last sweep launched by this context, from CUDA events recorded on the context's stream around
+ * the dominant kernel (bs_lattice_kernel or bs_sweep_kernel) and around the whole sweep (incl. remainder + reduce).
+ * Waits for that sweep to finish. */
+int vlc_last_sweep_ms(vlc_ctx* ctx, double* ms_kernel, double* ms_total);
 /* Evaluate the raw MUFU.RSQ64H seed and the full / fast refined reciprocal square roots of x[0..n)
  * (host arrays) -- lets the tests measure the error bounds the precision modes rely on. */
 int vlc_probe_rsqrt(vlc_ctx* ctx, int64_t n, const double* x, double* seed, double* full, double* fast);

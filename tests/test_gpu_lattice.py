@@ -1,0 +1,155 @@
+"""GPU parity of the device-resident lattice path (tier 3) and its shared-node sweep kernel (bs_lattice.cuh) against
+the CPU oracle evaluating the REFERENCE's enumeration (ring by ring, 4 filaments per ring, classdef.f90:1450-1469).
+
+The shared-node kernel regroups that sum (one evaluation per lattice node and per unique edge); results must agree
+within the per-call tolerance 1e-12 of the velocity scale, for targets that coincide with lattice nodes (the wake
+nodes themselves: every target lies on up to 4 edges, all of which must be skipped exactly like classdef.f90:498),
+for skipped rings (|gam| <= eps), with and without a far wake, and when the two copies of a shared edge carry
+different core radii, in which case the device falls back to the flat enumeration by itself.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import scaled_err
+from volcanor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _upload(ctx, lats, set_=3):
+    import torch
+    keep = []
+    for i, l in enumerate(lats):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        nodes, gam, rvc4 = t(l.nodes), t(l.gam), t(l.rvc4)
+        far = t(l.far_nodes) if l.F > 0 else None
+        gF = t(l.gamF) if l.F > 0 else None
+        rF = t(l.rvcF) if l.F > 0 else None
+        ctx.pack_lattice_dev(set_, i > 0, l.R, l.S, nodes, gam, rvc4, l.F, far, gF, rF)
+        keep += [nodes, gam, rvc4, far, gF, rF]
+    ctx.sync()
+    return keep
+
+
+def _sweep(ctx, P, set_=3):
+    import torch
+    dP = torch.from_numpy(np.ascontiguousarray(P)).cuda()
+    dV = torch.full_like(dP, float("nan"))
+    ctx.vind_dev(set_, P.shape[0], dP, dV)
+    ctx.sync()
+    return dV.cpu().numpy()
+
+
+def _check(ctx, oracle, lats, P, tol=TOL):
+    keep = _upload(ctx, lats)
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    assert ctx.num_sources(3) == rvc.size                   # reference enumeration count
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, P)
+    Vl, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, P)
+    ctx.set_shared_nodes(True)
+    Vs = _sweep(ctx, P)
+    ctx.set_shared_nodes(False)
+    Vf = _sweep(ctx, P)
+    ctx.set_shared_nodes(True)
+    assert np.all(np.isfinite(Vs)) and np.all(np.isfinite(Vf))
+    es, ef = scaled_err(Vs, Vo, Vabs), scaled_err(Vf, Vo, Vabs)
+    assert es < tol and ef < tol, (es, ef)
+    # neither GPU form is further from the long-double sum than the reference-order double sum is
+    assert scaled_err(Vs, Vl, Vabs) < 5 * max(scaled_err(Vo, Vl, Vabs), 1e-15)
+    return Vs, Vf, Vo, Vabs
+
+
+@pytest.mark.parametrize("kw", [dict(n=3000, n_rotor=1, nb=1, S=4, F=0, with_wing=False),
+                                dict(n=6000, n_rotor=1, nb=2, S=8, F=8, with_wing=True),
+                                dict(n=20000, n_rotor=4, nb=2, S=8, F=16, with_wing=True)])
+def test_wake_nodes_as_targets(ctx, oracle, kw):
+    """The convection sweep itself: targets are the lattice's own nodes (libCommon.f90:133-145)."""
+    kw = dict(kw)
+    lats = synth.multirotor(kw.pop("n"), seed=11, **kw)
+    _check(ctx, oracle, lats, synth.targets_all(lats))
+
+
+def test_off_lattice_targets_and_source_splits(ctx, oracle):
+    lats = synth.multirotor(8000, seed=5, n_rotor=2, nb=2, S=6, F=5)
+    P = np.random.default_rng(2).uniform(-4, 4, size=(333, 3))
+    for nsplit in (0, 1, 3, 16):
+        ctx.set_tuning(0, nsplit)
+        try:
+            _check(ctx, oracle, lats, P)
+        finally:
+            ctx.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("R,S,F", [(1, 1, 0), (1, 1, 3), (2, 1, 0), (1, 5, 2), (130, 2, 1), (3, 70, 0)])
+def test_degenerate_lattice_shapes(ctx, oracle, R, S, F):
+    rng = np.random.Generator(np.random.PCG64(R * 100 + S))
+    lat = synth._helix_lattice(rng, np.zeros(3), 1.0, 0.1, S, R, F, psi0=0.3, sense=1.0)
+    P = np.concatenate([lat.targets(), rng.uniform(-2, 2, size=(17, 3))])
+    _check(ctx, oracle, [lat], P)
+
+
+def test_skipped_rings_and_zero_strength(ctx, oracle):
+    """classdef.f90:1452: rings with |gam| <= eps contribute nothing; merged edge strengths use Gamma' = 0 for them."""
+    lats = synth.multirotor(5000, seed=9, n_rotor=1, nb=2, S=6, F=4, with_wing=False)
+    rng = np.random.default_rng(0)
+    for l in lats:
+        l.gam[rng.uniform(size=l.gam.shape) < 0.2] = 0.0
+        l.gam[rng.uniform(size=l.gam.shape) < 0.1] = 1e-17
+    _check(ctx, oracle, lats, synth.targets_all(lats))
+    for l in lats:
+        l.gam[...] = 1e-17
+        l.gamF[...] = 0.0
+    keep = _upload(ctx, lats)
+    V = _sweep(ctx, synth.targets_all(lats))
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, synth.targets_all(lats))
+    # only the horseshoe correction (no gam rule, classdef.f90:1460-1463) is left: O(1e-17)
+    assert np.max(np.abs(V - Vo)) < 1e-28
+
+
+def test_unmergeable_core_radii_fall_back_to_flat_enumeration(ctx, oracle):
+    """Non-uniform streamwise cores: vf3 of ring (r, j) and vf1 of ring (r, j+1) are the same edge with different
+    rVc (the reference keeps both).  The pack kernel detects it and the device runs the flat kernel."""
+    lats = synth.multirotor(6000, seed=4, n_rotor=1, nb=2, S=6, F=4, with_wing=False)
+    for l in lats:
+        l.rvc4[:, :, 2] *= 1.0 + 0.05 * np.arange(l.S)[:, None]      # vf3 differs from the neighbour's vf1
+    P = synth.targets_all(lats)
+    Vs, Vf, Vo, Vabs = _check(ctx, oracle, lats, P)
+    assert np.array_equal(Vs, Vf)          # same kernel, same records, same split -> bitwise equal
+    # and a mergeable set packed afterwards into the same slot uses the lattice kernel again
+    lats2 = synth.multirotor(6000, seed=4, n_rotor=1, nb=2, S=6, F=4, with_wing=False)
+    Vs2, Vf2, _, Vabs2 = _check(ctx, oracle, lats2, P)
+    assert not np.array_equal(Vs2, Vf2) and scaled_err(Vs2, Vf2, Vabs2) < TOL
+
+
+def test_lattice_state_kernels_vs_oracle(ctx, oracle):
+    """dissipate (classdef.f90:4364-4393), convect (:1531), AB2/AM2 (main.f90:1032-1034, :1094-1096) on device arrays."""
+    import torch
+    rng = np.random.default_rng(1)
+    R, S = 7, 5
+    rvc4 = rng.uniform(0.01, 0.05, size=(S, R, 4))
+    gam = rng.uniform(-1, 1, size=(S, R))
+    d_r, d_g = torch.from_numpy(rvc4.copy()).cuda(), torch.from_numpy(gam.copy()).cuda()
+    a, nu, k, dt = 5.0, 1.8e-5, 0.3, 2e-3
+    ctx.dissipate_lattice_dev(R, S, d_r, d_g, a, nu, k, dt)
+    ctx.sync()
+    exp = rvc4.copy()
+    g2 = 4.0 * 1.2564 * a * nu * dt
+    exp[:, :, 0] = np.sqrt(rvc4[:, :, 0] ** 2 + g2)
+    exp[:, :, 2] = exp[:, :, 0]
+    exp[:, :, 1] = np.sqrt(rvc4[:, :, 1] ** 2 + g2)
+    exp[:, 1:, 3] = exp[:, :-1, 1]
+    assert np.max(np.abs(d_r.cpu().numpy() - exp)) < 1e-17
+    assert np.max(np.abs(d_g.cpu().numpy() - gam * np.exp(-k * dt))) < 1e-16
+    x, v, v1 = rng.normal(size=(50, 3)), rng.normal(size=(50, 3)), rng.normal(size=(50, 3))
+    dx, dv, dv1 = (torch.from_numpy(t.copy()).cuda() for t in (x, v, v1))
+    out = torch.empty_like(dv)
+    ctx.convect_dev(50, dx, dv, dt)
+    ctx.ab2_dev(50, dv, dv1, out)
+    ctx.sync()
+    assert np.array_equal(dx.cpu().numpy(), x + v * dt)
+    assert np.array_equal(out.cpu().numpy(), 0.5 * (3.0 * v - v1))
+    ctx.am2_dev(50, dv, dv1, out)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), (v + v1) * 0.5)

@@ -118,6 +118,10 @@ def load_library() -> C.CDLL:
         "vlc_dissipate_lattice_dev": (i32, [_vp, i32, i32, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double]),
         "vlc_strain_dev": (i32, [_vp, i64, _vp, _vp, _vp, _vp, _vp]),
         "vlc_pack_lattice_dev": (i32, [_vp, i32, i32, i32, i32, _vp, _vp, _vp, i32, _vp, _vp, _vp]),
+        "vlc_pack_lattice": (i32, [_vp, i32, i32, i32, i32, _vp, _vp, _vp, i32, _vp, _vp, _vp]),
+        "vlc_set_shared_nodes": (i32, [_vp, i32]),
+        "vlc_set_info": (i32, [_vp, i32, C.POINTER(i64)]),
+        "vlc_last_sweep_ms": (i32, [_vp, _dp, _dp]),
         "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
@@ -357,6 +361,25 @@ class Context:
                          rvcF=None):
         self._ck(self.lib.vlc_pack_lattice_dev(self.h, set_, int(append), nrows, ns, _ptr(nodes), _ptr(gam),
                                                _ptr(rvc4), nfar, _ptr(far_nodes), _ptr(gamF), _ptr(rvcF)))
+
+    def pack_lattice(self, set_, append, nrows, ns, nodes, gam, rvc4, nfar=0, far_nodes=None, gamF=None, rvcF=None):
+        """Host arrays (numpy / pinned torch): nodes (ns+1, nrows+1, 3), gam (ns, nrows), rvc4 (ns, nrows, 4), far chain."""
+        self._ck(self.lib.vlc_pack_lattice(self.h, set_, int(append), nrows, ns, _ptr(nodes), _ptr(gam), _ptr(rvc4),
+                                           nfar, _ptr(far_nodes), _ptr(gamF), _ptr(rvcF)))
+
+    def set_shared_nodes(self, on: bool):
+        """Lattice sets: shared-node kernel (default) or the flat reference enumeration."""
+        self._ck(self.lib.vlc_set_shared_nodes(self.h, int(on)))
+
+    def set_info(self, set_: int) -> dict:
+        out = (C.c_int64 * 4)()
+        self._ck(self.lib.vlc_set_info(self.h, set_, out))
+        return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3]}
+
+    def last_sweep_ms(self) -> tuple[float, float]:
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.vlc_last_sweep_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def lattice_targets_dev(self, nrows, ns, nodes, P):
         self._ck(self.lib.vlc_lattice_targets_dev(self.h, nrows, ns, _ptr(nodes), _ptr(P)))

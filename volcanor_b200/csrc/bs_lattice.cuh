@@ -1,0 +1,172 @@
+// bs_lattice.cuh -- shared-node sweep over a vortex-ring LATTICE (near wake), the structured fast path of K1/K2.
+//
+// The reference enumerates a near wake ring by ring: 4 filaments per ring, every interior lattice edge twice (once
+// per adjacent ring, opposite directions), every node 8 times as a filament end point
+// (src/classdef.f90:1450-1456 -> vr_vind :527-542 -> vf_vind :476-503).  On a lattice the same sum can be
+// regrouped exactly:
+//   * per (target, NODE):  r = P - X,  u = 1/|r|                      -- once instead of 8 times
+//   * per (target, EDGE U->V) with merged strength g = (Gamma_a - Gamma_b)/4pi of the two rings that share it
+//     (the reversed copy of a filament induces exactly the negated velocity):
+//        c = rU x rV,  v += c * (g r0.rU * uU - g r0.rV * uV) / sqrt(K + |c|^4)
+// which is the reference formula with unitVec(r) = r*u.  A strip walk keeps the node quantities in registers:
+// a "ring-step record" (16 doubles) describes node A=(r,c), node B=(r,c+1), the spanwise edge A->B and the
+// streamwise edge A_prev->A (A_prev = node (r-1,c), the A of the previous record of the same strip).
+// Per record and target: 2 nodes (11 FP64 instr each) + 2 edges (25 each) = 72 FP64-pipe instructions for
+// 4 reference pair interactions = 18 per pair (the flat kernel needs 43).
+//
+// Merging needs both copies of an edge to carry the same core radius; pack_lattice_shared_kernel checks this
+// bitwise and raises a device flag otherwise, in which case this kernel returns immediately and the flat kernel
+// runs on the reference enumeration instead (capi.cu: sweep_shared) -- results never depend on the assumption.
+#pragma once
+#include "vlc_device.cuh"
+
+namespace vlc {
+
+// Ring-step record: 16 doubles = 128 B = 8 x 16 B.
+//   [0..2] A   [3..5] B   [6..8] gp*(B-A)  [9] gp*|B-A|^2  [10] Kp   [11..13] gs*(A-Aprev)  [14] gs*|A-Aprev|^2  [15] Ks
+constexpr int kLatDoubles = 16;
+constexpr int kLatBytes = kLatDoubles * 8;
+
+struct NodeQ {
+  double rx, ry, rz, u;  // r = P - X, u = 1/|r|
+};
+
+__device__ __forceinline__ NodeQ node_eval(double px, double py, double pz, double ax, double ay, double az) {
+  NodeQ n;
+  n.rx = px - ax;
+  n.ry = py - ay;
+  n.rz = pz - az;
+  const double d = fma(n.rz, n.rz, fma(n.ry, n.ry, n.rx * n.rx));
+  n.u = rsqrt_fp64<false>(d);  // d == 0 (target on the node) gives NaN; every edge that uses it has c == 0 and is guarded
+  return n;
+}
+
+// One (target, edge U->V) interaction: 25 FP64-pipe instructions.
+__device__ __forceinline__ void edge_accumulate(const NodeQ& a, const NodeQ& b, double gx, double gy, double gz,
+                                                double L2g, double K, double& vx, double& vy, double& vz) {
+  const double cx = fma(a.ry, b.rz, -(a.rz * b.ry));
+  const double cy = fma(a.rz, b.rx, -(a.rx * b.rz));
+  const double cz = fma(a.rx, b.ry, -(a.ry * b.rx));
+  const double c2 = fma(cz, cz, fma(cy, cy, cx * cx));
+  const double a1 = fma(gz, a.rz, fma(gy, a.ry, gx * a.rx));  // g r0.rU
+  const double a2 = a1 - L2g;                                  // g r0.rV
+  const double w = rsqrt_fp64<false>(fma(c2, c2, K));
+  double sc = fma(-a2, b.u, a1 * a.u) * w;
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.gt.s64 p, %1, 0x3970000000000000;\n\t"  // classdef.f90:498: c2 > eps^2 = 2^-104
+      "selp.f64 %0, %0, 0d0000000000000000, p;\n\t"
+      "}"
+      : "+d"(sc)
+      : "l"(__double_as_longlong(c2)));
+  vx = fma(cx, sc, vx);
+  vy = fma(cy, sc, vy);
+  vz = fma(cz, sc, vz);
+}
+
+template <int T, int THREADS, int TILE, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+bs_lattice_kernel(const double* __restrict__ lat,  // ring-step records, padded to a multiple of TILE
+                  long long chunk,                 // records per split (multiple of TILE)
+                  long long n_pad,                 // total padded records
+                  const double* __restrict__ P, long long m,
+                  double* __restrict__ out,        // [gridDim.y][3 m]
+                  const int* __restrict__ flag, int want) {
+  if (flag != nullptr && *flag != want) return;  // uniform: the set is not mergeable -> the flat kernel does the work
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* buf = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * kLatBytes);
+
+  const int tid = threadIdx.x;
+  const long long s_begin = (long long)blockIdx.y * chunk;
+  long long s_end = s_begin + chunk;
+  if (s_end > n_pad) s_end = n_pad;
+  const int ntiles = (s_end > s_begin) ? (int)((s_end - s_begin) / TILE) : 0;
+  const double* gsrc = lat + s_begin * kLatDoubles;
+  constexpr uint32_t kTileBytes = TILE * kLatBytes;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s)
+      if (s < ntiles) {
+        mbar_expect_tx(&bars[s], kTileBytes);
+        tma_bulk_g2s(buf + (size_t)s * TILE * kLatDoubles, gsrc + (size_t)s * TILE * kLatDoubles, kTileBytes, &bars[s]);
+      }
+  }
+
+  const long long t0 = (long long)blockIdx.x * (THREADS * T) + tid;
+  double px[T], py[T], pz[T], vx[T], vy[T], vz[T];
+  NodeQ prev[T];
+  // A_prev of the first record of this chunk = A of the record before it (same strip unless the record starts a
+  // strip, in which case its streamwise strength is 0 and any finite node will do).
+  const double* r0 = lat + (s_begin > 0 ? (s_begin - 1) : 0) * kLatDoubles;
+  const double ax0 = r0[0], ay0 = r0[1], az0 = r0[2];
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const long long t = t0 + (long long)k * THREADS;
+    const bool ok = t < m;
+    px[k] = ok ? P[3 * t + 0] : 0.0;
+    py[k] = ok ? P[3 * t + 1] : 0.0;
+    pz[k] = ok ? P[3 * t + 2] : 0.0;
+    vx[k] = vy[k] = vz[k] = 0.0;
+    prev[k] = node_eval(px[k], py[k], pz[k], ax0, ay0, az0);
+  }
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int stage = tile % STAGES;
+    const uint32_t phase = (uint32_t)(tile / STAGES) & 1u;
+    mbar_wait(&bars[stage], phase);
+    const double2* sb = reinterpret_cast<const double2*>(buf + (size_t)stage * TILE * kLatDoubles);
+#pragma unroll 2
+    for (int j = 0; j < TILE; ++j) {
+      const double2 q0 = sb[8 * j + 0], q1 = sb[8 * j + 1], q2 = sb[8 * j + 2], q3 = sb[8 * j + 3];
+      const double2 q4 = sb[8 * j + 4], q5 = sb[8 * j + 5], q6 = sb[8 * j + 6], q7 = sb[8 * j + 7];
+#pragma unroll
+      for (int k = 0; k < T; ++k) {
+        const NodeQ na = node_eval(px[k], py[k], pz[k], q0.x, q0.y, q1.x);
+        const NodeQ nb = node_eval(px[k], py[k], pz[k], q1.y, q2.x, q2.y);
+        edge_accumulate(prev[k], na, q5.y, q6.x, q6.y, q7.x, q7.y, vx[k], vy[k], vz[k]);  // streamwise A_prev -> A
+        edge_accumulate(na, nb, q3.x, q3.y, q4.x, q4.y, q5.x, vx[k], vy[k], vz[k]);       // spanwise   A -> B
+        prev[k] = na;
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && tile + STAGES < ntiles) {
+      mbar_expect_tx(&bars[stage], kTileBytes);
+      tma_bulk_g2s(buf + (size_t)stage * TILE * kLatDoubles, gsrc + (size_t)(tile + STAGES) * TILE * kLatDoubles,
+                   kTileBytes, &bars[stage]);
+    }
+  }
+
+  double* o = out + (size_t)blockIdx.y * 3 * (size_t)m;
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const long long t = t0 + (long long)k * THREADS;
+    if (t < m) {
+      o[3 * t + 0] = vx[k];
+      o[3 * t + 1] = vy[k];
+      o[3 * t + 2] = vz[k];
+    }
+  }
+}
+
+// Fixed-order sum of partial slots, selecting the slots of the path that actually ran:
+//   *flag == 0 -> slots [0, na)   (lattice + remainder kernels)      *flag != 0 -> slots [na, na+nb)  (flat fallback)
+__global__ void bs_reduce_select_kernel(const double* __restrict__ part, const int* __restrict__ flag, int na, int nb,
+                                        long long len, double* __restrict__ V) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const int first = (*flag == 0) ? 0 : na;
+  const int count = (*flag == 0) ? na : nb;
+  double a = 0.0;
+  for (int s = 0; s < count; ++s) a += part[(size_t)(first + s) * len + i];
+  V[i] = a;
+}
+
+}  // namespace vlc

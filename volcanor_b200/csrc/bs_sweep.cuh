@@ -21,8 +21,11 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
                 long long n_src_padded,           // total padded sources (multiple of TILE)
                 const double* __restrict__ P,     // targets (3, m) interleaved
                 long long m,
-                double* __restrict__ out)         // [gridDim.y][3 m]
+                double* __restrict__ out,         // [gridDim.y][3 m]
+                const int* __restrict__ flag,     // optional device flag: run only when *flag == want (capi.cu: sweep_shared)
+                int want)
 {
+  if (flag != nullptr && *flag != want) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * kSrcBytes);

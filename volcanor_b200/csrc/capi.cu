@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "bs_sweep.cuh"
+#include "bs_lattice.cuh"
 #include "pack.cuh"
 #include "wake_state.cuh"
 
@@ -23,6 +24,9 @@ namespace {
 constexpr int kThreads = 128;  // threads per sweep CTA
 constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
 constexpr int kStages = 3;     // TMA ring depth
+constexpr int kLatTile = 64;   // ring-step records per shared-memory tile of the lattice kernel (8 KB)
+constexpr int kLatT = 2;       // targets per thread of the lattice kernel
+constexpr int kLatMinB = 3;
 
 std::string g_create_error;
 
@@ -33,8 +37,15 @@ struct DevBuf {
 
 struct SourceSet {
   DevBuf rec;
-  long long n = 0;      // logical filaments
+  long long n = 0;      // logical filaments (reference enumeration)
   long long n_pad = 0;  // padded to kTile
+  // shared-node form of the same sources (tier 3 lattices, bs_lattice.cuh): strip records + flat remainder
+  DevBuf lat;
+  long long n_lat = 0, n_lat_pad = 0;  // ring-step records, padded to kLatTile
+  DevBuf rem;
+  long long n_rem = 0, n_rem_pad = 0;  // filaments no strip covers (last column, horseshoe, far chain)
+  int* d_unmergeable = nullptr;        // device flag raised by the pack kernels
+  bool has_shared = false;
 };
 
 struct Rotor {
@@ -69,6 +80,10 @@ struct vlc_ctx {
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   long long mem_bytes = 0;
   int tune_T = 0, tune_nsplit = 0;
+  bool shared_nodes = true;  // lattice sources: use the shared-node kernel when the set allows it
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // last sweep: before / after the dominant kernel, after the reduce
+  bool ev_valid = false;
+  int occ_lat = 0;
   bool fast = false;  // rsqrt refinement: false = third order (~1e-16), true = second order (~4e-14)
   long long launches = 0;
   SourceSet sets[VLC_MAX_SETS];
@@ -133,10 +148,10 @@ constexpr size_t kSweepSmem = (size_t)kStages * kTile * vlc::kSrcBytes + kStages
 
 template <int T, int MINB, bool FAST>
 int launch_sweep_T(vlc_ctx* c, const double* src, long long n_pad, long long chunk, int nsplit, long long m,
-                   const double* dP, double* out) {
+                   const double* dP, double* out, const int* flag, int want) {
   auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB, FAST>;
   dim3 grid(blocks_for(m, kThreads * T), (unsigned)nsplit, 1);
-  kern<<<grid, kThreads, kSweepSmem, c->stream>>>(src, chunk, n_pad, dP, m, out);
+  kern<<<grid, kThreads, kSweepSmem, c->stream>>>(src, chunk, n_pad, dP, m, out, flag, want);
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   return VLC_OK;
@@ -194,47 +209,137 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
   *nsplit_out = nsplit;
 }
 
-int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* dP, double* dV) {
-  if (m <= 0) return VLC_OK;
-  if (n_pad <= 0) {
-    CUDA_OK(c, cudaMemsetAsync(dV, 0, sizeof(double) * 3 * (size_t)m, c->stream));
-    return VLC_OK;
-  }
-  int T, nsplit;
-  choose_shape(c, m, n_pad, &T, &nsplit);
+struct FlatPlan {
+  int T = 4, nsplit = 1;
+  long long chunk = 0;
+};
+
+FlatPlan plan_flat(const vlc_ctx* c, long long m, long long n_pad) {
+  FlatPlan p;
+  choose_shape(c, m, n_pad, &p.T, &p.nsplit);
   const long long src_tiles = n_pad / kTile;
-  const long long chunk_tiles = (src_tiles + nsplit - 1) / nsplit;
-  nsplit = (int)((src_tiles + chunk_tiles - 1) / chunk_tiles);
-  const long long chunk = chunk_tiles * kTile;
-  double* out = dV;
-  if (nsplit > 1) {
-    int rc = reserve(c, c->part, (size_t)nsplit * 3 * (size_t)m);
-    if (rc) return rc;
-    out = c->part.p;
-  }
+  const long long chunk_tiles = (src_tiles + p.nsplit - 1) / p.nsplit;
+  p.nsplit = (int)((src_tiles + chunk_tiles - 1) / chunk_tiles);
+  p.chunk = chunk_tiles * kTile;
+  return p;
+}
+
+// out: [plan.nsplit][3 m] partial slots.  flag/want: optional device-side dispatch (see sweep_shared).
+int launch_flat(vlc_ctx* c, const double* src, long long n_pad, const FlatPlan& p, long long m, const double* dP,
+                double* out, const int* flag, int want) {
   int rc;
-#define VLC_SWEEP(TT, MB)                                                                        \
-  rc = c->fast ? launch_sweep_T<TT, MB, true>(c, src, n_pad, chunk, nsplit, m, dP, out)          \
-               : launch_sweep_T<TT, MB, false>(c, src, n_pad, chunk, nsplit, m, dP, out)
-  switch (T) {
+#define VLC_SWEEP(TT, MB)                                                                                    \
+  rc = c->fast ? launch_sweep_T<TT, MB, true>(c, src, n_pad, p.chunk, p.nsplit, m, dP, out, flag, want)      \
+               : launch_sweep_T<TT, MB, false>(c, src, n_pad, p.chunk, p.nsplit, m, dP, out, flag, want)
+  switch (p.T) {
     case 1: VLC_SWEEP(1, 5); break;
     case 2: VLC_SWEEP(2, 4); break;
     case 3: VLC_SWEEP(3, 3); break;
     default: VLC_SWEEP(4, 3); break;
   }
 #undef VLC_SWEEP
+  return rc;
+}
+
+int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* dP, double* dV) {
+  if (m <= 0) return VLC_OK;
+  if (n_pad <= 0) {
+    CUDA_OK(c, cudaMemsetAsync(dV, 0, sizeof(double) * 3 * (size_t)m, c->stream));
+    return VLC_OK;
+  }
+  const FlatPlan p = plan_flat(c, m, n_pad);
+  double* out = dV;
+  if (p.nsplit > 1) {
+    int rc = reserve(c, c->part, (size_t)p.nsplit * 3 * (size_t)m);
+    if (rc) return rc;
+    out = c->part.p;
+  }
+  cudaEventRecord(c->ev[0], c->stream);
+  int rc = launch_flat(c, src, n_pad, p, m, dP, out, nullptr, 0);
   if (rc) return rc;
-  if (nsplit > 1) {
+  cudaEventRecord(c->ev[1], c->stream);
+  if (p.nsplit > 1) {
     const long long len = 3 * m;
-    vlc::bs_reduce_kernel<<<blocks_for(len, 256), 256, 0, c->stream>>>(c->part.p, nsplit, len, dV);
+    vlc::bs_reduce_kernel<<<blocks_for(len, 256), 256, 0, c->stream>>>(c->part.p, p.nsplit, len, dV);
     CUDA_OK(c, cudaGetLastError());
     c->launches++;
   }
+  cudaEventRecord(c->ev[2], c->stream);
+  c->ev_valid = true;
+  return VLC_OK;
+}
+
+constexpr size_t kLatSmem = (size_t)kStages * kLatTile * vlc::kLatBytes + kStages * sizeof(uint64_t);
+
+// Source splits of the lattice kernel: whole waves of (SMs x resident CTAs), chunks of >= 4 tiles when possible.
+int plan_lattice_split(const vlc_ctx* c, long long m, long long n_lat_pad) {
+  if (c->tune_nsplit > 0) return c->tune_nsplit;
+  const long long tiles = n_lat_pad / kLatTile;
+  const long long ttiles = (m + (long long)kThreads * kLatT - 1) / ((long long)kThreads * kLatT);
+  const long long slots = (long long)c->sm_count * (c->occ_lat > 0 ? c->occ_lat : kLatMinB);
+  long long max_split = tiles / 4;
+  if (max_split < 1) max_split = 1;
+  if (max_split > 256) max_split = 256;
+  double best = -1.0;
+  int best_s = 1;
+  for (long long s = 1; s <= max_split; ++s) {
+    const long long chunk_tiles = (tiles + s - 1) / s;
+    const long long real_s = (tiles + chunk_tiles - 1) / chunk_tiles;
+    const double waves = (double)ttiles * (double)real_s / (double)slots;
+    const double eff = waves / (double)(long long)(waves + 0.999999);
+    const double score = (waves >= 1.0) ? eff - 1e-4 * (double)s : eff;
+    if (score > best + 1e-9) {
+      best = score;
+      best_s = (int)s;
+    }
+    if (waves >= 8.0 && eff > 0.97) break;
+  }
+  return best_s;
+}
+
+// Sweep over a set that also holds the shared-node form.  Three launches, dispatched ON THE DEVICE by the set's
+// mergeability flag so that no host synchronisation is needed: lattice strips + flat remainder run when the flag
+// is 0, the flat kernel over the reference enumeration runs when it is 1; bs_reduce_select_kernel sums the slots
+// of whichever path ran, in fixed order.
+int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, double* dV) {
+  if (m <= 0) return VLC_OK;
+  const long long lat_tiles = s.n_lat_pad / kLatTile;
+  int ns_l = plan_lattice_split(c, m, s.n_lat_pad);
+  const long long lat_chunk_tiles = (lat_tiles + ns_l - 1) / ns_l;
+  ns_l = (int)((lat_tiles + lat_chunk_tiles - 1) / lat_chunk_tiles);
+  const FlatPlan pr = s.n_rem_pad > 0 ? plan_flat(c, m, s.n_rem_pad) : FlatPlan();
+  const FlatPlan pf = plan_flat(c, m, s.n_pad);
+  const int ns_r = s.n_rem_pad > 0 ? pr.nsplit : 0;
+  const size_t len = 3 * (size_t)m;
+  int rc = reserve(c, c->part, (size_t)(ns_l + ns_r + pf.nsplit) * len);
+  if (rc) return rc;
+  double* part = c->part.p;
+  cudaEventRecord(c->ev[0], c->stream);
+  {
+    auto kern = vlc::bs_lattice_kernel<kLatT, kThreads, kLatTile, kStages, kLatMinB>;
+    dim3 grid(blocks_for(m, kThreads * kLatT), (unsigned)ns_l, 1);
+    kern<<<grid, kThreads, kLatSmem, c->stream>>>(s.lat.p, lat_chunk_tiles * kLatTile, s.n_lat_pad, dP, m, part,
+                                                  s.d_unmergeable, 0);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  cudaEventRecord(c->ev[1], c->stream);
+  if (ns_r > 0 && (rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part + (size_t)ns_l * len, s.d_unmergeable, 0)))
+    return rc;
+  if ((rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part + (size_t)(ns_l + ns_r) * len, s.d_unmergeable, 1)))
+    return rc;
+  vlc::bs_reduce_select_kernel<<<blocks_for((long long)len, 256), 256, 0, c->stream>>>(
+      part, s.d_unmergeable, ns_l + ns_r, pf.nsplit, (long long)len, dV);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  cudaEventRecord(c->ev[2], c->stream);
+  c->ev_valid = true;
   return VLC_OK;
 }
 
 // host-buffer sweep: H2D targets, sweep, D2H velocities (synchronous)
-int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* P, double* V) {
+int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* P, double* V,
+               const SourceSet* shared = nullptr) {
   if (m <= 0) return VLC_OK;
   if (!P || !V) return fail(c, VLC_ERR_ARG, "null target / output pointer");
   int rc = reserve(c, c->stage_P, 3 * (size_t)m);
@@ -242,7 +347,7 @@ int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, cons
   rc = reserve(c, c->stage_V, 3 * (size_t)m);
   if (rc) return rc;
   CUDA_OK(c, cudaMemcpyAsync(c->stage_P.p, P, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
-  rc = sweep(c, src, n_pad, m, c->stage_P.p, c->stage_V.p);
+  rc = shared ? sweep_shared(c, *shared, m, c->stage_P.p, c->stage_V.p) : sweep(c, src, n_pad, m, c->stage_P.p, c->stage_V.p);
   if (rc) return rc;
   CUDA_OK(c, cudaMemcpyAsync(V, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -424,11 +529,18 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
     return VLC_ERR_CUDA;
   }
   c->stream = c->own_stream;
+  for (auto& e : c->ev) cudaEventCreate(&e);
   int rc = 0;
   rc |= query_occ<1, 5>(c, &c->occ[1]);
   rc |= query_occ<2, 4>(c, &c->occ[2]);
   rc |= query_occ<3, 3>(c, &c->occ[3]);
   rc |= query_occ<4, 3>(c, &c->occ[4]);
+  {
+    auto kern = vlc::bs_lattice_kernel<kLatT, kThreads, kLatTile, kStages, kLatMinB>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lat, kern, kThreads, kLatSmem) != cudaSuccess)
+      rc |= 1;
+  }
   if (rc) {
     g_create_error = "sweep kernel not loadable on this device: " + c->err;
     cudaStreamDestroy(c->own_stream);
@@ -443,7 +555,12 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   if (!c) return VLC_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (auto& s : c->sets) release(s.rec);
+  for (auto& s : c->sets) {
+    release(s.rec);
+    release(s.lat);
+    release(s.rem);
+    if (s.d_unmergeable) cudaFree(s.d_unmergeable);
+  }
   release(c->part);
   release(c->stage_P);
   release(c->stage_V);
@@ -464,6 +581,8 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     if (r.d_info) cudaFree(r.d_info);
   }
   if (c->solver) cusolverDnDestroy(c->solver);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return VLC_OK;
@@ -534,6 +653,8 @@ extern "C" int vlc_set_sources_dev(vlc_ctx* c, int set, int64_t n, const double*
   }
   s.n = n;
   s.n_pad = n_pad;
+  s.has_shared = false;
+  s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = 0;
   return VLC_OK;
 }
 
@@ -585,7 +706,9 @@ extern "C" int vlc_vind_dev(vlc_ctx* c, int set, int64_t m, const double* dP, do
   if ((rc = check_set(c, set))) return rc;
   if (m < 0) return fail(c, VLC_ERR_ARG, "m < 0");
   if (m > 0 && (!dP || !dV)) return fail(c, VLC_ERR_ARG, "null target / output pointer");
-  return sweep(c, c->sets[set].rec.p, c->sets[set].n_pad, m, dP, dV);
+  const SourceSet& s = c->sets[set];
+  if (s.has_shared && c->shared_nodes && s.n_lat_pad > 0) return sweep_shared(c, s, m, dP, dV);
+  return sweep(c, s.rec.p, s.n_pad, m, dP, dV);
 }
 
 extern "C" int vlc_vind_range_dev(vlc_ctx* c, int set, int64_t first, int64_t count, int64_t m, const double* dP,
@@ -611,7 +734,9 @@ extern "C" int vlc_vind(vlc_ctx* c, int set, int64_t m, const double* P, double*
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
   if (m < 0) return fail(c, VLC_ERR_ARG, "m < 0");
-  return sweep_host(c, c->sets[set].rec.p, c->sets[set].n_pad, m, P, V);
+  const SourceSet& s = c->sets[set];
+  const bool sh = s.has_shared && c->shared_nodes && s.n_lat_pad > 0;
+  return sweep_host(c, s.rec.p, s.n_pad, m, P, V, sh ? &s : nullptr);
 }
 
 // ============================================================================ tier 2
@@ -1021,6 +1146,130 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
     LAUNCH1D(c, vlc::pack_null_kernel, n_pad - n_new, n_pad - n_new, s.rec.p + (size_t)n_new * vlc::kSrcDoubles);
   s.n = n_new;
   s.n_pad = n_pad;
+
+  // ---- shared-node form of the same lattice: strip records + flat remainder (bs_lattice.cuh) ----
+  if (!append) {
+    s.n_lat = s.n_rem = 0;
+    s.has_shared = true;
+    if (!s.d_unmergeable) CUDA_OK(c, cudaMalloc(&s.d_unmergeable, sizeof(int)));
+    CUDA_OK(c, cudaMemsetAsync(s.d_unmergeable, 0, sizeof(int), c->stream));
+  }
+  if (!s.has_shared) return VLC_OK;  // appended to a set that was not started by a lattice: flat form only
+  auto grow_keep = [&](DevBuf& b, size_t keep, size_t need) -> int {
+    if (need <= b.cap) return VLC_OK;
+    DevBuf nb;
+    int r2 = reserve(c, nb, need * 2);
+    if (r2) return r2;
+    if (keep > 0) CUDA_OK(c, cudaMemcpyAsync(nb.p, b.p, sizeof(double) * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    release(b);
+    b = nb;
+    return VLC_OK;
+  };
+  const long long lat_add = nrows > 0 ? (long long)ns * (nrows + 1) : 0;
+  const long long lat_new = s.n_lat + lat_add;
+  const long long lat_pad = (lat_new + kLatTile - 1) / kLatTile * kLatTile;
+  const long long rem_add = (nrows > 0 ? nrows : 0) + (nfar > 0 ? ns + nfar : 0);
+  const long long rem_new = s.n_rem + rem_add;
+  const long long rem_pad = pad_tile(rem_new);
+  if ((rc = grow_keep(s.lat, (size_t)s.n_lat * vlc::kLatDoubles, (size_t)lat_pad * vlc::kLatDoubles))) return rc;
+  if ((rc = grow_keep(s.rem, (size_t)s.n_rem * vlc::kSrcDoubles, (size_t)rem_pad * vlc::kSrcDoubles))) return rc;
+  if (nrows > 0) {
+    LAUNCH1D(c, vlc::pack_lattice_shared_kernel, lat_add, nrows, ns, nodes, gam, rvc4,
+             s.lat.p + (size_t)s.n_lat * vlc::kLatDoubles, s.d_unmergeable);
+    double* rrec = s.rem.p + (size_t)s.n_rem * vlc::kSrcDoubles;
+    LAUNCH1D(c, vlc::pack_lastcol_kernel, (long long)nrows, nrows, ns, nodes, gam, rvc4, rrec);
+    long long roff = nrows;
+    if (nfar > 0) {
+      LAUNCH1D(c, vlc::pack_horseshoe_kernel, (long long)ns, nrows, ns, nodes, gam, rvc4,
+               rrec + (size_t)roff * vlc::kSrcDoubles);
+      roff += ns;
+      LAUNCH1D(c, vlc::pack_chain_kernel, (long long)nfar, nfar, far_nodes, gamF, rvcF,
+               rrec + (size_t)roff * vlc::kSrcDoubles);
+    }
+  }
+  if (lat_pad > lat_new)
+    LAUNCH1D(c, vlc::pack_null_lat_kernel, lat_pad - lat_new, lat_pad - lat_new,
+             s.lat.p + (size_t)lat_new * vlc::kLatDoubles);
+  if (rem_pad > rem_new)
+    LAUNCH1D(c, vlc::pack_null_kernel, rem_pad - rem_new, rem_pad - rem_new, s.rem.p + (size_t)rem_new * vlc::kSrcDoubles);
+  s.n_lat = lat_new;
+  s.n_lat_pad = lat_pad;
+  s.n_rem = rem_new;
+  s.n_rem_pad = rem_pad;
+  return VLC_OK;
+}
+
+extern "C" int vlc_pack_lattice(vlc_ctx* c, int set, int append, int nrows, int ns, const double* nodes,
+                                const double* gam, const double* rvc4, int nfar, const double* far_nodes,
+                                const double* gamF, const double* rvcF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (nrows < 0 || ns < 1 || nfar < 0) return fail(c, VLC_ERR_ARG, "bad lattice shape");
+  if (nrows > 0 && (!nodes || !gam || !rvc4)) return fail(c, VLC_ERR_ARG, "null lattice array");
+  if (nfar > 0 && (!far_nodes || !gamF || !rvcF)) return fail(c, VLC_ERR_ARG, "null far-wake array");
+  const size_t n_nodes = 3 * (size_t)(nrows + 1) * (ns + 1), n_g = (size_t)nrows * ns, n_r = 4 * n_g;
+  const size_t n_fn = nfar > 0 ? 3 * (size_t)(nfar + 1) : 0, n_f = (size_t)nfar;
+  if ((rc = reserve(c, c->scratch, n_nodes + n_g + n_r + n_fn + 2 * n_f + 8))) return rc;
+  double* d = c->scratch.p;
+  double *d_nodes = d, *d_gam = d_nodes + n_nodes, *d_rvc = d_gam + n_g, *d_fn = d_rvc + n_r, *d_gF = d_fn + n_fn,
+         *d_rF = d_gF + n_f;
+  cudaStream_t st = c->stream;
+  if (nrows > 0) {
+    CUDA_OK(c, cudaMemcpyAsync(d_nodes, nodes, sizeof(double) * n_nodes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(d_gam, gam, sizeof(double) * n_g, cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(d_rvc, rvc4, sizeof(double) * n_r, cudaMemcpyHostToDevice, st));
+  }
+  if (nfar > 0) {
+    CUDA_OK(c, cudaMemcpyAsync(d_fn, far_nodes, sizeof(double) * n_fn, cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(d_gF, gamF, sizeof(double) * n_f, cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(d_rF, rvcF, sizeof(double) * n_f, cudaMemcpyHostToDevice, st));
+  }
+  rc = vlc_pack_lattice_dev(c, set, append, nrows, ns, d_nodes, d_gam, d_rvc, nfar, nfar > 0 ? d_fn : nullptr,
+                            nfar > 0 ? d_gF : nullptr, nfar > 0 ? d_rF : nullptr);
+  if (rc) return rc;
+  CUDA_OK(c, cudaStreamSynchronize(st));  // the scratch buffer is reused by the next call
+  return VLC_OK;
+}
+
+extern "C" int vlc_set_info(vlc_ctx* c, int set, int64_t* out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if ((rc = check_set(c, set))) return rc;
+  if (!out) return fail(c, VLC_ERR_ARG, "null pointer");
+  const SourceSet& s = c->sets[set];
+  out[0] = s.n;
+  out[1] = s.has_shared ? s.n_lat : 0;
+  out[2] = s.has_shared ? s.n_rem : 0;
+  out[3] = -1;
+  if (s.has_shared && s.d_unmergeable) {
+    int f = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&f, s.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    out[3] = (f == 0 && c->shared_nodes) ? 1 : 0;
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_last_sweep_ms(vlc_ctx* c, double* ms_kernel, double* ms_total) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (!c->ev_valid) return fail(c, VLC_ERR_STATE, "no sweep has been launched yet");
+  CUDA_OK(c, cudaEventSynchronize(c->ev[2]));
+  float a = 0.f, b = 0.f;
+  CUDA_OK(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+  CUDA_OK(c, cudaEventElapsedTime(&b, c->ev[0], c->ev[2]));
+  if (ms_kernel) *ms_kernel = a;
+  if (ms_total) *ms_total = b;
+  return VLC_OK;
+}
+
+extern "C" int vlc_set_shared_nodes(vlc_ctx* c, int on) {
+  CHECK_CTX(c);
+  c->shared_nodes = (on != 0);
   return VLC_OK;
 }
 

@@ -177,4 +177,88 @@ __global__ void pack_chain_kernel(int nfar, const double* __restrict__ p, const 
   write_rec(rec + (size_t)i * kSrcDoubles, a[0], a[1], a[2], b[0], b[1], b[2], rvcF[i], strength(gamF[i], true));
 }
 
+
+// ---- tier 3, shared-node form (bs_lattice.cuh) ------------------------------------------------
+// Ring-step records of one lattice: strip c = 0..ns-1 (columns c, c+1), node rows rr = 0..nrows, record index
+// c*(nrows+1) + rr.  Merged edge strengths (Gamma' = Gamma or 0 under the wake rule |Gamma| > eps, classdef.f90:1452):
+//   spanwise   (rr,c)->(rr,c+1): Gamma'(rr-1,c) - Gamma'(rr,c)     [f2 of ring (rr-1,c), reversed f4 of ring (rr,c)]
+//   streamwise (rr-1,c)->(rr,c): Gamma'(rr-1,c) - Gamma'(rr-1,c-1) [f1 of ring (rr-1,c), reversed f3 of ring (rr-1,c-1)]
+// with Gamma' = 0 outside the lattice.  *unmergeable is set when the two copies of a shared edge carry different
+// core radii (possible with a non-uniform streamwiseCoreVec): the sweep then uses the flat records.
+__device__ __forceinline__ void write_lat_rec(double* __restrict__ rec, const double* A, const double* B,
+                                              const double* Ap, double gp, double rvcp, double gs, double rvcs) {
+  const double px = B[0] - A[0], py = B[1] - A[1], pz = B[2] - A[2];
+  const double Lp = fma(pz, pz, fma(py, py, px * px));
+  const double qp = rvcp * rvcp * Lp;
+  const double sx = A[0] - Ap[0], sy = A[1] - Ap[1], sz = A[2] - Ap[2];
+  const double Ls = fma(sz, sz, fma(sy, sy, sx * sx));
+  const double qs = rvcs * rvcs * Ls;
+  double2* o = reinterpret_cast<double2*>(rec);
+  o[0] = make_double2(A[0], A[1]);
+  o[1] = make_double2(A[2], B[0]);
+  o[2] = make_double2(B[1], B[2]);
+  o[3] = make_double2(gp * px, gp * py);
+  o[4] = make_double2(gp * pz, gp * Lp);
+  o[5] = make_double2(qp * qp, gs * sx);
+  o[6] = make_double2(gs * sy, gs * sz);
+  o[7] = make_double2(gs * Ls, qs * qs);
+}
+
+__global__ void pack_null_lat_kernel(long long count, double* __restrict__ rec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double2* o = reinterpret_cast<double2*>(rec + i * 16);
+  const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = z;
+  o[1] = make_double2(0.0, 1.0);  // B = (1,0,0) != A: a well-formed edge of zero strength
+}
+
+__global__ void pack_lattice_shared_kernel(int nrows, int ns, const double* __restrict__ nodes,
+                                           const double* __restrict__ gam, const double* __restrict__ rvc4,
+                                           double* __restrict__ rec, int* __restrict__ unmergeable) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nr1 = nrows + 1;
+  if (q >= (long long)ns * nr1) return;
+  const int rr = (int)(q % nr1), c = (int)(q / nr1);
+  const double* A = nodes + 3 * ((size_t)rr + (size_t)nr1 * c);
+  const double* B = nodes + 3 * ((size_t)rr + (size_t)nr1 * (c + 1));
+  const double* Ap = (rr > 0) ? A - 3 : A;
+  auto G = [&](int r, int j) -> double {
+    return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(gam[(size_t)r + (size_t)nrows * j], true) : 0.0;
+  };
+  auto RV = [&](int r, int j, int f) -> double { return rvc4[4 * ((size_t)r + (size_t)nrows * j) + f]; };
+  // spanwise edge of node row rr
+  const double gp = G(rr - 1, c) - G(rr, c);
+  double rvcp;
+  if (rr >= 1) {
+    rvcp = RV(rr - 1, c, 1);
+    if (rr < nrows && RV(rr, c, 3) != rvcp) *unmergeable = 1;
+  } else {
+    rvcp = RV(0, c, 3);
+  }
+  // streamwise edge (rr-1,c) -> (rr,c)
+  double gs = 0.0, rvcs = 0.0;
+  if (rr >= 1) {
+    gs = G(rr - 1, c) - G(rr - 1, c - 1);
+    rvcs = RV(rr - 1, c, 0);
+    if (c >= 1 && RV(rr - 1, c - 1, 2) != rvcs) *unmergeable = 1;
+  }
+  write_lat_rec(rec + q * 16, A, B, Ap, gp, rvcp, gs, rvcs);
+}
+
+// Streamwise edges of the last column (f3 of ring (r, ns-1): corner 3 -> corner 4), which no strip covers.
+__global__ void pack_lastcol_kernel(int nrows, int ns, const double* __restrict__ nodes,
+                                    const double* __restrict__ gam, const double* __restrict__ rvc4,
+                                    double* __restrict__ rec) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int nr1 = nrows + 1;
+  const double* a = nodes + 3 * ((size_t)(r + 1) + (size_t)nr1 * ns);
+  const double* b = nodes + 3 * ((size_t)r + (size_t)nr1 * ns);
+  const size_t ring = (size_t)r + (size_t)nrows * (ns - 1);
+  write_rec(rec + (size_t)r * kSrcDoubles, a[0], a[1], a[2], b[0], b[1], b[2], rvc4[4 * ring + 2],
+            strength(gam[ring], true));
+}
+
 }  // namespace vlc
