@@ -153,3 +153,47 @@ def test_lattice_state_kernels_vs_oracle(ctx, oracle):
     ctx.am2_dev(50, dv, dv1, out)
     ctx.sync()
     assert np.array_equal(out.cpu().numpy(), (v + v1) * 0.5)
+
+
+# ------------------------------------------------------------------ tier 2: reference records -> shared-node form
+
+def test_rotor_records_shared_and_flat_forms_agree_with_oracle(ctx, oracle):
+    """vlc_rotor_vind_bywake / vlc_rotor_vind on uploaded waN records use the shared-node form when the records
+    describe a lattice (they do after blade_wake_continuity); both forms must match the oracle."""
+    from tests.test_gpu_parity import _make_rotor_pair, _tol_scale
+    P = np.random.default_rng(3).uniform(-1.5, 1.5, size=(300, 3))
+    for rows in ((1, 1), (3, 2), (7, 5)):
+        ro = _make_rotor_pair(ctx, oracle, seed=6, nNwake=7, nFwake=4, rowNear=rows[0], rowFar=rows[1])
+        s = _tol_scale(ro, P) * 50
+        res = {}
+        for shared in (True, False):
+            ctx.set_shared_nodes(shared)
+            try:
+                res[shared] = (ctx.rotor_vind_bywake(0, P), ctx.rotor_vind_bywake(0, P, True), ctx.rotor_vind(0, P))
+            finally:
+                ctx.set_shared_nodes(True)
+            assert np.max(np.abs(res[shared][0] - ro.vind_points(1, P))) < TOL * s
+            assert np.max(np.abs(res[shared][1] - ro.vind_points(1, P, True))) < TOL * s
+            assert np.max(np.abs(res[shared][2] - ro.vind_points(2, P))) < TOL * s
+        if rows[0] < 7:
+            assert not np.array_equal(res[True][0], res[False][0])     # really two different kernels
+
+
+def test_rotor_records_that_are_not_a_lattice_fall_back(ctx, oracle):
+    """One corner copy moved: the records no longer describe a lattice, the reference (and the oracle) still sum
+    them filament by filament; the device detects the mismatch and uses the flat enumeration."""
+    from tests.test_gpu_parity import _make_rotor_pair, _tol_scale
+    ro = _make_rotor_pair(ctx, oracle, seed=12, nNwake=6, nFwake=3, rowNear=2, rowFar=2)
+    w = ro.waN(0)
+    w[2, 3, 12 * 1 + 0] += 1e-3          # vf(2)%fc(1,1) of ring (row 4, col 3) only: breaks continuity with vf(1)%fc(:,2)
+    ctx.rotor_put_nwake(0, 0, w)
+    P = np.random.default_rng(4).uniform(-1.5, 1.5, size=(100, 3))
+    s = _tol_scale(ro, P) * 50
+    Va = ctx.rotor_vind_bywake(0, P)
+    ctx.set_shared_nodes(False)
+    try:
+        Vb = ctx.rotor_vind_bywake(0, P)
+    finally:
+        ctx.set_shared_nodes(True)
+    assert np.max(np.abs(Va - ro.vind_points(1, P))) < TOL * s
+    assert np.array_equal(Va, Vb)

@@ -25,8 +25,7 @@ constexpr int kThreads = 128;  // threads per sweep CTA
 constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
 constexpr int kStages = 3;     // TMA ring depth
 constexpr int kLatTile = 64;   // ring-step records per shared-memory tile of the lattice kernel (8 KB)
-constexpr int kLatT = 2;       // targets per thread of the lattice kernel
-constexpr int kLatMinB = 3;
+constexpr int kLatT = 2;       // default targets per thread of the lattice kernel (vlc_set_tuning: 1..3)
 
 std::string g_create_error;
 
@@ -83,7 +82,7 @@ struct vlc_ctx {
   bool shared_nodes = true;  // lattice sources: use the shared-node kernel when the set allows it
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // last sweep: before / after the dominant kernel, after the reduce
   bool ev_valid = false;
-  int occ_lat = 0;
+  int occ_lat[4] = {0, 0, 0, 0};  // resident CTAs/SM of the lattice kernel for T = 1..3
   bool fast = false;  // rsqrt refinement: false = third order (~1e-16), true = second order (~4e-14)
   long long launches = 0;
   SourceSet sets[VLC_MAX_SETS];
@@ -271,12 +270,20 @@ int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const dou
 
 constexpr size_t kLatSmem = (size_t)kStages * kLatTile * vlc::kLatBytes + kStages * sizeof(uint64_t);
 
+template <int T, int MINB>
+int query_occ_lat(vlc_ctx* c, int* out) {
+  auto kern = vlc::bs_lattice_kernel<T, kThreads, kLatTile, kStages, MINB>;
+  CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+  CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, kThreads, kLatSmem));
+  return VLC_OK;
+}
+
 // Source splits of the lattice kernel: whole waves of (SMs x resident CTAs), chunks of >= 4 tiles when possible.
-int plan_lattice_split(const vlc_ctx* c, long long m, long long n_lat_pad) {
+int plan_lattice_split(const vlc_ctx* c, int T, long long m, long long n_lat_pad) {
   if (c->tune_nsplit > 0) return c->tune_nsplit;
   const long long tiles = n_lat_pad / kLatTile;
-  const long long ttiles = (m + (long long)kThreads * kLatT - 1) / ((long long)kThreads * kLatT);
-  const long long slots = (long long)c->sm_count * (c->occ_lat > 0 ? c->occ_lat : kLatMinB);
+  const long long ttiles = (m + (long long)kThreads * T - 1) / ((long long)kThreads * T);
+  const long long slots = (long long)c->sm_count * (c->occ_lat[T] > 0 ? c->occ_lat[T] : 3);
   long long max_split = tiles / 4;
   if (max_split < 1) max_split = 1;
   if (max_split > 256) max_split = 256;
@@ -304,7 +311,9 @@ int plan_lattice_split(const vlc_ctx* c, long long m, long long n_lat_pad) {
 int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, double* dV) {
   if (m <= 0) return VLC_OK;
   const long long lat_tiles = s.n_lat_pad / kLatTile;
-  int ns_l = plan_lattice_split(c, m, s.n_lat_pad);
+  int LT = (c->tune_T >= 1 && c->tune_T <= 3) ? c->tune_T : kLatT;
+  if (c->tune_T == 0 && m <= kThreads) LT = 1;
+  int ns_l = plan_lattice_split(c, LT, m, s.n_lat_pad);
   const long long lat_chunk_tiles = (lat_tiles + ns_l - 1) / ns_l;
   ns_l = (int)((lat_tiles + lat_chunk_tiles - 1) / lat_chunk_tiles);
   const FlatPlan pr = s.n_rem_pad > 0 ? plan_flat(c, m, s.n_rem_pad) : FlatPlan();
@@ -316,10 +325,16 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   double* part = c->part.p;
   cudaEventRecord(c->ev[0], c->stream);
   {
-    auto kern = vlc::bs_lattice_kernel<kLatT, kThreads, kLatTile, kStages, kLatMinB>;
-    dim3 grid(blocks_for(m, kThreads * kLatT), (unsigned)ns_l, 1);
-    kern<<<grid, kThreads, kLatSmem, c->stream>>>(s.lat.p, lat_chunk_tiles * kLatTile, s.n_lat_pad, dP, m, part,
-                                                  s.d_unmergeable, 0);
+    dim3 grid(blocks_for(m, kThreads * LT), (unsigned)ns_l, 1);
+#define VLC_LAT(TT, MB)                                                                                             \
+  vlc::bs_lattice_kernel<TT, kThreads, kLatTile, kStages, MB><<<grid, kThreads, kLatSmem, c->stream>>>(             \
+      s.lat.p, lat_chunk_tiles * kLatTile, s.n_lat_pad, dP, m, part, s.d_unmergeable, 0)
+    switch (LT) {
+      case 1: VLC_LAT(1, 6); break;
+      case 3: VLC_LAT(3, 2); break;
+      default: VLC_LAT(2, 4); break;
+    }
+#undef VLC_LAT
     CUDA_OK(c, cudaGetLastError());
     c->launches++;
   }
@@ -441,7 +456,89 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   r.wing_pad[s] = wing_pad;
   r.wing_n = wing_n;
   r.dirty[s] = false;
+
+  // ---- shared-node form of the near wake (bs_lattice.cuh): strips per blade + [wing | remainder] flat ----
+  SourceSet& cs = r.comb[s];
+  cs.has_shared = false;
+  cs.n_lat = cs.n_lat_pad = cs.n_rem = cs.n_rem_pad = 0;
+  if (nrows > 0 && c->shared_nodes) {
+    const long long lat_n = (long long)r.nb * r.ns * (nrows + 1);
+    const long long lat_pad = (lat_n + kLatTile - 1) / kLatTile * kLatTile;
+    long long rem_per_blade = nrows;  // streamwise edges of the last column
+    if (has_far) rem_per_blade += r.ns + nfar + (r.have_pf[s] ? VLC_NPFWAKE : 0);
+    const long long rem_wake = rem_per_blade * r.nb;
+    const long long rem_pad = wing_pad + pad_tile(rem_wake);
+    if ((rc = reserve(c, cs.lat, (size_t)lat_pad * vlc::kLatDoubles))) return rc;
+    if ((rc = reserve(c, cs.rem, (size_t)rem_pad * vlc::kSrcDoubles))) return rc;
+    if (!cs.d_unmergeable) CUDA_OK(c, cudaMalloc(&cs.d_unmergeable, sizeof(int)));
+    CUDA_OK(c, cudaMemsetAsync(cs.d_unmergeable, 0, sizeof(int), st));
+    if (wing_pad > 0)
+      CUDA_OK(c, cudaMemcpyAsync(cs.rem.p, rec, sizeof(double) * (size_t)wing_pad * vlc::kSrcDoubles,
+                                 cudaMemcpyDeviceToDevice, st));
+    double* rrec = cs.rem.p + (size_t)wing_pad * vlc::kSrcDoubles;
+    long long roff = 0;
+    for (int ib = 0; ib < r.nb; ++ib) {
+      const double* waN = r.waN[s].p + (size_t)ib * r.nNwake * r.ns * vlc::kVr;
+      const long long nring = (long long)nrows * r.ns, nrec = (long long)r.ns * (nrows + 1);
+      vlc::check_rings_kernel<<<blocks_for(nring, 256), 256, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns,
+                                                                      cs.d_unmergeable);
+      vlc::pack_rings_shared_kernel<<<blocks_for(nrec, 256), 256, 0, st>>>(
+          waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, cs.lat.p + (size_t)ib * nrec * vlc::kLatDoubles,
+          cs.d_unmergeable);
+      // last column: f3 of ring (i, ns-1), wake rule applies (classdef.f90:1452)
+      vlc::pack_rings_kernel<<<blocks_for(nrows, 128), 128, 0, st>>>(
+          waN + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr, r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1,
+          rrec + (size_t)roff * vlc::kSrcDoubles);
+      roff += nrows;
+      c->launches += 3;
+      if (has_far) {
+        vlc::pack_rings_kernel<<<blocks_for(r.ns, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2,
+                                                                       1, -1.0, 0, rrec + (size_t)roff * vlc::kSrcDoubles);
+        roff += r.ns;
+        vlc::pack_fwake_kernel<<<blocks_for(nfar, 128), 128, 0, st>>>(r.waF[s].p + (size_t)ib * r.nFwake * vlc::kFw,
+                                                                       r.rowFar - 1, nfar,
+                                                                       rrec + (size_t)roff * vlc::kSrcDoubles);
+        roff += nfar;
+        c->launches += 2;
+        if (r.have_pf[s]) {
+          vlc::pack_fwake_kernel<<<blocks_for(VLC_NPFWAKE, 128), 128, 0, st>>>(
+              r.wapF[s].p + (size_t)ib * VLC_NPFWAKE * vlc::kFw, 0, VLC_NPFWAKE, rrec + (size_t)roff * vlc::kSrcDoubles);
+          roff += VLC_NPFWAKE;
+          c->launches++;
+        }
+      }
+    }
+    if (lat_pad > lat_n) {
+      vlc::pack_null_lat_kernel<<<blocks_for(lat_pad - lat_n, 256), 256, 0, st>>>(
+          lat_pad - lat_n, cs.lat.p + (size_t)lat_n * vlc::kLatDoubles);
+      c->launches++;
+    }
+    if (pad_tile(rem_wake) > roff) {
+      vlc::pack_null_kernel<<<blocks_for(pad_tile(rem_wake) - roff, 256), 256, 0, st>>>(
+          pad_tile(rem_wake) - roff, rrec + (size_t)roff * vlc::kSrcDoubles);
+      c->launches++;
+    }
+    CUDA_OK(c, cudaGetLastError());
+    cs.n_lat = lat_n;
+    cs.n_lat_pad = lat_pad;
+    cs.n_rem = wing_n + rem_wake;
+    cs.n_rem_pad = rem_pad;
+    cs.has_shared = true;
+  }
   return VLC_OK;
+}
+
+// View of a rotor's packed set without its wing segment (vind_bywake).
+SourceSet wake_view(const Rotor& r, int s) {
+  SourceSet v = r.comb[s];  // shallow: buffers stay owned by the rotor
+  const size_t off = (size_t)r.wing_pad[s] * vlc::kSrcDoubles;
+  v.rec.p = r.comb[s].rec.p + off;
+  v.n_pad = r.comb[s].n_pad - r.wing_pad[s];
+  if (v.has_shared) {
+    v.rem.p = r.comb[s].rem.p + off;
+    v.n_rem_pad = r.comb[s].n_rem_pad - r.wing_pad[s];
+  }
+  return v;
 }
 
 // bound-vortex set (classdef.f90:1376-1396): (vf2 + vf4)*gam of every ring, minus vf2*gam of row nc.
@@ -535,12 +632,9 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
   rc |= query_occ<2, 4>(c, &c->occ[2]);
   rc |= query_occ<3, 3>(c, &c->occ[3]);
   rc |= query_occ<4, 3>(c, &c->occ[4]);
-  {
-    auto kern = vlc::bs_lattice_kernel<kLatT, kThreads, kLatTile, kStages, kLatMinB>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lat, kern, kThreads, kLatSmem) != cudaSuccess)
-      rc |= 1;
-  }
+  rc |= query_occ_lat<1, 6>(c, &c->occ_lat[1]);
+  rc |= query_occ_lat<2, 4>(c, &c->occ_lat[2]);
+  rc |= query_occ_lat<3, 2>(c, &c->occ_lat[3]);
   if (rc) {
     g_create_error = "sweep kernel not loadable on this device: " + c->err;
     cudaStreamDestroy(c->own_stream);
@@ -574,6 +668,9 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
       release(r.waF[s]);
       release(r.wapF[s]);
       release(r.comb[s].rec);
+      release(r.comb[s].lat);
+      release(r.comb[s].rem);
+      if (r.comb[s].d_unmergeable) cudaFree(r.comb[s].d_unmergeable);
     }
     release(r.bound.rec);
     release(r.LU);
@@ -883,8 +980,8 @@ extern "C" int vlc_rotor_vind_bywake(vlc_ctx* c, int ir, int predicted, int64_t 
   if (!r) return VLC_ERR_STATE;
   const int s = predicted ? 1 : 0;
   if ((rc = pack_rotor(c, *r, s))) return rc;
-  return sweep_host(c, r->comb[s].rec.p + (size_t)r->wing_pad[s] * vlc::kSrcDoubles,
-                    r->comb[s].n_pad - r->wing_pad[s], m, P, V);
+  const SourceSet v = wake_view(*r, s);
+  return sweep_host(c, v.rec.p, v.n_pad, m, P, V, (v.has_shared && c->shared_nodes) ? &v : nullptr);
 }
 
 extern "C" int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
@@ -905,7 +1002,8 @@ extern "C" int vlc_rotor_vind(vlc_ctx* c, int ir, int predicted, int64_t m, cons
   if (!r) return VLC_ERR_STATE;
   const int s = predicted ? 1 : 0;
   if ((rc = pack_rotor(c, *r, s))) return rc;
-  return sweep_host(c, r->comb[s].rec.p, r->comb[s].n_pad, m, P, V);
+  const SourceSet& v = r->comb[s];
+  return sweep_host(c, v.rec.p, v.n_pad, m, P, V, (v.has_shared && c->shared_nodes) ? &v : nullptr);
 }
 
 extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake, int rows, int cols, int ld,
@@ -1270,6 +1368,7 @@ extern "C" int vlc_last_sweep_ms(vlc_ctx* c, double* ms_kernel, double* ms_total
 extern "C" int vlc_set_shared_nodes(vlc_ctx* c, int on) {
   CHECK_CTX(c);
   c->shared_nodes = (on != 0);
+  for (auto& r : c->rotors) r.dirty[0] = r.dirty[1] = true;
   return VLC_OK;
 }
 

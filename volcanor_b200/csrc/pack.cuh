@@ -261,4 +261,69 @@ __global__ void pack_lastcol_kernel(int nrows, int ns, const double* __restrict_
             strength(gam[ring], true));
 }
 
+
+// ---- tier 2, shared-node form from reference records (waN slices of vr_class records) ----------------------
+// ring(r, j) at base + stride*((i0 + r) + ld*j), r in [0, nrows), j in [0, ns).
+__device__ __forceinline__ const double* ring_ptr(const double* base, int stride, int ld, int i0, int r, int j) {
+  return base + (size_t)stride * ((size_t)(i0 + r) + (size_t)ld * j);
+}
+__device__ __forceinline__ bool same3(const double* a, const double* b) {
+  return a[0] == b[0] && a[1] == b[1] && a[2] == b[2];
+}
+
+// The shared-node form needs the records to describe a LATTICE: filament k ends where filament k+1 starts and
+// neighbouring rings share their corners bitwise (true after blade_wake_continuity, classdef.f90:1609-1702, and
+// assignshed, :4297-4325).  Anything else raises the flag and the sweep uses the flat enumeration.
+__global__ void check_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows, int ns,
+                                   int* __restrict__ unmergeable) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)nrows * ns) return;
+  const int r = (int)(q % nrows), j = (int)(q / nrows);
+  const double* g = ring_ptr(base, stride, ld, i0, r, j);
+  bool ok = true;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) ok = ok && same3(g + kVf * f + 3, g + kVf * ((f + 1) & 3));  // fc(:,2) of f == fc(:,1) of f+1
+  if (r >= 1) {
+    const double* up = ring_ptr(base, stride, ld, i0, r - 1, j);
+    ok = ok && same3(g, up + kVf * 1) && same3(g + kVf * 3, up + kVf * 2);  // corner 1 == up.corner2, corner 4 == up.corner3
+  }
+  if (j >= 1) {
+    const double* lf = ring_ptr(base, stride, ld, i0, r, j - 1);
+    ok = ok && same3(g, lf + kVf * 3) && same3(g + kVf * 1, lf + kVf * 2);  // corner 1 == left.corner4, corner 2 == left.corner3
+  }
+  if (!ok) *unmergeable = 1;
+}
+
+__global__ void pack_rings_shared_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows,
+                                         int ns, double* __restrict__ rec, int* __restrict__ unmergeable) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nr1 = nrows + 1;
+  if (q >= (long long)ns * nr1) return;
+  const int rr = (int)(q % nr1), c = (int)(q / nr1);
+  auto ring = [&](int r, int j) { return ring_ptr(base, stride, ld, i0, r, j); };
+  // node (rr, c) = corner 2 of ring (rr-1, c), or corner 1 of ring (0, c) on the leading row; (rr, c+1) likewise 3 / 4
+  const double* A = (rr >= 1) ? ring(rr - 1, c) + kVf * 1 : ring(0, c);
+  const double* B = (rr >= 1) ? ring(rr - 1, c) + kVf * 2 : ring(0, c) + kVf * 3;
+  const double* Ap = (rr >= 2) ? ring(rr - 2, c) + kVf * 1 : ((rr == 1) ? ring(0, c) : A);
+  auto G = [&](int r, int j) -> double {
+    return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(ring(r, j)[kVrGam], true) : 0.0;
+  };
+  auto RV = [&](int r, int j, int f) -> double { return ring(r, j)[kVf * f + kVfRvc]; };
+  const double gp = G(rr - 1, c) - G(rr, c);
+  double rvcp;
+  if (rr >= 1) {
+    rvcp = RV(rr - 1, c, 1);
+    if (rr < nrows && RV(rr, c, 3) != rvcp) *unmergeable = 1;
+  } else {
+    rvcp = RV(0, c, 3);
+  }
+  double gs = 0.0, rvcs = 0.0;
+  if (rr >= 1) {
+    gs = G(rr - 1, c) - G(rr - 1, c - 1);
+    rvcs = RV(rr - 1, c, 0);
+    if (c >= 1 && RV(rr - 1, c - 1, 2) != rvcs) *unmergeable = 1;
+  }
+  write_lat_rec(rec + q * 16, A, B, Ap, gp, rvcp, gs, rvcs);
+}
+
 }  // namespace vlc
