@@ -25,7 +25,7 @@ constexpr int kThreads = 128;  // threads per sweep CTA
 constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
 constexpr int kStages = 3;     // TMA ring depth
 constexpr int kLatTile = 64;   // ring-step records per shared-memory tile of the lattice kernel (8 KB)
-constexpr int kLatT = 2;       // default targets per thread of the lattice kernel (vlc_set_tuning: 1..3)
+constexpr int kLatT = 3;       // default targets per thread of the lattice kernel (vlc_set_tuning: 1..3)
 
 std::string g_create_error;
 
