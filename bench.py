@@ -30,7 +30,8 @@ sys.path.insert(0, str(ROOT))
 
 FLOPS_PER_PAIR = 76        # algorithmic flops of vf_vind as written + gam scale/accumulate
 PIPE_INSTR_PER_PAIR = {0: 43, 1: 41}   # FP64-pipe instructions per pair in bs_sweep_kernel (SASS count; full / fast)
-PIPE_INSTR_PER_RECORD = 72             # ... per (target, ring-step record) in bs_lattice_kernel = 4 reference pairs
+def pipe_instr_per_record(W):           # ... per (target, strip record of width W) in bs_lattice_kernel: W+1 nodes, 2W edges
+    return 11 * (W + 1) + 50 * W
 
 
 def parse():
@@ -45,6 +46,8 @@ def parse():
     ap.add_argument("--nsplit", type=int, default=0, help="source splits (0 = auto)")
     ap.add_argument("--precision", type=int, default=0, choices=[0, 1],
                     help="0 = full (third-order rsqrt, default), 1 = fast (second order, pair error <= 6.4e-13)")
+    ap.add_argument("--lat-w", type=int, default=0, help="strip width of the shared-node kernel, 1..4 (0 = default)")
+    ap.add_argument("--lat-t", type=int, default=0, help="targets per thread of the shared-node kernel, 1..3 (0 = default)")
     ap.add_argument("--flat", action="store_true",
                     help="force the flat kernel on the reference's enumeration (default: shared-node lattice kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -215,6 +218,7 @@ def main():
     ctx.set_tuning(args.T, args.nsplit)
     ctx.set_precision(args.precision)
     ctx.set_shared_nodes(not args.flat)
+    ctx.set_lattice_tuning(args.lat_w, args.lat_t)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -369,11 +373,11 @@ def main():
         # bs_lattice_kernel covers the 4 ring filaments of every near-wake ring; the remainder kernel the rest
         kernel = "bs_lattice_kernel"
         pairs_launch = float(m_loc) * 4.0 * float(sum(l.R * l.S for l in lats))
-        issued = float(m_loc) * float(info["lattice_records"]) * PIPE_INSTR_PER_RECORD
+        issued = float(m_loc) * float(info["lattice_records"]) * pipe_instr_per_record(info["strip_width"])
         note = ("shared-node lattice kernel: every lattice node evaluated once per target and every interior edge once "
                 "with the merged strength of its two rings -- the reference's ring-by-ring sum regrouped, so frac counts "
-                "the reference's 76 flop x 4 filaments per ring while the kernel issues 72 FP64 instructions per "
-                "(target, ring): frac may exceed 1; pipe_frac = issued FP64 instructions vs the pipe's peak")
+                "the reference's 76 flop x 4 filaments per ring while the kernel issues (11(W+1)+50W)/W = "
+                "72 / 66.5 / 64.7 / 63.75 FP64 instructions per (target, ring) for strip width W = 1..4: frac may exceed 1; pipe_frac = issued FP64 instructions vs the pipe's peak")
     else:
         kernel = "bs_sweep_kernel"
         pairs_launch = float(m_loc) * float(n_src)
@@ -403,7 +407,8 @@ def main():
                       "l2": "flushed every step by a 256 MiB memset inside the timed region",
                       "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather/stage",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
-                      "sources": ({"form": "shared-node lattice", "ring_step_records": int(info["lattice_records"]),
+                      "sources": ({"form": "shared-node lattice", "strip_width": int(info["strip_width"]),
+                                   "strip_records": int(info["lattice_records"]),
                                    "remainder_filaments": int(info["remainder_filaments"])} if shared
                                   else {"form": "flat reference enumeration"}),
                       "precision": ["full: third-order rsqrt refinement, pair error ~1e-16",

@@ -185,9 +185,13 @@ int vlc_pack_lattice(vlc_ctx* ctx, int set, int append, int nrows, int ns, const
  * instead of 43 FP64 instructions per reference pair.  If the two copies of a shared edge carry different core radii
  * the device falls back to the flat enumeration by itself.  on = 0 forces the flat enumeration (default on = 1). */
 int vlc_set_shared_nodes(vlc_ctx* ctx, int on);
-/* out[0] = filaments in the reference's enumeration, out[1] = ring-step records and out[2] = remainder filaments of
+/* Launch shape of the shared-node kernel: strip_width W in 1..4 ring columns per strip record (wider strips
+ * amortise the node work: 72 / 66.5 / 64.7 / 63.75 FP64 instructions per ring), targets_per_thread in 1..3;
+ * 0 = default.  Takes effect at the next pack.  Only speed and summation order change. */
+int vlc_set_lattice_tuning(vlc_ctx* ctx, int strip_width, int targets_per_thread);
+/* out[0..4]: out[0] = filaments in the reference's enumeration, out[1] = ring-step records and out[2] = remainder filaments of
  * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel, 0 if
- * the flat one (reads the device flag: synchronises), -1 for a flat-only set. */
+ * the flat one (reads the device flag: synchronises), -1 for a flat-only set, out[4] = strip width of the records. */
 int vlc_set_info(vlc_ctx* ctx, int set, int64_t* out);
 /* rotor_dissipate_wake on a lattice (classdef.f90:4364-4393): vf1 grows, vf3 <- vf1, gam decays, vf2 grows,
  * vf4(i) <- vf2(i-1) for i > first row. */

@@ -81,6 +81,26 @@ def test_off_lattice_targets_and_source_splits(ctx, oracle):
             ctx.set_tuning(0, 0)
 
 
+@pytest.mark.parametrize("W", [1, 2, 3, 4])
+@pytest.mark.parametrize("T", [1, 2, 3])
+def test_strip_widths_and_targets_per_thread(ctx, oracle, W, T):
+    """Launch shapes of the shared-node kernel (strip width W: ns not a multiple of W leaves a partly empty last strip;
+    T targets per thread) only change speed and summation order -- for lattices and for uploaded rotor records."""
+    from tests.test_gpu_parity import _make_rotor_pair, _tol_scale
+    ctx.set_lattice_tuning(W, T)
+    try:
+        lats = synth.multirotor(7000, seed=21, n_rotor=2, nb=2, S=7, F=6, with_wing=True)
+        _check(ctx, oracle, lats, synth.targets_all(lats))
+        assert ctx.set_info(3)["strip_width"] == W
+        ro = _make_rotor_pair(ctx, oracle, seed=6, ns=5, nNwake=7, nFwake=4, rowNear=2, rowFar=2)
+        P = np.random.default_rng(3).uniform(-1.5, 1.5, size=(300, 3))
+        s = _tol_scale(ro, P) * 50
+        assert np.max(np.abs(ctx.rotor_vind_bywake(0, P) - ro.vind_points(1, P))) < TOL * s
+        assert np.max(np.abs(ctx.rotor_vind(0, P, True) - ro.vind_points(2, P, True))) < TOL * s
+    finally:
+        ctx.set_lattice_tuning(0, 0)
+
+
 @pytest.mark.parametrize("R,S,F", [(1, 1, 0), (1, 1, 3), (2, 1, 0), (1, 5, 2), (130, 2, 1), (3, 70, 0)])
 def test_degenerate_lattice_shapes(ctx, oracle, R, S, F):
     rng = np.random.Generator(np.random.PCG64(R * 100 + S))

@@ -120,6 +120,7 @@ def load_library() -> C.CDLL:
         "vlc_pack_lattice_dev": (i32, [_vp, i32, i32, i32, i32, _vp, _vp, _vp, i32, _vp, _vp, _vp]),
         "vlc_pack_lattice": (i32, [_vp, i32, i32, i32, i32, _vp, _vp, _vp, i32, _vp, _vp, _vp]),
         "vlc_set_shared_nodes": (i32, [_vp, i32]),
+        "vlc_set_lattice_tuning": (i32, [_vp, i32, i32]),
         "vlc_set_info": (i32, [_vp, i32, C.POINTER(i64)]),
         "vlc_last_sweep_ms": (i32, [_vp, _dp, _dp]),
         "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
@@ -371,10 +372,14 @@ class Context:
         """Lattice sets: shared-node kernel (default) or the flat reference enumeration."""
         self._ck(self.lib.vlc_set_shared_nodes(self.h, int(on)))
 
+    def set_lattice_tuning(self, strip_width: int = 0, targets_per_thread: int = 0):
+        self._ck(self.lib.vlc_set_lattice_tuning(self.h, strip_width, targets_per_thread))
+
     def set_info(self, set_: int) -> dict:
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 5)()
         self._ck(self.lib.vlc_set_info(self.h, set_, out))
-        return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3]}
+        return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3],
+                "strip_width": out[4]}
 
     def last_sweep_ms(self) -> tuple[float, float]:
         a, b = C.c_double(), C.c_double()

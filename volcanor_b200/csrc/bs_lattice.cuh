@@ -9,10 +9,11 @@
 //     (the reversed copy of a filament induces exactly the negated velocity):
 //        c = rU x rV,  v += c * (g r0.rU * uU - g r0.rV * uV) / sqrt(K + |c|^4)
 // which is the reference formula with unitVec(r) = r*u.  A strip walk keeps the node quantities in registers:
-// a "ring-step record" (16 doubles) describes node A=(r,c), node B=(r,c+1), the spanwise edge A->B and the
-// streamwise edge A_prev->A (A_prev = node (r-1,c), the A of the previous record of the same strip).
-// Per record and target: 2 nodes (11 FP64 instr each) + 2 edges (25 each) = 72 FP64-pipe instructions for
-// 4 reference pair interactions = 18 per pair (the flat kernel needs 43).
+// a strip record of width W describes one node row of W+1 adjacent node columns, the W spanwise edges between
+// them and the W streamwise edges that reach the first W of them from the previous row (whose node quantities are
+// still in registers).  For W = 1: 2 nodes (11 FP64 instr each) + 2 edges (25 each) = 72 FP64-pipe instructions
+// per (target, ring) = 4 reference pair interactions = 18 per pair (the flat kernel needs 43); W = 2..4 bring it
+// to 66.5 / 64.7 / 63.75.
 //
 // Merging needs both copies of an edge to carry the same core radius; pack_lattice_shared_kernel checks this
 // bitwise and raises a device flag otherwise, in which case this kernel returns immediately and the flat kernel
@@ -22,10 +23,15 @@
 
 namespace vlc {
 
-// Ring-step record: 16 doubles = 128 B = 8 x 16 B.
-//   [0..2] A   [3..5] B   [6..8] gp*(B-A)  [9] gp*|B-A|^2  [10] Kp   [11..13] gs*(A-Aprev)  [14] gs*|A-Aprev|^2  [15] Ks
-constexpr int kLatDoubles = 16;
-constexpr int kLatBytes = kLatDoubles * 8;
+// Strip record of width W (W ring columns = W+1 node columns, one node row), all doubles:
+//   [0 .. 3(W+1))            nodes N_0 .. N_W of this row                     (padded to an even count)
+//   then for k = 0 .. W-1    spanwise edge N_k -> N_{k+1}:  g*(r0)[3], g*|r0|^2, K       (5)
+//                            streamwise edge Nprev_k -> N_k: g*(r0)[3], g*|r0|^2, K      (5)
+// W = 1: 16 doubles (A, B, edge A->B, edge A_prev->A).  Wider strips amortise the node work over more edges:
+// FP64 instructions per ring = (11 (W+1) + 50 W) / W = 72, 66.5, 64.7, 63.75 for W = 1..4.
+__host__ __device__ constexpr int lat_nodes_pad(int W) { return (3 * (W + 1) + 1) / 2 * 2; }
+__host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_nodes_pad(W) + 10 * W; }
+__host__ __device__ constexpr int lat_tile(int W) { return W <= 2 ? 64 : 32; }  // records per shared-memory tile
 
 struct NodeQ {
   double rx, ry, rz, u;  // r = P - X, u = 1/|r|
@@ -68,26 +74,27 @@ __device__ __forceinline__ void edge_accumulate(const NodeQ& a, const NodeQ& b, 
   vz = fma(cz, sc, vz);
 }
 
-template <int T, int THREADS, int TILE, int STAGES, int MINB>
+template <int W, int T, int THREADS, int STAGES, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-bs_lattice_kernel(const double* __restrict__ lat,  // ring-step records, padded to a multiple of TILE
-                  long long chunk,                 // records per split (multiple of TILE)
+bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, padded to a multiple of lat_tile(W)
+                  long long chunk,                 // records per split (multiple of the tile)
                   long long n_pad,                 // total padded records
                   const double* __restrict__ P, long long m,
                   double* __restrict__ out,        // [gridDim.y][3 m]
                   const int* __restrict__ flag, int want) {
   if (flag != nullptr && *flag != want) return;  // uniform: the set is not mergeable -> the flat kernel does the work
+  constexpr int RD = lat_rec_doubles(W), NP = lat_nodes_pad(W), TILE = lat_tile(W);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* buf = reinterpret_cast<double*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * kLatBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * RD * 8);
 
   const int tid = threadIdx.x;
   const long long s_begin = (long long)blockIdx.y * chunk;
   long long s_end = s_begin + chunk;
   if (s_end > n_pad) s_end = n_pad;
   const int ntiles = (s_end > s_begin) ? (int)((s_end - s_begin) / TILE) : 0;
-  const double* gsrc = lat + s_begin * kLatDoubles;
-  constexpr uint32_t kTileBytes = TILE * kLatBytes;
+  const double* gsrc = lat + s_begin * RD;
+  constexpr uint32_t kTileBytes = TILE * RD * 8;
 
   if (tid == 0) {
 #pragma unroll
@@ -100,17 +107,16 @@ bs_lattice_kernel(const double* __restrict__ lat,  // ring-step records, padded 
     for (int s = 0; s < STAGES; ++s)
       if (s < ntiles) {
         mbar_expect_tx(&bars[s], kTileBytes);
-        tma_bulk_g2s(buf + (size_t)s * TILE * kLatDoubles, gsrc + (size_t)s * TILE * kLatDoubles, kTileBytes, &bars[s]);
+        tma_bulk_g2s(buf + (size_t)s * TILE * RD, gsrc + (size_t)s * TILE * RD, kTileBytes, &bars[s]);
       }
   }
 
   const long long t0 = (long long)blockIdx.x * (THREADS * T) + tid;
   double px[T], py[T], pz[T], vx[T], vy[T], vz[T];
-  NodeQ prev[T];
-  // A_prev of the first record of this chunk = A of the record before it (same strip unless the record starts a
-  // strip, in which case its streamwise strength is 0 and any finite node will do).
-  const double* r0 = lat + (s_begin > 0 ? (s_begin - 1) : 0) * kLatDoubles;
-  const double ax0 = r0[0], ay0 = r0[1], az0 = r0[2];
+  NodeQ prev[T][W];
+  // Nprev of the first record of this chunk = the nodes of the record before it (same strip unless the record
+  // starts a strip, in which case its streamwise strengths are 0 and any finite nodes will do).
+  const double* r0 = lat + (s_begin > 0 ? (s_begin - 1) : 0) * RD;
 #pragma unroll
   for (int k = 0; k < T; ++k) {
     const long long t = t0 + (long long)k * THREADS;
@@ -119,32 +125,43 @@ bs_lattice_kernel(const double* __restrict__ lat,  // ring-step records, padded 
     py[k] = ok ? P[3 * t + 1] : 0.0;
     pz[k] = ok ? P[3 * t + 2] : 0.0;
     vx[k] = vy[k] = vz[k] = 0.0;
-    prev[k] = node_eval(px[k], py[k], pz[k], ax0, ay0, az0);
+#pragma unroll
+    for (int i = 0; i < W; ++i) prev[k][i] = node_eval(px[k], py[k], pz[k], r0[3 * i], r0[3 * i + 1], r0[3 * i + 2]);
   }
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int stage = tile % STAGES;
     const uint32_t phase = (uint32_t)(tile / STAGES) & 1u;
     mbar_wait(&bars[stage], phase);
-    const double2* sb = reinterpret_cast<const double2*>(buf + (size_t)stage * TILE * kLatDoubles);
+    const double* sbase = buf + (size_t)stage * TILE * RD;
 #pragma unroll 2
     for (int j = 0; j < TILE; ++j) {
-      const double2 q0 = sb[8 * j + 0], q1 = sb[8 * j + 1], q2 = sb[8 * j + 2], q3 = sb[8 * j + 3];
-      const double2 q4 = sb[8 * j + 4], q5 = sb[8 * j + 5], q6 = sb[8 * j + 6], q7 = sb[8 * j + 7];
+      const double2* sb = reinterpret_cast<const double2*>(sbase + (size_t)j * RD);
+      double q[RD];  // the record, in registers (constant indices after unrolling)
+#pragma unroll
+      for (int i = 0; i < RD / 2; ++i) {
+        const double2 v = sb[i];
+        q[2 * i] = v.x;
+        q[2 * i + 1] = v.y;
+      }
 #pragma unroll
       for (int k = 0; k < T; ++k) {
-        const NodeQ na = node_eval(px[k], py[k], pz[k], q0.x, q0.y, q1.x);
-        const NodeQ nb = node_eval(px[k], py[k], pz[k], q1.y, q2.x, q2.y);
-        edge_accumulate(prev[k], na, q5.y, q6.x, q6.y, q7.x, q7.y, vx[k], vy[k], vz[k]);  // streamwise A_prev -> A
-        edge_accumulate(na, nb, q3.x, q3.y, q4.x, q4.y, q5.x, vx[k], vy[k], vz[k]);       // spanwise   A -> B
-        prev[k] = na;
+        NodeQ n[W + 1];
+#pragma unroll
+        for (int i = 0; i <= W; ++i) n[i] = node_eval(px[k], py[k], pz[k], q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+          const double* e = &q[NP + 10 * i];
+          edge_accumulate(prev[k][i], n[i], e[5], e[6], e[7], e[8], e[9], vx[k], vy[k], vz[k]);  // streamwise Nprev_i -> N_i
+          edge_accumulate(n[i], n[i + 1], e[0], e[1], e[2], e[3], e[4], vx[k], vy[k], vz[k]);    // spanwise   N_i -> N_{i+1}
+          prev[k][i] = n[i];
+        }
       }
     }
     __syncthreads();
     if (tid == 0 && tile + STAGES < ntiles) {
       mbar_expect_tx(&bars[stage], kTileBytes);
-      tma_bulk_g2s(buf + (size_t)stage * TILE * kLatDoubles, gsrc + (size_t)(tile + STAGES) * TILE * kLatDoubles,
-                   kTileBytes, &bars[stage]);
+      tma_bulk_g2s(buf + (size_t)stage * TILE * RD, gsrc + (size_t)(tile + STAGES) * TILE * RD, kTileBytes, &bars[stage]);
     }
   }
 

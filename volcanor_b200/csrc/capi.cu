@@ -24,8 +24,11 @@ namespace {
 constexpr int kThreads = 128;  // threads per sweep CTA
 constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
 constexpr int kStages = 3;     // TMA ring depth
-constexpr int kLatTile = 64;   // ring-step records per shared-memory tile of the lattice kernel (8 KB)
-constexpr int kLatT = 3;       // default targets per thread of the lattice kernel (vlc_set_tuning: 1..3)
+// Lattice kernel shape (vlc_set_lattice_tuning): strip width W in 1..4, targets per thread T in 1..3; 0 = automatic:
+// W minimises the measured cost per ring (profiles/r01e_wt_sweep.md: W=1,T=3 1.000; W=2,T=3 0.944; W=3,T=2 0.935;
+// W=4,T=1 0.895) times the padding of the last strip, ceil(ns/W)*W/ns; T is the best measured one for that W.
+constexpr double kLatCost[5] = {0.0, 1.000, 0.944, 0.935, 0.895};
+constexpr int kLatBestT[5] = {0, 3, 3, 2, 1};
 
 std::string g_create_error;
 
@@ -40,7 +43,8 @@ struct SourceSet {
   long long n_pad = 0;  // padded to kTile
   // shared-node form of the same sources (tier 3 lattices, bs_lattice.cuh): strip records + flat remainder
   DevBuf lat;
-  long long n_lat = 0, n_lat_pad = 0;  // ring-step records, padded to kLatTile
+  long long n_lat = 0, n_lat_pad = 0;  // strip records, padded to lat_tile(lat_W)
+  int lat_W = 1;                       // strip width the records were packed with
   DevBuf rem;
   long long n_rem = 0, n_rem_pad = 0;  // filaments no strip covers (last column, horseshoe, far chain)
   int* d_unmergeable = nullptr;        // device flag raised by the pack kernels
@@ -82,7 +86,8 @@ struct vlc_ctx {
   bool shared_nodes = true;  // lattice sources: use the shared-node kernel when the set allows it
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // last sweep: before / after the dominant kernel, after the reduce
   bool ev_valid = false;
-  int occ_lat[4] = {0, 0, 0, 0};  // resident CTAs/SM of the lattice kernel for T = 1..3
+  int lat_W = 0, lat_T = 0;          // lattice kernel shape (vlc_set_lattice_tuning), 0 = automatic
+  int occ_lat[5][4] = {};            // resident CTAs/SM of the lattice kernel [W][T]
   bool fast = false;  // rsqrt refinement: false = third order (~1e-16), true = second order (~4e-14)
   long long launches = 0;
   SourceSet sets[VLC_MAX_SETS];
@@ -268,22 +273,52 @@ int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const dou
   return VLC_OK;
 }
 
-constexpr size_t kLatSmem = (size_t)kStages * kLatTile * vlc::kLatBytes + kStages * sizeof(uint64_t);
+inline int auto_strip_width(const vlc_ctx* c, int ns) {
+  if (c->lat_W >= 1 && c->lat_W <= 4) return c->lat_W;
+  int best = 1;
+  double bc = 1e300;
+  for (int W = 1; W <= 4; ++W) {
+    const double cost = kLatCost[W] * (double)((ns + W - 1) / W * W) / (double)ns;
+    if (cost < bc - 1e-12) {
+      bc = cost;
+      best = W;
+    }
+  }
+  return best;
+}
+inline int lat_tile_of(int W) { return vlc::lat_tile(W); }
+inline int lat_rd_of(int W) { return vlc::lat_rec_doubles(W); }
+inline size_t lat_smem_of(int W) { return (size_t)kStages * lat_tile_of(W) * lat_rd_of(W) * 8 + kStages * sizeof(uint64_t); }
+inline long long pad_lat(long long n, int W) { return (n + lat_tile_of(W) - 1) / lat_tile_of(W) * lat_tile_of(W); }
 
-template <int T, int MINB>
-int query_occ_lat(vlc_ctx* c, int* out) {
-  auto kern = vlc::bs_lattice_kernel<T, kThreads, kLatTile, kStages, MINB>;
-  CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
-  CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kern, kThreads, kLatSmem));
+// (W, T) instantiations of the lattice kernel and their __launch_bounds__ minimum resident CTAs
+#define VLC_LAT_SHAPES(X) X(1, 1, 6) X(1, 2, 4) X(1, 3, 2) X(2, 1, 4) X(2, 2, 2) X(2, 3, 2) X(3, 1, 3) X(3, 2, 2) X(4, 1, 2) X(4, 2, 2)
+
+int query_occ_lat_all(vlc_ctx* c) {
+#define X(WW, TT, MB)                                                                                           \
+  {                                                                                                             \
+    auto kern = vlc::bs_lattice_kernel<WW, TT, kThreads, kStages, MB>;                                          \
+    CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lat_smem_of(WW)));  \
+    CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lat[WW][TT], kern, kThreads, lat_smem_of(WW))); \
+  }
+  VLC_LAT_SHAPES(X)
+#undef X
   return VLC_OK;
 }
 
+bool lat_shape_exists(int W, int T) {
+#define X(WW, TT, MB) if (W == WW && T == TT) return true;
+  VLC_LAT_SHAPES(X)
+#undef X
+  return false;
+}
+
 // Source splits of the lattice kernel: whole waves of (SMs x resident CTAs), chunks of >= 4 tiles when possible.
-int plan_lattice_split(const vlc_ctx* c, int T, long long m, long long n_lat_pad) {
+int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad) {
   if (c->tune_nsplit > 0) return c->tune_nsplit;
-  const long long tiles = n_lat_pad / kLatTile;
+  const long long tiles = n_lat_pad / lat_tile_of(W);
   const long long ttiles = (m + (long long)kThreads * T - 1) / ((long long)kThreads * T);
-  const long long slots = (long long)c->sm_count * (c->occ_lat[T] > 0 ? c->occ_lat[T] : 3);
+  const long long slots = (long long)c->sm_count * (c->occ_lat[W][T] > 0 ? c->occ_lat[W][T] : 2);
   long long max_split = tiles / 4;
   if (max_split < 1) max_split = 1;
   if (max_split > 256) max_split = 256;
@@ -310,10 +345,12 @@ int plan_lattice_split(const vlc_ctx* c, int T, long long m, long long n_lat_pad
 // of whichever path ran, in fixed order.
 int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, double* dV) {
   if (m <= 0) return VLC_OK;
-  const long long lat_tiles = s.n_lat_pad / kLatTile;
-  int LT = (c->tune_T >= 1 && c->tune_T <= 3) ? c->tune_T : kLatT;
-  if (c->tune_T == 0 && m <= kThreads) LT = 1;
-  int ns_l = plan_lattice_split(c, LT, m, s.n_lat_pad);
+  const int LW = s.lat_W;
+  const long long lat_tiles = s.n_lat_pad / lat_tile_of(LW);
+  int LT = (c->lat_T >= 1 && c->lat_T <= 3) ? c->lat_T : kLatBestT[LW];
+  if (m <= kThreads) LT = 1;
+  while (LT > 1 && !lat_shape_exists(LW, LT)) --LT;
+  int ns_l = plan_lattice_split(c, LW, LT, m, s.n_lat_pad);
   const long long lat_chunk_tiles = (lat_tiles + ns_l - 1) / ns_l;
   ns_l = (int)((lat_tiles + lat_chunk_tiles - 1) / lat_chunk_tiles);
   const FlatPlan pr = s.n_rem_pad > 0 ? plan_flat(c, m, s.n_rem_pad) : FlatPlan();
@@ -326,15 +363,13 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   cudaEventRecord(c->ev[0], c->stream);
   {
     dim3 grid(blocks_for(m, kThreads * LT), (unsigned)ns_l, 1);
-#define VLC_LAT(TT, MB)                                                                                             \
-  vlc::bs_lattice_kernel<TT, kThreads, kLatTile, kStages, MB><<<grid, kThreads, kLatSmem, c->stream>>>(             \
-      s.lat.p, lat_chunk_tiles * kLatTile, s.n_lat_pad, dP, m, part, s.d_unmergeable, 0)
-    switch (LT) {
-      case 1: VLC_LAT(1, 6); break;
-      case 3: VLC_LAT(3, 2); break;
-      default: VLC_LAT(2, 4); break;
-    }
-#undef VLC_LAT
+    const long long lat_chunk = lat_chunk_tiles * lat_tile_of(LW);
+#define X(WW, TT, MB)                                                                                              \
+  if (LW == WW && LT == TT)                                                                                        \
+    vlc::bs_lattice_kernel<WW, TT, kThreads, kStages, MB><<<grid, kThreads, lat_smem_of(WW), c->stream>>>(          \
+        s.lat.p, lat_chunk, s.n_lat_pad, dP, m, part, s.d_unmergeable, 0);
+    VLC_LAT_SHAPES(X)
+#undef X
     CUDA_OK(c, cudaGetLastError());
     c->launches++;
   }
@@ -462,13 +497,15 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   cs.has_shared = false;
   cs.n_lat = cs.n_lat_pad = cs.n_rem = cs.n_rem_pad = 0;
   if (nrows > 0 && c->shared_nodes) {
-    const long long lat_n = (long long)r.nb * r.ns * (nrows + 1);
-    const long long lat_pad = (lat_n + kLatTile - 1) / kLatTile * kLatTile;
+    const int LW = auto_strip_width(c, r.ns), RD = lat_rd_of(LW), nstrips = (r.ns + LW - 1) / LW;
+    const long long lat_n = (long long)r.nb * nstrips * (nrows + 1);
+    const long long lat_pad = pad_lat(lat_n, LW);
+    cs.lat_W = LW;
     long long rem_per_blade = nrows;  // streamwise edges of the last column
     if (has_far) rem_per_blade += r.ns + nfar + (r.have_pf[s] ? VLC_NPFWAKE : 0);
     const long long rem_wake = rem_per_blade * r.nb;
     const long long rem_pad = wing_pad + pad_tile(rem_wake);
-    if ((rc = reserve(c, cs.lat, (size_t)lat_pad * vlc::kLatDoubles))) return rc;
+    if ((rc = reserve(c, cs.lat, (size_t)lat_pad * RD))) return rc;
     if ((rc = reserve(c, cs.rem, (size_t)rem_pad * vlc::kSrcDoubles))) return rc;
     if (!cs.d_unmergeable) CUDA_OK(c, cudaMalloc(&cs.d_unmergeable, sizeof(int)));
     CUDA_OK(c, cudaMemsetAsync(cs.d_unmergeable, 0, sizeof(int), st));
@@ -479,12 +516,16 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     long long roff = 0;
     for (int ib = 0; ib < r.nb; ++ib) {
       const double* waN = r.waN[s].p + (size_t)ib * r.nNwake * r.ns * vlc::kVr;
-      const long long nring = (long long)nrows * r.ns, nrec = (long long)r.ns * (nrows + 1);
+      const long long nring = (long long)nrows * r.ns, nrec = (long long)nstrips * (nrows + 1);
       vlc::check_rings_kernel<<<blocks_for(nring, 256), 256, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns,
                                                                       cs.d_unmergeable);
-      vlc::pack_rings_shared_kernel<<<blocks_for(nrec, 256), 256, 0, st>>>(
-          waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, cs.lat.p + (size_t)ib * nrec * vlc::kLatDoubles,
-          cs.d_unmergeable);
+      double* lrec = cs.lat.p + (size_t)ib * nrec * RD;
+#define X(WW)                                                                                                 \
+  if (LW == WW)                                                                                               \
+    vlc::pack_rings_shared_kernel<WW><<<blocks_for(nrec, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, \
+                                                                             nrows, r.ns, lrec, cs.d_unmergeable);
+      X(1) X(2) X(3) X(4)
+#undef X
       // last column: f3 of ring (i, ns-1), wake rule applies (classdef.f90:1452)
       vlc::pack_rings_kernel<<<blocks_for(nrows, 128), 128, 0, st>>>(
           waN + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr, r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1,
@@ -509,8 +550,12 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
       }
     }
     if (lat_pad > lat_n) {
-      vlc::pack_null_lat_kernel<<<blocks_for(lat_pad - lat_n, 256), 256, 0, st>>>(
-          lat_pad - lat_n, cs.lat.p + (size_t)lat_n * vlc::kLatDoubles);
+#define X(WW)                                                                                        \
+  if (LW == WW)                                                                                      \
+    vlc::pack_null_lat_kernel<WW><<<blocks_for(lat_pad - lat_n, 128), 128, 0, st>>>(lat_pad - lat_n, \
+                                                                                     cs.lat.p + (size_t)lat_n * RD);
+      X(1) X(2) X(3) X(4)
+#undef X
       c->launches++;
     }
     if (pad_tile(rem_wake) > roff) {
@@ -632,9 +677,7 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
   rc |= query_occ<2, 4>(c, &c->occ[2]);
   rc |= query_occ<3, 3>(c, &c->occ[3]);
   rc |= query_occ<4, 3>(c, &c->occ[4]);
-  rc |= query_occ_lat<1, 6>(c, &c->occ_lat[1]);
-  rc |= query_occ_lat<2, 4>(c, &c->occ_lat[2]);
-  rc |= query_occ_lat<3, 2>(c, &c->occ_lat[3]);
+  rc |= query_occ_lat_all(c);
   if (rc) {
     g_create_error = "sweep kernel not loadable on this device: " + c->err;
     cudaStreamDestroy(c->own_stream);
@@ -1249,6 +1292,7 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
   if (!append) {
     s.n_lat = s.n_rem = 0;
     s.has_shared = true;
+    s.lat_W = auto_strip_width(c, ns);  // lattices appended later share the record width of the first one
     if (!s.d_unmergeable) CUDA_OK(c, cudaMalloc(&s.d_unmergeable, sizeof(int)));
     CUDA_OK(c, cudaMemsetAsync(s.d_unmergeable, 0, sizeof(int), c->stream));
   }
@@ -1264,17 +1308,24 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
     b = nb;
     return VLC_OK;
   };
-  const long long lat_add = nrows > 0 ? (long long)ns * (nrows + 1) : 0;
+  const int LW = s.lat_W, RD = lat_rd_of(LW);
+  const long long lat_add = nrows > 0 ? (long long)((ns + LW - 1) / LW) * (nrows + 1) : 0;
   const long long lat_new = s.n_lat + lat_add;
-  const long long lat_pad = (lat_new + kLatTile - 1) / kLatTile * kLatTile;
+  const long long lat_pad = pad_lat(lat_new, LW);
   const long long rem_add = (nrows > 0 ? nrows : 0) + (nfar > 0 ? ns + nfar : 0);
   const long long rem_new = s.n_rem + rem_add;
   const long long rem_pad = pad_tile(rem_new);
-  if ((rc = grow_keep(s.lat, (size_t)s.n_lat * vlc::kLatDoubles, (size_t)lat_pad * vlc::kLatDoubles))) return rc;
+  if ((rc = grow_keep(s.lat, (size_t)s.n_lat * RD, (size_t)lat_pad * RD))) return rc;
   if ((rc = grow_keep(s.rem, (size_t)s.n_rem * vlc::kSrcDoubles, (size_t)rem_pad * vlc::kSrcDoubles))) return rc;
   if (nrows > 0) {
-    LAUNCH1D(c, vlc::pack_lattice_shared_kernel, lat_add, nrows, ns, nodes, gam, rvc4,
-             s.lat.p + (size_t)s.n_lat * vlc::kLatDoubles, s.d_unmergeable);
+#define X(WW)                                                                                              \
+  if (LW == WW)                                                                                            \
+    vlc::pack_lattice_shared_kernel<WW><<<blocks_for(lat_add, 128), 128, 0, c->stream>>>(nrows, ns, nodes, gam, rvc4, \
+                                                                                          s.lat.p + (size_t)s.n_lat * RD, s.d_unmergeable);
+    X(1) X(2) X(3) X(4)
+#undef X
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
     double* rrec = s.rem.p + (size_t)s.n_rem * vlc::kSrcDoubles;
     LAUNCH1D(c, vlc::pack_lastcol_kernel, (long long)nrows, nrows, ns, nodes, gam, rvc4, rrec);
     long long roff = nrows;
@@ -1286,9 +1337,16 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
                rrec + (size_t)roff * vlc::kSrcDoubles);
     }
   }
-  if (lat_pad > lat_new)
-    LAUNCH1D(c, vlc::pack_null_lat_kernel, lat_pad - lat_new, lat_pad - lat_new,
-             s.lat.p + (size_t)lat_new * vlc::kLatDoubles);
+  if (lat_pad > lat_new) {
+#define X(WW)                                                                                              \
+  if (LW == WW)                                                                                            \
+    vlc::pack_null_lat_kernel<WW><<<blocks_for(lat_pad - lat_new, 128), 128, 0, c->stream>>>(lat_pad - lat_new, \
+                                                                                             s.lat.p + (size_t)lat_new * RD);
+    X(1) X(2) X(3) X(4)
+#undef X
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
   if (rem_pad > rem_new)
     LAUNCH1D(c, vlc::pack_null_kernel, rem_pad - rem_new, rem_pad - rem_new, s.rem.p + (size_t)rem_new * vlc::kSrcDoubles);
   s.n_lat = lat_new;
@@ -1342,6 +1400,7 @@ extern "C" int vlc_set_info(vlc_ctx* c, int set, int64_t* out) {
   out[1] = s.has_shared ? s.n_lat : 0;
   out[2] = s.has_shared ? s.n_rem : 0;
   out[3] = -1;
+  out[4] = s.has_shared ? s.lat_W : 0;
   if (s.has_shared && s.d_unmergeable) {
     int f = 0;
     CUDA_OK(c, cudaMemcpyAsync(&f, s.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1362,6 +1421,16 @@ extern "C" int vlc_last_sweep_ms(vlc_ctx* c, double* ms_kernel, double* ms_total
   CUDA_OK(c, cudaEventElapsedTime(&b, c->ev[0], c->ev[2]));
   if (ms_kernel) *ms_kernel = a;
   if (ms_total) *ms_total = b;
+  return VLC_OK;
+}
+
+extern "C" int vlc_set_lattice_tuning(vlc_ctx* c, int strip_width, int targets_per_thread) {
+  CHECK_CTX(c);
+  const int W = strip_width, T = targets_per_thread;
+  if (W < 0 || W > 4 || T < 0 || T > 3) return fail(c, VLC_ERR_ARG, "strip_width in 1..4, targets_per_thread in 1..3 (0 = automatic)");
+  c->lat_W = W;
+  c->lat_T = T;
+  for (auto& r : c->rotors) r.dirty[0] = r.dirty[1] = true;  // tier-3 sets are re-packed by their owner
   return VLC_OK;
 }
 

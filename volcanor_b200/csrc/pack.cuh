@@ -178,73 +178,126 @@ __global__ void pack_chain_kernel(int nfar, const double* __restrict__ p, const 
 }
 
 
-// ---- tier 3, shared-node form (bs_lattice.cuh) ------------------------------------------------
-// Ring-step records of one lattice: strip c = 0..ns-1 (columns c, c+1), node rows rr = 0..nrows, record index
-// c*(nrows+1) + rr.  Merged edge strengths (Gamma' = Gamma or 0 under the wake rule |Gamma| > eps, classdef.f90:1452):
+// ---- shared-node form (bs_lattice.cuh): strip records of width W --------------------------------------------
+// One lattice of nrows x ns rings = (nrows+1) x (ns+1) nodes.  Strip s covers node columns s*W .. s*W+W; record
+// index = strip*(nrows+1) + rr for node row rr = 0..nrows.  Merged edge strengths (Gamma' = Gamma, or 0 under the
+// wake rule |Gamma| > eps, classdef.f90:1452; 0 outside the lattice):
 //   spanwise   (rr,c)->(rr,c+1): Gamma'(rr-1,c) - Gamma'(rr,c)     [f2 of ring (rr-1,c), reversed f4 of ring (rr,c)]
 //   streamwise (rr-1,c)->(rr,c): Gamma'(rr-1,c) - Gamma'(rr-1,c-1) [f1 of ring (rr-1,c), reversed f3 of ring (rr-1,c-1)]
-// with Gamma' = 0 outside the lattice.  *unmergeable is set when the two copies of a shared edge carry different
-// core radii (possible with a non-uniform streamwiseCoreVec): the sweep then uses the flat records.
-__device__ __forceinline__ void write_lat_rec(double* __restrict__ rec, const double* A, const double* B,
-                                              const double* Ap, double gp, double rvcp, double gs, double rvcs) {
-  const double px = B[0] - A[0], py = B[1] - A[1], pz = B[2] - A[2];
-  const double Lp = fma(pz, pz, fma(py, py, px * px));
-  const double qp = rvcp * rvcp * Lp;
-  const double sx = A[0] - Ap[0], sy = A[1] - Ap[1], sz = A[2] - Ap[2];
-  const double Ls = fma(sz, sz, fma(sy, sy, sx * sx));
-  const double qs = rvcs * rvcs * Ls;
-  double2* o = reinterpret_cast<double2*>(rec);
-  o[0] = make_double2(A[0], A[1]);
-  o[1] = make_double2(A[2], B[0]);
-  o[2] = make_double2(B[1], B[2]);
-  o[3] = make_double2(gp * px, gp * py);
-  o[4] = make_double2(gp * pz, gp * Lp);
-  o[5] = make_double2(qp * qp, gs * sx);
-  o[6] = make_double2(gs * sy, gs * sz);
-  o[7] = make_double2(gs * Ls, qs * qs);
+// The streamwise edges of the LAST node column (c = ns) are left to the flat remainder (pack_lastcol / fil_mask 0x4).
+// *unmergeable is raised when the two copies of a shared edge carry different core radii (possible with a
+// non-uniform streamwiseCoreVec): the sweep then uses the flat records instead.
+// Acc supplies node(rr, c, out[3]), gam(r, j) (raw circulation) and rvc(r, j, f).
+__device__ __forceinline__ void write_edge(double* __restrict__ e, const double* U, const double* V, double g, double rvc) {
+  const double x = V[0] - U[0], y = V[1] - U[1], z = V[2] - U[2];
+  const double L = fma(z, z, fma(y, y, x * x));
+  const double q = rvc * rvc * L;  // (rVc*|r0|)^2 ; reference: (rVc*norm2(r0))**4 (classdef.f90:501)
+  e[0] = g * x;
+  e[1] = g * y;
+  e[2] = g * z;
+  e[3] = g * L;
+  e[4] = q * q;
 }
 
+template <int W, class Acc>
+__device__ __forceinline__ void fill_strip_record(const Acc& acc, int nrows, int ns, int strip, int rr,
+                                                  double* __restrict__ rec, int* __restrict__ unmergeable) {
+  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2;
+  const int c0 = strip * W;
+  auto G = [&](int r, int j) -> double {
+    return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(acc.gam(r, j), true) : 0.0;
+  };
+  double N[W + 1][3], Np[W][3];
+#pragma unroll
+  for (int k = 0; k <= W; ++k) {
+    const int c = c0 + k;
+    if (c <= ns) {
+      acc.node(rr, c, N[k]);
+    } else {  // past the lattice: a well-separated dummy node; every edge touching it has zero strength
+      acc.node(rr, ns, N[k]);
+      const double off = (double)(c - ns);
+      N[k][0] += off;
+      N[k][1] += off;
+      N[k][2] += off;
+    }
+    if (k < W) {
+      if (rr >= 1 && c <= ns) {
+        acc.node(rr - 1, c, Np[k]);
+      } else {
+        Np[k][0] = N[k][0];
+        Np[k][1] = N[k][1];
+        Np[k][2] = N[k][2];
+      }
+    }
+    rec[3 * k] = N[k][0];
+    rec[3 * k + 1] = N[k][1];
+    rec[3 * k + 2] = N[k][2];
+  }
+  if (NP > 3 * (W + 1)) rec[NP - 1] = 0.0;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int c = c0 + k;
+    double* e = rec + NP + 10 * k;
+    // spanwise edge (rr, c) -> (rr, c+1), real when c + 1 <= ns
+    double gp = 0.0, rvcp = 0.0;
+    if (c + 1 <= ns) {
+      gp = G(rr - 1, c) - G(rr, c);
+      if (rr >= 1) {
+        rvcp = acc.rvc(rr - 1, c, 1);
+        if (rr < nrows && acc.rvc(rr, c, 3) != rvcp) *unmergeable = 1;
+      } else {
+        rvcp = acc.rvc(0, c, 3);
+      }
+    }
+    write_edge(e, N[k], N[k + 1], gp, rvcp);
+    // streamwise edge (rr-1, c) -> (rr, c), real when rr >= 1 and c <= ns - 1
+    double gs = 0.0, rvcs = 0.0;
+    if (rr >= 1 && c <= ns - 1) {
+      gs = G(rr - 1, c) - G(rr - 1, c - 1);
+      rvcs = acc.rvc(rr - 1, c, 0);
+      if (c >= 1 && acc.rvc(rr - 1, c - 1, 2) != rvcs) *unmergeable = 1;
+    }
+    write_edge(e + 5, Np[k], N[k], gs, rvcs);
+  }
+}
+
+// null strip records (padding): distinct finite nodes, zero strengths
+template <int W>
 __global__ void pack_null_lat_kernel(long long count, double* __restrict__ rec) {
+  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2, RD = NP + 10 * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  double2* o = reinterpret_cast<double2*>(rec + i * 16);
-  const double2 z = make_double2(0.0, 0.0);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = z;
-  o[1] = make_double2(0.0, 1.0);  // B = (1,0,0) != A: a well-formed edge of zero strength
+  double* r = rec + i * RD;
+  for (int k = 0; k < RD; ++k) r[k] = 0.0;
+  for (int k = 0; k <= W; ++k) r[3 * k] = (double)k;  // N_k = (k, 0, 0)
 }
 
+// tier 3: node-indexed lattice arrays (include/volcanor_b200.h)
+struct LatticeAcc {
+  const double* nodes;
+  const double* gamv;
+  const double* rvc4;
+  int nrows, ns;
+  __device__ __forceinline__ void node(int rr, int c, double* o) const {
+    const double* p = nodes + 3 * ((size_t)rr + (size_t)(nrows + 1) * c);
+    o[0] = p[0];
+    o[1] = p[1];
+    o[2] = p[2];
+  }
+  __device__ __forceinline__ double gam(int r, int j) const { return gamv[(size_t)r + (size_t)nrows * j]; }
+  __device__ __forceinline__ double rvc(int r, int j, int f) const { return rvc4[4 * ((size_t)r + (size_t)nrows * j) + f]; }
+};
+
+template <int W>
 __global__ void pack_lattice_shared_kernel(int nrows, int ns, const double* __restrict__ nodes,
                                            const double* __restrict__ gam, const double* __restrict__ rvc4,
                                            double* __restrict__ rec, int* __restrict__ unmergeable) {
+  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 10 * W;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nr1 = nrows + 1;
-  if (q >= (long long)ns * nr1) return;
-  const int rr = (int)(q % nr1), c = (int)(q / nr1);
-  const double* A = nodes + 3 * ((size_t)rr + (size_t)nr1 * c);
-  const double* B = nodes + 3 * ((size_t)rr + (size_t)nr1 * (c + 1));
-  const double* Ap = (rr > 0) ? A - 3 : A;
-  auto G = [&](int r, int j) -> double {
-    return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(gam[(size_t)r + (size_t)nrows * j], true) : 0.0;
-  };
-  auto RV = [&](int r, int j, int f) -> double { return rvc4[4 * ((size_t)r + (size_t)nrows * j) + f]; };
-  // spanwise edge of node row rr
-  const double gp = G(rr - 1, c) - G(rr, c);
-  double rvcp;
-  if (rr >= 1) {
-    rvcp = RV(rr - 1, c, 1);
-    if (rr < nrows && RV(rr, c, 3) != rvcp) *unmergeable = 1;
-  } else {
-    rvcp = RV(0, c, 3);
-  }
-  // streamwise edge (rr-1,c) -> (rr,c)
-  double gs = 0.0, rvcs = 0.0;
-  if (rr >= 1) {
-    gs = G(rr - 1, c) - G(rr - 1, c - 1);
-    rvcs = RV(rr - 1, c, 0);
-    if (c >= 1 && RV(rr - 1, c - 1, 2) != rvcs) *unmergeable = 1;
-  }
-  write_lat_rec(rec + q * 16, A, B, Ap, gp, rvcp, gs, rvcs);
+  const int nr1 = nrows + 1, nstrips = (ns + W - 1) / W;
+  if (q >= (long long)nstrips * nr1) return;
+  const LatticeAcc acc{nodes, gam, rvc4, nrows, ns};
+  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1), (int)(q % nr1), rec + q * RD, unmergeable);
 }
 
 // Streamwise edges of the last column (f3 of ring (r, ns-1): corner 3 -> corner 4), which no strip covers.
@@ -294,36 +347,35 @@ __global__ void check_rings_kernel(const double* __restrict__ base, int stride, 
   if (!ok) *unmergeable = 1;
 }
 
+// tier 2: reference records (vr_class) of one blade's near wake
+struct RingsAcc {
+  const double* base;
+  int stride, ld, i0, nrows, ns;
+  __device__ __forceinline__ const double* ring(int r, int j) const { return ring_ptr(base, stride, ld, i0, r, j); }
+  // node (rr, c) = corner 2 of ring (rr-1, c) [corner 3 of ring (rr-1, ns-1) for c = ns], or corner 1 [4] of row 0
+  __device__ __forceinline__ void node(int rr, int c, double* o) const {
+    const double* p;
+    if (c < ns)
+      p = (rr >= 1) ? ring(rr - 1, c) + kVf * 1 : ring(0, c);
+    else
+      p = (rr >= 1) ? ring(rr - 1, ns - 1) + kVf * 2 : ring(0, ns - 1) + kVf * 3;
+    o[0] = p[0];
+    o[1] = p[1];
+    o[2] = p[2];
+  }
+  __device__ __forceinline__ double gam(int r, int j) const { return ring(r, j)[kVrGam]; }
+  __device__ __forceinline__ double rvc(int r, int j, int f) const { return ring(r, j)[kVf * f + kVfRvc]; }
+};
+
+template <int W>
 __global__ void pack_rings_shared_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows,
                                          int ns, double* __restrict__ rec, int* __restrict__ unmergeable) {
+  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 10 * W;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nr1 = nrows + 1;
-  if (q >= (long long)ns * nr1) return;
-  const int rr = (int)(q % nr1), c = (int)(q / nr1);
-  auto ring = [&](int r, int j) { return ring_ptr(base, stride, ld, i0, r, j); };
-  // node (rr, c) = corner 2 of ring (rr-1, c), or corner 1 of ring (0, c) on the leading row; (rr, c+1) likewise 3 / 4
-  const double* A = (rr >= 1) ? ring(rr - 1, c) + kVf * 1 : ring(0, c);
-  const double* B = (rr >= 1) ? ring(rr - 1, c) + kVf * 2 : ring(0, c) + kVf * 3;
-  const double* Ap = (rr >= 2) ? ring(rr - 2, c) + kVf * 1 : ((rr == 1) ? ring(0, c) : A);
-  auto G = [&](int r, int j) -> double {
-    return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(ring(r, j)[kVrGam], true) : 0.0;
-  };
-  auto RV = [&](int r, int j, int f) -> double { return ring(r, j)[kVf * f + kVfRvc]; };
-  const double gp = G(rr - 1, c) - G(rr, c);
-  double rvcp;
-  if (rr >= 1) {
-    rvcp = RV(rr - 1, c, 1);
-    if (rr < nrows && RV(rr, c, 3) != rvcp) *unmergeable = 1;
-  } else {
-    rvcp = RV(0, c, 3);
-  }
-  double gs = 0.0, rvcs = 0.0;
-  if (rr >= 1) {
-    gs = G(rr - 1, c) - G(rr - 1, c - 1);
-    rvcs = RV(rr - 1, c, 0);
-    if (c >= 1 && RV(rr - 1, c - 1, 2) != rvcs) *unmergeable = 1;
-  }
-  write_lat_rec(rec + q * 16, A, B, Ap, gp, rvcp, gs, rvcs);
+  const int nr1 = nrows + 1, nstrips = (ns + W - 1) / W;
+  if (q >= (long long)nstrips * nr1) return;
+  const RingsAcc acc{base, stride, ld, i0, nrows, ns};
+  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1), (int)(q % nr1), rec + q * RD, unmergeable);
 }
 
 }  // namespace vlc
