@@ -222,68 +222,92 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
-    # ---- device-resident wake state (node-indexed SoA per lattice) ----
+    # ---- device-resident wake state (node-indexed SoA per lattice): current ('C') and predicted ('P') node sets ----
     d = []
     for l in lats:
-        d.append({"R": l.R, "S": l.S, "F": l.F,
-                  "nodes": torch.from_numpy(l.nodes).to(dev), "gam": torch.from_numpy(l.gam).to(dev),
-                  "rvc4": torch.from_numpy(l.rvc4).to(dev),
-                  "far": torch.from_numpy(l.far_nodes).to(dev) if l.F > 0 else None,
+        nodes = torch.from_numpy(l.nodes).to(dev)
+        far = torch.from_numpy(l.far_nodes).to(dev) if l.F > 0 else None
+        d.append({"R": l.R, "S": l.S, "F": l.F, "nodes": nodes, "nodesP": nodes.clone(),
+                  "gam": torch.from_numpy(l.gam).to(dev), "rvc4": torch.from_numpy(l.rvc4).to(dev),
+                  "far": far, "farP": far.clone() if far is not None else None,
                   "gamF": torch.from_numpy(l.gamF).to(dev) if l.F > 0 else None,
                   "rvcF": torch.from_numpy(l.rvcF).to(dev) if l.F > 0 else None})
     # target list = convected nodes of every lattice (+ far-chain nodes), padded to world * per
     from volcanor_b200.sharding import TargetShard, allgather_slices
     shard = TargetShard(m, world, rank)
     per, lo, hi, m_loc = shard.per, shard.lo, shard.hi, shard.count
-    P_all = torch.zeros(shard.padded, 3, dtype=torch.float64, device=dev)
-    V_loc = torch.zeros(per, 3, dtype=torch.float64, device=dev)
+    f64 = dict(dtype=torch.float64, device=dev)
+    P_all, Pp_all = torch.zeros(shard.padded, 3, **f64), torch.zeros(shard.padded, 3, **f64)
+    V, Vp, V1, Vw = (torch.zeros(max(per, 1), 3, **f64) for _ in range(4))   # this rank's slice: vel, predicted, previous, work
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    dt_step = 1e-9
+    dt_step, nu, visc_coeff = 1e-9, 1.8e-5, 5.0
+    state = {"first": True}
 
-    def gather_targets():
+    def gather_targets(key, far_key, dst):
         off = 0
         for L in d:
             k = L["R"] * (L["S"] + 1)
-            ctx.lattice_targets_dev(L["R"], L["S"], L["nodes"], P_all[off:off + k])
+            ctx.lattice_targets_dev(L["R"], L["S"], L[key], dst[off:off + k])
             off += k
             if L["F"] > 0:
-                P_all[off:off + L["F"]].copy_(L["far"][1:])
+                dst[off:off + L["F"]].copy_(L[far_key][1:])
                 off += L["F"]
 
-    def scatter_targets():
+    def scatter_targets(key, far_key, src):
         off = 0
         for L in d:
             k = L["R"] * (L["S"] + 1)
-            ctx.lattice_scatter_dev(L["R"], L["S"], L["nodes"], P_all[off:off + k])
+            ctx.lattice_scatter_dev(L["R"], L["S"], L[key], src[off:off + k])
             off += k
             if L["F"] > 0:
-                L["far"][1:].copy_(P_all[off:off + L["F"]])
+                L[far_key][1:].copy_(src[off:off + L["F"]])
                 off += L["F"]
 
-    def pack():
+    def pack(set_=0, key="nodes", far_key="far"):
         for i, L in enumerate(d):
-            ctx.pack_lattice_dev(0, i > 0, L["R"], L["S"], L["nodes"], L["gam"], L["rvc4"], L["F"], L["far"],
+            ctx.pack_lattice_dev(set_, i > 0, L["R"], L["S"], L[key], L["gam"], L["rvc4"], L["F"], L[far_key],
                                  L["gamF"], L["rvcF"])
 
     ev_k0, ev_k1 = [], []
 
-    def step(record=False):
-        flush.zero_()                                  # L2 flush (inside the timed region, ~0.05 ms)
-        pack()                                         # filament records from the current lattices
-        gather_targets()
+    def sweep(set_, P, out, record):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
         if m_loc > 0:
-            ctx.vind_dev(0, m_loc, P_all[lo:hi], V_loc)    # THE sweep: m_loc targets x n_src filaments
+            ctx.vind_dev(set_, m_loc, P[lo:hi], out)       # THE sweep: m_loc targets x n_src filaments
         if record:
             e1.record(stream)
             ev_k0.append(e0)
             ev_k1.append(e1)
+
+    def step(record=False):
+        """One wake time step of the reference's fdScheme 3 (main.f90:1002-1115) on device-resident state:
+        core growth, sweep on the current wake, Adams-Bashforth predictor, sweep on the predicted wake,
+        Adams-Moulton corrector; one all-gather of node positions per stage."""
+        flush.zero_()                                      # L2 flush (inside the timed region, ~0.05 ms)
+        for L in d:                                        # rotor_dissipate_wake (classdef.f90:4356-4408)
+            ctx.dissipate_lattice_dev(L["R"], L["S"], L["rvc4"], L["gam"], visc_coeff, nu, 0.0, dt_step)
+        pack(0, "nodes", "far")                            # sources 'C' from the current lattices
+        gather_targets("nodes", "far", P_all)
+        sweep(0, P_all, V, record)                         # stage 1
+        if state["first"]:
+            V1.copy_(V)                                    # iter == 1: plain convection (main.f90:1003-1020)
+            state["first"] = False
         if m_loc > 0:
-            ctx.convect_dev(m_loc, P_all[lo:hi], V_loc, dt_step)
-        allgather_slices(P_all, shard)                 # the one exchange step of a convection stage (NCCL)
-        scatter_targets()
+            ctx.ab2_dev(m_loc, V, V1, Vw)                  # vel = 0.5*(3 vel - vel1)      (main.f90:1032-1034)
+            Pp_all[lo:hi].copy_(P_all[lo:hi])
+            ctx.convect_dev(m_loc, Pp_all[lo:hi], Vw, dt_step)   # convectwake('P')
+        allgather_slices(Pp_all, shard)                    # exchange 1: predicted node positions (NCCL)
+        scatter_targets("nodesP", "farP", Pp_all)
+        pack(1, "nodesP", "farP")                          # sources 'P'
+        sweep(1, Pp_all, Vp, record)                       # stage 2 on the predicted wake
+        if m_loc > 0:
+            ctx.am2_dev(m_loc, Vp, V, Vw)                  # vel = (velPredicted + velStep)*0.5  (main.f90:1094-1096)
+            ctx.convect_dev(m_loc, P_all[lo:hi], Vw, dt_step)    # convectwake('C')
+        allgather_slices(P_all, shard)                     # exchange 2: corrected node positions
+        scatter_targets("nodes", "far", P_all)
+        V1.copy_(V)                                        # vel1 = velStep                  (main.f90:1105-1106)
 
     def barrier():
         if world > 1:
@@ -321,7 +345,7 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     elapsed_ms, kern_ms_max, sweep_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
-    pairs_step = float(m) * float(n_src)
+    pairs_step = 2.0 * float(m) * float(n_src)             # two sweeps per time step
     value = pairs_step * args.steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D + D2H inside the timed region) ----
@@ -338,12 +362,14 @@ def main():
         hV = torch.empty(max(m_loc, 1), 3, dtype=torch.float64).pin_memory()
 
         def e2e_step():
-            # the caller-facing C-ABI calls with HOST buffers: wake lattices in, velocities of this rank's targets out
-            for i, L in enumerate(hl):
-                ctx.pack_lattice(1, i > 0, L["R"], L["S"], L["nodes"], L["gam"], L["rvc4"], L["F"], L["far"],
-                                 L["gamF"], L["rvcF"])
-            if m_loc > 0:
-                ctx.vind_into(1, m_loc, hP, hV)
+            # the caller-facing C-ABI calls with HOST buffers, twice per time step (current and predicted wake):
+            # wake lattices in, velocities of this rank's targets out
+            for stage in range(2):
+                for i, L in enumerate(hl):
+                    ctx.pack_lattice(2, i > 0, L["R"], L["S"], L["nodes"], L["gam"], L["rvc4"], L["F"], L["far"],
+                                     L["gamF"], L["rvcF"])
+                if m_loc > 0:
+                    ctx.vind_into(2, m_loc, hP, hV)
 
         for _ in range(2):
             e2e_step()
@@ -357,9 +383,9 @@ def main():
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {"value": pairs_step * args.steps / float(tw[0]), "unit": "pair-interactions/s",
-               "h2d_bytes_per_step": int(h2d + 24 * m_loc), "d2h_bytes_per_step": int(24 * m_loc),
-               "call": "vlc_pack_lattice (host wake lattices of all blades) + vlc_vind (host targets -> host velocities), "
-                       "pinned buffers, per rank: all sources, its target slice",
+               "h2d_bytes_per_step": int(2 * (h2d + 24 * m_loc)), "d2h_bytes_per_step": int(2 * 24 * m_loc),
+               "call": "per time step 2 x [vlc_pack_lattice (host wake lattices of all blades) + vlc_vind (host targets -> "
+                       "host velocities)], pinned buffers, per rank: all sources, its target slice",
                "ms_per_step": 1e3 * float(tw[0]) / args.steps}
 
     if rank != 0:
@@ -403,9 +429,11 @@ def main():
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": name, "filaments": n_src, "targets": m, "targets_per_rank": per,
-                      "step": "pack lattices -> sweep (targets slice x all filaments) -> convect -> all-gather -> scatter",
+                      "step": "one wake time step of fdScheme 3 on device-resident state: core growth, pack, sweep on the "
+                              "current wake (targets slice x all filaments), AB2 predictor + all-gather, pack, sweep on the "
+                              "predicted wake, AM2 corrector + all-gather",
                       "l2": "flushed every step by a 256 MiB memset inside the timed region",
-                      "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather/stage",
+                      "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather per stage (2 per step)",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
                       "sources": ({"form": "shared-node lattice", "strip_width": int(info["strip_width"]),
                                    "strip_records": int(info["lattice_records"]),
@@ -414,7 +442,7 @@ def main():
                       "precision": ["full: third-order rsqrt refinement, pair error ~1e-16",
                                     "fast: second-order rsqrt refinement, pair error <= 6.4e-13"][args.precision]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-           "stages_per_s": args.steps / (elapsed_ms * 1e-3),
+           "timesteps_per_s": args.steps / (elapsed_ms * 1e-3), "sweeps_per_step": 2,
            "fp64_peak_measured_tflops": peak}
     print(json.dumps(out))
     if world > 1:

@@ -81,6 +81,7 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_vel_order2_Nwake": (None, [_vp, _vp, i32, i32, _vp]),
         "orc_vel_order2_Fwake": (None, [_vp, _vp, i32, _vp]),
         "orc_rotor_dims": (None, [_vp, _vp]),
+        "orc_gridgen": (None, [i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, _vp, _vp]),
         # case driver (vlc_case.c)
         "orc_case_new": (_vp, [i32]),
         "orc_case_free": (None, [_vp]),
@@ -162,6 +163,20 @@ def vind_flat_ld(p1, p2, rvc, gam, wake_flag, P, variant="strict"):
     lib.orc_vind_flat_ld(rec.shape[0], rec.ctypes.data, gam.ctypes.data, None if fl is None else fl.ctypes.data,
                          P.shape[0], P.ctypes.data, V.ctypes.data, A.ctypes.data)
     return V, A
+
+
+def gridgen(nx, ny, nz, xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake,
+            variant="strict"):
+    """program gridgen (src/gridgen.f90): returns (gridCentre, velCentre), each (nz-1, ny-1, nx-1, 3).
+    vrWing / vrNwake: (n, 50) vr_class records; vfNwakeTE / vfFwake: (n, 12) vf_class records + gam arrays."""
+    lib = load(variant)
+    a = [_f64(x) for x in (xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake)]
+    shape = (nz - 1, ny - 1, nx - 1, 3)
+    gc, vc = np.empty(shape), np.empty(shape)
+    lib.orc_gridgen(nx, ny, nz, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].size // VR, a[3].ctypes.data,
+                    a[4].size // VR, a[4].ctypes.data, a[5].size // VF, a[5].ctypes.data, a[6].ctypes.data,
+                    a[7].size // VF, a[7].ctypes.data, a[8].ctypes.data, gc.ctypes.data, vc.ctypes.data)
+    return gc, vc
 
 
 class Rotor:

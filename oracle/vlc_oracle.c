@@ -833,6 +833,63 @@ void orc_vind_flat_ld(long n, const orc_vf_t *fil, const double *gam, const unsi
   }
 }
 
+/* ------------------------------------------------------------------- gridgen */
+
+/* src/gridgen.f90:62-145: Cartesian grid, cell centres, velocity induced by the filaments of one
+ * filamentsNNNNN.dat (libPostprocess.f90:363-473) at every cell centre, plus the free stream.
+ * Quirk C12 restated: the wing loop ASSIGNS (gridgen.f90:122), so only the last wing ring survives.
+ * No |gam| > eps rule here (:125-135).  velCentre, gridCentre: (3, nx-1, ny-1, nz-1) column-major. */
+void orc_gridgen(int nx, int ny, int nz, const double xyzMin[3], const double xyzMax[3], const double vel[3],
+                 long nVrWing, const orc_vr_t *vrWing, long nVrNwake, const orc_vr_t *vrNwake, long nVfNwakeTE,
+                 const orc_vf_t *vfNwakeTE, const double *gamNwakeTE, long nVfFwake, const orc_vf_t *vfFwake,
+                 const double *gamFwake, double *gridCentre, double *velCentre) {
+  double *ax[3];
+  const int n[3] = {nx, ny, nz};
+  for (int d = 0; d < 3; ++d) { /* linspace, libMath.f90:138-157 */
+    ax[d] = (double *)malloc(sizeof(double) * (size_t)n[d]);
+    const double dx = (xyzMax[d] - xyzMin[d]) / (n[d] - 1);
+    for (int i = 0; i < n[d]; ++i) ax[d][i] = i * dx;
+    for (int i = 0; i < n[d]; ++i) ax[d][i] = ax[d][i] + xyzMin[d];
+  }
+  const long cx = nx - 1, cy = ny - 1, cz = nz - 1;
+  /* corner order of gridgen.f90:77-81 as offsets (dx, dy, dz) */
+  static const int off[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {1, 1, 1}, {0, 1, 0}, {0, 1, 1}, {0, 0, 1}, {1, 0, 1}};
+#ifdef _OPENMP
+#pragma omp parallel for collapse(3) schedule(runtime)
+#endif
+  for (long iz = 0; iz < cz; ++iz)
+    for (long iy = 0; iy < cy; ++iy)
+      for (long ix = 0; ix < cx; ++ix) {
+        const long q = ix + cx * (iy + cy * iz);
+        const long idx[3] = {ix, iy, iz};
+        double P[3], v[3] = {0, 0, 0}, t[3];
+        for (int d = 0; d < 3; ++d) {
+          double sum = ax[d][idx[d] + off[0][d]];
+          for (int k = 1; k < 8; ++k) sum = sum + ax[d][idx[d] + off[k][d]];
+          P[d] = sum * 0.125;
+          gridCentre[3 * q + d] = P[d];
+        }
+        for (long f = 0; f < nVrWing; ++f) { /* :121-123 (assignment, not accumulation) */
+          orc_vr_vind(&vrWing[f], P, t);
+          for (int d = 0; d < 3; ++d) v[d] = t[d] * vrWing[f].gam;
+        }
+        for (long f = 0; f < nVrNwake; ++f) { /* :125-127 */
+          orc_vr_vind(&vrNwake[f], P, t);
+          for (int d = 0; d < 3; ++d) v[d] = v[d] + t[d] * vrNwake[f].gam;
+        }
+        for (long f = 0; f < nVfNwakeTE; ++f) { /* :129-131 */
+          orc_vf_vind(&vfNwakeTE[f], P, t);
+          for (int d = 0; d < 3; ++d) v[d] = v[d] + t[d] * gamNwakeTE[f];
+        }
+        for (long f = 0; f < nVfFwake; ++f) { /* :133-135 */
+          orc_vf_vind(&vfFwake[f], P, t);
+          for (int d = 0; d < 3; ++d) v[d] = v[d] + t[d] * gamFwake[f];
+        }
+        for (int d = 0; d < 3; ++d) velCentre[3 * q + d] = v[d] + vel[d]; /* :142-144 */
+      }
+  for (int d = 0; d < 3; ++d) free(ax[d]);
+}
+
 /* ------------------------------------------------- allocation (test harness) */
 
 /* Mirrors the allocations of rotor_init (classdef.f90:3057-3123, :3733-3824 for fdScheme 3)

@@ -172,6 +172,11 @@ void orc_vind_flat(long n, const orc_vf_t *fil, const double *gam, const unsigne
 void orc_vind_flat_ld(long n, const orc_vf_t *fil, const double *gam, const unsigned char *skip,
                       long m, const double *P, double *V, double *Vabs);
 int orc_num_threads(void);
+/* program gridgen (src/gridgen.f90:62-145) */
+void orc_gridgen(int nx, int ny, int nz, const double xyzMin[3], const double xyzMax[3], const double vel[3],
+                 long nVrWing, const orc_vr_t *vrWing, long nVrNwake, const orc_vr_t *vrNwake, long nVfNwakeTE,
+                 const orc_vf_t *vfNwakeTE, const double *gamNwakeTE, long nVfFwake, const orc_vf_t *vfFwake,
+                 const double *gamFwake, double *gridCentre, double *velCentre);
 
 /* ---- allocation / raw views for the Python test harness ---- */
 orc_rotor_t *orc_rotor_new(int nb, int nc, int ns, int nNwake, int nFwake);

@@ -217,3 +217,27 @@ def test_rotor_records_that_are_not_a_lattice_fall_back(ctx, oracle):
         ctx.set_shared_nodes(True)
     assert np.max(np.abs(Va - ro.vind_points(1, P))) < TOL * s
     assert np.array_equal(Va, Vb)
+
+
+def test_far_wake_state_kernels(ctx):
+    """Far-wake core growth / decay (classdef.f90:4397-4404, Fwake_decay :975-980) and strain (:4410-4422, :505-521)
+    on flat device arrays."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 1000
+    rvc, gam = rng.uniform(0.01, 0.1, n), rng.normal(size=n)
+    d_r, d_g = torch.from_numpy(rvc.copy()).cuda(), torch.from_numpy(gam.copy()).cuda()
+    a, nu, k, dt = 5000.0, 1.81e-5, 0.2, 2.8e-3
+    ctx.dissipate_dev(n, d_r, n, d_g, a, nu, k, dt)
+    ctx.sync()
+    assert np.array_equal(d_r.cpu().numpy(), np.sqrt(rvc * rvc + 4.0 * 1.2564 * a * nu * dt))
+    assert np.max(np.abs(d_g.cpu().numpy() / (gam * np.exp(-k * dt)) - 1.0)) < 4e-16
+    p1, p2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    l0, rvc0 = rng.uniform(0.5, 2.0, n), rng.uniform(0.01, 0.1, n)
+    out = torch.zeros(n, dtype=torch.float64).cuda()
+    ctx.strain_dev(n, torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda(), torch.from_numpy(l0).cuda(),
+                   torch.from_numpy(rvc0).cuda(), out)
+    ctx.sync()
+    d = p1 - p2
+    lc = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    assert np.max(np.abs(out.cpu().numpy() / (rvc0 * np.sqrt(l0 / lc)) - 1.0)) < 4e-16

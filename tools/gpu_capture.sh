@@ -22,7 +22,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline \
   > $OUT/bench_under_ncu_$TAG.log 2>&1
 # one full capture of the dominant kernel
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:bs_lattice -s 2 -c 1 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:bs_lattice -s 4 -c 1 \
   -f -o $OUT/prof_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline \
   > $OUT/ncu_full_$TAG.log 2>&1
 ls -la $OUT | tail -20

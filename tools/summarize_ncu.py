@@ -94,7 +94,7 @@ def full(tag: str) -> str | None:
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     out = [f"# ncu --set full capture `{tag}` of the dominant kernel", "",
-           "command: `ncu --set full --clock-control none --import-source on -k regex:bs_lattice -s 2 -c 1 python bench.py "
+           "command: `ncu --set full --clock-control none --import-source on -k regex:bs_lattice -s 4 -c 1 python bench.py "
            "--steps 1 --warmup 3 --no-e2e --no-cpu-baseline` (1 000 192 filaments x 258 176 targets)", ""]
     for d in data:
         out.append(f"## `{short(d[idx['Kernel Name']])}`  grid {d[idx['Grid Size']]} block {d[idx['Block Size']]}")
