@@ -204,6 +204,21 @@ int vlc_dissipate_lattice_dev(vlc_ctx* ctx, int nrows, int ns, double* d_rvc4, d
 int vlc_lattice_targets_dev(vlc_ctx* ctx, int nrows, int ns, const double* d_nodes, double* d_P);
 int vlc_lattice_scatter_dev(vlc_ctx* ctx, int nrows, int ns, double* d_nodes, const double* d_P);
 
+/* ---- the Eulerian grid tool ------------------------------------------------------------------ */
+/*
+ * = program gridgen (src/gridgen.f90:62-145): velocity at the (nx-1)(ny-1)(nz-1) cell centres of the Cartesian grid
+ * xyzMin..xyzMax induced by the filaments of one filamentsNNNNN.dat (written by filaments2file,
+ * src/libPostprocess.f90:363-473), plus the free stream `vel`.  vrWing / vrNwake: vr_class records (50 doubles);
+ * vfNwakeTE / vfFwake: vf_class records (12 doubles) with their circulation arrays.  The file's arithmetic is kept,
+ * including its quirk that the wing loop assigns instead of accumulating (:122: only the last wing ring counts)
+ * and that no |gam| > eps rule applies here.  gridCentre (may be NULL) and velCentre: (3, nx-1, ny-1, nz-1).
+ * Uses source set VLC_MAX_SETS-1 as scratch.
+ */
+int vlc_gridgen(vlc_ctx* ctx, int nx, int ny, int nz, const double* xyzMin, const double* xyzMax, const double* vel,
+                int64_t nVrWing, const double* vrWing, int64_t nVrNwake, const double* vrNwake, int64_t nVfNwakeTE,
+                const double* vfNwakeTE, const double* gamNwakeTE, int64_t nVfFwake, const double* vfFwake,
+                const double* gamFwake, double* gridCentre, double* velCentre);
+
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Register-resident DFMA chains on every SM: returns sustained FP64 FMA rate in flop/s (DFMA = 2)
  * and the elapsed milliseconds; used by bench.py as the measured FP64 roofline denominator

@@ -125,6 +125,7 @@ def load_library() -> C.CDLL:
         "vlc_last_sweep_ms": (i32, [_vp, _dp, _dp]),
         "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
+        "vlc_gridgen": (i32, [_vp, i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, _vp, _vp]),
         "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
         "vlc_probe_rsqrt": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     }
@@ -336,6 +337,16 @@ class Context:
         A = np.empty((N, N), dtype=np.float64, order="F")
         self._ck(self.lib.vlc_rotor_get_AIC_inv(self.h, ir, _ptr(A)))
         return A
+
+    def gridgen(self, nx, ny, nz, xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake):
+        """program gridgen (src/gridgen.f90): (gridCentre, velCentre), each (nz-1, ny-1, nx-1, 3)."""
+        a = [_f64(x) for x in (xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake)]
+        shape = (nz - 1, ny - 1, nx - 1, 3)
+        gc, vc = np.empty(shape), np.empty(shape)
+        self._ck(self.lib.vlc_gridgen(self.h, nx, ny, nz, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), a[3].size // VR_DOUBLES,
+                                      _ptr(a[3]), a[4].size // VR_DOUBLES, _ptr(a[4]), a[5].size // 12, _ptr(a[5]),
+                                      _ptr(a[6]), a[7].size // 12, _ptr(a[7]), _ptr(a[8]), _ptr(gc), _ptr(vc)))
+        return gc, vc
 
     # -- tier 3 (device pointers: torch tensors or ints) --------------------------------------
     def convect_dev(self, n, x, v, dt):

@@ -1461,6 +1461,97 @@ extern "C" int vlc_lattice_scatter_dev(vlc_ctx* c, int nrows, int ns, double* no
   return VLC_OK;
 }
 
+// ============================================================================ gridgen
+
+extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyzMin, const double* xyzMax,
+                           const double* vel, int64_t nVrWing, const double* vrWing, int64_t nVrNwake,
+                           const double* vrNwake, int64_t nVfNwakeTE, const double* vfNwakeTE, const double* gamNwakeTE,
+                           int64_t nVfFwake, const double* vfFwake, const double* gamFwake, double* gridCentre,
+                           double* velCentre) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (nx < 2 || ny < 2 || nz < 2 || !xyzMin || !xyzMax || !vel || !velCentre) return fail(c, VLC_ERR_ARG, "bad grid arguments");
+  if (xyzMin[0] > xyzMax[0] || xyzMin[1] > xyzMax[1] || xyzMin[2] > xyzMax[2])
+    return fail(c, VLC_ERR_ARG, "ERROR: All XYZmin values should be greater than XYZmax values");  // gridgen.f90:43-45
+  if (nVrWing < 0 || nVrNwake < 0 || nVfNwakeTE < 0 || nVfFwake < 0 || (nVrWing > 0 && !vrWing) ||
+      (nVrNwake > 0 && !vrNwake) || (nVfNwakeTE > 0 && (!vfNwakeTE || !gamNwakeTE)) ||
+      (nVfFwake > 0 && (!vfFwake || !gamFwake)))
+    return fail(c, VLC_ERR_ARG, "bad filament arguments");
+  cudaStream_t st = c->stream;
+  // sources in the file's order; the wing loop of gridgen.f90:121-123 assigns, so only its last ring counts (C12)
+  const long long nw = nVrWing > 0 ? 1 : 0;
+  const long long n = 4 * nw + 4 * (long long)nVrNwake + nVfNwakeTE + nVfFwake;
+  const long long n_pad = pad_tile(n);
+  const size_t up = (size_t)(nw + nVrNwake) * vlc::kVr + (size_t)(nVfNwakeTE + nVfFwake) * (vlc::kVf + 1);
+  if ((rc = reserve(c, c->scratch, up + 8))) return rc;
+  SourceSet& s = c->sets[VLC_MAX_SETS - 1];  // the last set is the grid tool's scratch set
+  if ((rc = reserve(c, s.rec, (size_t)n_pad * vlc::kSrcDoubles + 8))) return rc;
+  double* d = c->scratch.p;
+  double* rec = s.rec.p;
+  long long off = 0;
+  auto h2d = [&](double* dst, const double* src, size_t cnt) -> int {
+    CUDA_OK(c, cudaMemcpyAsync(dst, src, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+    return VLC_OK;
+  };
+  if (nw) {
+    if ((rc = h2d(d, vrWing + (size_t)(nVrWing - 1) * vlc::kVr, vlc::kVr))) return rc;
+    vlc::pack_rings_kernel<<<1, 32, 0, st>>>(d, vlc::kVr, 1, 0, 1, 1, 0xF, 4, 1.0, 0, rec);
+    c->launches++;
+    d += vlc::kVr;
+    off += 4;
+  }
+  if (nVrNwake > 0) {
+    if ((rc = h2d(d, vrNwake, (size_t)nVrNwake * vlc::kVr))) return rc;
+    if (nVrNwake > 0x7fffffff / 8) return fail(c, VLC_ERR_ARG, "too many near-wake rings for one file");
+    vlc::pack_rings_kernel<<<blocks_for(4 * nVrNwake, 256), 256, 0, st>>>(d, vlc::kVr, (int)nVrNwake, 0, (int)nVrNwake, 1,
+                                                                          0xF, 4, 1.0, 0, rec + (size_t)off * vlc::kSrcDoubles);
+    c->launches++;
+    d += (size_t)nVrNwake * vlc::kVr;
+    off += 4 * nVrNwake;
+  }
+  const double* vfs[2] = {vfNwakeTE, vfFwake};
+  const double* gms[2] = {gamNwakeTE, gamFwake};
+  const long long cnt[2] = {nVfNwakeTE, nVfFwake};
+  for (int k = 0; k < 2; ++k)
+    if (cnt[k] > 0) {
+      if ((rc = h2d(d, vfs[k], (size_t)cnt[k] * vlc::kVf))) return rc;
+      if ((rc = h2d(d + (size_t)cnt[k] * vlc::kVf, gms[k], (size_t)cnt[k]))) return rc;
+      vlc::pack_vf_gam_kernel<<<blocks_for(cnt[k], 256), 256, 0, st>>>(cnt[k], d, d + (size_t)cnt[k] * vlc::kVf,
+                                                                       rec + (size_t)off * vlc::kSrcDoubles);
+      c->launches++;
+      d += (size_t)cnt[k] * (vlc::kVf + 1);
+      off += cnt[k];
+    }
+  if (n_pad > n) {
+    vlc::pack_null_kernel<<<blocks_for(n_pad - n, 256), 256, 0, st>>>(n_pad - n, rec + (size_t)n * vlc::kSrcDoubles);
+    c->launches++;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  s.n = n;
+  s.n_pad = n_pad;
+  s.has_shared = false;
+  s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = 0;
+  // targets = cell centres, computed on the device with the file's arithmetic
+  const long long m = (long long)(nx - 1) * (ny - 1) * (nz - 1);
+  if ((rc = reserve(c, c->stage_P, 3 * (size_t)m))) return rc;
+  if ((rc = reserve(c, c->stage_V, 3 * (size_t)m))) return rc;
+  const double dx = (xyzMax[0] - xyzMin[0]) / (nx - 1), dy = (xyzMax[1] - xyzMin[1]) / (ny - 1),
+               dz = (xyzMax[2] - xyzMin[2]) / (nz - 1);
+  vlc::grid_centres_kernel<<<blocks_for(m, 256), 256, 0, st>>>(nx, ny, nz, xyzMin[0], xyzMin[1], xyzMin[2], dx, dy, dz,
+                                                                c->stage_P.p);
+  c->launches++;
+  if ((rc = sweep(c, s.rec.p, s.n_pad, m, c->stage_P.p, c->stage_V.p))) return rc;
+  vlc::add_freestream_kernel<<<blocks_for(m, 256), 256, 0, st>>>(m, vel[0], vel[1], vel[2], c->stage_V.p);
+  c->launches++;
+  CUDA_OK(c, cudaGetLastError());
+  if (gridCentre)
+    CUDA_OK(c, cudaMemcpyAsync(gridCentre, c->stage_P.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(c, cudaMemcpyAsync(velCentre, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(c, cudaStreamSynchronize(st));
+  return VLC_OK;
+}
+
 // ============================================================================ measurement
 
 extern "C" int vlc_measure_fp64_peak(vlc_ctx* c, int iters, double* flops_per_s, double* ms_out) {

@@ -378,4 +378,48 @@ __global__ void pack_rings_shared_kernel(const double* __restrict__ base, int st
   fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1), (int)(q % nr1), rec + q * RD, unmergeable);
 }
 
+
+// ---- gridgen (src/gridgen.f90) ---------------------------------------------------------------------------
+// vf_class records (12 doubles) with a separate circulation array; no |gam| > eps rule (gridgen.f90:129-135).
+__global__ void pack_vf_gam_kernel(long long n, const double* __restrict__ vf, const double* __restrict__ gam,
+                                   double* __restrict__ rec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* f = vf + (size_t)kVf * i;
+  write_rec(rec + i * kSrcDoubles, f[0], f[1], f[2], f[3], f[4], f[5], f[kVfRvc], strength(gam[i], false));
+}
+
+// Cell centres of the Cartesian grid exactly as gridgen.f90:62-84 computes them: linspace (libMath.f90:138-157:
+// i*dx then + xstart), the 8 corners summed in the file's order, times 0.125.  P: (3, nx-1, ny-1, nz-1).
+__global__ void grid_centres_kernel(int nx, int ny, int nz, double x0, double y0, double z0, double dx, double dy,
+                                    double dz, double* __restrict__ P) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cx = nx - 1, cy = ny - 1, cz = nz - 1;
+  if (q >= cx * cy * cz) return;
+  const int ix = (int)(q % cx), iy = (int)((q / cx) % cy), iz = (int)(q / (cx * cy));
+  const double xa = __dadd_rn(__dmul_rn((double)ix, dx), x0), xb = __dadd_rn(__dmul_rn((double)(ix + 1), dx), x0);
+  const double ya = __dadd_rn(__dmul_rn((double)iy, dy), y0), yb = __dadd_rn(__dmul_rn((double)(iy + 1), dy), y0);
+  const double za = __dadd_rn(__dmul_rn((double)iz, dz), z0), zb = __dadd_rn(__dmul_rn((double)(iz + 1), dz), z0);
+  // corner order :77-81: (0,0,0) (1,0,0) (1,1,0) (1,1,1) (0,1,0) (0,1,1) (0,0,1) (1,0,1)
+  double sx = xa, sy = ya, sz = za;
+  sx = __dadd_rn(sx, xb); sy = __dadd_rn(sy, ya); sz = __dadd_rn(sz, za);
+  sx = __dadd_rn(sx, xb); sy = __dadd_rn(sy, yb); sz = __dadd_rn(sz, za);
+  sx = __dadd_rn(sx, xb); sy = __dadd_rn(sy, yb); sz = __dadd_rn(sz, zb);
+  sx = __dadd_rn(sx, xa); sy = __dadd_rn(sy, yb); sz = __dadd_rn(sz, za);
+  sx = __dadd_rn(sx, xa); sy = __dadd_rn(sy, yb); sz = __dadd_rn(sz, zb);
+  sx = __dadd_rn(sx, xa); sy = __dadd_rn(sy, ya); sz = __dadd_rn(sz, zb);
+  sx = __dadd_rn(sx, xb); sy = __dadd_rn(sy, ya); sz = __dadd_rn(sz, zb);
+  P[3 * q + 0] = sx * 0.125;
+  P[3 * q + 1] = sy * 0.125;
+  P[3 * q + 2] = sz * 0.125;
+}
+
+__global__ void add_freestream_kernel(long long m, double vx, double vy, double vz, double* __restrict__ V) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  V[3 * q + 0] = V[3 * q + 0] + vx;
+  V[3 * q + 1] = V[3 * q + 1] + vy;
+  V[3 * q + 2] = V[3 * q + 2] + vz;
+}
+
 }  // namespace vlc
