@@ -146,15 +146,16 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
       }
 #pragma unroll
       for (int k = 0; k < T; ++k) {
-        NodeQ n[W + 1];
-#pragma unroll
-        for (int i = 0; i <= W; ++i) n[i] = node_eval(px[k], py[k], pz[k], q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+        // nodes are evaluated one column ahead of the edges that need them (keeps few node quantities live)
+        NodeQ cur = node_eval(px[k], py[k], pz[k], q[0], q[1], q[2]);
 #pragma unroll
         for (int i = 0; i < W; ++i) {
+          const NodeQ nxt = node_eval(px[k], py[k], pz[k], q[3 * i + 3], q[3 * i + 4], q[3 * i + 5]);
           const double* e = &q[NP + 10 * i];
-          edge_accumulate(prev[k][i], n[i], e[5], e[6], e[7], e[8], e[9], vx[k], vy[k], vz[k]);  // streamwise Nprev_i -> N_i
-          edge_accumulate(n[i], n[i + 1], e[0], e[1], e[2], e[3], e[4], vx[k], vy[k], vz[k]);    // spanwise   N_i -> N_{i+1}
-          prev[k][i] = n[i];
+          edge_accumulate(prev[k][i], cur, e[5], e[6], e[7], e[8], e[9], vx[k], vy[k], vz[k]);  // streamwise Nprev_i -> N_i
+          edge_accumulate(cur, nxt, e[0], e[1], e[2], e[3], e[4], vx[k], vy[k], vz[k]);         // spanwise   N_i -> N_{i+1}
+          prev[k][i] = cur;
+          cur = nxt;
         }
       }
     }
