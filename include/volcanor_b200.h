@@ -157,6 +157,9 @@ int vlc_convect_dev(vlc_ctx* ctx, int64_t n, double* d_x, const double* d_v, dou
 int vlc_ab2_dev(vlc_ctx* ctx, int64_t n, const double* d_v, const double* d_v1, double* d_out);
 /* Adams-Moulton corrector velocity: out = (vp + vs) * 0.5   (main.f90:1094-1096) */
 int vlc_am2_dev(vlc_ctx* ctx, int64_t n, const double* d_vp, const double* d_vs, double* d_out);
+/* Predictor-corrector (fdScheme 1) velocity: vel_order2_Nwake / vel_order2_Fwake (libCommon.f90:213-258) on
+ * (3, rows, cols) arrays (cols = 1 for the far wake); out must not alias the inputs. */
+int vlc_vel_order2_dev(vlc_ctx* ctx, int rows, int cols, const double* d_vn, const double* d_vnp1, double* d_out);
 /* rVc <- sqrt(rVc^2 + 4*1.2564*apparentViscCoeff*nu*dt); gam <- gam*exp(-decayCoeff*dt)
  * (rotor_dissipate_wake classdef.f90:4356-4408, vr_decay :662-668).  Either pointer may be NULL. */
 int vlc_dissipate_dev(vlc_ctx* ctx, int64_t n_rvc, double* d_rvc, int64_t n_gam, double* d_gam,

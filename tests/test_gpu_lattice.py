@@ -241,3 +241,18 @@ def test_far_wake_state_kernels(ctx):
     d = p1 - p2
     lc = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
     assert np.max(np.abs(out.cpu().numpy() / (rvc0 * np.sqrt(l0 / lc)) - 1.0)) < 4e-16
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 3), (2, 2), (7, 6), (40, 1)])
+def test_vel_order2_vs_oracle(ctx, oracle, rows, cols):
+    """fdScheme 1 averaging (libCommon.f90:213-258) bit for bit against the oracle's restatement."""
+    import torch
+    rng = np.random.default_rng(rows * 10 + cols)
+    vn, vp = rng.normal(size=(cols, rows, 3)), rng.normal(size=(cols, rows, 3))
+    ref = np.empty_like(vn)
+    lib = oracle.load()
+    lib.orc_vel_order2_Nwake(vn.ctypes.data, vp.ctypes.data, rows, cols, ref.ctypes.data)
+    out = torch.zeros(cols, rows, 3, dtype=torch.float64).cuda()
+    ctx.vel_order2_dev(rows, cols, torch.from_numpy(vn).cuda(), torch.from_numpy(vp).cuda(), out)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), ref)

@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
         "vlc_convect_dev": (i32, [_vp, i64, _vp, _vp, C.c_double]),
         "vlc_ab2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
         "vlc_am2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
+        "vlc_vel_order2_dev": (i32, [_vp, i32, i32, _vp, _vp, _vp]),
         "vlc_dissipate_dev": (i32, [_vp, i64, _vp, i64, _vp, C.c_double, C.c_double, C.c_double, C.c_double]),
         "vlc_dissipate_lattice_dev": (i32, [_vp, i32, i32, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double]),
         "vlc_strain_dev": (i32, [_vp, i64, _vp, _vp, _vp, _vp, _vp]),
@@ -357,6 +358,9 @@ class Context:
 
     def am2_dev(self, n, vp, vs, out):
         self._ck(self.lib.vlc_am2_dev(self.h, n, _ptr(vp), _ptr(vs), _ptr(out)))
+
+    def vel_order2_dev(self, rows, cols, vn, vnp1, out):
+        self._ck(self.lib.vlc_vel_order2_dev(self.h, rows, cols, _ptr(vn), _ptr(vnp1), _ptr(out)))
 
     def dissipate_dev(self, n_rvc, rvc, n_gam, gam, apparentViscCoeff, kinematicVisc, decayCoeff, dt):
         self._ck(self.lib.vlc_dissipate_dev(self.h, n_rvc, _ptr(rvc), n_gam, _ptr(gam), apparentViscCoeff,

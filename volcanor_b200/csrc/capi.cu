@@ -1209,6 +1209,17 @@ extern "C" int vlc_am2_dev(vlc_ctx* c, int64_t n, const double* vp, const double
   return VLC_OK;
 }
 
+extern "C" int vlc_vel_order2_dev(vlc_ctx* c, int rows, int cols, const double* vn, const double* vnp1, double* out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (rows < 0 || cols < 0 || (rows > 0 && cols > 0 && (!vn || !vnp1 || !out)) || out == vn || out == vnp1)
+    return fail(c, VLC_ERR_ARG, "bad arguments (out must not alias the inputs)");
+  const long long n = 3LL * rows * cols;
+  LAUNCH1D(c, vlc::vel_order2_kernel, n, rows, cols, vn, vnp1, out);
+  return VLC_OK;
+}
+
 extern "C" int vlc_dissipate_dev(vlc_ctx* c, int64_t n_rvc, double* rvc, int64_t n_gam, double* gam,
                                  double apparentViscCoeff, double nu, double decayCoeff, double dt) {
   CHECK_CTX(c);

@@ -25,6 +25,19 @@ __global__ void am2_kernel(long long n, const double* __restrict__ vp, const dou
   if (i < n) out[i] = (vp[i] + vs[i]) * 0.5;
 }
 
+// libCommon.f90:213-258  vel_order2_Nwake / vel_order2_Fwake (fdScheme 1): arrays (3, rows, cols), cols = 1 for the
+// far wake.  Row 1 and row `rows`: (vnp1 + vn)*0.5; inner rows: (((vnp1(i) + vnp1(i-1)) + vn(i+1)) + vn(i))*0.25.
+__global__ void vel_order2_kernel(int rows, int cols, const double* __restrict__ vn, const double* __restrict__ vnp1,
+                                  double* __restrict__ out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 3LL * rows * cols) return;
+  const int i = (int)((q / 3) % rows);
+  if (i == 0 || i == rows - 1)
+    out[q] = __dmul_rn(__dadd_rn(vnp1[q], vn[q]), 0.5);
+  else
+    out[q] = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(vnp1[q], vnp1[q - 3]), vn[q + 3]), vn[q]), 0.25);
+}
+
 // classdef.f90:4368-4370 / :4398-4401  rVc = sqrt(rVc**2 + 4*oseenParameter*apparentViscCoeff*nu*dt)
 __device__ __forceinline__ double grow(double rvc, double a, double nu, double dt) {
   return sqrt(__dadd_rn(__dmul_rn(rvc, rvc), 4.0 * 1.2564 * a * nu * dt));
