@@ -204,7 +204,7 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
         best = (waves >= 1.0) ? score : eff;
         best_s = (int)s;
       }
-      if (waves >= 8.0 && eff > 0.97) break;
+      if (waves >= 8.0 && eff > 0.995) break;  // whole waves matter: equal-work CTAs leave a (1 - eff) tail idle
     }
     nsplit = best_s;
   }
@@ -334,7 +334,7 @@ int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_
       best = score;
       best_s = (int)s;
     }
-    if (waves >= 8.0 && eff > 0.97) break;
+    if (waves >= 8.0 && eff > 0.995) break;  // whole waves matter: equal-work CTAs leave a (1 - eff) tail idle
   }
   return best_s;
 }
