@@ -30,7 +30,9 @@ class VlcError(RuntimeError):
 
 
 def lib_path() -> Path:
-    return _HERE / "libvolcanor_b200.so"
+    # VOLCANOR_B200_LIB selects an experimental build of the same sources (tuning runs); default = the in-tree library
+    alt = os.environ.get("VOLCANOR_B200_LIB")
+    return Path(alt) if alt else _HERE / "libvolcanor_b200.so"
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:

@@ -31,7 +31,10 @@ namespace vlc {
 // FP64 instructions per ring = (11 (W+1) + 50 W) / W = 72, 66.5, 64.7, 63.75 for W = 1..4.
 __host__ __device__ constexpr int lat_nodes_pad(int W) { return (3 * (W + 1) + 1) / 2 * 2; }
 __host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_nodes_pad(W) + 10 * W; }
-__host__ __device__ constexpr int lat_tile(int W) { return W <= 2 ? 64 : 32; }  // records per shared-memory tile
+#ifndef VLC_LAT_TILE_DIV
+#define VLC_LAT_TILE_DIV 1
+#endif
+__host__ __device__ constexpr int lat_tile(int W) { return (W <= 2 ? 64 : 32) / VLC_LAT_TILE_DIV; }  // records per shared-memory tile
 
 struct NodeQ {
   double rx, ry, rz, u;  // r = P - X, u = 1/|r|

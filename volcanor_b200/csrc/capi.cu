@@ -22,6 +22,10 @@
 namespace {
 
 constexpr int kThreads = 128;  // threads per sweep CTA
+#ifndef VLC_LAT_THREADS
+#define VLC_LAT_THREADS 128
+#endif
+constexpr int kLatThreads = VLC_LAT_THREADS;  // threads per lattice-kernel CTA
 constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
 constexpr int kStages = 3;     // TMA ring depth
 // Lattice kernel shape (vlc_set_lattice_tuning): strip width W in 1..4, targets per thread T in 1..3; 0 = automatic:
@@ -297,9 +301,9 @@ inline long long pad_lat(long long n, int W) { return (n + lat_tile_of(W) - 1) /
 int query_occ_lat_all(vlc_ctx* c) {
 #define X(WW, TT, MB)                                                                                           \
   {                                                                                                             \
-    auto kern = vlc::bs_lattice_kernel<WW, TT, kThreads, kStages, MB>;                                          \
+    auto kern = vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB>;                                          \
     CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lat_smem_of(WW)));  \
-    CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lat[WW][TT], kern, kThreads, lat_smem_of(WW))); \
+    CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lat[WW][TT], kern, kLatThreads, lat_smem_of(WW))); \
   }
   VLC_LAT_SHAPES(X)
 #undef X
@@ -317,7 +321,7 @@ bool lat_shape_exists(int W, int T) {
 int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad) {
   if (c->tune_nsplit > 0) return c->tune_nsplit;
   const long long tiles = n_lat_pad / lat_tile_of(W);
-  const long long ttiles = (m + (long long)kThreads * T - 1) / ((long long)kThreads * T);
+  const long long ttiles = (m + (long long)kLatThreads * T - 1) / ((long long)kLatThreads * T);
   const long long slots = (long long)c->sm_count * (c->occ_lat[W][T] > 0 ? c->occ_lat[W][T] : 2);
   long long max_split = tiles / 4;
   if (max_split < 1) max_split = 1;
@@ -348,7 +352,7 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   const int LW = s.lat_W;
   const long long lat_tiles = s.n_lat_pad / lat_tile_of(LW);
   int LT = (c->lat_T >= 1 && c->lat_T <= 3) ? c->lat_T : kLatBestT[LW];
-  if (m <= kThreads) LT = 1;
+  if (m <= kLatThreads) LT = 1;
   while (LT > 1 && !lat_shape_exists(LW, LT)) --LT;
   int ns_l = plan_lattice_split(c, LW, LT, m, s.n_lat_pad);
   const long long lat_chunk_tiles = (lat_tiles + ns_l - 1) / ns_l;
@@ -362,11 +366,11 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   double* part = c->part.p;
   cudaEventRecord(c->ev[0], c->stream);
   {
-    dim3 grid(blocks_for(m, kThreads * LT), (unsigned)ns_l, 1);
+    dim3 grid(blocks_for(m, kLatThreads * LT), (unsigned)ns_l, 1);
     const long long lat_chunk = lat_chunk_tiles * lat_tile_of(LW);
 #define X(WW, TT, MB)                                                                                              \
   if (LW == WW && LT == TT)                                                                                        \
-    vlc::bs_lattice_kernel<WW, TT, kThreads, kStages, MB><<<grid, kThreads, lat_smem_of(WW), c->stream>>>(          \
+    vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>(          \
         s.lat.p, lat_chunk, s.n_lat_pad, dP, m, part, s.d_unmergeable, 0);
     VLC_LAT_SHAPES(X)
 #undef X
