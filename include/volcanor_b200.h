@@ -196,6 +196,9 @@ int vlc_set_lattice_tuning(vlc_ctx* ctx, int strip_width, int targets_per_thread
  * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel, 0 if
  * the flat one (reads the device flag: synchronises), -1 for a flat-only set, out[4] = strip width of the records. */
 int vlc_set_info(vlc_ctx* ctx, int set, int64_t* out);
+/* Same five numbers for the packed [wing | wake] set of rotor ir (packs it if needed): tells whether the uploaded
+ * records describe a lattice the shared-node kernel can use (out[3] = 1) or the flat enumeration is used (0). */
+int vlc_rotor_info(vlc_ctx* ctx, int ir, int predicted, int64_t* out);
 /* rotor_dissipate_wake on a lattice (classdef.f90:4364-4393): vf1 grows, vf3 <- vf1, gam decays, vf2 grows,
  * vf4(i) <- vf2(i-1) for i > first row. */
 int vlc_dissipate_lattice_dev(vlc_ctx* ctx, int nrows, int ns, double* d_rvc4, double* d_gam,

@@ -48,6 +48,9 @@ def test_katzNplotkin_50_steps_CL_and_circulation(ctx, oracle):
     print(f"K&P AR-4, 50 steps: max rel CL err {err[:, 0].max():.3e}, max rel gamVec err {err[:, 1].max():.3e}, "
           f"{h.stats['calls']} uploads")
     assert err[:, 0].max() < TOL_HISTORY and err[:, 1].max() < TOL_HISTORY
+    # the reference's own wake records describe a lattice: the shared-node kernel did the work (no silent fallback)
+    info = ctx.rotor_info(0)
+    assert info["shared_active"] == 1 and info["strip_width"] == 2 and info["lattice_records"] == 13 * 51, info
     # and the GPU-driven run still reproduces the reference's golden file to its 7 printed digits
     fx = json.loads((GOLDEN / "katzNplotkin_AR04.json").read_text())
     ref50 = fx["ref_ForceNonDim"]["rows"][50][1]
@@ -62,6 +65,9 @@ def test_elevate_rotor_50_steps_CT_and_circulation(ctx, oracle):
     a, b, err, h = _run_pair(oracle, ctx, "elevateTest", 50)
     print(f"elevateTest, 50 steps: max rel CT err {err[:, 0].max():.3e}, max rel gamVec err {err[:, 1].max():.3e}")
     assert err[:, 0].max() < TOL_HISTORY and err[:, 1].max() < TOL_HISTORY
+    for pred in (False, True):       # 5 blades (4 of them rotated copies), far wake present: still a lattice per blade
+        info = ctx.rotor_info(0, pred)
+        assert info["shared_active"] == 1 and info["strip_width"] == 4, info
     fx = json.loads((GOLDEN / "elevateTest.json").read_text())
     assert abs(b.force_nondim(0)[0] - fx["ref_ForceNonDim"]["rows"][50][1]) < 5e-9
     assert np.max(np.abs(a.rotor(0).waF(0) - b.rotor(0).waF(0))) < 1e-9

@@ -125,6 +125,7 @@ def load_library() -> C.CDLL:
         "vlc_set_shared_nodes": (i32, [_vp, i32]),
         "vlc_set_lattice_tuning": (i32, [_vp, i32, i32]),
         "vlc_set_info": (i32, [_vp, i32, C.POINTER(i64)]),
+        "vlc_rotor_info": (i32, [_vp, i32, i32, C.POINTER(i64)]),
         "vlc_last_sweep_ms": (i32, [_vp, _dp, _dp]),
         "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
@@ -395,6 +396,12 @@ class Context:
     def set_info(self, set_: int) -> dict:
         out = (C.c_int64 * 5)()
         self._ck(self.lib.vlc_set_info(self.h, set_, out))
+        return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3],
+                "strip_width": out[4]}
+
+    def rotor_info(self, ir: int, predicted: bool = False) -> dict:
+        out = (C.c_int64 * 5)()
+        self._ck(self.lib.vlc_rotor_info(self.h, ir, int(predicted), out))
         return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3],
                 "strip_width": out[4]}
 

@@ -89,6 +89,8 @@ struct vlc_ctx {
   int tune_T = 0, tune_nsplit = 0;
   bool shared_nodes = true;  // lattice sources: use the shared-node kernel when the set allows it
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // last sweep: before / after the dominant kernel, after the reduce
+  cudaStream_t aux = nullptr;                       // low-priority side stream: the flat remainder fills the lattice kernel's tail
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool ev_valid = false;
   int lat_W = 0, lat_T = 0;          // lattice kernel shape (vlc_set_lattice_tuning), 0 = automatic
   int occ_lat[5][4] = {};            // resident CTAs/SM of the lattice kernel [W][T]
@@ -364,6 +366,8 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   int rc = reserve(c, c->part, (size_t)(ns_l + ns_r + pf.nsplit) * len);
   if (rc) return rc;
   double* part = c->part.p;
+  const bool side = (c->aux != nullptr);
+  if (side) CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));  // inputs (records, targets, partial buffer) are ready here
   cudaEventRecord(c->ev[0], c->stream);
   {
     dim3 grid(blocks_for(m, kLatThreads * LT), (unsigned)ns_l, 1);
@@ -378,10 +382,21 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
     c->launches++;
   }
   cudaEventRecord(c->ev[1], c->stream);
-  if (ns_r > 0 && (rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part + (size_t)ns_l * len, s.d_unmergeable, 0)))
-    return rc;
-  if ((rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part + (size_t)(ns_l + ns_r) * len, s.d_unmergeable, 1)))
-    return rc;
+  // The flat remainder (and the fallback, which exits at once when the set is mergeable) go to a low-priority side
+  // stream launched AFTER the lattice kernel: their CTAs fill the SMs that the lattice kernel's last wave leaves idle.
+  cudaStream_t main_stream = c->stream;
+  if (side) {
+    CUDA_OK(c, cudaStreamWaitEvent(c->aux, c->ev_fork, 0));  // ev_fork was recorded BEFORE the lattice kernel
+    c->stream = c->aux;
+  }
+  if (ns_r > 0) rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part + (size_t)ns_l * len, s.d_unmergeable, 0);
+  if (!rc) rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part + (size_t)(ns_l + ns_r) * len, s.d_unmergeable, 1);
+  c->stream = main_stream;
+  if (rc) return rc;
+  if (side) {
+    CUDA_OK(c, cudaEventRecord(c->ev_join, c->aux));
+    CUDA_OK(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+  }
   vlc::bs_reduce_select_kernel<<<blocks_for((long long)len, 256), 256, 0, c->stream>>>(
       part, s.d_unmergeable, ns_l + ns_r, pf.nsplit, (long long)len, dV);
   CUDA_OK(c, cudaGetLastError());
@@ -676,6 +691,13 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
   }
   c->stream = c->own_stream;
   for (auto& e : c->ev) cudaEventCreate(&e);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = numerically largest = least urgent
+    if (cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, lo) != cudaSuccess) c->aux = nullptr;
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  }
   int rc = 0;
   rc |= query_occ<1, 5>(c, &c->occ[1]);
   rc |= query_occ<2, 4>(c, &c->occ[2]);
@@ -727,6 +749,9 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   if (c->solver) cusolverDnDestroy(c->solver);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->aux) cudaStreamDestroy(c->aux);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return VLC_OK;
@@ -1419,6 +1444,30 @@ extern "C" int vlc_set_info(vlc_ctx* c, int set, int64_t* out) {
   if (s.has_shared && s.d_unmergeable) {
     int f = 0;
     CUDA_OK(c, cudaMemcpyAsync(&f, s.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    out[3] = (f == 0 && c->shared_nodes) ? 1 : 0;
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_info(vlc_ctx* c, int ir, int predicted, int64_t* out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (!out) return fail(c, VLC_ERR_ARG, "null pointer");
+  const int s = predicted ? 1 : 0;
+  if ((rc = pack_rotor(c, *r, s))) return rc;
+  const SourceSet& cs = r->comb[s];
+  out[0] = cs.n;
+  out[1] = cs.has_shared ? cs.n_lat : 0;
+  out[2] = cs.has_shared ? cs.n_rem : 0;
+  out[3] = -1;
+  out[4] = cs.has_shared ? cs.lat_W : 0;
+  if (cs.has_shared && cs.d_unmergeable) {
+    int f = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&f, cs.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     out[3] = (f == 0 && c->shared_nodes) ? 1 : 0;
   }

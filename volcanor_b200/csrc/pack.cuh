@@ -320,13 +320,20 @@ __global__ void pack_lastcol_kernel(int nrows, int ns, const double* __restrict_
 __device__ __forceinline__ const double* ring_ptr(const double* base, int stride, int ld, int i0, int r, int j) {
   return base + (size_t)stride * ((size_t)(i0 + r) + (size_t)ld * j);
 }
+// Two copies of a lattice corner: equal up to 16 ulp of the largest coordinate.  The reference's own records are
+// bitwise equal where blade_wake_continuity copied them, but the axisymmetric blades (rotor_convectwake,
+// classdef.f90:4801-4823) hold ROTATED copies of blade 1's wake whose newest row meets the blade's own wing-TE
+// corners only to rounding (a few ulp).  The strip records use the upstream ring's TE corner as the node.
 __device__ __forceinline__ bool same3(const double* a, const double* b) {
-  return a[0] == b[0] && a[1] == b[1] && a[2] == b[2];
+  const double m = fmax(fmax(fmax(fabs(a[0]), fabs(a[1])), fabs(a[2])), fmax(fmax(fabs(b[0]), fabs(b[1])), fabs(b[2])));
+  const double tol = 16.0 * 2.220446049250313e-16 * m;
+  return fabs(a[0] - b[0]) <= tol && fabs(a[1] - b[1]) <= tol && fabs(a[2] - b[2]) <= tol;
 }
 
 // The shared-node form needs the records to describe a LATTICE: filament k ends where filament k+1 starts and
-// neighbouring rings share their corners bitwise (true after blade_wake_continuity, classdef.f90:1609-1702, and
-// assignshed, :4297-4325).  Anything else raises the flag and the sweep uses the flat enumeration.
+// neighbouring rings share their corners (same3: bitwise after blade_wake_continuity, classdef.f90:1609-1702, and
+// assignshed, :4297-4325; to rounding for rotated axisymmetric copies).  Anything else raises the flag and the sweep
+// uses the flat enumeration.
 __global__ void check_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows, int ns,
                                    int* __restrict__ unmergeable) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
