@@ -1,0 +1,112 @@
+/*
+ * case_gpu_hooks.c -- TEST INFRASTRUCTURE: the C twin of fortran/libGPU.f90.
+ *
+ * Installs, into the oracle's restatement of the reference driver (oracle/vlc_case.c), a hook table whose five
+ * hot-path call sites go straight to the C ABI of include/volcanor_b200.h -- upload the rotor's records
+ * (gpu_sync_rotor), call the batched entry point, hand the velocities back -- with no Python in the loop.
+ * tests/test_gpu_case.py uses it to run the reference's cases natively through the boundary (parity + per-step
+ * wall time of the whole driver loop, i.e. what a Fortran user would see).
+ *
+ * Build: tests/native/Makefile (gcc; links libvlc_oracle.so and libvolcanor_b200.so).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/volcanor_b200.h"
+#include "../../oracle/vlc_case.h"
+
+typedef struct {
+  orc_case_t *cas;
+  vlc_ctx *ctx;
+  int nr;
+  long uploads;
+  int last_rc;
+} gpu_user_t;
+
+/* = gpu_sync_rotor of fortran/libGPU.f90: row counters + wing + near/far wake records of every blade */
+static int sync_rotor(gpu_user_t *u, int jr, int predicted) {
+  orc_rotor_t *r = orc_case_rotor(u->cas, jr);
+  int d[10], rc;
+  orc_rotor_dims(r, d);
+  const int nb = d[0], nNwake = d[3], nFwake = d[4];
+  if ((rc = vlc_rotor_set_rows(u->ctx, jr, d[5], d[6]))) return rc;
+  for (int ib = 0; ib < nb; ++ib) {
+    if ((rc = vlc_rotor_put_wing(u->ctx, jr, ib, orc_rotor_wiP(r, ib)))) return rc;
+    if (nNwake > 0 && (rc = vlc_rotor_put_nwake(u->ctx, jr, ib, predicted, orc_rotor_waN(r, ib, predicted)))) return rc;
+    if (nFwake > 0 && (rc = vlc_rotor_put_fwake(u->ctx, jr, ib, predicted, orc_rotor_waF(r, ib, predicted)))) return rc;
+  }
+  u->uploads++;
+  return 0;
+}
+
+static int h_vind_points(void *user, int jr, int what, int predicted, long m, const double *P, double *V) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  int rc = sync_rotor(u, jr, predicted);
+  if (rc) return u->last_rc = rc;
+  switch (what) {
+    case 0: rc = vlc_rotor_vind_bywing(u->ctx, jr, m, P, V); break;
+    case 1: rc = vlc_rotor_vind_bywake(u->ctx, jr, predicted, m, P, V); break;
+    case 2: rc = vlc_rotor_vind(u->ctx, jr, predicted, m, P, V); break;
+    default: rc = vlc_rotor_vind_bywing_boundVortices(u->ctx, jr, m, P, V); break;
+  }
+  return u->last_rc = rc;
+}
+
+static int h_onN(void *user, int jr, const double *Nwake, int rows, int cols, int ld, int predicted, double *out) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  int rc = sync_rotor(u, jr, predicted);
+  if (rc) return u->last_rc = rc;
+  return u->last_rc = vlc_vind_onNwake_byRotor(u->ctx, jr, Nwake, rows, cols, ld, predicted, out);
+}
+
+static int h_onF(void *user, int jr, const double *Fwake, int rows, int predicted, double *out) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  int rc = sync_rotor(u, jr, predicted);
+  if (rc) return u->last_rc = rc;
+  return u->last_rc = vlc_vind_onFwake_byRotor(u->ctx, jr, Fwake, rows, predicted, out);
+}
+
+static int h_calcAIC(void *user, int ir, double *AIC, double *AIC_inv) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  (void)AIC_inv; /* the explicit inverse is not needed: vlc_rotor_solve uses the LU factors */
+  int rc = sync_rotor(u, ir, 0);
+  if (rc) return u->last_rc = rc;
+  return u->last_rc = vlc_rotor_calcAIC(u->ctx, ir, AIC);
+}
+
+static int h_solve(void *user, int ir, const double *RHS, double *gamVec) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  return u->last_rc = vlc_rotor_solve(u->ctx, ir, RHS, gamVec);
+}
+
+/* Declares every rotor to the library (gpu_init of the Fortran shim) and installs the hook table.
+ * The case must have its rotors initialised (orc_case_init_rotors).  Returns an opaque handle (free with
+ * case_gpu_hooks_free) or NULL. */
+void *case_gpu_hooks_install(orc_case_t *cas, vlc_ctx *ctx, int nr) {
+  gpu_user_t *u = (gpu_user_t *)calloc(1, sizeof(gpu_user_t));
+  u->cas = cas;
+  u->ctx = ctx;
+  u->nr = nr;
+  for (int ir = 0; ir < nr; ++ir) {
+    int d[10];
+    orc_rotor_dims(orc_case_rotor(cas, ir), d);
+    if (vlc_rotor_define(ctx, ir, d[0], d[1], d[2], d[3], d[4], 1)) {
+      free(u);
+      return NULL;
+    }
+  }
+  orc_hooks_t h;
+  h.user = u;
+  h.vind_points = h_vind_points;
+  h.vind_onNwake = h_onN;
+  h.vind_onFwake = h_onF;
+  h.calcAIC = h_calcAIC;
+  h.solve = h_solve;
+  orc_case_set_hooks(cas, &h);
+  return u;
+}
+
+long case_gpu_hooks_uploads(void *handle) { return ((gpu_user_t *)handle)->uploads; }
+int case_gpu_hooks_last_rc(void *handle) { return ((gpu_user_t *)handle)->last_rc; }
+void case_gpu_hooks_free(void *handle) { free(handle); }

@@ -81,3 +81,62 @@ def test_caradonna_two_blade_hover_20_steps(ctx, oracle):
     a, b, err, h = _run_pair(oracle, ctx, "caradonna", 20, short)
     print(f"caradonna (short), 20 steps: max rel CT err {err[:, 0].max():.3e}, gamVec {err[:, 1].max():.3e}")
     assert err[:, 0].max() < TOL_HISTORY and err[:, 1].max() < TOL_HISTORY
+
+
+# ------------------------------------------------------------------ native: no Python between the driver and the C ABI
+
+def _native_hooks(case, ctx):
+    """tests/native/case_gpu_hooks.c (the C twin of fortran/libGPU.f90) installed into the oracle's driver."""
+    import ctypes as C
+    import subprocess
+    here = Path(__file__).resolve().parent / "native"
+    so = here / "libcase_gpu_hooks.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(here)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    lib.case_gpu_hooks_install.restype = C.c_void_p
+    lib.case_gpu_hooks_install.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.case_gpu_hooks_uploads.restype = C.c_long
+    lib.case_gpu_hooks_uploads.argtypes = [C.c_void_p]
+    lib.case_gpu_hooks_last_rc.argtypes = [C.c_void_p]
+    lib.case_gpu_hooks_free.argtypes = [C.c_void_p]
+    case.init_rotors()
+    h = lib.case_gpu_hooks_install(case.h, ctx.h, case.nr)
+    assert h, "vlc_rotor_define failed"
+    return lib, h
+
+
+@pytest.mark.parametrize("name,nsteps", [("katzNplotkin_AR04", 160), ("elevateTest", 150)])
+def test_native_gpu_run_reproduces_reference_golden_history(ctx, name, nsteps, oracle):
+    """The reference's driver loop with its hot path on the GPU, natively through the C ABI, over the WHOLE history of
+    the reference's two golden cases: every row of r01ForceNonDim.csv.ref to the 7 printed digits."""
+    import time
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    c = oracle.Case(fx)
+    lib, h = _native_hooks(c, ctx)
+    t0 = time.perf_counter()
+    try:
+        c.init()
+    except RuntimeError as e:
+        raise AssertionError(f"init: {e}; library: rc={lib.case_gpu_hooks_last_rc(h)} {ctx.lib.vlc_last_error(ctx.h)}") from e
+    hist = [c.force_nondim(0)]
+    t1 = time.perf_counter()
+    pairs = 0.0
+    for it in range(nsteps):
+        try:
+            c.step()
+        except RuntimeError as e:
+            raise AssertionError(f"step {it + 1}: {e}; rc={lib.case_gpu_hooks_last_rc(h)} {ctx.lib.vlc_last_error(ctx.h)}") from e
+        pairs += c.pairs_last_step
+        hist.append(c.force_nondim(0))
+    t2 = time.perf_counter()
+    hist = np.array(hist)
+    ref = np.array(fx["ref_ForceNonDim"]["rows"])
+    ulp = 10.0 ** (np.floor(np.log10(np.abs(ref[:, 1]))) - 6)
+    d = np.abs(hist[:, 0] - ref[:len(hist), 1]) / ulp
+    print(f"{name}: {nsteps} steps natively through the C ABI in {t2 - t1:.2f} s ({(t2 - t1) / nsteps * 1e3:.1f} ms/step, "
+          f"{nsteps / (t2 - t1):.1f} timesteps/s incl. the driver's host work; init {t1 - t0:.2f} s; "
+          f"{pairs:.3e} pair interactions, {lib.case_gpu_hooks_uploads(h)} uploads); "
+          f"max deviation from the golden file {d.max():.2f} units of the 7th digit")
+    assert d.max() <= 1.0, (d.max(), int(d.argmax()))
+    lib.case_gpu_hooks_free(h)
