@@ -105,7 +105,9 @@ int vlc_source_tile(void);
 int vlc_rotor_define(vlc_ctx* ctx, int ir, int nb, int nc, int ns, int nNwake, int nFwake, int surfaceType);
 /* rotor%rowNear, rotor%rowFar (1-based, as in the reference, main.f90:412-417). */
 int vlc_rotor_set_rows(vlc_ctx* ctx, int ir, int rowNear, int rowFar);
-/* Upload blade ib (0-based) state in reference record layout. predicted != 0 -> waNPredicted etc. */
+/* Upload blade ib (0-based) state in reference record layout. predicted != 0 -> waNPredicted etc.
+ * The pointers address the WHOLE arrays (waN(1,1), waF(1)); only the active rows rowNear..nNwake / rowFar..nFwake of
+ * the last vlc_rotor_set_rows travel (no sweep reads the others), so set the rows first. */
 int vlc_rotor_put_wing(vlc_ctx* ctx, int ir, int ib, const double* wiP /* nc*ns x 104 */);
 int vlc_rotor_put_nwake(vlc_ctx* ctx, int ir, int ib, int predicted, const double* waN /* nNwake*ns x 50 */);
 int vlc_rotor_put_fwake(vlc_ctx* ctx, int ir, int ib, int predicted, const double* waF /* nFwake x 13 */);

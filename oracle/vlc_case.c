@@ -1131,6 +1131,9 @@ int orc_case_init_rotors(orc_case_t *c) {
       r->blade[ib - 1].theta = orc_rotor_gettheta(r, r->psiStart, ib);
       orc_blade_rot_pitch(&r->blade[ib - 1], sgn1(r->Omega) * r->blade[ib - 1].theta);
     }
+    r->gen_wing++;
+    r->gen_wake[0]++;
+    r->gen_wake[1]++;
   }
   c->rotors_inited = 1;
   return 0;
@@ -1186,6 +1189,7 @@ static int solve_all(orc_case_t *c) {
     int rc = c->hooks.solve(c->hooks.user, ir, r->RHS, r->gamVec);
     if (rc) return rc;
     orc_rotor_map_gam(r);
+    r->gen_wing++;
   }
   return 0;
 }
@@ -1292,6 +1296,7 @@ int orc_case_init(orc_case_t *c) {
     r->rowFar = r->nFwake + 1;
     r->rowNear = r->nNwake + 1;
     if (r->nNwake > 0) orc_rotor_assignshed(r, "TE");
+    r->gen_wake[0]++;
   }
   if (c->cfg.rotorForcePlot != 0) {
     rc = compute_forces(c);
@@ -1364,6 +1369,7 @@ static int wake_sweep(orc_case_t *c, int predicted) {
 }
 
 static void copy_wake_to_predicted(orc_rotor_t *r) { /* main.f90:869-872 / :1028-1036 */
+  r->gen_wake[1]++; /* the 'P' set is rewritten here and convected right after */
   for (int ib = 0; ib < r->nbConvect; ++ib) {
     orc_blade_t *b = &r->blade[ib];
     for (int j = 1; j <= r->ns; ++j)
@@ -1412,7 +1418,9 @@ int orc_case_step(orc_case_t *c) {
     rotor_move(r, d);
     rotor_rot_pts(r, w, r->cgCoords);
     rotor_rot_advance(r, r->omegaSlow * dt, 0);
+    r->gen_wing++;
   }
+  for (int ir = 0; ir < c->nr; ++ir) c->rotor[ir]->gen_wake[0]++; /* rows moved, shed row attached, aged, dissipated below */
   if (cfg->wakeSuppress == 0) { /* :466-506 */
     for (int ir = 0; ir < c->nr; ++ir)
       if (c->rotor[ir]->nNwake > 0) orc_rotor_assignshed(c->rotor[ir], "LE");
@@ -1572,6 +1580,7 @@ int orc_case_step(orc_case_t *c) {
         snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 3)", cfg->fdScheme);
         return 3;
     }
+    for (int ir = 0; ir < c->nr; ++ir) c->rotor[ir]->gen_wake[0]++; /* convectwake('C'), strain, roll-up, shed below */
     if (cfg->wakeStrain == 1) /* :1409-1416 */
       for (int ir = 0; ir < c->nr; ++ir)
         if (c->rotor[ir]->nNwake > 0) orc_rotor_strain_wake(c->rotor[ir]);

@@ -1004,6 +1004,11 @@ void orc_rotor_dims(const orc_rotor_t *r, int *out) {
   out[0] = r->nb; out[1] = r->nc; out[2] = r->ns; out[3] = r->nNwake; out[4] = r->nFwake;
   out[5] = r->rowNear; out[6] = r->rowFar; out[7] = r->nbConvect; out[8] = r->nNwakeEnd; out[9] = r->nFwakeEnd;
 }
+void orc_rotor_gens(const orc_rotor_t *r, unsigned long out[3]) {
+  out[0] = r->gen_wing;
+  out[1] = r->gen_wake[0];
+  out[2] = r->gen_wake[1];
+}
 void orc_rotor_set_rows(orc_rotor_t *r, int rowNear, int rowFar) {
   r->rowNear = rowNear;
   r->rowFar = rowFar;

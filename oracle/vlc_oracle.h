@@ -108,6 +108,9 @@ typedef struct {
   double rollupStartRadius, rollupEndRadius, initWakeVel, skewLimit;
   double nonDimforceDenominator;
   double forceInertial[3], lift[3], liftPrev[3], drag[3], liftUnsteady[3];
+  /* generation counters bumped by the case driver whenever it changes the wing / the 'C' wake / the 'P' wake, so a
+   * shim can skip uploads of unchanged state (tests/native/case_gpu_hooks.c) */
+  unsigned long gen_wing, gen_wake[2];
 } orc_rotor_t;
 
 /* ---- libMath.f90 ---- */
@@ -189,6 +192,7 @@ double *orc_rotor_vel(orc_rotor_t *r, int ib, int which);
 double *orc_rotor_AIC(orc_rotor_t *r, int inverse);
 double *orc_rotor_vec(orc_rotor_t *r, int which);
 void orc_rotor_dims(const orc_rotor_t *r, int *out);
+void orc_rotor_gens(const orc_rotor_t *r, unsigned long out[3]); /* gen_wing, gen_wake C, gen_wake P */
 void orc_rotor_set_rows(orc_rotor_t *r, int rowNear, int rowFar);
 void orc_rotor_set_params(orc_rotor_t *r, int surfaceType, int axisymmetrySwitch, int nbConvect, double Omega,
                           double omegaSlow, const double *shaftAxis, const double *hubCoords, double theta0,

@@ -16,25 +16,47 @@
 #include "../../include/volcanor_b200.h"
 #include "../../oracle/vlc_case.h"
 
+#define MAX_ROTORS 64
 typedef struct {
   orc_case_t *cas;
   vlc_ctx *ctx;
   int nr;
-  long uploads;
+  long uploads, skipped;
   int last_rc;
+  /* what the library currently holds: generation of the wing and of the 'C' / 'P' wake, and the row counters */
+  unsigned long have_wing[MAX_ROTORS], have_wake[MAX_ROTORS][2];
+  int have_rows[MAX_ROTORS][2][2];
 } gpu_user_t;
 
-/* = gpu_sync_rotor of fortran/libGPU.f90: row counters + wing + near/far wake records of every blade */
+/* = gpu_sync_rotor of fortran/libGPU.f90: row counters + wing + near/far wake records of every blade.  State the
+ * driver has not touched since the last transfer (generation counters of oracle/vlc_case.c; a Fortran shim would set
+ * the same flags where main.f90 calls convectwake / assignshed / dissipate_wake / map_gam / move) is not sent again. */
 static int sync_rotor(gpu_user_t *u, int jr, int predicted) {
   orc_rotor_t *r = orc_case_rotor(u->cas, jr);
   int d[10], rc;
+  unsigned long g[3];
   orc_rotor_dims(r, d);
-  const int nb = d[0], nNwake = d[3], nFwake = d[4];
+  orc_rotor_gens(r, g);
+  const int nb = d[0], nNwake = d[3], nFwake = d[4], s = predicted ? 1 : 0;
   if ((rc = vlc_rotor_set_rows(u->ctx, jr, d[5], d[6]))) return rc;
+  const int wing_new = (g[0] != u->have_wing[jr]);
+  const int wake_new = (g[1 + s] != u->have_wake[jr][s]) || u->have_rows[jr][s][0] != d[5] || u->have_rows[jr][s][1] != d[6];
+  if (!wing_new && !wake_new) {
+    u->skipped++;
+    return 0;
+  }
   for (int ib = 0; ib < nb; ++ib) {
-    if ((rc = vlc_rotor_put_wing(u->ctx, jr, ib, orc_rotor_wiP(r, ib)))) return rc;
-    if (nNwake > 0 && (rc = vlc_rotor_put_nwake(u->ctx, jr, ib, predicted, orc_rotor_waN(r, ib, predicted)))) return rc;
-    if (nFwake > 0 && (rc = vlc_rotor_put_fwake(u->ctx, jr, ib, predicted, orc_rotor_waF(r, ib, predicted)))) return rc;
+    if (wing_new && (rc = vlc_rotor_put_wing(u->ctx, jr, ib, orc_rotor_wiP(r, ib)))) return rc;
+    if (wake_new) {
+      if (nNwake > 0 && (rc = vlc_rotor_put_nwake(u->ctx, jr, ib, predicted, orc_rotor_waN(r, ib, predicted)))) return rc;
+      if (nFwake > 0 && (rc = vlc_rotor_put_fwake(u->ctx, jr, ib, predicted, orc_rotor_waF(r, ib, predicted)))) return rc;
+    }
+  }
+  u->have_wing[jr] = g[0];
+  if (wake_new) {
+    u->have_wake[jr][s] = g[1 + s];
+    u->have_rows[jr][s][0] = d[5];
+    u->have_rows[jr][s][1] = d[6];
   }
   u->uploads++;
   return 0;
@@ -84,6 +106,7 @@ static int h_solve(void *user, int ir, const double *RHS, double *gamVec) {
  * The case must have its rotors initialised (orc_case_init_rotors).  Returns an opaque handle (free with
  * case_gpu_hooks_free) or NULL. */
 void *case_gpu_hooks_install(orc_case_t *cas, vlc_ctx *ctx, int nr) {
+  if (nr > MAX_ROTORS) return NULL;
   gpu_user_t *u = (gpu_user_t *)calloc(1, sizeof(gpu_user_t));
   u->cas = cas;
   u->ctx = ctx;
@@ -108,5 +131,6 @@ void *case_gpu_hooks_install(orc_case_t *cas, vlc_ctx *ctx, int nr) {
 }
 
 long case_gpu_hooks_uploads(void *handle) { return ((gpu_user_t *)handle)->uploads; }
+long case_gpu_hooks_skipped(void *handle) { return ((gpu_user_t *)handle)->skipped; }
 int case_gpu_hooks_last_rc(void *handle) { return ((gpu_user_t *)handle)->last_rc; }
 void case_gpu_hooks_free(void *handle) { free(handle); }

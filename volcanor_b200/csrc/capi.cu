@@ -69,6 +69,8 @@ struct Rotor {
   SourceSet bound;
   bool dirty[2] = {true, true};
   bool bound_dirty = true;
+  // rows below these were not refreshed by the last put (only the active rows travel): [set][blade]
+  std::vector<int> stale_near[2], stale_far[2];
   // AIC
   int N = 0;
   DevBuf LU;
@@ -439,6 +441,10 @@ Rotor* get_rotor(vlc_ctx* c, int ir) {
 // (Re)build the packed [wing | wake] set of a rotor in the reference's enumeration order.
 int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   if (!r.dirty[s]) return VLC_OK;
+  for (int ib = 0; ib < r.nb; ++ib)
+    if ((r.nNwake > 0 && r.rowNear < r.stale_near[s][ib]) || (r.nFwake > 0 && r.rowFar < r.stale_far[s][ib]))
+      return fail(c, VLC_ERR_STATE, "wake rows between rowNear/rowFar and the last upload were never transferred: "
+                                    "call vlc_rotor_set_rows before vlc_rotor_put_nwake / _put_fwake");
   const int nrows = r.nNwake > 0 ? (r.nNwake - r.rowNear + 1) : 0;
   const bool has_far = (r.nNwake > 0) && (r.rowFar <= r.nFwake);  // classdef.f90:1458
   const int nfar = has_far ? (r.nFwake - r.rowFar + 1) : 0;
@@ -934,6 +940,10 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
   r.dirty[0] = r.dirty[1] = r.bound_dirty = true;
   r.factored = false;
   r.have_pf[0] = r.have_pf[1] = false;
+  for (int s2 = 0; s2 < 2; ++s2) {
+    r.stale_near[s2].assign(nb, 1);  // zero-filled below = gam 0 everywhere, like rotor_init (:3835-3836)
+    r.stale_far[s2].assign(nb, 1);
+  }
   int rc = bind_device(c);
   if (rc) return rc;
   // zero-initialised device copies so that never-uploaded rows hold gam = 0 like rotor_init (:3835-3836)
@@ -1002,7 +1012,16 @@ extern "C" int vlc_rotor_put_nwake(vlc_ctx* c, int ir, int ib, int predicted, co
   const size_t per = (size_t)r->nNwake * r->ns * vlc::kVr;
   r->dirty[s] = true;
   if (per == 0) return VLC_OK;
-  return upload(c, r->waN[s], per * r->nb, per * ib, waN, per);
+  // only the active rows rowNear..nNwake of every column travel (a sweep never reads the others, classdef.f90:1450)
+  const int first = r->rowNear - 1, nact = r->nNwake - first;
+  r->stale_near[s][ib] = r->rowNear;
+  if (nact <= 0) return VLC_OK;
+  if ((rc = reserve(c, r->waN[s], per * r->nb))) return rc;
+  const size_t pitch = (size_t)r->nNwake * vlc::kVr * sizeof(double);
+  CUDA_OK(c, cudaMemcpy2DAsync(r->waN[s].p + per * ib + (size_t)first * vlc::kVr, pitch, waN + (size_t)first * vlc::kVr, pitch,
+                               (size_t)nact * vlc::kVr * sizeof(double), (size_t)r->ns, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer right away
+  return VLC_OK;
 }
 
 extern "C" int vlc_rotor_put_fwake(vlc_ctx* c, int ir, int ib, int predicted, const double* waF) {
@@ -1017,7 +1036,11 @@ extern "C" int vlc_rotor_put_fwake(vlc_ctx* c, int ir, int ib, int predicted, co
   r->dirty[s] = true;
   if (per == 0) return VLC_OK;
   if (!waF) return fail(c, VLC_ERR_ARG, "null pointer");
-  return upload(c, r->waF[s], per * r->nb, per * ib, waF, per);
+  const int first = r->rowFar - 1, nact = r->nFwake - first;  // active rows rowFar..nFwake (classdef.f90:1465)
+  r->stale_far[s][ib] = r->rowFar;
+  if (nact <= 0) return VLC_OK;
+  return upload(c, r->waF[s], per * r->nb, per * ib + (size_t)first * vlc::kFw, waF + (size_t)first * vlc::kFw,
+                (size_t)nact * vlc::kFw);
 }
 
 extern "C" int vlc_rotor_put_pfwake(vlc_ctx* c, int ir, int ib, int predicted, const double* wapF) {
