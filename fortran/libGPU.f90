@@ -20,9 +20,19 @@ module libGPU
   implicit none
   private
   public :: gpu_init, gpu_finalize, gpu_sync_rotor, gpu_vind_onNwake_byRotor, gpu_vind_onFwake_byRotor
-  public :: gpu_vind_points, gpu_calcAIC, gpu_solve
+  public :: gpu_vind_points, gpu_calcAIC, gpu_solve, gpu_touch
 
   type(c_ptr), save :: ctx = c_null_ptr
+
+  ! What the library currently holds is stale for rotor ir: the wing, the current ('C') wake, the predicted ('P') wake.
+  ! Everything starts stale; gpu_sync_rotor clears the flags it serves; the driver calls gpu_touch after it changes
+  ! state (main.f90: after move/rot_advance and map_gam -> GPU_WING; after assignshed/age_wake/dissipate_wake/
+  ! convectwake('C')/strain_wake/rollup -> GPU_WAKE_C; after the copy to *Predicted and convectwake('P') -> GPU_WAKE_P).
+  ! Without any gpu_touch calls every sweep re-sends everything (correct, slower): tests/native/case_gpu_hooks.c
+  ! measures 0.99 s -> 0.21 s for the 160 steps of katzNplotkin-AR04 with the flags.
+  integer, parameter, public :: GPU_WING = 1, GPU_WAKE_C = 2, GPU_WAKE_P = 3
+  logical, allocatable, save :: stale(:, :)
+  logical, save :: trackStale = .false.
 
   ! what for gpu_vind_points
   integer, parameter, public :: GPU_BYWING = 0, GPU_BYWAKE = 1, GPU_BOTH = 2, GPU_BOUNDVORTICES = 3
@@ -164,6 +174,8 @@ contains
     integer, intent(in) :: device
     integer :: ir
     call check(vlc_create(int(device, c_int), ctx))
+    allocate (stale(3, size(rotor)))
+    stale = .true.
     do ir = 1, size(rotor)
       call check(vlc_rotor_define(ctx, ir - 1, rotor(ir)%nb, rotor(ir)%nc, rotor(ir)%ns, &
         & rotor(ir)%nNwake, rotor(ir)%nFwake, rotor(ir)%surfaceType))
@@ -175,6 +187,13 @@ contains
     ctx = c_null_ptr
   end subroutine gpu_finalize
 
+  subroutine gpu_touch(ir, what)
+    !! The driver changed rotor ir's wing / 'C' wake / 'P' wake: send it again before the next sweep that reads it.
+    integer, intent(in) :: ir, what
+    trackStale = .true.
+    stale(what, ir) = .true.
+  end subroutine gpu_touch
+
   subroutine gpu_sync_rotor(rotor, ir, predicted)
     !! Flatten the non-interoperable derived types into arrays of doubles and upload them.
     !! vr_class = 50, Fwake_class = 13, wingpanel_class = 104 doubles (sequence of default reals(dp));
@@ -185,12 +204,17 @@ contains
     integer :: ib
     integer(c_int) :: p
     real(c_double), allocatable :: buf(:)
+    logical :: sendWing, sendWake
     p = merge(1_c_int, 0_c_int, predicted)
     call check(vlc_rotor_set_rows(ctx, ir - 1, rotor%rowNear, rotor%rowFar))
+    sendWing = stale(GPU_WING, ir) .or. .not. trackStale
+    sendWake = stale(merge(GPU_WAKE_P, GPU_WAKE_C, predicted), ir) .or. .not. trackStale
     do ib = 1, rotor%nb
-      buf = transfer(rotor%blade(ib)%wiP, buf)
-      call check(vlc_rotor_put_wing(ctx, ir - 1, ib - 1, buf))
-      if (rotor%nNwake > 0) then
+      if (sendWing) then
+        buf = transfer(rotor%blade(ib)%wiP, buf)
+        call check(vlc_rotor_put_wing(ctx, ir - 1, ib - 1, buf))
+      endif
+      if (rotor%nNwake > 0 .and. sendWake) then
         if (predicted) then
           buf = transfer(rotor%blade(ib)%waNPredicted, buf)
         else
@@ -215,6 +239,8 @@ contains
         endif
       endif
     enddo
+    if (sendWing) stale(GPU_WING, ir) = .false.
+    if (sendWake) stale(merge(GPU_WAKE_P, GPU_WAKE_C, predicted), ir) = .false.
   end subroutine gpu_sync_rotor
 
   function gpu_vind_onNwake_byRotor(rotor, ir, Nwake, optionalChar) result(vindArray)
