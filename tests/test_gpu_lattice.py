@@ -256,3 +256,45 @@ def test_vel_order2_vs_oracle(ctx, oracle, rows, cols):
     ctx.vel_order2_dev(rows, cols, torch.from_numpy(vn).cuda(), torch.from_numpy(vp).cuda(), out)
     ctx.sync()
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_full_size_workload_properties_and_sampled_oracle(ctx, oracle):
+    """BASELINE.json's benchmark size (synthetic multirotor wake, 1 000 192 filaments x 258 176 targets): the whole
+    sweep through the shared-node kernel, checked (1) against the CPU oracle on 96 sampled targets (reference
+    enumeration, double and long double), (2) against the flat kernel on 4096 sampled targets, (3) for exact linearity
+    in the circulation (doubling every Gamma doubles every velocity bit for bit)."""
+    import torch
+    lats = synth.multirotor(1_000_000, seed=12345)
+    keep = _upload(ctx, lats)
+    P = synth.targets_all(lats)
+    m = P.shape[0]
+    info = ctx.set_info(3)
+    assert info["filaments"] == 1000192 and m == 258176 and info["shared_active"] == 1 and info["strip_width"] == 4
+    V = _sweep(ctx, P)
+    assert np.all(np.isfinite(V))
+    rng = np.random.default_rng(0)
+    # (1) oracle on a sample (6e7 pair evaluations on the CPU)
+    idx = np.sort(rng.choice(m, size=96, replace=False))
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, P[idx])
+    Vl, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, P[idx])
+    e = scaled_err(V[idx], Vo, Vabs)
+    el, eo = scaled_err(V[idx], Vl, Vabs), scaled_err(Vo, Vl, Vabs)
+    print(f"1e6 filaments: scaled error vs oracle {e:.3e}; vs long double: GPU {el:.3e}, reference-order double sum {eo:.3e}")
+    assert e < TOL and el < 5 * max(eo, 1e-15)
+    # (2) flat kernel (reference enumeration) on a larger sample
+    idx2 = np.sort(rng.choice(m, size=4096, replace=False))
+    ctx.set_shared_nodes(False)
+    try:
+        Vf = _sweep(ctx, P[idx2])
+    finally:
+        ctx.set_shared_nodes(True)
+    scale = np.max(Vabs)
+    assert np.max(np.abs(Vf - V[idx2])) < TOL * scale
+    # (3) linearity
+    for l in lats:
+        l.gam *= 2.0
+        l.gamF *= 2.0
+    keep2 = _upload(ctx, lats)
+    V2 = _sweep(ctx, P)
+    assert np.array_equal(V2, 2.0 * V)
