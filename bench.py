@@ -345,6 +345,15 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     elapsed_ms, kern_ms_max, sweep_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
+    # every rank must hold the same wake after the last all-gather (bitwise): max - min over ranks of a position checksum
+    chk = P_all[:m].sum(dim=0)
+    ranks_consistent = True
+    if world > 1:
+        hi_, lo_ = chk.clone(), chk.clone()
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        ranks_consistent = bool(torch.equal(hi_, lo_))
+    wake_finite = bool(torch.isfinite(chk).all())
     pairs_step = 2.0 * float(m) * float(n_src)             # two sweeps per time step
     value = pairs_step * args.steps / (elapsed_ms * 1e-3)
 
@@ -449,6 +458,7 @@ def main():
                                     "fast: second-order rsqrt refinement, pair error <= 6.4e-13"][args.precision]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
            "timesteps_per_s": args.steps / (elapsed_ms * 1e-3), "sweeps_per_step": 2,
+           "checks": {"ranks_hold_identical_wake": ranks_consistent, "wake_finite": wake_finite},
            "fp64_peak_measured_tflops": peak}
     print(json.dumps(out))
     if world > 1:
