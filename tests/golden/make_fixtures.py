@@ -94,8 +94,22 @@ def case_fixture(case_dir: Path, name: str, n_rotors: int = 1, results: bool = T
     return fx
 
 
+def check_formatter(ref: Path):
+    """oracle/casefile.py's E15.7 writer must reproduce the reference's golden text byte for byte."""
+    sys.path.insert(0, str(HERE.parent.parent))
+    from oracle import casefile
+    for f in ref.glob("tests/*.case/referenceResults/r01ForceNonDim.csv.ref"):
+        lines = f.read_text().splitlines()
+        assert lines[0] == casefile.HEADER, f
+        for l in lines[1:]:
+            vals = [float(l[5 + 15 * k:5 + 15 * (k + 1)]) for k in range(9)]
+            assert casefile.force_nondim_line(int(l[:5]), vals) == l, (f, l)
+        print(f"formatter round-trips {f.relative_to(ref)} ({len(lines) - 1} rows)")
+
+
 def main():
     ref = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    check_formatter(ref)
     jobs = [
         (ref / "tests" / "katzNplotkin-AR04.case", "katzNplotkin_AR04", True),
         (ref / "tests" / "elevateTest.case", "elevateTest", True),
