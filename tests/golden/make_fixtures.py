@@ -115,6 +115,7 @@ def main():
         (ref / "tests" / "elevateTest.case", "elevateTest", True),
         (ref / "tutorials" / "simplewing.case", "simplewing", False),
         (ref / "tutorials" / "caradonna.case", "caradonna", False),
+        (ref / "tutorials" / "tr1208.case", "tr1208", False),
     ]
     for d, name, res in jobs:
         if not d.exists():

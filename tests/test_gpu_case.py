@@ -140,3 +140,28 @@ def test_native_gpu_run_reproduces_reference_golden_history(ctx, name, nsteps, o
           f"max deviation from the golden file {d.max():.2f} units of the 7th digit")
     assert d.max() <= 1.0, (d.max(), int(d.argmax()))
     lib.case_gpu_hooks_free(h)
+
+
+@pytest.mark.parametrize("name,nsteps", [("simplewing", 40), ("tr1208", 30)])
+def test_native_gpu_vs_cpu_tutorial_cases(ctx, oracle, name, nsteps):
+    """BASELINE.json configs[0] (tutorials/simplewing.case, whole run) and configs[3] (tutorials/tr1208.case: swept wing
+    from a PLOT3D file, dissipation on): CL and circulation histories, GPU through the native shim vs CPU oracle."""
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    lib, h = _native_hooks(b, ctx)
+    a.init()
+    b.init()
+    worst = [0.0, 0.0]
+    for it in range(nsteps):
+        a.step()
+        b.step()
+        fa, fb = a.force_nondim(0), b.force_nondim(0)
+        ga, gb = a.rotor(0).vec(0), b.rotor(0).vec(0)
+        worst[0] = max(worst[0], abs(fb[0] / fa[0] - 1.0))
+        worst[1] = max(worst[1], float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+    print(f"{name}: {nsteps} steps, max rel CL err {worst[0]:.3e}, max rel gamVec err {worst[1]:.3e}, "
+          f"shared-node form active: {ctx.rotor_info(0)['shared_active']}")
+    assert worst[0] < TOL_HISTORY and worst[1] < TOL_HISTORY
+    assert ctx.rotor_info(0)["shared_active"] == 1
+    assert np.max(np.abs(a.rotor(0).waN(0) - b.rotor(0).waN(0))) < 1e-9
+    lib.case_gpu_hooks_free(h)
