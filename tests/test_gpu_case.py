@@ -165,3 +165,27 @@ def test_native_gpu_vs_cpu_tutorial_cases(ctx, oracle, name, nsteps):
     assert ctx.rotor_info(0)["shared_active"] == 1
     assert np.max(np.abs(a.rotor(0).waN(0) - b.rotor(0).waN(0))) < 1e-9
     lib.case_gpu_hooks_free(h)
+
+
+def test_native_gpu_vs_cpu_two_rotor_case(ctx, oracle):
+    """nr = 2 (wing + 2-blade rotor with far wake): the cross-rotor terms of the RHS and of both wake sweeps
+    (main.f90:147-153, :549-561, :814-827) on the GPU vs the CPU oracle."""
+    from tests.test_oracle_case import two_body_case
+    fx = two_body_case()
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    lib, h = _native_hooks(b, ctx)
+    a.init()
+    b.init()
+    worst = 0.0
+    for it in range(16):
+        a.step()
+        b.step()
+        for ir in range(2):
+            fa, fb = a.force_nondim(ir), b.force_nondim(ir)
+            ga, gb = a.rotor(ir).vec(0), b.rotor(ir).vec(0)
+            worst = max(worst, abs(fb[0] / fa[0] - 1.0), float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+    print(f"wing + rotor, 16 steps: max rel CL/CT/gamVec err {worst:.3e}; shared-node form: "
+          f"wing wake {ctx.rotor_info(0)['shared_active']}, rotor wake {ctx.rotor_info(1)['shared_active']}")
+    assert worst < TOL_HISTORY
+    assert ctx.rotor_info(0)["shared_active"] == 1 and ctx.rotor_info(1)["shared_active"] == 1
+    lib.case_gpu_hooks_free(h)
