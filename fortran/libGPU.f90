@@ -21,6 +21,11 @@ module libGPU
   private
   public :: gpu_init, gpu_finalize, gpu_sync_rotor, gpu_vind_onNwake_byRotor, gpu_vind_onFwake_byRotor
   public :: gpu_vind_points, gpu_calcAIC, gpu_solve, gpu_touch
+  ! device-resident time stepping (tier 2b of the C ABI): the wake is uploaded once and every wake mutator of the time
+  ! loop runs on the library's copies; tests/native/case_gpu_hooks.c (resident mode) is the tested C twin
+  public :: gpu_resident_begin, gpu_wake_prestep, gpu_wake_convect, gpu_download_wake
+  logical, save :: resident = .false.
+  integer(c_int), parameter :: VEL_FIRST_STEP = 0, VEL_AB2 = 1, VEL_AM2 = 2, VEL_SHIFT_HISTORY = 3, VEL_ORDER2 = 4
 
   type(c_ptr), save :: ctx = c_null_ptr
 
@@ -148,6 +153,81 @@ module libGPU
       real(c_double), intent(in) :: RHS(*)
       real(c_double), intent(out) :: gamVec(*)
     end function
+    ! ---- tier 2b: the reference's wake mutators on the device copies ----
+    integer(c_int) function vlc_rotor_set_wake_params(c, ir, nbConvect, axisymmetrySwitch, ductSwitch, &
+        & suppressFwakeSwitch, rollupStart, rollupEnd, rollupSign, apparentViscCoeff, decayCoeff, initWakeVel) &
+        & bind(C, name='vlc_rotor_set_wake_params')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, nbConvect, axisymmetrySwitch, ductSwitch, suppressFwakeSwitch, rollupStart, rollupEnd
+      real(c_double), value :: rollupSign, apparentViscCoeff, decayCoeff, initWakeVel
+    end function
+    integer(c_int) function vlc_rotor_set_frame(c, ir, shaftAxis, hubCoords) bind(C, name='vlc_rotor_set_frame')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), intent(in) :: shaftAxis(3), hubCoords(3)
+    end function
+    integer(c_int) function vlc_rotor_assignshed(c, ir, edge) bind(C, name='vlc_rotor_assignshed')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, edge
+    end function
+    integer(c_int) function vlc_rotor_age_wake(c, ir, dt, omegaSlow) bind(C, name='vlc_rotor_age_wake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), value :: dt, omegaSlow
+    end function
+    integer(c_int) function vlc_rotor_dissipate_wake(c, ir, dt, kinematicVisc) bind(C, name='vlc_rotor_dissipate_wake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), value :: dt, kinematicVisc
+    end function
+    integer(c_int) function vlc_rotor_strain_wake(c, ir) bind(C, name='vlc_rotor_strain_wake')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+    end function
+    integer(c_int) function vlc_rotor_wake_to_predicted(c, ir) bind(C, name='vlc_rotor_wake_to_predicted')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+    end function
+    integer(c_int) function vlc_rotor_convectwake(c, ir, dt, predicted) bind(C, name='vlc_rotor_convectwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, predicted
+      real(c_double), value :: dt
+    end function
+    integer(c_int) function vlc_rotor_rollup(c, ir) bind(C, name='vlc_rotor_rollup')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+    end function
+    integer(c_int) function vlc_wake_sweep(c, predicted, addInitWakeVel) bind(C, name='vlc_wake_sweep')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: predicted, addInitWakeVel
+    end function
+    integer(c_int) function vlc_rotor_wakevel_op(c, ir, op) bind(C, name='vlc_rotor_wakevel_op')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, op
+    end function
+    integer(c_int) function vlc_rotor_get_nwake(c, ir, ib, predicted, waN) bind(C, name='vlc_rotor_get_nwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(out) :: waN(*)
+    end function
+    integer(c_int) function vlc_rotor_get_fwake(c, ir, ib, predicted, waF) bind(C, name='vlc_rotor_get_fwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(out) :: waF(*)
+    end function
   end interface
 
 contains
@@ -209,6 +289,10 @@ contains
     call check(vlc_rotor_set_rows(ctx, ir - 1, rotor%rowNear, rotor%rowFar))
     sendWing = stale(GPU_WING, ir) .or. .not. trackStale
     sendWake = stale(merge(GPU_WAKE_P, GPU_WAKE_C, predicted), ir) .or. .not. trackStale
+    if (resident) then   ! the device's wake is the wake: only the frame and the wing travel
+      sendWake = .false.
+      call check(vlc_rotor_set_frame(ctx, ir - 1, rotor%shaftAxis, rotor%hubCoords))
+    endif
     do ib = 1, rotor%nb
       if (sendWing) then
         buf = transfer(rotor%blade(ib)%wiP, buf)
@@ -326,5 +410,148 @@ contains
     real(dp) :: gamVec(size(rotor%RHS))
     call check(vlc_rotor_solve(ctx, ir - 1, rotor%RHS, gamVec))
   end function gpu_solve
+
+  ! ------------------------------------------------------------------ device-resident time stepping (tier 2b)
+
+  subroutine gpu_resident_begin(rotor)
+    !! Once, before the time loop (after main.f90:227-234): the wake records as rotor%init and the first
+    !! assignshed('TE') left them go up whole, current and predicted; from here on the driver must not touch
+    !! waN / waF / waNPredicted / waFPredicted / velNwake* / velFwake* (gpu_download_wake brings them back for plots).
+    type(rotor_class), intent(in) :: rotor(:)
+    integer :: ir, ib
+    real(c_double), allocatable :: buf(:)
+    do ir = 1, size(rotor)
+      call check(vlc_rotor_set_wake_params(ctx, ir - 1, rotor(ir)%nbConvect, rotor(ir)%axisymmetrySwitch, &
+        & rotor(ir)%ductSwitch, rotor(ir)%suppressFwakeSwitch, rotor(ir)%rollupStart, rotor(ir)%rollupEnd, &
+        & rotor(ir)%Omega*rotor(ir)%controlPitch(1), rotor(ir)%apparentViscCoeff, rotor(ir)%decayCoeff, &
+        & rotor(ir)%initWakeVel))
+      call check(vlc_rotor_set_rows(ctx, ir - 1, 1, 1))   ! every row travels this once
+      do ib = 1, rotor(ir)%nb
+        if (rotor(ir)%nNwake > 0) then
+          buf = transfer(rotor(ir)%blade(ib)%waN, buf)
+          call check(vlc_rotor_put_nwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
+          buf = transfer(rotor(ir)%blade(ib)%waNPredicted, buf)
+          call check(vlc_rotor_put_nwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+        endif
+        if (rotor(ir)%nFwake > 0) then
+          buf = transfer(rotor(ir)%blade(ib)%waF, buf)
+          call check(vlc_rotor_put_fwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
+          buf = transfer(rotor(ir)%blade(ib)%waFPredicted, buf)
+          call check(vlc_rotor_put_fwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+        endif
+      enddo
+    enddo
+    resident = .true.
+    trackStale = .true.
+  end subroutine gpu_resident_begin
+
+  subroutine gpu_wake_prestep(rotor, dt, wakeDissipation, kinematicVisc)
+    !! Replaces main.f90:466-506: assignshed('LE'), age_wake, dissipate_wake of every rotor, in the driver's order.
+    !! Call gpu_touch(ir, GPU_WING) after the driver moves a rotor (main.f90:455-463) and after map_gam.
+    type(rotor_class), intent(in) :: rotor(:)
+    real(dp), intent(in) :: dt, kinematicVisc
+    integer, intent(in) :: wakeDissipation
+    integer :: ir
+    do ir = 1, size(rotor)
+      call gpu_sync_rotor(rotor(ir), ir, .false.)
+    enddo
+    do ir = 1, size(rotor)
+      call check(vlc_rotor_assignshed(ctx, ir - 1, 0_c_int))
+    enddo
+    do ir = 1, size(rotor)
+      call check(vlc_rotor_age_wake(ctx, ir - 1, dt, rotor(ir)%omegaSlow))
+    enddo
+    if (wakeDissipation == 1) then
+      do ir = 1, size(rotor)
+        call check(vlc_rotor_dissipate_wake(ctx, ir - 1, dt, kinematicVisc))
+      enddo
+    endif
+  end subroutine gpu_wake_prestep
+
+  subroutine gpu_wake_convect(rotor, iter, dt, fdScheme, wakeStrain, initWakeVelNt)
+    !! Replaces main.f90:800-1440: the wake sweeps, the fdScheme switch (0 explicit Euler :846-859, 1 predictor-
+    !! corrector :861-949, 3 Adams-Bashforth / Adams-Moulton :1002-1115) with its velocity bookkeeping, strain_wake,
+    !! rollup, assignshed('TE').
+    type(rotor_class), intent(in) :: rotor(:)
+    integer, intent(in) :: iter, fdScheme, wakeStrain, initWakeVelNt
+    real(dp), intent(in) :: dt
+    integer :: ir
+    integer(c_int) :: addInit
+    addInit = merge(1_c_int, 0_c_int, iter < initWakeVelNt)
+    do ir = 1, size(rotor)
+      call gpu_sync_rotor(rotor(ir), ir, .false.)   ! the solve changed the wing's circulation
+    enddo
+    call check(vlc_wake_sweep(ctx, 0_c_int, addInit))
+    select case (fdScheme)
+    case (0)
+      do ir = 1, size(rotor)
+        call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+      enddo
+    case (1)
+      do ir = 1, size(rotor)
+        call check(vlc_rotor_wake_to_predicted(ctx, ir - 1))
+        call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 1_c_int))
+      enddo
+      call check(vlc_wake_sweep(ctx, 1_c_int, addInit))
+      do ir = 1, size(rotor)
+        call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_ORDER2))
+        call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+      enddo
+    case (3)
+      if (iter == 1) then
+        do ir = 1, size(rotor)
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_FIRST_STEP))
+        enddo
+      else
+        do ir = 1, size(rotor)
+          call check(vlc_rotor_wake_to_predicted(ctx, ir - 1))
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_AB2))
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 1_c_int))
+        enddo
+        call check(vlc_wake_sweep(ctx, 1_c_int, addInit))
+        do ir = 1, size(rotor)
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_AM2))
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_SHIFT_HISTORY))
+        enddo
+      endif
+    case default
+      error stop 'ERROR: gpu_wake_convect: fdScheme 2, 4, 5 are not on the device path'
+    end select
+    if (wakeStrain == 1) then
+      do ir = 1, size(rotor)
+        call check(vlc_rotor_strain_wake(ctx, ir - 1))
+      enddo
+    endif
+    do ir = 1, size(rotor)
+      if (rotor(ir)%nNwake <= 0) cycle
+      if (rotor(ir)%rowNear == 1) call check(vlc_rotor_rollup(ctx, ir - 1))
+      call check(vlc_rotor_assignshed(ctx, ir - 1, 1_c_int))
+    enddo
+  end subroutine gpu_wake_convect
+
+  subroutine gpu_download_wake(rotor)
+    !! Bring the device's wake records back into the driver's derived types (before wake plots / restart files).
+    type(rotor_class), intent(inout) :: rotor(:)
+    integer :: ir, ib
+    real(c_double), allocatable :: buf(:)
+    do ir = 1, size(rotor)
+      do ib = 1, rotor(ir)%nb
+        if (rotor(ir)%nNwake > 0) then
+          allocate (buf(50*size(rotor(ir)%blade(ib)%waN)))
+          call check(vlc_rotor_get_nwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
+          rotor(ir)%blade(ib)%waN = reshape(transfer(buf, rotor(ir)%blade(ib)%waN), shape(rotor(ir)%blade(ib)%waN))
+          deallocate (buf)
+        endif
+        if (rotor(ir)%nFwake > 0) then
+          allocate (buf(13*size(rotor(ir)%blade(ib)%waF)))
+          call check(vlc_rotor_get_fwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
+          rotor(ir)%blade(ib)%waF = transfer(buf, rotor(ir)%blade(ib)%waF)
+          deallocate (buf)
+        endif
+      enddo
+    enddo
+  end subroutine gpu_download_wake
 
 end module libGPU

@@ -144,6 +144,64 @@ int vlc_rotor_solve(vlc_ctx* ctx, int ir, const double* RHS, double* gamVec);
 /* AIC_inv (N x N) if the caller wants the explicit inverse the reference stores. */
 int vlc_rotor_get_AIC_inv(vlc_ctx* ctx, int ir, double* AIC_inv);
 
+/* ---- tier 2b: the reference's wake mutators on the device copies (device-resident time stepping) ------------- */
+/*
+ * With these the wake records uploaded once by vlc_rotor_put_nwake / _put_fwake never travel again: every procedure
+ * of the reference's time loop that changes the wake (main.f90:466-506, :800-1440) has a device twin that works on the
+ * library's copies of waN / waF / waNPredicted / waFPredicted in the reference's own record layout, and the velocity
+ * arrays velNwake, velNwake1, velNwakePredicted, velNwakeStep, velFwake... (classdef.f90:285-292) live on the device
+ * too.  The driver keeps its row counters (vlc_rotor_set_rows) and its wing (vlc_rotor_put_wing: the shed edge and its
+ * circulation are read from it).  Arithmetic and statement order follow the reference; results are bit-identical to
+ * the CPU restatement for the same inputs (tests/test_gpu_resident.py).  nNwakeEnd = nNwake and nFwakeEnd = nFwake
+ * (classdef.f90:3054-3055; the prescribed-wake generator that would change them is out of scope).
+ */
+/* rotor_class members the mutators read: nbConvect (classdef.f90:3041-3045), axisymmetrySwitch, ductSwitch,
+ * suppressFwakeSwitch, rollupStart / rollupEnd (1-based columns, :3135-3136), rollupSign = Omega*controlPitch(1) (only
+ * its sign is used, :4541), apparentViscCoeff, decayCoeff, initWakeVel. */
+int vlc_rotor_set_wake_params(vlc_ctx* ctx, int ir, int nbConvect, int axisymmetrySwitch, int ductSwitch,
+                              int suppressFwakeSwitch, int rollupStart, int rollupEnd, double rollupSign,
+                              double apparentViscCoeff, double decayCoeff, double initWakeVel);
+/* rotor%shaftAxis, rotor%hubCoords of the current step (they move with the body, main.f90:455-463). */
+int vlc_rotor_set_frame(vlc_ctx* ctx, int ir, const double* shaftAxis, const double* hubCoords);
+/* = rotor%assignshed('LE' | 'TE') classdef.f90:4297-4325; edge 0 = 'LE', 1 = 'TE'.  Reads the uploaded wing. */
+int vlc_rotor_assignshed(vlc_ctx* ctx, int ir, int edge);
+/* = rotor%age_wake(dt) classdef.f90:4331-4354 (omegaSlow = rotor%omegaSlow) */
+int vlc_rotor_age_wake(vlc_ctx* ctx, int ir, double dt, double omegaSlow);
+/* = rotor%dissipate_wake(dt, kinematicVisc) classdef.f90:4356-4408 */
+int vlc_rotor_dissipate_wake(vlc_ctx* ctx, int ir, double dt, double kinematicVisc);
+/* = rotor%strain_wake() classdef.f90:4410-4422 */
+int vlc_rotor_strain_wake(vlc_ctx* ctx, int ir);
+/* waNPredicted(rowNear:, :) = waN(rowNear:, :), waFPredicted(rowFar:) = waF(rowFar:) of the convected blades
+ * (main.f90:869-872, :1028-1030) */
+int vlc_rotor_wake_to_predicted(vlc_ctx* ctx, int ir);
+/* = rotor%convectwake(iter, dt, 'C' | 'P') classdef.f90:4786-4830 with the device's velNwake / velFwake: shift the
+ * corners (blade_convectwake :1515-1575, the predictor's loop quirk included), re-stitch (wake_continuity
+ * :1609-1702), axisymmetric copy + rotate of blades 2..nb (:4801-4823). */
+int vlc_rotor_convectwake(vlc_ctx* ctx, int ir, double dt, int predicted);
+/* = rotor%rollup() classdef.f90:4515-4605 (shiftFwake :4500-4513 when the far wake is full, then shiftwake :4481-4498);
+ * the driver calls it when rowNear == 1 (main.f90:1421). */
+int vlc_rotor_rollup(vlc_ctx* ctx, int ir);
+/* The wake sweeps of the convection driver for ALL rotors at once (main.f90:800-838; 'P': :889-911, :1057-1081):
+ * vel{N,F}wake[Predicted](active rows) of every convected blade <- sum over source rotors of
+ * vind_on{N,F}wake_byRotor; addInitWakeVel != 0 adds -/+ initWakeVel*shaftAxis with the reference's signs. */
+int vlc_wake_sweep(vlc_ctx* ctx, int predicted, int addInitWakeVel);
+/* Bookkeeping of the velocity arrays between the sweeps (convected blades, whole arrays like the reference). */
+enum {
+  VLC_VEL_FIRST_STEP = 0,    /* main.f90:1013-1020  vel1 = vel                                         */
+  VLC_VEL_AB2 = 1,           /* main.f90:1031-1041  velStep = vel; vel = 0.5*(3*vel - vel1)            */
+  VLC_VEL_AM2 = 2,           /* main.f90:1094-1099  vel = (velPredicted + velStep)*0.5                 */
+  VLC_VEL_SHIFT_HISTORY = 3, /* main.f90:1103-1107  vel1 = velStep                                     */
+  VLC_VEL_ORDER2 = 4         /* main.f90:927-940    vel(active) = vel_order2(vel, velPredicted)        */
+};
+int vlc_rotor_wakevel_op(vlc_ctx* ctx, int ir, int op);
+/* Read the device copies back (plots, restart files, tests): whole arrays of blade ib in the reference layout.
+ * which: 0 = velNwake/velFwake, 1 = ...1, 2 = ...Predicted, 3 = ...Step; either pointer may be NULL. */
+int vlc_rotor_get_nwake(vlc_ctx* ctx, int ir, int ib, int predicted, double* waN /* nNwake*ns x 50 */);
+int vlc_rotor_get_fwake(vlc_ctx* ctx, int ir, int ib, int predicted, double* waF /* nFwake x 13 */);
+int vlc_rotor_put_wakevel(vlc_ctx* ctx, int ir, int ib, int which, const double* velN, const double* velF);
+int vlc_rotor_get_wakevel(vlc_ctx* ctx, int ir, int ib, int which, double* velN /* 3 x nNwake x (ns+1) */,
+                          double* velF /* 3 x nFwake */);
+
 /* ---- tier 3: device-resident wake state (node-indexed SoA) -------------------------------- */
 /*
  * A "lattice" is one blade's near wake kept on the device as TE nodes: nodes(3, nrows+1, ns+1)

@@ -81,6 +81,7 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_vel_order2_Nwake": (None, [_vp, _vp, i32, i32, _vp]),
         "orc_vel_order2_Fwake": (None, [_vp, _vp, i32, _vp]),
         "orc_rotor_dims": (None, [_vp, _vp]),
+        "orc_rotor_get_params": (None, [_vp, _vp]),
         "orc_gridgen": (None, [i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, _vp, _vp]),
         # case driver (vlc_case.c)
         "orc_case_new": (_vp, [i32]),
@@ -206,6 +207,16 @@ class Rotor:
         return dict(zip(["nb", "nc", "ns", "nNwake", "nFwake", "rowNear", "rowFar", "nbConvect", "nNwakeEnd",
                          "nFwakeEnd"], list(d)))
 
+    def params(self) -> dict:
+        """What the wake mutators read from rotor_class (orc_rotor_get_params)."""
+        o = np.zeros(18)
+        self.lib.orc_rotor_get_params(self.h, o.ctypes.data)
+        names = ["nbConvect", "axisymmetrySwitch", "ductSwitch", "suppressFwakeSwitch", "rollupStart", "rollupEnd"]
+        d = {n: int(o[i]) for i, n in enumerate(names)}
+        d.update(Omega=o[6], theta0=o[7], omegaSlow=o[8], apparentViscCoeff=o[9], decayCoeff=o[10], initWakeVel=o[11],
+                 shaftAxis=o[12:15].copy(), hubCoords=o[15:18].copy())
+        return d
+
     def sec(self, ib, name, width=1):
         """Sectional array of blade ib by name (vlc_case.c orc_blade_sec): (ns,) or (ns, 3)."""
         p = self.lib.orc_blade_sec(self.h, ib, name.encode())
@@ -310,8 +321,9 @@ class OrcHooks(C.Structure):
     VIND_ONF = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp)
     CALC_AIC = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, _vp)
     SOLVE = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, _vp)
+    WAKE_STAGE = C.CFUNCTYPE(C.c_int, _vp, C.c_int)   # optional device-resident stages (NULL = CPU restatement)
     _fields_ = [("user", _vp), ("vind_points", VIND_POINTS), ("vind_onNwake", VIND_ONN), ("vind_onFwake", VIND_ONF),
-                ("calcAIC", CALC_AIC), ("solve", SOLVE)]
+                ("calcAIC", CALC_AIC), ("solve", SOLVE), ("wake_prestep", WAKE_STAGE), ("wake_convect", WAKE_STAGE)]
 
 
 class Case:

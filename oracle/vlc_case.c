@@ -1002,6 +1002,8 @@ void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *h) {
     c->hooks.vind_onFwake = cpu_vind_onFwake;
     c->hooks.calcAIC = cpu_calcAIC;
     c->hooks.solve = cpu_solve;
+    c->hooks.wake_prestep = NULL;
+    c->hooks.wake_convect = NULL;
   }
 }
 
@@ -1421,7 +1423,10 @@ int orc_case_step(orc_case_t *c) {
     r->gen_wing++;
   }
   for (int ir = 0; ir < c->nr; ++ir) c->rotor[ir]->gen_wake[0]++; /* rows moved, shed row attached, aged, dissipated below */
-  if (cfg->wakeSuppress == 0) { /* :466-506 */
+  if (cfg->wakeSuppress == 0 && c->hooks.wake_prestep) { /* device-resident wake: the hook owner does :466-506 */
+    int rc = c->hooks.wake_prestep(c->hooks.user, iter);
+    if (rc) return rc;
+  } else if (cfg->wakeSuppress == 0) { /* :466-506 */
     for (int ir = 0; ir < c->nr; ++ir)
       if (c->rotor[ir]->nNwake > 0) orc_rotor_assignshed(c->rotor[ir], "LE");
     for (int ir = 0; ir < c->nr; ++ir)
@@ -1478,7 +1483,24 @@ int orc_case_step(orc_case_t *c) {
     if (rc) return rc;
   }
   /* wake convection, :800-1440 */
-  if (cfg->wakeSuppress == 0) {
+  if (cfg->wakeSuppress == 0 && c->hooks.wake_convect) { /* device-resident wake: the hook owner does :800-1440 */
+    if (cfg->fdScheme != 0 && cfg->fdScheme != 1 && cfg->fdScheme != 3) {
+      snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 3)", cfg->fdScheme);
+      return 3;
+    }
+    int rc = c->hooks.wake_convect(c->hooks.user, iter);
+    if (rc) return rc;
+    const int nsweeps = (cfg->fdScheme == 0 || (cfg->fdScheme == 3 && iter == 1)) ? 1 : 2;
+    for (int ir = 0; ir < c->nr; ++ir) { /* the same count wake_sweep() keeps */
+      const orc_rotor_t *r = c->rotor[ir];
+      if (r->nNwake <= 0) continue;
+      const int rowsN = r->nNwakeEnd - r->rowNear + 1, rowsF = r->nFwakeEnd - r->rowFar + 1;
+      for (int jr = 0; jr < c->nr; ++jr) {
+        const double nsrc = n_wing_fil(c->rotor[jr]) + n_wake_fil(c->rotor[jr]);
+        c->pairs += nsweeps * (double)r->nbConvect * ((rowsN > 0 ? (double)rowsN * (r->ns + 1) : 0.0) + (rowsF > 0 ? rowsF : 0)) * nsrc;
+      }
+    }
+  } else if (cfg->wakeSuppress == 0) {
     int rc = wake_sweep(c, 0);
     if (rc) return rc;
     switch (cfg->fdScheme) {

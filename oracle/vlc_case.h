@@ -52,6 +52,13 @@ typedef struct orc_hooks {
   int (*calcAIC)(void *user, int ir, double *AIC, double *AIC_inv);
   /* gamVec = matmulAX(AIC_inv, RHS) (main.f90:190, :596) */
   int (*solve)(void *user, int ir, const double *RHS, double *gamVec);
+  /* OPTIONAL, both or neither (NULL = this file's CPU restatement): device-resident stepping.  wake_prestep replaces
+   * main.f90:466-506 (assignshed 'LE', age_wake, dissipate_wake of every rotor); wake_convect replaces :800-1440 (the
+   * wake sweeps, the fdScheme switch with its velocity bookkeeping, strain_wake, rollup, assignshed 'TE').  When they
+   * are set the driver never reads or writes its own wake records or wake velocity arrays: the hook owner holds them
+   * (tests/native/case_gpu_hooks.c in resident mode: the C ABI's tier 2b). */
+  int (*wake_prestep)(void *user, int iter);
+  int (*wake_convect)(void *user, int iter);
 } orc_hooks_t;
 
 typedef struct orc_case orc_case_t;

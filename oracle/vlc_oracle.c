@@ -1009,6 +1009,17 @@ void orc_rotor_gens(const orc_rotor_t *r, unsigned long out[3]) {
   out[1] = r->gen_wake[0];
   out[2] = r->gen_wake[1];
 }
+/* out[0..17] = nbConvect axisymmetrySwitch ductSwitch suppressFwakeSwitch rollupStart rollupEnd Omega controlPitch(1)
+ * omegaSlow apparentViscCoeff decayCoeff initWakeVel shaftAxis(3) hubCoords(3): what the wake mutators read */
+void orc_rotor_get_params(const orc_rotor_t *r, double *out) {
+  out[0] = r->nbConvect; out[1] = r->axisymmetrySwitch; out[2] = r->ductSwitch; out[3] = r->suppressFwakeSwitch;
+  out[4] = r->rollupStart; out[5] = r->rollupEnd; out[6] = r->Omega; out[7] = r->controlPitch[0];
+  out[8] = r->omegaSlow; out[9] = r->apparentViscCoeff; out[10] = r->decayCoeff; out[11] = r->initWakeVel;
+  for (int k = 0; k < 3; ++k) {
+    out[12 + k] = r->shaftAxis[k];
+    out[15 + k] = r->hubCoords[k];
+  }
+}
 void orc_rotor_set_rows(orc_rotor_t *r, int rowNear, int rowFar) {
   r->rowNear = rowNear;
   r->rowFar = rowFar;

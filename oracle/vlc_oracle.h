@@ -194,6 +194,7 @@ double *orc_rotor_vec(orc_rotor_t *r, int which);
 void orc_rotor_dims(const orc_rotor_t *r, int *out);
 void orc_rotor_gens(const orc_rotor_t *r, unsigned long out[3]); /* gen_wing, gen_wake C, gen_wake P */
 void orc_rotor_set_rows(orc_rotor_t *r, int rowNear, int rowFar);
+void orc_rotor_get_params(const orc_rotor_t *r, double *out18);
 void orc_rotor_set_params(orc_rotor_t *r, int surfaceType, int axisymmetrySwitch, int nbConvect, double Omega,
                           double omegaSlow, const double *shaftAxis, const double *hubCoords, double theta0,
                           double apparentViscCoeff, double decayCoeff, int rollupStart, int rollupEnd);

@@ -26,7 +26,49 @@ typedef struct {
   /* what the library currently holds: generation of the wing and of the 'C' / 'P' wake, and the row counters */
   unsigned long have_wing[MAX_ROTORS], have_wake[MAX_ROTORS][2];
   int have_rows[MAX_ROTORS][2][2];
+  /* resident mode (tier 2b of the C ABI): the wake lives on the device; only the wing travels */
+  int resident, resident_started;
+  long wing_uploads;
 } gpu_user_t;
+
+#define CK(expr)                        \
+  do {                                  \
+    int rc_ = (expr);                   \
+    if (rc_) return u->last_rc = rc_;   \
+  } while (0)
+
+/* resident mode: row counters, frame and (when the driver moved it or changed its circulation) the wing */
+static int sync_wing(gpu_user_t *u, int jr) {
+  orc_rotor_t *r = orc_case_rotor(u->cas, jr);
+  CK(vlc_rotor_set_rows(u->ctx, jr, r->rowNear, r->rowFar));
+  CK(vlc_rotor_set_frame(u->ctx, jr, r->shaftAxis, r->hubCoords));
+  if (r->gen_wing != u->have_wing[jr]) {
+    for (int ib = 0; ib < r->nb; ++ib) CK(vlc_rotor_put_wing(u->ctx, jr, ib, orc_rotor_wiP(r, ib)));
+    u->have_wing[jr] = r->gen_wing;
+    u->wing_uploads++;
+  }
+  return 0;
+}
+
+/* resident mode, first step: the wake records as rotor_init left them (core radii, the first shed edge) go up once,
+ * whole arrays, current and predicted */
+static int resident_begin(gpu_user_t *u) {
+  for (int jr = 0; jr < u->nr; ++jr) {
+    orc_rotor_t *r = orc_case_rotor(u->cas, jr);
+    CK(vlc_rotor_set_wake_params(u->ctx, jr, r->nbConvect, r->axisymmetrySwitch, r->ductSwitch, r->suppressFwakeSwitch,
+                                 r->rollupStart, r->rollupEnd, r->Omega * r->controlPitch[0], r->apparentViscCoeff,
+                                 r->decayCoeff, r->initWakeVel));
+    CK(vlc_rotor_set_rows(u->ctx, jr, 1, 1));
+    for (int ib = 0; ib < r->nb; ++ib)
+      for (int s = 0; s < 2; ++s) {
+        if (r->nNwake > 0) CK(vlc_rotor_put_nwake(u->ctx, jr, ib, s, orc_rotor_waN(r, ib, s)));
+        if (r->nFwake > 0) CK(vlc_rotor_put_fwake(u->ctx, jr, ib, s, orc_rotor_waF(r, ib, s)));
+      }
+    u->uploads++;
+  }
+  u->resident_started = 1;
+  return 0;
+}
 
 /* = gpu_sync_rotor of fortran/libGPU.f90: row counters + wing + near/far wake records of every blade.  State the
  * driver has not touched since the last transfer (generation counters of oracle/vlc_case.c; a Fortran shim would set
@@ -38,6 +80,7 @@ static int sync_rotor(gpu_user_t *u, int jr, int predicted) {
   orc_rotor_dims(r, d);
   orc_rotor_gens(r, g);
   const int nb = d[0], nNwake = d[3], nFwake = d[4], s = predicted ? 1 : 0;
+  if (u->resident && u->resident_started) return sync_wing(u, jr); /* the device's wake is the wake */
   if ((rc = vlc_rotor_set_rows(u->ctx, jr, d[5], d[6]))) return rc;
   const int wing_new = (g[0] != u->have_wing[jr]);
   const int wake_new = (g[1 + s] != u->have_wake[jr][s]) || u->have_rows[jr][s][0] != d[5] || u->have_rows[jr][s][1] != d[6];
@@ -102,6 +145,78 @@ static int h_solve(void *user, int ir, const double *RHS, double *gamVec) {
   return u->last_rc = vlc_rotor_solve(u->ctx, ir, RHS, gamVec);
 }
 
+/* main.f90:466-506 on the device: assignshed('LE'), age_wake, dissipate_wake of every rotor, in the driver's order */
+static int h_wake_prestep(void *user, int iter) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  (void)iter;
+  const orc_config_t *cfg = orc_case_config(u->cas);
+  if (!u->resident_started) CK(resident_begin(u));
+  for (int ir = 0; ir < u->nr; ++ir) CK(sync_wing(u, ir));
+  for (int ir = 0; ir < u->nr; ++ir) CK(vlc_rotor_assignshed(u->ctx, ir, 0));
+  for (int ir = 0; ir < u->nr; ++ir) CK(vlc_rotor_age_wake(u->ctx, ir, cfg->dt, orc_case_rotor(u->cas, ir)->omegaSlow));
+  if (cfg->wakeDissipation == 1)
+    for (int ir = 0; ir < u->nr; ++ir) CK(vlc_rotor_dissipate_wake(u->ctx, ir, cfg->dt, cfg->kinematicVisc));
+  return 0;
+}
+
+/* main.f90:800-1440 on the device: the wake sweeps, the fdScheme switch (0: explicit Euler, 1: predictor-corrector,
+ * 3: Adams-Bashforth / Adams-Moulton), strain_wake, rollup, assignshed('TE') */
+static int h_wake_convect(void *user, int iter) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  const orc_config_t *cfg = orc_case_config(u->cas);
+  const double dt = cfg->dt;
+  const int addInit = iter < cfg->initWakeVelNt;
+  const int nr = u->nr;
+  for (int ir = 0; ir < nr; ++ir) CK(sync_wing(u, ir)); /* the solve changed the wing's circulation */
+  CK(vlc_wake_sweep(u->ctx, 0, addInit));
+  switch (cfg->fdScheme) {
+    case 0: /* :846-859 */
+      for (int ir = 0; ir < nr; ++ir) CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
+      break;
+    case 1: /* :861-949 */
+      for (int ir = 0; ir < nr; ++ir) {
+        CK(vlc_rotor_wake_to_predicted(u->ctx, ir));
+        CK(vlc_rotor_convectwake(u->ctx, ir, dt, 1));
+      }
+      CK(vlc_wake_sweep(u->ctx, 1, addInit));
+      for (int ir = 0; ir < nr; ++ir) {
+        CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_ORDER2));
+        CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
+      }
+      break;
+    case 3: /* :1002-1115 */
+      if (iter == 1) {
+        for (int ir = 0; ir < nr; ++ir) {
+          CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
+          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_FIRST_STEP));
+        }
+      } else {
+        for (int ir = 0; ir < nr; ++ir) {
+          CK(vlc_rotor_wake_to_predicted(u->ctx, ir));
+          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_AB2));
+          CK(vlc_rotor_convectwake(u->ctx, ir, dt, 1));
+        }
+        CK(vlc_wake_sweep(u->ctx, 1, addInit));
+        for (int ir = 0; ir < nr; ++ir) {
+          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_AM2));
+          CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
+          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_SHIFT_HISTORY));
+        }
+      }
+      break;
+    default: return u->last_rc = VLC_ERR_ARG;
+  }
+  if (cfg->wakeStrain == 1) /* :1409-1416 */
+    for (int ir = 0; ir < nr; ++ir) CK(vlc_rotor_strain_wake(u->ctx, ir));
+  for (int ir = 0; ir < nr; ++ir) { /* :1419-1439 */
+    const orc_rotor_t *r = orc_case_rotor(u->cas, ir);
+    if (r->nNwake <= 0) continue;
+    if (r->rowNear == 1) CK(vlc_rotor_rollup(u->ctx, ir));
+    CK(vlc_rotor_assignshed(u->ctx, ir, 1));
+  }
+  return 0;
+}
+
 /* Declares every rotor to the library (gpu_init of the Fortran shim) and installs the hook table.
  * The case must have its rotors initialised (orc_case_init_rotors).  Returns an opaque handle (free with
  * case_gpu_hooks_free) or NULL. */
@@ -120,6 +235,7 @@ void *case_gpu_hooks_install(orc_case_t *cas, vlc_ctx *ctx, int nr) {
     }
   }
   orc_hooks_t h;
+  memset(&h, 0, sizeof h);
   h.user = u;
   h.vind_points = h_vind_points;
   h.vind_onNwake = h_onN;
@@ -130,6 +246,45 @@ void *case_gpu_hooks_install(orc_case_t *cas, vlc_ctx *ctx, int nr) {
   return u;
 }
 
+/* Same, in resident mode: the two wake stages of the time loop run on the device too (tier 2b) and the wake records
+ * never travel after the first step. */
+void *case_gpu_hooks_install_resident(orc_case_t *cas, vlc_ctx *ctx, int nr) {
+  gpu_user_t *u = (gpu_user_t *)case_gpu_hooks_install(cas, ctx, nr);
+  if (!u) return NULL;
+  u->resident = 1;
+  orc_hooks_t h;
+  memset(&h, 0, sizeof h);
+  h.user = u;
+  h.vind_points = h_vind_points;
+  h.vind_onNwake = h_onN;
+  h.vind_onFwake = h_onF;
+  h.calcAIC = h_calcAIC;
+  h.solve = h_solve;
+  h.wake_prestep = h_wake_prestep;
+  h.wake_convect = h_wake_convect;
+  orc_case_set_hooks(cas, &h);
+  return u;
+}
+
+/* resident mode: bring the device's wake (records and velocity arrays) back into the driver's arrays */
+int case_gpu_hooks_download_wake(void *handle) {
+  gpu_user_t *u = (gpu_user_t *)handle;
+  for (int jr = 0; jr < u->nr; ++jr) {
+    orc_rotor_t *r = orc_case_rotor(u->cas, jr);
+    for (int ib = 0; ib < r->nb; ++ib) {
+      for (int s = 0; s < 2; ++s) {
+        if (r->nNwake > 0) CK(vlc_rotor_get_nwake(u->ctx, jr, ib, s, orc_rotor_waN(r, ib, s)));
+        if (r->nFwake > 0) CK(vlc_rotor_get_fwake(u->ctx, jr, ib, s, orc_rotor_waF(r, ib, s)));
+      }
+      for (int w = 0; w < 4; ++w)
+        CK(vlc_rotor_get_wakevel(u->ctx, jr, ib, w, r->nNwake > 0 ? orc_rotor_vel(r, ib, w) : NULL,
+                                 r->nFwake > 0 ? orc_rotor_vel(r, ib, 4 + w) : NULL));
+    }
+  }
+  return 0;
+}
+
+long case_gpu_hooks_wing_uploads(void *handle) { return ((gpu_user_t *)handle)->wing_uploads; }
 long case_gpu_hooks_uploads(void *handle) { return ((gpu_user_t *)handle)->uploads; }
 long case_gpu_hooks_skipped(void *handle) { return ((gpu_user_t *)handle)->skipped; }
 int case_gpu_hooks_last_rc(void *handle) { return ((gpu_user_t *)handle)->last_rc; }

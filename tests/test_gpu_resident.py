@@ -1,0 +1,302 @@
+"""Device-resident time stepping (tier 2b of the C ABI): the reference's wake mutators -- assignshed,
+age_wake, dissipate_wake, strain_wake, convectwake (+ wake_continuity, axisymmetric copy/rotate), rollup (+ shiftwake,
+shiftFwake) and the velocity bookkeeping of the convection driver -- on the library's device copies of the reference's
+own records.
+
+ 1. every mutator, alone, against the CPU restatement on the same developed wake: BIT-EXACT (integer/byte bar: these are
+    unfused elementwise maps in the reference's statement order);
+ 2. the whole time loop with the wake never leaving the device (tests/native/case_gpu_hooks.c in resident mode) against
+    the reference's golden CT/CL histories (every row, 7 digits) and against the CPU driver (1e-8 over the window).
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+TOL_HISTORY = 1e-8
+
+
+# --------------------------------------------------------------------------------------------- 1. mutators, bit-exact
+
+def _developed(oracle, name, nsteps, mutate=None):
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    if mutate:
+        mutate(fx)
+    c = oracle.Case(fx)
+    c.init()
+    for _ in range(nsteps):
+        c.step()
+    return c, fx
+
+
+def _upload(ctx, r, ir=0):
+    """The oracle rotor's whole state -> the library (wing, wake records 'C' and 'P', the four velocity arrays)."""
+    d, p = r.dims(), r.params()
+    ctx.rotor_define(ir, r.nb, r.nc, r.ns, r.nNwake, r.nFwake, 1)
+    ctx.rotor_set_wake_params(ir, p["nbConvect"], p["axisymmetrySwitch"], p["ductSwitch"], p["suppressFwakeSwitch"],
+                              p["rollupStart"], p["rollupEnd"], p["Omega"] * p["theta0"], p["apparentViscCoeff"],
+                              p["decayCoeff"], p["initWakeVel"])
+    ctx.rotor_set_frame(ir, p["shaftAxis"], p["hubCoords"])
+    ctx.rotor_set_rows(ir, 1, 1)
+    for ib in range(r.nb):
+        ctx.rotor_put_wing(ir, ib, r.wiP(ib))
+        for pred in (False, True):
+            ctx.rotor_put_nwake(ir, ib, r.waN(ib, pred), pred)
+            if r.nFwake:
+                ctx.rotor_put_fwake(ir, ib, r.waF(ib, pred), pred)
+        for w in range(4):
+            ctx.rotor_put_wakevel(ir, ib, w, r.vel(ib, w), r.vel(ib, 4 + w) if r.nFwake else None)
+    ctx.rotor_set_rows(ir, d["rowNear"], d["rowFar"])
+
+
+def _same(ctx, r, what, ir=0):
+    """Device copies == the oracle's arrays, bit for bit (NaN-free data: array_equal is a bit comparison up to -0)."""
+    for ib in range(r.nb):
+        for pred in (False, True):
+            g = ctx.rotor_get_nwake(ir, ib, r.nNwake, r.ns, pred)
+            h = r.waN(ib, pred)
+            assert np.array_equal(g, h), (what, "waN", ib, pred, float(np.max(np.abs(g - h))), np.argwhere(g != h)[:4])
+            if r.nFwake:
+                g, h = ctx.rotor_get_fwake(ir, ib, r.nFwake, pred), r.waF(ib, pred)
+                assert np.array_equal(g, h), (what, "waF", ib, pred, float(np.max(np.abs(g - h))), np.argwhere(g != h)[:4])
+        for w in range(4):
+            vn, vf = ctx.rotor_get_wakevel(ir, ib, w, r.nNwake, r.ns, r.nFwake)
+            assert np.array_equal(vn, r.vel(ib, w)), (what, "velN", ib, w)
+            if r.nFwake:
+                assert np.array_equal(vf, r.vel(ib, 4 + w)), (what, "velF", ib, w)
+
+
+def _to_predicted(r):  # main.f90:869-872 on the oracle's arrays
+    d, p = r.dims(), r.params()
+    for ib in range(p["nbConvect"]):
+        r.waN(ib, True)[:, d["rowNear"] - 1:, :] = r.waN(ib, False)[:, d["rowNear"] - 1:, :]
+        if r.nFwake:
+            r.waF(ib, True)[d["rowFar"] - 1:, :] = r.waF(ib, False)[d["rowFar"] - 1:, :]
+
+
+def _vel_op(oracle, r, op):
+    """main.f90:1013-1020, :1031-1041, :1094-1099, :1103-1107, :927-940 on the oracle's arrays (numpy: unfused)."""
+    d, p = r.dims(), r.params()
+    for ib in range(p["nbConvect"]):
+        for far in ((0, 4) if r.nFwake else (0,)):
+            v, v1, vp, vs = (r.vel(ib, far + k) for k in range(4))
+            if op == 0:
+                v1[...] = v
+            elif op == 1:
+                vs[...] = v
+                v[...] = 0.5 * (3.0 * v - v1)
+            elif op == 2:
+                v[...] = (vp + vs) * 0.5
+            elif op == 3:
+                v1[...] = vs
+            elif op == 4:
+                if far == 0:
+                    r0, rows = d["rowNear"], r.nNwake - d["rowNear"] + 1
+                    if rows > 0:
+                        a = np.ascontiguousarray(v[:, r0 - 1:, :])
+                        b = np.ascontiguousarray(vp[:, r0 - 1:, :])
+                        o = np.empty_like(a)
+                        r.lib.orc_vel_order2_Nwake(a.ctypes.data, b.ctypes.data, rows, r.ns + 1, o.ctypes.data)
+                        v[:, r0 - 1:, :] = o
+                else:
+                    r0, rows = d["rowFar"], r.nFwake - d["rowFar"] + 1
+                    if rows > 0:
+                        a = np.ascontiguousarray(v[r0 - 1:, :])
+                        b = np.ascontiguousarray(vp[r0 - 1:, :])
+                        o = np.empty_like(a)
+                        r.lib.orc_vel_order2_Fwake(a.ctypes.data, b.ctypes.data, rows, o.ctypes.data)
+                        v[r0 - 1:, :] = o
+
+
+def _exercise_mutators(ctx, oracle, c, fx, label):
+    r = c.rotor(0)
+    cfg = fx["config"]
+    dt, nu = float(c.config.dt), float(cfg.get("kinematicVisc", 0.0))
+    d, p = r.dims(), r.params()
+    rng = np.random.default_rng(7)
+    for ib in range(r.nb):              # velocity histories that differ from each other
+        for w in range(1, 4):
+            r.vel(ib, w)[...] = r.vel(ib, 0) * (1.0 + 0.1 * w) + 1e-3 * rng.standard_normal(r.vel(ib, 0).shape)
+            if r.nFwake:
+                r.vel(ib, 4 + w)[...] = r.vel(ib, 4) * (1.0 - 0.1 * w) + 1e-3 * rng.standard_normal(r.vel(ib, 4).shape)
+    _upload(ctx, r)
+    _same(ctx, r, "upload")
+    steps = []
+    # the order of one time step (main.f90:466-506, :800-1440), every stage checked on its own
+    r.lib.orc_rotor_assignshed(r.h, b"LE"); ctx.rotor_assignshed(0, "LE"); steps.append("assignshed LE"); _same(ctx, r, steps[-1])
+    r.lib.orc_rotor_age_wake(r.h, dt); ctx.rotor_age_wake(0, dt, p["omegaSlow"]); steps.append("age_wake"); _same(ctx, r, steps[-1])
+    r.lib.orc_rotor_dissipate_wake(r.h, dt, nu); ctx.rotor_dissipate_wake(0, dt, nu); steps.append("dissipate_wake"); _same(ctx, r, steps[-1])
+    for op, nm in ((1, "AB2"),):
+        _vel_op(oracle, r, op); ctx.rotor_wakevel_op(0, op); steps.append(nm); _same(ctx, r, nm)
+    _to_predicted(r); ctx.rotor_wake_to_predicted(0); steps.append("wake_to_predicted"); _same(ctx, r, steps[-1])
+    r.lib.orc_rotor_convectwake(r.h, 2, dt, b"P"); ctx.rotor_convectwake(0, dt, "P"); steps.append("convectwake P"); _same(ctx, r, steps[-1])
+    for op, nm in ((2, "AM2"), (4, "order2")):
+        _vel_op(oracle, r, op); ctx.rotor_wakevel_op(0, op); steps.append(nm); _same(ctx, r, nm)
+    r.lib.orc_rotor_convectwake(r.h, 2, dt, b"C"); ctx.rotor_convectwake(0, dt, "C"); steps.append("convectwake C"); _same(ctx, r, steps[-1])
+    for op, nm in ((3, "history"), (0, "first-step copy")):
+        _vel_op(oracle, r, op); ctx.rotor_wakevel_op(0, op); steps.append(nm); _same(ctx, r, nm)
+    if r.nFwake:
+        r.lib.orc_rotor_strain_wake(r.h); ctx.rotor_strain_wake(0); steps.append("strain_wake"); _same(ctx, r, steps[-1])
+    if d["rowNear"] == 1:
+        r.lib.orc_rotor_rollup(r.h); ctx.rotor_rollup(0); steps.append("rollup"); _same(ctx, r, steps[-1])
+    r.lib.orc_rotor_assignshed(r.h, b"TE"); ctx.rotor_assignshed(0, "TE"); steps.append("assignshed TE"); _same(ctx, r, steps[-1])
+    print(f"{label}: {len(steps)} device mutators bit-identical to the CPU restatement ({', '.join(steps)}); "
+          f"nb={r.nb} nbConvect={p['nbConvect']} rows {d['rowNear']}..{r.nNwake}, far {d['rowFar']}..{r.nFwake}")
+
+
+def test_mutators_bit_exact_axisymmetric_rotor_with_far_wake(ctx, oracle):
+    """elevateTest (5 blades, 4 of them rotated copies; dissipation; 30 near rows, far wake with truncation) after 34
+    steps: near wake full (roll-up + shiftwake active), far wake partly filled."""
+    c, fx = _developed(oracle, "elevateTest", 34)
+    _exercise_mutators(ctx, oracle, c, fx, "elevateTest @34")
+
+
+def test_mutators_bit_exact_far_wake_full(ctx, oracle):
+    """Short caradonna (2 blades convected independently, 12 near + 6 far rows) after 24 steps: the far wake is full,
+    so rollup goes through shiftFwake (classdef.f90:4570-4573)."""
+    def short(fx):
+        fx["config"]["nt"] = 40
+        fx["geom"][0]["nNwake"] = 12
+        fx["geom"][0]["wakeTruncateNt"] = 18      # nFwake = 6
+    c, fx = _developed(oracle, "caradonna", 24, short)
+    d = c.rotor(0).dims()
+    assert d["rowNear"] == 1 and d["rowFar"] == 1, d
+    _exercise_mutators(ctx, oracle, c, fx, "caradonna (short) @24")
+
+
+def test_mutators_bit_exact_growing_wing_wake(ctx, oracle):
+    """K&P wing after 20 steps: rowNear > 1 (the wake is still growing), no far wake, dissipation off."""
+    c, fx = _developed(oracle, "katzNplotkin_AR04", 20)
+    assert c.rotor(0).dims()["rowNear"] > 1
+    _exercise_mutators(ctx, oracle, c, fx, "K&P @20")
+
+
+# ------------------------------------------------------------------------ 2. the whole loop, wake resident on the GPU
+
+def _resident_hooks(case, ctx):
+    import ctypes as C
+    import subprocess
+    here = Path(__file__).resolve().parent / "native"
+    so = here / "libcase_gpu_hooks.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(here)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    lib.case_gpu_hooks_install_resident.restype = C.c_void_p
+    lib.case_gpu_hooks_install_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    for f in ("case_gpu_hooks_uploads", "case_gpu_hooks_wing_uploads"):
+        getattr(lib, f).restype = C.c_long
+        getattr(lib, f).argtypes = [C.c_void_p]
+    lib.case_gpu_hooks_last_rc.argtypes = [C.c_void_p]
+    lib.case_gpu_hooks_download_wake.argtypes = [C.c_void_p]
+    lib.case_gpu_hooks_free.argtypes = [C.c_void_p]
+    case.init_rotors()
+    h = lib.case_gpu_hooks_install_resident(case.h, ctx.h, case.nr)
+    assert h, "vlc_rotor_define failed"
+    return lib, h
+
+
+def _step(c, lib, h, ctx, it):
+    try:
+        c.step()
+    except RuntimeError as e:
+        raise AssertionError(f"step {it}: {e}; rc={lib.case_gpu_hooks_last_rc(h)} {ctx.lib.vlc_last_error(ctx.h)}") from e
+
+
+@pytest.mark.parametrize("name,nsteps", [("katzNplotkin_AR04", 160), ("elevateTest", 150)])
+def test_resident_run_reproduces_reference_golden_history(ctx, oracle, name, nsteps):
+    """Both golden histories of the reference, every row to the 7 printed digits, with the wake uploaded ONCE."""
+    import time
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    c = oracle.Case(fx)
+    lib, h = _resident_hooks(c, ctx)
+    c.init()
+    hist = [c.force_nondim(0)]
+    t1 = time.perf_counter()
+    pairs = 0.0
+    for it in range(nsteps):
+        _step(c, lib, h, ctx, it + 1)
+        pairs += c.pairs_last_step
+        hist.append(c.force_nondim(0))
+    t2 = time.perf_counter()
+    hist = np.array(hist)
+    ref = np.array(fx["ref_ForceNonDim"]["rows"])
+    ulp = 10.0 ** (np.floor(np.log10(np.abs(ref[:, 1]))) - 6)
+    dev = np.abs(hist[:, 0] - ref[:len(hist), 1]) / ulp
+    print(f"{name}: {nsteps} steps, wake resident on the device, in {t2 - t1:.2f} s ({nsteps / (t2 - t1):.1f} timesteps/s "
+          f"incl. the driver's host work; {pairs:.3e} pair interactions; wake uploads {lib.case_gpu_hooks_uploads(h)}, "
+          f"wing uploads {lib.case_gpu_hooks_wing_uploads(h)}); max deviation from the golden file {dev.max():.2f} units "
+          f"of the 7th digit")
+    assert dev.max() <= 1.0, (dev.max(), int(dev.argmax()))
+    # The device-made records still describe a lattice: the sweeps used the shared-node kernel.  Asked of the PREDICTED
+    # set, whose packed form is the one the last corrector sweep used; the current set is mid-update at the end of a
+    # step (after shiftwake the newest row's vf(4)%rVc waits for the next dissipate_wake, classdef.f90:4386-4392).
+    assert ctx.rotor_info(0, True)["shared_active"] == 1
+    lib.case_gpu_hooks_free(h)
+
+
+def _short_caradonna(fx):
+    fx["config"]["nt"] = 40
+    fx["geom"][0]["nNwake"] = 12
+
+
+# elevateTest amplifies rounding differences far more than the other cases (5 blades' wakes rolling up into each other:
+# the non-resident GPU run measures 1.6e-9 on CT after 50 steps too, tests/test_gpu_case.py), hence its wake tolerance
+@pytest.mark.parametrize("name,nsteps,mutate,wake_tol",
+                         [("simplewing", 40, None, 1e-9), ("tr1208", 30, None, 1e-9),
+                          ("caradonna", 30, _short_caradonna, 1e-9),
+                          ("elevateTest", 40, lambda fx: fx["config"].update(fdScheme=1), 1e-5),
+                          ("katzNplotkin_AR04", 30, lambda fx: fx["config"].update(fdScheme=0), 1e-9)])
+def test_resident_vs_cpu_driver(ctx, oracle, name, nsteps, mutate, wake_tol):
+    """CL/CT, circulation and the wake itself (downloaded at the end) against the CPU driver: the remaining BASELINE
+    configs, and the other two time-marching schemes (fdScheme 1 predictor-corrector, 0 explicit Euler)."""
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    if mutate:
+        mutate(fx)
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    lib, h = _resident_hooks(b, ctx)
+    a.init()
+    b.init()
+    worst = [0.0, 0.0]
+    for it in range(nsteps):
+        a.step()
+        _step(b, lib, h, ctx, it + 1)
+        fa, fb = a.force_nondim(0), b.force_nondim(0)
+        ga, gb = a.rotor(0).vec(0), b.rotor(0).vec(0)
+        worst[0] = max(worst[0], abs(fb[0] / fa[0] - 1.0))
+        worst[1] = max(worst[1], float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+    assert lib.case_gpu_hooks_download_wake(h) == 0
+    ra, rb = a.rotor(0), b.rotor(0)
+    dw = max(float(np.max(np.abs(ra.waN(ib) - rb.waN(ib)))) for ib in range(ra.nb))
+    if ra.nFwake:
+        dw = max(dw, max(float(np.max(np.abs(ra.waF(ib) - rb.waF(ib)))) for ib in range(ra.nb)))
+    print(f"{name} (fdScheme {fx['config'].get('fdScheme')}): {nsteps} steps resident, max rel CL/CT err {worst[0]:.3e}, "
+          f"gamVec {worst[1]:.3e}, wake records (all blades, incl. ages / core radii / far wake) max abs diff {dw:.3e}")
+    assert worst[0] < TOL_HISTORY and worst[1] < TOL_HISTORY
+    assert dw < wake_tol
+    lib.case_gpu_hooks_free(h)
+
+
+def test_resident_two_rotor_case(ctx, oracle):
+    """nr = 2 (wing + rotor): one batched sweep per source rotor over the wake nodes of both rotors."""
+    from tests.test_oracle_case import two_body_case
+    fx = two_body_case()
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    lib, h = _resident_hooks(b, ctx)
+    a.init()
+    b.init()
+    worst = 0.0
+    for it in range(16):
+        a.step()
+        _step(b, lib, h, ctx, it + 1)
+        for ir in range(2):
+            fa, fb = a.force_nondim(ir), b.force_nondim(ir)
+            ga, gb = a.rotor(ir).vec(0), b.rotor(ir).vec(0)
+            worst = max(worst, abs(fb[0] / fa[0] - 1.0), float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+    assert lib.case_gpu_hooks_download_wake(h) == 0
+    dw = max(float(np.max(np.abs(a.rotor(ir).waN(ib) - b.rotor(ir).waN(ib)))) for ir in range(2) for ib in range(a.rotor(ir).nb))
+    print(f"wing + rotor, 16 steps resident: max rel CL/CT/gamVec err {worst:.3e}, wake max abs diff {dw:.3e}")
+    assert worst < TOL_HISTORY and dw < 1e-9
+    lib.case_gpu_hooks_free(h)

@@ -113,6 +113,22 @@ def load_library() -> C.CDLL:
         "vlc_rotor_calcAIC": (i32, [_vp, i32, _vp]),
         "vlc_rotor_solve": (i32, [_vp, i32, _vp, _vp]),
         "vlc_rotor_get_AIC_inv": (i32, [_vp, i32, _vp]),
+        "vlc_rotor_set_wake_params": (i32, [_vp, i32, i32, i32, i32, i32, i32, i32, C.c_double, C.c_double, C.c_double,
+                                            C.c_double]),
+        "vlc_rotor_set_frame": (i32, [_vp, i32, _vp, _vp]),
+        "vlc_rotor_assignshed": (i32, [_vp, i32, i32]),
+        "vlc_rotor_age_wake": (i32, [_vp, i32, C.c_double, C.c_double]),
+        "vlc_rotor_dissipate_wake": (i32, [_vp, i32, C.c_double, C.c_double]),
+        "vlc_rotor_strain_wake": (i32, [_vp, i32]),
+        "vlc_rotor_wake_to_predicted": (i32, [_vp, i32]),
+        "vlc_rotor_convectwake": (i32, [_vp, i32, C.c_double, i32]),
+        "vlc_rotor_rollup": (i32, [_vp, i32]),
+        "vlc_wake_sweep": (i32, [_vp, i32, i32]),
+        "vlc_rotor_wakevel_op": (i32, [_vp, i32, i32]),
+        "vlc_rotor_get_nwake": (i32, [_vp, i32, i32, i32, _vp]),
+        "vlc_rotor_get_fwake": (i32, [_vp, i32, i32, i32, _vp]),
+        "vlc_rotor_put_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
+        "vlc_rotor_get_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_convect_dev": (i32, [_vp, i64, _vp, _vp, C.c_double]),
         "vlc_ab2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
         "vlc_am2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
@@ -341,6 +357,67 @@ class Context:
         A = np.empty((N, N), dtype=np.float64, order="F")
         self._ck(self.lib.vlc_rotor_get_AIC_inv(self.h, ir, _ptr(A)))
         return A
+
+    # ---- tier 2b: the reference's wake mutators on the device copies (device-resident stepping) ----
+    VEL_FIRST_STEP, VEL_AB2, VEL_AM2, VEL_SHIFT_HISTORY, VEL_ORDER2 = range(5)
+
+    def rotor_set_wake_params(self, ir, nbConvect, axisymmetrySwitch, ductSwitch, suppressFwakeSwitch, rollupStart,
+                              rollupEnd, rollupSign, apparentViscCoeff, decayCoeff, initWakeVel=0.0):
+        self._ck(self.lib.vlc_rotor_set_wake_params(self.h, ir, nbConvect, axisymmetrySwitch, ductSwitch,
+                                                    suppressFwakeSwitch, rollupStart, rollupEnd, rollupSign,
+                                                    apparentViscCoeff, decayCoeff, initWakeVel))
+
+    def rotor_set_frame(self, ir, shaftAxis, hubCoords):
+        self._ck(self.lib.vlc_rotor_set_frame(self.h, ir, _ptr(_f64(shaftAxis, (3,))), _ptr(_f64(hubCoords, (3,)))))
+
+    def rotor_assignshed(self, ir, edge: str):
+        self._ck(self.lib.vlc_rotor_assignshed(self.h, ir, {"LE": 0, "TE": 1}[edge]))
+
+    def rotor_age_wake(self, ir, dt, omegaSlow):
+        self._ck(self.lib.vlc_rotor_age_wake(self.h, ir, dt, omegaSlow))
+
+    def rotor_dissipate_wake(self, ir, dt, kinematicVisc):
+        self._ck(self.lib.vlc_rotor_dissipate_wake(self.h, ir, dt, kinematicVisc))
+
+    def rotor_strain_wake(self, ir):
+        self._ck(self.lib.vlc_rotor_strain_wake(self.h, ir))
+
+    def rotor_wake_to_predicted(self, ir):
+        self._ck(self.lib.vlc_rotor_wake_to_predicted(self.h, ir))
+
+    def rotor_convectwake(self, ir, dt, wakeType: str = "C"):
+        self._ck(self.lib.vlc_rotor_convectwake(self.h, ir, dt, {"C": 0, "P": 1}[wakeType]))
+
+    def rotor_rollup(self, ir):
+        self._ck(self.lib.vlc_rotor_rollup(self.h, ir))
+
+    def wake_sweep(self, predicted=False, add_init_wake_vel=False):
+        self._ck(self.lib.vlc_wake_sweep(self.h, int(predicted), int(add_init_wake_vel)))
+
+    def rotor_wakevel_op(self, ir, op: int):
+        self._ck(self.lib.vlc_rotor_wakevel_op(self.h, ir, op))
+
+    def rotor_get_nwake(self, ir, ib, nNwake, ns, predicted=False):
+        a = np.empty((ns, nNwake, 50), dtype=np.float64)
+        self._ck(self.lib.vlc_rotor_get_nwake(self.h, ir, ib, int(predicted), _ptr(a)))
+        return a
+
+    def rotor_get_fwake(self, ir, ib, nFwake, predicted=False):
+        a = np.empty((nFwake, 13), dtype=np.float64)
+        self._ck(self.lib.vlc_rotor_get_fwake(self.h, ir, ib, int(predicted), _ptr(a)))
+        return a
+
+    def rotor_put_wakevel(self, ir, ib, which, velN=None, velF=None):
+        vn = _f64(velN) if velN is not None else None   # keep the (possibly copied) arrays alive across the call
+        vf = _f64(velF) if velF is not None else None
+        self._ck(self.lib.vlc_rotor_put_wakevel(self.h, ir, ib, which, _ptr(vn), _ptr(vf)))
+
+    def rotor_get_wakevel(self, ir, ib, which, nNwake, ns, nFwake):
+        vn = np.empty((ns + 1, nNwake, 3), dtype=np.float64)
+        vf = np.empty((nFwake, 3), dtype=np.float64)
+        self._ck(self.lib.vlc_rotor_get_wakevel(self.h, ir, ib, which, _ptr(vn) if vn.size else None,
+                                                _ptr(vf) if vf.size else None))
+        return vn, vf
 
     def gridgen(self, nx, ny, nz, xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake):
         """program gridgen (src/gridgen.f90): (gridCentre, velCentre), each (nz-1, ny-1, nx-1, 3)."""

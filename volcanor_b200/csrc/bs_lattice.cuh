@@ -62,16 +62,10 @@ __device__ __forceinline__ void edge_accumulate(const NodeQ& a, const NodeQ& b, 
   const double w = rsqrt_fp64<false>(fma(c2, c2, K));
   double sc = fma(-a2, b.u, a1 * a.u) * w;
   // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`: c2 >= 0 orders like its bit pattern, eps^2 = 2^-104 =
-  // 0x3970000000000000: one 64-bit integer compare + select, nothing extra on the FP64 pipe.  (Predicating the three
+  // 0x3970000000000000: one 64-bit integer compare + a select of sc's high word (guard_scale), nothing extra on the FP64 pipe.  (Predicating the three
   // accumulates instead is if-converted by ptxas into three selects -- measured, worse.)  NaN/Inf in sc (target on a
   // node) never reach the accumulators because those edges have c == 0 exactly and are selected away here.
-  asm("{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.gt.s64 p, %1, 0x3970000000000000;\n\t"
-      "selp.f64 %0, %0, 0d0000000000000000, p;\n\t"
-      "}"
-      : "+d"(sc)
-      : "l"(__double_as_longlong(c2)));
+  guard_scale(sc, c2);
   vx = fma(cx, sc, vx);
   vy = fma(cy, sc, vy);
   vz = fma(cz, sc, vz);

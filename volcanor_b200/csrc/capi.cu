@@ -10,6 +10,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +20,7 @@
 #include "bs_lattice.cuh"
 #include "pack.cuh"
 #include "wake_state.cuh"
+#include "wake_records.cuh"
 
 namespace {
 
@@ -71,6 +74,16 @@ struct Rotor {
   bool bound_dirty = true;
   // rows below these were not refreshed by the last put (only the active rows travel): [set][blade]
   std::vector<int> stale_near[2], stale_far[2];
+  // tier 2b (device-resident stepping): rotor_class members the wake mutators read, and the velocity arrays of the
+  // convection driver (classdef.f90:285-292): [0] vel, [1] vel1, [2] velPredicted, [3] velStep
+  int nbConvect = 0, axisym = 0, duct = 0, suppressFwake = 0, rollupStart = 1, rollupEnd = 1, sgnPositive = 1;
+  double apparentViscCoeff = 0.0, decayCoeff = 0.0, initWakeVel = 0.0;
+  double shaftAxis[3] = {0.0, 0.0, 1.0}, hubCoords[3] = {0.0, 0.0, 0.0};
+  DevBuf velN[4], velF[4];
+  DevBuf waN_alt;  // second buffer of shiftwake (swapped with waN[0])
+  DevBuf order2_tmp;
+  vlc::AxiT* d_axi = nullptr;
+  std::vector<vlc::AxiT> h_axi;
   // AIC
   int N = 0;
   DevBuf LU;
@@ -103,6 +116,7 @@ struct vlc_ctx {
   DevBuf stage_P;  // host-API staging
   DevBuf stage_V;
   DevBuf scratch;  // packing inputs for host-API set_sources
+  DevBuf ws_P, ws_V, ws_acc;  // vlc_wake_sweep: targets of every convected blade, one source rotor's result, the sum
   unsigned char* d_flag = nullptr;
   size_t flag_cap = 0;
   std::vector<Rotor> rotors;
@@ -300,7 +314,10 @@ inline size_t lat_smem_of(int W) { return (size_t)kStages * lat_tile_of(W) * lat
 inline long long pad_lat(long long n, int W) { return (n + lat_tile_of(W) - 1) / lat_tile_of(W) * lat_tile_of(W); }
 
 // (W, T) instantiations of the lattice kernel and their __launch_bounds__ minimum resident CTAs
-#define VLC_LAT_SHAPES(X) X(1, 1, 6) X(1, 2, 4) X(1, 3, 2) X(2, 1, 4) X(2, 2, 2) X(2, 3, 2) X(3, 1, 3) X(3, 2, 2) X(4, 1, 2) X(4, 2, 2)
+#ifndef VLC_LAT_MINB41
+#define VLC_LAT_MINB41 2
+#endif
+#define VLC_LAT_SHAPES(X) X(1, 1, 6) X(1, 2, 4) X(1, 3, 2) X(2, 1, 4) X(2, 2, 2) X(2, 3, 2) X(3, 1, 3) X(3, 2, 2) X(4, 1, VLC_LAT_MINB41) X(4, 2, 2)
 
 int query_occ_lat_all(vlc_ctx* c) {
 #define X(WW, TT, MB)                                                                                           \
@@ -734,6 +751,9 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   release(c->stage_P);
   release(c->stage_V);
   release(c->scratch);
+  release(c->ws_P);
+  release(c->ws_V);
+  release(c->ws_acc);
   release(c->solver_work);
   if (c->d_flag) cudaFree(c->d_flag);
   for (auto& r : c->rotors) {
@@ -747,6 +767,13 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
       release(r.comb[s].rem);
       if (r.comb[s].d_unmergeable) cudaFree(r.comb[s].d_unmergeable);
     }
+    for (int k = 0; k < 4; ++k) {
+      release(r.velN[k]);
+      release(r.velF[k]);
+    }
+    release(r.waN_alt);
+    release(r.order2_tmp);
+    if (r.d_axi) cudaFree(r.d_axi);
     release(r.bound.rec);
     release(r.LU);
     if (r.d_ipiv) cudaFree(r.d_ipiv);
@@ -944,8 +971,15 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     r.stale_near[s2].assign(nb, 1);  // zero-filled below = gam 0 everywhere, like rotor_init (:3835-3836)
     r.stale_far[s2].assign(nb, 1);
   }
+  r.nbConvect = nb;
   int rc = bind_device(c);
   if (rc) return rc;
+  for (int k = 0; k < 4; ++k) {  // velNwake etc. start at zero like rotor_init (classdef.f90:3795-3812)
+    if ((rc = reserve(c, r.velN[k], (size_t)3 * nNwake * (ns + 1) * nb + 1))) return rc;
+    if ((rc = reserve(c, r.velF[k], (size_t)3 * nFwake * nb + 1))) return rc;
+    CUDA_OK(c, cudaMemsetAsync(r.velN[k].p, 0, r.velN[k].cap * sizeof(double), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(r.velF[k].p, 0, r.velF[k].cap * sizeof(double), c->stream));
+  }
   // zero-initialised device copies so that never-uploaded rows hold gam = 0 like rotor_init (:3835-3836)
   if ((rc = reserve(c, r.wiP, (size_t)nb * nc * ns * vlc::kWp))) return rc;
   CUDA_OK(c, cudaMemsetAsync(r.wiP.p, 0, r.wiP.cap * sizeof(double), c->stream));
@@ -1233,6 +1267,422 @@ extern "C" int vlc_rotor_get_AIC_inv(vlc_ctx* c, int ir, double* AIC_inv) {
       (c)->launches++;                                                                 \
     }                                                                                  \
   } while (0)
+
+// ============================================================================ tier 2b: device-resident stepping
+
+namespace {
+
+// getTransformAxis (libMath.f90:695-726): rotation by theta about axisVec, column-major 3x3
+void transform_axis(double theta, const double axisVec[3], double T[9]) {
+  const double n = std::sqrt(axisVec[0] * axisVec[0] + axisVec[1] * axisVec[1] + axisVec[2] * axisVec[2]);
+  const double ax[3] = {axisVec[0] / n, axisVec[1] / n, axisVec[2] / n};
+  const double ct = std::cos(theta), st = std::sin(theta), omct = 1.0 - ct;
+  T[0] = ct + ax[0] * ax[0] * omct;
+  T[1] = ax[2] * st + ax[1] * ax[0] * omct;
+  T[2] = -ax[1] * st + ax[2] * ax[0] * omct;
+  T[3] = -ax[2] * st + ax[0] * ax[1] * omct;
+  T[4] = ct + ax[1] * ax[1] * omct;
+  T[5] = ax[0] * st + ax[2] * ax[1] * omct;
+  T[6] = ax[1] * st + ax[0] * ax[2] * omct;
+  T[7] = -ax[0] * st + ax[1] * ax[2] * omct;
+  T[8] = ct + ax[2] * ax[2] * omct;
+}
+
+inline long long wake_targets_of(const Rotor& r) {  // targets of one rotor's convected blades in a wake sweep
+  if (r.nNwake <= 0) return 0;
+  const long long nact = r.nNwake - r.rowNear + 1 > 0 ? r.nNwake - r.rowNear + 1 : 0;
+  const long long nfar = r.nFwake - r.rowFar + 1 > 0 ? r.nFwake - r.rowFar + 1 : 0;
+  return (nact * (r.ns + 1) + nfar) * r.nbConvect;
+}
+
+}  // namespace
+
+extern "C" int vlc_rotor_set_wake_params(vlc_ctx* c, int ir, int nbConvect, int axisymmetrySwitch, int ductSwitch,
+                                         int suppressFwakeSwitch, int rollupStart, int rollupEnd, double rollupSign,
+                                         double apparentViscCoeff, double decayCoeff, double initWakeVel) {
+  CHECK_CTX(c);
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (nbConvect < 1 || nbConvect > r->nb) return fail(c, VLC_ERR_ARG, "nbConvect out of range");
+  if (r->nNwake > 0 && (rollupStart < 1 || rollupEnd > r->ns)) return fail(c, VLC_ERR_ARG, "rollupStart / rollupEnd out of range");
+  r->nbConvect = nbConvect;
+  r->axisym = axisymmetrySwitch;
+  r->duct = ductSwitch;
+  r->suppressFwake = suppressFwakeSwitch;
+  r->rollupStart = rollupStart;
+  r->rollupEnd = rollupEnd;
+  r->sgnPositive = std::copysign(1.0, rollupSign) > 2.220446049250313e-16 ? 1 : 0;  // classdef.f90:4541
+  r->apparentViscCoeff = apparentViscCoeff;
+  r->decayCoeff = decayCoeff;
+  r->initWakeVel = initWakeVel;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_set_frame(vlc_ctx* c, int ir, const double* shaftAxis, const double* hubCoords) {
+  CHECK_CTX(c);
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (!shaftAxis || !hubCoords) return fail(c, VLC_ERR_ARG, "null pointer");
+  for (int k = 0; k < 3; ++k) {
+    r->shaftAxis[k] = shaftAxis[k];
+    r->hubCoords[k] = hubCoords[k];
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_assignshed(vlc_ctx* c, int ir, int edge) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (edge != 0 && edge != 1) return fail(c, VLC_ERR_ARG, "edge: 0 = 'LE', 1 = 'TE' (classdef.f90:4303, :4313)");
+  if (r->nNwake <= 0) return VLC_OK;
+  if (r->rowNear < 1 || r->rowNear > r->nNwake) return fail(c, VLC_ERR_STATE, "assignshed: rowNear outside 1..nNwake");
+  const int n = r->nb * r->ns;
+  vlc::rec_assignshed_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(edge, r->nb, r->nc, r->ns, r->nNwake, r->rowNear,
+                                                                        r->wiP.p, r->waN[0].p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  r->dirty[0] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_age_wake(vlc_ctx* c, int ir, double dt, double omegaSlow) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (r->nNwake <= 0) return VLC_OK;
+  const long long nact = std::max(0, r->nNwake - r->rowNear + 1), nfar = std::max(0, r->nFwake - r->rowFar + 1);
+  const long long n = (long long)r->nb * (r->ns * nact + nfar);
+  if (n <= 0) return VLC_OK;
+  vlc::rec_age_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nb, r->ns, r->nNwake, r->nFwake, r->rowNear, r->rowFar, dt,
+                                                                 dt * omegaSlow, r->waN[0].p, r->waF[0].p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  return VLC_OK;  // ages are not read by any sweep: the packed sets stay valid
+}
+
+extern "C" int vlc_rotor_dissipate_wake(vlc_ctx* c, int ir, double dt, double kinematicVisc) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (r->nNwake <= 0) return VLC_OK;
+  const double oseenParameter = 1.2564;  // classdef.f90:4361
+  const double growTerm = 4.0 * oseenParameter * r->apparentViscCoeff * kinematicVisc * dt;
+  const double decayFactor = std::exp(-r->decayCoeff * dt);
+  const long long nact = std::max(0, r->nNwake - r->rowNear + 1), nfar = std::max(0, r->nFwake - r->rowFar + 1);
+  const long long n = (long long)r->nb * (r->ns * nact + nfar);
+  if (n <= 0) return VLC_OK;
+  vlc::rec_dissipate_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nb, r->ns, r->nNwake, r->nFwake, r->rowNear, r->rowFar,
+                                                                       growTerm, decayFactor, r->waN[0].p, r->waF[0].p);
+  c->launches++;
+  const long long n4 = (long long)r->nb * r->ns * (nact - 1);
+  if (n4 > 0) {
+    vlc::rec_dissipate_vf4_kernel<<<blocks_for(n4, 256), 256, 0, c->stream>>>(r->nb, r->ns, r->nNwake, r->rowNear, r->waN[0].p);
+    c->launches++;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  r->dirty[0] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_strain_wake(vlc_ctx* c, int ir) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const int nfar = r->nFwake - r->rowFar + 1;
+  if (r->nNwake <= 0 || nfar <= 0) return VLC_OK;
+  vlc::rec_strain_kernel<<<blocks_for(r->nb * nfar, 128), 128, 0, c->stream>>>(r->nb, r->nFwake, r->rowFar, r->waF[0].p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  r->dirty[0] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_wake_to_predicted(vlc_ctx* c, int ir) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (r->nNwake <= 0) return VLC_OK;
+  const int firstN = r->rowNear - 1, nactN = r->nNwake - firstN, firstF = r->rowFar - 1, nactF = r->nFwake - firstF;
+  if (nactN > 0) {  // columns of all convected blades are contiguous: one strided copy
+    const size_t pitch = (size_t)r->nNwake * vlc::kVr * sizeof(double);
+    CUDA_OK(c, cudaMemcpy2DAsync(r->waN[1].p + (size_t)firstN * vlc::kVr, pitch, r->waN[0].p + (size_t)firstN * vlc::kVr, pitch,
+                                 (size_t)nactN * vlc::kVr * sizeof(double), (size_t)r->ns * r->nbConvect,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (nactF > 0) {
+    const size_t pitch = (size_t)r->nFwake * vlc::kFw * sizeof(double);
+    CUDA_OK(c, cudaMemcpy2DAsync(r->waF[1].p + (size_t)firstF * vlc::kFw, pitch, r->waF[0].p + (size_t)firstF * vlc::kFw, pitch,
+                                 (size_t)nactF * vlc::kFw * sizeof(double), (size_t)r->nbConvect, cudaMemcpyDeviceToDevice,
+                                 c->stream));
+  }
+  for (int ib = 0; ib < r->nbConvect; ++ib) {
+    r->stale_near[1][ib] = std::min(r->stale_near[1][ib], std::max(r->rowNear, r->stale_near[0][ib]));
+    r->stale_far[1][ib] = std::min(r->stale_far[1][ib], std::max(r->rowFar, r->stale_far[0][ib]));
+  }
+  r->dirty[1] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicted) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (r->nNwake <= 0) return VLC_OK;
+  const int s = predicted ? 1 : 0;
+  const long long nfar = std::max(0, r->nFwake - r->rowFar + 1), nact = std::max(0, r->nNwake - r->rowNear + 1);
+  {
+    const long long n = (long long)r->nbConvect * ((long long)(r->ns + 1) * r->nNwake + nfar);
+    vlc::rec_convect_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(s, r->nbConvect, r->ns, r->nNwake, r->nFwake, r->rowNear,
+                                                                       r->rowFar, dt, r->velN[0].p, r->velF[0].p, r->waN[s].p,
+                                                                       r->waF[s].p);
+    c->launches++;
+  }
+  {
+    const long long n = (long long)r->nbConvect * (r->ns * nact + std::max(0LL, nfar - 1));
+    if (n > 0) {
+      vlc::rec_continuity_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(0, r->nbConvect, r->ns, r->nNwake, r->nFwake,
+                                                                            r->rowNear, r->rowFar, r->waN[s].p, r->waF[s].p);
+      c->launches++;
+      if (!predicted && r->duct == 1) {  // classdef.f90:1645-1656: only in the 'C' branch
+        vlc::rec_continuity_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(1, r->nbConvect, r->ns, r->nNwake, r->nFwake,
+                                                                              r->rowNear, r->rowFar, r->waN[s].p, r->waF[s].p);
+        c->launches++;
+      }
+    }
+  }
+  if (r->axisym == 1 && r->nb > 1) {  // classdef.f90:4801-4823
+    const double twoPi = 2.0 * (std::atan(1.0) * 4.0);
+    r->h_axi.resize(r->nb);
+    for (int ib = 2; ib <= r->nb; ++ib) {
+      const double bladeOffset = twoPi / r->nb * (ib - 1);
+      vlc::AxiT& t = r->h_axi[ib - 1];
+      t.rotate = std::fabs(bladeOffset) > 2.220446049250313e-16 ? 1 : 0;  // classdef.f90:1297
+      transform_axis(bladeOffset, r->shaftAxis, t.T);
+    }
+    if (!r->d_axi) CUDA_OK(c, cudaMalloc(&r->d_axi, sizeof(vlc::AxiT) * r->nb));
+    CUDA_OK(c, cudaMemcpyAsync(r->d_axi, r->h_axi.data(), sizeof(vlc::AxiT) * r->nb, cudaMemcpyHostToDevice, c->stream));
+    const long long n = (long long)(r->nb - 1) * (r->ns * nact + nfar);
+    if (n > 0) {
+      vlc::rec_axisym_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(r->nb, r->ns, r->nNwake, r->nFwake, r->rowNear, r->rowFar,
+                                                                        r->d_axi, r->hubCoords[0], r->hubCoords[1],
+                                                                        r->hubCoords[2], r->waN[s].p, r->waF[s].p);
+      c->launches++;
+    }
+  }
+  CUDA_OK(c, cudaGetLastError());
+  r->dirty[s] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_rollup(vlc_ctx* c, int ir) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (r->nNwake <= 0) return VLC_OK;
+  int rowFarNext = r->rowFar - 1;  // classdef.f90:4527
+  if (r->nFwake > 0 && rowFarNext == 0) {  // :4570-4573 (shiftFwake moves every blade, once)
+    vlc::rec_shiftFwake_kernel<<<blocks_for(r->nb * vlc::kFw, 64), 64, 0, c->stream>>>(r->nb, r->nFwake, r->waF[0].p);
+    c->launches++;
+    rowFarNext = 1;
+  }
+  vlc::rec_rollup_kernel<<<blocks_for(r->nb, 32), 32, 0, c->stream>>>(r->nb, r->ns, r->nNwake, r->nFwake, r->rollupStart,
+                                                                      r->rollupEnd, r->sgnPositive, r->suppressFwake, rowFarNext,
+                                                                      r->waN[0].p, r->waF[0].p);
+  c->launches++;
+  // shiftwake (:4603 -> :4481-4498) into the second buffer, then swap
+  const size_t total = (size_t)r->nb * r->nNwake * r->ns * vlc::kVr;
+  if ((rc = reserve(c, r->waN_alt, total + 1))) return rc;  // by the logical size: capacities differ after a swap
+  vlc::rec_shiftwake_kernel<<<blocks_for((long long)total, 256), 256, 0, c->stream>>>((long long)r->nb * r->ns, r->nNwake,
+                                                                                     r->waN[0].p, r->waN_alt.p);
+  c->launches++;
+  CUDA_OK(c, cudaGetLastError());
+  std::swap(r->waN[0], r->waN_alt);
+  r->dirty[0] = true;
+  return VLC_OK;
+}
+
+// main.f90:800-838 ('C') / :1057-1081, :889-911 ('P'): for every rotor ir and convected blade, velNwake(:, rowNear:nNwake, :)
+// and velFwake(:, rowFar:nFwake) <- sum over source rotors jr = 1..nr of vind_on{N,F}wake_byRotor(rotor(jr), ...) (+- the
+// initial wake velocity while iter < initWakeVelNt).  All targets of all rotors go through ONE sweep per source rotor
+// (the reference's per-(ir, ib, jr) calls evaluate the same sums target by target); nothing leaves the device.
+extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  const int s = predicted ? 1 : 0;
+  long long M = 0;
+  for (auto& r : c->rotors)
+    if (r.defined) M += wake_targets_of(r);
+  if (M <= 0) return VLC_OK;
+  if ((rc = reserve(c, c->ws_P, 3 * (size_t)M))) return rc;
+  if ((rc = reserve(c, c->ws_V, 3 * (size_t)M))) return rc;
+  if ((rc = reserve(c, c->ws_acc, 3 * (size_t)M))) return rc;
+  long long off = 0;
+  for (auto& r : c->rotors) {
+    const long long m = r.defined ? wake_targets_of(r) : 0;
+    if (m <= 0) continue;
+    vlc::rec_targets_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(r.nbConvect, r.ns, r.nNwake, r.nFwake, r.rowNear, r.rowFar,
+                                                                       r.waN[s].p, r.waF[s].p, c->ws_P.p + 3 * off);
+    c->launches++;
+    off += m;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  bool first = true;
+  for (auto& src : c->rotors) {  // jr = 1..nr in order (main.f90:817)
+    if (!src.defined) continue;
+    if ((rc = pack_rotor(c, src, s))) return rc;
+    const SourceSet& v = src.comb[s];
+    if (v.n_pad <= 0) continue;
+    rc = (v.has_shared && c->shared_nodes) ? sweep_shared(c, v, M, c->ws_P.p, c->ws_V.p)
+                                           : sweep(c, v.rec.p, v.n_pad, M, c->ws_P.p, c->ws_V.p);
+    if (rc) return rc;
+    vlc::rec_accumulate_kernel<<<blocks_for(3 * M, 256), 256, 0, c->stream>>>(3 * M, first ? 1 : 0, c->ws_V.p, c->ws_acc.p);
+    c->launches++;
+    first = false;
+  }
+  if (first) CUDA_OK(c, cudaMemsetAsync(c->ws_acc.p, 0, sizeof(double) * 3 * (size_t)M, c->stream));
+  off = 0;
+  for (auto& r : c->rotors) {
+    const long long m = r.defined ? wake_targets_of(r) : 0;
+    if (m <= 0) continue;
+    const double w[3] = {r.initWakeVel * r.shaftAxis[0], r.initWakeVel * r.shaftAxis[1], r.initWakeVel * r.shaftAxis[2]};
+    vlc::rec_scatter_vel_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(
+        r.nbConvect, r.ns, r.nNwake, r.nFwake, r.rowNear, r.rowFar, s, addInitWakeVel ? 1 : 0, w[0], w[1], w[2],
+        c->ws_acc.p + 3 * off, r.velN[s ? 2 : 0].p, r.velF[s ? 2 : 0].p);
+    c->launches++;
+    off += m;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_wakevel_op(vlc_ctx* c, int ir, int op) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (r->nNwake <= 0) return VLC_OK;
+  const size_t nn = (size_t)3 * r->nNwake * (r->ns + 1) * r->nbConvect, nf = (size_t)3 * r->nFwake * r->nbConvect;
+  auto copy = [&](DevBuf& dst, const DevBuf& src, size_t n) -> int {
+    if (n == 0) return VLC_OK;
+    CUDA_OK(c, cudaMemcpyAsync(dst.p, src.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return VLC_OK;
+  };
+  switch (op) {
+    case VLC_VEL_FIRST_STEP:  // main.f90:1013-1020: vel1 = vel
+      if ((rc = copy(r->velN[1], r->velN[0], nn)) || (rc = copy(r->velF[1], r->velF[0], nf))) return rc;
+      break;
+    case VLC_VEL_AB2:  // main.f90:1031-1041: velStep = vel; vel = 0.5*(3*vel - vel1), whole arrays
+      if ((rc = copy(r->velN[3], r->velN[0], nn)) || (rc = copy(r->velF[3], r->velF[0], nf))) return rc;
+      LAUNCH1D(c, vlc::ab2_kernel, (long long)nn, (long long)nn, r->velN[3].p, r->velN[1].p, r->velN[0].p);
+      LAUNCH1D(c, vlc::ab2_kernel, (long long)nf, (long long)nf, r->velF[3].p, r->velF[1].p, r->velF[0].p);
+      break;
+    case VLC_VEL_AM2:  // main.f90:1094-1099: vel = (velPredicted + velStep)*0.5
+      LAUNCH1D(c, vlc::am2_kernel, (long long)nn, (long long)nn, r->velN[2].p, r->velN[3].p, r->velN[0].p);
+      LAUNCH1D(c, vlc::am2_kernel, (long long)nf, (long long)nf, r->velF[2].p, r->velF[3].p, r->velF[0].p);
+      break;
+    case VLC_VEL_SHIFT_HISTORY:  // main.f90:1103-1107: vel1 = velStep
+      if ((rc = copy(r->velN[1], r->velN[3], nn)) || (rc = copy(r->velF[1], r->velF[3], nf))) return rc;
+      break;
+    case VLC_VEL_ORDER2: {  // main.f90:927-940: vel(active) = vel_order2(vel(active), velPredicted(active))
+      const int rowsN = r->nNwake - r->rowNear + 1, rowsF = r->nFwake - r->rowFar + 1;
+      if ((rc = reserve(c, r->order2_tmp, std::max(nn, nf) + 1))) return rc;
+      if (rowsN > 0) {
+        const long long n = 3LL * rowsN * (r->ns + 1) * r->nbConvect;
+        vlc::rec_vel_order2_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nbConvect, r->nNwake, r->ns + 1, r->rowNear, rowsN,
+                                                                              r->velN[0].p, r->velN[2].p, r->order2_tmp.p);
+        vlc::rec_copy_slice_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nbConvect, r->nNwake, r->ns + 1, r->rowNear, rowsN,
+                                                                              r->order2_tmp.p, r->velN[0].p);
+        c->launches += 2;
+      }
+      if (rowsF > 0) {
+        const long long n = 3LL * rowsF * r->nbConvect;
+        vlc::rec_vel_order2_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nbConvect, r->nFwake, 1, r->rowFar, rowsF,
+                                                                              r->velF[0].p, r->velF[2].p, r->order2_tmp.p);
+        vlc::rec_copy_slice_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nbConvect, r->nFwake, 1, r->rowFar, rowsF,
+                                                                              r->order2_tmp.p, r->velF[0].p);
+        c->launches += 2;
+      }
+      CUDA_OK(c, cudaGetLastError());
+    } break;
+    default: return fail(c, VLC_ERR_ARG, "unknown velocity operation");
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_nwake(vlc_ctx* c, int ir, int ib, int predicted, double* waN) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !waN) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const size_t per = (size_t)r->nNwake * r->ns * vlc::kVr;
+  if (per == 0) return VLC_OK;
+  CUDA_OK(c, cudaMemcpyAsync(waN, r->waN[predicted ? 1 : 0].p + per * ib, per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_fwake(vlc_ctx* c, int ir, int ib, int predicted, double* waF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb) return fail(c, VLC_ERR_ARG, "bad blade index");
+  const size_t per = (size_t)r->nFwake * vlc::kFw;
+  if (per == 0) return VLC_OK;
+  if (!waF) return fail(c, VLC_ERR_ARG, "null pointer");
+  CUDA_OK(c, cudaMemcpyAsync(waF, r->waF[predicted ? 1 : 0].p + per * ib, per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_put_wakevel(vlc_ctx* c, int ir, int ib, int which, const double* velN, const double* velF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || which < 0 || which > 3) return fail(c, VLC_ERR_ARG, "bad blade index / array selector");
+  const size_t pn = (size_t)3 * r->nNwake * (r->ns + 1), pf = (size_t)3 * r->nFwake;
+  if (velN && pn) CUDA_OK(c, cudaMemcpyAsync(r->velN[which].p + pn * ib, velN, pn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (velF && pf) CUDA_OK(c, cudaMemcpyAsync(r->velF[which].p + pf * ib, velF, pf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_wakevel(vlc_ctx* c, int ir, int ib, int which, double* velN, double* velF) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || which < 0 || which > 3) return fail(c, VLC_ERR_ARG, "bad blade index / array selector");
+  const size_t pn = (size_t)3 * r->nNwake * (r->ns + 1), pf = (size_t)3 * r->nFwake;
+  if (velN && pn) CUDA_OK(c, cudaMemcpyAsync(velN, r->velN[which].p + pn * ib, pn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (velF && pf) CUDA_OK(c, cudaMemcpyAsync(velF, r->velF[which].p + pf * ib, pf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
 
 extern "C" int vlc_convect_dev(vlc_ctx* c, int64_t n, double* x, const double* v, double dt) {
   CHECK_CTX(c);

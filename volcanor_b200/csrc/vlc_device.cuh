@@ -50,6 +50,38 @@ __device__ __forceinline__ double rsqrt_fp64(double x) {
   return fma(p, q, y);
 }
 
+// sc <- (c2 > eps^2) ? sc : 0 without touching the FP64 pipe.  VLC_GUARD_HI (default): only the HIGH word of sc is
+// selected (one SEL instead of two): a guarded sc becomes {lo, 0} = a denormal < 2^-1042 (whatever sc was, NaN and
+// Inf included), and every |c_i| <= 2^-52 there (c2 <= 2^-104), so |c_i * sc| < 2^-1094 rounds to zero in the three
+// accumulates that consume it: the same velocities (up to the sign of an exact zero), one issue slot fewer.
+// (Predicating the seed instruction instead -- `@p rsqrt.approx` into a zeroed pair -- is if-converted by ptxas into
+// MUFU + FSEL + MOV: no gain, tried.)
+#ifndef VLC_GUARD_HI
+#define VLC_GUARD_HI 1  // 0 = select both words (r01e and earlier)
+#endif
+__device__ __forceinline__ void guard_scale(double& sc, double c2) {
+#if VLC_GUARD_HI
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 lo, hi;\n\t"
+      "setp.gt.s64 p, %1, 0x3970000000000000;\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "selp.b32 hi, hi, 0, p;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t"
+      "}"
+      : "+d"(sc)
+      : "l"(__double_as_longlong(c2)));
+#else
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.gt.s64 p, %1, 0x3970000000000000;\n\t"
+      "selp.f64 %0, %0, 0d0000000000000000, p;\n\t"
+      "}"
+      : "+d"(sc)
+      : "l"(__double_as_longlong(c2)));
+#endif
+}
+
 struct Src {
   // r0g = G*(p2 - p1), L2g = G*|p2 - p1|^2 with G = gam/(4 pi): the strength is folded into the two
   // per-source quantities that enter the result linearly, which saves one FP64 multiply per pair.
@@ -89,13 +121,7 @@ __device__ __forceinline__ void pair_accumulate(const Src& s, double px, double 
   // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`: c2 >= 0, so its bit pattern orders like an integer;
   // eps^2 = 2^-104 = 0x3970000000000000.  One 64-bit integer compare + one select keep the guard off
   // the FP64 pipe (each FP64 instruction costs two issue cycles, an integer one costs one).
-  asm("{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.gt.s64 p, %1, 0x3970000000000000;\n\t"
-      "selp.f64 %0, %0, 0d0000000000000000, p;\n\t"
-      "}"
-      : "+d"(sc)
-      : "l"(__double_as_longlong(c2)));
+  guard_scale(sc, c2);
   vx = fma(cx, sc, vx);
   vy = fma(cy, sc, vy);
   vz = fma(cz, sc, vz);
