@@ -10,6 +10,12 @@
 //   vind_onFwake_byRotor(rotor, Fwake [, 'P'])  libCommon.f90:173  ->  vind_onFwake_byRotor(rotor, Fwake, rows, out, predicted)
 //   rotor%calcAIC()                 classdef.f90:4151    ->   rotor.calcAIC(AIC_out)
 //   matmulAX(AIC_inv, RHS)          libMath.f90:105      ->   rotor.solve(RHS, gamVec)
+//   rotor%assignshed('LE'|'TE')     classdef.f90:4297    ->   rotor.assignshed("LE")          (device copies, tier 2b)
+//   rotor%age_wake(dt)              classdef.f90:4331    ->   rotor.age_wake(dt, omegaSlow)
+//   rotor%dissipate_wake(dt, nu)    classdef.f90:4356    ->   rotor.dissipate_wake(dt, nu)
+//   rotor%strain_wake()             classdef.f90:4410    ->   rotor.strain_wake()
+//   rotor%convectwake(iter, dt, c)  classdef.f90:4786    ->   rotor.convectwake(dt, 'C' | 'P')
+//   rotor%rollup()                  classdef.f90:4515    ->   rotor.rollup()
 //
 // Errors: the reference aborts with `error stop '<msg>'`; here every failed call throws vlc::Error carrying the
 // library's message (there is no CPU fallback to catch it with).  Arrays are column-major (3, m) doubles exactly as
@@ -50,6 +56,8 @@ class Context {
     check(vlc_set_sources(h_, set, n, p1, p2, rvc, gam, wake_flag));
   }
   void vind(int set, std::int64_t m, const double* P, double* V) { check(vlc_vind(h_, set, m, P, V)); }
+  // the wake sweeps of the convection driver for all rotors at once (main.f90:800-838, :889-911), on device copies
+  void wake_sweep(bool predicted, bool addInitWakeVel = false) { check(vlc_wake_sweep(h_, predicted, addInitWakeVel)); }
   // program gridgen (src/gridgen.f90)
   void gridgen(int nx, int ny, int nz, const double* xyzMin, const double* xyzMax, const double* vel,
                std::int64_t nVrWing, const double* vrWing, std::int64_t nVrNwake, const double* vrNwake,
@@ -98,6 +106,31 @@ class Rotor {
   void calcAIC(double* AIC_out = nullptr) { c_.check(vlc_rotor_calcAIC(c_.handle(), ir_, AIC_out)); }
   void solve(const double* RHS, double* gamVec) { c_.check(vlc_rotor_solve(c_.handle(), ir_, RHS, gamVec)); }
   void get_AIC_inv(double* AIC_inv) { c_.check(vlc_rotor_get_AIC_inv(c_.handle(), ir_, AIC_inv)); }
+  // tier 2b: the reference's wake mutators on the library's device copies (device-resident time stepping)
+  void set_wake_params(int nbConvect, int axisymmetrySwitch, int ductSwitch, int suppressFwakeSwitch, int rollupStart,
+                       int rollupEnd, double rollupSign, double apparentViscCoeff, double decayCoeff, double initWakeVel) {
+    c_.check(vlc_rotor_set_wake_params(c_.handle(), ir_, nbConvect, axisymmetrySwitch, ductSwitch, suppressFwakeSwitch,
+                                       rollupStart, rollupEnd, rollupSign, apparentViscCoeff, decayCoeff, initWakeVel));
+  }
+  void set_frame(const double* shaftAxis, const double* hubCoords) {
+    c_.check(vlc_rotor_set_frame(c_.handle(), ir_, shaftAxis, hubCoords));
+  }
+  void assignshed(const std::string& edge) {
+    if (edge != "LE" && edge != "TE") throw Error(VLC_ERR_ARG, "ERROR: Wrong option for edge");  // classdef.f90:4322
+    c_.check(vlc_rotor_assignshed(c_.handle(), ir_, edge == "LE" ? 0 : 1));
+  }
+  void age_wake(double dt, double omegaSlow) { c_.check(vlc_rotor_age_wake(c_.handle(), ir_, dt, omegaSlow)); }
+  void dissipate_wake(double dt, double kinematicVisc) { c_.check(vlc_rotor_dissipate_wake(c_.handle(), ir_, dt, kinematicVisc)); }
+  void strain_wake() { c_.check(vlc_rotor_strain_wake(c_.handle(), ir_)); }
+  void wake_to_predicted() { c_.check(vlc_rotor_wake_to_predicted(c_.handle(), ir_)); }
+  void convectwake(double dt, char wakeType) {
+    if (wakeType != 'C' && wakeType != 'P') throw Error(VLC_ERR_ARG, "ERROR: Wrong character flag for convectwake()");
+    c_.check(vlc_rotor_convectwake(c_.handle(), ir_, dt, wakeType == 'P'));
+  }
+  void rollup() { c_.check(vlc_rotor_rollup(c_.handle(), ir_)); }
+  void wakevel_op(int op) { c_.check(vlc_rotor_wakevel_op(c_.handle(), ir_, op)); }
+  void get_nwake(int ib, double* waN, bool predicted = false) { c_.check(vlc_rotor_get_nwake(c_.handle(), ir_, ib, predicted, waN)); }
+  void get_fwake(int ib, double* waF, bool predicted = false) { c_.check(vlc_rotor_get_fwake(c_.handle(), ir_, ib, predicted, waF)); }
   Context& context() const { return c_; }
   int index() const { return ir_; }
 

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("case_dir")
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--resident", action="store_true", help="with --gpu: keep the wake on the device (C ABI tier 2b)")
     ap.add_argument("--nt", type=int, default=0, help="stop after this many steps (default: the case's nt)")
     ap.add_argument("--out", default=None, help="results directory (default: <case_dir>/Results)")
     args = ap.parse_args()
@@ -30,8 +31,9 @@ def main():
     if args.gpu:
         import volcanor_b200 as vb
         from tests.test_gpu_case import _native_hooks
+        from tests.test_gpu_resident import _resident_hooks
         ctx = vb.Context(0)
-        _native_hooks(c, ctx)
+        (_resident_hooks if args.resident else _native_hooks)(c, ctx)
     out = Path(args.out) if args.out else Path(args.case_dir) / "Results"
     out.mkdir(parents=True, exist_ok=True)
     t0 = time.perf_counter()

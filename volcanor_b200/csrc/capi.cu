@@ -147,15 +147,19 @@ int bind_device(vlc_ctx* c) {
   return VLC_OK;
 }
 
+// Grow-only device buffer.  A first allocation takes what is asked (+1/8); a RE-allocation at least doubles, because
+// cudaFree + cudaMalloc in the middle of a run is expensive and erratic (measured on the B200 box: 5 ms .. 2 s per
+// event, profiles/r01h_resident_cases.md) -- a wake that grows by one row per time step must not pay it every few steps.
 int reserve(vlc_ctx* c, DevBuf& b, size_t doubles) {
   if (doubles <= b.cap) return VLC_OK;
+  size_t want = doubles + doubles / 8 + 1024;
   if (b.p) {
+    want = std::max(want, 2 * b.cap);
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     CUDA_OK(c, cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;
   }
-  size_t want = doubles + doubles / 8 + 1024;
   CUDA_OK(c, cudaMalloc(&b.p, want * sizeof(double)));
   b.cap = want;
   return VLC_OK;
@@ -317,7 +321,10 @@ inline long long pad_lat(long long n, int W) { return (n + lat_tile_of(W) - 1) /
 #ifndef VLC_LAT_MINB41
 #define VLC_LAT_MINB41 2
 #endif
-#define VLC_LAT_SHAPES(X) X(1, 1, 6) X(1, 2, 4) X(1, 3, 2) X(2, 1, 4) X(2, 2, 2) X(2, 3, 2) X(3, 1, 3) X(3, 2, 2) X(4, 1, VLC_LAT_MINB41) X(4, 2, 2)
+#ifndef VLC_LAT_MINB42
+#define VLC_LAT_MINB42 2
+#endif
+#define VLC_LAT_SHAPES(X) X(1, 1, 6) X(1, 2, 4) X(1, 3, 2) X(2, 1, 4) X(2, 2, 2) X(2, 3, 2) X(3, 1, 3) X(3, 2, 2) X(4, 1, VLC_LAT_MINB41) X(4, 2, VLC_LAT_MINB42)
 
 int query_occ_lat_all(vlc_ctx* c) {
 #define X(WW, TT, MB)                                                                                           \
@@ -727,6 +734,9 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
   rc |= query_occ<3, 3>(c, &c->occ[3]);
   rc |= query_occ<4, 3>(c, &c->occ[4]);
   rc |= query_occ_lat_all(c);
+  // Source-split partials: the planners aim at >= 8 waves of CTAs, which makes splits x targets ~ constant (tens of MB)
+  // until the targets alone fill the machine; 128 MB up front covers every case-sized sweep without a re-allocation.
+  if (!rc) rc = reserve(c, c->part, (size_t)16 << 20);
   if (rc) {
     g_create_error = "sweep kernel not loadable on this device: " + c->err;
     cudaStreamDestroy(c->own_stream);
@@ -980,9 +990,23 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     CUDA_OK(c, cudaMemsetAsync(r.velN[k].p, 0, r.velN[k].cap * sizeof(double), c->stream));
     CUDA_OK(c, cudaMemsetAsync(r.velF[k].p, 0, r.velF[k].cap * sizeof(double), c->stream));
   }
+  {  // packed sets at their final size (all nNwake / nFwake rows active): no allocation while the wake grows
+    const long long wing_pad = pad_tile(4LL * nc * ns * nb);
+    const long long wake_n = (4LL * nNwake * ns + ns + nFwake + VLC_NPFWAKE) * nb;
+    const long long rem_n = ((long long)nNwake + ns + nFwake + VLC_NPFWAKE) * nb;
+    size_t lat_doubles = 0;
+    for (int W = 1; W <= 4; ++W)
+      lat_doubles = std::max(lat_doubles, (size_t)pad_lat((long long)nb * ((ns + W - 1) / W) * (nNwake + 1), W) * lat_rd_of(W));
+    for (int s = 0; s < 2 && nNwake > 0; ++s) {
+      if ((rc = reserve(c, r.comb[s].rec, (size_t)(wing_pad + pad_tile(wake_n)) * vlc::kSrcDoubles))) return rc;
+      if ((rc = reserve(c, r.comb[s].lat, lat_doubles))) return rc;
+      if ((rc = reserve(c, r.comb[s].rem, (size_t)(wing_pad + pad_tile(rem_n)) * vlc::kSrcDoubles))) return rc;
+    }
+  }
   // zero-initialised device copies so that never-uploaded rows hold gam = 0 like rotor_init (:3835-3836)
   if ((rc = reserve(c, r.wiP, (size_t)nb * nc * ns * vlc::kWp))) return rc;
   CUDA_OK(c, cudaMemsetAsync(r.wiP.p, 0, r.wiP.cap * sizeof(double), c->stream));
+  if ((rc = reserve(c, r.waN_alt, (size_t)nb * nNwake * ns * vlc::kVr + 1))) return rc;  // shiftwake's second buffer
   for (int s = 0; s < 2; ++s) {
     if ((rc = reserve(c, r.waN[s], (size_t)nb * nNwake * ns * vlc::kVr + 1))) return rc;
     if ((rc = reserve(c, r.waF[s], (size_t)nb * nFwake * vlc::kFw + 1))) return rc;
@@ -1529,9 +1553,12 @@ extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
   for (auto& r : c->rotors)
     if (r.defined) M += wake_targets_of(r);
   if (M <= 0) return VLC_OK;
-  if ((rc = reserve(c, c->ws_P, 3 * (size_t)M))) return rc;
-  if ((rc = reserve(c, c->ws_V, 3 * (size_t)M))) return rc;
-  if ((rc = reserve(c, c->ws_acc, 3 * (size_t)M))) return rc;
+  long long Mmax = 0;  // every row active: sized once
+  for (auto& r : c->rotors)
+    if (r.defined && r.nNwake > 0) Mmax += ((long long)r.nNwake * (r.ns + 1) + r.nFwake) * r.nbConvect;
+  if ((rc = reserve(c, c->ws_P, 3 * (size_t)Mmax))) return rc;
+  if ((rc = reserve(c, c->ws_V, 3 * (size_t)Mmax))) return rc;
+  if ((rc = reserve(c, c->ws_acc, 3 * (size_t)Mmax))) return rc;
   long long off = 0;
   for (auto& r : c->rotors) {
     const long long m = r.defined ? wake_targets_of(r) : 0;
