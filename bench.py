@@ -319,6 +319,7 @@ def main():
     info = ctx.set_info(0)
     shared = info["shared_active"] == 1
     fp64_peak, _ = ctx.measure_fp64_peak(20000)
+    fp64_rate3, _ = ctx.measure_fp64_rate(1, 20000)    # DFMA rate with three changing register operands (informational)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -430,8 +431,12 @@ def main():
                 "kernel": kernel, "kernel_ms": kern_ms_max, "sweep_ms": sweep_ms_max,
                 "pairs_per_launch": pairs_launch, "flops_per_pair": FLOPS_PER_PAIR,
                 "pipe_frac": issued * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
+                "dfma_3reg_tflops": fp64_rate3 / 1e12,
+                "pipe_frac_of_3reg_rate": issued * 2 / (kern_ms_max * 1e-3) / fp64_rate3 if kern_ms_max > 0 else 0.0,
                 "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); "
-                               "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
+                               "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2; dfma_3reg_tflops = the same "
+                               "measurement with three distinct changing register operands per DFMA (vlc_measure_fp64_rate "
+                               "pattern 1), the practical ceiling of register-fed FP64 code",
                 "note": "compute-bound pairwise N-body on the FP64 pipe (no tensor cores by construction); " + note}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -179,7 +179,7 @@ int vlc_rotor_wake_to_predicted(vlc_ctx* ctx, int ir);
  * :1609-1702), axisymmetric copy + rotate of blades 2..nb (:4801-4823). */
 int vlc_rotor_convectwake(vlc_ctx* ctx, int ir, double dt, int predicted);
 /* = rotor%rollup() classdef.f90:4515-4605 (shiftFwake :4500-4513 when the far wake is full, then shiftwake :4481-4498);
- * the driver calls it when rowNear == 1 (main.f90:1421). */
+ * the driver calls it when rowNear == 1 (main.f90:1424-1425). */
 int vlc_rotor_rollup(vlc_ctx* ctx, int ir);
 /* The wake sweeps of the convection driver for ALL rotors at once (main.f90:800-838; 'P': :889-911, :1057-1081):
  * vel{N,F}wake[Predicted](active rows) of every convected blade <- sum over source rotors of
@@ -290,6 +290,11 @@ int vlc_gridgen(vlc_ctx* ctx, int nx, int ny, int nz, const double* xyzMin, cons
  * and the elapsed milliseconds; used by bench.py as the measured FP64 roofline denominator
  * (MEASURED_PEAKS.json has no FP64 entry). */
 int vlc_measure_fp64_peak(vlc_ctx* ctx, int iters, double* flops_per_s, double* ms);
+/* Same measurement with a chosen operand pattern: 0 = the chains above (one changing register operand per DFMA, the
+ * other two a constant and a loop-invariant register: the pipe's best case), 1 = three distinct, changing register
+ * operands per DFMA (a = b*c + a; b = c*a + b; ...), which is what the instructions of a real kernel present to the
+ * register file.  bench.py reports pattern 1 next to the peak as the practical ceiling of register-fed FP64 code. */
+int vlc_measure_fp64_rate(vlc_ctx* ctx, int iters, int pattern, double* flops_per_s, double* ms);
 /* Device time of the last sweep launched by this context, from CUDA events recorded on the context's stream around
  * the dominant kernel (bs_lattice_kernel or bs_sweep_kernel) and around the whole sweep (incl. remainder + reduce).
  * Waits for that sweep to finish. */

@@ -147,6 +147,7 @@ def load_library() -> C.CDLL:
         "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_gridgen": (i32, [_vp, i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, _vp, _vp]),
         "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
+        "vlc_measure_fp64_rate": (i32, [_vp, i32, i32, _dp, _dp]),
         "vlc_probe_rsqrt": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
     }
     for name, (res, args) in sig.items():
@@ -232,6 +233,12 @@ class Context:
     def measure_fp64_peak(self, iters: int = 20000) -> tuple[float, float]:
         f, ms = C.c_double(), C.c_double()
         self._ck(self.lib.vlc_measure_fp64_peak(self.h, iters, C.byref(f), C.byref(ms)))
+        return f.value, ms.value
+
+    def measure_fp64_rate(self, pattern: int, iters: int = 20000) -> tuple[float, float]:
+        """pattern 0 = vlc_measure_fp64_peak's chains; 1 = three distinct changing register operands per DFMA."""
+        f, ms = C.c_double(), C.c_double()
+        self._ck(self.lib.vlc_measure_fp64_rate(self.h, iters, pattern, C.byref(f), C.byref(ms)))
         return f.value, ms.value
 
     def probe_rsqrt(self, x):

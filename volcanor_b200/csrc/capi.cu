@@ -32,10 +32,11 @@ constexpr int kLatThreads = VLC_LAT_THREADS;  // threads per lattice-kernel CTA
 constexpr int kTile = 128;     // filaments per shared-memory tile (12 KB)
 constexpr int kStages = 3;     // TMA ring depth
 // Lattice kernel shape (vlc_set_lattice_tuning): strip width W in 1..4, targets per thread T in 1..3; 0 = automatic:
-// W minimises the measured cost per ring (profiles/r01e_wt_sweep.md: W=1,T=3 1.000; W=2,T=3 0.944; W=3,T=2 0.935;
-// W=4,T=1 0.895) times the padding of the last strip, ceil(ns/W)*W/ns; T is the best measured one for that W.
-constexpr double kLatCost[5] = {0.0, 1.000, 0.944, 0.935, 0.895};
-constexpr int kLatBestT[5] = {0, 3, 3, 2, 1};
+// W minimises the measured cost per ring (profiles/r01h_wt_sweep.md: W=1,T=3 1.000; W=2,T=2 0.919; W=3,T=2 0.932;
+// W=4,T=2 0.885, T=1 0.887) times the padding of the last strip, ceil(ns/W)*W/ns; T is the best measured one for that W
+// (sweeps with at most one CTA of targets use T=1, sweep_shared).
+constexpr double kLatCost[5] = {0.0, 1.000, 0.919, 0.932, 0.885};
+constexpr int kLatBestT[5] = {0, 3, 2, 2, 2};
 
 std::string g_create_error;
 
@@ -2118,7 +2119,15 @@ extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyz
 
 // ============================================================================ measurement
 
+static int measure_fp64(vlc_ctx* c, int iters, int pattern, double* flops_per_s, double* ms_out);
 extern "C" int vlc_measure_fp64_peak(vlc_ctx* c, int iters, double* flops_per_s, double* ms_out) {
+  return measure_fp64(c, iters, 0, flops_per_s, ms_out);
+}
+extern "C" int vlc_measure_fp64_rate(vlc_ctx* c, int iters, int pattern, double* flops_per_s, double* ms_out) {
+  if (pattern != 0 && pattern != 1) return fail(c, VLC_ERR_ARG, "pattern: 0 = one register operand per DFMA, 1 = three");
+  return measure_fp64(c, iters, pattern, flops_per_s, ms_out);
+}
+static int measure_fp64(vlc_ctx* c, int iters, int pattern, double* flops_per_s, double* ms_out) {
   CHECK_CTX(c);
   int rc = bind_device(c);
   if (rc) return rc;
@@ -2128,9 +2137,10 @@ extern "C" int vlc_measure_fp64_peak(vlc_ctx* c, int iters, double* flops_per_s,
   cudaEvent_t e0, e1;
   CUDA_OK(c, cudaEventCreate(&e0));
   CUDA_OK(c, cudaEventCreate(&e1));
-  vlc::dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(iters / 4 + 1, c->scratch.p);  // warm-up
+  auto kern = pattern ? vlc::dfma_peak3_kernel : vlc::dfma_peak_kernel;  // same DFMA count per iteration
+  kern<<<blocks, threads, 0, c->stream>>>(iters / 4 + 1, c->scratch.p);  // warm-up
   CUDA_OK(c, cudaEventRecord(e0, c->stream));
-  vlc::dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(iters, c->scratch.p);
+  kern<<<blocks, threads, 0, c->stream>>>(iters, c->scratch.p);
   CUDA_OK(c, cudaEventRecord(e1, c->stream));
   CUDA_OK(c, cudaEventSynchronize(e1));
   CUDA_OK(c, cudaGetLastError());

@@ -38,16 +38,21 @@ constexpr int kSrcBytes = kSrcDoubles * 8;
 // No special-case branch: inputs are finite > 0 whenever the result is used (the c2 guard predicates
 // the accumulation otherwise).
 constexpr double kSeedRelErr = 9.5367431640625e-07;  // 2^-20 >= measured max 9.18e-7
+// Operand sourcing matters on this pipe (tools/micro/fp64_operands.cu, profiles/r01h_fp64_operands.md): a DFMA whose
+// three operands are three DIFFERENT registers issues every 3 cycles per scheduler, one with at most two different
+// registers (an immediate, or the same register in two slots) every 2.  The last refinement step is therefore written
+// y + y*(e*p) -- DMUL(e, p) then DFMA(y, ep, y), two different registers each -- instead of fma(p, e*y, y): the same
+// five instructions, the same single rounding of the result, one issue cycle less per reciprocal square root.
 template <bool FAST>
 __device__ __forceinline__ double rsqrt_fp64(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double t = y * y;
   const double e = fma(-x, t, 1.0);
-  const double q = e * y;
-  if (FAST) return fma(0.5, q, y);
+  if (FAST) return fma(y, 0.5 * e, y);
   const double p = fma(0.375, e, 0.5);
-  return fma(p, q, y);
+  const double ep = e * p;
+  return fma(y, ep, y);
 }
 
 // sc <- (c2 > eps^2) ? sc : 0 without touching the FP64 pipe.  VLC_GUARD_HI (default): only the HIGH word of sc is

@@ -130,6 +130,36 @@ __global__ void dfma_peak_kernel(int iters, double* __restrict__ out) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The same with THREE distinct, changing register operands per DFMA (a = b*c + a; b = c*a + b; c = a*b + c): what a real
+// kernel's instructions look like to the register file (the chain above feeds two of its three operands from a
+// constant and a loop-invariant register).  8 independent chains per phase.
+__global__ void dfma_peak3_kernel(int iters, double* __restrict__ out) {
+  double a[kPeakChains], b[kPeakChains], c[kPeakChains];
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k) {
+    a[k] = 1e-3 * (k + 1) + threadIdx.x * 1e-9;
+    b[k] = 0.5 + 1e-2 * k;
+    c[k] = 1e-4 * (threadIdx.x + 1) + 1e-5 * k;
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < kPeakUnroll / 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < kPeakChains; ++k) a[k] = fma(b[k], c[k], a[k]);
+#pragma unroll
+      for (int k = 0; k < kPeakChains; ++k) b[k] = fma(c[k], a[k], b[k]);
+#pragma unroll
+      for (int k = 0; k < kPeakChains; ++k) c[k] = fma(a[k], b[k], c[k]);
+#pragma unroll
+      for (int k = 0; k < kPeakChains; ++k) a[k] = fma(c[k], b[k], -a[k]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k) s += a[k] + b[k] + c[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace vlc
 
 // ---- probe: raw MUFU.RSQ64H seed and both Newton refinements (tests measure the seed error bound) ----
