@@ -209,8 +209,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: keep stdout = the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION, which the box also sets through nccl.conf
+            # (the environment variable is then empty): keep stdout = the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     lats, n_src, m, name = workload(args)
