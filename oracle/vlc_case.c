@@ -585,6 +585,7 @@ struct orc_case {
   geom_t *geom;
   orc_rotor_t **rotor;
   orc_hooks_t hooks;
+  void *stage_user; /* `user` of the two wake-stage hooks when they were installed separately (orc_case_set_stage_hooks) */
   char err[256];
 };
 
@@ -992,7 +993,14 @@ void orc_case_free(orc_case_t *c) {
   free(c);
 }
 
+void orc_case_set_stage_hooks(orc_case_t *c, void *user, int (*prestep)(void *, int), int (*convect)(void *, int)) {
+  c->stage_user = user;
+  c->hooks.wake_prestep = prestep;
+  c->hooks.wake_convect = convect;
+}
+
 void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *h) {
+  c->stage_user = NULL;
   if (h) {
     c->hooks = *h;
   } else {
@@ -1424,7 +1432,7 @@ int orc_case_step(orc_case_t *c) {
   }
   for (int ir = 0; ir < c->nr; ++ir) c->rotor[ir]->gen_wake[0]++; /* rows moved, shed row attached, aged, dissipated below */
   if (cfg->wakeSuppress == 0 && c->hooks.wake_prestep) { /* device-resident wake: the hook owner does :466-506 */
-    int rc = c->hooks.wake_prestep(c->hooks.user, iter);
+    int rc = c->hooks.wake_prestep(c->stage_user ? c->stage_user : c->hooks.user, iter);
     if (rc) return rc;
   } else if (cfg->wakeSuppress == 0) { /* :466-506 */
     for (int ir = 0; ir < c->nr; ++ir)
@@ -1488,7 +1496,7 @@ int orc_case_step(orc_case_t *c) {
       snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 3)", cfg->fdScheme);
       return 3;
     }
-    int rc = c->hooks.wake_convect(c->hooks.user, iter);
+    int rc = c->hooks.wake_convect(c->stage_user ? c->stage_user : c->hooks.user, iter);
     if (rc) return rc;
     const int nsweeps = (cfg->fdScheme == 0 || (cfg->fdScheme == 3 && iter == 1)) ? 1 : 2;
     for (int ir = 0; ir < c->nr; ++ir) { /* the same count wake_sweep() keeps */
@@ -1611,6 +1619,65 @@ int orc_case_step(orc_case_t *c) {
       if (r->nNwake <= 0) continue;
       if (r->rowNear == 1) orc_rotor_rollup(r);
       orc_rotor_assignshed(r, "TE");
+    }
+  }
+  return 0;
+}
+
+/* ---- the wake stages of the time loop as separate calls (what a hook owner in resident mode drives; the CPU versions
+ * let tests/native/case_gpu_hooks.c run its orchestration against this file's inline statement of main.f90) ---- */
+int orc_case_wake_sweep(orc_case_t *c, int predicted) { /* main.f90:800-838 / :889-911, :1057-1081 */
+  const double pairs = c->pairs; /* the driver counts the sweeps of a staged step itself */
+  const int rc = wake_sweep(c, predicted);
+  c->pairs = pairs;
+  return rc;
+}
+void orc_rotor_wake_to_predicted(orc_rotor_t *r) { copy_wake_to_predicted(r); }
+/* op: 0 first-step copy (main.f90:1013-1020), 1 AB2 (:1031-1041), 2 AM2 (:1094-1099), 3 history (:1103-1107),
+ * 4 vel_order2 on the active slices (:927-940) -- convected blades */
+int orc_rotor_wakevel_op(orc_rotor_t *r, int op) {
+  const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
+  for (int ib = 0; ib < r->nbConvect; ++ib) {
+    orc_blade_t *b = &r->blade[ib];
+    switch (op) {
+      case 0:
+        memcpy(b->velNwake1, b->velNwake, sizeof(double) * nn);
+        memcpy(b->velFwake1, b->velFwake, sizeof(double) * nf);
+        break;
+      case 1:
+        memcpy(b->velNwakeStep, b->velNwake, sizeof(double) * nn);
+        memcpy(b->velFwakeStep, b->velFwake, sizeof(double) * nf);
+        for (size_t q = 0; q < nn; ++q) b->velNwake[q] = 0.5 * (3.0 * b->velNwakeStep[q] - b->velNwake1[q]);
+        for (size_t q = 0; q < nf; ++q) b->velFwake[q] = 0.5 * (3.0 * b->velFwakeStep[q] - b->velFwake1[q]);
+        break;
+      case 2:
+        for (size_t q = 0; q < nn; ++q) b->velNwake[q] = (b->velNwakePredicted[q] + b->velNwakeStep[q]) * 0.5;
+        for (size_t q = 0; q < nf; ++q) b->velFwake[q] = (b->velFwakePredicted[q] + b->velFwakeStep[q]) * 0.5;
+        break;
+      case 3:
+        memcpy(b->velNwake1, b->velNwakeStep, sizeof(double) * nn);
+        memcpy(b->velFwake1, b->velFwakeStep, sizeof(double) * nf);
+        break;
+      case 4: {
+        const int rowsN = r->nNwakeEnd - r->rowNear + 1, rowsF = r->nFwakeEnd - r->rowFar + 1;
+        if (rowsN > 0) { /* column by column on the slice (:, rowNear:nNwakeEnd, j): rows are contiguous inside a column */
+          double *o = (double *)malloc(sizeof(double) * 3 * (size_t)rowsN);
+          for (int j = 1; j <= r->ns + 1; ++j) {
+            double *vn = &b->velNwake[3 * ((r->rowNear - 1) + (size_t)r->nNwake * (j - 1))];
+            const double *vp = &b->velNwakePredicted[3 * ((r->rowNear - 1) + (size_t)r->nNwake * (j - 1))];
+            orc_vel_order2_Nwake(vn, vp, rowsN, 1, o);
+            memcpy(vn, o, sizeof(double) * 3 * (size_t)rowsN);
+          }
+          free(o);
+        }
+        if (rowsF > 0) {
+          double *o = (double *)malloc(sizeof(double) * 3 * (size_t)rowsF);
+          orc_vel_order2_Fwake(&b->velFwake[3 * (r->rowFar - 1)], &b->velFwakePredicted[3 * (r->rowFar - 1)], rowsF, o);
+          memcpy(&b->velFwake[3 * (r->rowFar - 1)], o, sizeof(double) * 3 * (size_t)rowsF);
+          free(o);
+        }
+      } break;
+      default: return 2;
     }
   }
   return 0;

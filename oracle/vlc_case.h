@@ -71,6 +71,9 @@ int orc_case_set_config(orc_case_t *c, const char *key, double value);
  * "grid" passes a PLOT3D grid (3, nc+1, ns+1) as read by rotor_plot3dtoblade (classdef.f90:3957). */
 int orc_case_set_geom(orc_case_t *c, int ir, const char *key, int n, const double *values);
 void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *hooks); /* NULL = CPU oracle */
+/* Only the two wake-stage hooks, with their own `user`; the five call sites keep what orc_case_set_hooks installed
+ * (call it first).  NULL functions restore the inline stages. */
+void orc_case_set_stage_hooks(orc_case_t *c, void *user, int (*wake_prestep)(void *, int), int (*wake_convect)(void *, int));
 /* main.f90:1-382: init rotors, pitch, AIC, initial solution, initial forces.  Returns 0 / error code. */
 int orc_case_init(orc_case_t *c);
 /* one pass of the time loop main.f90:400-1452 (iter = 1..nt) */
@@ -84,6 +87,12 @@ const char *orc_case_error(const orc_case_t *c);
 void orc_case_force_nondim(orc_case_t *c, int ir, double out[9]);
 /* pair interactions (vf_vind evaluations in the reference's enumeration) of the last step */
 double orc_case_pairs_last_step(const orc_case_t *c);
+
+/* the wake stages as separate calls on the driver's own (CPU) state: the CPU backend of the staged orchestration in
+ * tests/native/case_gpu_hooks.c, whose result must equal this file's inline time loop bit for bit */
+int orc_case_wake_sweep(orc_case_t *c, int predicted);
+void orc_rotor_wake_to_predicted(orc_rotor_t *r);
+int orc_rotor_wakevel_op(orc_rotor_t *r, int op);
 
 /* pieces exposed for the KAT tests */
 int orc_case_init_rotors(orc_case_t *c); /* main.f90:31-58 only: rotor%init + initial pitch */

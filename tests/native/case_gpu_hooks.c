@@ -29,7 +29,25 @@ typedef struct {
   /* resident mode (tier 2b of the C ABI): the wake lives on the device; only the wing travels */
   int resident, resident_started;
   long wing_uploads;
+  const struct resident_ops *ops; /* who executes the wake stages: the C ABI (GPU) or the oracle's own mutators (CPU) */
 } gpu_user_t;
+
+/* The wake stages of one time step, as the orchestration below calls them.  Two backends: `gpu_ops` forwards each to the
+ * C ABI's tier 2b; `cpu_ops` to the CPU restatement acting on the driver's own arrays -- with it the SAME orchestration
+ * runs without a GPU and must reproduce the driver's inline time loop bit for bit (tests/test_staged_hooks.py). */
+typedef struct resident_ops {
+  int (*begin)(gpu_user_t *u);
+  int (*sync)(gpu_user_t *u, int ir);
+  int (*assignshed)(gpu_user_t *u, int ir, int edge);
+  int (*age_wake)(gpu_user_t *u, int ir, double dt, double omegaSlow);
+  int (*dissipate_wake)(gpu_user_t *u, int ir, double dt, double kinematicVisc);
+  int (*strain_wake)(gpu_user_t *u, int ir);
+  int (*wake_to_predicted)(gpu_user_t *u, int ir);
+  int (*convectwake)(gpu_user_t *u, int ir, int iter, double dt, int predicted);
+  int (*rollup)(gpu_user_t *u, int ir);
+  int (*wake_sweep)(gpu_user_t *u, int predicted, int addInitWakeVel);
+  int (*wakevel_op)(gpu_user_t *u, int ir, int op);
+} resident_ops_t;
 
 #define CK(expr)                        \
   do {                                  \
@@ -145,74 +163,123 @@ static int h_solve(void *user, int ir, const double *RHS, double *gamVec) {
   return u->last_rc = vlc_rotor_solve(u->ctx, ir, RHS, gamVec);
 }
 
-/* main.f90:466-506 on the device: assignshed('LE'), age_wake, dissipate_wake of every rotor, in the driver's order */
+/* ---- backends ---- */
+static int g_assignshed(gpu_user_t *u, int ir, int edge) { return vlc_rotor_assignshed(u->ctx, ir, edge); }
+static int g_age(gpu_user_t *u, int ir, double dt, double om) { return vlc_rotor_age_wake(u->ctx, ir, dt, om); }
+static int g_dissipate(gpu_user_t *u, int ir, double dt, double nu) { return vlc_rotor_dissipate_wake(u->ctx, ir, dt, nu); }
+static int g_strain(gpu_user_t *u, int ir) { return vlc_rotor_strain_wake(u->ctx, ir); }
+static int g_to_pred(gpu_user_t *u, int ir) { return vlc_rotor_wake_to_predicted(u->ctx, ir); }
+static int g_convect(gpu_user_t *u, int ir, int iter, double dt, int p) { (void)iter; return vlc_rotor_convectwake(u->ctx, ir, dt, p); }
+static int g_rollup(gpu_user_t *u, int ir) { return vlc_rotor_rollup(u->ctx, ir); }
+static int g_sweep(gpu_user_t *u, int p, int addInit) { return vlc_wake_sweep(u->ctx, p, addInit); }
+static int g_velop(gpu_user_t *u, int ir, int op) { return vlc_rotor_wakevel_op(u->ctx, ir, op); }
+static const resident_ops_t gpu_ops = {resident_begin, sync_wing, g_assignshed, g_age, g_dissipate, g_strain,
+                                       g_to_pred, g_convect, g_rollup, g_sweep, g_velop};
+
+#define ROT(u, ir) orc_case_rotor((u)->cas, (ir))
+static int c_begin(gpu_user_t *u) { u->resident_started = 1; return 0; }
+static int c_sync(gpu_user_t *u, int ir) { (void)u; (void)ir; return 0; }
+static int c_assignshed(gpu_user_t *u, int ir, int edge) {
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_assignshed(ROT(u, ir), edge ? "TE" : "LE");
+  return 0;
+}
+static int c_age(gpu_user_t *u, int ir, double dt, double om) {
+  (void)om; /* orc_rotor_age_wake reads rotor%omegaSlow itself */
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_age_wake(ROT(u, ir), dt);
+  return 0;
+}
+static int c_dissipate(gpu_user_t *u, int ir, double dt, double nu) {
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_dissipate_wake(ROT(u, ir), dt, nu);
+  return 0;
+}
+static int c_strain(gpu_user_t *u, int ir) {
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_strain_wake(ROT(u, ir));
+  return 0;
+}
+static int c_to_pred(gpu_user_t *u, int ir) {
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_wake_to_predicted(ROT(u, ir));
+  return 0;
+}
+static int c_convect(gpu_user_t *u, int ir, int iter, double dt, int p) {
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_convectwake(ROT(u, ir), iter, dt, p ? 'P' : 'C');
+  return 0;
+}
+static int c_rollup(gpu_user_t *u, int ir) { orc_rotor_rollup(ROT(u, ir)); return 0; }
+static int c_sweep(gpu_user_t *u, int p, int addInit) { (void)addInit; return orc_case_wake_sweep(u->cas, p); }
+static int c_velop(gpu_user_t *u, int ir, int op) { return ROT(u, ir)->nNwake > 0 ? orc_rotor_wakevel_op(ROT(u, ir), op) : 0; }
+static const resident_ops_t cpu_ops = {c_begin, c_sync, c_assignshed, c_age, c_dissipate, c_strain,
+                                       c_to_pred, c_convect, c_rollup, c_sweep, c_velop};
+
+/* main.f90:466-506 as separate stages: assignshed('LE'), age_wake, dissipate_wake of every rotor, in the driver's order */
 static int h_wake_prestep(void *user, int iter) {
   gpu_user_t *u = (gpu_user_t *)user;
+  const resident_ops_t *o = u->ops;
   (void)iter;
   const orc_config_t *cfg = orc_case_config(u->cas);
-  if (!u->resident_started) CK(resident_begin(u));
-  for (int ir = 0; ir < u->nr; ++ir) CK(sync_wing(u, ir));
-  for (int ir = 0; ir < u->nr; ++ir) CK(vlc_rotor_assignshed(u->ctx, ir, 0));
-  for (int ir = 0; ir < u->nr; ++ir) CK(vlc_rotor_age_wake(u->ctx, ir, cfg->dt, orc_case_rotor(u->cas, ir)->omegaSlow));
+  if (!u->resident_started) CK(o->begin(u));
+  for (int ir = 0; ir < u->nr; ++ir) CK(o->sync(u, ir));
+  for (int ir = 0; ir < u->nr; ++ir) CK(o->assignshed(u, ir, 0));
+  for (int ir = 0; ir < u->nr; ++ir) CK(o->age_wake(u, ir, cfg->dt, orc_case_rotor(u->cas, ir)->omegaSlow));
   if (cfg->wakeDissipation == 1)
-    for (int ir = 0; ir < u->nr; ++ir) CK(vlc_rotor_dissipate_wake(u->ctx, ir, cfg->dt, cfg->kinematicVisc));
+    for (int ir = 0; ir < u->nr; ++ir) CK(o->dissipate_wake(u, ir, cfg->dt, cfg->kinematicVisc));
   return 0;
 }
 
-/* main.f90:800-1440 on the device: the wake sweeps, the fdScheme switch (0: explicit Euler, 1: predictor-corrector,
+/* main.f90:800-1440 as separate stages: the wake sweeps, the fdScheme switch (0: explicit Euler, 1: predictor-corrector,
  * 3: Adams-Bashforth / Adams-Moulton), strain_wake, rollup, assignshed('TE') */
 static int h_wake_convect(void *user, int iter) {
   gpu_user_t *u = (gpu_user_t *)user;
+  const resident_ops_t *o = u->ops;
   const orc_config_t *cfg = orc_case_config(u->cas);
   const double dt = cfg->dt;
   const int addInit = iter < cfg->initWakeVelNt;
   const int nr = u->nr;
-  for (int ir = 0; ir < nr; ++ir) CK(sync_wing(u, ir)); /* the solve changed the wing's circulation */
-  CK(vlc_wake_sweep(u->ctx, 0, addInit));
+  for (int ir = 0; ir < nr; ++ir) CK(o->sync(u, ir)); /* the solve changed the wing's circulation */
+  CK(o->wake_sweep(u, 0, addInit));
   switch (cfg->fdScheme) {
     case 0: /* :846-859 */
-      for (int ir = 0; ir < nr; ++ir) CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
+      for (int ir = 0; ir < nr; ++ir) CK(o->convectwake(u, ir, iter, dt, 0));
       break;
     case 1: /* :861-949 */
       for (int ir = 0; ir < nr; ++ir) {
-        CK(vlc_rotor_wake_to_predicted(u->ctx, ir));
-        CK(vlc_rotor_convectwake(u->ctx, ir, dt, 1));
+        CK(o->wake_to_predicted(u, ir));
+        CK(o->convectwake(u, ir, iter, dt, 1));
       }
-      CK(vlc_wake_sweep(u->ctx, 1, addInit));
+      CK(o->wake_sweep(u, 1, addInit));
       for (int ir = 0; ir < nr; ++ir) {
-        CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_ORDER2));
-        CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
+        CK(o->wakevel_op(u, ir, VLC_VEL_ORDER2));
+        CK(o->convectwake(u, ir, iter, dt, 0));
       }
       break;
     case 3: /* :1002-1115 */
       if (iter == 1) {
         for (int ir = 0; ir < nr; ++ir) {
-          CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
-          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_FIRST_STEP));
+          CK(o->convectwake(u, ir, iter, dt, 0));
+          CK(o->wakevel_op(u, ir, VLC_VEL_FIRST_STEP));
         }
       } else {
         for (int ir = 0; ir < nr; ++ir) {
-          CK(vlc_rotor_wake_to_predicted(u->ctx, ir));
-          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_AB2));
-          CK(vlc_rotor_convectwake(u->ctx, ir, dt, 1));
+          CK(o->wake_to_predicted(u, ir));
+          CK(o->wakevel_op(u, ir, VLC_VEL_AB2));
+          CK(o->convectwake(u, ir, iter, dt, 1));
         }
-        CK(vlc_wake_sweep(u->ctx, 1, addInit));
+        CK(o->wake_sweep(u, 1, addInit));
         for (int ir = 0; ir < nr; ++ir) {
-          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_AM2));
-          CK(vlc_rotor_convectwake(u->ctx, ir, dt, 0));
-          CK(vlc_rotor_wakevel_op(u->ctx, ir, VLC_VEL_SHIFT_HISTORY));
+          CK(o->wakevel_op(u, ir, VLC_VEL_AM2));
+          CK(o->convectwake(u, ir, iter, dt, 0));
+          CK(o->wakevel_op(u, ir, VLC_VEL_SHIFT_HISTORY));
         }
       }
       break;
     default: return u->last_rc = VLC_ERR_ARG;
   }
   if (cfg->wakeStrain == 1) /* :1409-1416 */
-    for (int ir = 0; ir < nr; ++ir) CK(vlc_rotor_strain_wake(u->ctx, ir));
+    for (int ir = 0; ir < nr; ++ir) CK(o->strain_wake(u, ir));
   for (int ir = 0; ir < nr; ++ir) { /* :1419-1439 */
     const orc_rotor_t *r = orc_case_rotor(u->cas, ir);
     if (r->nNwake <= 0) continue;
-    if (r->rowNear == 1) CK(vlc_rotor_rollup(u->ctx, ir));
-    CK(vlc_rotor_assignshed(u->ctx, ir, 1));
+    if (r->rowNear == 1) CK(o->rollup(u, ir));
+    CK(o->assignshed(u, ir, 1));
   }
   return 0;
 }
@@ -252,6 +319,7 @@ void *case_gpu_hooks_install_resident(orc_case_t *cas, vlc_ctx *ctx, int nr) {
   gpu_user_t *u = (gpu_user_t *)case_gpu_hooks_install(cas, ctx, nr);
   if (!u) return NULL;
   u->resident = 1;
+  u->ops = &gpu_ops;
   orc_hooks_t h;
   memset(&h, 0, sizeof h);
   h.user = u;
@@ -263,6 +331,19 @@ void *case_gpu_hooks_install_resident(orc_case_t *cas, vlc_ctx *ctx, int nr) {
   h.wake_prestep = h_wake_prestep;
   h.wake_convect = h_wake_convect;
   orc_case_set_hooks(cas, &h);
+  return u;
+}
+
+/* The same staged orchestration with the CPU backend: nothing touches the library; only the two wake-stage hooks are
+ * installed (the five hot-path call sites keep the CPU oracle).  `ctx` is not used. */
+void *case_cpu_staged_hooks_install(orc_case_t *cas, int nr) {
+  if (nr > MAX_ROTORS) return NULL;
+  gpu_user_t *u = (gpu_user_t *)calloc(1, sizeof(gpu_user_t));
+  u->cas = cas;
+  u->nr = nr;
+  u->ops = &cpu_ops;
+  orc_case_set_hooks(cas, NULL);
+  orc_case_set_stage_hooks(cas, u, h_wake_prestep, h_wake_convect);
   return u;
 }
 
