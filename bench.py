@@ -424,10 +424,11 @@ def main():
                 "instr/pair (43 full, 41 fast)")
     achieved = pairs_launch * FLOPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12 if kern_ms_max > 0 else 0.0
     # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture of this same command
-    # (profiles/r01e_bs_sweep_full.md: dram__bytes_read.sum 34.37 MB + dram__bytes_write.sum 1.15 MB; the strip records
-    # are 28.0 MB, targets 6.2 MB, partial sums 18.6 MB mostly absorbed by L2): no wasted re-reads.  Only quoted for
-    # the workload the capture was taken on.
-    traffic = 35.53e6 if (shared and world == 1 and args.filaments == 1_000_000 and args.lat_w in (0, 4)) else None
+    # (profiles/r01i_bs_sweep_full.md: dram__bytes_read.sum 37.57 MB + dram__bytes_write.sum 29.13 MB; the strip records
+    # are 28.0 MB, targets 6.2 MB, the 12 source-split partial sums 74 MB, more than half of them absorbed by L2): no
+    # wasted re-reads -- 0.003 % of the HBM peak.  Only quoted for the workload and launch shape the capture was taken on.
+    traffic = 66.70e6 if (shared and world == 1 and args.filaments == 1_000_000 and args.lat_w in (0, 4)
+                          and args.lat_t in (0, 2) and args.nsplit == 0) else None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "kernel": kernel, "kernel_ms": kern_ms_max, "sweep_ms": sweep_ms_max,

@@ -108,7 +108,14 @@ def full(tag: str) -> str | None:
     if src.strip():
         (OUT / f"prof_{tag}_source.csv").write_text(src)
         try:
-            srows = list(csv.DictReader(io.StringIO(src)))
+            raw = list(csv.reader(io.StringIO(src)))
+            h = next(i for i, r in enumerate(raw) if "Source" in r or "SASS" in r)    # line 1 is the "Kernel Name" row
+            srows = [dict(zip(raw[h], r)) for r in raw[h + 1:] if len(r) == len(raw[h])]
+            stall = {c: sum(float(r[c] or 0) for r in srows) for c in raw[h] if c.startswith("stall_") and "Not Issued" not in c}
+            if sum(stall.values()) > 0:
+                tot_s = sum(stall.values())
+                out += ["## Warp-state samples by stall reason (source page, all samples)", "", "| reason | samples | share |", "|---|---:|---:|"]
+                out += [f"| {k} | {int(v)} | {100 * v / tot_s:.1f} % |" for k, v in sorted(stall.items(), key=lambda kv: -kv[1])[:8]] + [""]
             col_inst = next((c for c in srows[0] if c.startswith("# Instructions Executed") or c == "Instructions Executed"), None)
             col_src = next((c for c in srows[0] if c in ("Source", "SASS", "Instruction")), None)
             if col_inst and col_src:

@@ -29,8 +29,8 @@ constexpr int kSrcBytes = kSrcDoubles * 8;
 // Reciprocal square root on the FP64 pipe: MUFU.RSQ64H seed y0 (only the high word of x is used: measured
 // relative error d <= 9.2e-7 = 2^-20.06 on B200, tests/test_gpu_parity.py::test_rsqrt_seed_accuracy)
 // refined by Newton.
-//   FULL (third order, the sequence CUDA's own rsqrt() uses on its fast path): 5 FP64 instr, error ~2.5 d^3
-//        ~ 2e-18 -> results limited by rounding (measured 1.1e-16).  DEFAULT.
+//   FULL (third order: y1 = y0 + y0*e*(1/2 + 3/8 e), e = 1 - x y0^2): 5 FP64 instr, error ~2.5 d^3 ~ 2e-18 ->
+//        results limited by rounding (measured 1.1e-16).  DEFAULT.
 //   FAST (second order): 4 FP64 instr, y1 = y0 (1 - 1.5 d^2 + ...): relative error <= 1.5 d^2 = 1.3e-12,
 //        always low; bs_sweep_kernel centres it with one multiply by (1 + 0.75 d_max^2) per target, leaving
 //        <= 6.4e-13 per pair (1.5e-13 measured on a whole sweep).  Inside the 1e-12 tolerance but with
