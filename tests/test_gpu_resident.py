@@ -300,3 +300,33 @@ def test_resident_two_rotor_case(ctx, oracle):
     print(f"wing + rotor, 16 steps resident: max rel CL/CT/gamVec err {worst:.3e}, wake max abs diff {dw:.3e}")
     assert worst < TOL_HISTORY and dw < 1e-9
     lib.case_gpu_hooks_free(h)
+
+
+def test_tier2b_argument_and_state_errors(ctx):
+    """Error behaviour of the new entry points: status + message (the shim turns them into `error stop`), never a
+    silent no-op on bad input."""
+    import volcanor_b200 as vb
+    with pytest.raises(vb.VlcError, match="rotor not defined"):
+        ctx.rotor_assignshed(57, "LE")
+    ctx.rotor_define(5, 2, 3, 4, 6, 2, 1)
+    with pytest.raises(vb.VlcError, match="nbConvect"):
+        ctx.rotor_set_wake_params(5, 3, 0, 0, 0, 1, 4, 1.0, 1.0, 0.0)
+    with pytest.raises(vb.VlcError, match="rollupStart"):
+        ctx.rotor_set_wake_params(5, 2, 0, 0, 0, 0, 4, 1.0, 1.0, 0.0)
+    with pytest.raises(vb.VlcError, match="rollupStart"):
+        ctx.rotor_set_wake_params(5, 2, 0, 0, 0, 1, 5, 1.0, 1.0, 0.0)
+    with pytest.raises(vb.VlcError, match="rowNear outside"):       # rowNear = nNwake + 1 right after define
+        ctx.rotor_assignshed(5, "LE")
+    assert ctx.lib.vlc_rotor_assignshed(ctx.h, 5, 2) == 2            # VLC_ERR_ARG: edge must be 0 / 1
+    assert ctx.lib.vlc_rotor_wakevel_op(ctx.h, 5, 9) == 2
+    assert ctx.lib.vlc_rotor_get_nwake(ctx.h, 5, 2, 0, None) == 2    # blade index / null pointer
+    assert ctx.lib.vlc_rotor_set_frame(ctx.h, 5, None, None) == 2
+    # a sweep on wake rows that were never transferred is refused (no garbage velocities): rows 5..6 go up, then the
+    # driver claims rows 3..6 are active
+    ctx.rotor_set_rows(5, 5, 3)
+    for ib in range(2):
+        ctx.rotor_put_nwake(5, ib, np.zeros((4, 6, 50)))
+    ctx.rotor_set_rows(5, 3, 3)
+    with pytest.raises(vb.VlcError, match="never transferred"):
+        ctx.wake_sweep(False)
+    ctx.rotor_define(5, 1, 1, 1, 0, 0, 1)                            # leave no half-defined rotor behind for other tests

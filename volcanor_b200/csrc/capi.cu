@@ -974,6 +974,11 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     cudaFree(r.d_ipiv);
     r.d_ipiv = nullptr;
   }
+  if (r.d_axi) {  // sized by nb
+    cudaStreamSynchronize(c->stream);
+    cudaFree(r.d_axi);
+    r.d_axi = nullptr;
+  }
   r.N = nc * ns * nb;
   r.dirty[0] = r.dirty[1] = r.bound_dirty = true;
   r.factored = false;
@@ -1519,6 +1524,10 @@ extern "C" int vlc_rotor_rollup(vlc_ctx* c, int ir) {
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
   if (r->nNwake <= 0) return VLC_OK;
+  if (r->rollupStart < 1 || r->rollupEnd > r->ns)
+    return fail(c, VLC_ERR_STATE, "rollup: rollupStart / rollupEnd not set (vlc_rotor_set_wake_params)");
+  if (r->nFwake > 0 && (r->rowFar < 1 || r->rowFar > r->nFwake + 1))
+    return fail(c, VLC_ERR_STATE, "rollup: rowFar outside 1..nFwake+1");
   int rowFarNext = r->rowFar - 1;  // classdef.f90:4527
   if (r->nFwake > 0 && rowFarNext == 0) {  // :4570-4573 (shiftFwake moves every blade, once)
     vlc::rec_shiftFwake_kernel<<<blocks_for(r->nb * vlc::kFw, 64), 64, 0, c->stream>>>(r->nb, r->nFwake, r->waF[0].p);
