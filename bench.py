@@ -195,6 +195,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries ONE JSON line.  Native libraries write there too (NCCL prints "NCCL version ..." on rank 0 whatever
+    # NCCL_DEBUG / NCCL_DEBUG_FILE say on this image), so file descriptor 1 points at stderr until the line is printed.
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import volcanor_b200 as vb
@@ -209,10 +215,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION, which the box also sets through nccl.conf
-            # (the environment variable is then empty): keep stdout = the JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     lats, n_src, m, name = workload(args)
@@ -468,8 +470,11 @@ def main():
            "timesteps_per_s": args.steps / (elapsed_ms * 1e-3), "sweeps_per_step": 2,
            "checks": {"ranks_hold_identical_wake": ranks_consistent, "wake_finite": wake_finite},
            "fp64_peak_measured_tflops": peak}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
+        os.dup2(2, 1)          # NCCL teardown messages, if any
         dist.destroy_process_group()
 
 
