@@ -252,11 +252,13 @@ int vlc_set_shared_nodes(vlc_ctx* ctx, int on);
  * amortise the node work: 72 / 66.5 / 64.7 / 63.75 FP64 instructions per ring), targets_per_thread in 1..3;
  * 0 = default.  Takes effect at the next pack.  Only speed and summation order change. */
 int vlc_set_lattice_tuning(vlc_ctx* ctx, int strip_width, int targets_per_thread);
-/* out[0..4]: out[0] = filaments in the reference's enumeration, out[1] = ring-step records and out[2] = remainder filaments of
+/* out[0..5]: out[0] = filaments in the reference's enumeration, out[1] = strip records and out[2] = remainder filaments of
  * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel, 0 if
- * the flat one (reads the device flag: synchronises), -1 for a flat-only set, out[4] = strip width of the records. */
+ * the flat one (reads the device flag: synchronises), -1 for a flat-only set, out[4] = strip width of the records,
+ * out[5] = width of the tail strips (0 = none): a rotor's lattice with ns columns, ns not a multiple of 4, is covered by
+ * floor(ns/4) strips of width 4 plus one strip of width ns mod 4 when that is cheaper than padding the last strip. */
 int vlc_set_info(vlc_ctx* ctx, int set, int64_t* out);
-/* Same five numbers for the packed [wing | wake] set of rotor ir (packs it if needed): tells whether the uploaded
+/* Same six numbers for the packed [wing | wake] set of rotor ir (packs it if needed): tells whether the uploaded
  * records describe a lattice the shared-node kernel can use (out[3] = 1) or the flat enumeration is used (0). */
 int vlc_rotor_info(vlc_ctx* ctx, int ir, int predicted, int64_t* out);
 /* rotor_dissipate_wake on a lattice (classdef.f90:4364-4393): vf1 grows, vf3 <- vf1, gam decays, vf2 grows,

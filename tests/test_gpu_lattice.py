@@ -298,3 +298,33 @@ def test_full_size_workload_properties_and_sampled_oracle(ctx, oracle):
     keep2 = _upload(ctx, lats)
     V2 = _sweep(ctx, P)
     assert np.array_equal(V2, 2.0 * V)
+
+
+@pytest.mark.parametrize("ns,main,tail", [(5, 4, 1), (6, 4, 2), (7, 4, 3), (8, 4, 0), (9, 4, 1), (10, 4, 2), (13, 4, 1)])
+def test_tail_strips_cover_column_counts_that_are_not_multiples_of_four(ctx, oracle, ns, main, tail):
+    """A rotor's lattice with ns columns is covered by floor(ns/4) strips of width 4 plus ONE strip of width ns mod 4
+    (no padded columns) -- a second, small launch of the same kernel.  Same sums as the reference's ring-by-ring
+    enumeration: compared with the oracle on random targets and on the wake's own nodes (guarded pairs), for the current
+    and the predicted set; forcing one width with vlc_set_lattice_tuning gives the same velocities."""
+    from tests.test_gpu_parity import _make_rotor_pair, _tol_scale
+    ro = _make_rotor_pair(ctx, oracle, seed=40 + ns, ns=ns, nNwake=9, nFwake=4, rowNear=2, rowFar=2)
+    rng = np.random.default_rng(ns)
+    nodes = np.concatenate([ro.waN(ib)[:, 1:, 12:15].reshape(-1, 3) for ib in range(ro.nb)])     # corner 2 of the active rings
+    P = np.concatenate([rng.uniform(-1.5, 1.5, size=(300, 3)), nodes])
+    s = _tol_scale(ro, P) * 50
+    res = {}
+    for pred in (False, True):
+        info = ctx.rotor_info(0, pred)
+        assert info["shared_active"] == 1 and info["strip_width"] == main and info["tail_strip_width"] == tail, info
+        assert info["lattice_records"] == ro.nb * (ns // 4 + (1 if tail else 0)) * (8 + 1), info
+        res[pred] = ctx.rotor_vind_bywake(0, P, pred)
+        assert np.max(np.abs(res[pred] - ro.vind_points(1, P, pred))) < TOL * s
+    assert np.max(np.abs(ctx.rotor_vind(0, P) - ro.vind_points(2, P))) < TOL * s
+    try:
+        ctx.set_lattice_tuning(2, 0)                 # one width for every strip (the last one padded when ns is odd)
+        ro = _make_rotor_pair(ctx, oracle, seed=40 + ns, ns=ns, nNwake=9, nFwake=4, rowNear=2, rowFar=2)
+        info = ctx.rotor_info(0)
+        assert info["strip_width"] == 2 and info["tail_strip_width"] == 0 and info["shared_active"] == 1, info
+        assert np.max(np.abs(ctx.rotor_vind_bywake(0, P) - res[False])) < TOL * s
+    finally:
+        ctx.set_lattice_tuning(0, 0)

@@ -478,16 +478,16 @@ class Context:
         self._ck(self.lib.vlc_set_lattice_tuning(self.h, strip_width, targets_per_thread))
 
     def set_info(self, set_: int) -> dict:
-        out = (C.c_int64 * 5)()
+        out = (C.c_int64 * 6)()
         self._ck(self.lib.vlc_set_info(self.h, set_, out))
         return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3],
-                "strip_width": out[4]}
+                "strip_width": out[4], "tail_strip_width": out[5]}
 
     def rotor_info(self, ir: int, predicted: bool = False) -> dict:
-        out = (C.c_int64 * 5)()
+        out = (C.c_int64 * 6)()
         self._ck(self.lib.vlc_rotor_info(self.h, ir, int(predicted), out))
         return {"filaments": out[0], "lattice_records": out[1], "remainder_filaments": out[2], "shared_active": out[3],
-                "strip_width": out[4]}
+                "strip_width": out[4], "tail_strip_width": out[5]}
 
     def last_sweep_ms(self) -> tuple[float, float]:
         a, b = C.c_double(), C.c_double()

@@ -53,6 +53,10 @@ struct SourceSet {
   DevBuf lat;
   long long n_lat = 0, n_lat_pad = 0;  // strip records, padded to lat_tile(lat_W)
   int lat_W = 1;                       // strip width the records were packed with
+  // optional tail strips of another width (tier 2: ns = 4*floor(ns/4) + tail): same record kind, own buffer
+  DevBuf lat2;
+  long long n_lat2 = 0, n_lat2_pad = 0;
+  int lat2_W = 0;
   DevBuf rem;
   long long n_rem = 0, n_rem_pad = 0;  // filaments no strip covers (last column, horseshoe, far chain)
   int* d_unmergeable = nullptr;        // device flag raised by the pack kernels
@@ -313,6 +317,29 @@ inline int auto_strip_width(const vlc_ctx* c, int ns) {
   }
   return best;
 }
+// Strip cover of a lattice with ns ring columns: one width for all strips (the last one padded), or -- when nothing was
+// forced by vlc_set_lattice_tuning -- width-4 strips plus ONE tail strip of width ns mod 4 with no padding at all,
+// whichever costs less per ring (kLatCost; the tail is a second, small launch: +0.5 % to prefer the single cover on ties).
+struct StripPlan {
+  int W = 1, tailW = 0, nmain = 0;  // nmain strips of width W, then (tailW > 0) one strip of width tailW
+};
+inline StripPlan plan_strips(const vlc_ctx* c, int ns) {
+  StripPlan p;
+  p.W = auto_strip_width(c, ns);
+  p.nmain = (ns + p.W - 1) / p.W;
+  if (c->lat_W >= 1 && c->lat_W <= 4) return p;
+  const int t = ns % 4;
+  if (ns > 4 && t != 0) {
+    const double single = kLatCost[p.W] * (double)(p.nmain * p.W) / (double)ns;
+    const double mixed = (kLatCost[4] * (double)(ns - t) + kLatCost[t] * (double)t) / (double)ns + 0.005;
+    if (mixed < single) {
+      p.W = 4;
+      p.nmain = ns / 4;
+      p.tailW = t;
+    }
+  }
+  return p;
+}
 inline int lat_tile_of(int W) { return vlc::lat_tile(W); }
 inline int lat_rd_of(int W) { return vlc::lat_rec_doubles(W); }
 inline size_t lat_smem_of(int W) { return (size_t)kStages * lat_tile_of(W) * lat_rd_of(W) * 8 + kStages * sizeof(uint64_t); }
@@ -389,8 +416,20 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   const FlatPlan pr = s.n_rem_pad > 0 ? plan_flat(c, m, s.n_rem_pad) : FlatPlan();
   const FlatPlan pf = plan_flat(c, m, s.n_pad);
   const int ns_r = s.n_rem_pad > 0 ? pr.nsplit : 0;
+  // tail strips of another width (plan_strips): a second, small lattice launch with its own split
+  const int LW2 = s.n_lat2_pad > 0 ? s.lat2_W : 0;
+  int LT2 = LW2 ? kLatBestT[LW2] : 1, ns_l2 = 0;
+  long long lat2_chunk_tiles = 0;
+  if (LW2) {
+    if (m <= kLatThreads) LT2 = 1;
+    while (LT2 > 1 && !lat_shape_exists(LW2, LT2)) --LT2;
+    const long long tiles2 = s.n_lat2_pad / lat_tile_of(LW2);
+    ns_l2 = plan_lattice_split(c, LW2, LT2, m, s.n_lat2_pad);
+    lat2_chunk_tiles = (tiles2 + ns_l2 - 1) / ns_l2;
+    ns_l2 = (int)((tiles2 + lat2_chunk_tiles - 1) / lat2_chunk_tiles);
+  }
   const size_t len = 3 * (size_t)m;
-  int rc = reserve(c, c->part, (size_t)(ns_l + ns_r + pf.nsplit) * len);
+  int rc = reserve(c, c->part, (size_t)(ns_l + ns_l2 + ns_r + pf.nsplit) * len);
   if (rc) return rc;
   double* part = c->part.p;
   const bool side = (c->aux != nullptr);
@@ -416,8 +455,22 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
     CUDA_OK(c, cudaStreamWaitEvent(c->aux, c->ev_fork, 0));  // ev_fork was recorded BEFORE the lattice kernel
     c->stream = c->aux;
   }
-  if (ns_r > 0) rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part + (size_t)ns_l * len, s.d_unmergeable, 0);
-  if (!rc) rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part + (size_t)(ns_l + ns_r) * len, s.d_unmergeable, 1);
+  if (LW2) {
+    dim3 grid(blocks_for(m, kLatThreads * LT2), (unsigned)ns_l2, 1);
+    const long long chunk2 = lat2_chunk_tiles * lat_tile_of(LW2);
+#define X(WW, TT, MB)                                                                                       \
+  if (LW2 == WW && LT2 == TT)                                                                               \
+    vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>( \
+        s.lat2.p, chunk2, s.n_lat2_pad, dP, m, part + (size_t)ns_l * len, s.d_unmergeable, 0);
+    VLC_LAT_SHAPES(X)
+#undef X
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  if (ns_r > 0)
+    rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part + (size_t)(ns_l + ns_l2) * len, s.d_unmergeable, 0);
+  if (!rc)
+    rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part + (size_t)(ns_l + ns_l2 + ns_r) * len, s.d_unmergeable, 1);
   c->stream = main_stream;
   if (rc) return rc;
   if (side) {
@@ -425,7 +478,7 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
     CUDA_OK(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));
   }
   vlc::bs_reduce_select_kernel<<<blocks_for((long long)len, 256), 256, 0, c->stream>>>(
-      part, s.d_unmergeable, ns_l + ns_r, pf.nsplit, (long long)len, dV);
+      part, s.d_unmergeable, ns_l + ns_l2 + ns_r, pf.nsplit, (long long)len, dV);
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   cudaEventRecord(c->ev[2], c->stream);
@@ -545,12 +598,17 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   // ---- shared-node form of the near wake (bs_lattice.cuh): strips per blade + [wing | remainder] flat ----
   SourceSet& cs = r.comb[s];
   cs.has_shared = false;
-  cs.n_lat = cs.n_lat_pad = cs.n_rem = cs.n_rem_pad = 0;
+  cs.n_lat = cs.n_lat_pad = cs.n_rem = cs.n_rem_pad = cs.n_lat2 = cs.n_lat2_pad = 0;
+  cs.lat2_W = 0;
   if (nrows > 0 && c->shared_nodes) {
-    const int LW = auto_strip_width(c, r.ns), RD = lat_rd_of(LW), nstrips = (r.ns + LW - 1) / LW;
+    const StripPlan sp = plan_strips(c, r.ns);
+    const int LW = sp.W, RD = lat_rd_of(LW), nstrips = sp.nmain;
     const long long lat_n = (long long)r.nb * nstrips * (nrows + 1);
     const long long lat_pad = pad_lat(lat_n, LW);
     cs.lat_W = LW;
+    const int TW = sp.tailW, RD2 = TW ? lat_rd_of(TW) : 0;  // one tail strip per blade
+    const long long lat2_n = TW ? (long long)r.nb * (nrows + 1) : 0, lat2_pad = TW ? pad_lat(lat2_n, TW) : 0;
+    if (TW && (rc = reserve(c, cs.lat2, (size_t)lat2_pad * RD2))) return rc;
     long long rem_per_blade = nrows;  // streamwise edges of the last column
     if (has_far) rem_per_blade += r.ns + nfar + (r.have_pf[s] ? VLC_NPFWAKE : 0);
     const long long rem_wake = rem_per_blade * r.nb;
@@ -573,9 +631,19 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
 #define X(WW)                                                                                                 \
   if (LW == WW)                                                                                               \
     vlc::pack_rings_shared_kernel<WW><<<blocks_for(nrec, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, \
-                                                                             nrows, r.ns, lrec, cs.d_unmergeable);
+                                                                             nrows, r.ns, 0, nstrips, lrec, cs.d_unmergeable);
       X(1) X(2) X(3) X(4)
 #undef X
+      if (TW) {  // the tail strip: columns nstrips*LW .. ns-1
+        double* trec = cs.lat2.p + (size_t)ib * (nrows + 1) * RD2;
+#define X(WW)                                                                                                      \
+  if (TW == WW)                                                                                                    \
+    vlc::pack_rings_shared_kernel<WW><<<blocks_for(nrows + 1, 128), 128, 0, st>>>(                                 \
+        waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, nstrips * LW, 1, trec, cs.d_unmergeable);
+        X(1) X(2) X(3)
+#undef X
+        c->launches++;
+      }
       // last column: f3 of ring (i, ns-1), wake rule applies (classdef.f90:1452)
       vlc::pack_rings_kernel<<<blocks_for(nrows, 128), 128, 0, st>>>(
           waN + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr, r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1,
@@ -608,6 +676,15 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
 #undef X
       c->launches++;
     }
+    if (lat2_pad > lat2_n) {
+#define X(WW)                                                                                           \
+  if (TW == WW)                                                                                         \
+    vlc::pack_null_lat_kernel<WW><<<blocks_for(lat2_pad - lat2_n, 128), 128, 0, st>>>(lat2_pad - lat2_n, \
+                                                                                       cs.lat2.p + (size_t)lat2_n * RD2);
+      X(1) X(2) X(3)
+#undef X
+      c->launches++;
+    }
     if (pad_tile(rem_wake) > roff) {
       vlc::pack_null_kernel<<<blocks_for(pad_tile(rem_wake) - roff, 256), 256, 0, st>>>(
           pad_tile(rem_wake) - roff, rrec + (size_t)roff * vlc::kSrcDoubles);
@@ -616,6 +693,9 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     CUDA_OK(c, cudaGetLastError());
     cs.n_lat = lat_n;
     cs.n_lat_pad = lat_pad;
+    cs.n_lat2 = lat2_n;
+    cs.n_lat2_pad = lat2_pad;
+    cs.lat2_W = TW;
     cs.n_rem = wing_n + rem_wake;
     cs.n_rem_pad = rem_pad;
     cs.has_shared = true;
@@ -755,6 +835,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   for (auto& s : c->sets) {
     release(s.rec);
     release(s.lat);
+    release(s.lat2);
     release(s.rem);
     if (s.d_unmergeable) cudaFree(s.d_unmergeable);
   }
@@ -775,6 +856,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
       release(r.wapF[s]);
       release(r.comb[s].rec);
       release(r.comb[s].lat);
+      release(r.comb[s].lat2);
       release(r.comb[s].rem);
       if (r.comb[s].d_unmergeable) cudaFree(r.comb[s].d_unmergeable);
     }
@@ -867,7 +949,7 @@ extern "C" int vlc_set_sources_dev(vlc_ctx* c, int set, int64_t n, const double*
   s.n = n;
   s.n_pad = n_pad;
   s.has_shared = false;
-  s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = 0;
+  s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = s.n_lat2 = s.n_lat2_pad = 0;
   return VLC_OK;
 }
 
@@ -1006,6 +1088,7 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     for (int s = 0; s < 2 && nNwake > 0; ++s) {
       if ((rc = reserve(c, r.comb[s].rec, (size_t)(wing_pad + pad_tile(wake_n)) * vlc::kSrcDoubles))) return rc;
       if ((rc = reserve(c, r.comb[s].lat, lat_doubles))) return rc;
+      if ((rc = reserve(c, r.comb[s].lat2, (size_t)pad_lat((long long)nb * (nNwake + 1), 3) * lat_rd_of(3)))) return rc;
       if ((rc = reserve(c, r.comb[s].rem, (size_t)(wing_pad + pad_tile(rem_n)) * vlc::kSrcDoubles))) return rc;
     }
   }
@@ -1840,7 +1923,7 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
 
   // ---- shared-node form of the same lattice: strip records + flat remainder (bs_lattice.cuh) ----
   if (!append) {
-    s.n_lat = s.n_rem = 0;
+    s.n_lat = s.n_rem = s.n_lat2 = s.n_lat2_pad = 0;
     s.has_shared = true;
     s.lat_W = auto_strip_width(c, ns);  // lattices appended later share the record width of the first one
     if (!s.d_unmergeable) CUDA_OK(c, cudaMalloc(&s.d_unmergeable, sizeof(int)));
@@ -1947,10 +2030,11 @@ extern "C" int vlc_set_info(vlc_ctx* c, int set, int64_t* out) {
   if (!out) return fail(c, VLC_ERR_ARG, "null pointer");
   const SourceSet& s = c->sets[set];
   out[0] = s.n;
-  out[1] = s.has_shared ? s.n_lat : 0;
+  out[1] = s.has_shared ? s.n_lat + s.n_lat2 : 0;
   out[2] = s.has_shared ? s.n_rem : 0;
   out[3] = -1;
   out[4] = s.has_shared ? s.lat_W : 0;
+  out[5] = s.has_shared ? s.lat2_W : 0;
   if (s.has_shared && s.d_unmergeable) {
     int f = 0;
     CUDA_OK(c, cudaMemcpyAsync(&f, s.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1971,10 +2055,11 @@ extern "C" int vlc_rotor_info(vlc_ctx* c, int ir, int predicted, int64_t* out) {
   if ((rc = pack_rotor(c, *r, s))) return rc;
   const SourceSet& cs = r->comb[s];
   out[0] = cs.n;
-  out[1] = cs.has_shared ? cs.n_lat : 0;
+  out[1] = cs.has_shared ? cs.n_lat + cs.n_lat2 : 0;
   out[2] = cs.has_shared ? cs.n_rem : 0;
   out[3] = -1;
   out[4] = cs.has_shared ? cs.lat_W : 0;
+  out[5] = cs.has_shared ? cs.lat2_W : 0;
   if (cs.has_shared && cs.d_unmergeable) {
     int f = 0;
     CUDA_OK(c, cudaMemcpyAsync(&f, cs.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -2105,7 +2190,7 @@ extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyz
   s.n = n;
   s.n_pad = n_pad;
   s.has_shared = false;
-  s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = 0;
+  s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = s.n_lat2 = s.n_lat2_pad = 0;
   // targets = cell centres, computed on the device with the file's arithmetic
   const long long m = (long long)(nx - 1) * (ny - 1) * (nz - 1);
   if ((rc = reserve(c, c->stage_P, 3 * (size_t)m))) return rc;

@@ -200,10 +200,9 @@ __device__ __forceinline__ void write_edge(double* __restrict__ e, const double*
 }
 
 template <int W, class Acc>
-__device__ __forceinline__ void fill_strip_record(const Acc& acc, int nrows, int ns, int strip, int rr,
+__device__ __forceinline__ void fill_strip_record(const Acc& acc, int nrows, int ns, int c0, int rr,
                                                   double* __restrict__ rec, int* __restrict__ unmergeable) {
-  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2;
-  const int c0 = strip * W;
+  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2;  // c0 = first ring column of the strip (global column index)
   auto G = [&](int r, int j) -> double {
     return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(acc.gam(r, j), true) : 0.0;
   };
@@ -297,7 +296,7 @@ __global__ void pack_lattice_shared_kernel(int nrows, int ns, const double* __re
   const int nr1 = nrows + 1, nstrips = (ns + W - 1) / W;
   if (q >= (long long)nstrips * nr1) return;
   const LatticeAcc acc{nodes, gam, rvc4, nrows, ns};
-  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1), (int)(q % nr1), rec + q * RD, unmergeable);
+  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable);
 }
 
 // Streamwise edges of the last column (f3 of ring (r, ns-1): corner 3 -> corner 4), which no strip covers.
@@ -374,15 +373,18 @@ struct RingsAcc {
   __device__ __forceinline__ double rvc(int r, int j, int f) const { return ring(r, j)[kVf * f + kVfRvc]; }
 };
 
+// nstrips strips of width W starting at ring column col_base (a lattice may be covered by strips of two widths:
+// ns = 4*floor(ns/4) columns of width-4 strips + one tail strip of width ns mod 4, capi.cu: plan_strips).
 template <int W>
 __global__ void pack_rings_shared_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows,
-                                         int ns, double* __restrict__ rec, int* __restrict__ unmergeable) {
+                                         int ns, int col_base, int nstrips, double* __restrict__ rec,
+                                         int* __restrict__ unmergeable) {
   constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 10 * W;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nr1 = nrows + 1, nstrips = (ns + W - 1) / W;
+  const int nr1 = nrows + 1;
   if (q >= (long long)nstrips * nr1) return;
   const RingsAcc acc{base, stride, ld, i0, nrows, ns};
-  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1), (int)(q % nr1), rec + q * RD, unmergeable);
+  fill_strip_record<W>(acc, nrows, ns, col_base + (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable);
 }
 
 
