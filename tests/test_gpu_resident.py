@@ -242,13 +242,21 @@ def _short_caradonna(fx):
     fx["geom"][0]["nNwake"] = 12
 
 
+def _init_wake_vel(fx):
+    _short_caradonna(fx)
+    fx["config"].update(initWakeVelNt=8, wakeStrain=1, fdScheme=1)
+    fx["geom"][0].update(initWakeVel=-3.0)
+
+
 # elevateTest amplifies rounding differences far more than the other cases (5 blades' wakes rolling up into each other:
 # the non-resident GPU run measures 1.6e-9 on CT after 50 steps too, tests/test_gpu_case.py), hence its wake tolerance
 @pytest.mark.parametrize("name,nsteps,mutate,wake_tol",
                          [("simplewing", 40, None, 1e-9), ("tr1208", 30, None, 1e-9),
                           ("caradonna", 30, _short_caradonna, 1e-9),
                           ("elevateTest", 40, lambda fx: fx["config"].update(fdScheme=1), 1e-5),
-                          ("katzNplotkin_AR04", 30, lambda fx: fx["config"].update(fdScheme=0), 1e-9)])
+                          ("katzNplotkin_AR04", 30, lambda fx: fx["config"].update(fdScheme=0), 1e-9),
+                          # initial wake velocity along the shaft axis with the reference's signs, strain on
+                          ("caradonna", 20, _init_wake_vel, 1e-9)])
 def test_resident_vs_cpu_driver(ctx, oracle, name, nsteps, mutate, wake_tol):
     """CL/CT, circulation and the wake itself (downloaded at the end) against the CPU driver: the remaining BASELINE
     configs, and the other two time-marching schemes (fdScheme 1 predictor-corrector, 0 explicit Euler)."""

@@ -56,6 +56,7 @@ def main():
     out = np.nonzero(ps > 3 * med)[0]
     print(f"steps slower than 3x their neighbourhood median: {len(out)}, {ps[out].sum():.2f} s in total; "
           + ", ".join(f"{i + 1}:{ps[i] * 1e3:.0f}ms" for i in out[:30]))
+    print(f"kernel launches: {ctx.launch_count} = {ctx.launch_count / nt:.0f} per step")
     print(f"total {nt} steps in {t2 - t1:.2f} s = {nt / (t2 - t1):.2f} timesteps/s, {pairs:.3e} pair interactions "
           f"({pairs / (t2 - t1):.3e}/s incl. all host work), {lib.case_gpu_hooks_uploads(h)} uploads")
 

@@ -537,14 +537,15 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   if (rc) return rc;
   double* rec = r.comb[s].rec.p;
   cudaStream_t st = c->stream;
+  // one launch per kernel type for ALL blades (blockIdx.y = blade): their arrays and record blocks are equally spaced
+  auto grid2 = [&](long long n, int t) { return dim3(blocks_for(n, t), (unsigned)r.nb, 1); };
+  const long long wiP_blade = (long long)r.nc * r.ns * vlc::kWp, waN_blade = (long long)r.nNwake * r.ns * vlc::kVr;
+  const long long waF_blade = (long long)r.nFwake * vlc::kFw, wapF_blade = (long long)VLC_NPFWAKE * vlc::kFw;
   if (wing_n > 0) {
-    for (int ib = 0; ib < r.nb; ++ib) {
-      const long long cnt = 4LL * r.nc * r.ns;
-      vlc::pack_rings_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(
-          r.wiP.p + (size_t)ib * r.nc * r.ns * vlc::kWp, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0,
-          rec + (size_t)ib * cnt * vlc::kSrcDoubles);
-      c->launches++;
-    }
+    const long long cnt = 4LL * r.nc * r.ns;
+    vlc::pack_rings_kernel<<<grid2(cnt, 256), 256, 0, st>>>(r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0, rec,
+                                                            wiP_blade, cnt);
+    c->launches++;
   }
   if (wing_pad > wing_n) {
     vlc::pack_null_kernel<<<blocks_for(wing_pad - wing_n, 256), 256, 0, st>>>(wing_pad - wing_n,
@@ -552,35 +553,34 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     c->launches++;
   }
   double* wrec = rec + (size_t)wing_pad * vlc::kSrcDoubles;
-  long long off = 0;
-  for (int ib = 0; ib < r.nb && r.nNwake > 0; ++ib) {
-    const double* waN = r.waN[s].p + (size_t)ib * r.nNwake * r.ns * vlc::kVr;
+  long long off = 0;  // records of one blade's block written so far; the blocks are wake_per_blade apart
+  if (r.nNwake > 0) {
     if (nrows > 0) {
       const long long cnt = 4LL * nrows * r.ns;
-      vlc::pack_rings_kernel<<<blocks_for(cnt, 256), 256, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows,
-                                                                    r.ns, 0xF, 4, 1.0, 1,
-                                                                    wrec + (size_t)off * vlc::kSrcDoubles);
+      vlc::pack_rings_kernel<<<grid2(cnt, 256), 256, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, 0xF, 4,
+                                                              1.0, 1, wrec, waN_blade, wake_per_blade);
       c->launches++;
       off += cnt;
     }
     if (has_far) {
       // horseshoe correction: -vf(2) of the last near row, no gam rule (classdef.f90:1460-1463)
-      vlc::pack_rings_kernel<<<blocks_for(r.ns, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns,
-                                                                     0x2, 1, -1.0, 0,
-                                                                     wrec + (size_t)off * vlc::kSrcDoubles);
-      c->launches++;
+      vlc::pack_rings_kernel<<<grid2(r.ns, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2, 1,
+                                                               -1.0, 0, wrec + (size_t)off * vlc::kSrcDoubles, waN_blade,
+                                                               wake_per_blade);
       off += r.ns;
-      vlc::pack_fwake_kernel<<<blocks_for(nfar, 128), 128, 0, st>>>(
-          r.waF[s].p + (size_t)ib * r.nFwake * vlc::kFw, r.rowFar - 1, nfar, wrec + (size_t)off * vlc::kSrcDoubles);
-      c->launches++;
+      vlc::pack_fwake_kernel<<<grid2(nfar, 128), 128, 0, st>>>(r.waF[s].p, r.rowFar - 1, nfar,
+                                                               wrec + (size_t)off * vlc::kSrcDoubles, waF_blade, wake_per_blade);
       off += nfar;
+      c->launches += 2;
       if (r.have_pf[s]) {
-        vlc::pack_fwake_kernel<<<blocks_for(VLC_NPFWAKE, 128), 128, 0, st>>>(
-            r.wapF[s].p + (size_t)ib * VLC_NPFWAKE * vlc::kFw, 0, VLC_NPFWAKE, wrec + (size_t)off * vlc::kSrcDoubles);
+        vlc::pack_fwake_kernel<<<grid2(VLC_NPFWAKE, 128), 128, 0, st>>>(r.wapF[s].p, 0, VLC_NPFWAKE,
+                                                                        wrec + (size_t)off * vlc::kSrcDoubles, wapF_blade,
+                                                                        wake_per_blade);
         c->launches++;
         off += VLC_NPFWAKE;
       }
     }
+    off = wake_per_blade * r.nb;  // all blades' blocks are written
   }
   const long long wake_pad = pad_tile(wake_n);
   if (wake_pad > off) {
@@ -621,51 +621,51 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
       CUDA_OK(c, cudaMemcpyAsync(cs.rem.p, rec, sizeof(double) * (size_t)wing_pad * vlc::kSrcDoubles,
                                  cudaMemcpyDeviceToDevice, st));
     double* rrec = cs.rem.p + (size_t)wing_pad * vlc::kSrcDoubles;
-    long long roff = 0;
-    for (int ib = 0; ib < r.nb; ++ib) {
-      const double* waN = r.waN[s].p + (size_t)ib * r.nNwake * r.ns * vlc::kVr;
+    long long roff = 0;  // within one blade's block of the remainder; blocks are rem_per_blade apart
+    {
       const long long nring = (long long)nrows * r.ns, nrec = (long long)nstrips * (nrows + 1);
-      vlc::check_rings_kernel<<<blocks_for(nring, 256), 256, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns,
-                                                                      cs.d_unmergeable);
-      double* lrec = cs.lat.p + (size_t)ib * nrec * RD;
-#define X(WW)                                                                                                 \
-  if (LW == WW)                                                                                               \
-    vlc::pack_rings_shared_kernel<WW><<<blocks_for(nrec, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.rowNear - 1, \
-                                                                             nrows, r.ns, 0, nstrips, lrec, cs.d_unmergeable);
+      vlc::check_rings_kernel<<<grid2(nring, 256), 256, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns,
+                                                                 cs.d_unmergeable, waN_blade);
+#define X(WW)                                                                                                       \
+  if (LW == WW)                                                                                                     \
+    vlc::pack_rings_shared_kernel<WW><<<grid2(nrec, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, \
+                                                                        r.ns, 0, nstrips, cs.lat.p, cs.d_unmergeable, waN_blade);
       X(1) X(2) X(3) X(4)
 #undef X
       if (TW) {  // the tail strip: columns nstrips*LW .. ns-1
-        double* trec = cs.lat2.p + (size_t)ib * (nrows + 1) * RD2;
-#define X(WW)                                                                                                      \
-  if (TW == WW)                                                                                                    \
-    vlc::pack_rings_shared_kernel<WW><<<blocks_for(nrows + 1, 128), 128, 0, st>>>(                                 \
-        waN, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, nstrips * LW, 1, trec, cs.d_unmergeable);
+#define X(WW)                                                                                                         \
+  if (TW == WW)                                                                                                       \
+    vlc::pack_rings_shared_kernel<WW><<<grid2(nrows + 1, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1,    \
+                                                                             nrows, r.ns, nstrips * LW, 1, cs.lat2.p,         \
+                                                                             cs.d_unmergeable, waN_blade);
         X(1) X(2) X(3)
 #undef X
         c->launches++;
       }
       // last column: f3 of ring (i, ns-1), wake rule applies (classdef.f90:1452)
-      vlc::pack_rings_kernel<<<blocks_for(nrows, 128), 128, 0, st>>>(
-          waN + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr, r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1,
-          rrec + (size_t)roff * vlc::kSrcDoubles);
+      vlc::pack_rings_kernel<<<grid2(nrows, 128), 128, 0, st>>>(r.waN[s].p + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr,
+                                                                r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1, rrec, waN_blade,
+                                                                rem_per_blade);
       roff += nrows;
       c->launches += 3;
       if (has_far) {
-        vlc::pack_rings_kernel<<<blocks_for(r.ns, 128), 128, 0, st>>>(waN, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2,
-                                                                       1, -1.0, 0, rrec + (size_t)roff * vlc::kSrcDoubles);
+        vlc::pack_rings_kernel<<<grid2(r.ns, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2, 1,
+                                                                 -1.0, 0, rrec + (size_t)roff * vlc::kSrcDoubles, waN_blade,
+                                                                 rem_per_blade);
         roff += r.ns;
-        vlc::pack_fwake_kernel<<<blocks_for(nfar, 128), 128, 0, st>>>(r.waF[s].p + (size_t)ib * r.nFwake * vlc::kFw,
-                                                                       r.rowFar - 1, nfar,
-                                                                       rrec + (size_t)roff * vlc::kSrcDoubles);
+        vlc::pack_fwake_kernel<<<grid2(nfar, 128), 128, 0, st>>>(r.waF[s].p, r.rowFar - 1, nfar,
+                                                                 rrec + (size_t)roff * vlc::kSrcDoubles, waF_blade, rem_per_blade);
         roff += nfar;
         c->launches += 2;
         if (r.have_pf[s]) {
-          vlc::pack_fwake_kernel<<<blocks_for(VLC_NPFWAKE, 128), 128, 0, st>>>(
-              r.wapF[s].p + (size_t)ib * VLC_NPFWAKE * vlc::kFw, 0, VLC_NPFWAKE, rrec + (size_t)roff * vlc::kSrcDoubles);
+          vlc::pack_fwake_kernel<<<grid2(VLC_NPFWAKE, 128), 128, 0, st>>>(r.wapF[s].p, 0, VLC_NPFWAKE,
+                                                                          rrec + (size_t)roff * vlc::kSrcDoubles, wapF_blade,
+                                                                          rem_per_blade);
           roff += VLC_NPFWAKE;
           c->launches++;
         }
       }
+      roff = rem_per_blade * r.nb;
     }
     if (lat_pad > lat_n) {
 #define X(WW)                                                                                        \

@@ -70,11 +70,16 @@ __global__ void pack_null_kernel(long long count, double* __restrict__ rec) {
 //   ring(i, j) at base + stride*(i + ld*j) doubles, i in [i0, i0+ni), j in [0, nj); 4 filaments each.
 //   Output order: j outer, i inner, filament innermost  (classdef.f90:1350-1355, :1450-1456).
 //   fil_mask selects filaments (bit f), sign scales gam.
+//   blockIdx.y = blade: source arrays and record blocks of the blades of a rotor are equally shaped and equally spaced
+//   (src_blade doubles, dst_blade records apart), so one launch packs them all (gridDim.y = 1 and 0, 0 otherwise).
 __global__ void pack_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int ni, int nj,
-                                  int fil_mask, int nfil, double sign, int wake, double* __restrict__ rec) {
+                                  int fil_mask, int nfil, double sign, int wake, double* __restrict__ rec,
+                                  long long src_blade = 0, long long dst_blade = 0) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)ni * nj * nfil;
   if (q >= total) return;
+  base += (size_t)blockIdx.y * src_blade;
+  rec += (size_t)blockIdx.y * dst_blade * kSrcDoubles;
   const int fsel = (int)(q % nfil);
   const long long ring = q / nfil;
   const int i = (int)(ring % ni) + i0;
@@ -93,9 +98,12 @@ __global__ void pack_rings_kernel(const double* __restrict__ base, int stride, i
 }
 
 // Far-wake / prescribed-wake filaments stored as Fwake_class records (13 doubles), i in [i0, i0+ni).
-__global__ void pack_fwake_kernel(const double* __restrict__ base, int i0, int ni, double* __restrict__ rec) {
+__global__ void pack_fwake_kernel(const double* __restrict__ base, int i0, int ni, double* __restrict__ rec,
+                                  long long src_blade = 0, long long dst_blade = 0) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= ni) return;
+  base += (size_t)blockIdx.y * src_blade;
+  rec += (size_t)blockIdx.y * dst_blade * kSrcDoubles;
   const double* fw = base + (size_t)kFw * (i0 + q);
   write_rec(rec + (size_t)q * kSrcDoubles, fw[0], fw[1], fw[2], fw[3], fw[4], fw[5], fw[kVfRvc],
             strength(fw[kFwGam], true));
@@ -334,9 +342,10 @@ __device__ __forceinline__ bool same3(const double* a, const double* b) {
 // assignshed, :4297-4325; to rounding for rotated axisymmetric copies).  Anything else raises the flag and the sweep
 // uses the flat enumeration.
 __global__ void check_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows, int ns,
-                                   int* __restrict__ unmergeable) {
+                                   int* __restrict__ unmergeable, long long src_blade = 0) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (long long)nrows * ns) return;
+  base += (size_t)blockIdx.y * src_blade;
   const int r = (int)(q % nrows), j = (int)(q / nrows);
   const double* g = ring_ptr(base, stride, ld, i0, r, j);
   bool ok = true;
@@ -378,11 +387,13 @@ struct RingsAcc {
 template <int W>
 __global__ void pack_rings_shared_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows,
                                          int ns, int col_base, int nstrips, double* __restrict__ rec,
-                                         int* __restrict__ unmergeable) {
+                                         int* __restrict__ unmergeable, long long src_blade = 0) {
   constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 10 * W;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nr1 = nrows + 1;
   if (q >= (long long)nstrips * nr1) return;
+  base += (size_t)blockIdx.y * src_blade;          // blade blockIdx.y: its records follow the previous blade's
+  rec += (size_t)blockIdx.y * nstrips * nr1 * RD;
   const RingsAcc acc{base, stride, ld, i0, nrows, ns};
   fill_strip_record<W>(acc, nrows, ns, col_base + (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable);
 }

@@ -58,7 +58,8 @@ __device__ __forceinline__ double rsqrt_fp64(double x) {
 // sc <- (c2 > eps^2) ? sc : 0 without touching the FP64 pipe.  VLC_GUARD_HI (default): only the HIGH word of sc is
 // selected (one SEL instead of two): a guarded sc becomes {lo, 0} = a denormal < 2^-1042 (whatever sc was, NaN and
 // Inf included), and every |c_i| <= 2^-52 there (c2 <= 2^-104), so |c_i * sc| < 2^-1094 rounds to zero in the three
-// accumulates that consume it: the same velocities (up to the sign of an exact zero), one issue slot fewer.
+// accumulates that consume it: the same velocities (up to the sign of an exact zero), one instruction fewer (worth 0.2 %: the kernels are bound by
+// register-operand bandwidth of the FP64 unit, not by issue slots, profiles/r01h_fp64_operands.md).
 // (Predicating the seed instruction instead -- `@p rsqrt.approx` into a zeroed pair -- is if-converted by ptxas into
 // MUFU + FSEL + MOV: no gain, tried.)
 #ifndef VLC_GUARD_HI
@@ -125,7 +126,7 @@ __device__ __forceinline__ void pair_accumulate(const Src& s, double px, double 
   double sc = fma(a1, w1, -(a2 * w2));
   // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`: c2 >= 0, so its bit pattern orders like an integer;
   // eps^2 = 2^-104 = 0x3970000000000000.  One 64-bit integer compare + one select keep the guard off
-  // the FP64 pipe (each FP64 instruction costs two issue cycles, an integer one costs one).
+  // the FP64 pipe.
   guard_scale(sc, c2);
   vx = fma(cx, sc, vx);
   vy = fma(cy, sc, vy);
