@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--lat-t", type=int, default=0, help="targets per thread of the shared-node kernel, 1..3 (0 = default)")
     ap.add_argument("--flat", action="store_true",
                     help="force the flat kernel on the reference's enumeration (default: shared-node lattice kernel)")
+    ap.add_argument("--graph", action="store_true",
+                    help="1 GPU only: capture the time step in a CUDA graph and replay it (launch-bound small wakes: ~215 "
+                         "launches per step); the per-kernel roofline is then taken from one eager step after the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -328,6 +331,23 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    use_graph = bool(args.graph and world == 1)
+    graph = None
+    if use_graph:
+        # The whole step (library launches on the context's stream, its side-stream fork/join, torch copies) is captured
+        # once and replayed: one cudaGraphLaunch per time step instead of ~215 kernel launches.
+        gstream = torch.cuda.Stream()
+        gstream.wait_stream(stream)
+        ctx.set_stream(gstream.cuda_stream)
+        launches_before = ctx.launch_count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=gstream):
+            step()
+        launches_per_step = ctx.launch_count - launches_before
+        stream = gstream
+        with torch.cuda.stream(gstream):
+            graph.replay()                                   # warm replay
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -335,13 +355,22 @@ def main():
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record(stream)
-    for _ in range(args.steps):
-        step(record=True)
+    if use_graph:
+        with torch.cuda.stream(stream):
+            for _ in range(args.steps):
+                graph.replay()
+    else:
+        for _ in range(args.steps):
+            step(record=True)
     t1.record(stream)
     barrier()
     elapsed_ms = t0.elapsed_time(t1)
-    launches = ctx.launch_count - launches0
+    launches = (launches_per_step * args.steps) if use_graph else (ctx.launch_count - launches0)
     clocks = sampler.stop() if rank == 0 else None
+    if use_graph:                                            # per-kernel timings for the roofline: one eager step
+        with torch.cuda.stream(stream):
+            step(record=True)
+        torch.cuda.synchronize()
     sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)])) if ev_k0 else 0.0
     # dominant kernel alone (CUDA events recorded by the library on the launching stream around that launch, last step)
     main_ms, total_ms = ctx.last_sweep_ms() if m_loc > 0 else (0.0, 0.0)
@@ -459,6 +488,9 @@ def main():
                               "predicted wake, AM2 corrector + all-gather",
                       "l2": "flushed every step by a 256 MiB memset inside the timed region",
                       "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather per stage (2 per step)",
+                      "launch": ("the step is captured once in a CUDA graph and replayed (one graph launch per time step); "
+                                 "roofline kernel times from one eager step after the timed region") if use_graph
+                                else "eager: one stream, every kernel launched per step",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
                       "sources": ({"form": "shared-node lattice", "strip_width": int(info["strip_width"]),
                                    "strip_records": int(info["lattice_records"]),
