@@ -27,8 +27,8 @@ def kernel_instructions(path, name):
     return ins
 
 
-def main():
-    path, name = sys.argv[1], sys.argv[2]
+def analyse(path, name):
+    """-> dict(n_fp64, n_other, by={(op, distinct regs): count}, cycles, bound, other=Counter, reuse, loop=(lo, hi))"""
     ins = kernel_instructions(path, name)
     loops = []
     for a, t in ins:
@@ -62,6 +62,14 @@ def main():
             other[op] += 1
     n = sum(by.values())
     cycles = sum(v * (3 if k[1] == 3 else 2) for k, v in by.items())
+    return dict(n_fp64=n, n_other=sum(other.values()), by=dict(by), cycles=cycles, bound=2 * n / cycles, other=other,
+                reuse=reuse, loop=(lo, hi))
+
+
+def main():
+    path, name = sys.argv[1], sys.argv[2]
+    a = analyse(path, name)
+    n, cycles, by, other, reuse, (lo, hi) = a["n_fp64"], a["cycles"], a["by"], a["other"], a["reuse"], a["loop"]
     print(f"{name}: loop 0x{lo:x}..0x{hi:x}, {n} FP64 instructions, {sum(other.values())} others, {reuse} .reuse operands")
     for k in sorted(by):
         print(f"  {k[0]} with {k[1]} distinct source register(s): {by[k]}")
