@@ -725,17 +725,12 @@ int pack_bound(vlc_ctx* c, Rotor& r) {
   int rc = reserve(c, r.bound.rec, (size_t)n_pad * vlc::kSrcDoubles);
   if (rc) return rc;
   double* rec = r.bound.rec.p;
-  long long off = 0;
-  for (int ib = 0; ib < r.nb; ++ib) {
-    const double* wiP = r.wiP.p + (size_t)ib * r.nc * r.ns * vlc::kWp;
-    const long long cnt = 2LL * r.nc * r.ns;
-    vlc::pack_rings_kernel<<<blocks_for(cnt, 256), 256, 0, c->stream>>>(wiP, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xA, 2,
-                                                                         1.0, 0, rec + (size_t)off * vlc::kSrcDoubles);
-    off += cnt;
-    vlc::pack_rings_kernel<<<blocks_for(r.ns, 128), 128, 0, c->stream>>>(wiP, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2,
-                                                                          1, -1.0, 0,
-                                                                          rec + (size_t)off * vlc::kSrcDoubles);
-    off += r.ns;
+  {  // one launch per kernel type for all blades (blockIdx.y = blade), blocks of per_blade records
+    const long long cnt = 2LL * r.nc * r.ns, wiP_blade = (long long)r.nc * r.ns * vlc::kWp;
+    vlc::pack_rings_kernel<<<dim3(blocks_for(cnt, 256), (unsigned)r.nb, 1), 256, 0, c->stream>>>(
+        r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xA, 2, 1.0, 0, rec, wiP_blade, per_blade);
+    vlc::pack_rings_kernel<<<dim3(blocks_for(r.ns, 128), (unsigned)r.nb, 1), 128, 0, c->stream>>>(
+        r.wiP.p, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2, 1, -1.0, 0, rec + (size_t)cnt * vlc::kSrcDoubles, wiP_blade, per_blade);
     c->launches += 2;
   }
   if (n_pad > n) {
