@@ -185,6 +185,17 @@ int vlc_rotor_rollup(vlc_ctx* ctx, int ir);
  * vel{N,F}wake[Predicted](active rows) of every convected blade <- sum over source rotors of
  * vind_on{N,F}wake_byRotor; addInitWakeVel != 0 adds -/+ initWakeVel*shaftAxis with the reference's signs. */
 int vlc_wake_sweep(vlc_ctx* ctx, int predicted, int addInitWakeVel);
+/* The same in three parts, for one process per GPU (targets are independent, libCommon.f90:132-139): every rank keeps
+ * the whole wake (the O(N) mutators above run redundantly), sweeps only ITS slice of the target list against all
+ * sources, the ranks all-gather the velocity slices (NCCL, 24 bytes per target), and every rank scatters the complete
+ * list into its velocity arrays -- one exchange per wake sweep, i.e. one per predictor and one per corrector stage.
+ *   vlc_wake_sweep_count  : M = wake-node + far-wake targets of all convected blades at the current row counters
+ *   vlc_wake_sweep_slice  : velocities of targets [first, first+count) into d_vel(3, M) (device) at those positions
+ *   vlc_wake_sweep_scatter: d_vel(3, M) -> velNwake / velFwake [Predicted] (+- initWakeVel), as vlc_wake_sweep does
+ * vlc_wake_sweep(ctx, p, a) == count; slice(0, M) into an internal buffer; scatter. */
+int vlc_wake_sweep_count(vlc_ctx* ctx, int64_t* M);
+int vlc_wake_sweep_slice(vlc_ctx* ctx, int predicted, int64_t first, int64_t count, double* d_vel);
+int vlc_wake_sweep_scatter(vlc_ctx* ctx, int predicted, int addInitWakeVel, const double* d_vel);
 /* Bookkeeping of the velocity arrays between the sweeps (convected blades, whole arrays like the reference). */
 enum {
   VLC_VEL_FIRST_STEP = 0,    /* main.f90:1013-1020  vel1 = vel                                         */

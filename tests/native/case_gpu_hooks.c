@@ -30,6 +30,14 @@ typedef struct {
   int resident, resident_started;
   long wing_uploads;
   const struct resident_ops *ops; /* who executes the wake stages: the C ABI (GPU) or the oracle's own mutators (CPU) */
+  /* one process per GPU (world > 1): this rank sweeps targets [rank*per, (rank+1)*per) and `exchange` all-gathers the
+   * velocity slices in xbuf (device, (3, world*per_max)); set by case_gpu_hooks_set_sharding */
+  int world, rank;
+  double *xbuf;
+  long xbuf_targets;
+  int (*exchange)(void *arg, long per);
+  void *exchange_arg;
+  long exchanges;
 } gpu_user_t;
 
 /* The wake stages of one time step, as the orchestration below calls them.  Two backends: `gpu_ops` forwards each to the
@@ -171,7 +179,22 @@ static int g_strain(gpu_user_t *u, int ir) { return vlc_rotor_strain_wake(u->ctx
 static int g_to_pred(gpu_user_t *u, int ir) { return vlc_rotor_wake_to_predicted(u->ctx, ir); }
 static int g_convect(gpu_user_t *u, int ir, int iter, double dt, int p) { (void)iter; return vlc_rotor_convectwake(u->ctx, ir, dt, p); }
 static int g_rollup(gpu_user_t *u, int ir) { return vlc_rotor_rollup(u->ctx, ir); }
-static int g_sweep(gpu_user_t *u, int p, int addInit) { return vlc_wake_sweep(u->ctx, p, addInit); }
+static int g_sweep(gpu_user_t *u, int p, int addInit) {
+  if (u->world <= 1) return vlc_wake_sweep(u->ctx, p, addInit);
+  /* sharded: every rank holds the whole wake; it sweeps its slice of the targets, the slices are all-gathered (the one
+   * exchange of this stage), every rank scatters the complete list */
+  int64_t M = 0;
+  int rc = vlc_wake_sweep_count(u->ctx, &M);
+  if (rc || M <= 0) return rc;
+  const long per = (long)((M + u->world - 1) / u->world);
+  if (per * u->world > u->xbuf_targets) return VLC_ERR_ARG;
+  const int64_t first = (int64_t)u->rank * per, count = first >= M ? 0 : (first + per > M ? M - first : per);
+  if ((rc = vlc_wake_sweep_slice(u->ctx, p, first < M ? first : 0, count, u->xbuf))) return rc;
+  if ((rc = vlc_sync(u->ctx))) return rc;
+  if ((rc = u->exchange(u->exchange_arg, per))) return rc;
+  u->exchanges++;
+  return vlc_wake_sweep_scatter(u->ctx, p, addInit, u->xbuf);
+}
 static int g_velop(gpu_user_t *u, int ir, int op) { return vlc_rotor_wakevel_op(u->ctx, ir, op); }
 static const resident_ops_t gpu_ops = {resident_begin, sync_wing, g_assignshed, g_age, g_dissipate, g_strain,
                                        g_to_pred, g_convect, g_rollup, g_sweep, g_velop};
@@ -365,6 +388,19 @@ int case_gpu_hooks_download_wake(void *handle) {
   return 0;
 }
 
+/* One process per GPU: rank / world, the device exchange buffer (3 x xbuf_targets doubles, xbuf_targets >= world *
+ * ceil(M_max / world)) and the all-gather callback (NCCL through torch.distributed in tests/multi_gpu_case.py). */
+void case_gpu_hooks_set_sharding(void *handle, int world, int rank, double *xbuf, long xbuf_targets,
+                                 int (*exchange)(void *, long), void *arg) {
+  gpu_user_t *u = (gpu_user_t *)handle;
+  u->world = world;
+  u->rank = rank;
+  u->xbuf = xbuf;
+  u->xbuf_targets = xbuf_targets;
+  u->exchange = exchange;
+  u->exchange_arg = arg;
+}
+long case_gpu_hooks_exchanges(void *handle) { return ((gpu_user_t *)handle)->exchanges; }
 long case_gpu_hooks_wing_uploads(void *handle) { return ((gpu_user_t *)handle)->wing_uploads; }
 long case_gpu_hooks_uploads(void *handle) { return ((gpu_user_t *)handle)->uploads; }
 long case_gpu_hooks_skipped(void *handle) { return ((gpu_user_t *)handle)->skipped; }

@@ -124,6 +124,9 @@ def load_library() -> C.CDLL:
         "vlc_rotor_convectwake": (i32, [_vp, i32, C.c_double, i32]),
         "vlc_rotor_rollup": (i32, [_vp, i32]),
         "vlc_wake_sweep": (i32, [_vp, i32, i32]),
+        "vlc_wake_sweep_count": (i32, [_vp, C.POINTER(i64)]),
+        "vlc_wake_sweep_slice": (i32, [_vp, i32, i64, i64, _vp]),
+        "vlc_wake_sweep_scatter": (i32, [_vp, i32, i32, _vp]),
         "vlc_rotor_wakevel_op": (i32, [_vp, i32, i32]),
         "vlc_rotor_get_nwake": (i32, [_vp, i32, i32, i32, _vp]),
         "vlc_rotor_get_fwake": (i32, [_vp, i32, i32, i32, _vp]),
@@ -400,6 +403,17 @@ class Context:
 
     def wake_sweep(self, predicted=False, add_init_wake_vel=False):
         self._ck(self.lib.vlc_wake_sweep(self.h, int(predicted), int(add_init_wake_vel)))
+
+    def wake_sweep_count(self) -> int:
+        m = C.c_int64()
+        self._ck(self.lib.vlc_wake_sweep_count(self.h, C.byref(m)))
+        return m.value
+
+    def wake_sweep_slice(self, predicted, first, count, d_vel):
+        self._ck(self.lib.vlc_wake_sweep_slice(self.h, int(predicted), first, count, _ptr(d_vel)))
+
+    def wake_sweep_scatter(self, predicted, add_init_wake_vel, d_vel):
+        self._ck(self.lib.vlc_wake_sweep_scatter(self.h, int(predicted), int(add_init_wake_vel), _ptr(d_vel)))
 
     def rotor_wakevel_op(self, ir, op: int):
         self._ck(self.lib.vlc_rotor_wakevel_op(self.h, ir, op))

@@ -1632,21 +1632,35 @@ extern "C" int vlc_rotor_rollup(vlc_ctx* c, int ir) {
 // and velFwake(:, rowFar:nFwake) <- sum over source rotors jr = 1..nr of vind_on{N,F}wake_byRotor(rotor(jr), ...) (+- the
 // initial wake velocity while iter < initWakeVelNt).  All targets of all rotors go through ONE sweep per source rotor
 // (the reference's per-(ir, ib, jr) calls evaluate the same sums target by target); nothing leaves the device.
-extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
+extern "C" int vlc_wake_sweep_count(vlc_ctx* c, int64_t* M_out) {
+  CHECK_CTX(c);
+  if (!M_out) return fail(c, VLC_ERR_ARG, "null pointer");
+  long long M = 0;
+  for (auto& r : c->rotors)
+    if (r.defined) M += wake_targets_of(r);
+  *M_out = M;
+  return VLC_OK;
+}
+
+// Targets [first, first + count) of the wake-sweep list against every rotor; velocities into d_vel (3, M) at the same
+// positions.  One process per GPU calls this with its own slice and all-gathers d_vel (the targets are independent:
+// libCommon.f90:132-139 is a parallel loop over them); count = M on one GPU.
+extern "C" int vlc_wake_sweep_slice(vlc_ctx* c, int predicted, int64_t first, int64_t count, double* d_vel) {
   CHECK_CTX(c);
   int rc = bind_device(c);
   if (rc) return rc;
   const int s = predicted ? 1 : 0;
-  long long M = 0;
-  for (auto& r : c->rotors)
-    if (r.defined) M += wake_targets_of(r);
-  if (M <= 0) return VLC_OK;
-  long long Mmax = 0;  // every row active: sized once
-  for (auto& r : c->rotors)
-    if (r.defined && r.nNwake > 0) Mmax += ((long long)r.nNwake * (r.ns + 1) + r.nFwake) * r.nbConvect;
+  long long M = 0, Mmax = 0;  // Mmax: every row active, sized once
+  for (auto& r : c->rotors) {
+    if (!r.defined) continue;
+    M += wake_targets_of(r);
+    if (r.nNwake > 0) Mmax += ((long long)r.nNwake * (r.ns + 1) + r.nFwake) * r.nbConvect;
+  }
+  if (first < 0 || count < 0 || first + count > M) return fail(c, VLC_ERR_ARG, "target slice outside [0, M)");
+  if (count == 0) return VLC_OK;
+  if (!d_vel) return fail(c, VLC_ERR_ARG, "null pointer");
   if ((rc = reserve(c, c->ws_P, 3 * (size_t)Mmax))) return rc;
   if ((rc = reserve(c, c->ws_V, 3 * (size_t)Mmax))) return rc;
-  if ((rc = reserve(c, c->ws_acc, 3 * (size_t)Mmax))) return rc;
   long long off = 0;
   for (auto& r : c->rotors) {
     const long long m = r.defined ? wake_targets_of(r) : 0;
@@ -1657,33 +1671,58 @@ extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
     off += m;
   }
   CUDA_OK(c, cudaGetLastError());
-  bool first = true;
+  const double* P = c->ws_P.p + 3 * first;
+  double* acc = d_vel + 3 * first;
+  bool first_src = true;
   for (auto& src : c->rotors) {  // jr = 1..nr in order (main.f90:817)
     if (!src.defined) continue;
     if ((rc = pack_rotor(c, src, s))) return rc;
     const SourceSet& v = src.comb[s];
     if (v.n_pad <= 0) continue;
-    rc = (v.has_shared && c->shared_nodes) ? sweep_shared(c, v, M, c->ws_P.p, c->ws_V.p)
-                                           : sweep(c, v.rec.p, v.n_pad, M, c->ws_P.p, c->ws_V.p);
+    rc = (v.has_shared && c->shared_nodes) ? sweep_shared(c, v, count, P, c->ws_V.p) : sweep(c, v.rec.p, v.n_pad, count, P, c->ws_V.p);
     if (rc) return rc;
-    vlc::rec_accumulate_kernel<<<blocks_for(3 * M, 256), 256, 0, c->stream>>>(3 * M, first ? 1 : 0, c->ws_V.p, c->ws_acc.p);
+    vlc::rec_accumulate_kernel<<<blocks_for(3 * count, 256), 256, 0, c->stream>>>(3 * count, first_src ? 1 : 0, c->ws_V.p, acc);
     c->launches++;
-    first = false;
+    first_src = false;
   }
-  if (first) CUDA_OK(c, cudaMemsetAsync(c->ws_acc.p, 0, sizeof(double) * 3 * (size_t)M, c->stream));
-  off = 0;
+  if (first_src) CUDA_OK(c, cudaMemsetAsync(acc, 0, sizeof(double) * 3 * (size_t)count, c->stream));
+  CUDA_OK(c, cudaGetLastError());
+  return VLC_OK;
+}
+
+extern "C" int vlc_wake_sweep_scatter(vlc_ctx* c, int predicted, int addInitWakeVel, const double* d_vel) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  const int s = predicted ? 1 : 0;
+  long long off = 0;
   for (auto& r : c->rotors) {
     const long long m = r.defined ? wake_targets_of(r) : 0;
     if (m <= 0) continue;
+    if (!d_vel) return fail(c, VLC_ERR_ARG, "null pointer");
     const double w[3] = {r.initWakeVel * r.shaftAxis[0], r.initWakeVel * r.shaftAxis[1], r.initWakeVel * r.shaftAxis[2]};
     vlc::rec_scatter_vel_kernel<<<blocks_for(m, 256), 256, 0, c->stream>>>(
-        r.nbConvect, r.ns, r.nNwake, r.nFwake, r.rowNear, r.rowFar, s, addInitWakeVel ? 1 : 0, w[0], w[1], w[2],
-        c->ws_acc.p + 3 * off, r.velN[s ? 2 : 0].p, r.velF[s ? 2 : 0].p);
+        r.nbConvect, r.ns, r.nNwake, r.nFwake, r.rowNear, r.rowFar, s, addInitWakeVel ? 1 : 0, w[0], w[1], w[2], d_vel + 3 * off,
+        r.velN[s ? 2 : 0].p, r.velF[s ? 2 : 0].p);
     c->launches++;
     off += m;
   }
   CUDA_OK(c, cudaGetLastError());
   return VLC_OK;
+}
+
+extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
+  CHECK_CTX(c);
+  int64_t M = 0;
+  int rc = vlc_wake_sweep_count(c, &M);
+  if (rc || M <= 0) return rc;
+  long long Mmax = 0;
+  for (auto& r : c->rotors)
+    if (r.defined && r.nNwake > 0) Mmax += ((long long)r.nNwake * (r.ns + 1) + r.nFwake) * r.nbConvect;
+  if ((rc = bind_device(c))) return rc;
+  if ((rc = reserve(c, c->ws_acc, 3 * (size_t)Mmax))) return rc;
+  if ((rc = vlc_wake_sweep_slice(c, predicted, 0, M, c->ws_acc.p))) return rc;
+  return vlc_wake_sweep_scatter(c, predicted, addInitWakeVel, c->ws_acc.p);
 }
 
 extern "C" int vlc_rotor_wakevel_op(vlc_ctx* c, int ir, int op) {
