@@ -468,6 +468,11 @@ contains
     endif
   end subroutine gpu_wake_prestep
 
+  ! One MPI rank per GPU: replace each `vlc_wake_sweep(ctx, p, addInit)` below by
+  !   vlc_wake_sweep_count(ctx, M); vlc_wake_sweep_slice(ctx, p, first, count, d_vel) on this rank's slice of the M targets;
+  !   MPI_Allgather / ncclAllGather of d_vel (3*M doubles on the device, slices of ceiling(M/nranks) targets);
+  !   vlc_wake_sweep_scatter(ctx, p, addInit, d_vel)
+  ! -- every rank keeps the whole wake and runs the other stages redundantly (tests/multi_gpu_case.py is the tested twin).
   subroutine gpu_wake_convect(rotor, iter, dt, fdScheme, wakeStrain, initWakeVelNt)
     !! Replaces main.f90:800-1440: the wake sweeps, the fdScheme switch (0 explicit Euler :846-859, 1 predictor-
     !! corrector :861-949, 3 Adams-Bashforth / Adams-Moulton :1002-1115) with its velocity bookkeeping, strain_wake,
