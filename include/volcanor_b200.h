@@ -213,6 +213,44 @@ int vlc_rotor_put_wakevel(vlc_ctx* ctx, int ir, int ib, int which, const double*
 int vlc_rotor_get_wakevel(vlc_ctx* ctx, int ir, int ib, int which, double* velN /* 3 x nNwake x (ns+1) */,
                           double* velF /* 3 x nFwake */);
 
+/* ---- tier 2c: the collocation-point stage on the device copies of the wing records ---------------------------- */
+/*
+ * The rest of a time step between the two wake stages (main.f90:522-670): velocity at the collocation points, the
+ * right-hand side, the solve, map_gam and -- when the driver wants forces -- velCPTotal and the circulation-based
+ * sectional loads of forceCalcSwitch = 0.  The driver moves the wing and writes the KINEMATIC part of velCP into the
+ * wing records (main.f90:528-547: -velBody - omegaBody x r - omegaSlow*shaftAxis x r - flap term) before
+ * vlc_rotor_put_wing; after that neither the collocation-point velocities nor the right-hand side cross the bus.
+ * Needs vlc_rotor_set_wake_params (nbConvect, axisymmetrySwitch).  The O(nc*ns) arithmetic is unfused IEEE in the
+ * reference's statement order: given the same velCPTotal the loads are bit-identical to the CPU restatement
+ * (tests/test_cp_stage_host.py without a GPU on the same source, tests/test_zz_gpu_cp_stage.py through this ABI).
+ */
+/* main.f90:548-603 for rotor ir: wingpanel%velCP of its convected blades += for jr = 1..nr: rotor(jr)%vind_bywake(CP)
+ * [+ rotor(jr)%vind_bywing(CP) if jr /= ir]; RHS = -dot(velCP, nCap), blade 1's entries repeated for an axisymmetric
+ * rotor.  velCP stays in the device records, RHS on the device for vlc_rotor_solve_map_gam.  Optional host copies:
+ * velCP_out (3, nbConvect*nc*ns) in wiP order, RHS_out (nc*ns*nb); either may be NULL. */
+int vlc_rotor_calc_RHS(vlc_ctx* ctx, int ir, double* velCP_out, double* RHS_out);
+/* gamVec = matmulAX(AIC_inv, RHS) (main.f90:596; getrs with the factors of vlc_rotor_calcAIC) followed by
+ * rotor%map_gam() (classdef.f90:4181-4196) on the device records.  gamVec_out (nc*ns*nb) may be NULL. */
+int vlc_rotor_solve_map_gam(vlc_ctx* ctx, int ir, double* gamVec_out);
+/* Section frames of blade ib as the driver holds them after moving the wing, one block of 10*ns + 6 doubles:
+ * secTauCapChord(3,ns) | secNormalVec(3,ns) | secCP(3,ns) | secArea(ns) | yAxisAziFlap(3) | zAxisAziFlap(3)
+ * (blade_class, classdef.f90:238-358). */
+int vlc_rotor_put_sections(vlc_ctx* ctx, int ir, int ib, const double* sec);
+/* main.f90:630-663 for rotor ir: velCPTotal = velCP - sum over rotors of vind_bywing_boundVortices(CP)
+ * + rotor(ir)%vind_bywing(CP); blade 1's values for every blade of an axisymmetric rotor. */
+int vlc_rotor_calc_velCPTotal(vlc_ctx* ctx, int ir);
+/* = rotor%calc_secAlpha() + rotor%calc_force(density, dt) for forceCalcSwitch = 0 (classdef.f90:4766-4784, :4607-4671
+ * down to the blade sums of sumSecToNetForces :2368-2380; the sum over blades, sumBladeToNetForces :4954-4988, stays
+ * with the driver).  Updates gamPrev, gamTrapz, delP, delPUnsteady, normalForce, normalForceUnsteady, chordwiseResVel
+ * in the device records.  Omega = rotor%Omega (its sign sets invertGammaSign and the lift direction). */
+int vlc_rotor_calc_force(vlc_ctx* ctx, int ir, double density, double dt, double Omega, int spanwiseLiftSwitch);
+/* Loads of blade ib, one block of 12 + 25*ns doubles: forceInertial(3) lift(3) drag(3) liftUnsteady(3) |
+ * secChordwiseResVel secDragDir secLiftDir secForceInertial secLift secDrag secLiftUnsteady (3,ns each) |
+ * secAlpha secCL secCD secCLu (ns each). */
+int vlc_rotor_get_loads(vlc_ctx* ctx, int ir, int ib, double* loads);
+/* The device copy of blade ib's wing records (nc*ns x 104), e.g. to carry gamPrev / delP back into the driver's wiP. */
+int vlc_rotor_get_wing(vlc_ctx* ctx, int ir, int ib, double* wiP);
+
 /* ---- tier 3: device-resident wake state (node-indexed SoA) -------------------------------- */
 /*
  * A "lattice" is one blade's near wake kept on the device as TE nodes: nodes(3, nrows+1, ns+1)

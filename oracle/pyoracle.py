@@ -101,6 +101,8 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_rotor_dirLiftDrag": (None, [_vp]),
         "orc_rotor_calc_secAlpha": (None, [_vp]),
         "orc_rotor_calc_force": (None, [_vp, d, d]),
+        "orc_rotor_sum_forces": (None, [_vp]),
+        "orc_rotor_get_force_params": (None, [_vp, _vp]),
         "orc_blade_sec": (_vp, [_vp, i32, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
@@ -322,8 +324,11 @@ class OrcHooks(C.Structure):
     CALC_AIC = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, _vp)
     SOLVE = C.CFUNCTYPE(C.c_int, _vp, C.c_int, _vp, _vp)
     WAKE_STAGE = C.CFUNCTYPE(C.c_int, _vp, C.c_int)   # optional device-resident stages (NULL = CPU restatement)
+    CP_RHS_SOLVE = C.CFUNCTYPE(C.c_int, _vp)          # optional collocation-point stage (NULL = the call sites above)
+    CP_FORCES = C.CFUNCTYPE(C.c_int, _vp, C.c_int)
     _fields_ = [("user", _vp), ("vind_points", VIND_POINTS), ("vind_onNwake", VIND_ONN), ("vind_onFwake", VIND_ONF),
-                ("calcAIC", CALC_AIC), ("solve", SOLVE), ("wake_prestep", WAKE_STAGE), ("wake_convect", WAKE_STAGE)]
+                ("calcAIC", CALC_AIC), ("solve", SOLVE), ("wake_prestep", WAKE_STAGE), ("wake_convect", WAKE_STAGE),
+                ("cp_rhs_solve", CP_RHS_SOLVE), ("cp_forces", CP_FORCES)]
 
 
 class Case:

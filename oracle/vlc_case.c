@@ -513,6 +513,16 @@ void orc_rotor_calc_secAlpha(orc_rotor_t *r) {
 void orc_rotor_calc_force(orc_rotor_t *r, double density, double dt) {
   orc_rotor_dirLiftDrag(r);
   for (int ib = 0; ib < r->nbConvect; ++ib) blade_calc_force(&r->blade[ib], density, r->Omega, dt);
+  orc_rotor_sum_forces(r);
+}
+void orc_rotor_get_force_params(const orc_rotor_t *r, double out[4]) {
+  out[0] = r->Omega;
+  out[1] = r->spanwiseLiftSwitch;
+  out[2] = r->axisymmetrySwitch;
+  out[3] = r->nbConvect;
+}
+/* classdef.f90:4623-4671: the copies for an axisymmetric rotor + sumBladeToNetForces :4954-4988 */
+void orc_rotor_sum_forces(orc_rotor_t *r) {
   if (r->axisymmetrySwitch == 1) {
     const size_t n3 = sizeof(double) * 3 * (size_t)r->ns, n1 = sizeof(double) * (size_t)r->ns;
     for (int ib = 1; ib < r->nb; ++ib) {
@@ -1012,6 +1022,8 @@ void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *h) {
     c->hooks.solve = cpu_solve;
     c->hooks.wake_prestep = NULL;
     c->hooks.wake_convect = NULL;
+    c->hooks.cp_rhs_solve = NULL;
+    c->hooks.cp_forces = NULL;
   }
 }
 
@@ -1213,6 +1225,15 @@ static int compute_forces(orc_case_t *c) {
       return 3;
     }
     const long m = (long)r->nbConvect * r->ns * r->nc;
+    if (c->hooks.cp_forces) { /* :630-663, calc_secAlpha and calc_force down to the blade sums by the hook owner */
+      for (int jr = 0; jr < c->nr; ++jr)
+        c->pairs += (double)m * (2.0 * c->rotor[jr]->nc * c->rotor[jr]->ns + c->rotor[jr]->ns) * c->rotor[jr]->nb;
+      c->pairs += (double)m * n_wing_fil(r);
+      int rc = c->hooks.cp_forces(c->hooks.user, ir);
+      if (rc) return rc;
+      orc_rotor_sum_forces(r);
+      continue;
+    }
     double *P = (double *)malloc(sizeof(double) * 3 * (size_t)m);
     double *V = (double *)malloc(sizeof(double) * 3 * (size_t)m);
     long q = 0;
@@ -1444,6 +1465,22 @@ int orc_case_step(orc_case_t *c) {
         if (c->rotor[ir]->nNwake > 0) orc_rotor_dissipate_wake(c->rotor[ir], dt, cfg->kinematicVisc);
   }
   /* RHS, :522-615 */
+  if (c->hooks.cp_rhs_solve && cfg->ntSub == 0) { /* collocation-point stage by the hook owner (tier 2c of the C ABI) */
+    for (int ir = 0; ir < c->nr; ++ir) {
+      orc_rotor_t *r = c->rotor[ir];
+      const long m = (long)r->nbConvect * r->ns * r->nc;
+      double *P = (double *)malloc(sizeof(double) * 3 * (size_t)m);
+      kinematic_velCP(r, P); /* :528-547 stays with the driver */
+      free(P);
+      r->gen_wing++;
+      memcpy(r->gamVecPrev, r->gamVec, sizeof(double) * (size_t)(r->nc * r->ns * r->nb));
+      for (int jr = 0; jr < c->nr; ++jr)
+        c->pairs += (double)m * (n_wake_fil(c->rotor[jr]) + (jr != ir ? n_wing_fil(c->rotor[jr]) : 0.0));
+    }
+    int rc = c->hooks.cp_rhs_solve(c->hooks.user);
+    if (rc) return rc;
+    for (int ir = 0; ir < c->nr; ++ir) orc_rotor_map_gam(c->rotor[ir]); /* the hook owner holds this circulation already */
+  } else
   for (int i = 0; i <= cfg->ntSub; ++i) {
     for (int ir = 0; ir < c->nr; ++ir) {
       orc_rotor_t *r = c->rotor[ir];
@@ -1706,7 +1743,7 @@ double *orc_blade_sec(orc_rotor_t *r, int ib, const char *name) {
   S(secChord); S(secArea); S(secAlpha); S(secCL); S(secCLu); S(secCD); S(secMflapArm);
   S(secForceInertial); S(secLift); S(secDrag); S(secLiftDir); S(secDragDir); S(secLiftUnsteady);
   S(secTauCapChord); S(secTauCapSpan); S(secNormalVec); S(secCP); S(secChordwiseResVel);
-  S(forceInertial); S(lift);
+  S(forceInertial); S(lift); S(drag); S(liftUnsteady); S(yAxisAziFlap); S(zAxisAziFlap);
 #undef S
   return NULL;
 }

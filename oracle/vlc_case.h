@@ -59,6 +59,15 @@ typedef struct orc_hooks {
    * (tests/native/case_gpu_hooks.c in resident mode: the C ABI's tier 2b). */
   int (*wake_prestep)(void *user, int iter);
   int (*wake_convect)(void *user, int iter);
+  /* OPTIONAL, each on its own (NULL = the call sites above): the collocation-point stage by the hook owner (the C ABI's
+   * tier 2c).  cp_rhs_solve replaces main.f90:548-603 of every rotor inside the time loop (ntSub = 0): the driver has
+   * written the kinematic velCP into its wing records (:528-547) and saved gamVecPrev; the hook leaves velCP in the
+   * records, RHS and gamVec in the rotors' vectors and owns the new circulation (the driver maps gamVec into its own
+   * records afterwards without marking the wing as changed).  cp_forces replaces main.f90:630-663 + calc_secAlpha +
+   * calc_force of rotor ir down to the blade sums: it leaves the wing records, the sectional arrays and the blade
+   * forces of every blade in the driver's arrays; the driver then adds the blades (sumBladeToNetForces). */
+  int (*cp_rhs_solve)(void *user);
+  int (*cp_forces)(void *user, int ir);
 } orc_hooks_t;
 
 typedef struct orc_case orc_case_t;
@@ -101,6 +110,10 @@ double orc_rotor_gettheta(const orc_rotor_t *r, double psi, int ib);
 void orc_rotor_dirLiftDrag(orc_rotor_t *r);
 void orc_rotor_calc_secAlpha(orc_rotor_t *r);
 void orc_rotor_calc_force(orc_rotor_t *r, double density, double dt);
+/* the tail of rotor_calc_force: copies for an axisymmetric rotor + sumBladeToNetForces (classdef.f90:4623-4671) */
+void orc_rotor_sum_forces(orc_rotor_t *r);
+/* out[0..3] = Omega, spanwiseLiftSwitch, axisymmetrySwitch, nbConvect */
+void orc_rotor_get_force_params(const orc_rotor_t *r, double out[4]);
 double *orc_blade_sec(orc_rotor_t *r, int ib, const char *name); /* sectional arrays by name */
 
 #ifdef __cplusplus

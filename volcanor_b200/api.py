@@ -132,6 +132,13 @@ def load_library() -> C.CDLL:
         "vlc_rotor_get_fwake": (i32, [_vp, i32, i32, i32, _vp]),
         "vlc_rotor_put_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_rotor_get_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
+        "vlc_rotor_calc_RHS": (i32, [_vp, i32, _vp, _vp]),
+        "vlc_rotor_solve_map_gam": (i32, [_vp, i32, _vp]),
+        "vlc_rotor_put_sections": (i32, [_vp, i32, i32, _vp]),
+        "vlc_rotor_calc_velCPTotal": (i32, [_vp, i32]),
+        "vlc_rotor_calc_force": (i32, [_vp, i32, C.c_double, C.c_double, C.c_double, i32]),
+        "vlc_rotor_get_loads": (i32, [_vp, i32, i32, _vp]),
+        "vlc_rotor_get_wing": (i32, [_vp, i32, i32, _vp]),
         "vlc_convect_dev": (i32, [_vp, i64, _vp, _vp, C.c_double]),
         "vlc_ab2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
         "vlc_am2_dev": (i32, [_vp, i64, _vp, _vp, _vp]),
@@ -439,6 +446,53 @@ class Context:
         self._ck(self.lib.vlc_rotor_get_wakevel(self.h, ir, ib, which, _ptr(vn) if vn.size else None,
                                                 _ptr(vf) if vf.size else None))
         return vn, vf
+
+    # ---- tier 2c: the collocation-point stage on the device copies of the wing records ----
+    def rotor_calc_RHS(self, ir, m, N, want_velCP=True, want_RHS=True):
+        """main.f90:548-603 for rotor ir; m = nbConvect*nc*ns, N = nc*ns*nb.  Returns (velCP (m, 3), RHS (N,))."""
+        v = np.empty((m, 3), dtype=np.float64) if want_velCP else None
+        r = np.empty(N, dtype=np.float64) if want_RHS else None
+        self._ck(self.lib.vlc_rotor_calc_RHS(self.h, ir, _ptr(v), _ptr(r)))
+        return v, r
+
+    def rotor_solve_map_gam(self, ir, N, want_gamVec=True):
+        g = np.empty(N, dtype=np.float64) if want_gamVec else None
+        self._ck(self.lib.vlc_rotor_solve_map_gam(self.h, ir, _ptr(g)))
+        return g
+
+    @staticmethod
+    def pack_sections(secTauCapChord, secNormalVec, secCP, secArea, yAxisAziFlap, zAxisAziFlap) -> np.ndarray:
+        """The 10*ns + 6 block of vlc_rotor_put_sections from the blade_class arrays ((ns, 3) = Fortran (3, ns))."""
+        return np.concatenate([_f64(a).ravel() for a in (secTauCapChord, secNormalVec, secCP, secArea, yAxisAziFlap,
+                                                         zAxisAziFlap)])
+
+    def rotor_put_sections(self, ir, ib, sec):
+        self._ck(self.lib.vlc_rotor_put_sections(self.h, ir, ib, _ptr(_f64(sec))))
+
+    def rotor_calc_velCPTotal(self, ir):
+        self._ck(self.lib.vlc_rotor_calc_velCPTotal(self.h, ir))
+
+    def rotor_calc_force(self, ir, density, dt, Omega, spanwiseLiftSwitch=0):
+        self._ck(self.lib.vlc_rotor_calc_force(self.h, ir, float(density), float(dt), float(Omega), int(spanwiseLiftSwitch)))
+
+    LOADS_SEC3 = ("secChordwiseResVel", "secDragDir", "secLiftDir", "secForceInertial", "secLift", "secDrag", "secLiftUnsteady")
+    LOADS_SEC1 = ("secAlpha", "secCL", "secCD", "secCLu")
+
+    def rotor_get_loads(self, ir, ib, ns) -> dict:
+        """Loads block of blade ib (12 + 25*ns doubles) as a dict of named arrays."""
+        a = np.empty(12 + 25 * ns, dtype=np.float64)
+        self._ck(self.lib.vlc_rotor_get_loads(self.h, ir, ib, _ptr(a)))
+        out = {"forceInertial": a[0:3], "lift": a[3:6], "drag": a[6:9], "liftUnsteady": a[9:12]}
+        for k, name in enumerate(self.LOADS_SEC3):
+            out[name] = a[12 + 3 * ns * k: 12 + 3 * ns * (k + 1)].reshape(ns, 3)
+        for k, name in enumerate(self.LOADS_SEC1):
+            out[name] = a[12 + 21 * ns + ns * k: 12 + 21 * ns + ns * (k + 1)]
+        return out
+
+    def rotor_get_wing(self, ir, ib, nc, ns):
+        a = np.empty((ns, nc, 104), dtype=np.float64)
+        self._ck(self.lib.vlc_rotor_get_wing(self.h, ir, ib, _ptr(a)))
+        return a
 
     def gridgen(self, nx, ny, nz, xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake):
         """program gridgen (src/gridgen.f90): (gridCentre, velCentre), each (nz-1, ny-1, nx-1, 3)."""

@@ -21,6 +21,7 @@
 #include "pack.cuh"
 #include "wake_state.cuh"
 #include "wake_records.cuh"
+#include "cp_stage.cuh"
 
 namespace {
 
@@ -89,6 +90,10 @@ struct Rotor {
   DevBuf order2_tmp;
   vlc::AxiT* d_axi = nullptr;
   std::vector<vlc::AxiT> h_axi;
+  // tier 2c (collocation-point stage on the device): right-hand side, circulation vector, section frames, loads
+  DevBuf rhs, gamvec, sec, loads;
+  bool have_rhs = false;
+  std::vector<char> have_sec;  // per blade: vlc_rotor_put_sections seen
   // AIC
   int N = 0;
   DevBuf LU;
@@ -122,6 +127,7 @@ struct vlc_ctx {
   DevBuf stage_V;
   DevBuf scratch;  // packing inputs for host-API set_sources
   DevBuf ws_P, ws_V, ws_acc;  // vlc_wake_sweep: targets of every convected blade, one source rotor's result, the sum
+  DevBuf cp_P, cp_V;          // tier 2c: collocation points of one rotor, one source rotor's velocities there
   unsigned char* d_flag = nullptr;
   size_t flag_cap = 0;
   std::vector<Rotor> rotors;
@@ -841,6 +847,8 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   release(c->ws_P);
   release(c->ws_V);
   release(c->ws_acc);
+  release(c->cp_P);
+  release(c->cp_V);
   release(c->solver_work);
   if (c->d_flag) cudaFree(c->d_flag);
   for (auto& r : c->rotors) {
@@ -863,6 +871,10 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     release(r.order2_tmp);
     if (r.d_axi) cudaFree(r.d_axi);
     release(r.bound.rec);
+    release(r.rhs);
+    release(r.gamvec);
+    release(r.sec);
+    release(r.loads);
     release(r.LU);
     if (r.d_ipiv) cudaFree(r.d_ipiv);
     if (r.d_info) cudaFree(r.d_info);
@@ -1065,8 +1077,16 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     r.stale_far[s2].assign(nb, 1);
   }
   r.nbConvect = nb;
+  r.have_rhs = false;
+  r.have_sec.assign(nb, 0);
   int rc = bind_device(c);
   if (rc) return rc;
+  if ((rc = reserve(c, r.rhs, (size_t)r.N + 1)) || (rc = reserve(c, r.gamvec, (size_t)r.N + 1))) return rc;
+  if ((rc = reserve(c, r.sec, (size_t)nb * vlc::cp::sec_doubles(ns))) || (rc = reserve(c, r.loads, (size_t)nb * vlc::cp::loads_doubles(ns))))
+    return rc;
+  CUDA_OK(c, cudaMemsetAsync(r.gamvec.p, 0, r.gamvec.cap * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(r.sec.p, 0, r.sec.cap * sizeof(double), c->stream));
+  CUDA_OK(c, cudaMemsetAsync(r.loads.p, 0, r.loads.cap * sizeof(double), c->stream));
   for (int k = 0; k < 4; ++k) {  // velNwake etc. start at zero like rotor_init (classdef.f90:3795-3812)
     if ((rc = reserve(c, r.velN[k], (size_t)3 * nNwake * (ns + 1) * nb + 1))) return rc;
     if ((rc = reserve(c, r.velF[k], (size_t)3 * nFwake * nb + 1))) return rc;
@@ -1837,6 +1857,187 @@ extern "C" int vlc_rotor_get_wakevel(vlc_ctx* c, int ir, int ib, int which, doub
   return VLC_OK;
 }
 
+
+// ============================================================================ tier 2c: collocation-point stage
+
+namespace {
+
+// one source set swept at the collocation points held in c->cp_P, result in c->cp_V
+int cp_sweep(vlc_ctx* c, const double* rec, long long n_pad, long long m, const SourceSet* shared) {
+  return shared ? sweep_shared(c, *shared, m, c->cp_P.p, c->cp_V.p) : sweep(c, rec, n_pad, m, c->cp_P.p, c->cp_V.p);
+}
+
+int cp_accumulate(vlc_ctx* c, Rotor* r, long long m, int field, int sign) {
+  vlc::cp_accumulate_kernel<<<blocks_for(3 * m, 256), 256, 0, c->stream>>>(m, field, sign, c->cp_V.p, r->wiP.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  return VLC_OK;
+}
+
+int cp_targets(vlc_ctx* c, Rotor* r, long long m) {
+  int rc;
+  if ((rc = reserve(c, c->cp_P, 3 * (size_t)m)) || (rc = reserve(c, c->cp_V, 3 * (size_t)m))) return rc;
+  vlc::cp_targets_kernel<<<blocks_for(3 * m, 256), 256, 0, c->stream>>>(m, r->wiP.p, c->cp_P.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  return VLC_OK;
+}
+
+}  // namespace
+
+extern "C" int vlc_rotor_calc_RHS(vlc_ctx* c, int ir, double* velCP_out, double* RHS_out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const int npb = r->nc * r->ns;
+  const long long m = (long long)r->nbConvect * npb;
+  if ((rc = cp_targets(c, r, m))) return rc;
+  for (int jr = 0; jr < (int)c->rotors.size(); ++jr) {  // main.f90:551-560: wake of every rotor, wing of every other
+    Rotor& src = c->rotors[jr];
+    if (!src.defined) continue;
+    if ((rc = pack_rotor(c, src, 0))) return rc;
+    {
+      const SourceSet v = wake_view(src, 0);
+      if ((rc = cp_sweep(c, v.rec.p, v.n_pad, m, (v.has_shared && c->shared_nodes) ? &v : nullptr))) return rc;
+      if ((rc = cp_accumulate(c, r, m, vlc::cp::kVelCP, +1))) return rc;
+    }
+    if (jr != ir) {
+      if ((rc = cp_sweep(c, src.comb[0].rec.p, src.wing_pad[0], m, nullptr))) return rc;
+      if ((rc = cp_accumulate(c, r, m, vlc::cp::kVelCP, +1))) return rc;
+    }
+  }
+  vlc::cp_rhs_kernel<<<blocks_for(r->N, 128), 128, 0, c->stream>>>(r->N, npb, r->nbConvect, r->axisym, r->wiP.p, r->rhs.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  r->have_rhs = true;
+  if (velCP_out)
+    CUDA_OK(c, cudaMemcpy2DAsync(velCP_out, 3 * sizeof(double), r->wiP.p + vlc::cp::kVelCP, vlc::kWp * sizeof(double),
+                                 3 * sizeof(double), (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  if (RHS_out) CUDA_OK(c, cudaMemcpyAsync(RHS_out, r->rhs.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
+  if (velCP_out || RHS_out) CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_solve_map_gam(vlc_ctx* c, int ir, double* gamVec_out) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (!r->factored) return fail(c, VLC_ERR_STATE, "vlc_rotor_solve_map_gam before vlc_rotor_calcAIC");
+  if (!r->have_rhs) return fail(c, VLC_ERR_STATE, "vlc_rotor_solve_map_gam before vlc_rotor_calc_RHS");
+  CUDA_OK(c, cudaMemcpyAsync(r->gamvec.p, r->rhs.p, sizeof(double) * r->N, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = solve_dev(c, r, r->gamvec.p, 1))) return rc;
+  vlc::cp_map_gam_kernel<<<blocks_for(r->N, 128), 128, 0, c->stream>>>(r->nb, r->nc * r->ns, r->nbConvect, r->axisym, r->gamvec.p, r->wiP.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  r->have_rhs = false;  // one solve per right-hand side
+  r->dirty[0] = r->dirty[1] = r->bound_dirty = true;  // the wing's circulation changed
+  if (gamVec_out) {
+    CUDA_OK(c, cudaMemcpyAsync(gamVec_out, r->gamvec.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_put_sections(vlc_ctx* c, int ir, int ib, const double* sec) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !sec) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const size_t per = (size_t)vlc::cp::sec_doubles(r->ns);
+  r->have_sec[ib] = 1;
+  return upload(c, r->sec, per * r->nb, per * ib, sec, per);
+}
+
+extern "C" int vlc_rotor_calc_velCPTotal(vlc_ctx* c, int ir) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const int npb = r->nc * r->ns;
+  const long long m = (long long)r->nbConvect * npb;
+  if ((rc = cp_targets(c, r, m))) return rc;
+  vlc::cp_copy_field_kernel<<<blocks_for(3 * m, 256), 256, 0, c->stream>>>(m, vlc::cp::kVelCP, vlc::cp::kVelCPTotal, r->wiP.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  for (auto& src : c->rotors) {  // main.f90:639-645: minus the bound vortices of every rotor
+    if (!src.defined) continue;
+    if ((rc = pack_bound(c, src))) return rc;
+    if ((rc = cp_sweep(c, src.bound.rec.p, src.bound.n_pad, m, nullptr))) return rc;
+    if ((rc = cp_accumulate(c, r, m, vlc::cp::kVelCPTotal, -1))) return rc;
+  }
+  if ((rc = pack_rotor(c, *r, 0))) return rc;  // main.f90:647-652: plus the whole wing of this rotor
+  if ((rc = cp_sweep(c, r->comb[0].rec.p, r->wing_pad[0], m, nullptr))) return rc;
+  if ((rc = cp_accumulate(c, r, m, vlc::cp::kVelCPTotal, +1))) return rc;
+  if (r->axisym == 1 && r->nb > 1) {  // main.f90:658-663
+    const long long n = (long long)(r->nb - 1) * npb * 3;
+    vlc::cp_axisym_field_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nb, npb, vlc::cp::kVelCPTotal, 3, r->wiP.p);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_calc_force(vlc_ctx* c, int ir, double density, double dt, double Omega, int spanwiseLiftSwitch) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (!(dt > 0.0)) return fail(c, VLC_ERR_ARG, "dt must be positive");
+  for (int ib = 0; ib < r->nbConvect; ++ib)
+    if (!r->have_sec[ib]) return fail(c, VLC_ERR_STATE, "vlc_rotor_calc_force before vlc_rotor_put_sections of every convected blade");
+  const int npb = r->nc * r->ns, nld = vlc::cp::loads_doubles(r->ns);
+  vlc::cp_loads_kernel<<<r->nbConvect, 64, 0, c->stream>>>(r->nc, r->ns, density, dt, Omega, spanwiseLiftSwitch, r->wiP.p,
+                                                           r->sec.p, r->loads.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  if (r->axisym == 1 && r->nb > 1) {  // classdef.f90:4623-4650: blades 2..nb take blade 1's pressures, forces and loads
+    const int fields[3][2] = {{vlc::cp::kDelP, 2}, {vlc::cp::kGamPrev, 1}, {vlc::cp::kNormalForce, 6}};
+    for (auto& f : fields) {
+      const long long n = (long long)(r->nb - 1) * npb * f[1];
+      vlc::cp_axisym_field_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nb, npb, f[0], f[1], r->wiP.p);
+      c->launches++;
+    }
+    const long long n = (long long)(r->nb - 1) * nld;
+    vlc::cp_axisym_loads_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(r->nb, r->ns, nld, r->loads.p);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_loads(vlc_ctx* c, int ir, int ib, double* loads) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !loads) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const size_t per = (size_t)vlc::cp::loads_doubles(r->ns);
+  CUDA_OK(c, cudaMemcpyAsync(loads, r->loads.p + per * ib, per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_wing(vlc_ctx* c, int ir, int ib, double* wiP) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !wiP) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const size_t per = (size_t)r->nc * r->ns * vlc::kWp;
+  CUDA_OK(c, cudaMemcpyAsync(wiP, r->wiP.p + per * ib, per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
 
 extern "C" int vlc_convect_dev(vlc_ctx* c, int64_t n, double* x, const double* v, double dt) {
   CHECK_CTX(c);
