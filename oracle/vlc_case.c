@@ -596,6 +596,7 @@ struct orc_case {
   orc_rotor_t **rotor;
   orc_hooks_t hooks;
   void *stage_user; /* `user` of the two wake-stage hooks when they were installed separately (orc_case_set_stage_hooks) */
+  void *cp_user;    /* the same for the two collocation-point hooks (orc_case_set_cp_hooks) */
   char err[256];
 };
 
@@ -1009,8 +1010,15 @@ void orc_case_set_stage_hooks(orc_case_t *c, void *user, int (*prestep)(void *, 
   c->hooks.wake_convect = convect;
 }
 
+void orc_case_set_cp_hooks(orc_case_t *c, void *user, int (*rhs_solve)(void *), int (*forces)(void *, int)) {
+  c->cp_user = user;
+  c->hooks.cp_rhs_solve = rhs_solve;
+  c->hooks.cp_forces = forces;
+}
+
 void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *h) {
   c->stage_user = NULL;
+  c->cp_user = NULL;
   if (h) {
     c->hooks = *h;
   } else {
@@ -1229,7 +1237,7 @@ static int compute_forces(orc_case_t *c) {
       for (int jr = 0; jr < c->nr; ++jr)
         c->pairs += (double)m * (2.0 * c->rotor[jr]->nc * c->rotor[jr]->ns + c->rotor[jr]->ns) * c->rotor[jr]->nb;
       c->pairs += (double)m * n_wing_fil(r);
-      int rc = c->hooks.cp_forces(c->hooks.user, ir);
+      int rc = c->hooks.cp_forces(c->cp_user ? c->cp_user : c->hooks.user, ir);
       if (rc) return rc;
       orc_rotor_sum_forces(r);
       continue;
@@ -1477,7 +1485,7 @@ int orc_case_step(orc_case_t *c) {
       for (int jr = 0; jr < c->nr; ++jr)
         c->pairs += (double)m * (n_wake_fil(c->rotor[jr]) + (jr != ir ? n_wing_fil(c->rotor[jr]) : 0.0));
     }
-    int rc = c->hooks.cp_rhs_solve(c->hooks.user);
+    int rc = c->hooks.cp_rhs_solve(c->cp_user ? c->cp_user : c->hooks.user);
     if (rc) return rc;
     for (int ir = 0; ir < c->nr; ++ir) orc_rotor_map_gam(c->rotor[ir]); /* the hook owner holds this circulation already */
   } else

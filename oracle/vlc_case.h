@@ -83,6 +83,8 @@ void orc_case_set_hooks(orc_case_t *c, const orc_hooks_t *hooks); /* NULL = CPU 
 /* Only the two wake-stage hooks, with their own `user`; the five call sites keep what orc_case_set_hooks installed
  * (call it first).  NULL functions restore the inline stages. */
 void orc_case_set_stage_hooks(orc_case_t *c, void *user, int (*wake_prestep)(void *, int), int (*wake_convect)(void *, int));
+/* Only the two collocation-point hooks, with their own `user` (call orc_case_set_hooks first).  NULL restores the call sites. */
+void orc_case_set_cp_hooks(orc_case_t *c, void *user, int (*cp_rhs_solve)(void *), int (*cp_forces)(void *, int));
 /* main.f90:1-382: init rotors, pitch, AIC, initial solution, initial forces.  Returns 0 / error code. */
 int orc_case_init(orc_case_t *c);
 /* one pass of the time loop main.f90:400-1452 (iter = 1..nt) */

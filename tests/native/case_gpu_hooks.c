@@ -30,6 +30,9 @@ typedef struct {
   int resident, resident_started;
   long wing_uploads;
   const struct resident_ops *ops; /* who executes the wake stages: the C ABI (GPU) or the oracle's own mutators (CPU) */
+  const struct cp_ops *cp;        /* who executes the collocation-point stage (tier 2c): the C ABI or its CPU emulation */
+  struct cp_emu *emu;             /* CPU emulation only: the "library's" copies per rotor */
+  long cp_rhs_calls, cp_force_calls;
   /* one process per GPU (world > 1): this rank sweeps targets [rank*per, (rank+1)*per) and `exchange` all-gathers the
    * velocity slices in xbuf (device, (3, world*per_max)); set by case_gpu_hooks_set_sharding */
   int world, rank;
@@ -307,6 +310,207 @@ static int h_wake_convect(void *user, int iter) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ tier 2c: the collocation-point stage
+ * = gpu_cp_rhs_solve / gpu_cp_forces of fortran/libGPU.f90.  The stage's calls, as the orchestration below makes them;
+ * two backends like the wake stages: `gpu_cp_ops` forwards to the C ABI, `cpu_cp_ops` emulates the library on the CPU
+ * (its own copies of the wing records, the g++ build of cp_stage.cuh for the record arithmetic, the oracle for the
+ * sweeps), so that the orchestration and its write-backs run without a GPU and must reproduce the driver's inline
+ * statement bit for bit (tests/test_staged_hooks.py). */
+typedef struct cp_ops {
+  int (*sync)(gpu_user_t *u, int ir); /* the library's copy of rotor ir becomes current (wing; wake unless resident) */
+  int (*calc_RHS)(gpu_user_t *u, int ir, double *velCP, double *RHS);
+  int (*solve_map_gam)(gpu_user_t *u, int ir, double *gamVec);
+  int (*put_sections)(gpu_user_t *u, int ir, int ib, const double *sec);
+  int (*calc_velCPTotal)(gpu_user_t *u, int ir);
+  int (*calc_force)(gpu_user_t *u, int ir, double density, double dt, double Omega, int spanwiseLiftSwitch);
+  int (*get_loads)(gpu_user_t *u, int ir, int ib, double *loads);
+  int (*get_wing)(gpu_user_t *u, int ir, int ib, double *wiP);
+} cp_ops_t;
+
+static int gc_sync(gpu_user_t *u, int ir) { return sync_rotor(u, ir, 0); }
+static int gc_rhs(gpu_user_t *u, int ir, double *v, double *rhs) { return vlc_rotor_calc_RHS(u->ctx, ir, v, rhs); }
+static int gc_solve(gpu_user_t *u, int ir, double *g) { return vlc_rotor_solve_map_gam(u->ctx, ir, g); }
+static int gc_put_sec(gpu_user_t *u, int ir, int ib, const double *s) { return vlc_rotor_put_sections(u->ctx, ir, ib, s); }
+static int gc_veltot(gpu_user_t *u, int ir) { return vlc_rotor_calc_velCPTotal(u->ctx, ir); }
+static int gc_force(gpu_user_t *u, int ir, double rho, double dt, double Om, int sl) {
+  return vlc_rotor_calc_force(u->ctx, ir, rho, dt, Om, sl);
+}
+static int gc_get_loads(gpu_user_t *u, int ir, int ib, double *l) { return vlc_rotor_get_loads(u->ctx, ir, ib, l); }
+static int gc_get_wing(gpu_user_t *u, int ir, int ib, double *w) { return vlc_rotor_get_wing(u->ctx, ir, ib, w); }
+static const cp_ops_t gpu_cp_ops = {gc_sync, gc_rhs, gc_solve, gc_put_sec, gc_veltot, gc_force, gc_get_loads, gc_get_wing};
+
+/* CPU emulation of the library's tier 2c state (tests/native/cp_stage_host.cpp = cp_stage.cuh built by g++) */
+void cp_host_loads(int nbConvect, int nc, int ns, double density, double dt, double Omega, int spanwiseLiftSwitch, double *wiP,
+                   const double *sec, double *loads);
+void cp_host_rhs(int N, int npb, int nbConvect, int axisym, const double *wiP, double *RHS);
+void cp_host_map_gam(int nb, int npb, int nbConvect, int axisym, const double *gamVec, double *wiP);
+typedef struct cp_emu {
+  double *wiP, *sec, *loads, *rhs; /* what vlc_ctx holds per rotor: records of all blades, section frames, loads, RHS */
+} cp_emu_t;
+enum { WP_CP = 64, WP_VELCP = 76, WP_VELCPTOTAL = 79, WP_GAMPREV = 50, WP_NFORCE = 85, WP_DELP = 95 };
+#define SEC_N(ns) (10 * (ns) + 6)
+#define LOADS_N(ns) (12 + 25 * (ns))
+
+static int ec_sync(gpu_user_t *u, int ir) { /* = vlc_rotor_put_wing of every blade */
+  orc_rotor_t *r = ROT(u, ir);
+  const size_t per = (size_t)r->nc * r->ns * VLC_WINGPANEL_DOUBLES;
+  for (int ib = 0; ib < r->nb; ++ib) memcpy(u->emu[ir].wiP + per * ib, orc_rotor_wiP(r, ib), per * sizeof(double));
+  return 0;
+}
+/* one source swept at the collocation points of the emulated records and added to / subtracted from a record field */
+static void ec_sweep_acc(gpu_user_t *u, int ir, int jr, int what, int field, double sign) {
+  orc_rotor_t *r = ROT(u, ir);
+  const long m = (long)r->nbConvect * r->nc * r->ns;
+  double *w = u->emu[ir].wiP, *P = (double *)malloc(sizeof(double) * 3 * (size_t)m), *V = (double *)malloc(sizeof(double) * 3 * (size_t)m);
+  for (long q = 0; q < m; ++q) memcpy(P + 3 * q, w + VLC_WINGPANEL_DOUBLES * q + WP_CP, 3 * sizeof(double));
+  orc_rotor_vind_points(ROT(u, jr), what, 0, m, P, V);
+  for (long q = 0; q < m; ++q)
+    for (int k = 0; k < 3; ++k) {
+      double *x = w + VLC_WINGPANEL_DOUBLES * q + field + k;
+      *x = sign > 0 ? *x + V[3 * q + k] : *x - V[3 * q + k];
+    }
+  free(P);
+  free(V);
+}
+static int ec_rhs(gpu_user_t *u, int ir, double *velCP, double *RHS) {
+  orc_rotor_t *r = ROT(u, ir);
+  const int npb = r->nc * r->ns, N = npb * r->nb;
+  for (int jr = 0; jr < u->nr; ++jr) {
+    ec_sweep_acc(u, ir, jr, 1, WP_VELCP, +1.0);
+    if (jr != ir) ec_sweep_acc(u, ir, jr, 0, WP_VELCP, +1.0);
+  }
+  cp_host_rhs(N, npb, r->nbConvect, r->axisymmetrySwitch, u->emu[ir].wiP, u->emu[ir].rhs);
+  if (velCP)
+    for (long q = 0; q < (long)r->nbConvect * npb; ++q)
+      memcpy(velCP + 3 * q, u->emu[ir].wiP + VLC_WINGPANEL_DOUBLES * q + WP_VELCP, 3 * sizeof(double));
+  if (RHS) memcpy(RHS, u->emu[ir].rhs, sizeof(double) * (size_t)N);
+  return 0;
+}
+static int ec_solve(gpu_user_t *u, int ir, double *gamVec) {
+  orc_rotor_t *r = ROT(u, ir);
+  const int npb = r->nc * r->ns, N = npb * r->nb;
+  double *g = (double *)malloc(sizeof(double) * (size_t)N);
+  orc_matmulAX(N, N, r->AIC_inv, u->emu[ir].rhs, g);
+  cp_host_map_gam(r->nb, npb, r->nbConvect, r->axisymmetrySwitch, g, u->emu[ir].wiP);
+  if (gamVec) memcpy(gamVec, g, sizeof(double) * (size_t)N);
+  free(g);
+  return 0;
+}
+static int ec_put_sec(gpu_user_t *u, int ir, int ib, const double *s) {
+  memcpy(u->emu[ir].sec + (size_t)SEC_N(ROT(u, ir)->ns) * ib, s, sizeof(double) * (size_t)SEC_N(ROT(u, ir)->ns));
+  return 0;
+}
+static void ec_axisym_field(orc_rotor_t *r, double *w, int field, int n) { /* = cp_axisym_field_kernel */
+  const int npb = r->nc * r->ns;
+  for (int ib = 1; ib < r->nb; ++ib)
+    for (int q = 0; q < npb; ++q)
+      memcpy(w + VLC_WINGPANEL_DOUBLES * ((size_t)q + (size_t)npb * ib) + field, w + VLC_WINGPANEL_DOUBLES * (size_t)q + field,
+             sizeof(double) * (size_t)n);
+}
+static int ec_veltot(gpu_user_t *u, int ir) {
+  orc_rotor_t *r = ROT(u, ir);
+  double *w = u->emu[ir].wiP;
+  for (long q = 0; q < (long)r->nbConvect * r->nc * r->ns; ++q)
+    memcpy(w + VLC_WINGPANEL_DOUBLES * q + WP_VELCPTOTAL, w + VLC_WINGPANEL_DOUBLES * q + WP_VELCP, 3 * sizeof(double));
+  for (int jr = 0; jr < u->nr; ++jr) ec_sweep_acc(u, ir, jr, 3, WP_VELCPTOTAL, -1.0);
+  ec_sweep_acc(u, ir, ir, 0, WP_VELCPTOTAL, +1.0);
+  if (r->axisymmetrySwitch == 1) ec_axisym_field(r, w, WP_VELCPTOTAL, 3);
+  return 0;
+}
+static int ec_force(gpu_user_t *u, int ir, double rho, double dt, double Om, int sl) {
+  orc_rotor_t *r = ROT(u, ir);
+  double *w = u->emu[ir].wiP, *l = u->emu[ir].loads;
+  const int ns = r->ns, nld = LOADS_N(ns);
+  cp_host_loads(r->nbConvect, r->nc, ns, rho, dt, Om, sl, w, u->emu[ir].sec, l);
+  if (r->axisymmetrySwitch == 1) {
+    ec_axisym_field(r, w, WP_DELP, 2);
+    ec_axisym_field(r, w, WP_GAMPREV, 1);
+    ec_axisym_field(r, w, WP_NFORCE, 6);
+    for (int ib = 1; ib < r->nb; ++ib) /* = cp_axisym_loads_kernel: everything but secChordwiseResVel */
+      for (int k = 0; k < nld; ++k)
+        if (k < 12 || k >= 12 + 3 * ns) l[(size_t)nld * ib + k] = l[k];
+  }
+  return 0;
+}
+static int ec_get_loads(gpu_user_t *u, int ir, int ib, double *l) {
+  memcpy(l, u->emu[ir].loads + (size_t)LOADS_N(ROT(u, ir)->ns) * ib, sizeof(double) * (size_t)LOADS_N(ROT(u, ir)->ns));
+  return 0;
+}
+static int ec_get_wing(gpu_user_t *u, int ir, int ib, double *wq) {
+  const size_t per = (size_t)ROT(u, ir)->nc * ROT(u, ir)->ns * VLC_WINGPANEL_DOUBLES;
+  memcpy(wq, u->emu[ir].wiP + per * ib, per * sizeof(double));
+  return 0;
+}
+static const cp_ops_t cpu_cp_ops = {ec_sync, ec_rhs, ec_solve, ec_put_sec, ec_veltot, ec_force, ec_get_loads, ec_get_wing};
+
+/* main.f90:548-603 of every rotor through the stage's calls.  The driver has written the kinematic velCP into its
+ * records and saved gamVecPrev; it maps gamVec into its own records afterwards. */
+static int h_cp_rhs_solve(void *user) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  const cp_ops_t *o = u->cp;
+  for (int ir = 0; ir < u->nr; ++ir) CK(o->sync(u, ir));
+  for (int ir = 0; ir < u->nr; ++ir) {
+    orc_rotor_t *r = ROT(u, ir);
+    const int npb = r->nc * r->ns;
+    double *v = (double *)malloc(sizeof(double) * 3 * (size_t)r->nbConvect * npb);
+    int rc = o->calc_RHS(u, ir, v, r->RHS);
+    if (!rc)
+      for (int ib = 0; ib < r->nbConvect; ++ib) /* velCP back into the driver's records: blade_calc_force reads it */
+        for (int q = 0; q < npb; ++q)
+          memcpy(orc_rotor_wiP(r, ib) + (size_t)VLC_WINGPANEL_DOUBLES * q + WP_VELCP, v + 3 * ((size_t)q + (size_t)npb * ib),
+                 3 * sizeof(double));
+    free(v);
+    CK(rc);
+  }
+  for (int ir = 0; ir < u->nr; ++ir) CK(o->solve_map_gam(u, ir, ROT(u, ir)->gamVec));
+  u->cp_rhs_calls++;
+  return 0;
+}
+
+/* main.f90:630-663 + calc_secAlpha + calc_force of rotor ir down to the blade sums */
+static int h_cp_forces(void *user, int ir) {
+  gpu_user_t *u = (gpu_user_t *)user;
+  const cp_ops_t *o = u->cp;
+  const orc_config_t *cfg = orc_case_config(u->cas);
+  orc_rotor_t *r = ROT(u, ir);
+  const int ns = r->ns;
+  for (int jr = 0; jr < u->nr; ++jr) CK(o->sync(u, jr)); /* the bound vortices of every rotor are sources */
+  double *sec = (double *)malloc(sizeof(double) * (size_t)SEC_N(ns)), *l = (double *)malloc(sizeof(double) * (size_t)LOADS_N(ns));
+  int rc = 0;
+  for (int ib = 0; ib < r->nb && !rc; ++ib) {
+    const orc_blade_t *b = &r->blade[ib];
+    memcpy(sec, b->secTauCapChord, sizeof(double) * 3 * (size_t)ns);
+    memcpy(sec + 3 * ns, b->secNormalVec, sizeof(double) * 3 * (size_t)ns);
+    memcpy(sec + 6 * ns, b->secCP, sizeof(double) * 3 * (size_t)ns);
+    memcpy(sec + 9 * ns, b->secArea, sizeof(double) * (size_t)ns);
+    memcpy(sec + 10 * ns, b->yAxisAziFlap, 3 * sizeof(double));
+    memcpy(sec + 10 * ns + 3, b->zAxisAziFlap, 3 * sizeof(double));
+    rc = o->put_sections(u, ir, ib, sec);
+  }
+  if (!rc) rc = o->calc_velCPTotal(u, ir);
+  if (!rc) rc = o->calc_force(u, ir, cfg->density, cfg->dt, r->Omega, r->spanwiseLiftSwitch);
+  for (int ib = 0; ib < r->nb && !rc; ++ib) {
+    orc_blade_t *b = &r->blade[ib];
+    if (ib >= r->nbConvect && r->axisymmetrySwitch != 1) continue;
+    if ((rc = o->get_wing(u, ir, ib, orc_rotor_wiP(r, ib)))) break;
+    if ((rc = o->get_loads(u, ir, ib, l))) break;
+    double *s3[7] = {ib < r->nbConvect ? b->secChordwiseResVel : NULL, b->secDragDir, b->secLiftDir, b->secForceInertial,
+                     b->secLift, b->secDrag, b->secLiftUnsteady};
+    double *s1[4] = {b->secAlpha, b->secCL, b->secCD, b->secCLu};
+    memcpy(b->forceInertial, l, 3 * sizeof(double));
+    memcpy(b->lift, l + 3, 3 * sizeof(double));
+    memcpy(b->drag, l + 6, 3 * sizeof(double));
+    memcpy(b->liftUnsteady, l + 9, 3 * sizeof(double));
+    for (int k = 0; k < 7; ++k)
+      if (s3[k]) memcpy(s3[k], l + 12 + 3 * ns * k, sizeof(double) * 3 * (size_t)ns);
+    for (int k = 0; k < 4; ++k) memcpy(s1[k], l + 12 + 21 * ns + ns * k, sizeof(double) * (size_t)ns);
+  }
+  free(sec);
+  free(l);
+  u->cp_force_calls++;
+  return u->last_rc = rc;
+}
+
 /* Declares every rotor to the library (gpu_init of the Fortran shim) and installs the hook table.
  * The case must have its rotors initialised (orc_case_init_rotors).  Returns an opaque handle (free with
  * case_gpu_hooks_free) or NULL. */
@@ -370,6 +574,38 @@ void *case_cpu_staged_hooks_install(orc_case_t *cas, int nr) {
   return u;
 }
 
+/* Adds the collocation-point stage (tier 2c) to an installed table: the RHS / solve / map_gam of the time loop and the
+ * force evaluation go through the stage's calls -- to the C ABI when the handle drives a library context, to the CPU
+ * emulation otherwise. */
+int case_hooks_enable_cp(void *handle) {
+  gpu_user_t *u = (gpu_user_t *)handle;
+  if (u->ctx) {
+    u->cp = &gpu_cp_ops;
+    for (int ir = 0; ir < u->nr; ++ir) { /* nbConvect and the axisymmetry switch (resident mode sets them again, identically) */
+      const orc_rotor_t *r = ROT(u, ir);
+      int rc = vlc_rotor_set_wake_params(u->ctx, ir, r->nbConvect, r->axisymmetrySwitch, r->ductSwitch, r->suppressFwakeSwitch,
+                                         r->rollupStart, r->rollupEnd, r->Omega * r->controlPitch[0], r->apparentViscCoeff,
+                                         r->decayCoeff, r->initWakeVel);
+      if (rc) return u->last_rc = rc;
+    }
+  } else {
+    u->cp = &cpu_cp_ops;
+    u->emu = (cp_emu_t *)calloc((size_t)u->nr, sizeof(cp_emu_t));
+    for (int ir = 0; ir < u->nr; ++ir) {
+      const orc_rotor_t *r = ROT(u, ir);
+      const size_t npb = (size_t)r->nc * r->ns;
+      u->emu[ir].wiP = (double *)calloc(npb * r->nb * VLC_WINGPANEL_DOUBLES, sizeof(double));
+      u->emu[ir].sec = (double *)calloc((size_t)SEC_N(r->ns) * r->nb, sizeof(double));
+      u->emu[ir].loads = (double *)calloc((size_t)LOADS_N(r->ns) * r->nb, sizeof(double));
+      u->emu[ir].rhs = (double *)calloc(npb * r->nb, sizeof(double));
+    }
+  }
+  orc_case_set_cp_hooks(u->cas, u, h_cp_rhs_solve, h_cp_forces);
+  return 0;
+}
+long case_hooks_cp_rhs_calls(void *handle) { return ((gpu_user_t *)handle)->cp_rhs_calls; }
+long case_hooks_cp_force_calls(void *handle) { return ((gpu_user_t *)handle)->cp_force_calls; }
+
 /* resident mode: bring the device's wake (records and velocity arrays) back into the driver's arrays */
 int case_gpu_hooks_download_wake(void *handle) {
   gpu_user_t *u = (gpu_user_t *)handle;
@@ -405,4 +641,16 @@ long case_gpu_hooks_wing_uploads(void *handle) { return ((gpu_user_t *)handle)->
 long case_gpu_hooks_uploads(void *handle) { return ((gpu_user_t *)handle)->uploads; }
 long case_gpu_hooks_skipped(void *handle) { return ((gpu_user_t *)handle)->skipped; }
 int case_gpu_hooks_last_rc(void *handle) { return ((gpu_user_t *)handle)->last_rc; }
-void case_gpu_hooks_free(void *handle) { free(handle); }
+void case_gpu_hooks_free(void *handle) {
+  gpu_user_t *u = (gpu_user_t *)handle;
+  if (u && u->emu) {
+    for (int ir = 0; ir < u->nr; ++ir) {
+      free(u->emu[ir].wiP);
+      free(u->emu[ir].sec);
+      free(u->emu[ir].loads);
+      free(u->emu[ir].rhs);
+    }
+    free(u->emu);
+  }
+  free(u);
+}

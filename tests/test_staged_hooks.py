@@ -24,6 +24,11 @@ def _lib():
     lib.case_cpu_staged_hooks_install.restype = C.c_void_p
     lib.case_cpu_staged_hooks_install.argtypes = [C.c_void_p, C.c_int]
     lib.case_gpu_hooks_free.argtypes = [C.c_void_p]
+    lib.case_hooks_enable_cp.argtypes = [C.c_void_p]
+    lib.case_hooks_cp_rhs_calls.argtypes = [C.c_void_p]
+    lib.case_hooks_cp_rhs_calls.restype = C.c_long
+    lib.case_hooks_cp_force_calls.argtypes = [C.c_void_p]
+    lib.case_hooks_cp_force_calls.restype = C.c_long
     return lib
 
 
@@ -93,4 +98,66 @@ def test_staged_orchestration_two_rotors(oracle):
         assert np.array_equal(a.force_nondim(ir), b.force_nondim(ir))
         for ib in range(a.rotor(ir).nb):
             assert np.array_equal(a.rotor(ir).waN(ib), b.rotor(ir).waN(ib))
+    lib.case_gpu_hooks_free(h)
+
+
+SEC3 = ("secChordwiseResVel", "secDragDir", "secLiftDir", "secForceInertial", "secLift", "secDrag", "secLiftUnsteady")
+SEC1 = ("secAlpha", "secCL", "secCD", "secCLu")
+
+
+@pytest.mark.parametrize("name,nsteps,mutate", [CASES[0], CASES[3], CASES[4], CASES[6]])
+def test_cp_stage_orchestration_equals_inline_time_loop(oracle, name, nsteps, mutate):
+    """The collocation-point stage (tier 2c) through the C twin's orchestration -- h_cp_rhs_solve / h_cp_forces with
+    their write-backs into the driver's records -- against a CPU emulation of the library (own record copies, the g++
+    build of cp_stage.cuh, the oracle's sweeps): forces, circulations, wing records and every sectional array of the
+    driver BIT-IDENTICAL to its inline statement of main.f90:522-670."""
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    fx["config"]["rotorForcePlot"] = 1
+    if mutate:
+        mutate(fx)
+    lib = _lib()
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    b.init_rotors()
+    h = lib.case_cpu_staged_hooks_install(b.h, b.nr)
+    assert h and lib.case_hooks_enable_cp(h) == 0
+    a.init()
+    b.init()
+    for it in range(nsteps):
+        a.step()
+        b.step()
+        assert np.array_equal(a.force_nondim(0), b.force_nondim(0)), (name, it + 1)
+        assert a.pairs_last_step == b.pairs_last_step, (name, it + 1, a.pairs_last_step, b.pairs_last_step)
+    assert lib.case_hooks_cp_rhs_calls(h) == nsteps and lib.case_hooks_cp_force_calls(h) == nsteps + 1
+    ra, rb = a.rotor(0), b.rotor(0)
+    for w in range(3):
+        assert np.array_equal(ra.vec(w), rb.vec(w)), (name, "vec", w)      # gamVec, RHS, gamVecPrev
+    for ib in range(ra.nb):
+        assert np.array_equal(ra.wiP(ib), rb.wiP(ib)), (name, "wiP", ib)
+        assert np.array_equal(ra.waN(ib), rb.waN(ib)), (name, "waN", ib)
+        for n in SEC3:
+            assert np.array_equal(ra.sec(ib, n, 3), rb.sec(ib, n, 3)), (name, ib, n)
+        for n in SEC1:
+            assert np.array_equal(ra.sec(ib, n), rb.sec(ib, n)), (name, ib, n)
+    lib.case_gpu_hooks_free(h)
+
+
+def test_cp_stage_orchestration_two_rotors(oracle):
+    from tests.test_oracle_case import two_body_case
+    fx = two_body_case()
+    fx["config"]["rotorForcePlot"] = 1
+    lib = _lib()
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    b.init_rotors()
+    h = lib.case_cpu_staged_hooks_install(b.h, b.nr)
+    assert h and lib.case_hooks_enable_cp(h) == 0
+    a.init()
+    b.init()
+    for it in range(6):
+        a.step()
+        b.step()
+    for ir in range(2):
+        assert np.array_equal(a.force_nondim(ir), b.force_nondim(ir))
+        assert np.array_equal(a.rotor(ir).vec(0), b.rotor(ir).vec(0))
+        for ib in range(a.rotor(ir).nb):
+            assert np.array_equal(a.rotor(ir).wiP(ib), b.rotor(ir).wiP(ib))
     lib.case_gpu_hooks_free(h)
