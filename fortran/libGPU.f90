@@ -24,6 +24,9 @@ module libGPU
   ! device-resident time stepping (tier 2b of the C ABI): the wake is uploaded once and every wake mutator of the time
   ! loop runs on the library's copies; tests/native/case_gpu_hooks.c (resident mode) is the tested C twin
   public :: gpu_resident_begin, gpu_wake_prestep, gpu_wake_convect, gpu_download_wake
+  ! collocation-point stage on the device (tier 2c of the C ABI): velCP, RHS, solve, map_gam and -- forceCalcSwitch 0 --
+  ! velCPTotal and the sectional loads; tests/native/case_gpu_hooks.c (h_cp_rhs_solve / h_cp_forces) is the tested C twin
+  public :: gpu_cp_rhs_solve, gpu_cp_forces
   logical, save :: resident = .false.
   integer(c_int), parameter :: VEL_FIRST_STEP = 0, VEL_AB2 = 1, VEL_AM2 = 2, VEL_SHIFT_HISTORY = 3, VEL_ORDER2 = 4
 
@@ -227,6 +230,49 @@ module libGPU
       type(c_ptr), value :: c
       integer(c_int), value :: ir, ib, predicted
       real(c_double), intent(out) :: waF(*)
+    end function
+    ! tier 2c
+    integer(c_int) function vlc_rotor_calc_RHS(c, ir, velCP_out, RHS_out) bind(C, name='vlc_rotor_calc_RHS')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), intent(out) :: velCP_out(3, *), RHS_out(*)
+    end function
+    integer(c_int) function vlc_rotor_solve_map_gam(c, ir, gamVec_out) bind(C, name='vlc_rotor_solve_map_gam')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), intent(out) :: gamVec_out(*)
+    end function
+    integer(c_int) function vlc_rotor_put_sections(c, ir, ib, sec) bind(C, name='vlc_rotor_put_sections')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib
+      real(c_double), intent(in) :: sec(*)
+    end function
+    integer(c_int) function vlc_rotor_calc_velCPTotal(c, ir) bind(C, name='vlc_rotor_calc_velCPTotal')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+    end function
+    integer(c_int) function vlc_rotor_calc_force(c, ir, density, dt, Omega, spanwiseLiftSwitch) &
+        & bind(C, name='vlc_rotor_calc_force')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, spanwiseLiftSwitch
+      real(c_double), value :: density, dt, Omega
+    end function
+    integer(c_int) function vlc_rotor_get_loads(c, ir, ib, loads) bind(C, name='vlc_rotor_get_loads')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib
+      real(c_double), intent(out) :: loads(*)
+    end function
+    integer(c_int) function vlc_rotor_get_wing(c, ir, ib, wiP) bind(C, name='vlc_rotor_get_wing')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib
+      real(c_double), intent(out) :: wiP(*)
     end function
   end interface
 
@@ -535,6 +581,94 @@ contains
       call check(vlc_rotor_assignshed(ctx, ir - 1, 1_c_int))
     enddo
   end subroutine gpu_wake_convect
+
+  ! ------------------------------------------------------------------ collocation-point stage (tier 2c)
+
+  subroutine gpu_cp_rhs_solve(rotor)
+    !! Replaces main.f90:548-603 for every rotor inside the time loop (ntSub = 0).  The driver keeps :528-547 -- it writes
+    !! the kinematic part into wiP%velCP / velCPm -- saves gamVecPrev, calls gpu_touch(ir, GPU_WING) and then this routine;
+    !! velCP, RHS, gamVec come back, the wing circulation is mapped on both sides (rotor%map_gam() here, map_gam on the
+    !! device), so the wing is NOT stale afterwards.
+    type(rotor_class), intent(inout) :: rotor(:)
+    integer :: ir, ib, ic, is, q
+    real(c_double), allocatable :: velCP(:, :)
+    do ir = 1, size(rotor)
+      call gpu_sync_rotor(rotor(ir), ir, .false.)
+    enddo
+    do ir = 1, size(rotor)
+      allocate (velCP(3, rotor(ir)%nbConvect*rotor(ir)%nc*rotor(ir)%ns))
+      call check(vlc_rotor_calc_RHS(ctx, ir - 1, velCP, rotor(ir)%RHS))
+      q = 0
+      do ib = 1, rotor(ir)%nbConvect      ! wiP order: ic fastest, then is, then the blade
+        do is = 1, rotor(ir)%ns
+          do ic = 1, rotor(ir)%nc
+            q = q + 1
+            rotor(ir)%blade(ib)%wiP(ic, is)%velCP = velCP(:, q)
+          enddo
+        enddo
+      enddo
+      deallocate (velCP)
+    enddo
+    do ir = 1, size(rotor)
+      call check(vlc_rotor_solve_map_gam(ctx, ir - 1, rotor(ir)%gamVec))
+      call rotor(ir)%map_gam()
+    enddo
+  end subroutine gpu_cp_rhs_solve
+
+  subroutine gpu_cp_forces(rotor, ir, density, dt)
+    !! Replaces main.f90:630-663 and rotor(ir)%calc_secAlpha() / %calc_force(density, dt) (forceCalcSwitch 0) down to the
+    !! blade sums; the driver then calls rotor(ir)%sumBladeToNetForces() (classdef.f90:4954-4988).
+    type(rotor_class), intent(inout) :: rotor(:)
+    integer, intent(in) :: ir
+    real(dp), intent(in) :: density, dt
+    integer :: jr, ib, ns, k
+    real(c_double), allocatable :: sec(:), loads(:), buf(:)
+    ns = rotor(ir)%ns
+    do jr = 1, size(rotor)                ! the bound vortices of every rotor are sources
+      call gpu_sync_rotor(rotor(jr), jr, .false.)
+    enddo
+    allocate (sec(10*ns + 6), loads(12 + 25*ns))
+    do ib = 1, rotor(ir)%nb
+      associate (b => rotor(ir)%blade(ib))
+        sec(1:3*ns) = reshape(b%secTauCapChord, [3*ns])
+        sec(3*ns + 1:6*ns) = reshape(b%secNormalVec, [3*ns])
+        sec(6*ns + 1:9*ns) = reshape(b%secCP, [3*ns])
+        sec(9*ns + 1:10*ns) = b%secArea
+        sec(10*ns + 1:10*ns + 3) = b%yAxisAziFlap
+        sec(10*ns + 4:10*ns + 6) = b%zAxisAziFlap
+      end associate
+      call check(vlc_rotor_put_sections(ctx, ir - 1, ib - 1, sec))
+    enddo
+    call check(vlc_rotor_calc_velCPTotal(ctx, ir - 1))
+    call check(vlc_rotor_calc_force(ctx, ir - 1, density, dt, rotor(ir)%Omega, rotor(ir)%spanwiseLiftSwitch))
+    do ib = 1, rotor(ir)%nb
+      if (ib > rotor(ir)%nbConvect .and. rotor(ir)%axisymmetrySwitch /= 1) cycle
+      associate (b => rotor(ir)%blade(ib))
+        allocate (buf(104*rotor(ir)%nc*ns))
+        call check(vlc_rotor_get_wing(ctx, ir - 1, ib - 1, buf))
+        b%wiP = reshape(transfer(buf, b%wiP), shape(b%wiP))   ! gamPrev, gamTrapz, delP, normalForce, velCPTotal ...
+        deallocate (buf)
+        call check(vlc_rotor_get_loads(ctx, ir - 1, ib - 1, loads))
+        b%forceInertial = loads(1:3)
+        b%lift = loads(4:6)
+        b%drag = loads(7:9)
+        b%liftUnsteady = loads(10:12)
+        k = 12
+        if (ib <= rotor(ir)%nbConvect) b%secChordwiseResVel = reshape(loads(k + 1:k + 3*ns), [3, ns])
+        b%secDragDir = reshape(loads(k + 3*ns + 1:k + 6*ns), [3, ns])
+        b%secLiftDir = reshape(loads(k + 6*ns + 1:k + 9*ns), [3, ns])
+        b%secForceInertial = reshape(loads(k + 9*ns + 1:k + 12*ns), [3, ns])
+        b%secLift = reshape(loads(k + 12*ns + 1:k + 15*ns), [3, ns])
+        b%secDrag = reshape(loads(k + 15*ns + 1:k + 18*ns), [3, ns])
+        b%secLiftUnsteady = reshape(loads(k + 18*ns + 1:k + 21*ns), [3, ns])
+        k = 12 + 21*ns
+        b%secAlpha = loads(k + 1:k + ns)
+        b%secCL = loads(k + ns + 1:k + 2*ns)
+        b%secCD = loads(k + 2*ns + 1:k + 3*ns)
+        b%secCLu = loads(k + 3*ns + 1:k + 4*ns)
+      end associate
+    enddo
+  end subroutine gpu_cp_forces
 
   subroutine gpu_download_wake(rotor)
     !! Bring the device's wake records back into the driver's derived types (before wake plots / restart files).

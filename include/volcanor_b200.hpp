@@ -131,6 +131,20 @@ class Rotor {
   void wakevel_op(int op) { c_.check(vlc_rotor_wakevel_op(c_.handle(), ir_, op)); }
   void get_nwake(int ib, double* waN, bool predicted = false) { c_.check(vlc_rotor_get_nwake(c_.handle(), ir_, ib, predicted, waN)); }
   void get_fwake(int ib, double* waF, bool predicted = false) { c_.check(vlc_rotor_get_fwake(c_.handle(), ir_, ib, predicted, waF)); }
+  // tier 2c: the collocation-point stage on the device copies of the wing records (main.f90:548-670)
+  void calc_RHS(double* velCP_out = nullptr, double* RHS_out = nullptr) {
+    c_.check(vlc_rotor_calc_RHS(c_.handle(), ir_, velCP_out, RHS_out));
+  }
+  void solve_map_gam(double* gamVec_out = nullptr) { c_.check(vlc_rotor_solve_map_gam(c_.handle(), ir_, gamVec_out)); }
+  void put_sections(int ib, const double* sec) { c_.check(vlc_rotor_put_sections(c_.handle(), ir_, ib, sec)); }
+  void calc_velCPTotal() { c_.check(vlc_rotor_calc_velCPTotal(c_.handle(), ir_)); }
+  void calc_force(double density, double dt, double Omega, int spanwiseLiftSwitch = 0) {  // + calc_secAlpha
+    c_.check(vlc_rotor_calc_force(c_.handle(), ir_, density, dt, Omega, spanwiseLiftSwitch));
+  }
+  void get_loads(int ib, double* loads) { c_.check(vlc_rotor_get_loads(c_.handle(), ir_, ib, loads)); }
+  void get_wing(int ib, double* wiP) { c_.check(vlc_rotor_get_wing(c_.handle(), ir_, ib, wiP)); }
+  int sections_doubles() const { return 10 * ns_ + 6; }
+  int loads_doubles() const { return 12 + 25 * ns_; }
   Context& context() const { return c_; }
   int index() const { return ir_; }
 

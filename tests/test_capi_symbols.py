@@ -48,3 +48,10 @@ def test_product_does_not_reference_oracle():
         assert "pyoracle" not in txt and "vlc_oracle" not in txt and "orc_" not in txt, p
     out = subprocess.run(["ldd", str(vb.lib_path())], capture_output=True, text=True).stdout
     assert "oracle" not in out
+    # outside tests/ only bench.py (cpu_baseline / --impl reference) and __graft_entry__ (build, smoke) may use the oracle
+    repo = root.parent
+    for d in ("tools", "include", "fortran"):
+        for p in (repo / d).rglob("*"):
+            if p.is_file() and p.suffix in (".py", ".sh", ".h", ".hpp", ".f90", ".cu", ".c", ".cpp"):
+                txt = p.read_text()
+                assert "pyoracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, p

@@ -3,7 +3,7 @@
 path on the GPU (tests/native/case_gpu_hooks.c), prints CT history checkpoints and timings.  Test infrastructure
 (uses oracle/): a profiling aid for profiles/, not a benchmark arm.
 
-  python tools/run_case_native.py caradonna [nsteps] [--resident]     (--resident: tier 2b, the wake stays on the device)
+  python tests/tools/run_case_native.py caradonna [nsteps] [--resident]     (--resident: tier 2b, the wake stays on the device)
 """
 import json
 import sys
@@ -12,7 +12,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 
 

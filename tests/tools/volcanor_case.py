@@ -4,14 +4,14 @@ reference's driver and writes Results/r01ForceNonDim.csv in the reference's own 
 demonstration of the caller side of the path; `--gpu` forwards the hot path to libvolcanor_b200.so
 through tests/native/case_gpu_hooks.c, without it the CPU oracle computes everything.
 
-  python tools/volcanor_case.py /path/to/some.case [--gpu] [--nt N] [--out DIR]
+  python tests/tools/volcanor_case.py /path/to/some.case [--gpu] [--nt N] [--out DIR]
 """
 import argparse
 import sys
 import time
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 
 
