@@ -73,20 +73,13 @@ def read_case(case_dir) -> dict:
 
 
 def fortran_e15_7(x: float) -> str:
-    """One value in Fortran E15.7: 0.dddddddE+xx right-justified in 15 columns."""
+    """One value in Fortran E15.7: 0.dddddddE+xx right-justified in 15 columns (correctly rounded from the exact
+    binary value, like gfortran's formatted write)."""
     if x == 0.0 or not math.isfinite(x):
         return "  0.0000000E+00" if x == 0.0 else f"{x:>15}"
-    sign = "-" if x < 0 else ""
-    a = abs(x)
-    e = math.floor(math.log10(a)) + 1
-    mant = round(a / 10.0 ** e * 1e7)
-    if mant >= 10 ** 7:                      # rounding carried into the next decade
-        mant //= 10
-        e += 1
-    elif mant < 10 ** 6:                     # log10 landed one decade high
-        e -= 1
-        mant = round(a / 10.0 ** e * 1e7)
-    return f"{sign}0.{mant:07d}E{'+' if e >= 0 else '-'}{abs(e):02d}".rjust(15)
+    mant, exp = f"{abs(x):.6E}".split("E")
+    e = int(exp) + 1
+    return f"{'-' if x < 0 else ''}0.{mant.replace('.', '')}E{'+' if e >= 0 else '-'}{abs(e):02d}".rjust(15)
 
 
 def force_nondim_line(it: int, f) -> str:
