@@ -69,3 +69,21 @@ def test_tma_bulk_copy_and_no_local_memory_in_hot_kernels(sass):
         assert "UBLKCP" in body, kernel                          # cp.async.bulk (1-D TMA) staging of the source tiles
         assert "SYNCS" in body, kernel                           # mbarrier
         assert not re.search(r"\b(LDL|STL)\b", body), kernel     # no local-memory traffic
+
+
+def test_bit_exact_record_kernels_have_no_contracted_fma(sass):
+    """The O(N) kernels whose results must equal the CPU restatement bit for bit (tier 2b wake mutators without a
+    division or a square root, the tier 2c accumulate / RHS kernels) contain no DFMA at all: every product and sum is a
+    separately rounded DMUL / DADD, as written (`__dmul_rn`, `__dadd_rn`).  Division and square root expand into
+    Newton iterations that use DFMA internally and round correctly; kernels containing them are checked on data."""
+    path, _ = sass
+    text = path.read_text()
+    for kernel in ("cp_rhs_kernel", "cp_accumulate_kernel", "cp_copy_field_kernel", "cp_map_gam_kernel", "rec_age_kernel",
+                   "rec_accumulate_kernel"):
+        start = text.index(kernel)
+        nxt = text.find("Function :", start + 10)
+        body = text[start:nxt] if nxt > 0 else text[start:]
+        assert "DFMA" not in body, kernel
+    start = text.index("cp_rhs_kernel")
+    body = text[start:text.find("Function :", start + 10)]
+    assert len(re.findall(r"\bDMUL\b", body)) == 4 and len(re.findall(r"\bDADD\b", body)) == 2, body   # 3 products + (-1)*, 2 sums
