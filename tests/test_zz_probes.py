@@ -64,6 +64,19 @@ def test_probe_velocities_vs_oracle(oracle, tmp_path):
         scale = max(scale, float(np.abs(a).max()), float(np.abs(b).max()))
     assert np.array_equal(loc, probe + probeVel * t)
     assert np.max(np.abs(vel - ref)) < 1e-12 * 50.0 * scale, (float(np.max(np.abs(vel - ref))), scale)
+    # inflow2file: -zAxis inflow at the section points of the rotor's blades (main.f90:771)
+    rot = rots[1]
+    secCP = np.stack([rot.sec(ib, "secCP", 3) for ib in range(rot.nb)])
+    d = np.array([0.0, 0.0, -1.0])
+    got = probes.inflow_velocities(ctx, len(rots), secCP, d)
+    P = secCP.reshape(-1, 3)
+    refi = np.zeros(P.shape[0])
+    for r in rots:
+        refi = refi + r.vind_points(0, P) @ d
+        refi = refi - r.vind_points(3, P) @ d
+        refi = refi + r.vind_points(1, P) @ d
+    assert got.shape == (rot.nb, rot.ns)
+    assert np.max(np.abs(got.ravel() - refi)) < 1e-12 * 50.0 * max(scale, float(np.abs(refi).max())), float(np.max(np.abs(got.ravel() - refi)))
     out = probes.probes2file(ctx, len(rots), tmp_path, "00010", probe, probeVel, t)
     assert out.name == "probes00010.csv" and len(out.read_text().splitlines()) == 65
     ctx.close()

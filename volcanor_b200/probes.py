@@ -1,6 +1,7 @@
 """The caller side of the reference's velocity probes (`switches%probe`, src/main.f90:83-93, :792-797;
 `probes2file`, src/libPostprocess.f90:333-361): `probes.in` reader, the probe velocities through the batched point
-calls of the C ABI, and `Results/probesNNNNN.csv` in the reference's format.
+calls of the C ABI, and `Results/probesNNNNN.csv` in the reference's format; the blade inflow of `inflow2file`
+(libPostprocess.f90:900-945) through the same calls.
 
     vel(:, i) = probeVel(:, i) + sum over rotors of [vind_bywing(P_i) + vind_bywake(P_i)],   P_i = probe(:, i) + probeVel(:, i)*t
 
@@ -36,6 +37,24 @@ def probe_velocities(ctx, n_rotors: int, probe, probeVel, t: float) -> tuple[np.
     for ir in range(n_rotors):                      # :349-353, terms added left to right
         vel = (vel + ctx.rotor_vind_bywing(ir, loc)) + ctx.rotor_vind_bywake(ir, loc)
     return vel, loc
+
+
+def inflow_velocities(ctx, n_rotors: int, secCP, directionVector) -> np.ndarray:
+    """The inflow along `directionVector` at the section points of one rotor's blades (`inflow2file`,
+    libPostprocess.f90:900-928): secCP (nb, ns, 3) -> inflowVel (nb, ns) = sum over rotors of
+    dot(vind_bywing - vind_bywing_boundVortices + vind_bywake, directionVector), terms added in the reference's order."""
+    secCP = np.ascontiguousarray(secCP, dtype=np.float64)
+    P = secCP.reshape(-1, 3)
+    d = np.asarray(directionVector, dtype=np.float64).reshape(3)
+
+    def dot(v):  # dot_product of each row with d, unfused
+        return (v[:, 0] * d[0] + v[:, 1] * d[1]) + v[:, 2] * d[2]
+    inflow = np.zeros(P.shape[0])
+    for ir in range(n_rotors):                      # :913-921
+        inflow = inflow + dot(ctx.rotor_vind_bywing(ir, P))
+        inflow = inflow - dot(ctx.rotor_vind_bywing_boundVortices(ir, P))
+        inflow = inflow + dot(ctx.rotor_vind_bywake(ir, P))
+    return inflow.reshape(secCP.shape[:-1])
 
 
 def fortran_e(x: float, width: int = 15, digits: int = 7) -> str:
