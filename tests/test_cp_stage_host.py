@@ -140,3 +140,19 @@ def test_rhs_and_map_gam_follow_the_oracle(oracle, name, nsteps, mutate):
     rot.lib.orc_rotor_map_gam(rot.h)
     ref = np.concatenate([rot.wiP(ib).reshape(-1) for ib in range(nb)])
     assert np.array_equal(wiP, ref)
+
+
+# ---- the bodies of the GPU tests (tests/test_zz_gpu_cp_stage.py) on the CPU stand-in for the library's tier 2c
+
+@pytest.mark.parametrize("name,nsteps,mutate", [("katzNplotkin_AR04", 6, None), ("elevateTest", 5, _mut(nNwake=6))])
+def test_gpu_test_body_calc_force_on_the_emulation(oracle, name, nsteps, mutate):
+    from tests.cp_stage_emulation import EmulatedCpContext
+    from tests.test_zz_gpu_cp_stage import check_calc_force
+    check_calc_force(EmulatedCpContext(host_lib()), oracle, name, nsteps, mutate)
+
+
+@pytest.mark.parametrize("case", ["elevateTest", "two_body"])
+def test_gpu_test_body_rhs_solve_velcptotal_on_the_emulation(oracle, case):
+    from tests.cp_stage_emulation import EmulatedCpContext
+    from tests.test_zz_gpu_cp_stage import check_rhs_solve_velcptotal
+    check_rhs_solve_velcptotal(EmulatedCpContext(host_lib()), oracle, case)

@@ -44,6 +44,8 @@ def _developed(oracle, fx, nsteps):
 def _define(ctx, rot, ir, wake=True):
     d, p = rot.dims(), rot.params()
     ctx.rotor_define(ir, rot.nb, rot.nc, rot.ns, rot.nNwake, rot.nFwake, 1)
+    if hasattr(ctx, "attach_sources"):
+        ctx.attach_sources(ir, rot)
     ctx.rotor_set_wake_params(ir, p["nbConvect"], p["axisymmetrySwitch"], p["ductSwitch"], p["suppressFwakeSwitch"],
                               p["rollupStart"], p["rollupEnd"], p["Omega"] * p["theta0"], p["apparentViscCoeff"],
                               p["decayCoeff"], p["initWakeVel"])
@@ -62,6 +64,11 @@ def _define(ctx, rot, ir, wake=True):
                                                 ("elevateTest", 5, _mut(nNwake=6)),
                                                 ("simplewing", 4, _mut(spanwiseLiftSwitch=1))])
 def test_calc_force_bit_identical_to_the_oracle(cctx, oracle, name, nsteps, mutate):
+    check_calc_force(cctx, oracle, name, nsteps, mutate)
+
+
+def check_calc_force(cctx, oracle, name, nsteps, mutate):
+    """Body of the test above; also run on the CPU stand-in of tests/cp_stage_emulation.py (tests/test_cp_stage_host.py)."""
     fx = json.loads((GOLDEN / f"{name}.json").read_text())
     fx["config"]["rotorForcePlot"] = 1
     if mutate:
@@ -108,6 +115,10 @@ def _two_body():
 
 @pytest.mark.parametrize("case", ["caradonna", "elevateTest", "two_body"])
 def test_rhs_solve_and_velcptotal_vs_oracle(cctx, oracle, case):
+    check_rhs_solve_velcptotal(cctx, oracle, case)
+
+
+def check_rhs_solve_velcptotal(cctx, oracle, case):
     if case == "two_body":
         fx, nsteps = _two_body(), 10
     else:
