@@ -1751,7 +1751,7 @@ double *orc_blade_sec(orc_rotor_t *r, int ib, const char *name) {
   S(secChord); S(secArea); S(secAlpha); S(secCL); S(secCLu); S(secCD); S(secMflapArm);
   S(secForceInertial); S(secLift); S(secDrag); S(secLiftDir); S(secDragDir); S(secLiftUnsteady);
   S(secTauCapChord); S(secTauCapSpan); S(secNormalVec); S(secCP); S(secChordwiseResVel);
-  S(forceInertial); S(lift); S(drag); S(liftUnsteady); S(yAxisAziFlap); S(zAxisAziFlap);
+  S(forceInertial); S(lift); S(drag); S(liftUnsteady); S(yAxisAziFlap); S(zAxisAziFlap); S(yAxis);
 #undef S
   return NULL;
 }

@@ -88,6 +88,13 @@ def case_fixture(case_dir: Path, name: str, n_rotors: int = 1, results: bool = T
             cols = lines[0].split()
             rows = [[float(x) for x in l.split()] for l in lines[1:] if l.strip()]
             fx["ref_ForceDist"] = {"file": dist[0].name, "columns": cols, "rows": rows}
+            # every sectional distribution the reference ships (libPostprocess.f90:849-881, format 16(E15.7)), by time step
+            fx["ref_ForceDists"] = []
+            for f in dist:
+                ls = f.read_text().splitlines()
+                fx["ref_ForceDists"].append({"file": f.name, "iter": int(re.search(r"ForceDist(\d+)", f.name).group(1)),
+                                             "columns": ls[0].split(),
+                                             "rows": [[float(x) for x in l.split()] for l in ls[1:] if l.strip()]})
         pj = ref / "r01Params.json.ref"
         if pj.exists():
             fx["ref_Params"] = json.loads(pj.read_text())

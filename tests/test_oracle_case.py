@@ -167,9 +167,11 @@ def _history(oracle, name, nsteps=None):
     ref = np.array(fx["ref_ForceNonDim"]["rows"])
     n = c.config.nt if nsteps is None else min(nsteps, c.config.nt)
     hist = [c.force_nondim(0)]
+    c.dists_checked = 0
     for _ in range(n):
         c.step()
         hist.append(c.force_nondim(0))
+        c.dists_checked += check_force_dist(c, fx, c.iter) > 0     # r01b01ForceDistNNNNN.csv.ref of this step, if shipped
     return c, np.array(hist), ref
 
 
@@ -178,6 +180,39 @@ def _digits7(a, b):
     b = np.asarray(b, dtype=float)
     ulp = 10.0 ** (np.floor(np.log10(np.maximum(np.abs(b), 1e-300))) - 6)
     return np.abs(np.asarray(a) - b) / ulp
+
+
+def force_dist_columns(c, ir=0, ib=0):
+    """The columns of rNNbMMForceDistNNNNN.csv (force2file, libPostprocess.f90:849-881) that the hot path and the loads
+    determine, from the driver's sectional arrays: {column index: values(ns)}.  secLiftInPl/OutPl, secTheta, secPhi,
+    secViz, secVix are output-only diagnostics outside the restatement."""
+    r = c.rotor(ir)
+    p = r.params()
+    yAxis = r.sec(ib, "yAxis", 3)[0]
+    n3 = lambda a: np.sqrt(a[:, 0] * a[:, 0] + a[:, 1] * a[:, 1] + a[:, 2] * a[:, 2])
+    return {0: (r.sec(ib, "secCP", 3) - p["hubCoords"]) @ yAxis, 1: r.sec(ib, "secCL"), 2: r.sec(ib, "secCD"),
+            3: r.sec(ib, "secCLu"), 4: n3(r.sec(ib, "secLift", 3)), 5: n3(r.sec(ib, "secDrag", 3)), 8: r.sec(ib, "secArea"),
+            9: n3(r.sec(ib, "secChordwiseResVel", 3)), 10: r.sec(ib, "secChord"), 12: np.degrees(r.sec(ib, "secAlpha"))}
+
+
+def check_force_dist(c, fx, it):
+    """Sectional distribution of time step `it` against the reference's golden file, 7 printed digits (a value that
+    prints as 0.0000000E+00 is compared absolutely).  secCLu is a TIME DIFFERENCE of circulations over dt
+    (delPUnsteady, classdef.f90:1786): where it is 1e-2 ... 1e-4 of secCL (elevateTest at step 150: steady hover) the
+    ~1e-9 agreement of the circulations that the rolled-up wake of that case allows leaves it 5-6 digits, so this one
+    column is held to max(7th digit, 1e-7 * secCL); at step 1 and in the K&P file it agrees to the 7th digit as well."""
+    found = [d for d in fx.get("ref_ForceDists", []) if d["iter"] == it]
+    if not found:
+        return 0
+    ref = np.array(found[0]["rows"])
+    cols = force_dist_columns(c)
+    for k, v in cols.items():
+        d = _digits7(v, ref[:, k])
+        d = np.where(ref[:, k] == 0.0, np.abs(v) / 1e-7, d)
+        if k == 3:
+            d = np.minimum(d, np.abs(v - ref[:, 3]) / (1e-7 * np.abs(ref[:, 1])))
+        assert d.max() <= 1.0, (found[0]["file"], found[0]["columns"][k], float(d.max()), int(d.argmax()))
+    return len(cols)
 
 
 def test_katzNplotkin_AR04_CL_history_matches_reference_file(oracle):
@@ -193,6 +228,7 @@ def test_katzNplotkin_AR04_CL_history_matches_reference_file(oracle):
     assert abs(hist[50, 0] - 0.3118085) < 5e-8            # CL at iter 50
     if FULL:
         assert abs(hist[-1, 0] - ref[-1, 1]) < 5e-7 and abs(hist[-10:, 0].mean() - ref[-10:, 1].mean()) < 5e-7
+        assert c.dists_checked == 1                       # r01b01ForceDist00160: sectional loads to 7 digits
 
 
 def test_elevateTest_CT_history_matches_reference_file(oracle):
@@ -206,6 +242,7 @@ def test_elevateTest_CT_history_matches_reference_file(oracle):
         dd = _digits7(hist[:, col], ref[:hist.shape[0], rc])
         assert dd.max() <= 1.0, (col, dd.max(), int(dd.argmax()))
     assert abs(hist[150, 0] - 0.01940482) < 5e-9
+    assert c.dists_checked == 2                           # r01b01ForceDist00001 / 00150: sectional loads to 7 digits
 
 
 def test_pair_count_matches_survey_table(oracle):

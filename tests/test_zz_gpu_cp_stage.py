@@ -7,8 +7,9 @@ through the C ABI on the GPU:
  2. vlc_rotor_calc_RHS / _solve_map_gam / _calc_velCPTotal against the oracle's sweeps added in the driver's order
     (tolerance 1e-12 of the velocity scale, the per-call bar of the sweeps), two rotors included;
  3. whole cases with the stage on the device (tests/native/case_gpu_hooks.c: h_cp_rhs_solve / h_cp_forces), wake
-    resident: both golden histories of the reference to 7 digits on every row, CL/CT and circulations against the CPU
-    driver within 1e-8.
+    resident: both golden histories of the reference to 7 digits on every row and its golden sectional distributions
+    (r01b01ForceDistNNNNN.csv.ref: secCL, secCLu, secLift, secVel, secAlpha ...) from the device's loads, CL/CT and
+    circulations against the CPU driver within 1e-8.
 
 Runs last (file name) and on its own library context: the stage sums over every rotor the context knows."""
 import json
@@ -243,11 +244,14 @@ def test_cp_stage_run_reproduces_reference_golden_history(cctx, oracle, name, ns
     c = oracle.Case(fx)
     lib, h = _cp_hooks(c, cctx)
     c.init()
+    from tests.test_oracle_case import check_force_dist
     hist = [c.force_nondim(0)]
     t1 = time.perf_counter()
+    dists = 0
     for it in range(nsteps):
         _step(c, lib, h, cctx, it + 1)
         hist.append(c.force_nondim(0))
+        dists += check_force_dist(c, fx, it + 1) > 0      # the reference's r01b01ForceDistNNNNN.csv.ref of this step
     t2 = time.perf_counter()
     hist = np.array(hist)
     ref = np.array(fx["ref_ForceNonDim"]["rows"])
@@ -259,6 +263,8 @@ def test_cp_stage_run_reproduces_reference_golden_history(cctx, oracle, name, ns
           f"the 7th digit")
     assert lib.case_hooks_cp_rhs_calls(h) == nsteps and lib.case_hooks_cp_force_calls(h) >= nsteps
     assert dev.max() <= 1.0, (dev.max(), int(dev.argmax()))
+    # the sectional loads came from the device (vlc_rotor_calc_force): the golden distributions to 7 digits as well
+    assert dists == len(fx["ref_ForceDists"])
     lib.case_gpu_hooks_free(h)
 
 
