@@ -335,6 +335,13 @@ int vlc_gridgen(vlc_ctx* ctx, int nx, int ny, int nz, const double* xyzMin, cons
                 int64_t nVrWing, const double* vrWing, int64_t nVrNwake, const double* vrNwake, int64_t nVfNwakeTE,
                 const double* vfNwakeTE, const double* gamNwakeTE, int64_t nVfFwake, const double* vfFwake,
                 const double* gamFwake, double* gridCentre, double* velCentre);
+/* The same for cells [first, first + count) of the cell list (x fastest, then y, then z): gridCentre (may be NULL) and
+ * velCentre are (3, count).  One process per GPU takes a contiguous slice each (the cells are independent,
+ * gridgen.f90:116-139) and the slices are gathered by the caller (volcanor_b200/gridgen.py under torchrun). */
+int vlc_gridgen_slice(vlc_ctx* ctx, int nx, int ny, int nz, const double* xyzMin, const double* xyzMax, const double* vel,
+                      int64_t nVrWing, const double* vrWing, int64_t nVrNwake, const double* vrNwake, int64_t nVfNwakeTE,
+                      const double* vfNwakeTE, const double* gamNwakeTE, int64_t nVfFwake, const double* vfFwake,
+                      const double* gamFwake, int64_t first, int64_t count, double* gridCentre, double* velCentre);
 
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Register-resident DFMA chains on every SM: returns sustained FP64 FMA rate in flop/s (DFMA = 2)

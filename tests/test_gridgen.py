@@ -75,3 +75,26 @@ def test_vlc_gridgen_rejects_inverted_box(ctx):
     z50, z12, z1 = np.zeros((0, 50)), np.zeros((0, 12)), np.zeros(0)
     with pytest.raises(vb.VlcError):
         ctx.gridgen(3, 3, 3, [1.0, 0, 0], [0.0, 1, 1], [0, 0, 0], z50, z50, z12, z1, z12, z1)   # gridgen.f90:43-45
+
+
+@pytest.mark.gpu
+def test_vlc_gridgen_slices_cover_the_full_call(ctx, oracle):
+    """vlc_gridgen_slice (one process per GPU takes a contiguous slice of the cell list): same cell centres bit for bit,
+    velocities as the full call up to the summation order of the source split (1e-13 of the velocity scale)."""
+    import volcanor_b200 as vb
+    vrWing, vrN, te, gte, vfF, gF = _filament_file(oracle, seed=9)
+    nx, ny, nz = 12, 9, 6
+    lo, hi, vel = np.array([-2.0, -1.5, -1.0]), np.array([2.0, 1.5, 0.5]), np.array([3.0, 0.0, -1.0])
+    args = (nx, ny, nz, lo, hi, vel, vrWing, vrN, te, gte, vfF, gF)
+    gc, vc = ctx.gridgen(*args)
+    m = (nx - 1) * (ny - 1) * (nz - 1)
+    scale = max(float(np.max(np.abs(vc - vel))), 1.0)
+    for world in (2, 3):
+        per = (m + world - 1) // world
+        parts = [ctx.gridgen_slice(*args, r * per, min(per, m - r * per)) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), gc.reshape(-1, 3))
+        assert np.max(np.abs(np.concatenate([p[1] for p in parts]) - vc.reshape(-1, 3))) < 1e-13 * 50 * scale
+    g0, v0 = ctx.gridgen_slice(*args, 7, 0)
+    assert g0.shape == (0, 3) and v0.shape == (0, 3)
+    with pytest.raises(vb.VlcError, match="cell slice"):
+        ctx.gridgen_slice(*args, m - 3, 4)

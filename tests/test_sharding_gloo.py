@@ -76,3 +76,59 @@ def test_shard_arithmetic(m, world):
         assert 0 <= s.lo <= s.hi <= m and s.count <= s.per and s.padded >= m
         covered += list(range(s.lo, s.hi))
     assert covered == list(range(m))                         # contiguous, disjoint, complete
+
+
+# ---- gridgen: the cell list sharded across ranks (volcanor_b200/gridgen.py:sharded_velocities) ----
+
+class _OracleGridCtx:
+    """Stand-in for Context.gridgen / .gridgen_slice backed by the oracle's restatement of program gridgen (test
+    infrastructure): the host logic under test is the slicing and the gather, not the velocities."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def gridgen(self, *a):
+        return self.o.gridgen(*a)
+
+    def gridgen_slice(self, *a):
+        *args, first, count = a
+        gc, vc = self.o.gridgen(*args)
+        return gc.reshape(-1, 3)[first:first + count].copy(), vc.reshape(-1, 3)[first:first + count].copy()
+
+
+def _grid_case():
+    rng = np.random.default_rng(5)
+    f = {"vrWing": np.zeros((0, 50)), "vrNwake": np.zeros((0, 50)), "vfNwakeTE": np.zeros((0, 12)), "gamNwakeTE": np.zeros(0),
+         "vfFwake": np.concatenate([rng.uniform(-1, 1, (40, 6)), np.zeros((40, 3)), np.full((40, 1), 0.05), np.zeros((40, 2))], axis=1),
+         "gamFwake": rng.uniform(-1, 1, 40)}
+    cfg = {"nx": 6, "ny": 5, "nz": 4, "xyzMin": [-2.0, -1.5, -1.0], "xyzMax": [2.0, 1.5, 0.5], "vel": [3.0, 0.0, -1.0]}
+    return cfg, f
+
+
+def _grid_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      OMP_NUM_THREADS="2")
+    import torch.distributed as dist
+    from oracle import pyoracle
+    from volcanor_b200 import gridgen
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg, f = _grid_case()
+    vc = gridgen.sharded_velocities(_OracleGridCtx(pyoracle), cfg, f, world, rank)
+    np.save(Path(out_dir) / f"vc_rank{rank}.npy", vc)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gridgen_cells_sharded_across_ranks(tmp_path, oracle, world):
+    """60 cells over 2 and 3 ranks (3: the last slice is shorter than the others): every rank ends with the whole field,
+    equal to the single-process call."""
+    import torch.multiprocessing as mp
+    from volcanor_b200 import gridgen
+    mp.start_processes(_grid_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    cfg, f = _grid_case()
+    ref = gridgen.sharded_velocities(_OracleGridCtx(oracle), cfg, f, 1, 0)
+    assert ref.shape == (3, 4, 5, 3) and np.any(ref != np.array(cfg["vel"]))
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"vc_rank{r}.npy"), ref), r

@@ -156,6 +156,8 @@ def load_library() -> C.CDLL:
         "vlc_lattice_targets_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_lattice_scatter_dev": (i32, [_vp, i32, i32, _vp, _vp]),
         "vlc_gridgen": (i32, [_vp, i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, _vp, _vp]),
+        "vlc_gridgen_slice": (i32, [_vp, i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, i64, i64,
+                                    _vp, _vp]),
         "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
         "vlc_measure_fp64_rate": (i32, [_vp, i32, i32, _dp, _dp]),
         "vlc_probe_rsqrt": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
@@ -502,6 +504,17 @@ class Context:
         self._ck(self.lib.vlc_gridgen(self.h, nx, ny, nz, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), a[3].size // VR_DOUBLES,
                                       _ptr(a[3]), a[4].size // VR_DOUBLES, _ptr(a[4]), a[5].size // 12, _ptr(a[5]),
                                       _ptr(a[6]), a[7].size // 12, _ptr(a[7]), _ptr(a[8]), _ptr(gc), _ptr(vc)))
+        return gc, vc
+
+    def gridgen_slice(self, nx, ny, nz, xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake,
+                      first, count):
+        """Cells [first, first+count) of program gridgen's cell list: (gridCentre, velCentre), each (count, 3)."""
+        a = [_f64(x) for x in (xyzMin, xyzMax, vel, vrWing, vrNwake, vfNwakeTE, gamNwakeTE, vfFwake, gamFwake)]
+        gc, vc = np.empty((count, 3)), np.empty((count, 3))
+        self._ck(self.lib.vlc_gridgen_slice(self.h, nx, ny, nz, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), a[3].size // VR_DOUBLES,
+                                            _ptr(a[3]), a[4].size // VR_DOUBLES, _ptr(a[4]), a[5].size // 12, _ptr(a[5]),
+                                            _ptr(a[6]), a[7].size // 12, _ptr(a[7]), _ptr(a[8]), int(first), int(count),
+                                            _ptr(gc) if count else None, _ptr(vc) if count else None))
         return gc, vc
 
     # -- tier 3 (device pointers: torch tensors or ints) --------------------------------------

@@ -2357,15 +2357,18 @@ extern "C" int vlc_lattice_scatter_dev(vlc_ctx* c, int nrows, int ns, double* no
 
 // ============================================================================ gridgen
 
-extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyzMin, const double* xyzMax,
-                           const double* vel, int64_t nVrWing, const double* vrWing, int64_t nVrNwake,
-                           const double* vrNwake, int64_t nVfNwakeTE, const double* vfNwakeTE, const double* gamNwakeTE,
-                           int64_t nVfFwake, const double* vfFwake, const double* gamFwake, double* gridCentre,
-                           double* velCentre) {
+// Cells [first, first + count) of the grid (x fastest, then y, then z): one process per GPU takes a contiguous slice
+// of the cell list, like the wake sweeps (targets are independent, gridgen.f90:116-139 is a loop over cells).
+extern "C" int vlc_gridgen_slice(vlc_ctx* c, int nx, int ny, int nz, const double* xyzMin, const double* xyzMax,
+                                 const double* vel, int64_t nVrWing, const double* vrWing, int64_t nVrNwake,
+                                 const double* vrNwake, int64_t nVfNwakeTE, const double* vfNwakeTE, const double* gamNwakeTE,
+                                 int64_t nVfFwake, const double* vfFwake, const double* gamFwake, int64_t first, int64_t count,
+                                 double* gridCentre, double* velCentre) {
   CHECK_CTX(c);
   int rc = bind_device(c);
   if (rc) return rc;
-  if (nx < 2 || ny < 2 || nz < 2 || !xyzMin || !xyzMax || !vel || !velCentre) return fail(c, VLC_ERR_ARG, "bad grid arguments");
+  if (nx < 2 || ny < 2 || nz < 2 || !xyzMin || !xyzMax || !vel || (count > 0 && !velCentre))
+    return fail(c, VLC_ERR_ARG, "bad grid arguments");
   if (xyzMin[0] > xyzMax[0] || xyzMin[1] > xyzMax[1] || xyzMin[2] > xyzMax[2])
     return fail(c, VLC_ERR_ARG, "ERROR: All XYZmin values should be greater than XYZmax values");  // gridgen.f90:43-45
   if (nVrWing < 0 || nVrNwake < 0 || nVfNwakeTE < 0 || nVfFwake < 0 || (nVrWing > 0 && !vrWing) ||
@@ -2428,6 +2431,8 @@ extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyz
   s.n_lat = s.n_lat_pad = s.n_rem = s.n_rem_pad = s.n_lat2 = s.n_lat2_pad = 0;
   // targets = cell centres, computed on the device with the file's arithmetic
   const long long m = (long long)(nx - 1) * (ny - 1) * (nz - 1);
+  if (first < 0 || count < 0 || first + count > m) return fail(c, VLC_ERR_ARG, "cell slice outside [0, (nx-1)(ny-1)(nz-1))");
+  if (count == 0) return VLC_OK;
   if ((rc = reserve(c, c->stage_P, 3 * (size_t)m))) return rc;
   if ((rc = reserve(c, c->stage_V, 3 * (size_t)m))) return rc;
   const double dx = (xyzMax[0] - xyzMin[0]) / (nx - 1), dy = (xyzMax[1] - xyzMin[1]) / (ny - 1),
@@ -2435,15 +2440,27 @@ extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyz
   vlc::grid_centres_kernel<<<blocks_for(m, 256), 256, 0, st>>>(nx, ny, nz, xyzMin[0], xyzMin[1], xyzMin[2], dx, dy, dz,
                                                                 c->stage_P.p);
   c->launches++;
-  if ((rc = sweep(c, s.rec.p, s.n_pad, m, c->stage_P.p, c->stage_V.p))) return rc;
-  vlc::add_freestream_kernel<<<blocks_for(m, 256), 256, 0, st>>>(m, vel[0], vel[1], vel[2], c->stage_V.p);
+  const double* dP = c->stage_P.p + 3 * (size_t)first;
+  double* dV = c->stage_V.p + 3 * (size_t)first;
+  if ((rc = sweep(c, s.rec.p, s.n_pad, count, dP, dV))) return rc;
+  vlc::add_freestream_kernel<<<blocks_for(count, 256), 256, 0, st>>>(count, vel[0], vel[1], vel[2], dV);
   c->launches++;
   CUDA_OK(c, cudaGetLastError());
-  if (gridCentre)
-    CUDA_OK(c, cudaMemcpyAsync(gridCentre, c->stage_P.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(c, cudaMemcpyAsync(velCentre, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, st));
+  if (gridCentre) CUDA_OK(c, cudaMemcpyAsync(gridCentre, dP, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(c, cudaMemcpyAsync(velCentre, dV, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost, st));
   CUDA_OK(c, cudaStreamSynchronize(st));
   return VLC_OK;
+}
+
+extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyzMin, const double* xyzMax,
+                           const double* vel, int64_t nVrWing, const double* vrWing, int64_t nVrNwake,
+                           const double* vrNwake, int64_t nVfNwakeTE, const double* vfNwakeTE, const double* gamNwakeTE,
+                           int64_t nVfFwake, const double* vfFwake, const double* gamFwake, double* gridCentre,
+                           double* velCentre) {
+  if (nx < 2 || ny < 2 || nz < 2) return fail(c, VLC_ERR_ARG, "bad grid arguments");
+  return vlc_gridgen_slice(c, nx, ny, nz, xyzMin, xyzMax, vel, nVrWing, vrWing, nVrNwake, vrNwake, nVfNwakeTE, vfNwakeTE,
+                           gamNwakeTE, nVfFwake, vfFwake, gamFwake, 0, (int64_t)(nx - 1) * (ny - 1) * (nz - 1), gridCentre,
+                           velCentre);
 }
 
 // ============================================================================ measurement

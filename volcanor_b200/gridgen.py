@@ -142,26 +142,65 @@ def read_tecplot(path):
     return nx, ny, nz, nodes, vel
 
 
-def run(case_dir, ctx=None, verbose=True) -> list:
-    """program gridgen in `case_dir` (reads gridconfig.nml and Results/filamentsNNNNN.dat, writes Results/gridNNNNN.tec)."""
+def sharded_velocities(ctx, cfg, f, world: int = 1, rank: int = 0, gather=None) -> np.ndarray:
+    """velCentre (nz-1, ny-1, nx-1, 3) of one filaments record set with the cell list cut into contiguous slices, one
+    per rank (one process per GPU; the cells are independent, gridgen.f90:116-139).  `gather(padded, shard)` all-gathers
+    the (world*per, 3) host array in place (default: torch.distributed, any backend); world == 1 is the plain call."""
+    from .sharding import TargetShard
+    nx, ny, nz = cfg["nx"], cfg["ny"], cfg["nz"]
+    m = (nx - 1) * (ny - 1) * (nz - 1)
+    args = (nx, ny, nz, cfg["xyzMin"], cfg["xyzMax"], cfg["vel"], f["vrWing"], f["vrNwake"], f["vfNwakeTE"], f["gamNwakeTE"],
+            f["vfFwake"], f["gamFwake"])
+    if world == 1:
+        return ctx.gridgen(*args)[1]
+    sh = TargetShard(m, world, rank)
+    padded = np.zeros((sh.padded, 3))
+    if sh.count > 0:
+        padded[sh.lo:sh.hi] = ctx.gridgen_slice(*args, sh.lo, sh.count)[1]
+    (gather or _allgather_host)(padded, sh)
+    return padded[:m].reshape(nz - 1, ny - 1, nx - 1, 3)
+
+
+def _allgather_host(padded: np.ndarray, sh) -> None:
+    """All-gather of the ranks' row slices of a host array through torch.distributed (NCCL needs device tensors)."""
+    import torch
+    import torch.distributed as dist
+    from .sharding import allgather_slices
+    t = torch.from_numpy(padded)
+    if dist.get_backend() == "nccl":
+        d = t.cuda()
+        allgather_slices(d, sh)
+        t.copy_(d.cpu())
+    else:
+        allgather_slices(t, sh)
+
+
+def run(case_dir, ctx=None, verbose=True, world: int | None = None, rank: int | None = None, gather=None) -> list:
+    """program gridgen in `case_dir` (reads gridconfig.nml and Results/filamentsNNNNN.dat, writes Results/gridNNNNN.tec).
+    Under torchrun (WORLD_SIZE > 1, process group initialised by the caller) every rank evaluates its slice of the cells
+    and rank 0 writes the files."""
+    import os
     from .api import Context
     case_dir = Path(case_dir)
     cfg = read_gridconfig(case_dir / "gridconfig.nml")
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
     own = ctx is None
-    ctx = ctx or Context(0)          # raises without a CUDA device: no CPU path
+    ctx = ctx or Context(int(os.environ.get("LOCAL_RANK", "0")))          # raises without a CUDA device: no CPU path
     written = []
     try:
         for k in range(cfg["fileRangeStart"], cfg["fileRangeEnd"] + 1, cfg["fileRangeStep"]):
             stamp = f"{k:05d}"
             f = read_filaments(case_dir / "Results" / f"filaments{stamp}.dat")
-            _, vc = ctx.gridgen(cfg["nx"], cfg["ny"], cfg["nz"], cfg["xyzMin"], cfg["xyzMax"], cfg["vel"], f["vrWing"],
-                                f["vrNwake"], f["vfNwakeTE"], f["gamNwakeTE"], f["vfFwake"], f["gamFwake"])
+            vc = sharded_velocities(ctx, cfg, f, world, rank, gather)
             out = case_dir / "Results" / f"grid{stamp}.tec"
-            write_tecplot(out, cfg["nx"], cfg["ny"], cfg["nz"], cfg["xyzMin"], cfg["xyzMax"], vc)
+            if rank == 0:
+                write_tecplot(out, cfg["nx"], cfg["ny"], cfg["nz"], cfg["xyzMin"], cfg["xyzMax"], vc)
             written.append(out)
-            if verbose:
+            if verbose and rank == 0:
                 nfil = 4 * (len(f["vrWing"]) + len(f["vrNwake"])) + len(f["vfNwakeTE"]) + len(f["vfFwake"])
-                print(f"grid{stamp}.tec: {(cfg['nx'] - 1) * (cfg['ny'] - 1) * (cfg['nz'] - 1)} cell centres x {nfil} filaments")
+                print(f"grid{stamp}.tec: {(cfg['nx'] - 1) * (cfg['ny'] - 1) * (cfg['nz'] - 1)} cell centres x {nfil} filaments"
+                      + (f" on {world} GPUs" if world > 1 else ""))
     finally:
         if own:
             ctx.close()
@@ -169,4 +208,10 @@ def run(case_dir, ctx=None, verbose=True) -> list:
 
 
 if __name__ == "__main__":
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:          # torchrun: one process per GPU
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     run(sys.argv[1] if len(sys.argv) > 1 else ".")
