@@ -103,6 +103,7 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_rotor_calc_force": (None, [_vp, d, d]),
         "orc_rotor_sum_forces": (None, [_vp]),
         "orc_rotor_get_force_params": (None, [_vp, _vp]),
+        "orc_rotor_get_file_params": (None, [_vp, _vp]),
         "orc_blade_sec": (_vp, [_vp, i32, C.c_char_p]),
     }
     for name, (res, args) in sig.items():

@@ -521,6 +521,18 @@ void orc_rotor_get_force_params(const orc_rotor_t *r, double out[4]) {
   out[2] = r->axisymmetrySwitch;
   out[3] = r->nbConvect;
 }
+/* what params2file writes about a rotor (libPostprocess.f90:76-128) as far as rotor_init derives it:
+ * out[0..7] = radius root_cut chord Omega nonDimforceDenominator nNwake wakeTruncateNt prescWakeNt */
+void orc_rotor_get_file_params(const orc_rotor_t *r, double out[8]) {
+  out[0] = r->radius;
+  out[1] = r->root_cut;
+  out[2] = r->chord;
+  out[3] = r->Omega;
+  out[4] = r->nonDimforceDenominator;
+  out[5] = r->nNwake;
+  out[6] = r->wakeTruncateNt;
+  out[7] = r->prescWakeNt;
+}
 /* classdef.f90:4623-4671: the copies for an axisymmetric rotor + sumBladeToNetForces :4954-4988 */
 void orc_rotor_sum_forces(orc_rotor_t *r) {
   if (r->axisymmetrySwitch == 1) {

@@ -114,6 +114,8 @@ void orc_rotor_calc_secAlpha(orc_rotor_t *r);
 void orc_rotor_calc_force(orc_rotor_t *r, double density, double dt);
 /* the tail of rotor_calc_force: copies for an axisymmetric rotor + sumBladeToNetForces (classdef.f90:4623-4671) */
 void orc_rotor_sum_forces(orc_rotor_t *r);
+/* out[0..7] = radius root_cut chord Omega nonDimforceDenominator nNwake wakeTruncateNt prescWakeNt (params2file) */
+void orc_rotor_get_file_params(const orc_rotor_t *r, double out[8]);
 /* out[0..3] = Omega, spanwiseLiftSwitch, axisymmetrySwitch, nbConvect */
 void orc_rotor_get_force_params(const orc_rotor_t *r, double out[4]);
 double *orc_blade_sec(orc_rotor_t *r, int ib, const char *name); /* sectional arrays by name */

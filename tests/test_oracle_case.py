@@ -245,6 +245,24 @@ def test_elevateTest_CT_history_matches_reference_file(oracle):
     assert c.dists_checked == 2                           # r01b01ForceDist00001 / 00150: sectional loads to 7 digits
 
 
+@pytest.mark.parametrize("name", ["katzNplotkin_AR04", "elevateTest"])
+def test_derived_run_parameters_match_reference_params_file(oracle, name):
+    """r01Params.json.ref (params2file, libPostprocess.f90:52-141): what rotor%init derives from the case files -- dt and
+    nt from revolutions / chords, nNwake and the truncation step from revolutions, the radius from the PLOT3D grid, the
+    denominator of the force coefficients -- to the digits of the list-directed write (1e-14 relative)."""
+    fx = json.loads((GOLDEN / f"{name}.json").read_text())
+    ref = fx["ref_Params"]
+    c = oracle.Case(fx)
+    c.init_rotors()
+    r = c.rotor(0)
+    o = np.zeros(8)
+    r.lib.orc_rotor_get_file_params(r.h, o.ctypes.data)
+    got = dict(radius=o[0], root_cut=o[1], chord=o[2], Omega=o[3], nonDimForceDenom=o[4], nNwake=o[5], wakeTruncateNt=o[6],
+               prescWakeNt=o[7], nt=c.config.nt, dt=c.config.dt, nb=r.nb, nc=r.nc, ns=r.ns)
+    for k, v in got.items():
+        assert abs(v - ref[k]) <= 1e-14 * abs(ref[k]), (k, v, ref[k])
+
+
 def test_pair_count_matches_survey_table(oracle):
     """SURVEY D: K&P AR-4 at iter 50 evaluates ~1.6e7 pair interactions per step (reference enumeration)."""
     fx = json.loads((GOLDEN / "katzNplotkin_AR04.json").read_text())
