@@ -94,6 +94,7 @@ static double pwl_interp1d(int n, const double *x, const double *y, double q) {
   if (idx < 0) idx = 0; /* the reference error-stops when out of range; never hit for chordwiseFraction in (0,1) */
   return y[idx] + (y[idx + 1] - y[idx]) / (x[idx + 1] - x[idx]) * (q - x[idx]);
 }
+double orc_pwl_interp1d(int n, const double *x, const double *y, double q) { return pwl_interp1d(n, x, y, q); } /* KAT access */
 /* libMath.f90:577-605 lsq2_scalar.  The reference inverts the 3x3 normal matrix with its native Doolittle
  * `inv` (libMath.f90:293-426); here the same system is solved by Gaussian elimination with partial pivoting
  * (the quantity only feeds the direction of secChordwiseResVel; agreement is to rounding). */

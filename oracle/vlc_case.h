@@ -106,6 +106,7 @@ void orc_rotor_wake_to_predicted(orc_rotor_t *r);
 int orc_rotor_wakevel_op(orc_rotor_t *r, int op);
 
 /* pieces exposed for the KAT tests */
+double orc_pwl_interp1d(int n, const double *x, const double *y, double q); /* libMath.f90:476-517 */
 int orc_case_init_rotors(orc_case_t *c); /* main.f90:31-58 only: rotor%init + initial pitch */
 void orc_blade_rot_pitch(orc_blade_t *b, double theta);
 double orc_rotor_gettheta(const orc_rotor_t *r, double psi, int ib);

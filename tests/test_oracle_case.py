@@ -99,6 +99,54 @@ def test_rotor1x2_geometry_aic_gamvec_forces(oracle):
     assert np.max(np.abs(r.sec(0, "secLift", 3)[0] - [0, 0, w[0, 0, O_NF + 2]])) < TOL
 
 
+def test_rotor1x2_negative_pitch_flips_circulation_and_loads(oracle):
+    """tests/rotor1x2NegPitch_test.f90: theta0 = -5 deg.  Same AIC (:180-184), vortex-ring TE corners with +z (:114-137),
+    nCap = [st, 0, ct] with st = sin(-5 deg) (:166-170), gamVec = +[8.753162, 11.069649] (:218), secAlpha = theta0 (:239-243),
+    delP and the z components of the forces negated (:247-267), secCL = -[0.773413, 0.534898] (:269-270)."""
+    fx = {"config": dict(nt=1, dt=float(np.float32(-0.014)), density=1.2, fdScheme=3, wakeDissipation=1),
+          "geom": [_base_geom(span=2.0, rootcut=0.5, Omega=100.0, theta0=-5.0)]}
+    c = oracle.Case(fx)
+    c.init_rotors()
+    r = c.rotor(0)
+    th = np.deg2rad(-5.0)
+    ct, st = np.cos(th), np.sin(th)
+    w = r.wiP(0)
+    vf11 = np.array([[-0.75, 1.0, 0.0], [3.71826e-3, 1.0, 6.59418e-2], [3.71826e-3, 1.5, 6.59418e-2], [-0.75, 1.5, 0.0]])
+    assert np.max(np.abs(np.array([w[0, 0, 12 * f:12 * f + 3] for f in range(4)]) - vf11)) < TOL
+    for j in range(2):
+        assert np.max(np.abs(w[j, 0, O_NCAP:O_NCAP + 3] - [st, 0.0, ct])) < TOL
+    omega = np.array([0.0, 0.0, 100.0])
+    g = _solve_without_wake(r, lambda cp: -np.cross(omega, cp))
+    assert np.max(np.abs(r.AIC() - np.array([[1.600113, -0.281091], [-0.281091, 1.600113]]))) < TOL
+    assert np.max(np.abs(g - [8.753162, 11.069649])) < TOL
+    r.lib.orc_rotor_dirLiftDrag(r.h)
+    assert np.max(np.abs(r.sec(0, "secLiftDir", 3) - [0, 0, 1])) < TOL
+    assert np.max(np.abs(r.sec(0, "secDragDir", 3) - [1, 0, 0])) < TOL
+    r.lib.orc_rotor_calc_secAlpha(r.h)
+    assert np.max(np.abs(r.sec(0, "secAlpha") - th)) < TOL
+    r.lib.orc_rotor_calc_force(r.h, 1.2, c.config.dt)
+    w = r.wiP(0)
+    assert np.max(np.abs(w[:, 0, O_DELP] + [7278.445742, 9866.306155])) < TOL
+    assert np.max(np.abs(w[0, 0, O_NF:O_NF + 3] - [317.179172, 0.0, -3625.374529])) < TOL
+    assert np.max(np.abs(w[1, 0, O_NF:O_NF + 3] - [429.952620, 0.0, -4914.380941])) < TOL
+    assert np.max(np.abs(r.sec(0, "secForceInertial", 3) - w[:, 0, O_NF:O_NF + 3])) < TOL
+    assert np.max(np.abs(r.sec(0, "secLift", 3) - np.array([[0, 0, w[0, 0, O_NF + 2]], [0, 0, w[1, 0, O_NF + 2]]]))) < TOL
+    assert np.max(np.abs(r.sec(0, "secCL") + [0.773413, 0.534898])) < TOL
+
+
+def test_pwl_interp1d_kat(oracle):
+    """tests/libMath_test.f90:97-108 (pwl_interp1d, used by blade_calc_secLocations): ascending and descending abscissae."""
+    lib = oracle.load()
+    import ctypes as C
+    lib.orc_pwl_interp1d.restype = C.c_double
+    lib.orc_pwl_interp1d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+    x = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    y = 2 * x
+    assert abs(lib.orc_pwl_interp1d(5, x.ctypes.data, y.ctypes.data, 1.3) - 2.6) < TOL
+    xr, yr = x[::-1].copy(), y[::-1].copy()
+    assert abs(lib.orc_pwl_interp1d(5, xr.ctypes.data, yr.ctypes.data, 1.3) - 2.6) < TOL
+
+
 def test_rotor1x2_reverse_rotation_flips_aic_sign(oracle):
     """tests/rotor1x2Rev_test.f90:183-184: Omega = -100 -> AIC = -[1.600113, -0.281091; ...]."""
     fx = {"config": dict(nt=1, dt=-0.014, density=1.2, fdScheme=3),
