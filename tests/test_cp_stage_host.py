@@ -156,3 +156,49 @@ def test_gpu_test_body_rhs_solve_velcptotal_on_the_emulation(oracle, case):
     from tests.cp_stage_emulation import EmulatedCpContext
     from tests.test_zz_gpu_cp_stage import check_rhs_solve_velcptotal
     check_rhs_solve_velcptotal(EmulatedCpContext(host_lib()), oracle, case)
+
+
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_reference_wing1x3_force_kat_through_the_product_source(oracle, sign):
+    """The reference's own known-answer test of the loads (tests/wing1x3_test.f90:150-194, 15 digits; NegPitch variant
+    :150-194, 6 decimals) evaluated by the PRODUCT's source (cp_stage.cuh, host build): geometry and circulations from
+    the oracle's restatement of rotor%init / the solve, the loads from section_loads + blade_sum_loads."""
+    from tests.test_oracle_case import _base_geom, O_NCAP, O_VELCP, O_VELCPM, O_VELCPTOT
+    fx = {"config": dict(nt=1, dt=0.00625, density=1.2, fdScheme=3),
+          "geom": [_base_geom(spanSpacing=2, ns=3, chord=0.3, span=2.0, Omega=0.0, shaftAxis=[0, 0, 0], velBody=[-6, 0, 0],
+                              theta0=7.0 * sign, symmetricTau=1, pivotLE=0.25, apparentViscCoeff=5.0)]}
+    fx0 = json.loads(json.dumps(fx))
+    fx0["geom"][0]["theta0"] = 0.0
+    c0 = oracle.Case(fx0)
+    c0.init_rotors()
+    r0 = c0.rotor(0)
+    assert r0.calcAIC() == 0
+    c = oracle.Case(fx)
+    c.init_rotors()
+    r = c.rotor(0)
+    w = r.wiP(0)
+    for j in range(3):
+        for off in (O_VELCP, O_VELCPM, O_VELCPTOT):
+            w[j, 0, off:off + 3] = [6.0, 0.0, 0.0]
+    lib = host_lib()
+    rec = np.ascontiguousarray(w.reshape(-1))
+    rhs = np.zeros(3)
+    lib.cp_host_rhs(3, 3, 1, 0, rec.ctypes.data, rhs.ctypes.data)                 # RHS = -velCP.nCap
+    g = np.ascontiguousarray(r0.AIC(inverse=True) @ rhs)
+    assert np.max(np.abs(g - sign * np.array([-0.240131, -0.249833, -0.240131]))) < 1e-6
+    lib.cp_host_map_gam(1, 3, 1, 0, g.ctypes.data, rec.ctypes.data)
+    loads = np.zeros(12 + 25 * 3)
+    sec = pack_sections(r, 0)
+    lib.cp_host_loads(1, 1, 3, 1.2, 0.00625, 0.0, 0, rec.ctypes.data, sec.ctypes.data, loads.ctypes.data)
+    got = unpack_loads(loads, 3)
+    rec = rec.reshape(3, 1, WP)
+    tol = 1e-11 if sign > 0 else 1e-6
+    assert np.max(np.abs(rec[:, 0, 95] - sign * np.array([28.7727659410054, 29.9353746086400, 28.7727659410054]))) < tol
+    nf = np.array([[0.525977713977048, 0.0, sign * 4.28374471602321], [1.09446133444262, 0.0, sign * 8.91367225972409],
+                   [0.525977713977048, 0.0, sign * 4.28374471602321]])
+    assert np.max(np.abs(rec[:, 0, 85:88] - nf)) < tol
+    assert np.max(np.abs(got["secForceInertial"] - nf)) < tol and np.max(np.abs(got["secLift"] - nf * [0, 0, 1])) < tol
+    assert np.max(np.abs(got["secLiftDir"] - [0, 0, 1])) < 1e-12 and np.max(np.abs(got["secDragDir"] - [1, 0, 0])) < 1e-12
+    assert np.max(np.abs(got["secCL"] - sign * np.array([1.32214343087136, 1.37556670674755, 1.32214343087136]))) < tol
+    assert np.max(np.abs(got["forceInertial"] - [2.14641676239672, 0.0, sign * 17.4811616917705])) < tol
+    assert np.max(np.abs(got["lift"] - [0.0, 0.0, sign * 17.4811616917705])) < tol

@@ -208,6 +208,51 @@ def test_wing1x3_gamvec_through_driver(oracle):
     assert np.max(np.abs(g - [-0.240131, -0.249833, -0.240131])) < TOL
 
 
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_wing1x3_forces_both_pitch_signs(oracle, sign):
+    """tests/wing1x3_test.f90:100-197 and tests/wing1x3NegPitch_test.f90:100-197 (theta0 = +-7 deg): the AIC of the
+    un-pitched wing (:80-98), velCP = -velBody, gamVec, dirLiftDrag, calc_force -> delP, normalForce, secForceInertial,
+    secLift, secCL, forceInertial, lift (the positive-pitch values are given to 15 digits)."""
+    fx = {"config": dict(nt=1, dt=0.00625, density=1.2, fdScheme=3),
+          "geom": [_base_geom(spanSpacing=2, ns=3, chord=0.3, span=2.0, Omega=0.0, shaftAxis=[0, 0, 0], velBody=[-6, 0, 0],
+                              theta0=7.0 * sign, symmetricTau=1, pivotLE=0.25, apparentViscCoeff=5.0)]}
+    fx0 = json.loads(json.dumps(fx))
+    fx0["geom"][0]["theta0"] = 0.0
+    c0 = oracle.Case(fx0)
+    c0.init_rotors()
+    r0 = c0.rotor(0)
+    assert r0.calcAIC() == 0
+    c = oracle.Case(fx)
+    c.init_rotors()
+    r = c.rotor(0)
+    w = r.wiP(0)
+    th = np.deg2rad(7.0 * sign)
+    for j in range(3):
+        assert np.max(np.abs(w[j, 0, O_NCAP:O_NCAP + 3] - [np.sin(th), 0.0, np.cos(th)])) < TOL
+        for off in (O_VELCP, O_VELCPM, O_VELCPTOT):
+            w[j, 0, off:off + 3] = [6.0, 0.0, 0.0]
+    rhs = -np.array([np.dot(w[j, 0, O_VELCP:O_VELCP + 3], w[j, 0, O_NCAP:O_NCAP + 3]) for j in range(3)])
+    g = r0.AIC(inverse=True) @ rhs
+    assert np.max(np.abs(g - sign * np.array([-0.240131, -0.249833, -0.240131]))) < TOL
+    r.vec(0)[:] = g
+    r.lib.orc_rotor_map_gam(r.h)
+    r.lib.orc_rotor_dirLiftDrag(r.h)
+    assert np.max(np.abs(r.sec(0, "secLiftDir", 3) - [0, 0, 1])) < TOL
+    assert np.max(np.abs(r.sec(0, "secDragDir", 3) - [1, 0, 0])) < TOL
+    r.lib.orc_rotor_calc_force(r.h, 1.2, 0.00625)
+    w = r.wiP(0)
+    tol = 1e-11 if sign > 0 else TOL                       # 15 printed digits / 6 printed decimals
+    assert np.max(np.abs(w[:, 0, O_DELP] - sign * np.array([28.7727659410054, 29.9353746086400, 28.7727659410054]))) < tol
+    nf = np.array([[0.525977713977048, 0.0, sign * 4.28374471602321], [1.09446133444262, 0.0, sign * 8.91367225972409],
+                   [0.525977713977048, 0.0, sign * 4.28374471602321]])
+    assert np.max(np.abs(w[:, 0, O_NF:O_NF + 3] - nf)) < tol
+    assert np.max(np.abs(r.sec(0, "secForceInertial", 3) - nf)) < tol
+    assert np.max(np.abs(r.sec(0, "secLift", 3) - nf * [0, 0, 1])) < tol
+    assert np.max(np.abs(r.sec(0, "secCL") - sign * np.array([1.32214343087136, 1.37556670674755, 1.32214343087136]))) < tol
+    assert np.max(np.abs(r.sec(0, "forceInertial", 3)[0] - [2.14641676239672, 0.0, sign * 17.4811616917705])) < tol
+    assert np.max(np.abs(r.sec(0, "lift", 3)[0] - [0.0, 0.0, sign * 17.4811616917705])) < tol
+
+
 def _history(oracle, name, nsteps=None):
     fx = json.loads((GOLDEN / f"{name}.json").read_text())
     c = oracle.Case(fx)
