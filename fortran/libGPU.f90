@@ -28,7 +28,8 @@ module libGPU
   ! velCPTotal and the sectional loads; tests/native/case_gpu_hooks.c (h_cp_rhs_solve / h_cp_forces) is the tested C twin
   public :: gpu_cp_rhs_solve, gpu_cp_forces
   logical, save :: resident = .false.
-  integer(c_int), parameter :: VEL_FIRST_STEP = 0, VEL_AB2 = 1, VEL_AM2 = 2, VEL_SHIFT_HISTORY = 3, VEL_ORDER2 = 4
+  integer(c_int), parameter :: VEL_FIRST_STEP = 0, VEL_AB2 = 1, VEL_AM2 = 2, VEL_SHIFT_HISTORY = 3, VEL_ORDER2 = 4, &
+    & VEL_COPY_TO_STEP = 5
 
   type(c_ptr), save :: ctx = c_null_ptr
 
@@ -538,6 +539,18 @@ contains
       do ir = 1, size(rotor)
         call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
       enddo
+    case (2)   ! explicit Adams-Bashforth (:951-1000): velStep = vel1 = vel = 0.5*(3*vel - vel1), then convect
+      do ir = 1, size(rotor)
+        if (iter == 1) then
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_FIRST_STEP))
+        else
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_AB2))
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_FIRST_STEP))
+          call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_COPY_TO_STEP))
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+        endif
+      enddo
     case (1)
       do ir = 1, size(rotor)
         call check(vlc_rotor_wake_to_predicted(ctx, ir - 1))
@@ -568,7 +581,7 @@ contains
         enddo
       endif
     case default
-      error stop 'ERROR: gpu_wake_convect: fdScheme 2, 4, 5 are not on the device path'
+      error stop 'ERROR: gpu_wake_convect: fdScheme 4, 5 are not on the device path'
     end select
     if (wakeStrain == 1) then
       do ir = 1, size(rotor)

@@ -202,7 +202,9 @@ enum {
   VLC_VEL_AB2 = 1,           /* main.f90:1031-1041  velStep = vel; vel = 0.5*(3*vel - vel1)            */
   VLC_VEL_AM2 = 2,           /* main.f90:1094-1099  vel = (velPredicted + velStep)*0.5                 */
   VLC_VEL_SHIFT_HISTORY = 3, /* main.f90:1103-1107  vel1 = velStep                                     */
-  VLC_VEL_ORDER2 = 4         /* main.f90:927-940    vel(active) = vel_order2(vel, velPredicted)        */
+  VLC_VEL_ORDER2 = 4,        /* main.f90:927-940    vel(active) = vel_order2(vel, velPredicted)        */
+  VLC_VEL_COPY_TO_STEP = 5   /* velStep = vel; fdScheme 2 (explicit Adams-Bashforth, main.f90:975-988) is
+                                AB2, FIRST_STEP, COPY_TO_STEP: velStep = vel1 = vel = 0.5*(3*vel - vel1)   */
 };
 int vlc_rotor_wakevel_op(vlc_ctx* ctx, int ir, int op);
 /* Read the device copies back (plots, restart files, tests): whole arrays of blade ib in the reference layout.

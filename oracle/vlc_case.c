@@ -1550,13 +1550,13 @@ int orc_case_step(orc_case_t *c) {
   }
   /* wake convection, :800-1440 */
   if (cfg->wakeSuppress == 0 && c->hooks.wake_convect) { /* device-resident wake: the hook owner does :800-1440 */
-    if (cfg->fdScheme != 0 && cfg->fdScheme != 1 && cfg->fdScheme != 3) {
-      snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 3)", cfg->fdScheme);
+    if (cfg->fdScheme < 0 || cfg->fdScheme > 3) {
+      snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 2, 3)", cfg->fdScheme);
       return 3;
     }
     int rc = c->hooks.wake_convect(c->stage_user ? c->stage_user : c->hooks.user, iter);
     if (rc) return rc;
-    const int nsweeps = (cfg->fdScheme == 0 || (cfg->fdScheme == 3 && iter == 1)) ? 1 : 2;
+    const int nsweeps = (cfg->fdScheme == 0 || cfg->fdScheme == 2 || (cfg->fdScheme == 3 && iter == 1)) ? 1 : 2;
     for (int ir = 0; ir < c->nr; ++ir) { /* the same count wake_sweep() keeps */
       const orc_rotor_t *r = c->rotor[ir];
       if (r->nNwake <= 0) continue;
@@ -1617,6 +1617,32 @@ int orc_case_step(orc_case_t *c) {
           orc_rotor_convectwake(r, iter, dt, 'C');
         }
         break;
+      case 2: /* :951-1000 explicit Adams-Bashforth: one sweep per step */
+        for (int ir = 0; ir < c->nr; ++ir) {
+          orc_rotor_t *r = c->rotor[ir];
+          if (r->nNwake <= 0) continue;
+          const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
+          if (iter == 1) {
+            orc_rotor_convectwake(r, iter, dt, 'C');
+            for (int ib = 0; ib < r->nbConvect; ++ib) {
+              orc_blade_t *b = &r->blade[ib];
+              memcpy(b->velNwake1, b->velNwake, sizeof(double) * nn);
+              memcpy(b->velFwake1, b->velFwake, sizeof(double) * nf);
+            }
+          } else {
+            for (int ib = 0; ib < r->nbConvect; ++ib) { /* :975-988 */
+              orc_blade_t *b = &r->blade[ib];
+              for (size_t q = 0; q < nn; ++q) b->velNwakeStep[q] = 0.5 * (3.0 * b->velNwake[q] - b->velNwake1[q]);
+              for (size_t q = 0; q < nf; ++q) b->velFwakeStep[q] = 0.5 * (3.0 * b->velFwake[q] - b->velFwake1[q]);
+              memcpy(b->velNwake1, b->velNwakeStep, sizeof(double) * nn);
+              memcpy(b->velFwake1, b->velFwakeStep, sizeof(double) * nf);
+              memcpy(b->velNwake, b->velNwakeStep, sizeof(double) * nn);
+              memcpy(b->velFwake, b->velFwakeStep, sizeof(double) * nf);
+            }
+            orc_rotor_convectwake(r, iter, dt, 'C');
+          }
+        }
+        break;
       case 3: /* :1002-1115 */
         if (iter == 1) {
           for (int ir = 0; ir < c->nr; ++ir) {
@@ -1665,7 +1691,7 @@ int orc_case_step(orc_case_t *c) {
         }
         break;
       default:
-        snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 3)", cfg->fdScheme);
+        snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 2, 3)", cfg->fdScheme);
         return 3;
     }
     for (int ir = 0; ir < c->nr; ++ir) c->rotor[ir]->gen_wake[0]++; /* convectwake('C'), strain, roll-up, shed below */
@@ -1715,6 +1741,10 @@ int orc_rotor_wakevel_op(orc_rotor_t *r, int op) {
       case 3:
         memcpy(b->velNwake1, b->velNwakeStep, sizeof(double) * nn);
         memcpy(b->velFwake1, b->velFwakeStep, sizeof(double) * nf);
+        break;
+      case 5: /* velStep = vel (whole arrays) */
+        memcpy(b->velNwakeStep, b->velNwake, sizeof(double) * nn);
+        memcpy(b->velFwakeStep, b->velFwake, sizeof(double) * nf);
         break;
       case 4: {
         const int rowsN = r->nNwakeEnd - r->rowNear + 1, rowsF = r->nFwakeEnd - r->rowFar + 1;

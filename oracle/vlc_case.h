@@ -15,10 +15,10 @@
  * performs.
  *
  * Scope: surfaceType 1 (lifting) rotors and wings, geometryFile '0' or a PLOT3D grid passed in
- * memory, forceCalcSwitch 0, fdScheme 0/1/3, slowStart 0-3, wake dissipation / strain,
+ * memory, forceCalcSwitch 0, fdScheme 0/1/2/3, slowStart 0-3, wake dissipation / strain,
  * axisymmetry, far-wake roll-up and truncation.  Not restated (unused by every shipped case):
  * image surfaces, non-lifting STL bodies, camber files, C81 tables, blade/body dynamics, custom
- * trajectories, wake burst, prescribed far wake generation, fdScheme 2/4/5.
+ * trajectories, wake burst, prescribed far wake generation, fdScheme 4/5.
  */
 #ifndef VLC_CASE_H
 #define VLC_CASE_H

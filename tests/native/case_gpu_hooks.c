@@ -277,6 +277,19 @@ static int h_wake_convect(void *user, int iter) {
         CK(o->convectwake(u, ir, iter, dt, 0));
       }
       break;
+    case 2: /* :951-1000 explicit Adams-Bashforth: velStep = vel1 = vel = 0.5*(3*vel - vel1), then convect */
+      for (int ir = 0; ir < nr; ++ir) {
+        if (iter == 1) {
+          CK(o->convectwake(u, ir, iter, dt, 0));
+          CK(o->wakevel_op(u, ir, VLC_VEL_FIRST_STEP));
+        } else {
+          CK(o->wakevel_op(u, ir, VLC_VEL_AB2));
+          CK(o->wakevel_op(u, ir, VLC_VEL_FIRST_STEP));
+          CK(o->wakevel_op(u, ir, VLC_VEL_COPY_TO_STEP));
+          CK(o->convectwake(u, ir, iter, dt, 0));
+        }
+      }
+      break;
     case 3: /* :1002-1115 */
       if (iter == 1) {
         for (int ir = 0; ir < nr; ++ir) {

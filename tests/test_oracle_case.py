@@ -356,6 +356,28 @@ def test_derived_run_parameters_match_reference_params_file(oracle, name):
         assert abs(v - ref[k]) <= 1e-14 * abs(ref[k]), (k, v, ref[k])
 
 
+def test_fdscheme2_explicit_adams_bashforth_tracks_the_other_schemes(oracle):
+    """fdScheme 2 (main.f90:951-1000) has no golden file; it must be another consistent integrator of the same wake: over
+    40 steps of the K&P wing its CL history stays within 2e-3 of fdScheme 3's and fdScheme 1's without coinciding with
+    either.  (While a wake is still growing fdScheme 3 itself coincides with explicit Euler bit for bit: the predictor's
+    loop `do i = 1, rowNear, nNwake`, SURVEY C1, moves no active row, so velPredicted == velStep.)"""
+    hist = {}
+    for fd in (0, 1, 2, 3):
+        fx = json.loads((GOLDEN / "katzNplotkin_AR04.json").read_text())
+        fx["config"]["fdScheme"] = fd
+        c = oracle.Case(fx)
+        c.init()
+        h = []
+        for _ in range(40):
+            c.step()
+            h.append(c.force_nondim(0)[0])
+        hist[fd] = np.array(h)
+    for other in (1, 3):
+        d = np.max(np.abs(hist[2] / hist[other] - 1.0))
+        assert 0.0 < d < 2e-3, (other, d)
+    assert np.array_equal(hist[0], hist[3])
+
+
 def test_pair_count_matches_survey_table(oracle):
     """SURVEY D: K&P AR-4 at iter 50 evaluates ~1.6e7 pair interactions per step (reference enumeration)."""
     fx = json.loads((GOLDEN / "katzNplotkin_AR04.json").read_text())

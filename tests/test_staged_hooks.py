@@ -47,6 +47,7 @@ def _elevate_short(fd):
 
 
 CASES = [("katzNplotkin_AR04", 12, None), ("katzNplotkin_AR04", 8, lambda fx: fx["config"].update(fdScheme=0)),
+         ("katzNplotkin_AR04", 10, lambda fx: fx["config"].update(fdScheme=2)), ("elevateTest", 14, _elevate_short(2)),
          ("katzNplotkin_AR04", 8, lambda fx: fx["config"].update(fdScheme=1, wakeDissipation=1)),
          ("caradonna", 22, _short_caradonna), ("elevateTest", 14, _elevate_short(3)), ("elevateTest", 14, _elevate_short(1)),
          ("simplewing", 10, lambda fx: fx["config"].update(wakeStrain=1))]
@@ -105,7 +106,7 @@ SEC3 = ("secChordwiseResVel", "secDragDir", "secLiftDir", "secForceInertial", "s
 SEC1 = ("secAlpha", "secCL", "secCD", "secCLu")
 
 
-@pytest.mark.parametrize("name,nsteps,mutate", [CASES[0], CASES[3], CASES[4], CASES[6]])
+@pytest.mark.parametrize("name,nsteps,mutate", [CASES[0], CASES[5], CASES[6], CASES[8]])
 def test_cp_stage_orchestration_equals_inline_time_loop(oracle, name, nsteps, mutate):
     """The collocation-point stage (tier 2c) through the C twin's orchestration -- h_cp_rhs_solve / h_cp_forces with
     their write-backs into the driver's records -- against a CPU emulation of the library (own record copies, the g++

@@ -378,7 +378,7 @@ class Context:
         return A
 
     # ---- tier 2b: the reference's wake mutators on the device copies (device-resident stepping) ----
-    VEL_FIRST_STEP, VEL_AB2, VEL_AM2, VEL_SHIFT_HISTORY, VEL_ORDER2 = range(5)
+    VEL_FIRST_STEP, VEL_AB2, VEL_AM2, VEL_SHIFT_HISTORY, VEL_ORDER2, VEL_COPY_TO_STEP = range(6)
 
     def rotor_set_wake_params(self, ir, nbConvect, axisymmetrySwitch, ductSwitch, suppressFwakeSwitch, rollupStart,
                               rollupEnd, rollupSign, apparentViscCoeff, decayCoeff, initWakeVel=0.0):

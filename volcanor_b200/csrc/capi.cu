@@ -1774,6 +1774,9 @@ extern "C" int vlc_rotor_wakevel_op(vlc_ctx* c, int ir, int op) {
     case VLC_VEL_SHIFT_HISTORY:  // main.f90:1103-1107: vel1 = velStep
       if ((rc = copy(r->velN[1], r->velN[3], nn)) || (rc = copy(r->velF[1], r->velF[3], nf))) return rc;
       break;
+    case VLC_VEL_COPY_TO_STEP:  // velStep = vel (fdScheme 2, main.f90:975-988 together with AB2 and FIRST_STEP)
+      if ((rc = copy(r->velN[3], r->velN[0], nn)) || (rc = copy(r->velF[3], r->velF[0], nf))) return rc;
+      break;
     case VLC_VEL_ORDER2: {  // main.f90:927-940: vel(active) = vel_order2(vel(active), velPredicted(active))
       const int rowsN = r->nNwake - r->rowNear + 1, rowsF = r->nFwake - r->rowFar + 1;
       if ((rc = reserve(c, r->order2_tmp, std::max(nn, nf) + 1))) return rc;
