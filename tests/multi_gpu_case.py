@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--case", default="katzNplotkin_AR04")
     ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--short-caradonna", action="store_true", help="nt 40, nNwake 12 (roll-up inside a short window)")
+    ap.add_argument("--cp", action="store_true",
+                    help="also run the collocation-point stage (RHS, solve, map_gam, loads: C ABI tier 2c) on every rank's device")
     args = ap.parse_args()
 
     import torch
@@ -64,6 +66,10 @@ def main():
     lib.case_gpu_hooks_set_sharding.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     lib.case_gpu_hooks_exchanges.restype = C.c_long
     lib.case_gpu_hooks_exchanges.argtypes = [C.c_void_p]
+    if args.cp:                                          # O(nc*ns) stage, replicated on every rank like the wake mutators
+        lib.case_hooks_enable_cp.argtypes = [C.c_void_p]
+        if lib.case_hooks_enable_cp(h) != 0:
+            raise RuntimeError(f"case_hooks_enable_cp: {ctx.lib.vlc_last_error(ctx.h)}")
 
     m_max = 0
     for ir in range(c.nr):
@@ -125,7 +131,8 @@ def main():
         out = {"case": args.case, "world": world, "exchange": ("nccl" if own_gpu else "gloo via host") if world > 1 else "none",
                "steps": len(hist) - 1, "wall_s": max(g[1] for g in gathered), "ok": ok and not any(g[2] for g in gathered),
                "errors": [e for g in gathered for e in g[2]][:3], "ranks_identical": identical,
-               "exchanges": int(lib.case_gpu_hooks_exchanges(h)), "final_CT_or_CL": float(hist[-1, 0])}
+               "exchanges": int(lib.case_gpu_hooks_exchanges(h)), "final_CT_or_CL": float(hist[-1, 0]),
+               "cp_stage_on_device": bool(args.cp)}
         out["timesteps_per_s"] = out["steps"] / out["wall_s"] if out["wall_s"] > 0 else 0.0
         if "ref_ForceNonDim" in fx and not args.short_caradonna:
             ref = np.array(fx["ref_ForceNonDim"]["rows"])[:len(hist)]
