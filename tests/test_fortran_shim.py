@@ -210,3 +210,40 @@ def test_every_called_binding_is_declared_in_the_interface_block():
             if l[start:i - 1].strip() == "":
                 n = 0
             assert n == len(IFACES[m.group(1)]["args"]), (l, n, len(IFACES[m.group(1)]["args"]))
+
+
+REF_CLASSDEF = Path("/root/reference/src/classdef.f90")
+
+
+@pytest.mark.skipif(not REF_CLASSDEF.exists(), reason="the reference tree is only present in the build container")
+def test_every_derived_type_member_the_shim_touches_exists_in_the_reference():
+    """`rotor%blade(ib)%secTauCapChord`, `rotor%nbConvect`, `...%wiP(ic, is)%velCP`, `call rotor(ir)%map_gam()` ...: each
+    component / type-bound procedure name used after a `%` is declared in the reference's classdef.f90 (in the type that
+    owns it: rotor_class, blade_class, wingpanel_class, pFwake_class)."""
+    ref = REF_CLASSDEF.read_text()
+    types = {}
+    for m in re.finditer(r"^\s*type(?:\s*,\s*\w+)*\s*(?:::)?\s*(\w+_class)\s*$(.*?)^\s*end type", ref, flags=re.S | re.M | re.I):
+        body = m.group(2)
+        names = set()
+        for l in body.splitlines():
+            l = l.split("!")[0]
+            if "::" in l:
+                for n in re.split(r",(?![^()]*\))", l.split("::", 1)[1]):
+                    n = n.strip()
+                    if "=>" in n:
+                        n = n.split("=>")[0].strip()
+                    mm = re.match(r"\w+", n)
+                    if mm:
+                        names.add(mm.group(0).lower())
+        types[m.group(1).lower()] = names
+    assert {"rotor_class", "blade_class", "wingpanel_class"} <= set(types)
+    owner = {"rotor": "rotor_class", "blade": "blade_class", "wip": "wingpanel_class", "b": "blade_class",
+             "wapf": "pfwake_class", "wapfpredicted": "pfwake_class"}
+    checked = 0
+    for l in LINES:
+        for m in re.finditer(r"\b(\w+)(?:\([^()]*(?:\([^()]*\)[^()]*)*\))?%(\w+)", l):
+            base, member = m.group(1).lower(), m.group(2).lower()
+            if base in owner:
+                assert member in types[owner[base]], (l.strip(), base, member)
+                checked += 1
+    assert checked > 80, checked
