@@ -121,6 +121,11 @@ int vlc_rotor_vind_bywing(vlc_ctx* ctx, int ir, int64_t m, const double* P, doub
 int vlc_rotor_vind_bywake(vlc_ctx* ctx, int ir, int predicted, int64_t m, const double* P, double* V);
 /* = rotor%vind_bywing_boundVortices(P) classdef.f90:4445 */
 int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* ctx, int ir, int64_t m, const double* P, double* V);
+/* = sum over blades of blade%vind_bywing_chordwiseVortices(P) classdef.f90:1398-1418: (vf(1) + vf(3))*gam of every wing
+ * ring plus vf(2)*gam of the trailing-edge row -- the complement of the bound vortices: bywing = boundVortices +
+ * chordwiseVortices.  (The reference evaluates it only for `velInduced`, whose consumers are commented out,
+ * classdef.f90:1733-1735, :1802-1806; provided so that SURVEY 8a row a6 is complete.) */
+int vlc_rotor_vind_bywing_chordwiseVortices(vlc_ctx* ctx, int ir, int64_t m, const double* P, double* V);
 /* = vind_bywing(P) + vind_bywake(P[, 'P']) of rotor ir in one sweep */
 int vlc_rotor_vind(vlc_ctx* ctx, int ir, int predicted, int64_t m, const double* P, double* V);
 /*

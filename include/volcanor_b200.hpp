@@ -100,6 +100,9 @@ class Rotor {
   void vind_bywing_boundVortices(const double* P, std::int64_t m, double* V) {
     c_.check(vlc_rotor_vind_bywing_boundVortices(c_.handle(), ir_, m, P, V));
   }
+  void vind_bywing_chordwiseVortices(const double* P, std::int64_t m, double* V) {
+    c_.check(vlc_rotor_vind_bywing_chordwiseVortices(c_.handle(), ir_, m, P, V));
+  }
   void vind(const double* P, std::int64_t m, double* V, bool predicted = false) {
     c_.check(vlc_rotor_vind(c_.handle(), ir_, predicted, m, P, V));
   }

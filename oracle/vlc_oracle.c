@@ -1053,6 +1053,12 @@ void orc_rotor_vind_points(const orc_rotor_t *r, int what, int predicted, long m
     if (what == 0 || what == 2) orc_rotor_vind_bywing(r, &P[3 * t], a);
     if (what == 1 || what == 2) orc_rotor_vind_bywake(r, &P[3 * t], predicted, w);
     if (what == 3) orc_rotor_vind_bywing_boundVortices(r, &P[3 * t], a);
+    if (what == 4) /* sum over blades of blade%vind_bywing_chordwiseVortices (classdef.f90:1398-1418) */
+      for (int ib = 0; ib < r->nb; ++ib) {
+        double t3[3];
+        orc_blade_vind_bywing_chordwiseVortices(&r->blade[ib], &P[3 * t], t3);
+        for (int k = 0; k < 3; ++k) a[k] = a[k] + t3[k];
+      }
     for (int k = 0; k < 3; ++k) V[3 * t + k] = a[k] + w[k];
   }
 }

@@ -100,3 +100,22 @@ def test_flat_equals_structured(oracle):
     Vf = oracle.vind_flat(p1, p2, rvc, gam, flag, P)
     _, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, P)
     assert np.max(np.abs(Vs - Vf) / Vabs.max()) < 1e-14
+
+
+def test_bound_plus_chordwise_vortices_equal_the_whole_wing(oracle):
+    """classdef.f90:1376-1418: vind_bywing_boundVortices (filaments 2, 4 minus the trailing-edge row) and
+    vind_bywing_chordwiseVortices (filaments 1, 3 plus the trailing-edge row) partition the wing's rings, so their sum is
+    vind_bywing up to the order of summation."""
+    import json
+    from pathlib import Path
+    fx = json.loads((Path(__file__).resolve().parent / "golden" / "caradonna.json").read_text())
+    fx["geom"][0]["nNwake"] = 6
+    c = oracle.Case(fx)
+    c.init()
+    for _ in range(3):
+        c.step()
+    r = c.rotor(0)
+    P = np.random.default_rng(2).uniform(-1.5, 1.5, (40, 3))
+    whole, bound, chord = r.vind_points(0, P), r.vind_points(3, P), r.vind_points(4, P)
+    assert np.max(np.abs(chord)) > 0 and np.max(np.abs(bound)) > 0
+    assert np.max(np.abs(bound + chord - whole)) < 1e-13 * max(np.max(np.abs(bound)), np.max(np.abs(chord)))

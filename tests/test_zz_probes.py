@@ -77,6 +77,13 @@ def test_probe_velocities_vs_oracle(oracle, tmp_path):
         refi = refi + r.vind_points(1, P) @ d
     assert got.shape == (rot.nb, rot.ns)
     assert np.max(np.abs(got.ravel() - refi)) < 1e-12 * 50.0 * max(scale, float(np.abs(refi).max())), float(np.max(np.abs(got.ravel() - refi)))
+    # row a6 complete: the chordwise vortices (classdef.f90:1398-1418), and bound + chordwise = the whole wing
+    for ir, r in enumerate(rots):
+        ch, bd, wh = ctx.rotor_vind_bywing_chordwiseVortices(ir, loc), ctx.rotor_vind_bywing_boundVortices(ir, loc), \
+            ctx.rotor_vind_bywing(ir, loc)
+        s6 = 50.0 * max(float(np.abs(r.vind_points(4, loc)).max()), float(np.abs(r.vind_points(3, loc)).max()))
+        assert np.max(np.abs(ch - r.vind_points(4, loc))) < 1e-12 * s6
+        assert np.max(np.abs(ch + bd - wh)) < 1e-12 * s6
     out = probes.probes2file(ctx, len(rots), tmp_path, "00010", probe, probeVel, t)
     assert out.name == "probes00010.csv" and len(out.read_text().splitlines()) == 65
     ctx.close()

@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
         "vlc_rotor_vind_bywing": (i32, [_vp, i32, i64, _vp, _vp]),
         "vlc_rotor_vind_bywake": (i32, [_vp, i32, i32, i64, _vp, _vp]),
         "vlc_rotor_vind_bywing_boundVortices": (i32, [_vp, i32, i64, _vp, _vp]),
+        "vlc_rotor_vind_bywing_chordwiseVortices": (i32, [_vp, i32, i64, _vp, _vp]),
         "vlc_rotor_vind": (i32, [_vp, i32, i32, i64, _vp, _vp]),
         "vlc_vind_onNwake_byRotor": (i32, [_vp, i32, _vp, i32, i32, i32, i32, _vp]),
         "vlc_vind_onFwake_byRotor": (i32, [_vp, i32, _vp, i32, i32, _vp]),
@@ -330,6 +331,9 @@ class Context:
 
     def rotor_vind_bywing_boundVortices(self, ir, P):
         return self._points(self.lib.vlc_rotor_vind_bywing_boundVortices, P, ir)
+
+    def rotor_vind_bywing_chordwiseVortices(self, ir, P):
+        return self._points(self.lib.vlc_rotor_vind_bywing_chordwiseVortices, P, ir)
 
     def rotor_vind(self, ir, P, predicted=False):
         return self._points(self.lib.vlc_rotor_vind, P, ir, int(predicted))

@@ -78,6 +78,8 @@ struct Rotor {
   SourceSet bound;
   bool dirty[2] = {true, true};
   bool bound_dirty = true;
+  SourceSet chord;  // chordwise-vortex set (classdef.f90:1398-1418), same shape as `bound`
+  bool chord_dirty = true;
   // rows below these were not refreshed by the last put (only the active rows travel): [set][blade]
   std::vector<int> stale_near[2], stale_far[2];
   // tier 2b (device-resident stepping): rotor_class members the wake mutators read, and the velocity arrays of the
@@ -751,6 +753,36 @@ int pack_bound(vlc_ctx* c, Rotor& r) {
   return VLC_OK;
 }
 
+// chordwise-vortex set (classdef.f90:1398-1418): (vf1 + vf3)*gam of every ring, plus vf2*gam of row nc -- the same
+// layout and kernels as pack_bound with the other two filaments and the opposite sign on the trailing-edge row.
+int pack_chord(vlc_ctx* c, Rotor& r) {
+  if (!r.chord_dirty) return VLC_OK;
+  const long long per_blade = 2LL * r.nc * r.ns + r.ns;
+  const long long n = per_blade * r.nb;
+  const long long n_pad = pad_tile(n);
+  int rc = reserve(c, r.chord.rec, (size_t)n_pad * vlc::kSrcDoubles);
+  if (rc) return rc;
+  double* rec = r.chord.rec.p;
+  {
+    const long long cnt = 2LL * r.nc * r.ns, wiP_blade = (long long)r.nc * r.ns * vlc::kWp;
+    vlc::pack_rings_kernel<<<dim3(blocks_for(cnt, 256), (unsigned)r.nb, 1), 256, 0, c->stream>>>(
+        r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0x5, 2, 1.0, 0, rec, wiP_blade, per_blade);
+    vlc::pack_rings_kernel<<<dim3(blocks_for(r.ns, 128), (unsigned)r.nb, 1), 128, 0, c->stream>>>(
+        r.wiP.p, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2, 1, 1.0, 0, rec + (size_t)cnt * vlc::kSrcDoubles, wiP_blade, per_blade);
+    c->launches += 2;
+  }
+  if (n_pad > n) {
+    vlc::pack_null_kernel<<<blocks_for(n_pad - n, 256), 256, 0, c->stream>>>(n_pad - n,
+                                                                              rec + (size_t)n * vlc::kSrcDoubles);
+    c->launches++;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  r.chord.n = n;
+  r.chord.n_pad = n_pad;
+  r.chord_dirty = false;
+  return VLC_OK;
+}
+
 int upload(vlc_ctx* c, DevBuf& b, size_t total, size_t offset, const double* host, size_t count) {
   int rc = reserve(c, b, total);
   if (rc) return rc;
@@ -871,6 +903,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     release(r.order2_tmp);
     if (r.d_axi) cudaFree(r.d_axi);
     release(r.bound.rec);
+    release(r.chord.rec);
     release(r.rhs);
     release(r.gamvec);
     release(r.sec);
@@ -1069,7 +1102,7 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     r.d_axi = nullptr;
   }
   r.N = nc * ns * nb;
-  r.dirty[0] = r.dirty[1] = r.bound_dirty = true;
+  r.dirty[0] = r.dirty[1] = r.bound_dirty = r.chord_dirty = true;
   r.factored = false;
   r.have_pf[0] = r.have_pf[1] = false;
   for (int s2 = 0; s2 < 2; ++s2) {
@@ -1142,7 +1175,7 @@ extern "C" int vlc_rotor_put_wing(vlc_ctx* c, int ir, int ib, const double* wiP)
   if (!r) return VLC_ERR_STATE;
   if (ib < 0 || ib >= r->nb || !wiP) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
   const size_t per = (size_t)r->nc * r->ns * vlc::kWp;
-  r->dirty[0] = r->dirty[1] = r->bound_dirty = true;
+  r->dirty[0] = r->dirty[1] = r->bound_dirty = r->chord_dirty = true;
   // The LU factors stay valid: the reference computes AIC once, before the time loop, and keeps using it while the
   // wing moves rigidly (main.f90:65-81); only vlc_rotor_calcAIC replaces them.
   return upload(c, r->wiP, per * r->nb, per * ib, wiP, per);
@@ -1159,7 +1192,7 @@ extern "C" int vlc_rotor_put_wing_gam(vlc_ctx* c, int ir, int ib, const double* 
   CUDA_OK(c, cudaMemcpy2DAsync(r->wiP.p + (size_t)ib * np * vlc::kWp + vlc::kVrGam, vlc::kWp * sizeof(double), gam,
                                sizeof(double), sizeof(double), np, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  r->dirty[0] = r->dirty[1] = r->bound_dirty = true;
+  r->dirty[0] = r->dirty[1] = r->bound_dirty = r->chord_dirty = true;
   return VLC_OK;
 }
 
@@ -1249,6 +1282,16 @@ extern "C" int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* c, int ir, int64_t m
   if (!r) return VLC_ERR_STATE;
   if ((rc = pack_bound(c, *r))) return rc;
   return sweep_host(c, r->bound.rec.p, r->bound.n_pad, m, P, V);
+}
+
+extern "C" int vlc_rotor_vind_bywing_chordwiseVortices(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if ((rc = pack_chord(c, *r))) return rc;
+  return sweep_host(c, r->chord.rec.p, r->chord.n_pad, m, P, V);
 }
 
 extern "C" int vlc_rotor_vind(vlc_ctx* c, int ir, int predicted, int64_t m, const double* P, double* V) {
@@ -1937,7 +1980,7 @@ extern "C" int vlc_rotor_solve_map_gam(vlc_ctx* c, int ir, double* gamVec_out) {
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   r->have_rhs = false;  // one solve per right-hand side
-  r->dirty[0] = r->dirty[1] = r->bound_dirty = true;  // the wing's circulation changed
+  r->dirty[0] = r->dirty[1] = r->bound_dirty = r->chord_dirty = true;  // the wing's circulation changed
   if (gamVec_out) {
     CUDA_OK(c, cudaMemcpyAsync(gamVec_out, r->gamvec.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
