@@ -58,6 +58,11 @@ typedef struct resident_ops {
   int (*rollup)(gpu_user_t *u, int ir);
   int (*wake_sweep)(gpu_user_t *u, int predicted, int addInitWakeVel);
   int (*wakevel_op)(gpu_user_t *u, int ir, int op);
+  /* the wake sweep in three parts for one process per GPU (vlc_wake_sweep_count / _slice / _scatter) + stream sync */
+  int (*sweep_count)(gpu_user_t *u, int64_t *M);
+  int (*sweep_slice)(gpu_user_t *u, int predicted, int64_t first, int64_t count, double *xbuf);
+  int (*sweep_scatter)(gpu_user_t *u, int predicted, int addInitWakeVel, const double *xbuf);
+  int (*stream_sync)(gpu_user_t *u);
 } resident_ops_t;
 
 #define CK(expr)                        \
@@ -182,25 +187,17 @@ static int g_strain(gpu_user_t *u, int ir) { return vlc_rotor_strain_wake(u->ctx
 static int g_to_pred(gpu_user_t *u, int ir) { return vlc_rotor_wake_to_predicted(u->ctx, ir); }
 static int g_convect(gpu_user_t *u, int ir, int iter, double dt, int p) { (void)iter; return vlc_rotor_convectwake(u->ctx, ir, dt, p); }
 static int g_rollup(gpu_user_t *u, int ir) { return vlc_rotor_rollup(u->ctx, ir); }
-static int g_sweep(gpu_user_t *u, int p, int addInit) {
-  if (u->world <= 1) return vlc_wake_sweep(u->ctx, p, addInit);
-  /* sharded: every rank holds the whole wake; it sweeps its slice of the targets, the slices are all-gathered (the one
-   * exchange of this stage), every rank scatters the complete list */
-  int64_t M = 0;
-  int rc = vlc_wake_sweep_count(u->ctx, &M);
-  if (rc || M <= 0) return rc;
-  const long per = (long)((M + u->world - 1) / u->world);
-  if (per * u->world > u->xbuf_targets) return VLC_ERR_ARG;
-  const int64_t first = (int64_t)u->rank * per, count = first >= M ? 0 : (first + per > M ? M - first : per);
-  if ((rc = vlc_wake_sweep_slice(u->ctx, p, first < M ? first : 0, count, u->xbuf))) return rc;
-  if ((rc = vlc_sync(u->ctx))) return rc;
-  if ((rc = u->exchange(u->exchange_arg, per))) return rc;
-  u->exchanges++;
-  return vlc_wake_sweep_scatter(u->ctx, p, addInit, u->xbuf);
+static int g_sweep(gpu_user_t *u, int p, int addInit) { return vlc_wake_sweep(u->ctx, p, addInit); }
+static int g_sweep_count(gpu_user_t *u, int64_t *M) { return vlc_wake_sweep_count(u->ctx, M); }
+static int g_sweep_slice(gpu_user_t *u, int p, int64_t first, int64_t count, double *x) {
+  return vlc_wake_sweep_slice(u->ctx, p, first, count, x);
 }
+static int g_sweep_scatter(gpu_user_t *u, int p, int addInit, const double *x) { return vlc_wake_sweep_scatter(u->ctx, p, addInit, x); }
+static int g_stream_sync(gpu_user_t *u) { return vlc_sync(u->ctx); }
 static int g_velop(gpu_user_t *u, int ir, int op) { return vlc_rotor_wakevel_op(u->ctx, ir, op); }
 static const resident_ops_t gpu_ops = {resident_begin, sync_wing, g_assignshed, g_age, g_dissipate, g_strain,
-                                       g_to_pred, g_convect, g_rollup, g_sweep, g_velop};
+                                       g_to_pred, g_convect, g_rollup, g_sweep, g_velop,
+                                       g_sweep_count, g_sweep_slice, g_sweep_scatter, g_stream_sync};
 
 #define ROT(u, ir) orc_case_rotor((u)->cas, (ir))
 static int c_begin(gpu_user_t *u) { u->resident_started = 1; return 0; }
@@ -233,8 +230,72 @@ static int c_convect(gpu_user_t *u, int ir, int iter, double dt, int p) {
 static int c_rollup(gpu_user_t *u, int ir) { orc_rotor_rollup(ROT(u, ir)); return 0; }
 static int c_sweep(gpu_user_t *u, int p, int addInit) { (void)addInit; return orc_case_wake_sweep(u->cas, p); }
 static int c_velop(gpu_user_t *u, int ir, int op) { return ROT(u, ir)->nNwake > 0 ? orc_rotor_wakevel_op(ROT(u, ir), op) : 0; }
+/* CPU emulation of vlc_wake_sweep_count / _slice / _scatter: the target list in the library's order (per rotor, per
+ * convected blade: wake nodes of columns 1..ns+1 with the rows rowNear..nNwake fastest, then the far rows rowFar..nFwake).
+ * `visit` walks it and hands out the address of each target's velocity in velNwake / velFwake [Predicted]. */
+static int64_t c_walk(gpu_user_t *u, int p, void (*visit)(double *vel, int64_t q, void *arg), void *arg) {
+  int64_t q = 0;
+  for (int ir = 0; ir < u->nr; ++ir) {
+    orc_rotor_t *r = ROT(u, ir);
+    if (r->nNwake <= 0) continue;
+    const int nact = r->nNwake - r->rowNear + 1 > 0 ? r->nNwake - r->rowNear + 1 : 0;
+    const int nfar = r->nFwake - r->rowFar + 1 > 0 ? r->nFwake - r->rowFar + 1 : 0;
+    for (int ib = 0; ib < r->nbConvect; ++ib) {
+      orc_blade_t *b = &r->blade[ib];
+      double *vn = p ? b->velNwakePredicted : b->velNwake, *vf = p ? b->velFwakePredicted : b->velFwake;
+      for (int j = 1; j <= r->ns + 1; ++j)
+        for (int i = r->rowNear; i < r->rowNear + nact; ++i, ++q)
+          if (visit) visit(vn + 3 * ((size_t)(i - 1) + (size_t)r->nNwake * (j - 1)), q, arg);
+      for (int i = r->rowFar; i < r->rowFar + nfar; ++i, ++q)
+        if (visit) visit(vf + 3 * (size_t)(i - 1), q, arg);
+    }
+  }
+  return q;
+}
+typedef struct { double *x; int64_t first, count; } c_slice_t;
+static void c_take(double *vel, int64_t q, void *arg) { /* own slice into the exchange buffer, then poison the array entry */
+  c_slice_t *s = (c_slice_t *)arg;
+  if (q >= s->first && q < s->first + s->count) memcpy(s->x + 3 * q, vel, 3 * sizeof(double));
+  vel[0] = vel[1] = vel[2] = 0.0 / 0.0 * (double)(q + 1); /* NaN: only the scatter below may make it a number again */
+}
+static void c_put(double *vel, int64_t q, void *arg) { memcpy(vel, ((c_slice_t *)arg)->x + 3 * q, 3 * sizeof(double)); }
+static int c_sweep_count(gpu_user_t *u, int64_t *M) { *M = c_walk(u, 0, NULL, NULL); return 0; }
+static int c_sweep_slice(gpu_user_t *u, int p, int64_t first, int64_t count, double *x) {
+  int rc = orc_case_wake_sweep(u->cas, p); /* the whole sweep by the oracle (incl. the initWakeVel terms) ... */
+  if (rc) return rc;
+  c_slice_t s = {x, first, count};
+  c_walk(u, p, c_take, &s); /* ... of which this rank keeps only its slice */
+  return 0;
+}
+static int c_sweep_scatter(gpu_user_t *u, int p, int addInit, const double *x) {
+  (void)addInit; /* already inside the oracle's sweep */
+  c_slice_t s = {(double *)x, 0, 0};
+  c_walk(u, p, c_put, &s);
+  return 0;
+}
+static int c_stream_sync(gpu_user_t *u) { (void)u; return 0; }
 static const resident_ops_t cpu_ops = {c_begin, c_sync, c_assignshed, c_age, c_dissipate, c_strain,
-                                       c_to_pred, c_convect, c_rollup, c_sweep, c_velop};
+                                       c_to_pred, c_convect, c_rollup, c_sweep, c_velop,
+                                       c_sweep_count, c_sweep_slice, c_sweep_scatter, c_stream_sync};
+
+/* One wake sweep of the staged orchestration.  One process: the backend's whole sweep.  One process per GPU (world > 1):
+ * every rank holds the whole wake; it sweeps its slice of the targets, the slices are all-gathered (the one exchange of
+ * this stage), every rank scatters the complete list. */
+static int staged_sweep(gpu_user_t *u, int p, int addInit) {
+  const resident_ops_t *o = u->ops;
+  if (u->world <= 1) return o->wake_sweep(u, p, addInit);
+  int64_t M = 0;
+  int rc = o->sweep_count(u, &M);
+  if (rc || M <= 0) return rc;
+  const long per = (long)((M + u->world - 1) / u->world);
+  if (per * u->world > u->xbuf_targets) return VLC_ERR_ARG;
+  const int64_t first = (int64_t)u->rank * per, count = first >= M ? 0 : (first + per > M ? M - first : per);
+  if ((rc = o->sweep_slice(u, p, first < M ? first : 0, count, u->xbuf))) return rc;
+  if ((rc = o->stream_sync(u))) return rc;
+  if ((rc = u->exchange(u->exchange_arg, per))) return rc;
+  u->exchanges++;
+  return o->sweep_scatter(u, p, addInit, u->xbuf);
+}
 
 /* main.f90:466-506 as separate stages: assignshed('LE'), age_wake, dissipate_wake of every rotor, in the driver's order */
 static int h_wake_prestep(void *user, int iter) {
@@ -261,7 +322,7 @@ static int h_wake_convect(void *user, int iter) {
   const int addInit = iter < cfg->initWakeVelNt;
   const int nr = u->nr;
   for (int ir = 0; ir < nr; ++ir) CK(o->sync(u, ir)); /* the solve changed the wing's circulation */
-  CK(o->wake_sweep(u, 0, addInit));
+  CK(staged_sweep(u, 0, addInit));
   switch (cfg->fdScheme) {
     case 0: /* :846-859 */
       for (int ir = 0; ir < nr; ++ir) CK(o->convectwake(u, ir, iter, dt, 0));
@@ -271,7 +332,7 @@ static int h_wake_convect(void *user, int iter) {
         CK(o->wake_to_predicted(u, ir));
         CK(o->convectwake(u, ir, iter, dt, 1));
       }
-      CK(o->wake_sweep(u, 1, addInit));
+      CK(staged_sweep(u, 1, addInit));
       for (int ir = 0; ir < nr; ++ir) {
         CK(o->wakevel_op(u, ir, VLC_VEL_ORDER2));
         CK(o->convectwake(u, ir, iter, dt, 0));
@@ -302,7 +363,7 @@ static int h_wake_convect(void *user, int iter) {
           CK(o->wakevel_op(u, ir, VLC_VEL_AB2));
           CK(o->convectwake(u, ir, iter, dt, 1));
         }
-        CK(o->wake_sweep(u, 1, addInit));
+        CK(staged_sweep(u, 1, addInit));
         for (int ir = 0; ir < nr; ++ir) {
           CK(o->wakevel_op(u, ir, VLC_VEL_AM2));
           CK(o->convectwake(u, ir, iter, dt, 0));

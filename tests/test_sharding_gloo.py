@@ -132,3 +132,83 @@ def test_gridgen_cells_sharded_across_ranks(tmp_path, oracle, world):
     assert ref.shape == (3, 4, 5, 3) and np.any(ref != np.array(cfg["vel"]))
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"vc_rank{r}.npy"), ref), r
+
+
+# ---- the reference cases with one process per GPU: the staged orchestration's sharded wake sweep on the CPU backend ----
+
+def _case_worker(rank, world, port, out_dir, name, nsteps):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      OMP_NUM_THREADS="2")
+    import ctypes as C
+    import json
+    import torch
+    import torch.distributed as dist
+    from oracle import pyoracle
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = json.loads((ROOT / "tests" / "golden" / f"{name}.json").read_text())
+    if name == "caradonna":
+        fx["config"]["nt"] = 40
+        fx["geom"][0].update(nNwake=12, wakeTruncateNt=18)
+    lib = C.CDLL(str(ROOT / "tests" / "native" / "libcase_gpu_hooks.so"))
+    lib.case_cpu_staged_hooks_install.restype = C.c_void_p
+    lib.case_cpu_staged_hooks_install.argtypes = [C.c_void_p, C.c_int]
+    lib.case_gpu_hooks_set_sharding.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+    lib.case_gpu_hooks_exchanges.restype = C.c_long
+    lib.case_gpu_hooks_exchanges.argtypes = [C.c_void_p]
+    c = pyoracle.Case(fx)
+    c.init_rotors()
+    h = lib.case_cpu_staged_hooks_install(c.h, c.nr)
+    m_max = sum((c.rotor(ir).dims()["nNwake"] * (c.rotor(ir).ns + 1) + c.rotor(ir).nFwake) * c.rotor(ir).dims()["nbConvect"]
+                for ir in range(c.nr))
+    per_max = (m_max + world - 1) // world
+    xbuf = np.full(3 * world * per_max, np.nan)          # host exchange buffer (the CPU backend's "device" memory)
+
+    def exchange(_arg, per):
+        n = 3 * per
+        mine = torch.from_numpy(xbuf[rank * n:(rank + 1) * n].copy())
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        xbuf[:world * n] = torch.cat(parts).numpy()
+        return 0
+
+    cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_long)(exchange)
+    lib.case_gpu_hooks_set_sharding(h, world, rank, xbuf.ctypes.data, world * per_max, C.cast(cb, C.c_void_p), None)
+    c.init()
+    hist = [c.force_nondim(0).copy()]
+    for _ in range(nsteps):
+        c.step()
+        hist.append(c.force_nondim(0).copy())
+    r = c.rotor(0)
+    np.savez(Path(out_dir) / f"case_rank{rank}.npz", hist=np.array(hist), waN=r.waN(0), gam=r.vec(0),
+             vel=r.vel(0, 0), exchanges=lib.case_gpu_hooks_exchanges(h))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,nsteps", [("katzNplotkin_AR04", 10), ("caradonna", 22)])
+def test_case_path_sharded_wake_sweep_two_ranks(tmp_path, oracle, name, nsteps):
+    """tests/native/case_gpu_hooks.c:staged_sweep with world = 2 on its CPU backend: each rank keeps only its slice of
+    the swept velocities (the rest of its arrays is poisoned with NaN), the slices are all-gathered over gloo, every rank
+    scatters the whole list.  Both ranks must end bit-identical to the single-process driver: forces, circulations, wake,
+    velocity arrays; one exchange per wake sweep (fdScheme 3: 1 in the first step, 2 afterwards)."""
+    import json
+    import torch.multiprocessing as mp
+    mp.start_processes(_case_worker, args=(2, _free_port(), str(tmp_path), name, nsteps), nprocs=2, join=True, start_method="spawn")
+    fx = json.loads((ROOT / "tests" / "golden" / f"{name}.json").read_text())
+    if name == "caradonna":
+        fx["config"]["nt"] = 40
+        fx["geom"][0].update(nNwake=12, wakeTruncateNt=18)
+    a = oracle.Case(fx)
+    a.init()
+    hist = [a.force_nondim(0).copy()]
+    for _ in range(nsteps):
+        a.step()
+        hist.append(a.force_nondim(0).copy())
+    ra = a.rotor(0)
+    for rank in range(2):
+        z = np.load(tmp_path / f"case_rank{rank}.npz")
+        assert np.array_equal(z["hist"], np.array(hist)), rank
+        assert np.array_equal(z["gam"], ra.vec(0)) and np.array_equal(z["waN"], ra.waN(0)), rank
+        assert np.array_equal(z["vel"], ra.vel(0, 0), equal_nan=False), rank
+        assert int(z["exchanges"]) == 2 * nsteps - 1, (rank, int(z["exchanges"]))
