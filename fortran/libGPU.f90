@@ -30,6 +30,8 @@ module libGPU
   logical, save :: resident = .false.
   integer(c_int), parameter :: VEL_FIRST_STEP = 0, VEL_AB2 = 1, VEL_AM2 = 2, VEL_SHIFT_HISTORY = 3, VEL_ORDER2 = 4, &
     & VEL_COPY_TO_STEP = 5
+  ! velocity arrays by id (vlc_rotor_wakevel_copy / _lincomb)
+  integer(c_int), parameter :: ARR_VEL = 0, ARR_VEL1 = 1, ARR_PREDICTED = 2, ARR_STEP = 3, ARR_VEL2 = 4, ARR_VEL3 = 5
 
   type(c_ptr), save :: ctx = c_null_ptr
 
@@ -231,6 +233,20 @@ module libGPU
       type(c_ptr), value :: c
       integer(c_int), value :: ir, ib, predicted
       real(c_double), intent(out) :: waF(*)
+    end function
+    integer(c_int) function vlc_rotor_wakevel_copy(c, ir, dst, src) bind(C, name='vlc_rotor_wakevel_copy')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, dst, src
+    end function
+    integer(c_int) function vlc_rotor_wakevel_lincomb(c, ir, dst, nterms, src, coef, divisor) &
+        & bind(C, name='vlc_rotor_wakevel_lincomb')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, dst, nterms
+      integer(c_int), intent(in) :: src(*)
+      real(c_double), intent(in) :: coef(*)
+      real(c_double), value :: divisor
     end function
     ! tier 2c
     integer(c_int) function vlc_rotor_calc_RHS(c, ir, velCP_out, RHS_out) bind(C, name='vlc_rotor_calc_RHS')
@@ -522,13 +538,14 @@ contains
   ! -- every rank keeps the whole wake and runs the other stages redundantly (tests/multi_gpu_case.py is the tested twin).
   subroutine gpu_wake_convect(rotor, iter, dt, fdScheme, wakeStrain, initWakeVelNt)
     !! Replaces main.f90:800-1440: the wake sweeps, the fdScheme switch (0 explicit Euler :846-859, 1 predictor-
-    !! corrector :861-949, 3 Adams-Bashforth / Adams-Moulton :1002-1115) with its velocity bookkeeping, strain_wake,
-    !! rollup, assignshed('TE').
+    !! corrector :861-949, 2 explicit Adams-Bashforth :951-1000, 3 Adams-Bashforth / Adams-Moulton :1002-1115, 4 and 5 the
+    !! same of third and fourth order :1117-1404) with its velocity bookkeeping, strain_wake, rollup, assignshed('TE').
     type(rotor_class), intent(in) :: rotor(:)
     integer, intent(in) :: iter, fdScheme, wakeStrain, initWakeVelNt
     real(dp), intent(in) :: dt
-    integer :: ir
+    integer :: ir, start
     integer(c_int) :: addInit
+    integer(c_int), parameter :: hist(3) = [ARR_VEL1, ARR_VEL2, ARR_VEL3]
     addInit = merge(1_c_int, 0_c_int, iter < initWakeVelNt)
     do ir = 1, size(rotor)
       call gpu_sync_rotor(rotor(ir), ir, .false.)   ! the solve changed the wing's circulation
@@ -580,8 +597,51 @@ contains
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_SHIFT_HISTORY))
         enddo
       endif
+    case (4, 5)   ! Adams-Bashforth / Adams-Moulton of third (:1117-1248) and fourth order (:1250-1404)
+      if (fdScheme == 4) then        ! its `iter == 0` start branch never runs inside the time loop
+        start = merge(2, 0, iter == 2)
+      else
+        start = merge(iter, 0, iter <= 3)
+      endif
+      if (start > 0) then            ! this step only fills the history vel1 / vel2 / vel3
+        do ir = 1, size(rotor)
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call check(vlc_rotor_wakevel_copy(ctx, ir - 1, hist(start), ARR_VEL))
+        enddo
+      else
+        do ir = 1, size(rotor)
+          call check(vlc_rotor_wake_to_predicted(ctx, ir - 1))
+          call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_STEP, ARR_VEL))
+          if (fdScheme == 4) then
+            call check(vlc_rotor_wakevel_lincomb(ctx, ir - 1, ARR_VEL, 3_c_int, [ARR_VEL, ARR_VEL2, ARR_VEL1], &
+              & [23._c_double, -16._c_double, 5._c_double], 12._c_double))
+          else
+            call check(vlc_rotor_wakevel_lincomb(ctx, ir - 1, ARR_VEL, 4_c_int, [ARR_VEL, ARR_VEL3, ARR_VEL2, ARR_VEL1], &
+              & [55._c_double, -59._c_double, 37._c_double, -9._c_double], 24._c_double))
+          endif
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 1_c_int))
+        enddo
+        call check(vlc_wake_sweep(ctx, 1_c_int, addInit))
+        do ir = 1, size(rotor)
+          if (fdScheme == 4) then
+            call check(vlc_rotor_wakevel_lincomb(ctx, ir - 1, ARR_VEL, 3_c_int, [ARR_PREDICTED, ARR_STEP, ARR_VEL2], &
+              & [5._c_double, 8._c_double, -1._c_double], 12._c_double))
+          else
+            call check(vlc_rotor_wakevel_lincomb(ctx, ir - 1, ARR_VEL, 4_c_int, [ARR_PREDICTED, ARR_STEP, ARR_VEL3, ARR_VEL2], &
+              & [9._c_double, 19._c_double, -5._c_double, 1._c_double], 24._c_double))
+          endif
+          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_VEL1, ARR_VEL2))
+          if (fdScheme == 4) then
+            call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_VEL2, ARR_STEP))
+          else
+            call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_VEL2, ARR_VEL3))
+            call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_VEL3, ARR_STEP))
+          endif
+        enddo
+      endif
     case default
-      error stop 'ERROR: gpu_wake_convect: fdScheme 4, 5 are not on the device path'
+      error stop 'ERROR: gpu_wake_convect: unknown fdScheme'
     end select
     if (wakeStrain == 1) then
       do ir = 1, size(rotor)

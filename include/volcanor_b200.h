@@ -212,8 +212,21 @@ enum {
                                 AB2, FIRST_STEP, COPY_TO_STEP: velStep = vel1 = vel = 0.5*(3*vel - vel1)   */
 };
 int vlc_rotor_wakevel_op(vlc_ctx* ctx, int ir, int op);
+/* The same bookkeeping in general form, for the multistep schemes fdScheme 4 / 5 (main.f90:1117-1404), which keep two
+ * more histories per blade (velNwake2 / 3, velFwake2 / 3, classdef.f90:3733-3824; here allocated on first use).
+ * Arrays by id, near and far wake together, whole arrays of the convected blades: */
+enum {
+  VLC_VEL_ARRAY = 0, VLC_VEL_ARRAY_1 = 1, VLC_VEL_ARRAY_PREDICTED = 2, VLC_VEL_ARRAY_STEP = 3, VLC_VEL_ARRAY_2 = 4,
+  VLC_VEL_ARRAY_3 = 5
+};
+/* dst = src */
+int vlc_rotor_wakevel_copy(vlc_ctx* ctx, int ir, int dst, int src);
+/* dst = (coef[0]*src[0] + ... + coef[nterms-1]*src[nterms-1]) / divisor, 1 <= nterms <= 4, terms added left to right, e.g.
+ * the third-order predictor vel = (23*vel - 16*vel2 + 5*vel1)/12 (main.f90:1160-1163) is dst = VLC_VEL_ARRAY,
+ * src = {ARRAY, ARRAY_2, ARRAY_1}, coef = {23, -16, 5}, divisor = 12.  dst may be one of the sources. */
+int vlc_rotor_wakevel_lincomb(vlc_ctx* ctx, int ir, int dst, int nterms, const int* src, const double* coef, double divisor);
 /* Read the device copies back (plots, restart files, tests): whole arrays of blade ib in the reference layout.
- * which: 0 = velNwake/velFwake, 1 = ...1, 2 = ...Predicted, 3 = ...Step; either pointer may be NULL. */
+ * which: 0 = velNwake/velFwake, 1 = ...1, 2 = ...Predicted, 3 = ...Step, 4 = ...2, 5 = ...3; either pointer may be NULL. */
 int vlc_rotor_get_nwake(vlc_ctx* ctx, int ir, int ib, int predicted, double* waN /* nNwake*ns x 50 */);
 int vlc_rotor_get_fwake(vlc_ctx* ctx, int ir, int ib, int predicted, double* waF /* nFwake x 13 */);
 int vlc_rotor_put_wakevel(vlc_ctx* ctx, int ir, int ib, int which, const double* velN, const double* velF);

@@ -132,6 +132,10 @@ class Rotor {
   }
   void rollup() { c_.check(vlc_rotor_rollup(c_.handle(), ir_)); }
   void wakevel_op(int op) { c_.check(vlc_rotor_wakevel_op(c_.handle(), ir_, op)); }
+  void wakevel_copy(int dst, int src) { c_.check(vlc_rotor_wakevel_copy(c_.handle(), ir_, dst, src)); }
+  void wakevel_lincomb(int dst, int nterms, const int* src, const double* coef, double divisor) {
+    c_.check(vlc_rotor_wakevel_lincomb(c_.handle(), ir_, dst, nterms, src, coef, divisor));
+  }
   void get_nwake(int ib, double* waN, bool predicted = false) { c_.check(vlc_rotor_get_nwake(c_.handle(), ir_, ib, predicted, waN)); }
   void get_fwake(int ib, double* waF, bool predicted = false) { c_.check(vlc_rotor_get_fwake(c_.handle(), ir_, ib, predicted, waF)); }
   // tier 2c: the collocation-point stage on the device copies of the wing records (main.f90:548-670)

@@ -256,7 +256,8 @@ class Rotor:
         return self._view(self.lib.orc_rotor_wapF(self.h, ib, int(predicted)), (NPF, FW))
 
     def vel(self, ib, which):
-        if which < 4:
+        """0-3 velNwake, 1, Predicted, Step; 4-7 the same for velFwake; 8, 9 velNwake2 / 3; 10, 11 velFwake2 / 3."""
+        if which < 4 or which in (8, 9):
             return self._view(self.lib.orc_rotor_vel(self.h, ib, which), (self.ns + 1, self.nNwake, 3))
         return self._view(self.lib.orc_rotor_vel(self.h, ib, which), (self.nFwake, 3))
 

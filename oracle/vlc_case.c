@@ -1550,13 +1550,14 @@ int orc_case_step(orc_case_t *c) {
   }
   /* wake convection, :800-1440 */
   if (cfg->wakeSuppress == 0 && c->hooks.wake_convect) { /* device-resident wake: the hook owner does :800-1440 */
-    if (cfg->fdScheme < 0 || cfg->fdScheme > 3) {
-      snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 2, 3)", cfg->fdScheme);
+    if (cfg->fdScheme < 0 || cfg->fdScheme > 5) {
+      snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0 ... 5)", cfg->fdScheme);
       return 3;
     }
     int rc = c->hooks.wake_convect(c->stage_user ? c->stage_user : c->hooks.user, iter);
     if (rc) return rc;
-    const int nsweeps = (cfg->fdScheme == 0 || cfg->fdScheme == 2 || (cfg->fdScheme == 3 && iter == 1)) ? 1 : 2;
+    const int nsweeps = (cfg->fdScheme == 0 || cfg->fdScheme == 2 || (cfg->fdScheme == 3 && iter == 1) ||
+                         (cfg->fdScheme == 4 && iter == 2) || (cfg->fdScheme == 5 && iter <= 3)) ? 1 : 2;
     for (int ir = 0; ir < c->nr; ++ir) { /* the same count wake_sweep() keeps */
       const orc_rotor_t *r = c->rotor[ir];
       if (r->nNwake <= 0) continue;
@@ -1690,8 +1691,77 @@ int orc_case_step(orc_case_t *c) {
           }
         }
         break;
+      case 4: /* :1117-1248 predictor-corrector Adams-Moulton, third order.  The first branch tests `iter == 0`, which
+               * never holds inside the time loop (iter = 1..nt): step 1 already takes the multistep branch with zero
+               * histories, step 2 only stores velNwake2 -- restated as written */
+      case 5: /* :1250-1404 fourth order: steps 1, 2, 3 fill velNwake1, 2, 3 */
+      {
+        const int order = cfg->fdScheme == 4 ? 3 : 4;
+        const int start = (order == 3) ? (iter == 2 ? 2 : 0) : (iter <= 3 ? iter : 0); /* which history this step fills */
+        if (start) {
+          for (int ir = 0; ir < c->nr; ++ir) {
+            orc_rotor_t *r = c->rotor[ir];
+            if (r->nNwake <= 0) continue;
+            orc_rotor_convectwake(r, iter, dt, 'C');
+            orc_rotor_wakevel_copy(r, start == 1 ? ORC_VEL_1 : (start == 2 ? ORC_VEL_2 : ORC_VEL_3), ORC_VEL);
+          }
+        } else {
+          for (int ir = 0; ir < c->nr; ++ir) {
+            orc_rotor_t *r = c->rotor[ir];
+            if (r->nNwake <= 0) continue;
+            copy_wake_to_predicted(r);
+            for (int ib = 0; ib < r->nbConvect; ++ib) { /* :1158-1172 / :1307-1325 */
+              orc_blade_t *b = &r->blade[ib];
+              const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
+              memcpy(b->velNwakeStep, b->velNwake, sizeof(double) * nn);
+              memcpy(b->velFwakeStep, b->velFwake, sizeof(double) * nf);
+              if (order == 3) {
+                for (size_t q = 0; q < nn; ++q)
+                  b->velNwake[q] = (23.0 * b->velNwake[q] - 16.0 * b->velNwake2[q] + 5.0 * b->velNwake1[q]) / 12.0;
+                for (size_t q = 0; q < nf; ++q)
+                  b->velFwake[q] = (23.0 * b->velFwake[q] - 16.0 * b->velFwake2[q] + 5.0 * b->velFwake1[q]) / 12.0;
+              } else {
+                for (size_t q = 0; q < nn; ++q)
+                  b->velNwake[q] = (55.0 * b->velNwake[q] - 59.0 * b->velNwake3[q] + 37.0 * b->velNwake2[q] - 9.0 * b->velNwake1[q]) / 24.0;
+                for (size_t q = 0; q < nf; ++q)
+                  b->velFwake[q] = (55.0 * b->velFwake[q] - 59.0 * b->velFwake3[q] + 37.0 * b->velFwake2[q] - 9.0 * b->velFwake1[q]) / 24.0;
+              }
+            }
+            orc_rotor_convectwake(r, iter, dt, 'P');
+          }
+          rc = wake_sweep(c, 1);
+          if (rc) return rc;
+          for (int ir = 0; ir < c->nr; ++ir) {
+            orc_rotor_t *r = c->rotor[ir];
+            if (r->nNwake <= 0) continue;
+            for (int ib = 0; ib < r->nbConvect; ++ib) { /* :1222-1231 / :1370-1381 */
+              orc_blade_t *b = &r->blade[ib];
+              const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
+              if (order == 3) {
+                for (size_t q = 0; q < nn; ++q)
+                  b->velNwake[q] = (5.0 * b->velNwakePredicted[q] + 8.0 * b->velNwakeStep[q] - 1.0 * b->velNwake2[q]) / 12.0;
+                for (size_t q = 0; q < nf; ++q)
+                  b->velFwake[q] = (5.0 * b->velFwakePredicted[q] + 8.0 * b->velFwakeStep[q] - 1.0 * b->velFwake2[q]) / 12.0;
+              } else {
+                for (size_t q = 0; q < nn; ++q)
+                  b->velNwake[q] = (9.0 * b->velNwakePredicted[q] + 19.0 * b->velNwakeStep[q] - 5.0 * b->velNwake3[q] + 1.0 * b->velNwake2[q]) / 24.0;
+                for (size_t q = 0; q < nf; ++q)
+                  b->velFwake[q] = (9.0 * b->velFwakePredicted[q] + 19.0 * b->velFwakeStep[q] - 5.0 * b->velFwake3[q] + 1.0 * b->velFwake2[q]) / 24.0;
+              }
+            }
+            orc_rotor_convectwake(r, iter, dt, 'C');
+            orc_rotor_wakevel_copy(r, ORC_VEL_1, ORC_VEL_2); /* :1234-1239 / :1384-1391: shift the histories */
+            if (order == 3) {
+              orc_rotor_wakevel_copy(r, ORC_VEL_2, ORC_VEL_STEP);
+            } else {
+              orc_rotor_wakevel_copy(r, ORC_VEL_2, ORC_VEL_3);
+              orc_rotor_wakevel_copy(r, ORC_VEL_3, ORC_VEL_STEP);
+            }
+          }
+        }
+      } break;
       default:
-        snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0, 1, 2, 3)", cfg->fdScheme);
+        snprintf(c->err, sizeof c->err, "fdScheme %d is outside the oracle's scope (0 ... 5)", cfg->fdScheme);
         return 3;
     }
     for (int ir = 0; ir < c->nr; ++ir) c->rotor[ir]->gen_wake[0]++; /* convectwake('C'), strain, roll-up, shed below */
@@ -1719,6 +1789,50 @@ int orc_case_wake_sweep(orc_case_t *c, int predicted) { /* main.f90:800-838 / :8
 void orc_rotor_wake_to_predicted(orc_rotor_t *r) { copy_wake_to_predicted(r); }
 /* op: 0 first-step copy (main.f90:1013-1020), 1 AB2 (:1031-1041), 2 AM2 (:1094-1099), 3 history (:1103-1107),
  * 4 vel_order2 on the active slices (:927-940) -- convected blades */
+/* the six velocity arrays of a blade by id (near / far): 0 vel, 1 vel1, 2 velPredicted, 3 velStep, 4 vel2, 5 vel3 */
+static void vel_arrays(orc_blade_t *b, double *n[6], double *f[6]) {
+  double *nn[6] = {b->velNwake, b->velNwake1, b->velNwakePredicted, b->velNwakeStep, b->velNwake2, b->velNwake3};
+  double *ff[6] = {b->velFwake, b->velFwake1, b->velFwakePredicted, b->velFwakeStep, b->velFwake2, b->velFwake3};
+  memcpy(n, nn, sizeof nn);
+  memcpy(f, ff, sizeof ff);
+}
+/* dst = src, whole arrays of the convected blades */
+int orc_rotor_wakevel_copy(orc_rotor_t *r, int dst, int src) {
+  if (dst < 0 || dst > 5 || src < 0 || src > 5) return 2;
+  const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
+  for (int ib = 0; ib < r->nbConvect; ++ib) {
+    double *n[6], *f[6];
+    vel_arrays(&r->blade[ib], n, f);
+    if (dst != src) {
+      memcpy(n[dst], n[src], sizeof(double) * nn);
+      memcpy(f[dst], f[src], sizeof(double) * nf);
+    }
+  }
+  return 0;
+}
+/* dst = (coef[0]*src[0] + coef[1]*src[1] + ...)/divisor, terms added left to right (the multistep formulas of
+ * main.f90:1160-1172, :1222-1231, :1309-1325, :1370-1381 with the signs in the coefficients); dst may be one of src */
+int orc_rotor_wakevel_lincomb(orc_rotor_t *r, int dst, int nterms, const int *src, const double *coef, double divisor) {
+  if (dst < 0 || dst > 5 || nterms < 1 || nterms > 4) return 2;
+  for (int k = 0; k < nterms; ++k)
+    if (src[k] < 0 || src[k] > 5) return 2;
+  const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
+  for (int ib = 0; ib < r->nbConvect; ++ib) {
+    double *n[6], *f[6];
+    vel_arrays(&r->blade[ib], n, f);
+    for (int far = 0; far < 2; ++far) {
+      double **a = far ? f : n;
+      const size_t cnt = far ? nf : nn;
+      for (size_t q = 0; q < cnt; ++q) {
+        double acc = coef[0] * a[src[0]][q];
+        for (int k = 1; k < nterms; ++k) acc = acc + coef[k] * a[src[k]][q];
+        a[dst][q] = acc / divisor;
+      }
+    }
+  }
+  return 0;
+}
+
 int orc_rotor_wakevel_op(orc_rotor_t *r, int op) {
   const size_t nn = 3 * (size_t)r->nNwake * (r->ns + 1), nf = 3 * (size_t)r->nFwake;
   for (int ib = 0; ib < r->nbConvect; ++ib) {

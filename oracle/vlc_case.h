@@ -15,10 +15,10 @@
  * performs.
  *
  * Scope: surfaceType 1 (lifting) rotors and wings, geometryFile '0' or a PLOT3D grid passed in
- * memory, forceCalcSwitch 0, fdScheme 0/1/2/3, slowStart 0-3, wake dissipation / strain,
+ * memory, forceCalcSwitch 0, fdScheme 0-5, slowStart 0-3, wake dissipation / strain,
  * axisymmetry, far-wake roll-up and truncation.  Not restated (unused by every shipped case):
  * image surfaces, non-lifting STL bodies, camber files, C81 tables, blade/body dynamics, custom
- * trajectories, wake burst, prescribed far wake generation, fdScheme 4/5.
+ * trajectories, wake burst, prescribed far wake generation.
  */
 #ifndef VLC_CASE_H
 #define VLC_CASE_H
@@ -104,6 +104,10 @@ double orc_case_pairs_last_step(const orc_case_t *c);
 int orc_case_wake_sweep(orc_case_t *c, int predicted);
 void orc_rotor_wake_to_predicted(orc_rotor_t *r);
 int orc_rotor_wakevel_op(orc_rotor_t *r, int op);
+/* velocity arrays by id, as in the C ABI (vlc_rotor_wakevel_copy / _lincomb) */
+enum { ORC_VEL = 0, ORC_VEL_1 = 1, ORC_VEL_PREDICTED = 2, ORC_VEL_STEP = 3, ORC_VEL_2 = 4, ORC_VEL_3 = 5 };
+int orc_rotor_wakevel_copy(orc_rotor_t *r, int dst, int src);
+int orc_rotor_wakevel_lincomb(orc_rotor_t *r, int dst, int nterms, const int *src, const double *coef, double divisor);
 
 /* pieces exposed for the KAT tests */
 double orc_pwl_interp1d(int n, const double *x, const double *y, double q); /* libMath.f90:476-517 */

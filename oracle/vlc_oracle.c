@@ -936,6 +936,10 @@ orc_rotor_t *orc_rotor_new(int nb, int nc, int ns, int nNwake, int nFwake) {
     b->velFwake1 = (double *)calloc(vf, sizeof(double));
     b->velFwakePredicted = (double *)calloc(vf, sizeof(double));
     b->velFwakeStep = (double *)calloc(vf, sizeof(double));
+    b->velNwake2 = (double *)calloc(vn, sizeof(double));
+    b->velNwake3 = (double *)calloc(vn, sizeof(double));
+    b->velFwake2 = (double *)calloc(vf, sizeof(double));
+    b->velFwake3 = (double *)calloc(vf, sizeof(double));
     /* sectional arrays of the case driver (vlc_case.c; classdef.f90:3091-3122) */
     double **s1[] = {&b->secChord, &b->secArea, &b->secAlpha, &b->secCL, &b->secCLu, &b->secCD, &b->secMflapArm};
     double **s3[] = {&b->secForceInertial, &b->secLift, &b->secDrag, &b->secLiftDir, &b->secDragDir, &b->secLiftUnsteady,
@@ -964,6 +968,10 @@ void orc_rotor_free(orc_rotor_t *r) {
     free(b->velFwake1);
     free(b->velFwakePredicted);
     free(b->velFwakeStep);
+    free(b->velNwake2);
+    free(b->velNwake3);
+    free(b->velFwake2);
+    free(b->velFwake3);
     double *s[] = {b->secChord, b->secArea, b->secAlpha, b->secCL, b->secCLu, b->secCD, b->secMflapArm,
                    b->secForceInertial, b->secLift, b->secDrag, b->secLiftDir, b->secDragDir, b->secLiftUnsteady,
                    b->secTauCapChord, b->secTauCapSpan, b->secNormalVec, b->secCP, b->secChordwiseResVel};
@@ -990,11 +998,13 @@ double *orc_rotor_waF(orc_rotor_t *r, int ib, int predicted) {
 double *orc_rotor_wapF(orc_rotor_t *r, int ib, int predicted) {
   return (double *)(predicted ? r->blade[ib].wapFPredicted : r->blade[ib].wapF);
 }
-/* which: 0 velNwake 1 velNwake1 2 velNwakePredicted 3 velNwakeStep 4 velFwake 5 velFwake1 6 velFwakePredicted 7 velFwakeStep */
+/* which: 0 velNwake 1 velNwake1 2 velNwakePredicted 3 velNwakeStep 4 velFwake 5 velFwake1 6 velFwakePredicted 7 velFwakeStep
+ *        8 velNwake2 9 velNwake3 10 velFwake2 11 velFwake3 */
 double *orc_rotor_vel(orc_rotor_t *r, int ib, int which) {
   orc_blade_t *b = &r->blade[ib];
-  double *t[8] = {b->velNwake, b->velNwake1, b->velNwakePredicted, b->velNwakeStep,
-                  b->velFwake, b->velFwake1, b->velFwakePredicted, b->velFwakeStep};
+  double *t[12] = {b->velNwake, b->velNwake1, b->velNwakePredicted, b->velNwakeStep,
+                   b->velFwake, b->velFwake1, b->velFwakePredicted, b->velFwakeStep,
+                   b->velNwake2, b->velNwake3, b->velFwake2, b->velFwake3};
   return t[which];
 }
 double *orc_rotor_AIC(orc_rotor_t *r, int inverse) { return inverse ? r->AIC_inv : r->AIC; }

@@ -70,6 +70,7 @@ typedef struct {
   orc_fwake_t wapF[ORC_NPFWAKE], wapFPredicted[ORC_NPFWAKE];
   double *velNwake, *velNwake1, *velNwakePredicted, *velNwakeStep; /* (3,nNwake,ns+1) */
   double *velFwake, *velFwake1, *velFwakePredicted, *velFwakeStep; /* (3,nFwake) */
+  double *velNwake2, *velNwake3, *velFwake2, *velFwake3;           /* fdScheme 4 / 5 histories (classdef.f90:3733-3824) */
   /* ---- case-driver state (vlc_case.c; classdef.f90:238-312) ---- */
   double theta, psi, pivotLE, preconeAngle, flap, dflap;
   double flapOrigin[3];

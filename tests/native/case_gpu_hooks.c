@@ -63,6 +63,9 @@ typedef struct resident_ops {
   int (*sweep_slice)(gpu_user_t *u, int predicted, int64_t first, int64_t count, double *xbuf);
   int (*sweep_scatter)(gpu_user_t *u, int predicted, int addInitWakeVel, const double *xbuf);
   int (*stream_sync)(gpu_user_t *u);
+  /* general velocity bookkeeping of the multistep schemes (fdScheme 4 / 5): array ids VLC_VEL_ARRAY_* */
+  int (*wakevel_copy)(gpu_user_t *u, int ir, int dst, int src);
+  int (*wakevel_lincomb)(gpu_user_t *u, int ir, int dst, int nterms, const int *src, const double *coef, double divisor);
 } resident_ops_t;
 
 #define CK(expr)                        \
@@ -195,9 +198,13 @@ static int g_sweep_slice(gpu_user_t *u, int p, int64_t first, int64_t count, dou
 static int g_sweep_scatter(gpu_user_t *u, int p, int addInit, const double *x) { return vlc_wake_sweep_scatter(u->ctx, p, addInit, x); }
 static int g_stream_sync(gpu_user_t *u) { return vlc_sync(u->ctx); }
 static int g_velop(gpu_user_t *u, int ir, int op) { return vlc_rotor_wakevel_op(u->ctx, ir, op); }
+static int g_velcopy(gpu_user_t *u, int ir, int dst, int src) { return vlc_rotor_wakevel_copy(u->ctx, ir, dst, src); }
+static int g_vellin(gpu_user_t *u, int ir, int dst, int n, const int *src, const double *coef, double div) {
+  return vlc_rotor_wakevel_lincomb(u->ctx, ir, dst, n, src, coef, div);
+}
 static const resident_ops_t gpu_ops = {resident_begin, sync_wing, g_assignshed, g_age, g_dissipate, g_strain,
                                        g_to_pred, g_convect, g_rollup, g_sweep, g_velop,
-                                       g_sweep_count, g_sweep_slice, g_sweep_scatter, g_stream_sync};
+                                       g_sweep_count, g_sweep_slice, g_sweep_scatter, g_stream_sync, g_velcopy, g_vellin};
 
 #define ROT(u, ir) orc_case_rotor((u)->cas, (ir))
 static int c_begin(gpu_user_t *u) { u->resident_started = 1; return 0; }
@@ -274,9 +281,15 @@ static int c_sweep_scatter(gpu_user_t *u, int p, int addInit, const double *x) {
   return 0;
 }
 static int c_stream_sync(gpu_user_t *u) { (void)u; return 0; }
+static int c_velcopy(gpu_user_t *u, int ir, int dst, int src) {
+  return ROT(u, ir)->nNwake > 0 ? orc_rotor_wakevel_copy(ROT(u, ir), dst, src) : 0;
+}
+static int c_vellin(gpu_user_t *u, int ir, int dst, int n, const int *src, const double *coef, double div) {
+  return ROT(u, ir)->nNwake > 0 ? orc_rotor_wakevel_lincomb(ROT(u, ir), dst, n, src, coef, div) : 0;
+}
 static const resident_ops_t cpu_ops = {c_begin, c_sync, c_assignshed, c_age, c_dissipate, c_strain,
                                        c_to_pred, c_convect, c_rollup, c_sweep, c_velop,
-                                       c_sweep_count, c_sweep_slice, c_sweep_scatter, c_stream_sync};
+                                       c_sweep_count, c_sweep_slice, c_sweep_scatter, c_stream_sync, c_velcopy, c_vellin};
 
 /* One wake sweep of the staged orchestration.  One process: the backend's whole sweep.  One process per GPU (world > 1):
  * every rank holds the whole wake; it sweeps its slice of the targets, the slices are all-gathered (the one exchange of
@@ -371,6 +384,47 @@ static int h_wake_convect(void *user, int iter) {
         }
       }
       break;
+    case 4:   /* :1117-1248 Adams-Bashforth / Adams-Moulton, third order (its `iter == 0` start branch never runs) */
+    case 5: { /* :1250-1404 fourth order: steps 1, 2, 3 fill vel1, vel2, vel3 */
+      const int order = cfg->fdScheme == 4 ? 3 : 4;
+      const int start = (order == 3) ? (iter == 2 ? 2 : 0) : (iter <= 3 ? iter : 0);
+      static const int hist[4] = {0, VLC_VEL_ARRAY_1, VLC_VEL_ARRAY_2, VLC_VEL_ARRAY_3};
+      static const int p3[3] = {VLC_VEL_ARRAY, VLC_VEL_ARRAY_2, VLC_VEL_ARRAY_1};
+      static const double pc3[3] = {23.0, -16.0, 5.0};
+      static const int c3[3] = {VLC_VEL_ARRAY_PREDICTED, VLC_VEL_ARRAY_STEP, VLC_VEL_ARRAY_2};
+      static const double cc3[3] = {5.0, 8.0, -1.0};
+      static const int p4[4] = {VLC_VEL_ARRAY, VLC_VEL_ARRAY_3, VLC_VEL_ARRAY_2, VLC_VEL_ARRAY_1};
+      static const double pc4[4] = {55.0, -59.0, 37.0, -9.0};
+      static const int c4[4] = {VLC_VEL_ARRAY_PREDICTED, VLC_VEL_ARRAY_STEP, VLC_VEL_ARRAY_3, VLC_VEL_ARRAY_2};
+      static const double cc4[4] = {9.0, 19.0, -5.0, 1.0};
+      if (start) {
+        for (int ir = 0; ir < nr; ++ir) {
+          CK(o->convectwake(u, ir, iter, dt, 0));
+          CK(o->wakevel_copy(u, ir, hist[start], VLC_VEL_ARRAY));
+        }
+      } else {
+        for (int ir = 0; ir < nr; ++ir) {
+          CK(o->wake_to_predicted(u, ir));
+          CK(o->wakevel_copy(u, ir, VLC_VEL_ARRAY_STEP, VLC_VEL_ARRAY));
+          if (order == 3) CK(o->wakevel_lincomb(u, ir, VLC_VEL_ARRAY, 3, p3, pc3, 12.0));
+          else CK(o->wakevel_lincomb(u, ir, VLC_VEL_ARRAY, 4, p4, pc4, 24.0));
+          CK(o->convectwake(u, ir, iter, dt, 1));
+        }
+        CK(staged_sweep(u, 1, addInit));
+        for (int ir = 0; ir < nr; ++ir) {
+          if (order == 3) CK(o->wakevel_lincomb(u, ir, VLC_VEL_ARRAY, 3, c3, cc3, 12.0));
+          else CK(o->wakevel_lincomb(u, ir, VLC_VEL_ARRAY, 4, c4, cc4, 24.0));
+          CK(o->convectwake(u, ir, iter, dt, 0));
+          CK(o->wakevel_copy(u, ir, VLC_VEL_ARRAY_1, VLC_VEL_ARRAY_2));
+          if (order == 3) {
+            CK(o->wakevel_copy(u, ir, VLC_VEL_ARRAY_2, VLC_VEL_ARRAY_STEP));
+          } else {
+            CK(o->wakevel_copy(u, ir, VLC_VEL_ARRAY_2, VLC_VEL_ARRAY_3));
+            CK(o->wakevel_copy(u, ir, VLC_VEL_ARRAY_3, VLC_VEL_ARRAY_STEP));
+          }
+        }
+      }
+    } break;
     default: return u->last_rc = VLC_ERR_ARG;
   }
   if (cfg->wakeStrain == 1) /* :1409-1416 */
@@ -693,6 +747,10 @@ int case_gpu_hooks_download_wake(void *handle) {
       for (int w = 0; w < 4; ++w)
         CK(vlc_rotor_get_wakevel(u->ctx, jr, ib, w, r->nNwake > 0 ? orc_rotor_vel(r, ib, w) : NULL,
                                  r->nFwake > 0 ? orc_rotor_vel(r, ib, 4 + w) : NULL));
+      if (orc_case_config(u->cas)->fdScheme >= 4) /* the two extra histories of the multistep schemes */
+        for (int w = 4; w < 6; ++w)
+          CK(vlc_rotor_get_wakevel(u->ctx, jr, ib, w, r->nNwake > 0 ? orc_rotor_vel(r, ib, 4 + w) : NULL,
+                                   r->nFwake > 0 ? orc_rotor_vel(r, ib, 6 + w) : NULL));
     }
   }
   return 0;

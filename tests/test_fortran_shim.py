@@ -136,8 +136,10 @@ def test_interface_matches_the_c_prototype(name):
 
 def test_named_constants_equal_the_header_enums():
     txt = re.sub(r"/\*.*?\*/", "", HDR, flags=re.S)
-    enums = {k: int(v) for k, v in re.findall(r"\b(VLC_VEL_\w+)\s*=\s*(\d+)", txt)}
-    assert len(enums) == 6
+    every = {k: int(v) for k, v in re.findall(r"\b(VLC_VEL_\w+)\s*=\s*(\d+)", txt)}
+    enums = {k: v for k, v in every.items() if not k.startswith("VLC_VEL_ARRAY")}
+    arrays = {k: v for k, v in every.items() if k.startswith("VLC_VEL_ARRAY")}
+    assert len(enums) == 6 and len(arrays) == 6
     consts = {}
     for l in LINES:
         if "parameter" in l.lower() and "::" in l:
@@ -146,6 +148,10 @@ def test_named_constants_equal_the_header_enums():
     for k, v in enums.items():
         assert consts.get(k.replace("VLC_", "")) == v, (k, v, consts.get(k.replace("VLC_", "")))
     assert (consts["GPU_BYWING"], consts["GPU_BYWAKE"], consts["GPU_BOTH"], consts["GPU_BOUNDVORTICES"]) == (0, 1, 2, 3)
+    names = {"VLC_VEL_ARRAY": "ARR_VEL", "VLC_VEL_ARRAY_1": "ARR_VEL1", "VLC_VEL_ARRAY_PREDICTED": "ARR_PREDICTED",
+             "VLC_VEL_ARRAY_STEP": "ARR_STEP", "VLC_VEL_ARRAY_2": "ARR_VEL2", "VLC_VEL_ARRAY_3": "ARR_VEL3"}
+    for k, v in arrays.items():
+        assert consts.get(names[k]) == v, (k, v)
 
 
 def test_blocks_balance_and_public_procedures_exist():

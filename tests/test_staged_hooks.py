@@ -50,7 +50,10 @@ CASES = [("katzNplotkin_AR04", 12, None), ("katzNplotkin_AR04", 8, lambda fx: fx
          ("katzNplotkin_AR04", 10, lambda fx: fx["config"].update(fdScheme=2)), ("elevateTest", 14, _elevate_short(2)),
          ("katzNplotkin_AR04", 8, lambda fx: fx["config"].update(fdScheme=1, wakeDissipation=1)),
          ("caradonna", 22, _short_caradonna), ("elevateTest", 14, _elevate_short(3)), ("elevateTest", 14, _elevate_short(1)),
-         ("simplewing", 10, lambda fx: fx["config"].update(wakeStrain=1))]
+         ("simplewing", 10, lambda fx: fx["config"].update(wakeStrain=1)),
+         # fdScheme 4 / 5: third / fourth order Adams-Bashforth / Adams-Moulton with the histories vel2, vel3
+         ("katzNplotkin_AR04", 9, lambda fx: fx["config"].update(fdScheme=4)), ("elevateTest", 14, _elevate_short(4)),
+         ("katzNplotkin_AR04", 9, lambda fx: fx["config"].update(fdScheme=5)), ("elevateTest", 14, _elevate_short(5))]
 
 
 @pytest.mark.parametrize("name,nsteps,mutate", CASES)
@@ -78,7 +81,7 @@ def test_staged_orchestration_equals_inline_time_loop(oracle, name, nsteps, muta
             assert np.array_equal(ra.waN(ib, pred), rb.waN(ib, pred)), (name, "waN", ib, pred)
             if ra.nFwake:
                 assert np.array_equal(ra.waF(ib, pred), rb.waF(ib, pred)), (name, "waF", ib, pred)
-        for w in range(8 if ra.nFwake else 4):
+        for w in (list(range(8)) + [8, 9, 10, 11]) if ra.nFwake else [0, 1, 2, 3, 8, 9]:
             assert np.array_equal(ra.vel(ib, w), rb.vel(ib, w)), (name, "vel", ib, w)
     lib.case_gpu_hooks_free(h)
 

@@ -129,6 +129,8 @@ def load_library() -> C.CDLL:
         "vlc_wake_sweep_slice": (i32, [_vp, i32, i64, i64, _vp]),
         "vlc_wake_sweep_scatter": (i32, [_vp, i32, i32, _vp]),
         "vlc_rotor_wakevel_op": (i32, [_vp, i32, i32]),
+        "vlc_rotor_wakevel_copy": (i32, [_vp, i32, i32, i32]),
+        "vlc_rotor_wakevel_lincomb": (i32, [_vp, i32, i32, i32, C.POINTER(i32), _dp, C.c_double]),
         "vlc_rotor_get_nwake": (i32, [_vp, i32, i32, i32, _vp]),
         "vlc_rotor_get_fwake": (i32, [_vp, i32, i32, i32, _vp]),
         "vlc_rotor_put_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
@@ -430,6 +432,17 @@ class Context:
 
     def rotor_wakevel_op(self, ir, op: int):
         self._ck(self.lib.vlc_rotor_wakevel_op(self.h, ir, op))
+
+    VEL_ARRAY, VEL_ARRAY_1, VEL_ARRAY_PREDICTED, VEL_ARRAY_STEP, VEL_ARRAY_2, VEL_ARRAY_3 = range(6)
+
+    def rotor_wakevel_copy(self, ir, dst: int, src: int):
+        self._ck(self.lib.vlc_rotor_wakevel_copy(self.h, ir, dst, src))
+
+    def rotor_wakevel_lincomb(self, ir, dst: int, src, coef, divisor: float):
+        """dst = (coef[0]*src[0] + ...)/divisor on the velocity arrays (ids VEL_ARRAY_*), terms added left to right."""
+        n = len(src)
+        self._ck(self.lib.vlc_rotor_wakevel_lincomb(self.h, ir, dst, n, (C.c_int * n)(*[int(x) for x in src]),
+                                                    (C.c_double * n)(*[float(x) for x in coef]), float(divisor)))
 
     def rotor_get_nwake(self, ir, ib, nNwake, ns, predicted=False):
         a = np.empty((ns, nNwake, 50), dtype=np.float64)

@@ -88,6 +88,7 @@ struct Rotor {
   double apparentViscCoeff = 0.0, decayCoeff = 0.0, initWakeVel = 0.0;
   double shaftAxis[3] = {0.0, 0.0, 1.0}, hubCoords[3] = {0.0, 0.0, 0.0};
   DevBuf velN[4], velF[4];
+  DevBuf velNx[2], velFx[2];  // [0] vel2, [1] vel3: histories of fdScheme 4 / 5 (classdef.f90:3733-3824), allocated on first use
   DevBuf waN_alt;  // second buffer of shiftwake (swapped with waN[0])
   DevBuf order2_tmp;
   vlc::AxiT* d_axi = nullptr;
@@ -899,6 +900,10 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
       release(r.velN[k]);
       release(r.velF[k]);
     }
+    for (int k = 0; k < 2; ++k) {
+      release(r.velNx[k]);
+      release(r.velFx[k]);
+    }
     release(r.waN_alt);
     release(r.order2_tmp);
     if (r.d_axi) cudaFree(r.d_axi);
@@ -1117,6 +1122,10 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
   if ((rc = reserve(c, r.rhs, (size_t)r.N + 1)) || (rc = reserve(c, r.gamvec, (size_t)r.N + 1))) return rc;
   if ((rc = reserve(c, r.sec, (size_t)nb * vlc::cp::sec_doubles(ns))) || (rc = reserve(c, r.loads, (size_t)nb * vlc::cp::loads_doubles(ns))))
     return rc;
+  for (int k = 0; k < 2; ++k) {  // vel2 / vel3 of an earlier definition start from zero again
+    if (r.velNx[k].p) CUDA_OK(c, cudaMemsetAsync(r.velNx[k].p, 0, r.velNx[k].cap * sizeof(double), c->stream));
+    if (r.velFx[k].p) CUDA_OK(c, cudaMemsetAsync(r.velFx[k].p, 0, r.velFx[k].cap * sizeof(double), c->stream));
+  }
   CUDA_OK(c, cudaMemsetAsync(r.gamvec.p, 0, r.gamvec.cap * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(r.sec.p, 0, r.sec.cap * sizeof(double), c->stream));
   CUDA_OK(c, cudaMemsetAsync(r.loads.p, 0, r.loads.cap * sizeof(double), c->stream));
@@ -1846,6 +1855,81 @@ extern "C" int vlc_rotor_wakevel_op(vlc_ctx* c, int ir, int op) {
   return VLC_OK;
 }
 
+namespace {
+// velocity array by id: 0 vel, 1 vel1, 2 velPredicted, 3 velStep, 4 vel2, 5 vel3 (VLC_VEL_ARRAY_*)
+DevBuf& vel_array(Rotor& r, int id, bool far) {
+  if (id < 4) return far ? r.velF[id] : r.velN[id];
+  return far ? r.velFx[id - 4] : r.velNx[id - 4];
+}
+// vel2 / vel3 exist from their first use on, zero like the other arrays after vlc_rotor_define
+int ensure_histories(vlc_ctx* c, Rotor& r) {
+  int rc;
+  for (int k = 0; k < 2; ++k) {
+    const size_t nn = (size_t)3 * r.nNwake * (r.ns + 1) * r.nb + 1, nf = (size_t)3 * r.nFwake * r.nb + 1;
+    if (r.velNx[k].cap < nn) {
+      if ((rc = reserve(c, r.velNx[k], nn))) return rc;
+      CUDA_OK(c, cudaMemsetAsync(r.velNx[k].p, 0, r.velNx[k].cap * sizeof(double), c->stream));
+    }
+    if (r.velFx[k].cap < nf) {
+      if ((rc = reserve(c, r.velFx[k], nf))) return rc;
+      CUDA_OK(c, cudaMemsetAsync(r.velFx[k].p, 0, r.velFx[k].cap * sizeof(double), c->stream));
+    }
+  }
+  return VLC_OK;
+}
+}  // namespace
+
+extern "C" int vlc_rotor_wakevel_copy(vlc_ctx* c, int ir, int dst, int src) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (dst < 0 || dst > 5 || src < 0 || src > 5) return fail(c, VLC_ERR_ARG, "velocity array id outside 0..5");
+  if (r->nNwake <= 0 || dst == src) return VLC_OK;
+  if ((dst > 3 || src > 3) && (rc = ensure_histories(c, *r))) return rc;
+  const size_t nn = (size_t)3 * r->nNwake * (r->ns + 1) * r->nbConvect, nf = (size_t)3 * r->nFwake * r->nbConvect;
+  if (nn) CUDA_OK(c, cudaMemcpyAsync(vel_array(*r, dst, false).p, vel_array(*r, src, false).p, nn * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+  if (nf) CUDA_OK(c, cudaMemcpyAsync(vel_array(*r, dst, true).p, vel_array(*r, src, true).p, nf * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_wakevel_lincomb(vlc_ctx* c, int ir, int dst, int nterms, const int* src, const double* coef,
+                                         double divisor) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (dst < 0 || dst > 5 || nterms < 1 || nterms > 4 || !src || !coef || divisor == 0.0)
+    return fail(c, VLC_ERR_ARG, "bad linear combination of velocity arrays");
+  bool hist = dst > 3;
+  for (int k = 0; k < nterms; ++k) {
+    if (src[k] < 0 || src[k] > 5) return fail(c, VLC_ERR_ARG, "velocity array id outside 0..5");
+    hist = hist || src[k] > 3;
+  }
+  if (r->nNwake <= 0) return VLC_OK;
+  if (hist && (rc = ensure_histories(c, *r))) return rc;
+  const long long nn = 3LL * r->nNwake * (r->ns + 1) * r->nbConvect, nf = 3LL * r->nFwake * r->nbConvect;
+  for (int far = 0; far < 2; ++far) {
+    const long long n = far ? nf : nn;
+    if (n <= 0) continue;
+    const double* s[4];
+    double cf[4];
+    for (int k = 0; k < 4; ++k) {
+      s[k] = vel_array(*r, src[k < nterms ? k : 0], far != 0).p;
+      cf[k] = k < nterms ? coef[k] : 0.0;
+    }
+    vlc::rec_lincomb_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(n, nterms, s[0], s[1], s[2], s[3], cf[0], cf[1], cf[2], cf[3],
+                                                                        divisor, vel_array(*r, dst, far != 0).p);
+    c->launches++;
+  }
+  CUDA_OK(c, cudaGetLastError());
+  return VLC_OK;
+}
+
 extern "C" int vlc_rotor_get_nwake(vlc_ctx* c, int ir, int ib, int predicted, double* waN) {
   CHECK_CTX(c);
   int rc = bind_device(c);
@@ -1881,10 +1965,11 @@ extern "C" int vlc_rotor_put_wakevel(vlc_ctx* c, int ir, int ib, int which, cons
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
-  if (ib < 0 || ib >= r->nb || which < 0 || which > 3) return fail(c, VLC_ERR_ARG, "bad blade index / array selector");
+  if (ib < 0 || ib >= r->nb || which < 0 || which > 5) return fail(c, VLC_ERR_ARG, "bad blade index / array selector");
+  if (which > 3 && (rc = ensure_histories(c, *r))) return rc;
   const size_t pn = (size_t)3 * r->nNwake * (r->ns + 1), pf = (size_t)3 * r->nFwake;
-  if (velN && pn) CUDA_OK(c, cudaMemcpyAsync(r->velN[which].p + pn * ib, velN, pn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (velF && pf) CUDA_OK(c, cudaMemcpyAsync(r->velF[which].p + pf * ib, velF, pf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (velN && pn) CUDA_OK(c, cudaMemcpyAsync(vel_array(*r, which, false).p + pn * ib, velN, pn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (velF && pf) CUDA_OK(c, cudaMemcpyAsync(vel_array(*r, which, true).p + pf * ib, velF, pf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }
@@ -1895,10 +1980,11 @@ extern "C" int vlc_rotor_get_wakevel(vlc_ctx* c, int ir, int ib, int which, doub
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
-  if (ib < 0 || ib >= r->nb || which < 0 || which > 3) return fail(c, VLC_ERR_ARG, "bad blade index / array selector");
+  if (ib < 0 || ib >= r->nb || which < 0 || which > 5) return fail(c, VLC_ERR_ARG, "bad blade index / array selector");
+  if (which > 3 && (rc = ensure_histories(c, *r))) return rc;
   const size_t pn = (size_t)3 * r->nNwake * (r->ns + 1), pf = (size_t)3 * r->nFwake;
-  if (velN && pn) CUDA_OK(c, cudaMemcpyAsync(velN, r->velN[which].p + pn * ib, pn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (velF && pf) CUDA_OK(c, cudaMemcpyAsync(velF, r->velF[which].p + pf * ib, pf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (velN && pn) CUDA_OK(c, cudaMemcpyAsync(velN, vel_array(*r, which, false).p + pn * ib, pn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (velF && pf) CUDA_OK(c, cudaMemcpyAsync(velF, vel_array(*r, which, true).p + pf * ib, pf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }

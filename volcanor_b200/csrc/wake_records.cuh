@@ -383,6 +383,20 @@ __global__ void rec_accumulate_kernel(long long n, int first, const double* __re
   if (i < n) acc[i] = first ? __dadd_rn(0.0, v[i]) : __dadd_rn(acc[i], v[i]);
 }
 
+// dst = (c0*s0 + c1*s1 + c2*s2 + c3*s3)/div with the terms added left to right: the multistep velocity formulas of
+// fdScheme 4 / 5 (main.f90:1160-1172, :1222-1231, :1309-1325, :1370-1381; signs in the coefficients: a - 16*b is
+// a + (-16)*b bit for bit).  dst may be one of the sources: a thread reads its element of every source before it writes.
+__global__ void rec_lincomb_kernel(long long n, int nterms, const double* s0, const double* s1, const double* s2,
+                                   const double* s3, double c0, double c1, double c2, double c3, double div, double* dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = __dmul_rn(c0, s0[i]);
+  if (nterms > 1) acc = __dadd_rn(acc, __dmul_rn(c1, s1[i]));
+  if (nterms > 2) acc = __dadd_rn(acc, __dmul_rn(c2, s2[i]));
+  if (nterms > 3) acc = __dadd_rn(acc, __dmul_rn(c3, s3[i]));
+  dst[i] = __ddiv_rn(acc, div);
+}
+
 // Scatter the swept velocities into velNwake(:, rowNear:nNwake, :) / velFwake(:, rowFar:nFwake) of every convected
 // blade and add the initial wake velocity w = initWakeVel*shaftAxis with the reference's signs (main.f90:829-838,
 // :904-911): 'C' near +w, everything else -w; addInit = 0 leaves it out (iter >= initWakeVelNt).
