@@ -3,7 +3,8 @@
 path on the GPU (tests/native/case_gpu_hooks.c), prints CT history checkpoints and timings.  Test infrastructure
 (uses oracle/): a profiling aid for profiles/, not a benchmark arm.
 
-  python tests/tools/run_case_native.py caradonna [nsteps] [--resident]     (--resident: tier 2b, the wake stays on the device)
+  python tests/tools/run_case_native.py caradonna [nsteps] [--resident] [--cp]
+      --resident: tier 2b, the wake stays on the device; --cp: tier 2c as well (RHS, solve, map_gam, loads on the device)
 """
 import json
 import sys
@@ -20,6 +21,9 @@ def main():
     resident = "--resident" in sys.argv
     if resident:
         sys.argv.remove("--resident")
+    cp = "--cp" in sys.argv
+    if cp:
+        sys.argv.remove("--cp")
     name = sys.argv[1] if len(sys.argv) > 1 else "caradonna"
     import volcanor_b200 as vb
     from oracle import pyoracle
@@ -30,11 +34,15 @@ def main():
     c = pyoracle.Case(fx)
     ctx = vb.Context(0)
     lib, h = (_resident_hooks if resident else _native_hooks)(c, ctx)
+    if cp:
+        import ctypes as C
+        lib.case_hooks_enable_cp.argtypes = [C.c_void_p]
+        assert lib.case_hooks_enable_cp(h) == 0, ctx.lib.vlc_last_error(ctx.h)
     t0 = time.perf_counter()
     c.init()
     nt = c.config.nt if len(sys.argv) < 3 else min(int(sys.argv[2]), c.config.nt)
     d = c.rotor(0).dims()
-    print(f"{name}{' (wake resident on the device)' if resident else ''}: nt {c.config.nt} dt {c.config.dt:.6e} {d}; init {time.perf_counter() - t0:.2f} s")
+    print(f"{name}{' (wake resident on the device)' if resident else ''}{' (collocation-point stage on the device)' if cp else ''}: nt {c.config.nt} dt {c.config.dt:.6e} {d}; init {time.perf_counter() - t0:.2f} s")
     t1 = time.perf_counter()
     pairs, tlast = 0.0, t1
     per_step = []

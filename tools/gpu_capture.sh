@@ -25,5 +25,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:bs_lattice -s 4 -c 1 \
   -f -o $OUT/prof_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline \
   > $OUT/ncu_full_$TAG.log 2>&1
+# the reference cases through the C ABI: wake resident (tier 2b) and with the collocation-point stage on the device (tier 2c)
+for CASE in katzNplotkin_AR04 elevateTest caradonna; do
+  timeout 300 python tests/tools/run_case_native.py $CASE --resident > $OUT/${CASE}_resident_$TAG.log 2>&1
+  timeout 300 python tests/tools/run_case_native.py $CASE --resident --cp > $OUT/${CASE}_resident_cp_$TAG.log 2>&1
+  tail -1 $OUT/${CASE}_resident_$TAG.log; tail -1 $OUT/${CASE}_resident_cp_$TAG.log
+done
 ls -la $OUT | tail -20
 grep -h -o '"value": [0-9.e+]*' $OUT/bench_$TAG.json | head -3
