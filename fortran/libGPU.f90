@@ -531,6 +531,42 @@ contains
     endif
   end subroutine gpu_wake_prestep
 
+  subroutine gpu_convect(rotor, ir, iter, dt, p)
+    !! rotor%convectwake(iter, dt, wakeType) (classdef.f90:4786-4830) on the device records.  Its last statement, the
+    !! prescribed far wake (:4826-4828, rotor%updatePrescribedWake :5170-5218), keeps its generator on the host: the far
+    !! rows come down (104 bytes each), the 240 helix filaments per blade go up -- O(nFwake + 240) per blade per stage.
+    !! rowFar is the driver's own counter (main.f90:412-417); nFwakeEnd never changes after init.
+    type(rotor_class), intent(inout) :: rotor
+    integer, intent(in) :: ir, iter
+    real(dp), intent(in) :: dt
+    integer(c_int), intent(in) :: p
+    integer :: ib
+    real(c_double), allocatable :: buf(:)
+    call check(vlc_rotor_convectwake(ctx, ir - 1, dt, p))
+    if (.not. (rotor%prescWakeNt > 0 .and. iter > rotor%prescWakeNt)) return
+    allocate (buf(13*rotor%nFwake))
+    do ib = 1, rotor%nb
+      call check(vlc_rotor_get_fwake(ctx, ir - 1, ib - 1, p, buf))
+      if (p == 1) then
+        rotor%blade(ib)%waFPredicted = transfer(buf, rotor%blade(ib)%waFPredicted)
+      else
+        rotor%blade(ib)%waF = transfer(buf, rotor%blade(ib)%waF)
+      endif
+    enddo
+    deallocate (buf)
+    call rotor%updatePrescribedWake(dt, merge('P', 'C', p == 1))
+    allocate (buf(13*240))
+    do ib = 1, rotor%nb
+      if (p == 1) then
+        buf = transfer(rotor%blade(ib)%wapFPredicted%waF, buf)
+      else
+        buf = transfer(rotor%blade(ib)%wapF%waF, buf)
+      endif
+      call check(vlc_rotor_put_pfwake(ctx, ir - 1, ib - 1, p, buf))
+    enddo
+    deallocate (buf)
+  end subroutine gpu_convect
+
   ! One MPI rank per GPU: replace each `vlc_wake_sweep(ctx, p, addInit)` below by
   !   vlc_wake_sweep_count(ctx, M); vlc_wake_sweep_slice(ctx, p, first, count, d_vel) on this rank's slice of the M targets;
   !   MPI_Allgather / ncclAllGather of d_vel (3*M doubles on the device, slices of ceiling(M/nranks) targets);
@@ -540,7 +576,7 @@ contains
     !! Replaces main.f90:800-1440: the wake sweeps, the fdScheme switch (0 explicit Euler :846-859, 1 predictor-
     !! corrector :861-949, 2 explicit Adams-Bashforth :951-1000, 3 Adams-Bashforth / Adams-Moulton :1002-1115, 4 and 5 the
     !! same of third and fourth order :1117-1404) with its velocity bookkeeping, strain_wake, rollup, assignshed('TE').
-    type(rotor_class), intent(in) :: rotor(:)
+    type(rotor_class), intent(inout) :: rotor(:)   ! inout: the prescribed far wake, when used, is regenerated on the host
     integer, intent(in) :: iter, fdScheme, wakeStrain, initWakeVelNt
     real(dp), intent(in) :: dt
     integer :: ir, start
@@ -554,46 +590,46 @@ contains
     select case (fdScheme)
     case (0)
       do ir = 1, size(rotor)
-        call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+        call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
       enddo
     case (2)   ! explicit Adams-Bashforth (:951-1000): velStep = vel1 = vel = 0.5*(3*vel - vel1), then convect
       do ir = 1, size(rotor)
         if (iter == 1) then
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_FIRST_STEP))
         else
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_AB2))
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_FIRST_STEP))
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_COPY_TO_STEP))
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
         endif
       enddo
     case (1)
       do ir = 1, size(rotor)
         call check(vlc_rotor_wake_to_predicted(ctx, ir - 1))
-        call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 1_c_int))
+        call gpu_convect(rotor(ir), ir, iter, dt, 1_c_int)
       enddo
       call check(vlc_wake_sweep(ctx, 1_c_int, addInit))
       do ir = 1, size(rotor)
         call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_ORDER2))
-        call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+        call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
       enddo
     case (3)
       if (iter == 1) then
         do ir = 1, size(rotor)
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_FIRST_STEP))
         enddo
       else
         do ir = 1, size(rotor)
           call check(vlc_rotor_wake_to_predicted(ctx, ir - 1))
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_AB2))
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 1_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 1_c_int)
         enddo
         call check(vlc_wake_sweep(ctx, 1_c_int, addInit))
         do ir = 1, size(rotor)
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_AM2))
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
           call check(vlc_rotor_wakevel_op(ctx, ir - 1, VEL_SHIFT_HISTORY))
         enddo
       endif
@@ -605,7 +641,7 @@ contains
       endif
       if (start > 0) then            ! this step only fills the history vel1 / vel2 / vel3
         do ir = 1, size(rotor)
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
           call check(vlc_rotor_wakevel_copy(ctx, ir - 1, hist(start), ARR_VEL))
         enddo
       else
@@ -619,7 +655,7 @@ contains
             call check(vlc_rotor_wakevel_lincomb(ctx, ir - 1, ARR_VEL, 4_c_int, [ARR_VEL, ARR_VEL3, ARR_VEL2, ARR_VEL1], &
               & [55._c_double, -59._c_double, 37._c_double, -9._c_double], 24._c_double))
           endif
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 1_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 1_c_int)
         enddo
         call check(vlc_wake_sweep(ctx, 1_c_int, addInit))
         do ir = 1, size(rotor)
@@ -630,7 +666,7 @@ contains
             call check(vlc_rotor_wakevel_lincomb(ctx, ir - 1, ARR_VEL, 4_c_int, [ARR_PREDICTED, ARR_STEP, ARR_VEL3, ARR_VEL2], &
               & [9._c_double, 19._c_double, -5._c_double, 1._c_double], 24._c_double))
           endif
-          call check(vlc_rotor_convectwake(ctx, ir - 1, dt, 0_c_int))
+          call gpu_convect(rotor(ir), ir, iter, dt, 0_c_int)
           call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_VEL1, ARR_VEL2))
           if (fdScheme == 4) then
             call check(vlc_rotor_wakevel_copy(ctx, ir - 1, ARR_VEL2, ARR_STEP))

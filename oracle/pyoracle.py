@@ -73,6 +73,8 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_rotor_calcAIC": (i32, [_vp]),
         "orc_rotor_map_gam": (None, [_vp]),
         "orc_rotor_convectwake": (None, [_vp, i32, d, C.c_char]),
+        "orc_pfwake_update": (i32, [_vp, _vp, _vp, _vp, i32, _vp, _vp, d]),
+        "orc_rotor_updatePrescribedWake": (i32, [_vp, d, C.c_char]),
         "orc_rotor_assignshed": (None, [_vp, C.c_char_p]),
         "orc_rotor_age_wake": (None, [_vp, d]),
         "orc_rotor_dissipate_wake": (None, [_vp, d, d]),

@@ -652,6 +652,7 @@ static orc_rotor_t *rotor_init(orc_case_t *c, geom_t *g) {
   toChordsRevs(g, &g->prescWakeAfterTruncNt, dt);
   toChordsRevs(g, &g->prescWakeGenNt, dt);
   toChordsRevs(g, &g->nNwake, dt);
+  const int prescWakeNt = (g->wakeTruncateNt > 0 && g->prescWakeAfterTruncNt > 0) ? g->wakeTruncateNt + g->prescWakeAfterTruncNt : 0; /* :3013-3017 */
   if (g->wakeTruncateNt > 0 && g->wakeTruncateNt < g->nNwake + 1) g->wakeTruncateNt = g->nNwake + 1; /* :3019-3021 */
   if (g->surfaceType == 0) g->surfaceType = 1;
   if (g->nNwake > 0 && g->nNwake < 2) {
@@ -678,7 +679,9 @@ static orc_rotor_t *rotor_init(orc_case_t *c, geom_t *g) {
   r->symmetricTau = g->symmetricTau;
   r->forceCalcSwitch = g->forceCalcSwitch;
   r->wakeTruncateNt = g->wakeTruncateNt;
-  r->prescWakeNt = 0;
+  r->prescWakeNt = prescWakeNt;
+  r->prescWakeAfterTruncNt = g->prescWakeAfterTruncNt;
+  r->prescWakeGenNt = g->prescWakeGenNt;
   r->radius = g->span;
   r->root_cut = g->rootcut;
   r->chord = g->chord;

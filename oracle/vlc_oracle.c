@@ -547,10 +547,85 @@ static void blade_rot_wake_axis(orc_blade_t *b, double theta, const double axisV
   }
 }
 
-/* classdef.f90:4786-4830.  The prescribed-wake generator (:4826-4828, :5172-5217) is
- * out of scope (prescWakeAfterTruncNt = 0 in every shipped case => prescWakeNt = 0). */
+/* classdef.f90:998-1066 pFwake_update: a helix of 10 revolutions in 240 filaments of 15 degrees, fitted to the mean radius
+ * and pitch of the far-wake filaments waF(1:nFwake) handed in, relaxed against the previous fit, attached to the last of
+ * them.  PARITY UNPINNED (no shipped case, no reference test).  isClockwiseRotor keeps its default .true. everywhere. */
+int orc_pfwake_update(orc_fwake_t *pf, double *helixPitch, double *helixRadius, const orc_fwake_t *waF, int nFwake,
+                      const double hubCoords[3], const double shaftAxis[3], double deltaPsi) {
+  const double twoPi = 2.0 * orc_pi(), relaxFactor = 0.5, nRevs = 10.0;
+  if (fabs(shaftAxis[0]) > ORC_EPS || fabs(shaftAxis[1]) > ORC_EPS) return 1; /* "only implemented for shaft along Z-axis" */
+  if (nFwake < 1) return 2;
+  double anchor[3] = {waF[nFwake - 1].vf.fc[0][0], waF[nFwake - 1].vf.fc[0][1], waF[nFwake - 1].vf.fc[0][2]};
+  double pitchCur = 0.0, radiusCur = 0.0;
+  for (int i = 1; i <= nFwake; ++i) {
+    const double y = waF[i - 1].vf.fc[0][1], x = waF[i - 1].vf.fc[0][0];
+    radiusCur = radiusCur + sqrt(y * y + x * x); /* norm2([fc(2,1), fc(1,1)]) */
+    if (i < nFwake) pitchCur = pitchCur + waF[i - 1].vf.fc[0][2] - waF[i].vf.fc[0][2];
+  }
+  pitchCur = fabs(pitchCur) * (-twoPi / deltaPsi) / (nFwake - 1);
+  radiusCur = radiusCur / nFwake;
+  *helixPitch = relaxFactor * pitchCur + (1 - relaxFactor) * *helixPitch;
+  *helixRadius = relaxFactor * radiusCur + (1 - relaxFactor) * *helixRadius;
+  const double dTheta = atan2(anchor[1], anchor[0]);
+  const double deltaZ = anchor[2] - hubCoords[2];
+  double coords[ORC_NPFWAKE + 1][3];
+  const double dx = (twoPi * nRevs - 0.0) / ((ORC_NPFWAKE + 1) - 1); /* linspace, libMath.f90:138-157 */
+  for (int i = 0; i <= ORC_NPFWAKE; ++i) {
+    double theta = i * dx;
+    theta = theta + 0.0;
+    theta = -1.0 * theta; /* isClockwiseRotor */
+    coords[i][0] = *helixRadius * cos(theta + dTheta);
+    coords[i][1] = *helixRadius * sin(theta + dTheta);
+    coords[i][2] = *helixPitch * fabs(theta) / twoPi + deltaZ;
+  }
+  for (int i = 1; i <= ORC_NPFWAKE; ++i)
+    for (int k = 0; k < 3; ++k) {
+      pf[i - 1].vf.fc[1][k] = hubCoords[k] + coords[i - 1][k]; /* assignP(2, ...) */
+      pf[i - 1].vf.fc[0][k] = hubCoords[k] + coords[i][k];     /* assignP(1, ...) */
+    }
+  for (int k = 0; k < 3; ++k) pf[0].vf.fc[1][k] = anchor[k]; /* continuity with the far wake */
+  for (int i = 0; i < ORC_NPFWAKE; ++i) {
+    pf[i].gam = waF[nFwake - 1].gam;
+    pf[i].vf.rVc = waF[nFwake - 1].vf.rVc;
+  }
+  return 0;
+}
+
+/* classdef.f90:5170-5218 */
+int orc_rotor_updatePrescribedWake(orc_rotor_t *r, double dt, char wakeType) {
+  const double twoPi = 2.0 * orc_pi();
+  const int s = (wakeType == 'C') ? 0 : 1;
+  const int rowStart = (r->prescWakeGenNt == 0) ? r->rowFar : r->nFwakeEnd - r->prescWakeGenNt;
+  if (rowStart < 1 || rowStart > r->nFwakeEnd) return 2;
+  for (int ib = 0; ib < r->nbConvect; ++ib) {
+    orc_blade_t *b = &r->blade[ib];
+    int rc = orc_pfwake_update(s ? b->wapFPredicted : b->wapF, &b->pfHelixPitch[s], &b->pfHelixRadius[s],
+                               (s ? b->waFPredicted : b->waF) + (rowStart - 1), r->nFwakeEnd - rowStart + 1, r->hubCoords,
+                               r->shaftAxis, r->omegaSlow * dt);
+    if (rc) return rc;
+  }
+  if (r->axisymmetrySwitch == 1)
+    for (int ib = 2; ib <= r->nb; ++ib) {
+      const double bladeOffset = twoPi / r->nb * (ib - 1);
+      orc_blade_t *b = &r->blade[ib - 1], *b1 = &r->blade[0];
+      orc_fwake_t *pf = s ? b->wapFPredicted : b->wapF;
+      memcpy(pf, s ? b1->wapFPredicted : b1->wapF, sizeof(orc_fwake_t) * ORC_NPFWAKE);
+      b->pfHelixPitch[s] = b1->pfHelixPitch[s];
+      b->pfHelixRadius[s] = b1->pfHelixRadius[s];
+      if (fabs(bladeOffset) > ORC_EPS) { /* pFwake_rot_wake_axis :1068-1086 */
+        double T[9];
+        orc_getTransformAxis(bladeOffset, r->shaftAxis, T);
+        for (int i = 0; i < ORC_NPFWAKE; ++i) {
+          rot_point(T, r->hubCoords, pf[i].vf.fc[0]);
+          rot_point(T, r->hubCoords, pf[i].vf.fc[1]);
+        }
+      }
+    }
+  return 0;
+}
+
+/* classdef.f90:4786-4830 */
 void orc_rotor_convectwake(orc_rotor_t *r, int iter, double dt, char wakeType) {
-  (void)iter;
   const double twoPi = 2.0 * orc_pi();
   for (int ib = 0; ib < r->nbConvect; ++ib)
     orc_blade_convectwake(&r->blade[ib], r->rowNear, r->rowFar, dt, wakeType, r->ductSwitch);
@@ -569,6 +644,7 @@ void orc_rotor_convectwake(orc_rotor_t *r, int iter, double dt, char wakeType) {
       blade_rot_wake_axis(b, bladeOffset, r->shaftAxis, r->hubCoords, r->rowNear, r->rowFar, wakeType);
     }
   }
+  if (r->prescWakeNt > 0 && iter > r->prescWakeNt) orc_rotor_updatePrescribedWake(r, dt, wakeType); /* :4826-4828 */
 }
 
 /* classdef.f90:4297-4325 */

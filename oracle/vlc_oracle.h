@@ -68,6 +68,7 @@ typedef struct {
   orc_vr_t *waN, *waNPredicted;
   orc_fwake_t *waF, *waFPredicted;
   orc_fwake_t wapF[ORC_NPFWAKE], wapFPredicted[ORC_NPFWAKE];
+  double pfHelixPitch[2], pfHelixRadius[2]; /* pFwake_class%helixPitch / helixRadius of wapF [0] and wapFPredicted [1] */
   double *velNwake, *velNwake1, *velNwakePredicted, *velNwakeStep; /* (3,nNwake,ns+1) */
   double *velFwake, *velFwake1, *velFwakePredicted, *velFwakeStep; /* (3,nFwake) */
   double *velNwake2, *velNwake3, *velFwake2, *velFwake3;           /* fdScheme 4 / 5 histories (classdef.f90:3733-3824) */
@@ -124,6 +125,11 @@ void orc_matmulAX(int m, int n, const double *A, const double *X, double *AX); /
 
 /* ---- pair kernel: classdef.f90:476-503, 527-542 ---- */
 void orc_vf_vind(const orc_vf_t *f, const double P[3], double v[3]);
+/* classdef.f90:998-1066 pFwake_update and :5170-5218 rotor_updatePrescribedWake (PARITY UNPINNED: no shipped case and no
+ * reference test enables the prescribed far wake; restated from the source only) */
+int orc_pfwake_update(orc_fwake_t *pf, double *helixPitch, double *helixRadius, const orc_fwake_t *waF, int nFwake,
+                      const double hubCoords[3], const double shaftAxis[3], double deltaPsi);
+int orc_rotor_updatePrescribedWake(orc_rotor_t *r, double dt, char wakeType);
 void orc_vr_vind(const orc_vr_t *r, const double P[3], double v[3]);
 
 /* ---- source loops: classdef.f90:1342-1513, 4424-4479 ---- */

@@ -130,6 +130,7 @@ static int sync_rotor(gpu_user_t *u, int jr, int predicted) {
     if (wake_new) {
       if (nNwake > 0 && (rc = vlc_rotor_put_nwake(u->ctx, jr, ib, predicted, orc_rotor_waN(r, ib, predicted)))) return rc;
       if (nFwake > 0 && (rc = vlc_rotor_put_fwake(u->ctx, jr, ib, predicted, orc_rotor_waF(r, ib, predicted)))) return rc;
+      if (r->prescWakeNt > 0 && (rc = vlc_rotor_put_pfwake(u->ctx, jr, ib, predicted, orc_rotor_wapF(r, ib, predicted)))) return rc;
     }
   }
   u->have_wing[jr] = g[0];
@@ -188,7 +189,19 @@ static int g_age(gpu_user_t *u, int ir, double dt, double om) { return vlc_rotor
 static int g_dissipate(gpu_user_t *u, int ir, double dt, double nu) { return vlc_rotor_dissipate_wake(u->ctx, ir, dt, nu); }
 static int g_strain(gpu_user_t *u, int ir) { return vlc_rotor_strain_wake(u->ctx, ir); }
 static int g_to_pred(gpu_user_t *u, int ir) { return vlc_rotor_wake_to_predicted(u->ctx, ir); }
-static int g_convect(gpu_user_t *u, int ir, int iter, double dt, int p) { (void)iter; return vlc_rotor_convectwake(u->ctx, ir, dt, p); }
+/* convectwake on the device; the prescribed far wake (classdef.f90:4826-4828), when the case uses one, keeps its generator on
+ * the host: far rows down, rotor%updatePrescribedWake, the 240 helix filaments up */
+static int g_convect(gpu_user_t *u, int ir, int iter, double dt, int p) {
+  int rc = vlc_rotor_convectwake(u->ctx, ir, dt, p);
+  orc_rotor_t *r = orc_case_rotor(u->cas, ir);
+  if (rc || !(r->prescWakeNt > 0 && iter > r->prescWakeNt)) return rc;
+  for (int ib = 0; ib < r->nb; ++ib)
+    if ((rc = vlc_rotor_get_fwake(u->ctx, ir, ib, p, orc_rotor_waF(r, ib, p)))) return rc;
+  if (orc_rotor_updatePrescribedWake(r, dt, p ? 'P' : 'C')) return VLC_ERR_STATE;
+  for (int ib = 0; ib < r->nb; ++ib)
+    if ((rc = vlc_rotor_put_pfwake(u->ctx, ir, ib, p, orc_rotor_wapF(r, ib, p)))) return rc;
+  return 0;
+}
 static int g_rollup(gpu_user_t *u, int ir) { return vlc_rotor_rollup(u->ctx, ir); }
 static int g_sweep(gpu_user_t *u, int p, int addInit) { return vlc_wake_sweep(u->ctx, p, addInit); }
 static int g_sweep_count(gpu_user_t *u, int64_t *M) { return vlc_wake_sweep_count(u->ctx, M); }

@@ -1,0 +1,173 @@
+"""Prescribed far wake (classdef.f90:222-236 pFwake_class, :998-1066 pFwake_update, :5170-5218
+rotor_updatePrescribedWake, hook :4826-4828 in rotor_convectwake).  PARITY UNPINNED: no shipped case and no reference test
+enables it (prescWakeAfterTruncNt = 0 everywhere), so these tests pin the oracle's restatement against a second, independent
+numpy restatement written from the same source lines, against the structural properties the source guarantees, and check
+that the staged orchestration (the library's resident mode keeps this generator on the host) reproduces the
+driver's inline statement bit for bit, 240 helix filaments included."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+NPF, FW = 240, 13
+
+
+def _np_pfwake_update(waF, hub, dpsi, pitch0, radius0):
+    """pFwake_update (classdef.f90:998-1066) with numpy; waF (n, 13) records: fc(:,1) = [0:3], fc(:,2) = [3:6], rVc = [9],
+    gam = [12].  Returns (records (240, 13) with only fc / rVc / gam filled, helixPitch, helixRadius)."""
+    two_pi = 2.0 * (np.arctan(1.0) * 4.0)
+    n = waF.shape[0]
+    anchor = waF[-1, 0:3]
+    radius = 0.0
+    pitch = 0.0
+    for i in range(n):                                           # :1022-1030, summation order of the source
+        radius = radius + np.sqrt(waF[i, 1] ** 2 + waF[i, 0] ** 2)
+        if i < n - 1:
+            pitch = pitch + waF[i, 2] - waF[i + 1, 2]
+    pitch = abs(pitch) * (-two_pi / dpsi) / (n - 1)
+    radius = radius / n
+    pitch = 0.5 * pitch + (1 - 0.5) * pitch0                     # :1035-1038
+    radius = 0.5 * radius + (1 - 0.5) * radius0
+    d_theta = np.arctan2(anchor[1], anchor[0])
+    dz = anchor[2] - hub[2]
+    theta = -1.0 * (np.arange(NPF + 1) * ((two_pi * 10.0) / NPF) + 0.0)   # linspace libMath.f90:138-157, clockwise
+    coords = np.stack([radius * np.cos(theta + d_theta), radius * np.sin(theta + d_theta),
+                       pitch * np.abs(theta) / two_pi + dz])     # (3, 241)
+    out = np.zeros((NPF, FW))
+    out[:, 3:6] = (hub[:, None] + coords[:, :NPF]).T             # assignP(2, ...) :1057
+    out[:, 0:3] = (hub[:, None] + coords[:, 1:]).T               # assignP(1, ...) :1058
+    out[0, 3:6] = anchor                                         # :1062
+    out[:, 12] = waF[-1, 12]
+    out[:, 9] = waF[-1, 9]
+    return out, pitch, radius
+
+
+def _call_update(oracle, pf, pitch, radius, waF, hub, axis, dpsi):
+    lib = oracle.load()
+    p, r = C.c_double(pitch), C.c_double(radius)
+    waF = np.ascontiguousarray(waF)
+    hub = np.ascontiguousarray(hub, dtype=np.float64)
+    axis = np.ascontiguousarray(axis, dtype=np.float64)
+    rc = lib.orc_pfwake_update(pf.ctypes.data, C.addressof(p), C.addressof(r), waF.ctypes.data, waF.shape[0],
+                               hub.ctypes.data, axis.ctypes.data, dpsi)
+    return rc, p.value, r.value
+
+
+def _helical_far_wake(rng, n, hub):
+    psi = -np.arange(n)[::-1] * np.deg2rad(12.0) + 0.3           # last record = the newest... any order is legal input
+    rad = 1.9 + 0.05 * rng.standard_normal(n)
+    waF = np.zeros((n, FW))
+    waF[:, 0] = hub[0] * 0 + rad * np.cos(psi)                   # the source measures the radius from the origin, not the hub
+    waF[:, 1] = rad * np.sin(psi)
+    waF[:, 2] = hub[2] - 0.8 - 0.07 * np.arange(n)[::-1] + 0.002 * rng.standard_normal(n)
+    waF[1:, 3:6] = waF[:-1, 0:3]
+    waF[0, 3:6] = waF[0, 0:3] + [0.1, 0.0, 0.05]
+    waF[:, 9] = 0.03 + 0.01 * rng.random(n)
+    waF[:, 8] = waF[:, 9]
+    waF[:, 12] = -1.3 + 0.1 * rng.random(n)
+    return waF
+
+
+@pytest.mark.parametrize("n,seed", [(2, 1), (7, 2), (40, 3)])
+def test_pfwake_update_against_numpy_restatement(oracle, n, seed):
+    rng = np.random.default_rng(seed)
+    hub = np.array([0.0, 0.0, 0.4])
+    waF = _helical_far_wake(rng, n, hub)
+    dpsi = 130.9 * 1.92e-3
+    pf = np.full((NPF, FW), 7.0)                                  # members the update must leave alone keep the 7
+    rc, pitch, radius = _call_update(oracle, pf, 0.0, 0.0, waF, hub, [0, 0, 1], dpsi)
+    assert rc == 0
+    ref, pitch_np, radius_np = _np_pfwake_update(waF, hub, dpsi, 0.0, 0.0)
+    assert pitch == pitch_np and radius == radius_np              # plain sums and products: bit-identical
+    assert pitch < 0 and abs(2 * radius - 1.9) < 0.1              # descending along -z; half the fit: relaxed from 0
+    for sl in (slice(0, 3), slice(3, 6)):                         # cos / sin: libm vs numpy, a few ulp of the radius
+        assert np.max(np.abs(pf[:, sl] - ref[:, sl])) <= 8 * np.finfo(float).eps * (abs(radius) + 10 * abs(pitch) + 1.0)
+    assert np.array_equal(pf[:, 9], ref[:, 9]) and np.array_equal(pf[:, 12], ref[:, 12])
+    assert np.all(pf[:, [6, 7, 8, 10, 11]] == 7.0)                # l0, lc, rVc0, age, ageAzimuthal untouched (:1064-1065)
+    # structure: starts at the anchor, contiguous polyline, 10 revolutions of 15 degree filaments at the fitted radius
+    assert np.array_equal(pf[0, 3:6], waF[-1, 0:3])
+    assert np.array_equal(pf[1:, 3:6], pf[:-1, 0:3])
+    r_xy = np.hypot(pf[:, 0] - hub[0], pf[:, 1] - hub[1])
+    assert np.allclose(r_xy, radius, rtol=1e-13)
+    ang = np.unwrap(np.arctan2(pf[:, 1], pf[:, 0]))
+    assert np.allclose(np.diff(ang), -np.deg2rad(15.0), atol=1e-12)
+    assert np.allclose(np.diff(pf[:, 2]), pitch / 24.0, rtol=1e-10)
+    # relaxation against the previous fit (:1035-1038): a second call moves half of the remaining way
+    rc, pitch2, radius2 = _call_update(oracle, pf, pitch, radius, waF, hub, [0, 0, 1], dpsi)
+    assert rc == 0
+    assert pitch2 == 0.5 * (2 * pitch) + 0.5 * pitch and radius2 == 0.5 * (2 * radius) + 0.5 * radius
+
+
+def test_pfwake_update_refuses_tilted_shaft(oracle):
+    """error stop "Prescribed far wake only implemented for shaft along Z-axis" (classdef.f90:1010-1012)."""
+    rng = np.random.default_rng(5)
+    hub = np.zeros(3)
+    waF = _helical_far_wake(rng, 5, hub)
+    pf = np.zeros((NPF, FW))
+    rc, _, _ = _call_update(oracle, pf, 0.0, 0.0, waF, hub, [0.0, 1e-3, 1.0], 0.25)
+    assert rc != 0 and not pf.any()
+
+
+def _with_prescribed_wake(gen):
+    def m(fx):
+        g = fx["geom"][0]
+        g["nNwake"] = 6                      # roll-up, far wake and truncation inside a short window
+        g["wakeTruncateNt"] = 10
+        g["prescWakeAfterTruncNt"] = 2       # prescWakeNt = 12: the helix is attached from step 13 on (:3013-3017, :4826)
+        g["prescWakeGenNt"] = gen            # 0: fitted to rows rowFar..nFwakeEnd; 2: to the last three rows (:5180-5184)
+    return m
+
+
+@pytest.mark.parametrize("fd,gen", [(3, 0), (3, 2), (1, 0), (5, 2)])
+def test_prescribed_wake_staged_orchestration_equals_inline_time_loop(oracle, fd, gen):
+    from tests.test_staged_hooks import _lib
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())      # 5 blades, axisymmetric: copy + rotate of :5203-5216
+    _with_prescribed_wake(gen)(fx)
+    fx["config"]["fdScheme"] = fd
+    plain = json.loads(json.dumps(fx))
+    plain["geom"][0]["prescWakeAfterTruncNt"] = 0
+    lib = _lib()
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    c = oracle.Case(plain) if (fd, gen) == (3, 0) else None   # the same case without the helix: one comparison is enough
+    b.init_rotors()
+    h = lib.case_cpu_staged_hooks_install(b.h, b.nr)
+    assert h
+    runs = [x for x in (a, b, c) if x is not None]
+    for x in runs:
+        x.init()
+    assert a.rotor(0).nFwake == 4
+    differs = False
+    for it in range(18):
+        for x in runs:
+            x.step()
+        assert np.array_equal(a.force_nondim(0), b.force_nondim(0)), (fd, it + 1)
+        assert a.pairs_last_step == b.pairs_last_step
+        if c is None:
+            continue
+        if it + 1 <= 13:   # attached at the end of step 13 (iter > prescWakeNt = 12): first felt by the RHS of step 14
+            assert np.array_equal(a.force_nondim(0), c.force_nondim(0)), (fd, it + 1)
+        else:
+            differs = differs or not np.array_equal(a.force_nondim(0), c.force_nondim(0))
+    assert differs or c is None                                               # the 240 filaments per blade are live sources
+    ra, rb = a.rotor(0), b.rotor(0)
+    two_pi_5 = 2.0 * np.pi / 5
+    for ib in range(ra.nb):
+        for pred in (False, True):
+            assert np.array_equal(ra.wapF(ib, pred), rb.wapF(ib, pred)), (fd, "wapF", ib, pred)
+            assert np.array_equal(ra.waF(ib, pred), rb.waF(ib, pred))
+            assert np.array_equal(ra.waN(ib, pred), rb.waN(ib, pred))
+        w = ra.wapF(ib)
+        # one strength for the whole helix (the last far filament's at the time of the update; the roll-up / shiftFwake that
+        # end the step have moved the far wake on since)
+        assert np.all(np.abs(w[:, 12]) > 0) and np.all(w[:, 12] == w[0, 12]) and np.all(w[:, 9] == w[0, 9])
+        assert np.array_equal(w[1:, 3:6], w[:-1, 0:3])
+        if ib > 0:                                                        # blades 2..nb: rotated copies of blade 1's
+            w0 = ra.wapF(0)
+            a0 = np.arctan2(w0[:, 1], w0[:, 0])
+            ai = np.arctan2(w[:, 1], w[:, 0])
+            d = np.angle(np.exp(1j * (ai - a0 - two_pi_5 * ib)))
+            assert np.max(np.abs(d)) < 1e-12 and np.allclose(w[:, 2], w0[:, 2], rtol=0, atol=1e-13)
+    lib.case_gpu_hooks_free(h)

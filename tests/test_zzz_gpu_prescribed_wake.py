@@ -1,0 +1,80 @@
+"""Prescribed far wake (classdef.f90:4826-4828, :5170-5218, :998-1066) with the wake resident on the device: the 240 helix
+filaments per blade are sources of every sweep (vlc_rotor_put_pfwake, the abs(gam) > eps rule of classdef.f90:1471-1476),
+their generator stays on the host (tests/native/case_gpu_hooks.c: g_convect = vlc_rotor_convectwake, vlc_rotor_get_fwake,
+rotor%updatePrescribedWake, vlc_rotor_put_pfwake -- the C twin of fortran/libGPU.f90: gpu_convect).  Against the CPU driver
+(oracle; PARITY UNPINNED for this feature: no shipped case enables it, tests/test_prescribed_wake.py) over a window in which
+the helix is attached and felt.  Runs last (file name): written after the round's GPU minutes were spent."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests.test_prescribed_wake import _with_prescribed_wake
+from tests.test_zz_gpu_cp_stage import TOL_HISTORY, _cp_hooks, _step, cctx  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.mark.parametrize("gen,cp", [(0, True), (2, False)])
+def test_prescribed_wake_resident_vs_cpu_driver(cctx, oracle, gen, cp):  # noqa: F811
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())          # 5 blades, axisymmetric
+    _with_prescribed_wake(gen)(fx)                                       # prescWakeNt = 12
+    fx["config"]["rotorForcePlot"] = 1
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    if cp:
+        lib, h = _cp_hooks(b, cctx, True)
+    else:
+        from tests.test_gpu_resident import _resident_hooks
+        lib, h = _resident_hooks(b, cctx)
+    a.init()
+    b.init()
+    worst = [0.0, 0.0]
+    for it in range(20):
+        a.step()
+        _step(b, lib, h, cctx, it + 1)
+        fa, fb = a.force_nondim(0), b.force_nondim(0)
+        ga, gb = a.rotor(0).vec(0), b.rotor(0).vec(0)
+        worst[0] = max(worst[0], abs(fb[0] / fa[0] - 1.0))
+        worst[1] = max(worst[1], float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+    ra, rb = a.rotor(0), b.rotor(0)
+    for ib in range(ra.nb):                                              # the host-side generator saw the device's far wake
+        wa, wb = ra.wapF(ib), rb.wapF(ib)
+        assert np.all(np.abs(wa[:, 12]) > 0)
+        assert np.max(np.abs(wb[:, :6] - wa[:, :6])) < 1e-9 * np.max(np.abs(wa[:, :6]))
+        assert np.max(np.abs(wb[:, 12] - wa[:, 12])) < 1e-9 * np.max(np.abs(wa[:, 12]))
+    print(f"elevateTest + prescribed far wake (prescWakeGenNt = {gen}), 20 steps, wake resident"
+          f"{', collocation-point stage on the device' if cp else ''}: max rel err CT {worst[0]:.3e}, gamVec {worst[1]:.3e}")
+    assert max(worst) < TOL_HISTORY, worst
+    lib.case_gpu_hooks_free(h)
+
+
+@pytest.mark.parametrize("predicted", [False, True])
+def test_prescribed_filaments_are_sources_of_vind_bywake(cctx, oracle, predicted):  # noqa: F811
+    """Per call: rotor%vind_bywake(P[, 'P']) with a live helix (classdef.f90:1471-1476, :1501-1507) against the oracle's
+    loop at the per-call bar (1e-12 of the velocity scale); without vlc_rotor_put_pfwake the difference is the helix's own
+    contribution, so the comparison is not vacuous."""
+    from tests.test_zz_gpu_cp_stage import TOL, _define, _developed
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    _with_prescribed_wake(0)(fx)
+    case = _developed(oracle, fx, 16)
+    rot = case.rotor(0)
+    assert np.all(np.abs(rot.wapF(0, predicted)[:, 12]) > 0)
+    _define(cctx, rot, 0)
+    if predicted:
+        for ib in range(rot.nb):
+            cctx.rotor_put_nwake(0, ib, rot.waN(ib, True), predicted=True)
+            cctx.rotor_put_fwake(0, ib, rot.waF(ib, True), predicted=True)
+    rng = np.random.default_rng(11)
+    P = np.concatenate([rng.uniform(-1.5, 1.5, (200, 3)) * np.max(np.abs(rot.wapF(0, predicted)[:, 0:2])),
+                        rot.wapF(0, predicted)[::7, 0:3],                 # on the helix's own nodes: the c2 <= eps^2 rule
+                        0.5 * (rot.wapF(2, predicted)[::9, 0:3] + rot.wapF(2, predicted)[::9, 3:6])])
+    ref = rot.vind_points(1, P, predicted)
+    without = cctx.rotor_vind_bywake(0, P, predicted)
+    for ib in range(rot.nb):
+        cctx.rotor_put_pfwake(0, ib, rot.wapF(ib, predicted), predicted=predicted)
+    got = cctx.rotor_vind_bywake(0, P, predicted)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(got - ref)) < TOL * scale, np.max(np.abs(got - ref)) / scale
+    assert np.max(np.abs(without - ref)) > 1e-6 * scale
