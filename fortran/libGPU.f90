@@ -234,6 +234,21 @@ module libGPU
       integer(c_int), value :: ir, ib, predicted
       real(c_double), intent(out) :: waF(*)
     end function
+    integer(c_int) function vlc_rotor_updatePrescribedWake(c, ir, deltaPsi, prescWakeGenNt, predicted) &
+      & bind(C, name='vlc_rotor_updatePrescribedWake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), value :: deltaPsi
+      integer(c_int), value :: prescWakeGenNt, predicted
+    end function
+    integer(c_int) function vlc_rotor_get_pfwake(c, ir, ib, predicted, wapF, helix) bind(C, name='vlc_rotor_get_pfwake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(out) :: wapF(*)
+      real(c_double), intent(out) :: helix(*)
+    end function
     integer(c_int) function vlc_rotor_wakevel_copy(c, ir, dst, src) bind(C, name='vlc_rotor_wakevel_copy')
       import :: c_int, c_ptr
       type(c_ptr), value :: c
@@ -532,39 +547,17 @@ contains
   end subroutine gpu_wake_prestep
 
   subroutine gpu_convect(rotor, ir, iter, dt, p)
-    !! rotor%convectwake(iter, dt, wakeType) (classdef.f90:4786-4830) on the device records.  Its last statement, the
-    !! prescribed far wake (:4826-4828, rotor%updatePrescribedWake :5170-5218), keeps its generator on the host: the far
-    !! rows come down (104 bytes each), the 240 helix filaments per blade go up -- O(nFwake + 240) per blade per stage.
-    !! rowFar is the driver's own counter (main.f90:412-417); nFwakeEnd never changes after init.
-    type(rotor_class), intent(inout) :: rotor
+    !! rotor%convectwake(iter, dt, wakeType) (classdef.f90:4786-4830) on the device records, its last statement included:
+    !! the prescribed far wake (:4826-4828, rotor%updatePrescribedWake :5170-5218) is regenerated on the device from the
+    !! device's own far rows; gpu_download_wake brings the helix back for wake plots.
+    type(rotor_class), intent(in) :: rotor
     integer, intent(in) :: ir, iter
     real(dp), intent(in) :: dt
     integer(c_int), intent(in) :: p
-    integer :: ib
-    real(c_double), allocatable :: buf(:)
     call check(vlc_rotor_convectwake(ctx, ir - 1, dt, p))
-    if (.not. (rotor%prescWakeNt > 0 .and. iter > rotor%prescWakeNt)) return
-    allocate (buf(13*rotor%nFwake))
-    do ib = 1, rotor%nb
-      call check(vlc_rotor_get_fwake(ctx, ir - 1, ib - 1, p, buf))
-      if (p == 1) then
-        rotor%blade(ib)%waFPredicted = transfer(buf, rotor%blade(ib)%waFPredicted)
-      else
-        rotor%blade(ib)%waF = transfer(buf, rotor%blade(ib)%waF)
-      endif
-    enddo
-    deallocate (buf)
-    call rotor%updatePrescribedWake(dt, merge('P', 'C', p == 1))
-    allocate (buf(13*240))
-    do ib = 1, rotor%nb
-      if (p == 1) then
-        buf = transfer(rotor%blade(ib)%wapFPredicted%waF, buf)
-      else
-        buf = transfer(rotor%blade(ib)%wapF%waF, buf)
-      endif
-      call check(vlc_rotor_put_pfwake(ctx, ir - 1, ib - 1, p, buf))
-    enddo
-    deallocate (buf)
+    if (rotor%prescWakeNt > 0 .and. iter > rotor%prescWakeNt) then
+      call check(vlc_rotor_updatePrescribedWake(ctx, ir - 1, rotor%omegaSlow*dt, int(rotor%prescWakeGenNt, c_int), p))
+    endif
   end subroutine gpu_convect
 
   ! One MPI rank per GPU: replace each `vlc_wake_sweep(ctx, p, addInit)` below by
@@ -576,7 +569,7 @@ contains
     !! Replaces main.f90:800-1440: the wake sweeps, the fdScheme switch (0 explicit Euler :846-859, 1 predictor-
     !! corrector :861-949, 2 explicit Adams-Bashforth :951-1000, 3 Adams-Bashforth / Adams-Moulton :1002-1115, 4 and 5 the
     !! same of third and fourth order :1117-1404) with its velocity bookkeeping, strain_wake, rollup, assignshed('TE').
-    type(rotor_class), intent(inout) :: rotor(:)   ! inout: the prescribed far wake, when used, is regenerated on the host
+    type(rotor_class), intent(in) :: rotor(:)
     integer, intent(in) :: iter, fdScheme, wakeStrain, initWakeVelNt
     real(dp), intent(in) :: dt
     integer :: ir, start
@@ -784,6 +777,7 @@ contains
     type(rotor_class), intent(inout) :: rotor(:)
     integer :: ir, ib
     real(c_double), allocatable :: buf(:)
+    real(c_double) :: helix(2)
     do ir = 1, size(rotor)
       do ib = 1, rotor(ir)%nb
         if (rotor(ir)%nNwake > 0) then
@@ -796,6 +790,15 @@ contains
           allocate (buf(13*size(rotor(ir)%blade(ib)%waF)))
           call check(vlc_rotor_get_fwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
           rotor(ir)%blade(ib)%waF = transfer(buf, rotor(ir)%blade(ib)%waF)
+          deallocate (buf)
+        endif
+        if (rotor(ir)%prescWakeNt > 0) then   ! records and fit parameters of the prescribed far wake made on the device
+          allocate (buf(13*240))
+          call check(vlc_rotor_get_pfwake(ctx, ir - 1, ib - 1, 0_c_int, buf, helix))
+          rotor(ir)%blade(ib)%wapF%waF = transfer(buf, rotor(ir)%blade(ib)%wapF%waF)
+          rotor(ir)%blade(ib)%wapF%helixPitch = helix(1)
+          rotor(ir)%blade(ib)%wapF%helixRadius = helix(2)
+          rotor(ir)%blade(ib)%wapF%isPresent = .true.
           deallocate (buf)
         endif
       enddo

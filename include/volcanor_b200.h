@@ -183,6 +183,17 @@ int vlc_rotor_wake_to_predicted(vlc_ctx* ctx, int ir);
  * corners (blade_convectwake :1515-1575, the predictor's loop quirk included), re-stitch (wake_continuity
  * :1609-1702), axisymmetric copy + rotate of blades 2..nb (:4801-4823). */
 int vlc_rotor_convectwake(vlc_ctx* ctx, int ir, double dt, int predicted);
+/* = rotor%updatePrescribedWake(dt, 'C' | 'P') classdef.f90:5170-5218, the statement that ends rotor%convectwake when
+ * prescWakeNt > 0 and iter > prescWakeNt (:4826-4828): per convected blade pFwake_update (:998-1066) -- a helix of 240
+ * filaments fitted to the far-wake rows rowStart..nFwake of the device's waF / waFPredicted (rowStart = rowFar when
+ * prescWakeGenNt == 0, else nFwake - prescWakeGenNt), relaxed against the blade's previous fit, which the device keeps
+ * per record set -- then the axisymmetric copies of blade 1's (pFwake_rot_wake_axis :1068-1086).  deltaPsi = omegaSlow*dt.
+ * From then on the helix is a source of the sweeps of that record set.  VLC_ERR_ARG when the shaft is not along z (the
+ * reference's error stop), VLC_ERR_STATE without a far-wake row to fit. */
+int vlc_rotor_updatePrescribedWake(vlc_ctx* ctx, int ir, double deltaPsi, int prescWakeGenNt, int predicted);
+/* Device -> host copy of a blade's prescribed wake records (wake plots, libPostprocess.f90:266-284; restart files);
+ * helix, when not NULL, receives (helixPitch, helixRadius) of that blade and record set. */
+int vlc_rotor_get_pfwake(vlc_ctx* ctx, int ir, int ib, int predicted, double* wapF /* 240 x 13 */, double* helix /* 2 or NULL */);
 /* = rotor%rollup() classdef.f90:4515-4605 (shiftFwake :4500-4513 when the far wake is full, then shiftwake :4481-4498);
  * the driver calls it when rowNear == 1 (main.f90:1424-1425). */
 int vlc_rotor_rollup(vlc_ctx* ctx, int ir);

@@ -130,6 +130,11 @@ class Rotor {
     if (wakeType != 'C' && wakeType != 'P') throw Error(VLC_ERR_ARG, "ERROR: Wrong character flag for convectwake()");
     c_.check(vlc_rotor_convectwake(c_.handle(), ir_, dt, wakeType == 'P'));
   }
+  // rotor%updatePrescribedWake(dt, wakeType) classdef.f90:5170-5218; deltaPsi = omegaSlow*dt
+  void updatePrescribedWake(double deltaPsi, int prescWakeGenNt, char wakeType) {
+    if (wakeType != 'C' && wakeType != 'P') throw Error(VLC_ERR_ARG, "ERROR: Wrong character flag for updatePrescribedWake()");
+    c_.check(vlc_rotor_updatePrescribedWake(c_.handle(), ir_, deltaPsi, prescWakeGenNt, wakeType == 'P'));
+  }
   void rollup() { c_.check(vlc_rotor_rollup(c_.handle(), ir_)); }
   void wakevel_op(int op) { c_.check(vlc_rotor_wakevel_op(c_.handle(), ir_, op)); }
   void wakevel_copy(int dst, int src) { c_.check(vlc_rotor_wakevel_copy(c_.handle(), ir_, dst, src)); }
@@ -138,6 +143,9 @@ class Rotor {
   }
   void get_nwake(int ib, double* waN, bool predicted = false) { c_.check(vlc_rotor_get_nwake(c_.handle(), ir_, ib, predicted, waN)); }
   void get_fwake(int ib, double* waF, bool predicted = false) { c_.check(vlc_rotor_get_fwake(c_.handle(), ir_, ib, predicted, waF)); }
+  void get_pfwake(int ib, double* wapF, double* helix = nullptr, bool predicted = false) {
+    c_.check(vlc_rotor_get_pfwake(c_.handle(), ir_, ib, predicted, wapF, helix));
+  }
   // tier 2c: the collocation-point stage on the device copies of the wing records (main.f90:548-670)
   void calc_RHS(double* velCP_out = nullptr, double* RHS_out = nullptr) {
     c_.check(vlc_rotor_calc_RHS(c_.handle(), ir_, velCP_out, RHS_out));

@@ -75,6 +75,9 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_rotor_convectwake": (None, [_vp, i32, d, C.c_char]),
         "orc_pfwake_update": (i32, [_vp, _vp, _vp, _vp, i32, _vp, _vp, d]),
         "orc_rotor_updatePrescribedWake": (i32, [_vp, d, C.c_char]),
+        "orc_rotor_get_pfHelix": (None, [_vp, i32, i32, _vp]),
+        "orc_rotor_set_pfHelix": (None, [_vp, i32, i32, _vp]),
+        "orc_rotor_get_presc": (None, [_vp, _vp]),
         "orc_rotor_assignshed": (None, [_vp, C.c_char_p]),
         "orc_rotor_age_wake": (None, [_vp, d]),
         "orc_rotor_dissipate_wake": (None, [_vp, d, d]),
@@ -211,6 +214,12 @@ class Rotor:
         self.lib.orc_rotor_dims(self.h, d)
         return dict(zip(["nb", "nc", "ns", "nNwake", "nFwake", "rowNear", "rowFar", "nbConvect", "nNwakeEnd",
                          "nFwakeEnd"], list(d)))
+
+    def presc(self):
+        """(prescWakeNt, prescWakeAfterTruncNt, prescWakeGenNt) in time steps (classdef.f90:400, :3013-3017)."""
+        d = (C.c_int * 3)()
+        self.lib.orc_rotor_get_presc(self.h, d)
+        return tuple(d)
 
     def params(self) -> dict:
         """What the wake mutators read from rotor_class (orc_rotor_get_params)."""

@@ -1071,6 +1071,19 @@ double *orc_rotor_waN(orc_rotor_t *r, int ib, int predicted) {
 double *orc_rotor_waF(orc_rotor_t *r, int ib, int predicted) {
   return (double *)(predicted ? r->blade[ib].waFPredicted : r->blade[ib].waF);
 }
+void orc_rotor_get_presc(const orc_rotor_t *r, int out[3]) {
+  out[0] = r->prescWakeNt;
+  out[1] = r->prescWakeAfterTruncNt;
+  out[2] = r->prescWakeGenNt;
+}
+void orc_rotor_set_pfHelix(orc_rotor_t *r, int ib, int predicted, const double in[2]) {
+  r->blade[ib].pfHelixPitch[predicted ? 1 : 0] = in[0];
+  r->blade[ib].pfHelixRadius[predicted ? 1 : 0] = in[1];
+}
+void orc_rotor_get_pfHelix(const orc_rotor_t *r, int ib, int predicted, double out[2]) {
+  out[0] = r->blade[ib].pfHelixPitch[predicted ? 1 : 0];
+  out[1] = r->blade[ib].pfHelixRadius[predicted ? 1 : 0];
+}
 double *orc_rotor_wapF(orc_rotor_t *r, int ib, int predicted) {
   return (double *)(predicted ? r->blade[ib].wapFPredicted : r->blade[ib].wapF);
 }

@@ -130,6 +130,9 @@ void orc_vf_vind(const orc_vf_t *f, const double P[3], double v[3]);
 int orc_pfwake_update(orc_fwake_t *pf, double *helixPitch, double *helixRadius, const orc_fwake_t *waF, int nFwake,
                       const double hubCoords[3], const double shaftAxis[3], double deltaPsi);
 int orc_rotor_updatePrescribedWake(orc_rotor_t *r, double dt, char wakeType);
+void orc_rotor_get_presc(const orc_rotor_t *r, int out[3]); /* prescWakeNt, prescWakeAfterTruncNt, prescWakeGenNt */
+void orc_rotor_set_pfHelix(orc_rotor_t *r, int ib, int predicted, const double in[2]);
+void orc_rotor_get_pfHelix(const orc_rotor_t *r, int ib, int predicted, double out[2]); /* helixPitch, helixRadius */
 void orc_vr_vind(const orc_vr_t *r, const double P[3], double v[3]);
 
 /* ---- source loops: classdef.f90:1342-1513, 4424-4479 ---- */

@@ -189,18 +189,13 @@ static int g_age(gpu_user_t *u, int ir, double dt, double om) { return vlc_rotor
 static int g_dissipate(gpu_user_t *u, int ir, double dt, double nu) { return vlc_rotor_dissipate_wake(u->ctx, ir, dt, nu); }
 static int g_strain(gpu_user_t *u, int ir) { return vlc_rotor_strain_wake(u->ctx, ir); }
 static int g_to_pred(gpu_user_t *u, int ir) { return vlc_rotor_wake_to_predicted(u->ctx, ir); }
-/* convectwake on the device; the prescribed far wake (classdef.f90:4826-4828), when the case uses one, keeps its generator on
- * the host: far rows down, rotor%updatePrescribedWake, the 240 helix filaments up */
+/* convectwake on the device, its last statement included: the prescribed far wake (classdef.f90:4826-4828), when the case
+ * uses one, is regenerated from the device's own far rows (vlc_rotor_updatePrescribedWake) -- nothing crosses the bus */
 static int g_convect(gpu_user_t *u, int ir, int iter, double dt, int p) {
   int rc = vlc_rotor_convectwake(u->ctx, ir, dt, p);
   orc_rotor_t *r = orc_case_rotor(u->cas, ir);
   if (rc || !(r->prescWakeNt > 0 && iter > r->prescWakeNt)) return rc;
-  for (int ib = 0; ib < r->nb; ++ib)
-    if ((rc = vlc_rotor_get_fwake(u->ctx, ir, ib, p, orc_rotor_waF(r, ib, p)))) return rc;
-  if (orc_rotor_updatePrescribedWake(r, dt, p ? 'P' : 'C')) return VLC_ERR_STATE;
-  for (int ib = 0; ib < r->nb; ++ib)
-    if ((rc = vlc_rotor_put_pfwake(u->ctx, ir, ib, p, orc_rotor_wapF(r, ib, p)))) return rc;
-  return 0;
+  return vlc_rotor_updatePrescribedWake(u->ctx, ir, r->omegaSlow * dt, r->prescWakeGenNt, p);
 }
 static int g_rollup(gpu_user_t *u, int ir) { return vlc_rotor_rollup(u->ctx, ir); }
 static int g_sweep(gpu_user_t *u, int p, int addInit) { return vlc_wake_sweep(u->ctx, p, addInit); }
@@ -756,6 +751,7 @@ int case_gpu_hooks_download_wake(void *handle) {
       for (int s = 0; s < 2; ++s) {
         if (r->nNwake > 0) CK(vlc_rotor_get_nwake(u->ctx, jr, ib, s, orc_rotor_waN(r, ib, s)));
         if (r->nFwake > 0) CK(vlc_rotor_get_fwake(u->ctx, jr, ib, s, orc_rotor_waF(r, ib, s)));
+        if (r->prescWakeNt > 0) CK(vlc_rotor_get_pfwake(u->ctx, jr, ib, s, orc_rotor_wapF(r, ib, s), NULL));
       }
       for (int w = 0; w < 4; ++w)
         CK(vlc_rotor_get_wakevel(u->ctx, jr, ib, w, r->nNwake > 0 ? orc_rotor_vel(r, ib, w) : NULL,

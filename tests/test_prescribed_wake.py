@@ -171,3 +171,64 @@ def test_prescribed_wake_staged_orchestration_equals_inline_time_loop(oracle, fd
             d = np.angle(np.exp(1j * (ai - a0 - two_pi_5 * ib)))
             assert np.max(np.abs(d)) < 1e-12 and np.allclose(w[:, 2], w0[:, 2], rtol=0, atol=1e-13)
     lib.case_gpu_hooks_free(h)
+
+
+def _pf_host():
+    import subprocess
+    here = Path(__file__).resolve().parent / "native"
+    so = here / "libpfwake_host.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(here)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    vp = C.c_void_p
+    lib.pf_host_update.restype = C.c_int
+    lib.pf_host_update.argtypes = [C.c_int] * 6 + [C.c_double] + [vp] * 6
+    return lib
+
+
+@pytest.mark.parametrize("gen,axisym", [(0, 1), (2, 1), (3, 0)])
+def test_product_generator_host_build_is_bit_identical_to_the_oracle(oracle, gen, axisym):
+    """volcanor_b200/csrc/pfwake.cuh (what pf_fit_kernel / pf_helix_kernel run per thread) compiled with g++ and driven in
+    the kernels' loops, against orc_rotor_updatePrescribedWake on a developed five-blade case with the helix live: records
+    of every blade and both fit parameters BIT-IDENTICAL, for the current and the predicted record set, over three
+    successive updates (the relaxation carries state).  On the device only cos / sin / atan2 may differ (<= 2 ulp)."""
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    _with_prescribed_wake(gen)(fx)
+    fx["geom"][0]["axisymmetrySwitch"] = axisym
+    case = oracle.Case(fx)
+    case.init()
+    for _ in range(15):
+        case.step()
+    rot = case.rotor(0)
+    p, d = rot.params(), rot.dims()
+    nb, nF = rot.nb, rot.nFwake
+    lib, olib = _pf_host(), oracle.load()
+    two_pi = 2.0 * (np.arctan(1.0) * 4.0)
+    T = np.zeros((nb, 9))
+    rotate = np.zeros(nb, dtype=np.int32)
+    for ib in range(1, nb):
+        off = two_pi / nb * ib
+        rotate[ib] = abs(off) > np.finfo(float).eps
+        olib.orc_getTransformAxis.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
+        olib.orc_getTransformAxis(off, p["shaftAxis"].ctypes.data, T[ib].ctypes.data)
+    hub = np.ascontiguousarray(p["hubCoords"])
+    for pred in (False, True):
+        helix = np.zeros((nb, 2))
+        for ib in range(nb):
+            olib.orc_rotor_get_pfHelix(rot.h, ib, int(pred), helix[ib].ctypes.data)
+        wapF = np.stack([rot.wapF(ib, pred).copy() for ib in range(nb)])
+        for rep in range(3):
+            waF = np.stack([rot.waF(ib, pred).copy() for ib in range(nb)])
+            step_dt = 0.0137 * (rep + 1)
+            rc = lib.pf_host_update(nb, p["nbConvect"], axisym, nF, d["rowFar"], rot.presc()[2], p["omegaSlow"] * step_dt,
+                                    hub.ctypes.data, T.ctypes.data, rotate.ctypes.data, waF.ctypes.data, wapF.ctypes.data,
+                                    helix.ctypes.data)
+            assert rc == 0
+            assert olib.orc_rotor_updatePrescribedWake(rot.h, step_dt, b"P" if pred else b"C") == 0
+            for ib in range(nb):
+                ref = np.zeros(2)
+                olib.orc_rotor_get_pfHelix(rot.h, ib, int(pred), ref.ctypes.data)
+                assert np.array_equal(rot.wapF(ib, pred), wapF[ib]), (gen, axisym, pred, rep, ib)
+                if ib < p["nbConvect"] or axisym:
+                    assert np.array_equal(ref, helix[ib]), (gen, axisym, pred, rep, ib)
+            assert np.all(np.abs(wapF[:, :, 12]) > 0)

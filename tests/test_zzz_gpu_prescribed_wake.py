@@ -1,7 +1,7 @@
 """Prescribed far wake (classdef.f90:4826-4828, :5170-5218, :998-1066) with the wake resident on the device: the 240 helix
-filaments per blade are sources of every sweep (vlc_rotor_put_pfwake, the abs(gam) > eps rule of classdef.f90:1471-1476),
-their generator stays on the host (tests/native/case_gpu_hooks.c: g_convect = vlc_rotor_convectwake, vlc_rotor_get_fwake,
-rotor%updatePrescribedWake, vlc_rotor_put_pfwake -- the C twin of fortran/libGPU.f90: gpu_convect).  Against the CPU driver
+filaments per blade are sources of every sweep (the abs(gam) > eps rule of classdef.f90:1471-1476), uploaded
+(vlc_rotor_put_pfwake) or made on the device from its own far rows (vlc_rotor_updatePrescribedWake: pf_fit_kernel +
+pf_helix_kernel; tests/native/case_gpu_hooks.c: g_convect is the C twin of fortran/libGPU.f90: gpu_convect).  Against the CPU driver
 (oracle; PARITY UNPINNED for this feature: no shipped case enables it, tests/test_prescribed_wake.py) over a window in which
 the helix is attached and felt.  Runs last (file name): written after the round's GPU minutes were spent."""
 import json
@@ -38,8 +38,9 @@ def test_prescribed_wake_resident_vs_cpu_driver(cctx, oracle, gen, cp):  # noqa:
         ga, gb = a.rotor(0).vec(0), b.rotor(0).vec(0)
         worst[0] = max(worst[0], abs(fb[0] / fa[0] - 1.0))
         worst[1] = max(worst[1], float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+    assert lib.case_gpu_hooks_download_wake(h) == 0                      # the helix made on the device, back in b's records
     ra, rb = a.rotor(0), b.rotor(0)
-    for ib in range(ra.nb):                                              # the host-side generator saw the device's far wake
+    for ib in range(ra.nb):
         wa, wb = ra.wapF(ib), rb.wapF(ib)
         assert np.all(np.abs(wa[:, 12]) > 0)
         assert np.max(np.abs(wb[:, :6] - wa[:, :6])) < 1e-9 * np.max(np.abs(wa[:, :6]))
@@ -78,3 +79,59 @@ def test_prescribed_filaments_are_sources_of_vind_bywake(cctx, oracle, predicted
     scale = np.max(np.abs(ref))
     assert np.max(np.abs(got - ref)) < TOL * scale, np.max(np.abs(got - ref)) / scale
     assert np.max(np.abs(without - ref)) > 1e-6 * scale
+
+
+@pytest.mark.parametrize("gen,axisym", [(0, 1), (2, 0)])
+def test_update_prescribed_wake_on_the_device_vs_oracle(cctx, oracle, gen, axisym):  # noqa: F811
+    """vlc_rotor_updatePrescribedWake alone, on the oracle's far wake: the fit parameters (sums, products, sqrt: no
+    transcendental) BIT-IDENTICAL, the end points within 1e-13 of the helix radius (cos / sin / atan2 of CUDA vs libm), gam
+    and rVc bit-identical; two successive updates from a zero fit (the relaxation carries state), both record sets."""
+    import ctypes as C
+    from tests.test_zz_gpu_cp_stage import _define, _developed
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    _with_prescribed_wake(gen)(fx)
+    fx["geom"][0]["axisymmetrySwitch"] = axisym
+    case = _developed(oracle, fx, 15)
+    rot = case.rotor(0)
+    p = rot.params()
+    olib = oracle.load()
+    _define(cctx, rot, 0)
+    cctx.rotor_set_frame(0, p["shaftAxis"], p["hubCoords"])
+    for ib in range(rot.nb):
+        cctx.rotor_put_nwake(0, ib, rot.waN(ib, True), predicted=True)
+        cctx.rotor_put_fwake(0, ib, rot.waF(ib, True), predicted=True)
+    zero = np.zeros(2)
+    for pred in (False, True):
+        for ib in range(rot.nb):
+            olib.orc_rotor_set_pfHelix(rot.h, ib, int(pred), zero.ctypes.data)
+        for rep in range(2):
+            dt = 0.0137 * (rep + 1)
+            assert olib.orc_rotor_updatePrescribedWake(rot.h, dt, b"P" if pred else b"C") == 0
+            cctx.rotor_updatePrescribedWake(0, p["omegaSlow"] * dt, gen, "P" if pred else "C")
+            for ib in range(rot.nb):
+                w, hx = cctx.rotor_get_pfwake(0, ib, pred)
+                ref, hr = rot.wapF(ib, pred), np.zeros(2)
+                olib.orc_rotor_get_pfHelix(rot.h, ib, int(pred), hr.ctypes.data)
+                assert np.array_equal(hx, hr), (pred, rep, ib, hx, hr)
+                assert np.array_equal(w[:, 9], ref[:, 9]) and np.array_equal(w[:, 12], ref[:, 12])
+                assert np.all(np.abs(w[:, 12]) > 0)
+                scale = abs(hr[1]) + 10 * abs(hr[0]) + np.max(np.abs(p["hubCoords"]))
+                assert np.max(np.abs(w[:, 0:6] - ref[:, 0:6])) < 1e-13 * scale, (pred, rep, ib)
+
+
+def test_update_prescribed_wake_error_behaviour(cctx):  # noqa: F811
+    """error stop "Prescribed far wake only implemented for shaft along Z-axis" (classdef.f90:1010-1012) -> VLC_ERR_ARG with
+    the message; no far wake / no row to fit -> VLC_ERR_STATE."""
+    cctx.rotor_define(0, 2, 2, 3, 4, 0, 1)
+    with pytest.raises(Exception, match="far wake"):
+        cctx.rotor_updatePrescribedWake(0, 0.1, 0, "C")
+    cctx.rotor_define(0, 2, 2, 3, 4, 5, 1)
+    cctx.rotor_set_frame(0, [0.0, 1e-3, 1.0], [0.0, 0.0, 0.0])
+    with pytest.raises(Exception, match="shaft along Z-axis"):
+        cctx.rotor_updatePrescribedWake(0, 0.1, 0, "C")
+    cctx.rotor_set_frame(0, [0.0, 0.0, 1.0], [0.0, 0.0, 0.0])
+    with pytest.raises(Exception, match="no far-wake row"):       # rowFar = nFwake + 1 after vlc_rotor_define
+        cctx.rotor_updatePrescribedWake(0, 0.1, 0, "C")
+    with pytest.raises(Exception, match="no far-wake row"):
+        cctx.rotor_updatePrescribedWake(0, 0.1, 5, "C")           # rowStart = 0
+    cctx.rotor_updatePrescribedWake(0, 0.1, 2, "C")               # rows 3..5 of an all-zero far wake: a degenerate helix, no error

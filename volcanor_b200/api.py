@@ -123,6 +123,8 @@ def load_library() -> C.CDLL:
         "vlc_rotor_strain_wake": (i32, [_vp, i32]),
         "vlc_rotor_wake_to_predicted": (i32, [_vp, i32]),
         "vlc_rotor_convectwake": (i32, [_vp, i32, C.c_double, i32]),
+        "vlc_rotor_updatePrescribedWake": (i32, [_vp, i32, C.c_double, i32, i32]),
+        "vlc_rotor_get_pfwake": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_rotor_rollup": (i32, [_vp, i32]),
         "vlc_wake_sweep": (i32, [_vp, i32, i32]),
         "vlc_wake_sweep_count": (i32, [_vp, C.POINTER(i64)]),
@@ -412,6 +414,16 @@ class Context:
 
     def rotor_convectwake(self, ir, dt, wakeType: str = "C"):
         self._ck(self.lib.vlc_rotor_convectwake(self.h, ir, dt, {"C": 0, "P": 1}[wakeType]))
+
+    def rotor_updatePrescribedWake(self, ir, deltaPsi, prescWakeGenNt=0, wakeType: str = "C"):
+        """rotor%updatePrescribedWake(dt, wakeType) (classdef.f90:5170-5218) on the device records; deltaPsi = omegaSlow*dt."""
+        self._ck(self.lib.vlc_rotor_updatePrescribedWake(self.h, ir, deltaPsi, prescWakeGenNt, {"C": 0, "P": 1}[wakeType]))
+
+    def rotor_get_pfwake(self, ir, ib, predicted=False):
+        """-> (wapF (240, 13), (helixPitch, helixRadius)) of one blade."""
+        w, hx = np.empty((240, 13)), np.empty(2)
+        self._ck(self.lib.vlc_rotor_get_pfwake(self.h, ir, ib, int(predicted), _ptr(w), _ptr(hx)))
+        return w, hx
 
     def rotor_rollup(self, ir):
         self._ck(self.lib.vlc_rotor_rollup(self.h, ir))

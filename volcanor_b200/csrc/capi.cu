@@ -71,6 +71,7 @@ struct Rotor {
   // reference-layout copies (all blades, blade-major)
   DevBuf wiP, waN[2], waF[2], wapF[2];
   bool have_pf[2] = {false, false};
+  DevBuf pfHelix[2], pfFits;  // prescribed far wake made on the device: (helixPitch, helixRadius) per blade and set; fit scratch
   // packed: [wing | wake] per set (C, P), and bound-vortex set
   SourceSet comb[2];
   long long wing_pad[2] = {0, 0};  // padded wing segment length inside comb[s]
@@ -890,6 +891,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
       release(r.waN[s]);
       release(r.waF[s]);
       release(r.wapF[s]);
+      release(r.pfHelix[s]);
       release(r.comb[s].rec);
       release(r.comb[s].lat);
       release(r.comb[s].lat2);
@@ -906,6 +908,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     }
     release(r.waN_alt);
     release(r.order2_tmp);
+    release(r.pfFits);
     if (r.d_axi) cudaFree(r.d_axi);
     release(r.bound.rec);
     release(r.chord.rec);
@@ -1160,7 +1163,10 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     CUDA_OK(c, cudaMemsetAsync(r.waN[s].p, 0, r.waN[s].cap * sizeof(double), c->stream));
     CUDA_OK(c, cudaMemsetAsync(r.waF[s].p, 0, r.waF[s].cap * sizeof(double), c->stream));
     CUDA_OK(c, cudaMemsetAsync(r.wapF[s].p, 0, r.wapF[s].cap * sizeof(double), c->stream));
+    if ((rc = reserve(c, r.pfHelix[s], (size_t)2 * nb))) return rc;  // helixPitch = helixRadius = 0 (classdef.f90:228-229)
+    CUDA_OK(c, cudaMemsetAsync(r.pfHelix[s].p, 0, r.pfHelix[s].cap * sizeof(double), c->stream));
   }
+  if ((rc = reserve(c, r.pfFits, (size_t)nb * (sizeof(vlc::pf::Fit) / sizeof(double))))) return rc;
   return VLC_OK;
 }
 
@@ -1614,6 +1620,23 @@ extern "C" int vlc_rotor_wake_to_predicted(vlc_ctx* c, int ir) {
   return VLC_OK;
 }
 
+namespace {
+// Tmat(ib) = getTransformAxis(twoPi/nb*(ib-1), shaftAxis) of blades 2..nb (classdef.f90:4803-4805, :5204-5205) on the device
+int upload_blade_rotations(vlc_ctx* c, Rotor& r) {
+  const double twoPi = 2.0 * (std::atan(1.0) * 4.0);
+  r.h_axi.resize(r.nb);
+  for (int ib = 2; ib <= r.nb; ++ib) {
+    const double bladeOffset = twoPi / r.nb * (ib - 1);
+    vlc::AxiT& t = r.h_axi[ib - 1];
+    t.rotate = std::fabs(bladeOffset) > 2.220446049250313e-16 ? 1 : 0;  // classdef.f90:1297
+    transform_axis(bladeOffset, r.shaftAxis, t.T);
+  }
+  if (!r.d_axi) CUDA_OK(c, cudaMalloc(&r.d_axi, sizeof(vlc::AxiT) * r.nb));
+  CUDA_OK(c, cudaMemcpyAsync(r.d_axi, r.h_axi.data(), sizeof(vlc::AxiT) * r.nb, cudaMemcpyHostToDevice, c->stream));
+  return VLC_OK;
+}
+}  // namespace
+
 extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicted) {
   CHECK_CTX(c);
   int rc = bind_device(c);
@@ -1644,16 +1667,7 @@ extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicte
     }
   }
   if (r->axisym == 1 && r->nb > 1) {  // classdef.f90:4801-4823
-    const double twoPi = 2.0 * (std::atan(1.0) * 4.0);
-    r->h_axi.resize(r->nb);
-    for (int ib = 2; ib <= r->nb; ++ib) {
-      const double bladeOffset = twoPi / r->nb * (ib - 1);
-      vlc::AxiT& t = r->h_axi[ib - 1];
-      t.rotate = std::fabs(bladeOffset) > 2.220446049250313e-16 ? 1 : 0;  // classdef.f90:1297
-      transform_axis(bladeOffset, r->shaftAxis, t.T);
-    }
-    if (!r->d_axi) CUDA_OK(c, cudaMalloc(&r->d_axi, sizeof(vlc::AxiT) * r->nb));
-    CUDA_OK(c, cudaMemcpyAsync(r->d_axi, r->h_axi.data(), sizeof(vlc::AxiT) * r->nb, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_blade_rotations(c, *r))) return rc;
     const long long n = (long long)(r->nb - 1) * (r->ns * nact + nfar);
     if (n > 0) {
       vlc::rec_axisym_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(r->nb, r->ns, r->nNwake, r->nFwake, r->rowNear, r->rowFar,
@@ -1664,6 +1678,49 @@ extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicte
   }
   CUDA_OK(c, cudaGetLastError());
   r->dirty[s] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_updatePrescribedWake(vlc_ctx* c, int ir, double deltaPsi, int prescWakeGenNt, int predicted) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (std::fabs(r->shaftAxis[0]) > 2.220446049250313e-16 || std::fabs(r->shaftAxis[1]) > 2.220446049250313e-16)
+    return fail(c, VLC_ERR_ARG, "Prescribed far wake only implemented for shaft along Z-axis");  // classdef.f90:1010-1012
+  if (r->nFwake <= 0 || prescWakeGenNt < 0) return fail(c, VLC_ERR_STATE, "prescribed far wake needs a far wake (nFwake > 0, prescWakeGenNt >= 0)");
+  const int rowStart = prescWakeGenNt == 0 ? r->rowFar : r->nFwake - prescWakeGenNt;  // :5180-5184 (nFwakeEnd = nFwake)
+  if (rowStart < 1 || rowStart > r->nFwake)
+    return fail(c, VLC_ERR_STATE, "prescribed far wake: no far-wake row to fit (rowFar / prescWakeGenNt outside 1..nFwake)");
+  const int s = predicted ? 1 : 0;
+  const bool copies = r->axisym == 1 && r->nb > 1;
+  if (copies && (rc = upload_blade_rotations(c, *r))) return rc;
+  vlc::pf::Fit* fits = reinterpret_cast<vlc::pf::Fit*>(r->pfFits.p);
+  vlc::pf_fit_kernel<<<blocks_for(r->nbConvect, 32), 32, 0, c->stream>>>(r->nbConvect, r->nFwake, rowStart, r->nFwake - rowStart + 1,
+                                                                         deltaPsi, r->hubCoords[2], r->waF[s].p, r->pfHelix[s].p, fits);
+  vlc::pf_helix_kernel<<<blocks_for((long long)r->nb * VLC_NPFWAKE, 128), 128, 0, c->stream>>>(
+      r->nb, r->nbConvect, r->axisym, fits, copies ? r->d_axi : nullptr, r->hubCoords[0], r->hubCoords[1], r->hubCoords[2],
+      r->wapF[s].p, r->pfHelix[s].p);
+  c->launches += 2;
+  CUDA_OK(c, cudaGetLastError());
+  r->have_pf[s] = true;
+  r->dirty[s] = true;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotor_get_pfwake(vlc_ctx* c, int ir, int ib, int predicted, double* wapF, double* helix) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !wapF) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  const int s = predicted ? 1 : 0;
+  const size_t per = (size_t)VLC_NPFWAKE * vlc::kFw;
+  CUDA_OK(c, cudaMemcpyAsync(wapF, r->wapF[s].p + per * ib, per * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (helix) CUDA_OK(c, cudaMemcpyAsync(helix, r->pfHelix[s].p + 2 * ib, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "pack.cuh"
+#include "pfwake.cuh"
 
 namespace vlc {
 
@@ -270,6 +271,25 @@ __global__ void rec_axisym_kernel(int nb, int ns, int nNwake, int nFwake, int ro
       rot_point(t, o, dst + kVfFc2);
     }
   }
+}
+
+// rotor_updatePrescribedWake (classdef.f90:5170-5218) in two launches, arithmetic in pfwake.cuh.  helix = (helixPitch,
+// helixRadius) per blade of this record set; fits = scratch, one per blade; the far rows rowStart..rowStart+n-1 are fitted.
+__global__ void pf_fit_kernel(int nbConvect, int nFwake, int rowStart, int n, double deltaPsi, double hubZ,
+                              const double* __restrict__ waF, double* __restrict__ helix, pf::Fit* __restrict__ fits) {
+  const int ib = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ib >= nbConvect) return;
+  pf::fit(waF + (size_t)kFw * ((size_t)(rowStart - 1) + (size_t)nFwake * ib), n, deltaPsi, hubZ, helix + 2 * ib, fits + ib);
+}
+// Ts: the blade rotations of the axisymmetric branch (as rec_axisym_kernel), may be null when axisym != 1
+__global__ void pf_helix_kernel(int nb, int nbConvect, int axisym, const pf::Fit* __restrict__ fits, const AxiT* __restrict__ Ts,
+                                double ox, double oy, double oz, double* __restrict__ wapF, double* __restrict__ helix) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nb * pf::kNpf) return;
+  const int ib = q / pf::kNpf, i = q % pf::kNpf;
+  const double hub[3] = {ox, oy, oz};
+  const bool copy = axisym == 1 && ib > 0;
+  pf::blade_filament(ib, i, nbConvect, axisym, fits, copy ? Ts[ib].T : nullptr, copy ? Ts[ib].rotate : 0, hub, wapF, helix);
 }
 
 // rotor_shiftFwake (classdef.f90:4500-4513): waF(i) = waF(i-1), i = nFwake..2, then waF(1)%vf%age = 0.  One thread per
