@@ -24,6 +24,7 @@ module libGPU
   ! device-resident time stepping (tier 2b of the C ABI): the wake is uploaded once and every wake mutator of the time
   ! loop runs on the library's copies; tests/native/case_gpu_hooks.c (resident mode) is the tested C twin
   public :: gpu_resident_begin, gpu_wake_prestep, gpu_wake_convect, gpu_download_wake
+  public :: gpu_burst_wake
   ! collocation-point stage on the device (tier 2c of the C ABI): velCP, RHS, solve, map_gam and -- forceCalcSwitch 0 --
   ! velCPTotal and the sectional loads; tests/native/case_gpu_hooks.c (h_cp_rhs_solve / h_cp_forces) is the tested C twin
   public :: gpu_cp_rhs_solve, gpu_cp_forces
@@ -233,6 +234,12 @@ module libGPU
       type(c_ptr), value :: c
       integer(c_int), value :: ir, ib, predicted
       real(c_double), intent(out) :: waF(*)
+    end function
+    integer(c_int) function vlc_rotor_burst_wake(c, ir, skewLimit, largeCoreRadius) bind(C, name='vlc_rotor_burst_wake')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+      real(c_double), value :: skewLimit, largeCoreRadius
     end function
     integer(c_int) function vlc_rotor_updatePrescribedWake(c, ir, deltaPsi, prescWakeGenNt, predicted) &
       & bind(C, name='vlc_rotor_updatePrescribedWake')
@@ -545,6 +552,14 @@ contains
       enddo
     endif
   end subroutine gpu_wake_prestep
+
+  subroutine gpu_burst_wake(rotor, ir)
+    !! Replaces `call rotor(ir)%burst_wake()` (main.f90:490-497; classdef.f90:4911-4917) in resident mode: the driver keeps
+    !! its `mod(iter, switches%wakeBurst)` test and calls this right after gpu_wake_prestep.
+    type(rotor_class), intent(in) :: rotor
+    integer, intent(in) :: ir
+    call check(vlc_rotor_burst_wake(ctx, ir - 1, rotor%skewLimit, rotor%chord))
+  end subroutine gpu_burst_wake
 
   subroutine gpu_convect(rotor, ir, iter, dt, p)
     !! rotor%convectwake(iter, dt, wakeType) (classdef.f90:4786-4830) on the device records, its last statement included:

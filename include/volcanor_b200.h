@@ -176,6 +176,10 @@ int vlc_rotor_age_wake(vlc_ctx* ctx, int ir, double dt, double omegaSlow);
 int vlc_rotor_dissipate_wake(vlc_ctx* ctx, int ir, double dt, double kinematicVisc);
 /* = rotor%strain_wake() classdef.f90:4410-4422 */
 int vlc_rotor_strain_wake(vlc_ctx* ctx, int ir);
+/* = rotor%burst_wake() classdef.f90:4911-4917 (blade_burst_wake :2306-2339; the driver calls it every wakeBurst-th step,
+ * main.f90:490-497): where successive far-wake filaments of the current wake kink by skewLimit or more (skew =
+ * |angle - pi|/pi), both get the core radius largeCoreRadius (= rotor%chord). */
+int vlc_rotor_burst_wake(vlc_ctx* ctx, int ir, double skewLimit, double largeCoreRadius);
 /* waNPredicted(rowNear:, :) = waN(rowNear:, :), waFPredicted(rowFar:) = waF(rowFar:) of the convected blades
  * (main.f90:869-872, :1028-1030) */
 int vlc_rotor_wake_to_predicted(vlc_ctx* ctx, int ir);

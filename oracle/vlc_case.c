@@ -1487,6 +1487,9 @@ int orc_case_step(orc_case_t *c) {
     if (cfg->wakeDissipation == 1)
       for (int ir = 0; ir < c->nr; ++ir)
         if (c->rotor[ir]->nNwake > 0) orc_rotor_dissipate_wake(c->rotor[ir], dt, cfg->kinematicVisc);
+    if (cfg->wakeBurst != 0 && iter % cfg->wakeBurst == 0) /* :490-497 */
+      for (int ir = 0; ir < c->nr; ++ir)
+        if (c->rotor[ir]->nNwake > 0) orc_rotor_burst_wake(c->rotor[ir]);
   }
   /* RHS, :522-615 */
   if (c->hooks.cp_rhs_solve && cfg->ntSub == 0) { /* collocation-point stage by the hook owner (tier 2c of the C ABI) */

@@ -16,9 +16,10 @@
  *
  * Scope: surfaceType 1 (lifting) rotors and wings, geometryFile '0' or a PLOT3D grid passed in
  * memory, forceCalcSwitch 0, fdScheme 0-5, slowStart 0-3, wake dissipation / strain,
- * axisymmetry, far-wake roll-up and truncation.  Not restated (unused by every shipped case):
+ * axisymmetry, far-wake roll-up and truncation, wake burst, prescribed far wake.  Not restated (unused by every shipped case):
  * image surfaces, non-lifting STL bodies, camber files, C81 tables, blade/body dynamics, custom
- * trajectories, wake burst, prescribed far wake generation.
+ * trajectories.  (Restated although unused by every shipped case, parity unpinned: wake strain, wake burst, the
+ * prescribed far wake.)
  */
 #ifndef VLC_CASE_H
 #define VLC_CASE_H

@@ -730,6 +730,33 @@ void orc_rotor_strain_wake(orc_rotor_t *r) {
   }
 }
 
+/* classdef.f90:4911-4917 rotor_burst_wake -> :2306-2339 blade_burst_wake (far wake only; the near-wake branch is commented
+ * out in the source): a kink between successive far filaments beyond skewLimit gives both the core radius `chord`.
+ * getAngleCos libMath.f90:238-247.  PARITY UNPINNED: wakeBurst = 0 in every shipped case, no reference test. */
+int orc_burst_pair(const orc_fwake_t *f0, const orc_fwake_t *f1, double skewLimit) {
+  const double pi = orc_pi();
+  double a[3], b[3];
+  for (int k = 0; k < 3; ++k) {
+    a[k] = f0->vf.fc[1][k] - f0->vf.fc[0][k];
+    b[k] = f1->vf.fc[0][k] - f1->vf.fc[1][k];
+  }
+  const double dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+  const double sa = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], sb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+  const double skewVal = fabs(acos(dot / sqrt(sa * sb)) - pi) / pi;
+  return skewVal >= skewLimit;
+}
+void orc_rotor_burst_wake(orc_rotor_t *r) {
+  for (int ib = 0; ib < r->nb; ++ib) {
+    orc_blade_t *b = &r->blade[ib];
+    if (r->rowFar > r->nFwake) continue;
+    for (int i = r->rowFar; i <= r->nFwake - 1; ++i)
+      if (orc_burst_pair(&WAF(b, i), &WAF(b, i + 1), r->skewLimit)) {
+        WAF(b, i + 1).vf.rVc = r->chord;
+        WAF(b, i).vf.rVc = r->chord;
+      }
+  }
+}
+
 /* classdef.f90:4481-4498 */
 void orc_rotor_shiftwake(orc_rotor_t *r) {
   for (int ib = 0; ib < r->nb; ++ib) {

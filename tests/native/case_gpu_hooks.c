@@ -66,6 +66,7 @@ typedef struct resident_ops {
   /* general velocity bookkeeping of the multistep schemes (fdScheme 4 / 5): array ids VLC_VEL_ARRAY_* */
   int (*wakevel_copy)(gpu_user_t *u, int ir, int dst, int src);
   int (*wakevel_lincomb)(gpu_user_t *u, int ir, int dst, int nterms, const int *src, const double *coef, double divisor);
+  int (*burst_wake)(gpu_user_t *u, int ir); /* rotor%burst_wake(), every wakeBurst-th step (main.f90:490-497) */
 } resident_ops_t;
 
 #define CK(expr)                        \
@@ -210,9 +211,14 @@ static int g_velcopy(gpu_user_t *u, int ir, int dst, int src) { return vlc_rotor
 static int g_vellin(gpu_user_t *u, int ir, int dst, int n, const int *src, const double *coef, double div) {
   return vlc_rotor_wakevel_lincomb(u->ctx, ir, dst, n, src, coef, div);
 }
+static int g_burst(gpu_user_t *u, int ir) {
+  const orc_rotor_t *r = orc_case_rotor(u->cas, ir);
+  return vlc_rotor_burst_wake(u->ctx, ir, r->skewLimit, r->chord);
+}
 static const resident_ops_t gpu_ops = {resident_begin, sync_wing, g_assignshed, g_age, g_dissipate, g_strain,
                                        g_to_pred, g_convect, g_rollup, g_sweep, g_velop,
-                                       g_sweep_count, g_sweep_slice, g_sweep_scatter, g_stream_sync, g_velcopy, g_vellin};
+                                       g_sweep_count, g_sweep_slice, g_sweep_scatter, g_stream_sync, g_velcopy, g_vellin,
+                                       g_burst};
 
 #define ROT(u, ir) orc_case_rotor((u)->cas, (ir))
 static int c_begin(gpu_user_t *u) { u->resident_started = 1; return 0; }
@@ -295,9 +301,14 @@ static int c_velcopy(gpu_user_t *u, int ir, int dst, int src) {
 static int c_vellin(gpu_user_t *u, int ir, int dst, int n, const int *src, const double *coef, double div) {
   return ROT(u, ir)->nNwake > 0 ? orc_rotor_wakevel_lincomb(ROT(u, ir), dst, n, src, coef, div) : 0;
 }
+static int c_burst(gpu_user_t *u, int ir) {
+  if (ROT(u, ir)->nNwake > 0) orc_rotor_burst_wake(ROT(u, ir));
+  return 0;
+}
 static const resident_ops_t cpu_ops = {c_begin, c_sync, c_assignshed, c_age, c_dissipate, c_strain,
                                        c_to_pred, c_convect, c_rollup, c_sweep, c_velop,
-                                       c_sweep_count, c_sweep_slice, c_sweep_scatter, c_stream_sync, c_velcopy, c_vellin};
+                                       c_sweep_count, c_sweep_slice, c_sweep_scatter, c_stream_sync, c_velcopy, c_vellin,
+                                       c_burst};
 
 /* One wake sweep of the staged orchestration.  One process: the backend's whole sweep.  One process per GPU (world > 1):
  * every rank holds the whole wake; it sweeps its slice of the targets, the slices are all-gathered (the one exchange of
@@ -322,7 +333,6 @@ static int staged_sweep(gpu_user_t *u, int p, int addInit) {
 static int h_wake_prestep(void *user, int iter) {
   gpu_user_t *u = (gpu_user_t *)user;
   const resident_ops_t *o = u->ops;
-  (void)iter;
   const orc_config_t *cfg = orc_case_config(u->cas);
   if (!u->resident_started) CK(o->begin(u));
   for (int ir = 0; ir < u->nr; ++ir) CK(o->sync(u, ir));
@@ -330,6 +340,9 @@ static int h_wake_prestep(void *user, int iter) {
   for (int ir = 0; ir < u->nr; ++ir) CK(o->age_wake(u, ir, cfg->dt, orc_case_rotor(u->cas, ir)->omegaSlow));
   if (cfg->wakeDissipation == 1)
     for (int ir = 0; ir < u->nr; ++ir) CK(o->dissipate_wake(u, ir, cfg->dt, cfg->kinematicVisc));
+  if (cfg->wakeBurst != 0 && iter % cfg->wakeBurst == 0) /* main.f90:490-497 */
+    for (int ir = 0; ir < u->nr; ++ir)
+      if (orc_case_rotor(u->cas, ir)->nNwake > 0) CK(o->burst_wake(u, ir));
   return 0;
 }
 

@@ -1,5 +1,5 @@
 // pfwake_host.cpp -- TEST INFRASTRUCTURE: the host + device routines of volcanor_b200/csrc/pfwake.cuh (prescribed far
-// wake: the fit of pFwake_update, the helix filaments, the axisymmetric copies) compiled by g++ and driven with the loops
+// wake: the fit of pFwake_update, the helix filaments, the axisymmetric copies; wake burst) compiled by g++ and driven with the loops
 // the two CUDA kernels run (pf_fit_kernel: one "thread" per convected blade; pf_helix_kernel: one per (blade, filament),
 // here in reverse order: the threads are independent), so tests/test_prescribed_wake.py can check arithmetic and index
 // logic against the oracle bit for bit without a GPU.  Nothing in the product links or loads this file.
@@ -27,6 +27,19 @@ int pf_host_update(int nb, int nbConvect, int axisym, int nFwake, int rowFar, in
                             helix);
   }
   return 0;
+}
+
+// = rec_burst_kernel, pairs visited in reverse order (the decisions read only end points; every write stores the same value)
+void pf_host_burst(int nb, int nFwake, int rowFar, double skewLimit, double largeCoreRadius, double* waF) {
+  const int npair = nFwake - rowFar;
+  for (int q = nb * (npair > 0 ? npair : 0) - 1; q >= 0; --q) {
+    const int ib = q / npair, irow = rowFar + q % npair;
+    double* f0 = waF + (size_t)vlc::pf::kFwRec * ((size_t)(irow - 1) + (size_t)nFwake * ib);
+    if (vlc::pf::burst_pair(f0, f0 + vlc::pf::kFwRec, skewLimit)) {
+      f0[vlc::pf::kFwRec + vlc::pf::kRvc] = largeCoreRadius;
+      f0[vlc::pf::kRvc] = largeCoreRadius;
+    }
+  }
 }
 
 }  // extern "C"

@@ -232,3 +232,98 @@ def test_product_generator_host_build_is_bit_identical_to_the_oracle(oracle, gen
                 if ib < p["nbConvect"] or axisym:
                     assert np.array_equal(ref, helix[ib]), (gen, axisym, pred, rep, ib)
             assert np.all(np.abs(wapF[:, :, 12]) > 0)
+
+
+# ------------------------------------------------------------------------------------------------------- wake burst
+# rotor%burst_wake() (classdef.f90:4911-4917 -> :2306-2339): PARITY UNPINNED as well (wakeBurst = 0 in every shipped case).
+
+def _kinked_far_wake(rng, n):
+    """A far-wake chain (fc2(i+1) = fc1(i)) along -z with a few sharp kinks."""
+    nodes = np.zeros((n + 1, 3))
+    step = np.array([0.0, 0.0, -0.1])
+    for i in range(1, n + 1):
+        d = step + 0.004 * rng.standard_normal(3)
+        if i in (3, 4, n - 2):
+            d = d + np.array([0.12, -0.05, 0.03])              # a kink well beyond the limit used below
+        nodes[i] = nodes[i - 1] + d
+    waF = np.zeros((n, FW))
+    waF[:, 3:6] = nodes[:-1]                                    # fc(:,2): the newer end
+    waF[:, 0:3] = nodes[1:]                                     # fc(:,1): the older end; fc2(i+1) = fc1(i) (wake_continuity)
+    waF[:, 9] = 0.02 + 0.001 * np.arange(n)
+    waF[:, 12] = -1.0
+    return waF
+
+
+def test_burst_wake_oracle_properties_and_host_build_of_the_product(oracle):
+    rng = np.random.default_rng(21)
+    n, limit, core = 12, 0.05, 0.77
+    waF = _kinked_far_wake(rng, n)
+    assert np.array_equal(waF[1:, 3:6], waF[:-1, 0:3])          # the chain rule of the far wake (wake_continuity)
+    olib, lib = oracle.load(), _pf_host()
+    olib.orc_burst_pair.restype = C.c_int
+    olib.orc_burst_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    # the skew by an independent formula: angle between successive segments, as a fraction of pi
+    seg = waF[:, 3:6] - waF[:, 0:3]
+    cosang = np.einsum("ij,ij->i", seg[:-1], -seg[1:]) / (np.linalg.norm(seg[:-1], axis=1) * np.linalg.norm(seg[1:], axis=1))
+    skew = np.abs(np.arccos(np.clip(cosang, -1, 1)) - np.pi) / np.pi
+    want = skew >= limit
+    assert 2 <= want.sum() < n - 1 and np.min(np.abs(skew - limit)) > 1e-3      # clear decisions, both kinds
+    got = np.array([olib.orc_burst_pair(waF[i].ctypes.data, waF[i + 1].ctypes.data, limit) for i in range(n - 1)], dtype=bool)
+    assert np.array_equal(got, want)
+    # straight chain: skew 0, nothing bursts; limit 0 bursts everything (>=)
+    straight = waF.copy()
+    straight[:, 0:3] = np.arange(n, 0, -1)[:, None] * np.array([0.0, 0.0, 0.1])
+    straight[:, 3:6] = (np.arange(n, 0, -1)[:, None] + 1) * np.array([0.0, 0.0, 0.1])
+    assert not olib.orc_burst_pair(straight[2].ctypes.data, straight[3].ctypes.data, 1e-7)
+    assert olib.orc_burst_pair(straight[2].ctypes.data, straight[3].ctypes.data, 0.0)
+    # the product's routine in its host build, driven like rec_burst_kernel: two blades, rowFar = 3 (rows 1, 2 inactive)
+    lib.pf_host_burst.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    lib.pf_host_burst.restype = None
+    two = np.stack([waF, waF[:, :]]).copy()
+    two[1, :, 9] += 0.5
+    before = two.copy()
+    lib.pf_host_burst(2, n, 3, limit, core, two.ctypes.data)
+    for ib in range(2):
+        hit = np.zeros(n, dtype=bool)
+        for i in range(2, n - 1):                               # 0-based rows rowFar-1 .. nFwake-2
+            if want[i]:
+                hit[i] = hit[i + 1] = True
+        assert np.array_equal(two[ib, hit, 9], np.full(hit.sum(), core))
+        assert np.array_equal(two[ib, ~hit, 9], before[ib, ~hit, 9])
+        keep = [k for k in range(FW) if k != 9]
+        assert np.array_equal(two[ib][:, keep], before[ib][:, keep])
+
+
+@pytest.mark.parametrize("fd", [3, 1])
+def test_wake_burst_staged_orchestration_equals_inline_time_loop(oracle, fd):
+    """The driver's `mod(iter, wakeBurst)` statement (main.f90:490-497) through the staged orchestration: bit-identical to
+    the inline loop, and the burst really changes far-wake core radii (and with them the loads)."""
+    from tests.test_staged_hooks import _lib
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    g = fx["geom"][0]
+    g["nNwake"], g["wakeTruncateNt"], g["skewLimit"] = 6, 14, 0.004
+    fx["config"]["fdScheme"] = fd
+    fx["config"]["wakeBurst"] = 2
+    plain = json.loads(json.dumps(fx))
+    plain["config"]["wakeBurst"] = 0
+    lib = _lib()
+    a, b, c = oracle.Case(fx), oracle.Case(fx), oracle.Case(plain)
+    b.init_rotors()
+    h = lib.case_cpu_staged_hooks_install(b.h, b.nr)
+    assert h
+    for x in (a, b, c):
+        x.init()
+    for it in range(16):
+        for x in (a, b, c):
+            x.step()
+        assert np.array_equal(a.force_nondim(0), b.force_nondim(0)), (fd, it + 1)
+    ra, rb, rc = a.rotor(0), b.rotor(0), c.rotor(0)
+    chord = g["chord"]
+    burst = 0
+    for ib in range(ra.nb):
+        assert np.array_equal(ra.waF(ib), rb.waF(ib)) and np.array_equal(ra.waN(ib), rb.waN(ib))
+        burst += int(np.sum(ra.waF(ib)[:, 9] == chord))
+        assert not np.any(rc.waF(ib)[:, 9] == chord)
+    assert burst >= 2
+    assert not np.array_equal(a.force_nondim(0), c.force_nondim(0))
+    lib.case_gpu_hooks_free(h)

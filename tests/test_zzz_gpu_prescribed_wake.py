@@ -4,6 +4,7 @@ filaments per blade are sources of every sweep (the abs(gam) > eps rule of class
 pf_helix_kernel; tests/native/case_gpu_hooks.c: g_convect is the C twin of fortran/libGPU.f90: gpu_convect).  Against the CPU driver
 (oracle; PARITY UNPINNED for this feature: no shipped case enables it, tests/test_prescribed_wake.py) over a window in which
 the helix is attached and felt.  Runs last (file name): written after the round's GPU minutes were spent."""
+import ctypes as C
 import json
 from pathlib import Path
 
@@ -86,7 +87,6 @@ def test_update_prescribed_wake_on_the_device_vs_oracle(cctx, oracle, gen, axisy
     """vlc_rotor_updatePrescribedWake alone, on the oracle's far wake: the fit parameters (sums, products, sqrt: no
     transcendental) BIT-IDENTICAL, the end points within 1e-13 of the helix radius (cos / sin / atan2 of CUDA vs libm), gam
     and rVc bit-identical; two successive updates from a zero fit (the relaxation carries state), both record sets."""
-    import ctypes as C
     from tests.test_zz_gpu_cp_stage import _define, _developed
     fx = json.loads((GOLDEN / "elevateTest.json").read_text())
     _with_prescribed_wake(gen)(fx)
@@ -135,3 +135,74 @@ def test_update_prescribed_wake_error_behaviour(cctx):  # noqa: F811
     with pytest.raises(Exception, match="no far-wake row"):
         cctx.rotor_updatePrescribedWake(0, 0.1, 5, "C")           # rowStart = 0
     cctx.rotor_updatePrescribedWake(0, 0.1, 2, "C")               # rows 3..5 of an all-zero far wake: a degenerate helix, no error
+
+
+def _burst_case():
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    g = fx["geom"][0]
+    g["nNwake"], g["wakeTruncateNt"], g["skewLimit"] = 6, 14, 0.004
+    fx["config"]["wakeBurst"] = 2
+    return fx
+
+
+def test_burst_wake_on_the_device_vs_oracle(cctx, oracle):  # noqa: F811
+    """vlc_rotor_burst_wake against rotor%burst_wake() of the oracle (classdef.f90:4911-4917, :2306-2339) on a developed far
+    wake, with a limit placed in the widest gap of the skew values so that the last bits of acos cannot decide: far-wake
+    records bit-identical (only rVc of the burst pairs changes)."""
+    from tests.test_zz_gpu_cp_stage import _define, _developed
+    fx = _burst_case()
+    fx["config"]["wakeBurst"] = 0
+    case = _developed(oracle, fx, 15)
+    rot = case.rotor(0)
+    skews = []
+    for ib in range(rot.nb):
+        w = rot.waF(ib)[rot.dims()["rowFar"] - 1:]
+        seg = w[:, 3:6] - w[:, 0:3]
+        cosang = np.einsum("ij,ij->i", seg[:-1], -seg[1:]) / (np.linalg.norm(seg[:-1], axis=1) * np.linalg.norm(seg[1:], axis=1))
+        skews += list(np.abs(np.arccos(np.clip(cosang, -1, 1)) - np.pi) / np.pi)
+    sk = np.sort(np.array(skews))
+    assert len(sk) >= 4
+    k = int(np.argmax(np.diff(sk)))
+    limit = 0.5 * (sk[k] + sk[k + 1])
+    assert sk[k + 1] - sk[k] > 1e-9
+    _define(cctx, rot, 0)
+    core = 0.77
+    cctx.rotor_burst_wake(0, limit, core)
+    olib = oracle.load()
+    rot_skew, rot_chord = limit, core
+    before = [rot.waF(ib).copy() for ib in range(rot.nb)]
+    # the oracle reads skewLimit / chord from the rotor: drive its pair test directly with the same limit
+    olib.orc_burst_pair.restype = C.c_int
+    olib.orc_burst_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    changed = 0
+    for ib in range(rot.nb):
+        ref = before[ib].copy()
+        for i in range(rot.dims()["rowFar"] - 1, rot.nFwake - 1):
+            if olib.orc_burst_pair(before[ib][i].ctypes.data, before[ib][i + 1].ctypes.data, rot_skew):
+                ref[i, 9] = ref[i + 1, 9] = rot_chord
+        got = cctx.rotor_get_fwake(0, ib, rot.nFwake)
+        assert np.array_equal(got, ref), ib
+        changed += int(np.sum(ref[:, 9] != before[ib][:, 9]))
+    assert changed >= 2
+
+
+def test_wake_burst_resident_vs_cpu_driver(cctx, oracle):  # noqa: F811
+    fx = _burst_case()
+    fx["config"]["rotorForcePlot"] = 1
+    a, b = oracle.Case(fx), oracle.Case(fx)
+    lib, h = _cp_hooks(b, cctx, True)
+    a.init()
+    b.init()
+    worst = 0.0
+    for it in range(18):
+        a.step()
+        _step(b, lib, h, cctx, it + 1)
+        worst = max(worst, abs(b.force_nondim(0)[0] / a.force_nondim(0)[0] - 1.0))
+    assert lib.case_gpu_hooks_download_wake(h) == 0
+    chord = fx["geom"][0]["chord"]
+    for ib in range(a.rotor(0).nb):
+        assert np.array_equal(a.rotor(0).waF(ib)[:, 9] == chord, b.rotor(0).waF(ib)[:, 9] == chord)   # the same filaments burst
+    assert sum(int(np.sum(a.rotor(0).waF(ib)[:, 9] == chord)) for ib in range(a.rotor(0).nb)) >= 2
+    print(f"elevateTest + wakeBurst = 2 (skewLimit 0.004), 18 steps, resident: max rel err CT {worst:.3e}")
+    assert worst < TOL_HISTORY, worst
+    lib.case_gpu_hooks_free(h)

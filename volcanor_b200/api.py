@@ -124,6 +124,7 @@ def load_library() -> C.CDLL:
         "vlc_rotor_wake_to_predicted": (i32, [_vp, i32]),
         "vlc_rotor_convectwake": (i32, [_vp, i32, C.c_double, i32]),
         "vlc_rotor_updatePrescribedWake": (i32, [_vp, i32, C.c_double, i32, i32]),
+        "vlc_rotor_burst_wake": (i32, [_vp, i32, C.c_double, C.c_double]),
         "vlc_rotor_get_pfwake": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_rotor_rollup": (i32, [_vp, i32]),
         "vlc_wake_sweep": (i32, [_vp, i32, i32]),
@@ -414,6 +415,10 @@ class Context:
 
     def rotor_convectwake(self, ir, dt, wakeType: str = "C"):
         self._ck(self.lib.vlc_rotor_convectwake(self.h, ir, dt, {"C": 0, "P": 1}[wakeType]))
+
+    def rotor_burst_wake(self, ir, skewLimit, largeCoreRadius):
+        """rotor%burst_wake() (classdef.f90:4911-4917) on the device's far wake."""
+        self._ck(self.lib.vlc_rotor_burst_wake(self.h, ir, skewLimit, largeCoreRadius))
 
     def rotor_updatePrescribedWake(self, ir, deltaPsi, prescWakeGenNt=0, wakeType: str = "C"):
         """rotor%updatePrescribedWake(dt, wakeType) (classdef.f90:5170-5218) on the device records; deltaPsi = omegaSlow*dt."""

@@ -1681,6 +1681,22 @@ extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicte
   return VLC_OK;
 }
 
+extern "C" int vlc_rotor_burst_wake(vlc_ctx* c, int ir, double skewLimit, double largeCoreRadius) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const long long n = (long long)r->nb * std::max(0, r->nFwake - r->rowFar);
+  if (n <= 0) return VLC_OK;  // classdef.f90:2323: fewer than two active far filaments
+  vlc::rec_burst_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(r->nb, r->nFwake, r->rowFar, skewLimit, largeCoreRadius,
+                                                                   r->waF[0].p);
+  c->launches++;
+  CUDA_OK(c, cudaGetLastError());
+  r->dirty[0] = true;
+  return VLC_OK;
+}
+
 extern "C" int vlc_rotor_updatePrescribedWake(vlc_ctx* c, int ir, double deltaPsi, int prescWakeGenNt, int predicted) {
   CHECK_CTX(c);
   int rc = bind_device(c);

@@ -127,5 +127,24 @@ VLC_HD void blade_filament(int ib, int i, int nbConvect, int axisym, const Fit* 
   }
 }
 
+// ---- wake burst (classdef.f90:4911-4917 rotor_burst_wake -> :2306-2339 blade_burst_wake; far wake only, the near-wake
+// branch is commented out in the source).  skewVal = |getAngleCos(fc2(i) - fc1(i), fc1(i+1) - fc2(i+1)) - pi|/pi
+// (libMath.f90:238-247): 0 for a straight chain; at or beyond skewLimit both filaments get the core radius
+// largeCoreRadius (= rotor%chord).  f0, f1 = records irow, irow + 1.  acos is the device's (<= 2 ulp from libm's): a
+// decision can differ from a CPU run only for a kink within that distance of the limit.
+VLC_HD bool burst_pair(const double* f0, const double* f1, double skewLimit) {
+  const double pi = 3.141592653589793;
+  double a[3], b[3];
+  for (int k = 0; k < 3; ++k) {
+    a[k] = sub(f0[kFc2 + k], f0[kFc1 + k]);
+    b[k] = sub(f1[kFc1 + k], f1[kFc2 + k]);
+  }
+  const double dot = add(add(mul(a[0], b[0]), mul(a[1], b[1])), mul(a[2], b[2]));
+  const double sa = add(add(mul(a[0], a[0]), mul(a[1], a[1])), mul(a[2], a[2]));
+  const double sb = add(add(mul(b[0], b[0]), mul(b[1], b[1])), mul(b[2], b[2]));
+  const double skewVal = quo(fabs(sub(acos(quo(dot, root(mul(sa, sb)))), pi)), pi);
+  return skewVal >= skewLimit;
+}
+
 }  // namespace pf
 }  // namespace vlc

@@ -292,6 +292,21 @@ __global__ void pf_helix_kernel(int nb, int nbConvect, int axisym, const pf::Fit
   pf::blade_filament(ib, i, nbConvect, axisym, fits, copy ? Ts[ib].T : nullptr, copy ? Ts[ib].rotate : 0, hub, wapF, helix);
 }
 
+// rotor_burst_wake (classdef.f90:4911-4917, :2306-2339): one thread per (blade, pair of successive far filaments irow,
+// irow + 1 with irow = rowFar..nFwake-1).  The source's loop is sequential but order-free: the test reads only end points,
+// which nothing here writes, and every write stores the same value, so overlapping pairs may race harmlessly.
+__global__ void rec_burst_kernel(int nb, int nFwake, int rowFar, double skewLimit, double largeCoreRadius, double* __restrict__ waF) {
+  const int npair = nFwake - rowFar;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (npair <= 0 || q >= nb * npair) return;
+  const int ib = q / npair, irow = rowFar + q % npair;
+  double* f0 = waF + (size_t)kFw * ((size_t)(irow - 1) + (size_t)nFwake * ib);
+  if (pf::burst_pair(f0, f0 + kFw, skewLimit)) {
+    f0[kFw + kVfRvc] = largeCoreRadius;
+    f0[kVfRvc] = largeCoreRadius;
+  }
+}
+
 // rotor_shiftFwake (classdef.f90:4500-4513): waF(i) = waF(i-1), i = nFwake..2, then waF(1)%vf%age = 0.  One thread per
 // (blade, double of the record), walking the rows downwards like the reference (nFwake is a few hundred at most).
 __global__ void rec_shiftFwake_kernel(int nb, int nFwake, double* __restrict__ waF) {
