@@ -86,37 +86,10 @@ def test_prescribed_filaments_are_sources_of_vind_bywake(cctx, oracle, predicted
 def test_update_prescribed_wake_on_the_device_vs_oracle(cctx, oracle, gen, axisym):  # noqa: F811
     """vlc_rotor_updatePrescribedWake alone, on the oracle's far wake: the fit parameters (sums, products, sqrt: no
     transcendental) BIT-IDENTICAL, the end points within 1e-13 of the helix radius (cos / sin / atan2 of CUDA vs libm), gam
-    and rVc bit-identical; two successive updates from a zero fit (the relaxation carries state), both record sets."""
-    from tests.test_zz_gpu_cp_stage import _define, _developed
-    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
-    _with_prescribed_wake(gen)(fx)
-    fx["geom"][0]["axisymmetrySwitch"] = axisym
-    case = _developed(oracle, fx, 15)
-    rot = case.rotor(0)
-    p = rot.params()
-    olib = oracle.load()
-    _define(cctx, rot, 0)
-    cctx.rotor_set_frame(0, p["shaftAxis"], p["hubCoords"])
-    for ib in range(rot.nb):
-        cctx.rotor_put_nwake(0, ib, rot.waN(ib, True), predicted=True)
-        cctx.rotor_put_fwake(0, ib, rot.waF(ib, True), predicted=True)
-    zero = np.zeros(2)
-    for pred in (False, True):
-        for ib in range(rot.nb):
-            olib.orc_rotor_set_pfHelix(rot.h, ib, int(pred), zero.ctypes.data)
-        for rep in range(2):
-            dt = 0.0137 * (rep + 1)
-            assert olib.orc_rotor_updatePrescribedWake(rot.h, dt, b"P" if pred else b"C") == 0
-            cctx.rotor_updatePrescribedWake(0, p["omegaSlow"] * dt, gen, "P" if pred else "C")
-            for ib in range(rot.nb):
-                w, hx = cctx.rotor_get_pfwake(0, ib, pred)
-                ref, hr = rot.wapF(ib, pred), np.zeros(2)
-                olib.orc_rotor_get_pfHelix(rot.h, ib, int(pred), hr.ctypes.data)
-                assert np.array_equal(hx, hr), (pred, rep, ib, hx, hr)
-                assert np.array_equal(w[:, 9], ref[:, 9]) and np.array_equal(w[:, 12], ref[:, 12])
-                assert np.all(np.abs(w[:, 12]) > 0)
-                scale = abs(hr[1]) + 10 * abs(hr[0]) + np.max(np.abs(p["hubCoords"]))
-                assert np.max(np.abs(w[:, 0:6] - ref[:, 0:6])) < 1e-13 * scale, (pred, rep, ib)
+    and rVc bit-identical; two successive updates from a zero fit (the relaxation carries state), both record sets.
+    The body also runs on the CPU against the host build of the product's source (tests/test_prescribed_wake.py)."""
+    from tests.test_prescribed_wake import check_update_prescribed_wake
+    check_update_prescribed_wake(cctx, oracle, gen, axisym)
 
 
 def test_update_prescribed_wake_error_behaviour(cctx):  # noqa: F811
@@ -148,42 +121,9 @@ def _burst_case():
 def test_burst_wake_on_the_device_vs_oracle(cctx, oracle):  # noqa: F811
     """vlc_rotor_burst_wake against rotor%burst_wake() of the oracle (classdef.f90:4911-4917, :2306-2339) on a developed far
     wake, with a limit placed in the widest gap of the skew values so that the last bits of acos cannot decide: far-wake
-    records bit-identical (only rVc of the burst pairs changes)."""
-    from tests.test_zz_gpu_cp_stage import _define, _developed
-    fx = _burst_case()
-    fx["config"]["wakeBurst"] = 0
-    case = _developed(oracle, fx, 15)
-    rot = case.rotor(0)
-    skews = []
-    for ib in range(rot.nb):
-        w = rot.waF(ib)[rot.dims()["rowFar"] - 1:]
-        seg = w[:, 3:6] - w[:, 0:3]
-        cosang = np.einsum("ij,ij->i", seg[:-1], -seg[1:]) / (np.linalg.norm(seg[:-1], axis=1) * np.linalg.norm(seg[1:], axis=1))
-        skews += list(np.abs(np.arccos(np.clip(cosang, -1, 1)) - np.pi) / np.pi)
-    sk = np.sort(np.array(skews))
-    assert len(sk) >= 4
-    k = int(np.argmax(np.diff(sk)))
-    limit = 0.5 * (sk[k] + sk[k + 1])
-    assert sk[k + 1] - sk[k] > 1e-9
-    _define(cctx, rot, 0)
-    core = 0.77
-    cctx.rotor_burst_wake(0, limit, core)
-    olib = oracle.load()
-    rot_skew, rot_chord = limit, core
-    before = [rot.waF(ib).copy() for ib in range(rot.nb)]
-    # the oracle reads skewLimit / chord from the rotor: drive its pair test directly with the same limit
-    olib.orc_burst_pair.restype = C.c_int
-    olib.orc_burst_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
-    changed = 0
-    for ib in range(rot.nb):
-        ref = before[ib].copy()
-        for i in range(rot.dims()["rowFar"] - 1, rot.nFwake - 1):
-            if olib.orc_burst_pair(before[ib][i].ctypes.data, before[ib][i + 1].ctypes.data, rot_skew):
-                ref[i, 9] = ref[i + 1, 9] = rot_chord
-        got = cctx.rotor_get_fwake(0, ib, rot.nFwake)
-        assert np.array_equal(got, ref), ib
-        changed += int(np.sum(ref[:, 9] != before[ib][:, 9]))
-    assert changed >= 2
+    records bit-identical (only rVc of the burst pairs changes).  Body shared with the CPU run on the host build."""
+    from tests.test_prescribed_wake import check_burst_wake
+    check_burst_wake(cctx, oracle, _burst_case())
 
 
 def test_wake_burst_resident_vs_cpu_driver(cctx, oracle):  # noqa: F811
