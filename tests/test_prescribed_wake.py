@@ -330,7 +330,7 @@ def test_wake_burst_staged_orchestration_equals_inline_time_loop(oracle, fd):
 
 
 # ------------------------------------------------------------ bodies shared by the GPU tests and their CPU emulation
-# (tests/test_zzz_gpu_prescribed_wake.py calls them with a volcanor_b200.Context; here they run on EmulatedWakeContext:
+# (tests/test_zzz_gpu_first_run.py calls them with a volcanor_b200.Context; here they run on EmulatedWakeContext:
 # the host build of the product's pfwake.cuh driven like the kernels, so what the GPU tests upload, call and compare is
 # exercised without a GPU)
 

@@ -1,9 +1,16 @@
-"""Prescribed far wake (classdef.f90:4826-4828, :5170-5218, :998-1066) with the wake resident on the device: the 240 helix
-filaments per blade are sources of every sweep (the abs(gam) > eps rule of classdef.f90:1471-1476), uploaded
-(vlc_rotor_put_pfwake) or made on the device from its own far rows (vlc_rotor_updatePrescribedWake: pf_fit_kernel +
-pf_helix_kernel; tests/native/case_gpu_hooks.c: g_convect is the C twin of fortran/libGPU.f90: gpu_convect).  Against the CPU driver
-(oracle; PARITY UNPINNED for this feature: no shipped case enables it, tests/test_prescribed_wake.py) over a window in which
-the helix is attached and felt.  Runs last (file name): written after the round's GPU minutes were spent."""
+"""GPU tests written after the round's GPU minutes were spent: they have not run on a B200 yet, so they come last (file
+name) and a surprise here cannot hide the results of the suite before them.  Their logic is covered on the CPU -- same
+orchestration on the CPU backend bit-identical to the driver's inline loop (tests/test_staged_hooks.py,
+tests/test_prescribed_wake.py), host builds of the host + device sources against the oracle, test bodies run on an
+emulated context -- what is left for the GPU is the CUDA side of each call.
+
+ * Prescribed far wake (classdef.f90:4826-4828, :5170-5218, :998-1066): the 240 helix filaments per blade as sources of
+   every sweep (the abs(gam) > eps rule of classdef.f90:1471-1476), uploaded (vlc_rotor_put_pfwake) or made on the device
+   from its own far rows (vlc_rotor_updatePrescribedWake: pf_fit_kernel + pf_helix_kernel; tests/native/case_gpu_hooks.c:
+   g_convect is the C twin of fortran/libGPU.f90: gpu_convect).  PARITY UNPINNED for this feature: no shipped case
+   enables it.
+ * rotor%burst_wake (classdef.f90:4911-4917): vlc_rotor_burst_wake per call and in a resident run.  Parity unpinned too.
+ * fdScheme 2 / 4 / 5 with the collocation-point stage on the device (vlc_rotor_wakevel_copy / _lincomb, vel2 / vel3)."""
 import ctypes as C
 import json
 from pathlib import Path
@@ -12,7 +19,9 @@ import numpy as np
 import pytest
 
 from tests.test_prescribed_wake import _with_prescribed_wake
-from tests.test_zz_gpu_cp_stage import TOL_HISTORY, _cp_hooks, _step, cctx  # noqa: F401  (fixture)
+from tests.test_cp_stage_host import _mut
+from tests.test_zz_gpu_cp_stage import (TOL_HISTORY, _cp_hooks, _short_caradonna, _step, cctx,  # noqa: F401  (fixture)
+                                        check_cp_stage_vs_cpu_driver)
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
@@ -146,3 +155,13 @@ def test_wake_burst_resident_vs_cpu_driver(cctx, oracle):  # noqa: F811
     print(f"elevateTest + wakeBurst = 2 (skewLimit 0.004), 18 steps, resident: max rel err CT {worst:.3e}")
     assert worst < TOL_HISTORY, worst
     lib.case_gpu_hooks_free(h)
+
+
+@pytest.mark.parametrize("name,nsteps,mutate",
+                         [  # fdScheme 2 (explicit Adams-Bashforth): AB2 + FIRST_STEP + COPY_TO_STEP on the device arrays
+                          ("katzNplotkin_AR04", 25, _mut(fdScheme=2)),
+                          # fdScheme 4 / 5 (third / fourth order multistep): vlc_rotor_wakevel_copy / _lincomb, vel2 / vel3
+                          ("katzNplotkin_AR04", 25, _mut(fdScheme=4)),
+                          ("caradonna", 30, lambda fx: (_short_caradonna(fx), fx["config"].update(fdScheme=5)))])
+def test_cp_stage_vs_cpu_driver_other_fd_schemes(cctx, oracle, name, nsteps, mutate):  # noqa: F811
+    check_cp_stage_vs_cpu_driver(cctx, oracle, name, nsteps, mutate, True)
