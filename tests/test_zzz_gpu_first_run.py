@@ -27,17 +27,23 @@ pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
-@pytest.mark.parametrize("gen,cp", [(0, True), (2, False)])
-def test_prescribed_wake_resident_vs_cpu_driver(cctx, oracle, gen, cp):  # noqa: F811
+@pytest.mark.parametrize("gen,mode", [(0, "resident+cp"), (2, "resident"), (0, "per-sweep")])
+def test_prescribed_wake_case_vs_cpu_driver(cctx, oracle, gen, mode):  # noqa: F811
+    """resident: the helix is made on the device (vlc_rotor_updatePrescribedWake after each vlc_rotor_convectwake);
+    per-sweep: the driver makes it (rotor%updatePrescribedWake) and the shim uploads it with the wake (vlc_rotor_put_pfwake)."""
     fx = json.loads((GOLDEN / "elevateTest.json").read_text())          # 5 blades, axisymmetric
     _with_prescribed_wake(gen)(fx)                                       # prescWakeNt = 12
     fx["config"]["rotorForcePlot"] = 1
     a, b = oracle.Case(fx), oracle.Case(fx)
+    cp = mode == "resident+cp"
     if cp:
         lib, h = _cp_hooks(b, cctx, True)
-    else:
+    elif mode == "resident":
         from tests.test_gpu_resident import _resident_hooks
         lib, h = _resident_hooks(b, cctx)
+    else:
+        from tests.test_gpu_case import _native_hooks
+        lib, h = _native_hooks(b, cctx)
     a.init()
     b.init()
     worst = [0.0, 0.0]
@@ -48,15 +54,16 @@ def test_prescribed_wake_resident_vs_cpu_driver(cctx, oracle, gen, cp):  # noqa:
         ga, gb = a.rotor(0).vec(0), b.rotor(0).vec(0)
         worst[0] = max(worst[0], abs(fb[0] / fa[0] - 1.0))
         worst[1] = max(worst[1], float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
-    assert lib.case_gpu_hooks_download_wake(h) == 0                      # the helix made on the device, back in b's records
+    if mode != "per-sweep":
+        assert lib.case_gpu_hooks_download_wake(h) == 0                  # the helix made on the device, back in b's records
     ra, rb = a.rotor(0), b.rotor(0)
     for ib in range(ra.nb):
         wa, wb = ra.wapF(ib), rb.wapF(ib)
         assert np.all(np.abs(wa[:, 12]) > 0)
         assert np.max(np.abs(wb[:, :6] - wa[:, :6])) < 1e-9 * np.max(np.abs(wa[:, :6]))
         assert np.max(np.abs(wb[:, 12] - wa[:, 12])) < 1e-9 * np.max(np.abs(wa[:, 12]))
-    print(f"elevateTest + prescribed far wake (prescWakeGenNt = {gen}), 20 steps, wake resident"
-          f"{', collocation-point stage on the device' if cp else ''}: max rel err CT {worst[0]:.3e}, gamVec {worst[1]:.3e}")
+    print(f"elevateTest + prescribed far wake (prescWakeGenNt = {gen}), 20 steps, {mode}: max rel err CT {worst[0]:.3e}, "
+          f"gamVec {worst[1]:.3e}")
     assert max(worst) < TOL_HISTORY, worst
     lib.case_gpu_hooks_free(h)
 
