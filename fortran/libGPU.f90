@@ -235,6 +235,26 @@ module libGPU
       integer(c_int), value :: ir, ib, predicted
       real(c_double), intent(out) :: waF(*)
     end function
+    integer(c_int) function vlc_rotor_put_pfwake_helix(c, ir, ib, predicted, helix) bind(C, name='vlc_rotor_put_pfwake_helix')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, predicted
+      real(c_double), intent(in) :: helix(*)
+    end function
+    integer(c_int) function vlc_rotor_put_wakevel(c, ir, ib, which, velN, velF) bind(C, name='vlc_rotor_put_wakevel')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, which
+      real(c_double), intent(in) :: velN(*)
+      real(c_double), intent(in) :: velF(*)
+    end function
+    integer(c_int) function vlc_rotor_get_wakevel(c, ir, ib, which, velN, velF) bind(C, name='vlc_rotor_get_wakevel')
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir, ib, which
+      real(c_double), intent(out) :: velN(*)
+      real(c_double), intent(out) :: velF(*)
+    end function
     integer(c_int) function vlc_rotor_burst_wake(c, ir, skewLimit, largeCoreRadius) bind(C, name='vlc_rotor_burst_wake')
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: c
@@ -515,14 +535,35 @@ contains
         if (rotor(ir)%nNwake > 0) then
           buf = transfer(rotor(ir)%blade(ib)%waN, buf)
           call check(vlc_rotor_put_nwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
-          buf = transfer(rotor(ir)%blade(ib)%waNPredicted, buf)
-          call check(vlc_rotor_put_nwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+          if (allocated(rotor(ir)%blade(ib)%waNPredicted)) then   ! fdScheme 1, 3, 4, 5 (classdef.f90:3733-3824)
+            buf = transfer(rotor(ir)%blade(ib)%waNPredicted, buf)
+            call check(vlc_rotor_put_nwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+          endif
+          ! zero at a fresh start like the device's own; the histories of a run resumed from a restart file
+          call put_vel(ir, ib, ARR_VEL, rotor(ir)%blade(ib)%velNwake, rotor(ir)%blade(ib)%velFwake)
+          call put_vel(ir, ib, ARR_VEL1, rotor(ir)%blade(ib)%velNwake1, rotor(ir)%blade(ib)%velFwake1)
+          call put_vel(ir, ib, ARR_PREDICTED, rotor(ir)%blade(ib)%velNwakePredicted, rotor(ir)%blade(ib)%velFwakePredicted)
+          call put_vel(ir, ib, ARR_STEP, rotor(ir)%blade(ib)%velNwakeStep, rotor(ir)%blade(ib)%velFwakeStep)
+          call put_vel(ir, ib, ARR_VEL2, rotor(ir)%blade(ib)%velNwake2, rotor(ir)%blade(ib)%velFwake2)
+          call put_vel(ir, ib, ARR_VEL3, rotor(ir)%blade(ib)%velNwake3, rotor(ir)%blade(ib)%velFwake3)
         endif
         if (rotor(ir)%nFwake > 0) then
           buf = transfer(rotor(ir)%blade(ib)%waF, buf)
           call check(vlc_rotor_put_fwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
-          buf = transfer(rotor(ir)%blade(ib)%waFPredicted, buf)
-          call check(vlc_rotor_put_fwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+          if (allocated(rotor(ir)%blade(ib)%waFPredicted)) then
+            buf = transfer(rotor(ir)%blade(ib)%waFPredicted, buf)
+            call check(vlc_rotor_put_fwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+          endif
+        endif
+        if (rotor(ir)%prescWakeNt > 0) then   ! all zero at a fresh start; the helix and its fit of a resumed run
+          buf = transfer(rotor(ir)%blade(ib)%wapF%waF, buf)
+          call check(vlc_rotor_put_pfwake(ctx, ir - 1, ib - 1, 0_c_int, buf))
+          call check(vlc_rotor_put_pfwake_helix(ctx, ir - 1, ib - 1, 0_c_int, &
+            & [rotor(ir)%blade(ib)%wapF%helixPitch, rotor(ir)%blade(ib)%wapF%helixRadius]))
+          buf = transfer(rotor(ir)%blade(ib)%wapFPredicted%waF, buf)
+          call check(vlc_rotor_put_pfwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+          call check(vlc_rotor_put_pfwake_helix(ctx, ir - 1, ib - 1, 1_c_int, &
+            & [rotor(ir)%blade(ib)%wapFPredicted%helixPitch, rotor(ir)%blade(ib)%wapFPredicted%helixRadius]))
         endif
       enddo
     enddo
@@ -788,7 +829,8 @@ contains
   end subroutine gpu_cp_forces
 
   subroutine gpu_download_wake(rotor)
-    !! Bring the device's wake records back into the driver's derived types (before wake plots / restart files).
+    !! Bring the device's wake back into the driver's derived types (before wake plots / restart files): records of the
+    !! current and the predicted wake, the prescribed helix, the velocity arrays of the convection driver.
     type(rotor_class), intent(inout) :: rotor(:)
     integer :: ir, ib
     real(c_double), allocatable :: buf(:)
@@ -816,8 +858,64 @@ contains
           rotor(ir)%blade(ib)%wapF%isPresent = .true.
           deallocate (buf)
         endif
+        if (rotor(ir)%nNwake > 0) then   ! the predicted records and the velocity arrays of the fdScheme in use (restart files)
+          if (allocated(rotor(ir)%blade(ib)%waNPredicted)) then
+            allocate (buf(50*size(rotor(ir)%blade(ib)%waNPredicted)))
+            call check(vlc_rotor_get_nwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+            rotor(ir)%blade(ib)%waNPredicted = reshape(transfer(buf, rotor(ir)%blade(ib)%waNPredicted), &
+              & shape(rotor(ir)%blade(ib)%waNPredicted))
+            deallocate (buf)
+          endif
+          if (allocated(rotor(ir)%blade(ib)%waFPredicted)) then
+            if (size(rotor(ir)%blade(ib)%waFPredicted) > 0) then
+              allocate (buf(13*size(rotor(ir)%blade(ib)%waFPredicted)))
+              call check(vlc_rotor_get_fwake(ctx, ir - 1, ib - 1, 1_c_int, buf))
+              rotor(ir)%blade(ib)%waFPredicted = transfer(buf, rotor(ir)%blade(ib)%waFPredicted)
+              deallocate (buf)
+            endif
+          endif
+          call get_vel(ir, ib, ARR_VEL, rotor(ir)%blade(ib)%velNwake, rotor(ir)%blade(ib)%velFwake)
+          call get_vel(ir, ib, ARR_VEL1, rotor(ir)%blade(ib)%velNwake1, rotor(ir)%blade(ib)%velFwake1)
+          call get_vel(ir, ib, ARR_PREDICTED, rotor(ir)%blade(ib)%velNwakePredicted, rotor(ir)%blade(ib)%velFwakePredicted)
+          call get_vel(ir, ib, ARR_STEP, rotor(ir)%blade(ib)%velNwakeStep, rotor(ir)%blade(ib)%velFwakeStep)
+          call get_vel(ir, ib, ARR_VEL2, rotor(ir)%blade(ib)%velNwake2, rotor(ir)%blade(ib)%velFwake2)
+          call get_vel(ir, ib, ARR_VEL3, rotor(ir)%blade(ib)%velNwake3, rotor(ir)%blade(ib)%velFwake3)
+        endif
       enddo
     enddo
   end subroutine gpu_download_wake
+
+  subroutine get_vel(ir, ib, which, velN, velF)
+    !! One pair of the convection driver's velocity arrays (classdef.f90:285-292), when this fdScheme allocated it
+    integer, intent(in) :: ir, ib
+    integer(c_int), intent(in) :: which
+    real(dp), allocatable, intent(inout) :: velN(:, :, :), velF(:, :)
+    real(c_double) :: none(1)
+    if (.not. allocated(velN)) return
+    if (allocated(velF)) then
+      if (size(velF) > 0) then
+        call check(vlc_rotor_get_wakevel(ctx, ir - 1, ib - 1, which, velN, velF))
+        return
+      endif
+    endif
+    call check(vlc_rotor_get_wakevel(ctx, ir - 1, ib - 1, which, velN, none))   ! nFwake = 0: nothing is written to it
+  end subroutine get_vel
+
+  subroutine put_vel(ir, ib, which, velN, velF)
+    !! Upload twin of get_vel
+    integer, intent(in) :: ir, ib
+    integer(c_int), intent(in) :: which
+    real(dp), allocatable, intent(in) :: velN(:, :, :), velF(:, :)
+    real(c_double) :: none(1)
+    if (.not. allocated(velN)) return
+    if (allocated(velF)) then
+      if (size(velF) > 0) then
+        call check(vlc_rotor_put_wakevel(ctx, ir - 1, ib - 1, which, velN, velF))
+        return
+      endif
+    endif
+    none = 0._c_double
+    call check(vlc_rotor_put_wakevel(ctx, ir - 1, ib - 1, which, velN, none))   ! nFwake = 0: nothing is read from it
+  end subroutine put_vel
 
 end module libGPU

@@ -198,6 +198,10 @@ int vlc_rotor_updatePrescribedWake(vlc_ctx* ctx, int ir, double deltaPsi, int pr
 /* Device -> host copy of a blade's prescribed wake records (wake plots, libPostprocess.f90:266-284; restart files);
  * helix, when not NULL, receives (helixPitch, helixRadius) of that blade and record set. */
 int vlc_rotor_get_pfwake(vlc_ctx* ctx, int ir, int ib, int predicted, double* wapF /* 240 x 13 */, double* helix /* 2 or NULL */);
+/* Host -> device: (helixPitch, helixRadius) of a blade's prescribed wake, the state the relaxation of the next
+ * vlc_rotor_updatePrescribedWake starts from (zero after vlc_rotor_define, like pFwake_class classdef.f90:228-229) -- with
+ * vlc_rotor_put_pfwake what a driver resuming from a restart file sends. */
+int vlc_rotor_put_pfwake_helix(vlc_ctx* ctx, int ir, int ib, int predicted, const double* helix /* 2 */);
 /* = rotor%rollup() classdef.f90:4515-4605 (shiftFwake :4500-4513 when the far wake is full, then shiftwake :4481-4498);
  * the driver calls it when rowNear == 1 (main.f90:1424-1425). */
 int vlc_rotor_rollup(vlc_ctx* ctx, int ir);

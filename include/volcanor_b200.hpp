@@ -144,6 +144,9 @@ class Rotor {
   }
   void get_nwake(int ib, double* waN, bool predicted = false) { c_.check(vlc_rotor_get_nwake(c_.handle(), ir_, ib, predicted, waN)); }
   void get_fwake(int ib, double* waF, bool predicted = false) { c_.check(vlc_rotor_get_fwake(c_.handle(), ir_, ib, predicted, waF)); }
+  void put_pfwake_helix(int ib, const double* helix, bool predicted = false) {
+    c_.check(vlc_rotor_put_pfwake_helix(c_.handle(), ir_, ib, predicted, helix));
+  }
   void get_pfwake(int ib, double* wapF, double* helix = nullptr, bool predicted = false) {
     c_.check(vlc_rotor_get_pfwake(c_.handle(), ir_, ib, predicted, wapF, helix));
   }

@@ -124,6 +124,14 @@ def test_update_prescribed_wake_error_behaviour(cctx):  # noqa: F811
     with pytest.raises(Exception, match="no far-wake row"):
         cctx.rotor_updatePrescribedWake(0, 0.1, 5, "C")           # rowStart = 0
     cctx.rotor_updatePrescribedWake(0, 0.1, 2, "C")               # rows 3..5 of an all-zero far wake: a degenerate helix, no error
+    # restart resume: records + fit parameters round trip, per blade and record set
+    rng = np.random.default_rng(3)
+    w = rng.standard_normal((240, 13))
+    cctx.rotor_put_pfwake(0, 1, w, predicted=True)
+    cctx.rotor_put_pfwake_helix(0, 1, [1.5, 2.5], predicted=True)
+    got, hx = cctx.rotor_get_pfwake(0, 1, predicted=True)
+    assert np.array_equal(got, w) and np.array_equal(hx, [1.5, 2.5])
+    assert np.array_equal(cctx.rotor_get_pfwake(0, 1, predicted=False)[1], [0.0, 0.0])
 
 
 def _burst_case():

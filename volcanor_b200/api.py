@@ -126,6 +126,7 @@ def load_library() -> C.CDLL:
         "vlc_rotor_updatePrescribedWake": (i32, [_vp, i32, C.c_double, i32, i32]),
         "vlc_rotor_burst_wake": (i32, [_vp, i32, C.c_double, C.c_double]),
         "vlc_rotor_get_pfwake": (i32, [_vp, i32, i32, i32, _vp, _vp]),
+        "vlc_rotor_put_pfwake_helix": (i32, [_vp, i32, i32, i32, _vp]),
         "vlc_rotor_rollup": (i32, [_vp, i32]),
         "vlc_wake_sweep": (i32, [_vp, i32, i32]),
         "vlc_wake_sweep_count": (i32, [_vp, C.POINTER(i64)]),
@@ -423,6 +424,9 @@ class Context:
     def rotor_updatePrescribedWake(self, ir, deltaPsi, prescWakeGenNt=0, wakeType: str = "C"):
         """rotor%updatePrescribedWake(dt, wakeType) (classdef.f90:5170-5218) on the device records; deltaPsi = omegaSlow*dt."""
         self._ck(self.lib.vlc_rotor_updatePrescribedWake(self.h, ir, deltaPsi, prescWakeGenNt, {"C": 0, "P": 1}[wakeType]))
+
+    def rotor_put_pfwake_helix(self, ir, ib, helix, predicted=False):
+        self._ck(self.lib.vlc_rotor_put_pfwake_helix(self.h, ir, ib, int(predicted), _ptr(_f64(helix, (2,)))))
 
     def rotor_get_pfwake(self, ir, ib, predicted=False):
         """-> (wapF (240, 13), (helixPitch, helixRadius)) of one blade."""

@@ -1725,6 +1725,16 @@ extern "C" int vlc_rotor_updatePrescribedWake(vlc_ctx* c, int ir, double deltaPs
   return VLC_OK;
 }
 
+extern "C" int vlc_rotor_put_pfwake_helix(vlc_ctx* c, int ir, int ib, int predicted, const double* helix) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  if (ib < 0 || ib >= r->nb || !helix) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
+  return upload(c, r->pfHelix[predicted ? 1 : 0], (size_t)2 * r->nb, (size_t)2 * ib, helix, 2);
+}
+
 extern "C" int vlc_rotor_get_pfwake(vlc_ctx* c, int ir, int ib, int predicted, double* wapF, double* helix) {
   CHECK_CTX(c);
   int rc = bind_device(c);
