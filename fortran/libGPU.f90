@@ -24,7 +24,7 @@ module libGPU
   ! device-resident time stepping (tier 2b of the C ABI): the wake is uploaded once and every wake mutator of the time
   ! loop runs on the library's copies; tests/native/case_gpu_hooks.c (resident mode) is the tested C twin
   public :: gpu_resident_begin, gpu_wake_prestep, gpu_wake_convect, gpu_download_wake
-  public :: gpu_burst_wake
+  public :: gpu_burst_wake, gpu_calc_skew
   ! collocation-point stage on the device (tier 2c of the C ABI): velCP, RHS, solve, map_gam and -- forceCalcSwitch 0 --
   ! velCPTotal and the sectional loads; tests/native/case_gpu_hooks.c (h_cp_rhs_solve / h_cp_forces) is the tested C twin
   public :: gpu_cp_rhs_solve, gpu_cp_forces
@@ -254,6 +254,11 @@ module libGPU
       integer(c_int), value :: ir, ib, which
       real(c_double), intent(out) :: velN(*)
       real(c_double), intent(out) :: velF(*)
+    end function
+    integer(c_int) function vlc_rotor_calc_skew(c, ir) bind(C, name='vlc_rotor_calc_skew')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
     end function
     integer(c_int) function vlc_rotor_burst_wake(c, ir, skewLimit, largeCoreRadius) bind(C, name='vlc_rotor_burst_wake')
       import :: c_int, c_ptr, c_double
@@ -601,6 +606,13 @@ contains
     integer, intent(in) :: ir
     call check(vlc_rotor_burst_wake(ctx, ir - 1, rotor%skewLimit, rotor%chord))
   end subroutine gpu_burst_wake
+
+  subroutine gpu_calc_skew(ir)
+    !! Replaces `call rotor(ir)%calc_skew()` (main.f90:499-504; classdef.f90:4919-4936) in resident mode; skew2file then
+    !! needs the records on the host: gpu_download_wake.
+    integer, intent(in) :: ir
+    call check(vlc_rotor_calc_skew(ctx, ir - 1))
+  end subroutine gpu_calc_skew
 
   subroutine gpu_convect(rotor, ir, iter, dt, p)
     !! rotor%convectwake(iter, dt, wakeType) (classdef.f90:4786-4830) on the device records, its last statement included:

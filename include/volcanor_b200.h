@@ -180,6 +180,9 @@ int vlc_rotor_strain_wake(vlc_ctx* ctx, int ir);
  * main.f90:490-497): where successive far-wake filaments of the current wake kink by skewLimit or more (skew =
  * |angle - pi|/pi), both get the core radius largeCoreRadius (= rotor%chord). */
 int vlc_rotor_burst_wake(vlc_ctx* ctx, int ir, double skewLimit, double largeCoreRadius);
+/* = rotor%calc_skew() classdef.f90:4919-4936 (the driver calls it every skewPlotSwitch-th step before skew2file,
+ * main.f90:499-504): vr%skew of the active near-wake rings of the current wake; vlc_rotor_get_nwake brings it back. */
+int vlc_rotor_calc_skew(vlc_ctx* ctx, int ir);
 /* waNPredicted(rowNear:, :) = waN(rowNear:, :), waFPredicted(rowFar:) = waF(rowFar:) of the convected blades
  * (main.f90:869-872, :1028-1030) */
 int vlc_rotor_wake_to_predicted(vlc_ctx* ctx, int ir);

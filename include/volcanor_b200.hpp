@@ -125,6 +125,7 @@ class Rotor {
   void age_wake(double dt, double omegaSlow) { c_.check(vlc_rotor_age_wake(c_.handle(), ir_, dt, omegaSlow)); }
   void dissipate_wake(double dt, double kinematicVisc) { c_.check(vlc_rotor_dissipate_wake(c_.handle(), ir_, dt, kinematicVisc)); }
   void strain_wake() { c_.check(vlc_rotor_strain_wake(c_.handle(), ir_)); }
+  void calc_skew() { c_.check(vlc_rotor_calc_skew(c_.handle(), ir_)); }
   void burst_wake(double skewLimit, double largeCoreRadius) { c_.check(vlc_rotor_burst_wake(c_.handle(), ir_, skewLimit, largeCoreRadius)); }
   void wake_to_predicted() { c_.check(vlc_rotor_wake_to_predicted(c_.handle(), ir_)); }
   void convectwake(double dt, char wakeType) {

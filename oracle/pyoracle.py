@@ -83,6 +83,7 @@ def _bind(lib: C.CDLL) -> C.CDLL:
         "orc_rotor_dissipate_wake": (None, [_vp, d, d]),
         "orc_rotor_strain_wake": (None, [_vp]),
         "orc_rotor_burst_wake": (None, [_vp]),
+        "orc_rotor_calc_skew": (None, [_vp]),
         "orc_rotor_rollup": (None, [_vp]),
         "orc_vel_order2_Nwake": (None, [_vp, _vp, i32, i32, _vp]),
         "orc_vel_order2_Fwake": (None, [_vp, _vp, i32, _vp]),

@@ -730,6 +730,31 @@ void orc_rotor_strain_wake(orc_rotor_t *r) {
   }
 }
 
+/* classdef.f90:4919-4936 rotor_calc_skew -> :2341-2353 blade_calc_skew -> :737-747 calc_skew -> :704-721 vr_getBimedianCos:
+ * skew of a wake ring = |cos| of the angle between its bimedians (0 good, 1 bad), 0 for rings without circulation; an
+ * output for skew2file only.  PARITY UNPINNED (skewPlotSwitch = 0 in every shipped case, no reference test). */
+double orc_vr_skew(const orc_vr_t *v) {
+  if (!(fabs(v->gam) > ORC_EPS)) return 0.0;
+  const double *p1 = v->vf[0].fc[0], *p2 = v->vf[1].fc[0], *p3 = v->vf[2].fc[0], *p4 = v->vf[3].fc[0];
+  double x1[3], x2[3];
+  for (int k = 0; k < 3; ++k) {
+    x1[k] = p3[k] + p4[k] - p1[k] - p2[k];
+    x2[k] = p4[k] + p1[k] - p2[k] - p3[k];
+  }
+  const double d12 = x1[0] * x2[0] + x1[1] * x2[1] + x1[2] * x2[2];
+  const double d11 = x1[0] * x1[0] + x1[1] * x1[1] + x1[2] * x1[2], d22 = x2[0] * x2[0] + x2[1] * x2[1] + x2[2] * x2[2];
+  return fabs(d12 / sqrt(d11 * d22));
+}
+void orc_rotor_calc_skew(orc_rotor_t *r) {
+  for (int ib = 0; ib < r->nbConvect; ++ib)
+    for (int j = 1; j <= r->ns; ++j)
+      for (int i = r->rowNear; i <= r->nNwake; ++i) WAN(&r->blade[ib], i, j).skew = orc_vr_skew(&WAN(&r->blade[ib], i, j));
+  if (r->axisymmetrySwitch == 1)
+    for (int ib = 1; ib < r->nb; ++ib)
+      for (int j = 1; j <= r->ns; ++j)
+        for (int i = r->rowNear; i <= r->nNwake; ++i) WAN(&r->blade[ib], i, j).skew = WAN(&r->blade[0], i, j).skew;
+}
+
 /* classdef.f90:4911-4917 rotor_burst_wake -> :2306-2339 blade_burst_wake (far wake only; the near-wake branch is commented
  * out in the source): a kink between successive far filaments beyond skewLimit gives both the core radius `chord`.
  * getAngleCos libMath.f90:238-247.  PARITY UNPINNED: wakeBurst = 0 in every shipped case, no reference test. */

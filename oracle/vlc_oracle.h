@@ -167,6 +167,8 @@ void orc_rotor_age_wake(orc_rotor_t *r, double dt);                             
 void orc_rotor_dissipate_wake(orc_rotor_t *r, double dt, double kinematicViscosity);                            /* :4356-4408 */
 void orc_rotor_strain_wake(orc_rotor_t *r);                                                                     /* :4410-4422 */
 void orc_rotor_burst_wake(orc_rotor_t *r); /* :4911-4917, :2306-2339 (far wake; parity unpinned: no shipped case) */
+void orc_rotor_calc_skew(orc_rotor_t *r); /* :4919-4936 (output for skew2file; parity unpinned) */
+double orc_vr_skew(const orc_vr_t *v);
 int orc_burst_pair(const orc_fwake_t *f0, const orc_fwake_t *f1, double skewLimit);
 void orc_rotor_shiftwake(orc_rotor_t *r);                                                                       /* :4481-4498 */
 void orc_rotor_shiftFwake(orc_rotor_t *r);                                                                      /* :4500-4513 */

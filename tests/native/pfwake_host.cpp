@@ -42,4 +42,17 @@ void pf_host_burst(int nb, int nFwake, int rowFar, double skewLimit, double larg
   }
 }
 
+// = rec_skew_kernel
+void pf_host_skew(int nb, int nbConvect, int axisym, int ns, int nNwake, int rowNear, double* waN) {
+  const int nact = nNwake - rowNear + 1;
+  const size_t blade = (size_t)nNwake * ns * 50;
+  for (long long q = (long long)nb * ns * (nact > 0 ? nact : 0) - 1; q >= 0; --q) {
+    const int i = rowNear + (int)(q % nact), j = (int)((q / nact) % ns) + 1, ib = (int)(q / ((long long)nact * ns));
+    const int src = vlc::pf::source_blade(ib, nbConvect, axisym);
+    if (src < 0) continue;
+    const size_t at = 50 * ((size_t)(i - 1) + (size_t)nNwake * (j - 1));
+    waN[blade * ib + at + 49] = vlc::pf::ring_skew(waN + blade * src + at);
+  }
+}
+
 }  // extern "C"

@@ -403,6 +403,30 @@ def check_burst_wake(ctx, oracle, fx):
     assert changed >= 2 and changed < rot.nb * rot.nFwake
 
 
+def check_calc_skew(ctx, oracle, axisym):
+    """vlc_rotor_calc_skew against rotor%calc_skew() of the oracle (classdef.f90:4919-4936) on a developed near wake: the
+    records BIT-IDENTICAL (sums, products, one sqrt, one division); values in [0, 1], 0 only where gam is 0."""
+    from tests.test_zz_gpu_cp_stage import _define, _developed
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    g = fx["geom"][0]
+    g["nNwake"], g["wakeTruncateNt"], g["axisymmetrySwitch"] = 6, 10, axisym
+    case = _developed(oracle, fx, 4)                                      # rowNear = 3: rows 1, 2 are not yet shed
+    rot = case.rotor(0)
+    assert rot.dims()["rowNear"] == 3
+    _define(ctx, rot, 0)
+    ctx.rotor_calc_skew(0)
+    oracle.load().orc_rotor_calc_skew(rot.h)
+    for ib in range(rot.nb):
+        got, ref = ctx.rotor_get_nwake(0, ib, rot.nNwake, rot.ns), rot.waN(ib)
+        assert np.array_equal(got, ref), ib
+        sk = ref[:, 2:, 49]
+        assert np.all((sk >= 0) & (sk <= 1)) and np.any(sk > 0)
+        assert np.all((sk > 0) | (np.abs(ref[:, 2:, 48]) <= np.finfo(float).eps) | (sk == 0))
+        assert np.all(ref[:, :2, 49] == 0)                               # inactive rows untouched
+    if axisym:
+        assert np.array_equal(rot.waN(3)[:, 2:, 49], rot.waN(0)[:, 2:, 49])
+
+
 class EmulatedWakeContext:
     """Stand-in for volcanor_b200.Context: its own copies of the far-wake records, the g++ build of pfwake.cuh for the work."""
 
@@ -422,6 +446,7 @@ class EmulatedWakeContext:
 
     def rotor_set_rows(self, ir, rowNear, rowFar):
         self.r[ir]["rowFar"] = rowFar
+        self.r[ir]["rowNear"] = rowNear
 
     def rotor_set_frame(self, ir, shaftAxis, hubCoords):
         self.r[ir].update(axis=np.array(shaftAxis, dtype=float), hub=np.array(hubCoords, dtype=float))
@@ -430,7 +455,20 @@ class EmulatedWakeContext:
         pass
 
     def rotor_put_nwake(self, ir, ib, waN, predicted=False):
-        pass
+        r = self.r[ir]
+        if "waN" not in r:
+            r["waN"] = np.zeros((2, r["nb"]) + np.asarray(waN).shape)
+        r["waN"][int(predicted), ib] = waN
+
+    def rotor_get_nwake(self, ir, ib, nNwake, ns, predicted=False):
+        return self.r[ir]["waN"][int(predicted), ib].copy()
+
+    def rotor_calc_skew(self, ir):
+        r = self.r[ir]
+        ns, nNwake = r["waN"].shape[2], r["waN"].shape[3]
+        self.lib.pf_host_skew.argtypes = [C.c_int] * 6 + [C.c_void_p]
+        self.lib.pf_host_skew.restype = None
+        self.lib.pf_host_skew(r["nb"], r["nbConvect"], r["axisym"], ns, nNwake, r["rowNear"], r["waN"][0].ctypes.data)
 
     def rotor_put_fwake(self, ir, ib, waF, predicted=False):
         self.r[ir]["waF"][int(predicted), ib] = waF
@@ -473,3 +511,34 @@ def test_body_of_the_gpu_burst_test_on_the_host_build(oracle):
     g = fx["geom"][0]
     g["nNwake"], g["wakeTruncateNt"], g["skewLimit"] = 6, 14, 0.004
     check_burst_wake(EmulatedWakeContext(), oracle, fx)
+
+
+@pytest.mark.parametrize("axisym", [1, 0])
+def test_body_of_the_gpu_skew_test_on_the_host_build(oracle, axisym):
+    check_calc_skew(EmulatedWakeContext(), oracle, axisym)
+
+
+def test_skew_oracle_against_an_independent_formula(oracle):
+    """|cos| of the angle between the bimedians (lines joining the midpoints of opposite sides) of a quadrilateral ring."""
+    rng = np.random.default_rng(8)
+    olib = oracle.load()
+    olib.orc_vr_skew.restype = C.c_double
+    olib.orc_vr_skew.argtypes = [C.c_void_p]
+    for trial in range(20):
+        corners = rng.standard_normal((4, 3)) + np.array([[0, 0, 0], [2, 0, 0], [2, 2, 0], [0, 2, 0]])
+        if trial == 0:
+            corners = np.array([[0.0, 0, 0], [1, 0, 0], [1, 3, 0], [0, 3, 0]])      # rectangle: bimedians orthogonal
+        ring = np.zeros(50)
+        for n in range(4):
+            ring[12 * n:12 * n + 3] = corners[n]
+            ring[12 * n + 3:12 * n + 6] = corners[(n + 1) % 4]
+        ring[48] = -0.7
+        m = [0.5 * (corners[n] + corners[(n + 1) % 4]) for n in range(4)]       # side midpoints 12, 23, 34, 41
+        b1, b2 = m[2] - m[0], m[3] - m[1]
+        want = abs(b1 @ b2) / (np.linalg.norm(b1) * np.linalg.norm(b2))
+        got = olib.orc_vr_skew(ring.ctypes.data)
+        assert abs(got - want) < 1e-14, (trial, got, want)
+        if trial == 0:
+            assert got == 0.0
+        ring[48] = 0.0
+        assert olib.orc_vr_skew(ring.ctypes.data) == 0.0

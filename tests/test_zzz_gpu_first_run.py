@@ -10,6 +10,7 @@ emulated context -- what is left for the GPU is the CUDA side of each call.
    g_convect is the C twin of fortran/libGPU.f90: gpu_convect).  PARITY UNPINNED for this feature: no shipped case
    enables it.
  * rotor%burst_wake (classdef.f90:4911-4917): vlc_rotor_burst_wake per call and in a resident run.  Parity unpinned too.
+ * rotor%calc_skew (classdef.f90:4919-4936): vlc_rotor_calc_skew per call.  Parity unpinned too.
  * fdScheme 2 / 4 / 5 with the collocation-point stage on the device (vlc_rotor_wakevel_copy / _lincomb, vel2 / vel3)."""
 import ctypes as C
 import json
@@ -180,3 +181,11 @@ def test_wake_burst_resident_vs_cpu_driver(cctx, oracle):  # noqa: F811
                           ("caradonna", 30, lambda fx: (_short_caradonna(fx), fx["config"].update(fdScheme=5)))])
 def test_cp_stage_vs_cpu_driver_other_fd_schemes(cctx, oracle, name, nsteps, mutate):  # noqa: F811
     check_cp_stage_vs_cpu_driver(cctx, oracle, name, nsteps, mutate, True)
+
+
+@pytest.mark.parametrize("axisym", [1, 0])
+def test_calc_skew_on_the_device_vs_oracle(cctx, oracle, axisym):  # noqa: F811
+    """vlc_rotor_calc_skew (rec_skew_kernel) against rotor%calc_skew() of the oracle: records bit-identical.  Body shared with
+    the CPU run on the host build."""
+    from tests.test_prescribed_wake import check_calc_skew
+    check_calc_skew(cctx, oracle, axisym)

@@ -125,6 +125,7 @@ def load_library() -> C.CDLL:
         "vlc_rotor_convectwake": (i32, [_vp, i32, C.c_double, i32]),
         "vlc_rotor_updatePrescribedWake": (i32, [_vp, i32, C.c_double, i32, i32]),
         "vlc_rotor_burst_wake": (i32, [_vp, i32, C.c_double, C.c_double]),
+        "vlc_rotor_calc_skew": (i32, [_vp, i32]),
         "vlc_rotor_get_pfwake": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_rotor_put_pfwake_helix": (i32, [_vp, i32, i32, i32, _vp]),
         "vlc_rotor_rollup": (i32, [_vp, i32]),
@@ -416,6 +417,10 @@ class Context:
 
     def rotor_convectwake(self, ir, dt, wakeType: str = "C"):
         self._ck(self.lib.vlc_rotor_convectwake(self.h, ir, dt, {"C": 0, "P": 1}[wakeType]))
+
+    def rotor_calc_skew(self, ir):
+        """rotor%calc_skew() (classdef.f90:4919-4936): vr%skew of the active near-wake rings (record member 49)."""
+        self._ck(self.lib.vlc_rotor_calc_skew(self.h, ir))
 
     def rotor_burst_wake(self, ir, skewLimit, largeCoreRadius):
         """rotor%burst_wake() (classdef.f90:4911-4917) on the device's far wake."""

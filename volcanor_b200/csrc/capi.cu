@@ -1681,6 +1681,21 @@ extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicte
   return VLC_OK;
 }
 
+extern "C" int vlc_rotor_calc_skew(vlc_ctx* c, int ir) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const long long n = (long long)r->nb * r->ns * std::max(0, r->nNwake - r->rowNear + 1);
+  if (n <= 0) return VLC_OK;
+  vlc::rec_skew_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(r->nb, r->nbConvect, r->axisym, r->ns, r->nNwake, r->rowNear,
+                                                                  r->waN[0].p);
+  c->launches++;
+  CUDA_OK(c, cudaGetLastError());
+  return VLC_OK;  // the skew member is not a source quantity: the packed sets stay valid
+}
+
 extern "C" int vlc_rotor_burst_wake(vlc_ctx* c, int ir, double skewLimit, double largeCoreRadius) {
   CHECK_CTX(c);
   int rc = bind_device(c);

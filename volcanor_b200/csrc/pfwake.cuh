@@ -146,5 +146,21 @@ VLC_HD bool burst_pair(const double* f0, const double* f1, double skewLimit) {
   return skewVal >= skewLimit;
 }
 
+// ---- wake skew (classdef.f90:737-747 calc_skew, :704-721 vr_getBimedianCos): |cos| of the angle between the bimedians of a
+// wake ring (vr_class record: 4 filaments of 12 doubles, corner n = fc(:,1) of filament n; gam at 48), 0 without circulation.
+VLC_HD double ring_skew(const double* ring) {
+  if (!(fabs(ring[48]) > kEps)) return 0.0;
+  const double *p1 = ring, *p2 = ring + 12, *p3 = ring + 24, *p4 = ring + 36;
+  double x1[3], x2[3];
+  for (int k = 0; k < 3; ++k) {
+    x1[k] = sub(sub(add(p3[k], p4[k]), p1[k]), p2[k]);
+    x2[k] = sub(sub(add(p4[k], p1[k]), p2[k]), p3[k]);
+  }
+  const double d12 = add(add(mul(x1[0], x2[0]), mul(x1[1], x2[1])), mul(x1[2], x2[2]));
+  const double d11 = add(add(mul(x1[0], x1[0]), mul(x1[1], x1[1])), mul(x1[2], x1[2]));
+  const double d22 = add(add(mul(x2[0], x2[0]), mul(x2[1], x2[1])), mul(x2[2], x2[2]));
+  return fabs(quo(d12, root(mul(d11, d22))));
+}
+
 }  // namespace pf
 }  // namespace vlc

@@ -307,6 +307,20 @@ __global__ void rec_burst_kernel(int nb, int nFwake, int rowFar, double skewLimi
   }
 }
 
+// rotor_calc_skew (classdef.f90:4919-4936): vr%skew of every active near-wake ring of the convected blades; with
+// axisymmetry blades 2..nb receive blade 1's value (computed here from blade 1's ring: the same operands, the same result).
+// One thread per (blade, column, active row); reads corners and gam, writes only the skew member (49).
+__global__ void rec_skew_kernel(int nb, int nbConvect, int axisym, int ns, int nNwake, int rowNear, double* __restrict__ waN) {
+  const int nact = nNwake - rowNear + 1;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (nact <= 0 || q >= (long long)nb * ns * nact) return;
+  const int i = rowNear + (int)(q % nact), j = (int)((q / nact) % ns) + 1, ib = (int)(q / ((long long)nact * ns));
+  const int src = pf::source_blade(ib, nbConvect, axisym);
+  if (src < 0) return;
+  const size_t blade = (size_t)nNwake * ns * kVr;
+  ring_at(waN + blade * ib, nNwake, i, j)[kVrGam + 1] = pf::ring_skew(ring_at(waN + blade * src, nNwake, i, j));
+}
+
 // rotor_shiftFwake (classdef.f90:4500-4513): waF(i) = waF(i-1), i = nFwake..2, then waF(1)%vf%age = 0.  One thread per
 // (blade, double of the record), walking the rows downwards like the reference (nFwake is a few hundred at most).
 __global__ void rec_shiftFwake_kernel(int nb, int nFwake, double* __restrict__ waF) {
