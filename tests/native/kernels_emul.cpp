@@ -1,0 +1,92 @@
+// kernels_emul.cpp -- TEST INFRASTRUCTURE: the product's O(N) record kernels (volcanor_b200/csrc/wake_records.cuh, the
+// arithmetic of pfwake.cuh) compiled by g++ against a stand-in for <cuda_runtime.h> (tests/native/emul) and run thread by
+// thread, serially and in REVERSE thread order, with the launch shapes volcanor_b200/csrc/capi.cu uses.  What runs is
+// the kernel body itself -- its index decoding, its guards, its unfused arithmetic -- so tests/test_kernels_emul.py can
+// hold the kernels against the oracle bit for bit without a GPU (cos / sin / atan2 / acos are then libm's on both
+// sides).  Nothing in the product links or loads this file.  Build: tests/native/Makefile (g++ -O2 -ffp-contract=off).
+#include <algorithm>
+#include <vector>
+
+#include "../../volcanor_b200/csrc/wake_records.cuh"
+
+namespace {
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+}  // namespace
+
+extern "C" {
+
+// = vlc_rotor_age_wake
+void emul_age_wake(int nb, int ns, int nNwake, int nFwake, int rowNear, int rowFar, double dt, double omegaSlow, double* waN,
+                   double* waF) {
+  const long long nact = std::max(0, nNwake - rowNear + 1), nfar = std::max(0, nFwake - rowFar + 1);
+  const long long n = (long long)nb * (ns * nact + nfar);
+  if (n <= 0) return;
+  emul_launch(blocks_for(n, 256), 1, 256, vlc::rec_age_kernel, nb, ns, nNwake, nFwake, rowNear, rowFar, dt, dt * omegaSlow, waN, waF);
+}
+
+// = vlc_rotor_dissipate_wake
+void emul_dissipate_wake(int nb, int ns, int nNwake, int nFwake, int rowNear, int rowFar, double apparentViscCoeff,
+                         double decayCoeff, double dt, double kinematicVisc, double* waN, double* waF) {
+  const double growTerm = 4.0 * 1.2564 * apparentViscCoeff * kinematicVisc * dt;
+  const double decayFactor = std::exp(-decayCoeff * dt);
+  const long long nact = std::max(0, nNwake - rowNear + 1), nfar = std::max(0, nFwake - rowFar + 1);
+  const long long n = (long long)nb * (ns * nact + nfar);
+  if (n <= 0) return;
+  emul_launch(blocks_for(n, 256), 1, 256, vlc::rec_dissipate_kernel, nb, ns, nNwake, nFwake, rowNear, rowFar, growTerm, decayFactor,
+              waN, waF);
+  const long long n4 = (long long)nb * ns * (nact - 1);
+  if (n4 > 0) emul_launch(blocks_for(n4, 256), 1, 256, vlc::rec_dissipate_vf4_kernel, nb, ns, nNwake, rowNear, waN);
+}
+
+// = vlc_rotor_strain_wake
+void emul_strain_wake(int nb, int nFwake, int rowFar, double* waF) {
+  const int nfar = nFwake - rowFar + 1;
+  if (nfar <= 0) return;
+  emul_launch(blocks_for((long long)nb * nfar, 128), 1, 128, vlc::rec_strain_kernel, nb, nFwake, rowFar, waF);
+}
+
+// = vlc_rotor_burst_wake
+void emul_burst_wake(int nb, int nFwake, int rowFar, double skewLimit, double largeCoreRadius, double* waF) {
+  const long long n = (long long)nb * std::max(0, nFwake - rowFar);
+  if (n <= 0) return;
+  emul_launch(blocks_for(n, 128), 1, 128, vlc::rec_burst_kernel, nb, nFwake, rowFar, skewLimit, largeCoreRadius, waF);
+}
+
+// = vlc_rotor_calc_skew
+void emul_calc_skew(int nb, int nbConvect, int axisym, int ns, int nNwake, int rowNear, double* waN) {
+  const long long n = (long long)nb * ns * std::max(0, nNwake - rowNear + 1);
+  if (n <= 0) return;
+  emul_launch(blocks_for(n, 128), 1, 128, vlc::rec_skew_kernel, nb, nbConvect, axisym, ns, nNwake, rowNear, waN);
+}
+
+// = vlc_rotor_updatePrescribedWake; T9 = 9 doubles per blade (column-major, blade 0 unused), rotate = flag per blade
+int emul_updatePrescribedWake(int nb, int nbConvect, int axisym, int nFwake, int rowFar, int prescWakeGenNt, double deltaPsi,
+                              const double* hub, const double* T9, const int* rotate, const double* waF, double* wapF,
+                              double* helix) {
+  const int rowStart = prescWakeGenNt == 0 ? rowFar : nFwake - prescWakeGenNt;
+  if (nFwake <= 0 || rowStart < 1 || rowStart > nFwake) return 2;
+  std::vector<vlc::AxiT> Ts(nb);
+  for (int ib = 0; ib < nb; ++ib) {
+    for (int k = 0; k < 9; ++k) Ts[ib].T[k] = T9[9 * ib + k];
+    Ts[ib].rotate = rotate[ib];
+  }
+  std::vector<vlc::pf::Fit> fits(nb);
+  const bool copies = axisym == 1 && nb > 1;
+  emul_launch(blocks_for(nbConvect, 32), 1, 32, vlc::pf_fit_kernel, nbConvect, nFwake, rowStart, nFwake - rowStart + 1, deltaPsi,
+              hub[2], waF, helix, fits.data());
+  emul_launch(blocks_for((long long)nb * 240, 128), 1, 128, vlc::pf_helix_kernel, nb, nbConvect, axisym,
+              (const vlc::pf::Fit*)fits.data(), copies ? (const vlc::AxiT*)Ts.data() : (const vlc::AxiT*)nullptr, hub[0], hub[1],
+              hub[2], wapF, helix);
+  return 0;
+}
+
+// = vlc_rotor_wakevel_lincomb on one array (the caller passes the near- or the far-wake arrays)
+void emul_lincomb(long long n, int nterms, const double* s0, const double* s1, const double* s2, const double* s3,
+                  const double* coef, double divisor, double* dst) {
+  if (n <= 0) return;
+  double cf[4] = {0, 0, 0, 0};
+  for (int k = 0; k < nterms; ++k) cf[k] = coef[k];
+  emul_launch(blocks_for(n, 256), 1, 256, vlc::rec_lincomb_kernel, n, nterms, s0, s1, s2, s3, cf[0], cf[1], cf[2], cf[3], divisor, dst);
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""The product's O(N) record kernels run on the CPU: tests/native/kernels_emul.cpp compiles volcanor_b200/csrc/
+wake_records.cuh (with pack.cuh, pfwake.cuh, vlc_device.cuh) with g++ against a stand-in for <cuda_runtime.h> and runs each
+kernel body for every thread of the launch shape capi.cu uses, serially and in reverse thread order.  Held against the
+oracle BIT FOR BIT.  Two purposes: kernels that have run on a B200 (age, dissipate, strain) show that the emulation tells
+the truth; kernels written after the round's GPU minutes were spent (burst, skew, the prescribed far wake, the linear
+combinations of fdScheme 4 / 5) get their index logic and arithmetic checked before their first GPU run."""
+import ctypes as C
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+i32, f64, vp = C.c_int, C.c_double, C.c_void_p
+
+
+def emul_lib():
+    here = Path(__file__).resolve().parent / "native"
+    so = here / "libkernels_emul.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(here)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    sig = {"emul_age_wake": (None, [i32] * 6 + [f64, f64, vp, vp]),
+           "emul_dissipate_wake": (None, [i32] * 6 + [f64] * 4 + [vp, vp]),
+           "emul_strain_wake": (None, [i32] * 3 + [vp]),
+           "emul_burst_wake": (None, [i32] * 3 + [f64, f64, vp]),
+           "emul_calc_skew": (None, [i32] * 6 + [vp]),
+           "emul_updatePrescribedWake": (i32, [i32] * 6 + [f64] + [vp] * 6),
+           "emul_lincomb": (None, [C.c_longlong, i32, vp, vp, vp, vp, vp, f64, vp])}
+    for k, (res, args) in sig.items():
+        getattr(lib, k).restype = res
+        getattr(lib, k).argtypes = args
+    return lib
+
+
+def _case(oracle, nsteps, **geom):
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    g = fx["geom"][0]
+    g["nNwake"], g["wakeTruncateNt"] = 6, 10
+    g.update(geom)
+    c = oracle.Case(fx)
+    c.init()
+    for _ in range(nsteps):
+        c.step()
+    return c, fx
+
+
+def _stack(rot, what, *a):
+    return np.ascontiguousarray(np.stack([getattr(rot, what)(ib, *a) for ib in range(rot.nb)]))
+
+
+@pytest.mark.parametrize("nsteps", [4, 9])          # wake still growing (rowNear = 3, no far wake yet) / rolled up, far wake
+def test_emulation_agrees_with_the_oracle_on_kernels_that_ran_on_a_b200(oracle, nsteps):
+    case, fx = _case(oracle, nsteps)
+    rot, lib, olib = case.rotor(0), emul_lib(), oracle.load()
+    d, p = rot.dims(), rot.params()
+    dt, nu = 0.0031, fx["config"]["kinematicVisc"]
+    dims = (rot.nb, rot.ns, rot.nNwake, rot.nFwake, d["rowNear"], d["rowFar"])
+    waN, waF = _stack(rot, "waN"), _stack(rot, "waF")
+    lib.emul_age_wake(*dims, dt, p["omegaSlow"], waN.ctypes.data, waF.ctypes.data)
+    olib.orc_rotor_age_wake(rot.h, dt)
+    assert np.array_equal(waN, _stack(rot, "waN")) and np.array_equal(waF, _stack(rot, "waF"))
+    lib.emul_dissipate_wake(*dims, p["apparentViscCoeff"], p["decayCoeff"], dt, nu, waN.ctypes.data, waF.ctypes.data)
+    olib.orc_rotor_dissipate_wake(rot.h, dt, nu)
+    assert np.array_equal(waN, _stack(rot, "waN")) and np.array_equal(waF, _stack(rot, "waF"))
+    if rot.nFwake and d["rowFar"] <= rot.nFwake:
+        before = waF.copy()
+        lib.emul_strain_wake(rot.nb, rot.nFwake, d["rowFar"], waF.ctypes.data)
+        olib.orc_rotor_strain_wake(rot.h)
+        assert np.array_equal(waF, _stack(rot, "waF")) and not np.array_equal(waF, before)
+
+
+@pytest.mark.parametrize("axisym", [1, 0])
+def test_skew_kernel(oracle, axisym):
+    case, _ = _case(oracle, 4, axisymmetrySwitch=axisym)
+    rot, lib = case.rotor(0), emul_lib()
+    d, p = rot.dims(), rot.params()
+    assert d["rowNear"] == 3
+    waN = _stack(rot, "waN")
+    lib.emul_calc_skew(rot.nb, p["nbConvect"], axisym, rot.ns, rot.nNwake, d["rowNear"], waN.ctypes.data)
+    oracle.load().orc_rotor_calc_skew(rot.h)
+    ref = _stack(rot, "waN")
+    assert np.array_equal(waN, ref)
+    assert np.any(ref[:, :, 2:, 49] > 0) and np.all(ref[:, :, :2, 49] == 0)
+
+
+def test_burst_kernel(oracle):
+    case, _ = _case(oracle, 15, wakeTruncateNt=14)
+    rot, lib, olib = case.rotor(0), emul_lib(), oracle.load()
+    d = rot.dims()
+    olib.orc_burst_pair.restype = C.c_int
+    olib.orc_burst_pair.argtypes = [vp, vp, f64]
+    waF = _stack(rot, "waF")
+    row0 = d["rowFar"] - 1
+    skews = []
+    for ib in range(rot.nb):
+        seg = waF[ib, row0:, 3:6] - waF[ib, row0:, 0:3]
+        cosang = np.einsum("ij,ij->i", seg[:-1], -seg[1:]) / (np.linalg.norm(seg[:-1], axis=1) * np.linalg.norm(seg[1:], axis=1))
+        skews += list(np.abs(np.arccos(np.clip(cosang, -1, 1)) - np.pi) / np.pi)
+    sk = np.sort(skews)
+    k = int(np.argmax(np.diff(sk)))
+    limit = 0.5 * (sk[k] + sk[k + 1])
+    ref = waF.copy()
+    for ib in range(rot.nb):
+        for i in range(row0, rot.nFwake - 1):
+            if olib.orc_burst_pair(waF[ib, i].ctypes.data, waF[ib, i + 1].ctypes.data, limit):
+                ref[ib, i, 9] = ref[ib, i + 1, 9] = 0.77
+    got = waF.copy()
+    lib.emul_burst_wake(rot.nb, rot.nFwake, d["rowFar"], limit, 0.77, got.ctypes.data)
+    assert np.array_equal(got, ref)
+    n_burst = int(np.sum(ref[:, :, 9] != waF[:, :, 9]))
+    assert 2 <= n_burst < rot.nb * rot.nFwake
+    # rowFar = nFwake (one active filament) and rowFar > nFwake (none): nothing to do, nothing touched
+    for rowFar in (rot.nFwake, rot.nFwake + 1):
+        got = waF.copy()
+        lib.emul_burst_wake(rot.nb, rot.nFwake, rowFar, 0.0, 0.77, got.ctypes.data)
+        assert np.array_equal(got, waF)
+
+
+def _rotations(oracle, nb, axis):
+    olib = oracle.load()
+    olib.orc_getTransformAxis.argtypes = [f64, vp, vp]
+    T, rotate = np.zeros((nb, 9)), np.zeros(nb, dtype=np.int32)
+    two_pi = 2.0 * (np.arctan(1.0) * 4.0)
+    for ib in range(1, nb):
+        off = two_pi / nb * ib
+        rotate[ib] = abs(off) > np.finfo(float).eps
+        olib.orc_getTransformAxis(off, np.ascontiguousarray(axis).ctypes.data, T[ib].ctypes.data)
+    return T, rotate
+
+
+@pytest.mark.parametrize("gen,axisym", [(0, 1), (2, 1), (3, 0)])
+def test_prescribed_wake_kernels(oracle, gen, axisym):
+    """pf_fit_kernel + pf_helix_kernel against rotor%updatePrescribedWake of the oracle over three successive updates of
+    both record sets: records of every blade and the fit parameters bit-identical (libm's cos / sin on both sides)."""
+    case, _ = _case(oracle, 15, prescWakeAfterTruncNt=2, prescWakeGenNt=gen, axisymmetrySwitch=axisym)
+    rot, lib, olib = case.rotor(0), emul_lib(), oracle.load()
+    d, p = rot.dims(), rot.params()
+    T, rotate = _rotations(oracle, rot.nb, p["shaftAxis"])
+    hub = np.ascontiguousarray(p["hubCoords"])
+    for pred in (False, True):
+        helix = np.zeros((rot.nb, 2))
+        for ib in range(rot.nb):
+            olib.orc_rotor_get_pfHelix(rot.h, ib, int(pred), helix[ib].ctypes.data)
+        wapF = _stack(rot, "wapF", pred)
+        assert np.all(np.abs(wapF[:, :, 12]) > 0)
+        for rep in range(3):
+            dt = 0.0137 * (rep + 1)
+            waF = _stack(rot, "waF", pred)
+            rc = lib.emul_updatePrescribedWake(rot.nb, p["nbConvect"], axisym, rot.nFwake, d["rowFar"], gen, p["omegaSlow"] * dt,
+                                               hub.ctypes.data, T.ctypes.data, rotate.ctypes.data, waF.ctypes.data,
+                                               wapF.ctypes.data, helix.ctypes.data)
+            assert rc == 0
+            assert olib.orc_rotor_updatePrescribedWake(rot.h, dt, b"P" if pred else b"C") == 0
+            assert np.array_equal(wapF, _stack(rot, "wapF", pred)), (pred, rep)
+            for ib in range(rot.nb):
+                ref = np.zeros(2)
+                olib.orc_rotor_get_pfHelix(rot.h, ib, int(pred), ref.ctypes.data)
+                assert np.array_equal(helix[ib], ref), (pred, rep, ib)
+
+
+@pytest.mark.parametrize("nterms,coef,div", [(3, [23.0, -16.0, 5.0], 12.0), (4, [55.0, -59.0, 37.0, -9.0], 24.0),
+                                             (3, [5.0, 8.0, -1.0], 12.0), (4, [9.0, 19.0, -5.0, 1.0], 24.0), (1, [1.0], 1.0)])
+def test_lincomb_kernel(nterms, coef, div):
+    """rec_lincomb_kernel = the multistep formulas of fdScheme 4 / 5 (main.f90:1160-1172, :1222-1231, :1309-1325, :1370-1381),
+    left to right, unfused, dst allowed to be the first source; n not a multiple of the block size."""
+    rng = np.random.default_rng(nterms)
+    n = 3 * 7 * 17 * 2 + 1
+    src = [rng.standard_normal(n) for _ in range(4)]
+    want = coef[0] * src[0]
+    for k in range(1, nterms):
+        want = want + coef[k] * src[k]
+    want = want / div
+    dst = src[0]                                       # in place, like vel = (23*vel - 16*vel2 + 5*vel1)/12
+    guard = src[1].copy()
+    c = np.array(coef + [0.0] * (4 - nterms))
+    emul_lib().emul_lincomb(n, nterms, src[0].ctypes.data, src[1].ctypes.data, src[2].ctypes.data, src[3].ctypes.data,
+                            c.ctypes.data, div, dst.ctypes.data)
+    assert np.array_equal(dst, want) and np.array_equal(src[1], guard)

@@ -330,9 +330,8 @@ def test_wake_burst_staged_orchestration_equals_inline_time_loop(oracle, fd):
 
 
 # ------------------------------------------------------------ bodies shared by the GPU tests and their CPU emulation
-# (tests/test_zzz_gpu_first_run.py calls them with a volcanor_b200.Context; here they run on EmulatedWakeContext:
-# the host build of the product's pfwake.cuh driven like the kernels, so what the GPU tests upload, call and compare is
-# exercised without a GPU)
+# (tests/test_zzz_gpu_first_run.py calls them with a volcanor_b200.Context; here they run on EmulatedWakeContext: the
+# product's kernels compiled for the host, so what the GPU tests upload, call and compare is exercised without a GPU)
 
 def check_update_prescribed_wake(ctx, oracle, gen, axisym):
     from tests.test_zz_gpu_cp_stage import _define, _developed
@@ -428,12 +427,12 @@ def check_calc_skew(ctx, oracle, axisym):
 
 
 class EmulatedWakeContext:
-    """Stand-in for volcanor_b200.Context: its own copies of the far-wake records, the g++ build of pfwake.cuh for the work."""
+    """Stand-in for volcanor_b200.Context: its own copies of the wake records; the work is done by the product's KERNELS
+    compiled for the host and run thread by thread (tests/native/kernels_emul.cpp, tests/test_kernels_emul.py)."""
 
     def __init__(self):
-        self.lib = _pf_host()
-        self.lib.pf_host_burst.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
-        self.lib.pf_host_burst.restype = None
+        from tests.test_kernels_emul import emul_lib
+        self.lib = emul_lib()
         self.r = {}
 
     def rotor_define(self, ir, nb, nc, ns, nNwake, nFwake, surfaceType=1):
@@ -466,9 +465,7 @@ class EmulatedWakeContext:
     def rotor_calc_skew(self, ir):
         r = self.r[ir]
         ns, nNwake = r["waN"].shape[2], r["waN"].shape[3]
-        self.lib.pf_host_skew.argtypes = [C.c_int] * 6 + [C.c_void_p]
-        self.lib.pf_host_skew.restype = None
-        self.lib.pf_host_skew(r["nb"], r["nbConvect"], r["axisym"], ns, nNwake, r["rowNear"], r["waN"][0].ctypes.data)
+        self.lib.emul_calc_skew(r["nb"], r["nbConvect"], r["axisym"], ns, nNwake, r["rowNear"], r["waN"][0].ctypes.data)
 
     def rotor_put_fwake(self, ir, ib, waF, predicted=False):
         self.r[ir]["waF"][int(predicted), ib] = waF
@@ -491,22 +488,22 @@ class EmulatedWakeContext:
             off = two_pi / nb * ib
             rotate[ib] = abs(off) > np.finfo(float).eps
             olib.orc_getTransformAxis(off, r["axis"].ctypes.data, T[ib].ctypes.data)
-        rc = self.lib.pf_host_update(nb, r["nbConvect"], r["axisym"], r["nFwake"], r["rowFar"], prescWakeGenNt, deltaPsi,
+        rc = self.lib.emul_updatePrescribedWake(nb, r["nbConvect"], r["axisym"], r["nFwake"], r["rowFar"], prescWakeGenNt, deltaPsi,
                                      r["hub"].ctypes.data, T.ctypes.data, rotate.ctypes.data, r["waF"][s].ctypes.data,
                                      r["wapF"][s].ctypes.data, r["helix"][s].ctypes.data)
         assert rc == 0
 
     def rotor_burst_wake(self, ir, skewLimit, largeCoreRadius):
         r = self.r[ir]
-        self.lib.pf_host_burst(r["nb"], r["nFwake"], r["rowFar"], skewLimit, largeCoreRadius, r["waF"][0].ctypes.data)
+        self.lib.emul_burst_wake(r["nb"], r["nFwake"], r["rowFar"], skewLimit, largeCoreRadius, r["waF"][0].ctypes.data)
 
 
 @pytest.mark.parametrize("gen,axisym", [(0, 1), (2, 0)])
-def test_body_of_the_gpu_update_test_on_the_host_build(oracle, gen, axisym):
+def test_body_of_the_gpu_update_test_on_emulated_kernels(oracle, gen, axisym):
     check_update_prescribed_wake(EmulatedWakeContext(), oracle, gen, axisym)
 
 
-def test_body_of_the_gpu_burst_test_on_the_host_build(oracle):
+def test_body_of_the_gpu_burst_test_on_emulated_kernels(oracle):
     fx = json.loads((GOLDEN / "elevateTest.json").read_text())
     g = fx["geom"][0]
     g["nNwake"], g["wakeTruncateNt"], g["skewLimit"] = 6, 14, 0.004
@@ -514,7 +511,7 @@ def test_body_of_the_gpu_burst_test_on_the_host_build(oracle):
 
 
 @pytest.mark.parametrize("axisym", [1, 0])
-def test_body_of_the_gpu_skew_test_on_the_host_build(oracle, axisym):
+def test_body_of_the_gpu_skew_test_on_emulated_kernels(oracle, axisym):
     check_calc_skew(EmulatedWakeContext(), oracle, axisym)
 
 

@@ -46,7 +46,11 @@ constexpr double kSeedRelErr = 9.5367431640625e-07;  // 2^-20 >= measured max 9.
 template <bool FAST>
 __device__ __forceinline__ double rsqrt_fp64(double x) {
   double y;
+#if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/emul): an exact seed in place of MUFU.RSQ64H
+  y = 1.0 / std::sqrt(x);
+#else
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#endif
   const double t = y * y;
   const double e = fma(-x, t, 1.0);
   if (FAST) return fma(y, 0.5 * e, y);
@@ -66,7 +70,12 @@ __device__ __forceinline__ double rsqrt_fp64(double x) {
 #define VLC_GUARD_HI 1  // 0 = select both words (r01e and earlier)
 #endif
 __device__ __forceinline__ void guard_scale(double& sc, double c2) {
-#if VLC_GUARD_HI
+#if defined(__CUDA_EMUL__)  // host build of the tests: the same integer compare and high-word select in C++
+  if (!(__double_as_longlong(c2) > 0x3970000000000000LL)) {
+    long long b = __double_as_longlong(sc) & 0xFFFFFFFFLL;
+    std::memcpy(&sc, &b, sizeof sc);
+  }
+#elif VLC_GUARD_HI
   asm("{\n\t"
       ".reg .pred p;\n\t"
       ".reg .b32 lo, hi;\n\t"
@@ -134,6 +143,7 @@ __device__ __forceinline__ void pair_accumulate(const Src& s, double px, double 
 }
 
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----
+#if !defined(__CUDA_EMUL__)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -168,5 +178,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+#endif  // !__CUDA_EMUL__
 
 }  // namespace vlc
