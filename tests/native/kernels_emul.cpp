@@ -80,6 +80,60 @@ int emul_updatePrescribedWake(int nb, int nbConvect, int axisym, int nFwake, int
   return 0;
 }
 
+// = vlc_rotor_assignshed
+void emul_assignshed(int edge, int nb, int nc, int ns, int nNwake, int rowNear, const double* wiP, double* waN) {
+  emul_launch(blocks_for((long long)nb * ns, 128), 1, 128, vlc::rec_assignshed_kernel, edge, nb, nc, ns, nNwake, rowNear, wiP, waN);
+}
+
+// = vlc_rotor_convectwake (without the prescribed far wake: emul_updatePrescribedWake follows it like in g_convect)
+void emul_convectwake(int predicted, int nb, int nbConvect, int axisym, int duct, int ns, int nNwake, int nFwake, int rowNear,
+                      int rowFar, double dt, const double* hub, const double* T9, const int* rotate, const double* velN,
+                      const double* velF, double* waN, double* waF) {
+  const long long nfar = std::max(0, nFwake - rowFar + 1), nact = std::max(0, nNwake - rowNear + 1);
+  {
+    const long long n = (long long)nbConvect * ((long long)(ns + 1) * nNwake + nfar);
+    emul_launch(blocks_for(n, 256), 1, 256, vlc::rec_convect_kernel, predicted, nbConvect, ns, nNwake, nFwake, rowNear, rowFar, dt,
+                velN, velF, waN, waF);
+  }
+  {
+    const long long n = (long long)nbConvect * (ns * nact + std::max(0LL, nfar - 1));
+    if (n > 0) {
+      emul_launch(blocks_for(n, 256), 1, 256, vlc::rec_continuity_kernel, 0, nbConvect, ns, nNwake, nFwake, rowNear, rowFar, waN, waF);
+      if (!predicted && duct == 1)
+        emul_launch(blocks_for(n, 256), 1, 256, vlc::rec_continuity_kernel, 1, nbConvect, ns, nNwake, nFwake, rowNear, rowFar, waN,
+                    waF);
+    }
+  }
+  if (axisym == 1 && nb > 1) {
+    std::vector<vlc::AxiT> Ts(nb);
+    for (int ib = 0; ib < nb; ++ib) {
+      for (int k = 0; k < 9; ++k) Ts[ib].T[k] = T9[9 * ib + k];
+      Ts[ib].rotate = rotate[ib];
+    }
+    const long long n = (long long)(nb - 1) * (ns * nact + nfar);
+    if (n > 0)
+      emul_launch(blocks_for(n, 128), 1, 128, vlc::rec_axisym_kernel, nb, ns, nNwake, nFwake, rowNear, rowFar,
+                  (const vlc::AxiT*)Ts.data(), hub[0], hub[1], hub[2], waN, waF);
+  }
+}
+
+// = vlc_rotor_rollup: waN is replaced by its shifted copy like the swap of the two device buffers
+void emul_rollup(int nb, int ns, int nNwake, int nFwake, int rowFar, int rollupStart, int rollupEnd, int sgnPositive,
+                 int suppressFwake, double* waN, double* waF) {
+  int rowFarNext = rowFar - 1;
+  if (nFwake > 0 && rowFarNext == 0) {
+    emul_launch(blocks_for(nb * vlc::kFw, 64), 1, 64, vlc::rec_shiftFwake_kernel, nb, nFwake, waF);
+    rowFarNext = 1;
+  }
+  emul_launch(blocks_for(nb, 32), 1, 32, vlc::rec_rollup_kernel, nb, ns, nNwake, nFwake, rollupStart, rollupEnd, sgnPositive,
+              suppressFwake, rowFarNext, (const double*)waN, waF);
+  const size_t total = (size_t)nb * nNwake * ns * vlc::kVr;
+  std::vector<double> alt(total);
+  emul_launch(blocks_for((long long)total, 256), 1, 256, vlc::rec_shiftwake_kernel, (long long)nb * ns, nNwake, (const double*)waN,
+              alt.data());
+  std::memcpy(waN, alt.data(), total * sizeof(double));
+}
+
 // = vlc_rotor_wakevel_lincomb on one array (the caller passes the near- or the far-wake arrays)
 void emul_lincomb(long long n, int nterms, const double* s0, const double* s1, const double* s2, const double* s3,
                   const double* coef, double divisor, double* dst) {

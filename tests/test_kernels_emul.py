@@ -28,7 +28,10 @@ def emul_lib():
            "emul_burst_wake": (None, [i32] * 3 + [f64, f64, vp]),
            "emul_calc_skew": (None, [i32] * 6 + [vp]),
            "emul_updatePrescribedWake": (i32, [i32] * 6 + [f64] + [vp] * 6),
-           "emul_lincomb": (None, [C.c_longlong, i32, vp, vp, vp, vp, vp, f64, vp])}
+           "emul_lincomb": (None, [C.c_longlong, i32, vp, vp, vp, vp, vp, f64, vp]),
+           "emul_assignshed": (None, [i32] * 6 + [vp, vp]),
+           "emul_convectwake": (None, [i32] * 10 + [f64] + [vp] * 7),
+           "emul_rollup": (None, [i32] * 9 + [vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
         getattr(lib, k).argtypes = args
@@ -70,6 +73,43 @@ def test_emulation_agrees_with_the_oracle_on_kernels_that_ran_on_a_b200(oracle, 
         lib.emul_strain_wake(rot.nb, rot.nFwake, d["rowFar"], waF.ctypes.data)
         olib.orc_rotor_strain_wake(rot.h)
         assert np.array_equal(waF, _stack(rot, "waF")) and not np.array_equal(waF, before)
+
+
+@pytest.mark.parametrize("nsteps,axisym", [(4, 1), (7, 1), (12, 1), (12, 0)])
+def test_emulated_convect_rollup_assignshed_agree_with_the_oracle(oracle, nsteps, axisym):
+    """rec_convect / rec_continuity / rec_axisym, rec_shiftFwake / rec_rollup / rec_shiftwake, rec_assignshed (all green on a
+    B200 through the C ABI) in the launch sequences of vlc_rotor_convectwake / _rollup / _assignshed: 'C' and 'P' (the
+    predictor's loop quirk), growing wake, rolled-up wake with free far rows, full far wake (shiftFwake)."""
+    case, fx = _case(oracle, nsteps, axisymmetrySwitch=axisym)
+    rot, lib, olib = case.rotor(0), emul_lib(), oracle.load()
+    d, p = rot.dims(), rot.params()
+    T, rotate = _rotations(oracle, rot.nb, p["shaftAxis"])
+    hub = np.ascontiguousarray(p["hubCoords"])
+    dt = abs(case.dt) if hasattr(case, "dt") else 0.0007
+    velN, velF = _stack(rot, "vel", 0), _stack(rot, "vel", 4)
+    assert np.any(velN != 0)
+    for pred in (True, False):
+        waN, waF = _stack(rot, "waN", pred), _stack(rot, "waF", pred)
+        lib.emul_convectwake(int(pred), rot.nb, p["nbConvect"], axisym, p["ductSwitch"], rot.ns, rot.nNwake, rot.nFwake,
+                             d["rowNear"], d["rowFar"], dt, hub.ctypes.data, T.ctypes.data, rotate.ctypes.data, velN.ctypes.data,
+                             velF.ctypes.data, waN.ctypes.data, waF.ctypes.data)
+        before = _stack(rot, "waN", pred)
+        olib.orc_rotor_convectwake(rot.h, 0, dt, b"P" if pred else b"C")
+        assert np.array_equal(waN, _stack(rot, "waN", pred)) and np.array_equal(waF, _stack(rot, "waF", pred)), pred
+        assert pred or not np.array_equal(waN, before)      # the predictor's near-wake loop only visits row 1 (quirk C1)
+    wiP = _stack(rot, "wiP")
+    for edge in (b"TE", b"LE"):
+        waN = _stack(rot, "waN")
+        lib.emul_assignshed(int(edge == b"TE"), rot.nb, rot.nc, rot.ns, rot.nNwake, d["rowNear"], wiP.ctypes.data, waN.ctypes.data)
+        olib.orc_rotor_assignshed(rot.h, edge)
+        assert np.array_equal(waN, _stack(rot, "waN")), edge
+    if d["rowNear"] == 1:
+        waN, waF = _stack(rot, "waN"), _stack(rot, "waF")
+        sgn = int(np.copysign(1.0, p["Omega"] * p["theta0"]) > np.finfo(float).eps)
+        lib.emul_rollup(rot.nb, rot.ns, rot.nNwake, rot.nFwake, d["rowFar"], p["rollupStart"], p["rollupEnd"], sgn,
+                        p["suppressFwakeSwitch"], waN.ctypes.data, waF.ctypes.data)
+        olib.orc_rotor_rollup(rot.h)
+        assert np.array_equal(waN, _stack(rot, "waN")) and np.array_equal(waF, _stack(rot, "waF"))
 
 
 @pytest.mark.parametrize("axisym", [1, 0])
