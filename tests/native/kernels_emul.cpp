@@ -134,6 +134,39 @@ void emul_rollup(int nb, int ns, int nNwake, int nFwake, int rowFar, int rollupS
   std::memcpy(waN, alt.data(), total * sizeof(double));
 }
 
+// ---- source packing (pack.cuh) + the pair arithmetic of the sweeps (vlc_device.cuh: pair_accumulate with an exact seed
+// in place of MUFU.RSQ64H), summed record by record in enumeration order: what a flat sweep computes, up to summation order
+
+// = pack_bound (what = 3) / pack_chord (what = 4) of capi.cu; rec holds (2*nc*ns + ns)*nb records of 12 doubles
+void emul_pack_wing_subset(int what, int nb, int nc, int ns, const double* wiP, double* rec) {
+  const long long per_blade = 2LL * nc * ns + ns, cnt = 2LL * nc * ns, wiP_blade = (long long)nc * ns * vlc::kWp;
+  const int mask = what == 3 ? 0xA : 0x5;
+  const double te_sign = what == 3 ? -1.0 : 1.0;
+  emul_launch(blocks_for(cnt, 256), (unsigned)nb, 256, vlc::pack_rings_kernel, wiP, vlc::kWp, nc, 0, nc, ns, mask, 2, 1.0, 0, rec,
+              wiP_blade, per_blade);
+  emul_launch(blocks_for(ns, 128), (unsigned)nb, 128, vlc::pack_rings_kernel, wiP, vlc::kWp, nc, nc - 1, 1, ns, 0x2, 1, te_sign, 0,
+              rec + (size_t)cnt * vlc::kSrcDoubles, wiP_blade, per_blade);
+}
+
+// = the prescribed-wake part of pack_rotor: 240 records per blade
+void emul_pack_pfwake(int nb, const double* wapF, double* rec) {
+  emul_launch(blocks_for(240, 128), (unsigned)nb, 128, vlc::pack_fwake_kernel, wapF, 0, 240, rec, (long long)240 * vlc::kFw,
+              (long long)240);
+}
+
+void emul_vind_records(long long n, const double* rec, long long m, const double* P, double* V) {
+  for (long long t = 0; t < m; ++t) {
+    double vx = 0.0, vy = 0.0, vz = 0.0;
+    for (long long k = 0; k < n; ++k) {
+      const vlc::Src s = vlc::load_src(rec + k * vlc::kSrcDoubles);
+      vlc::pair_accumulate<false>(s, P[3 * t], P[3 * t + 1], P[3 * t + 2], vx, vy, vz);
+    }
+    V[3 * t] = vx;
+    V[3 * t + 1] = vy;
+    V[3 * t + 2] = vz;
+  }
+}
+
 // = vlc_rotor_wakevel_lincomb on one array (the caller passes the near- or the far-wake arrays)
 void emul_lincomb(long long n, int nterms, const double* s0, const double* s1, const double* s2, const double* s3,
                   const double* coef, double divisor, double* dst) {

@@ -31,7 +31,10 @@ def emul_lib():
            "emul_lincomb": (None, [C.c_longlong, i32, vp, vp, vp, vp, vp, f64, vp]),
            "emul_assignshed": (None, [i32] * 6 + [vp, vp]),
            "emul_convectwake": (None, [i32] * 10 + [f64] + [vp] * 7),
-           "emul_rollup": (None, [i32] * 9 + [vp, vp])}
+           "emul_rollup": (None, [i32] * 9 + [vp, vp]),
+           "emul_pack_wing_subset": (None, [i32] * 4 + [vp, vp]),
+           "emul_pack_pfwake": (None, [i32, vp, vp]),
+           "emul_vind_records": (None, [C.c_longlong, vp, C.c_longlong, vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
         getattr(lib, k).argtypes = args
@@ -219,3 +222,50 @@ def test_lincomb_kernel(nterms, coef, div):
     emul_lib().emul_lincomb(n, nterms, src[0].ctypes.data, src[1].ctypes.data, src[2].ctypes.data, src[3].ctypes.data,
                             c.ctypes.data, div, dst.ctypes.data)
     assert np.array_equal(dst, want) and np.array_equal(src[1], guard)
+
+
+def _vind(lib, rec, P):
+    rec, P = np.ascontiguousarray(rec), np.ascontiguousarray(P)
+    V = np.empty_like(P)
+    lib.emul_vind_records(rec.size // 12, rec.ctypes.data, P.shape[0], P.ctypes.data, V.ctypes.data)
+    return V
+
+
+def test_pack_kernels_and_pair_arithmetic_bound_chordwise_prescribed(oracle):
+    """pack_rings_kernel with the filament masks of pack_bound (vf2 + vf4 - TE; green on a B200) and pack_chord (vf1 + vf3 +
+    TE; not yet run on a GPU), pack_fwake_kernel on the 240 prescribed filaments per blade, evaluated with the sweeps' pair
+    arithmetic (pair_accumulate, exact seed): against the oracle's source loops (classdef.f90:1376-1418, :1471-1476) at the
+    per-call bar 1e-12 of the velocity scale; bound + chordwise = the whole wing."""
+    case, _ = _case(oracle, 16, prescWakeAfterTruncNt=2)
+    rot, lib = case.rotor(0), emul_lib()
+    wiP = _stack(rot, "wiP")
+    rng = np.random.default_rng(2)
+    span = float(np.max(np.abs(wiP[:, :, :, 0:3])))
+    P = np.concatenate([rng.uniform(-1.2, 1.2, (60, 3)) * span, wiP[0, ::3, 0, 64:67] + [0.0, 0.0, 0.02],
+                        wiP[2, ::5, 1, 0:3]])                   # random, just above collocation points, on ring corners
+    per_blade = 2 * rot.nc * rot.ns + rot.ns
+    got = {}
+    for what in (3, 4):
+        rec = np.zeros((rot.nb * per_blade, 12))
+        lib.emul_pack_wing_subset(what, rot.nb, rot.nc, rot.ns, wiP.ctypes.data, rec.ctypes.data)
+        assert np.all(np.any(rec[:, 0:6] != 0, axis=1))           # every record written
+        got[what] = _vind(lib, rec, P)
+        ref = rot.vind_points(what, P)
+        scale = 50.0 * float(np.abs(ref).max())
+        assert np.max(np.abs(got[what] - ref)) < 1e-12 * scale, (what, float(np.max(np.abs(got[what] - ref))) / scale)
+    whole = rot.vind_points(0, P)
+    assert np.max(np.abs(got[3] + got[4] - whole)) < 1e-12 * 50.0 * float(np.abs(whole).max())
+    # the prescribed helix alone: vind_bywake with and without it differ by exactly its 240 x nb filaments
+    wapF = _stack(rot, "wapF")
+    assert np.all(np.abs(wapF[:, :, 12]) > 0)
+    rec = np.zeros((rot.nb * 240, 12))
+    lib.emul_pack_pfwake(rot.nb, wapF.ctypes.data, rec.ctypes.data)
+    Pw = np.concatenate([rng.uniform(-1.5, 1.5, (60, 3)) * float(np.max(np.abs(wapF[:, :, 0:2]))), wapF[0, ::11, 0:3]])
+    helix = _vind(lib, rec, Pw)
+    with_helix = rot.vind_points(1, Pw)
+    for ib in range(rot.nb):
+        rot.wapF(ib)[:, 12] = 0.0                                 # abs(gam) > eps rule: the helix drops out
+    without = rot.vind_points(1, Pw)
+    scale = 50.0 * float(np.abs(with_helix).max())
+    assert np.max(np.abs(helix - (with_helix - without))) < 1e-12 * scale
+    assert np.max(np.abs(helix)) > 1e-4 * float(np.abs(with_helix).max())
