@@ -19,7 +19,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from tests.test_prescribed_wake import _with_prescribed_wake
+from tests.test_prescribed_wake import _with_prescribed_wake, rotor_fx
 from tests.test_cp_stage_host import _mut
 from tests.test_zz_gpu_cp_stage import (TOL_HISTORY, _cp_hooks, _short_caradonna, _step, cctx,  # noqa: F401  (fixture)
                                         check_cp_stage_vs_cpu_driver)
@@ -32,7 +32,7 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 def test_prescribed_wake_case_vs_cpu_driver(cctx, oracle, gen, mode):  # noqa: F811
     """resident: the helix is made on the device (vlc_rotor_updatePrescribedWake after each vlc_rotor_convectwake);
     per-sweep: the driver makes it (rotor%updatePrescribedWake) and the shim uploads it with the wake (vlc_rotor_put_pfwake)."""
-    fx = json.loads((GOLDEN / "elevateTest.json").read_text())          # 5 blades, axisymmetric
+    fx = rotor_fx(small=(mode != "resident+cp"))                         # elevateTest (5 blades) once, else the small rotor
     _with_prescribed_wake(gen)(fx)                                       # prescWakeNt = 12
     fx["config"]["rotorForcePlot"] = 1
     a, b = oracle.Case(fx), oracle.Case(fx)
@@ -63,7 +63,7 @@ def test_prescribed_wake_case_vs_cpu_driver(cctx, oracle, gen, mode):  # noqa: F
         assert np.all(np.abs(wa[:, 12]) > 0)
         assert np.max(np.abs(wb[:, :6] - wa[:, :6])) < 1e-9 * np.max(np.abs(wa[:, :6]))
         assert np.max(np.abs(wb[:, 12] - wa[:, 12])) < 1e-9 * np.max(np.abs(wa[:, 12]))
-    print(f"elevateTest + prescribed far wake (prescWakeGenNt = {gen}), 20 steps, {mode}: max rel err CT {worst[0]:.3e}, "
+    print(f"{fx['name']} ({ra.nb} blades) + prescribed far wake (prescWakeGenNt = {gen}), 20 steps, {mode}: max rel err CT {worst[0]:.3e}, "
           f"gamVec {worst[1]:.3e}")
     assert max(worst) < TOL_HISTORY, worst
     lib.case_gpu_hooks_free(h)
@@ -75,7 +75,7 @@ def test_prescribed_filaments_are_sources_of_vind_bywake(cctx, oracle, predicted
     loop at the per-call bar (1e-12 of the velocity scale); without vlc_rotor_put_pfwake the difference is the helix's own
     contribution, so the comparison is not vacuous."""
     from tests.test_zz_gpu_cp_stage import TOL, _define, _developed
-    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    fx = rotor_fx()
     _with_prescribed_wake(0)(fx)
     case = _developed(oracle, fx, 16)
     rot = case.rotor(0)
@@ -136,7 +136,7 @@ def test_update_prescribed_wake_error_behaviour(cctx):  # noqa: F811
 
 
 def _burst_case():
-    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+    fx = rotor_fx()
     g = fx["geom"][0]
     g["nNwake"], g["wakeTruncateNt"], g["skewLimit"] = 6, 14, 0.004
     fx["config"]["wakeBurst"] = 2
@@ -168,7 +168,7 @@ def test_wake_burst_resident_vs_cpu_driver(cctx, oracle):  # noqa: F811
     for ib in range(a.rotor(0).nb):
         assert np.array_equal(a.rotor(0).waF(ib)[:, 9] == chord, b.rotor(0).waF(ib)[:, 9] == chord)   # the same filaments burst
     assert sum(int(np.sum(a.rotor(0).waF(ib)[:, 9] == chord)) for ib in range(a.rotor(0).nb)) >= 2
-    print(f"elevateTest + wakeBurst = 2 (skewLimit 0.004), 18 steps, resident: max rel err CT {worst:.3e}")
+    print(f"small rotor + wakeBurst = 2 (skewLimit 0.004), 18 steps, resident: max rel err CT {worst:.3e}")
     assert worst < TOL_HISTORY, worst
     lib.case_gpu_hooks_free(h)
 

@@ -10,7 +10,8 @@
 // latency-bound, a few microseconds, but they keep the far rows and the helix from crossing the bus in each stage.
 // Arithmetic: explicit unfused IEEE operations in the reference's statement order; the only calls whose low bits may
 // differ from a CPU run are cos / sin / atan2 (CUDA's vs libm's, <= 2 ulp each).  The routines are `VLC_HD` (host +
-// device): tests/native/pfwake_host.cpp compiles THIS file with g++, where it is bit-identical to the oracle.
+// device): tests/native/kernels_emul.cpp compiles THIS file and the kernels that call it with g++, where they are
+// bit-identical to the oracle (tests/test_kernels_emul.py).
 #pragma once
 
 #include "cp_stage.cuh"  // VLC_HD, the unfused mul / add / sub / quo / root
