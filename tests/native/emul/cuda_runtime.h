@@ -16,6 +16,8 @@
 #define __constant__ static
 #define __shared__ static
 #define __CUDA_EMUL__ 1
+#define __align__(n) alignas(n)
+static inline void __syncthreads() {}
 
 struct emul_dim3 {
   unsigned x = 1, y = 1, z = 1;

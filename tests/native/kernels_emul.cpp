@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../volcanor_b200/csrc/wake_records.cuh"
+#include "../../volcanor_b200/csrc/bs_lattice.cuh"
 
 namespace {
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -165,6 +166,47 @@ void emul_vind_records(long long n, const double* rec, long long m, const double
     V[3 * t + 1] = vy;
     V[3 * t + 2] = vz;
   }
+}
+
+// ---- the dominant kernel: bs_lattice_kernel<W, T, 128, 3, .> on the strip records pack_rings_shared_kernel<W> makes from
+// one blade's near-wake ring records (rows i0 .. i0+nrows-1 of waN(nNwake, ns), ns a multiple of W), one split; plus the
+// flat remainder (the last column's outer streamwise edges, pack_rings_kernel mask 0x4 with the wake rule) through the
+// pair arithmetic.  V = what vind_bywake gives for a blade without a far wake, regrouped node by node and edge by edge.
+}  // extern "C"
+
+template <int W, int T>
+static int lattice_vind(const double* waN, int nNwake, int ns, int i0, int nrows, long long m, const double* P, double* V) {
+  constexpr int RD = vlc::lat_rec_doubles(W), TILE = vlc::lat_tile(W), THREADS = 128;
+  const int nstrips = ns / W;
+  const long long nrec = (long long)nstrips * (nrows + 1), npad = (nrec + TILE - 1) / TILE * TILE;
+  std::vector<double> lat((size_t)npad * RD);
+  int unmergeable = 0;
+  emul_launch(blocks_for(nrec, 128), 1, 128, vlc::pack_rings_shared_kernel<W>, waN, vlc::kVr, nNwake, i0, nrows, ns, 0, nstrips,
+              lat.data(), &unmergeable, 0LL);
+  if (npad > nrec)
+    emul_launch(blocks_for(npad - nrec, 128), 1, 128, vlc::pack_null_lat_kernel<W>, npad - nrec, lat.data() + (size_t)nrec * RD);
+  if (unmergeable) return 1;
+  std::vector<double> out(3 * (size_t)m);
+  emul_launch(blocks_for(m, THREADS * T), 1, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>, (const double*)lat.data(), npad,
+              npad, P, m, out.data(), (const int*)&unmergeable, 0);
+  std::vector<double> rem((size_t)nrows * vlc::kSrcDoubles), vrem(3 * (size_t)m);
+  emul_launch(blocks_for(nrows, 128), 1, 128, vlc::pack_rings_kernel, waN + (size_t)vlc::kVr * nNwake * (ns - 1), vlc::kVr, nNwake, i0,
+              nrows, 1, 0x4, 1, 1.0, 1, rem.data(), 0LL, 0LL);
+  emul_vind_records(nrows, rem.data(), m, P, vrem.data());
+  for (size_t k = 0; k < 3 * (size_t)m; ++k) V[k] = out[k] + vrem[k];
+  return 0;
+}
+
+extern "C" {
+
+int emul_lattice_vind(int W, int T, const double* waN, int nNwake, int ns, int i0, int nrows, long long m, const double* P,
+                      double* V) {
+  if (ns % W != 0) return 2;
+#define X(WW, TT) \
+  if (W == WW && T == TT) return lattice_vind<WW, TT>(waN, nNwake, ns, i0, nrows, m, P, V);
+  X(1, 1) X(1, 3) X(2, 2) X(3, 1) X(3, 2) X(4, 1) X(4, 2)
+#undef X
+  return 3;
 }
 
 // = vlc_rotor_wakevel_lincomb on one array (the caller passes the near- or the far-wake arrays)

@@ -34,7 +34,8 @@ def emul_lib():
            "emul_rollup": (None, [i32] * 9 + [vp, vp]),
            "emul_pack_wing_subset": (None, [i32] * 4 + [vp, vp]),
            "emul_pack_pfwake": (None, [i32, vp, vp]),
-           "emul_vind_records": (None, [C.c_longlong, vp, C.c_longlong, vp, vp])}
+           "emul_vind_records": (None, [C.c_longlong, vp, C.c_longlong, vp, vp]),
+           "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
         getattr(lib, k).argtypes = args
@@ -272,3 +273,45 @@ def test_pack_kernels_and_pair_arithmetic_bound_chordwise_prescribed(oracle):
     scale = 50.0 * float(np.abs(with_helix).max())
     assert np.max(np.abs(helix - (with_helix - without))) < 1e-12 * scale
     assert np.max(np.abs(helix)) > 1e-4 * float(np.abs(with_helix).max())
+
+
+@pytest.mark.parametrize("W,T,ns,nsteps", [(1, 1, 6, 4), (2, 2, 6, 4), (3, 1, 6, 8), (3, 2, 6, 4), (4, 1, 8, 4), (4, 2, 8, 8), (1, 3, 5, 4)])
+def test_lattice_kernel_on_the_cpu(oracle, W, T, ns, nsteps):
+    """The dominant kernel itself: pack_rings_shared_kernel<W> -> bs_lattice_kernel<W, T> (node-by-node, edge-by-edge
+    regrouping with merged strengths, strip walk with the previous row in registers, tile staging, the c2 > eps^2 guard) +
+    the flat remainder, per blade, on the near wake of a hovering rotor: against rotor%vind_bywake of the oracle at the
+    per-call bar.  Targets: random points, the wake's own nodes (every adjacent edge must drop out exactly) and points on
+    edges.  Wake still growing (rows 1, 2 inactive) and fully shed.  The reciprocal-square-root seed is exact here instead of
+    MUFU.RSQ64H's 20 bits; its refinement and everything else is the product's source."""
+    case, _ = _case(oracle, nsteps, ns=ns, wakeTruncateNt=0, nNwake=8)       # no far wake within 8 steps
+    rot, lib = case.rotor(0), emul_lib()
+    d = rot.dims()
+    assert d["rowFar"] > rot.nFwake and d["rowNear"] == max(1, 9 - nsteps)
+    nrows, i0 = rot.nNwake - d["rowNear"] + 1, d["rowNear"] - 1
+    # end of a step with every row shed: the current records are mid-update (after shiftwake the newest row's vf(4)%rVc waits
+    # for the next dissipate_wake, classdef.f90:4386-4392) and NOT mergeable -- pack_rings_shared_kernel must say so (the
+    # product then sweeps the flat enumeration); the predicted records, which the last corrector sweep used, are a lattice
+    pred = d["rowNear"] == 1
+    if pred:
+        V = np.empty((1, 3))
+        assert lib.emul_lattice_vind(W, T, np.ascontiguousarray(_stack(rot, "waN")[0]).ctypes.data, rot.nNwake, rot.ns, i0, nrows,
+                                     1, np.zeros((1, 3)).ctypes.data, V.ctypes.data) == 1
+    waN = _stack(rot, "waN", pred)
+    rng = np.random.default_rng(W * 10 + T)
+    nodes = waN[0, :, i0:, 12:15].reshape(-1, 3)                                # corner 2 of every active ring of blade 1
+    mid = 0.5 * (waN[1, :, i0:, 12:15] + waN[1, :, i0:, 24:27]).reshape(-1, 3)  # on the TE edges of blade 2
+    P = np.ascontiguousarray(np.concatenate([rng.uniform(-1.3, 1.3, (300, 3)) * float(np.abs(nodes).max()), nodes, mid[::3]]))
+    got = np.zeros_like(P)
+    for ib in range(rot.nb):
+        V = np.empty_like(P)
+        rc = lib.emul_lattice_vind(W, T, np.ascontiguousarray(waN[ib]).ctypes.data, rot.nNwake, rot.ns, i0, nrows, P.shape[0],
+                                   P.ctypes.data, V.ctypes.data)
+        assert rc == 0
+        got = got + V
+    ref = rot.vind_points(1, P, pred)
+    assert np.all(np.isfinite(got))
+    scale = 50.0 * float(np.abs(ref).max())
+    err = float(np.max(np.abs(got - ref)))
+    print(f"lattice kernel W={W} T={T} on the CPU: {P.shape[0]} targets x {rot.nb * nrows * rot.ns} rings, max error "
+          f"{err / scale * 50:.2e} of the velocity scale")
+    assert err < 1e-12 * scale, err / scale

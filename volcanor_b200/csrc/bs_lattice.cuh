@@ -36,6 +36,13 @@ __host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_nodes_pad(
 #endif
 __host__ __device__ constexpr int lat_tile(int W) { return (W <= 2 ? 64 : 32) / VLC_LAT_TILE_DIV; }  // records per shared-memory tile
 
+// the thread that issues the bulk copies of a CTA
+#if defined(__CUDA_EMUL__)
+#define VLC_PRODUCER(tid) true
+#else
+#define VLC_PRODUCER(tid) ((tid) == 0)
+#endif
+
 struct NodeQ {
   double rx, ry, rz, u;  // r = P - X, u = 1/|r|
 };
@@ -81,7 +88,12 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
                   const int* __restrict__ flag, int want) {
   if (flag != nullptr && *flag != want) return;  // uniform: the set is not mergeable -> the flat kernel does the work
   constexpr int RD = lat_rec_doubles(W), NP = lat_nodes_pad(W), TILE = lat_tile(W);
+#if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/kernels_emul.cpp): one emulated thread at a time, which
+  // stages its own tiles (VLC_PRODUCER) into a static buffer with memcpy standing in for the bulk copy
+  alignas(128) static unsigned char smem_raw[(size_t)STAGES * TILE * RD * 8 + STAGES * 8];
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   double* buf = reinterpret_cast<double*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * RD * 8);
 
@@ -93,13 +105,13 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
   const double* gsrc = lat + s_begin * RD;
   constexpr uint32_t kTileBytes = TILE * RD * 8;
 
-  if (tid == 0) {
+  if (VLC_PRODUCER(tid)) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
+  if (VLC_PRODUCER(tid)) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s)
       if (s < ntiles) {
@@ -157,7 +169,7 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
       }
     }
     __syncthreads();
-    if (tid == 0 && tile + STAGES < ntiles) {
+    if (VLC_PRODUCER(tid) && tile + STAGES < ntiles) {
       mbar_expect_tx(&bars[stage], kTileBytes);
       tma_bulk_g2s(buf + (size_t)stage * TILE * RD, gsrc + (size_t)(tile + STAGES) * TILE * RD, kTileBytes, &bars[stage]);
     }

@@ -178,6 +178,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+#else  // __CUDA_EMUL__: no barriers, the bulk copy is a memcpy that has completed when it returns
+inline void mbar_init(uint64_t*, uint32_t) {}
+inline void fence_mbar_init() {}
+inline void mbar_expect_tx(uint64_t*, uint32_t) {}
+inline void mbar_wait(uint64_t*, uint32_t) {}
+inline void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) { std::memcpy(smem_dst, gmem_src, bytes); }
 #endif  // !__CUDA_EMUL__
 
 }  // namespace vlc
