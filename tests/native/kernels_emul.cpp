@@ -209,6 +209,11 @@ int emul_lattice_vind(int W, int T, const double* waN, int nNwake, int ns, int i
   return 3;
 }
 
+// rsqrt_fp64<FAST> of vlc_device.cuh (seed modelled, refinement = the product's source)
+void emul_rsqrt(int fast, long long n, const double* x, double* y) {
+  for (long long i = 0; i < n; ++i) y[i] = fast ? vlc::rsqrt_fp64<true>(x[i]) : vlc::rsqrt_fp64<false>(x[i]);
+}
+
 // = vlc_rotor_wakevel_lincomb on one array (the caller passes the near- or the far-wake arrays)
 void emul_lincomb(long long n, int nterms, const double* s0, const double* s1, const double* s2, const double* s3,
                   const double* coef, double divisor, double* dst) {

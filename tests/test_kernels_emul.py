@@ -35,6 +35,7 @@ def emul_lib():
            "emul_pack_wing_subset": (None, [i32] * 4 + [vp, vp]),
            "emul_pack_pfwake": (None, [i32, vp, vp]),
            "emul_vind_records": (None, [C.c_longlong, vp, C.c_longlong, vp, vp]),
+           "emul_rsqrt": (None, [i32, C.c_longlong, vp, vp]),
            "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
@@ -315,3 +316,20 @@ def test_lattice_kernel_on_the_cpu(oracle, W, T, ns, nsteps):
     print(f"lattice kernel W={W} T={T} on the CPU: {P.shape[0]} targets x {rot.nb * nrows * rot.ns} rings, max error "
           f"{err / scale * 50:.2e} of the velocity scale")
     assert err < 1e-12 * scale, err / scale
+
+
+def test_rsqrt_refinement_with_a_seed_as_coarse_as_the_devices():
+    """rsqrt_fp64 (vlc_device.cuh): the emulation's seed keeps ~21 bits like MUFU.RSQ64H (measured 2^-20.06 on a B200,
+    tests/test_gpu_parity.py::test_rsqrt_seed_accuracy); the third-order step must bring it to rounding level, the
+    second-order step (opt-in precision mode) to <= 1.5 d^2, always low -- the bounds DESIGN.md section 4 states."""
+    rng = np.random.default_rng(0)
+    x = np.ascontiguousarray(np.exp(rng.uniform(np.log(1e-60), np.log(1e60), 200000)))
+    lib = emul_lib()
+    exact = 1.0 / np.sqrt(x.astype(np.longdouble))
+    for fast, bound in ((0, 4e-16), (1, 1.5 * 2.0 ** -40 * 1.3)):
+        y = np.empty_like(x)
+        lib.emul_rsqrt(fast, x.size, x.ctypes.data, y.ctypes.data)
+        rel = ((y.astype(np.longdouble) - exact) / exact).astype(np.float64)
+        assert np.max(np.abs(rel)) < bound, (fast, float(np.max(np.abs(rel))))
+        if fast:
+            assert np.max(rel) < 1e-15                               # never high: what the centring factor relies on

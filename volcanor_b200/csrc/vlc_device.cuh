@@ -46,8 +46,17 @@ constexpr double kSeedRelErr = 9.5367431640625e-07;  // 2^-20 >= measured max 9.
 template <bool FAST>
 __device__ __forceinline__ double rsqrt_fp64(double x) {
   double y;
-#if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/emul): an exact seed in place of MUFU.RSQ64H
-  y = 1.0 / std::sqrt(x);
+#if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/emul): a model of MUFU.RSQ64H -- only the high word of x
+  // is read and the result carries about 23 bits (relative error <= 2^-21 + 2^-23, the device's measured 2^-20.06 is of
+  // the same size), so that the refinement below is exercised with a seed as coarse as the real one
+  {
+    long long xb = __double_as_longlong(x) & ~0xFFFFFFFFLL;
+    double xh;
+    std::memcpy(&xh, &xb, sizeof xh);
+    y = 1.0 / std::sqrt(xh);
+    long long yb = __double_as_longlong(y) & ~0x1FFFFFFFLL;
+    std::memcpy(&y, &yb, sizeof y);
+  }
 #else
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #endif
