@@ -9,6 +9,7 @@
 
 #include "../../volcanor_b200/csrc/wake_records.cuh"
 #include "../../volcanor_b200/csrc/bs_lattice.cuh"
+#include "../../volcanor_b200/csrc/bs_sweep.cuh"
 
 namespace {
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -207,6 +208,27 @@ int emul_lattice_vind(int W, int T, const double* waN, int nNwake, int ns, int i
   X(1, 1) X(1, 3) X(2, 2) X(3, 1) X(3, 2) X(4, 1) X(4, 2)
 #undef X
   return 3;
+}
+
+// ---- the flat sweep: pack_flat_kernel (tier 1 arrays -> records, padded with null filaments to whole tiles) ->
+// bs_sweep_kernel<4, 128, 128, 3, ., FAST> with nsplit source splits -> bs_reduce_kernel (fixed-order sum of the partials)
+int emul_flat_sweep(int fast, int nsplit, long long n, const double* p1, const double* p2, const double* rvc, const double* gam,
+                    const unsigned char* wake_flag, long long m, const double* P, double* V) {
+  constexpr int T = 4, THREADS = 128, TILE = 128;
+  if (nsplit < 1 || n < 0 || m <= 0) return 2;
+  const long long npad = std::max(1LL, (n + TILE - 1) / TILE) * TILE;
+  std::vector<double> rec((size_t)npad * vlc::kSrcDoubles);
+  emul_launch(blocks_for(npad, 256), 1, 256, vlc::pack_flat_kernel, n, npad, p1, p2, rvc, gam, wake_flag, rec.data());
+  const long long tiles = npad / TILE, chunk = (tiles + nsplit - 1) / nsplit * TILE;
+  std::vector<double> part((size_t)nsplit * 3 * (size_t)m);
+  if (fast)
+    emul_launch(blocks_for(m, THREADS * T), (unsigned)nsplit, THREADS, vlc::bs_sweep_kernel<T, THREADS, TILE, 3, 1, true>,
+                (const double*)rec.data(), chunk, npad, P, m, part.data(), (const int*)nullptr, 0);
+  else
+    emul_launch(blocks_for(m, THREADS * T), (unsigned)nsplit, THREADS, vlc::bs_sweep_kernel<T, THREADS, TILE, 3, 1, false>,
+                (const double*)rec.data(), chunk, npad, P, m, part.data(), (const int*)nullptr, 0);
+  emul_launch(blocks_for(3 * m, 256), 1, 256, vlc::bs_reduce_kernel, (const double*)part.data(), nsplit, 3 * m, V);
+  return 0;
 }
 
 // rsqrt_fp64<FAST> of vlc_device.cuh (seed modelled, refinement = the product's source)

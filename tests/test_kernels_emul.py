@@ -35,6 +35,7 @@ def emul_lib():
            "emul_pack_wing_subset": (None, [i32] * 4 + [vp, vp]),
            "emul_pack_pfwake": (None, [i32, vp, vp]),
            "emul_vind_records": (None, [C.c_longlong, vp, C.c_longlong, vp, vp]),
+           "emul_flat_sweep": (i32, [i32, i32, C.c_longlong] + [vp] * 5 + [C.c_longlong, vp, vp]),
            "emul_rsqrt": (None, [i32, C.c_longlong, vp, vp]),
            "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
     for k, (res, args) in sig.items():
@@ -333,3 +334,28 @@ def test_rsqrt_refinement_with_a_seed_as_coarse_as_the_devices():
         assert np.max(np.abs(rel)) < bound, (fast, float(np.max(np.abs(rel))))
         if fast:
             assert np.max(rel) < 1e-15                               # never high: what the centring factor relies on
+
+
+@pytest.mark.parametrize("n,m,nsplit,fast", [(1, 1, 1, 0), (7, 3, 1, 0), (127, 129, 1, 0), (129, 513, 2, 0), (1000, 77, 3, 0),
+                                             (2000, 520, 4, 0), (1000, 77, 2, 1)])
+def test_flat_sweep_kernel_on_the_cpu(oracle, n, m, nsplit, fast):
+    """pack_flat_kernel -> bs_sweep_kernel<4, 128, 128, 3> (tile ring, T = 4 targets per thread, source splits) ->
+    bs_reduce_kernel on the random sets of tests/test_gpu_parity.py::test_flat_random_vs_oracle (targets on end points and
+    on filaments, gam = 0 and |gam| <= eps with and without the wake rule): the same measure and the same bar as on the GPU,
+    err = max|V - V_oracle| / max sum|terms| < 1e-12; second-order precision mode included."""
+    from tests.helpers import scaled_err
+    from volcanor_b200 import synth
+    p1, p2, rvc, gam, flag, P = synth.random_filaments(n, m, seed=n + m)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (p1, p2, rvc, gam)]
+    flag = np.ascontiguousarray(flag, dtype=np.uint8)
+    P = np.ascontiguousarray(P)
+    V = np.empty_like(P)
+    rc = emul_lib().emul_flat_sweep(fast, nsplit, n, *[a.ctypes.data for a in arrs], flag.ctypes.data, m, P.ctypes.data,
+                                    V.ctypes.data)
+    assert rc == 0 and np.all(np.isfinite(V))
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, P)
+    _, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, P)
+    e = scaled_err(V, Vo, Vabs)
+    assert e < 1e-12, e
+    if not fast:
+        assert e < 1e-14, e                                       # full precision sits at rounding level

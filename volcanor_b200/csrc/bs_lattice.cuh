@@ -36,13 +36,6 @@ __host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_nodes_pad(
 #endif
 __host__ __device__ constexpr int lat_tile(int W) { return (W <= 2 ? 64 : 32) / VLC_LAT_TILE_DIV; }  // records per shared-memory tile
 
-// the thread that issues the bulk copies of a CTA
-#if defined(__CUDA_EMUL__)
-#define VLC_PRODUCER(tid) true
-#else
-#define VLC_PRODUCER(tid) ((tid) == 0)
-#endif
-
 struct NodeQ {
   double rx, ry, rz, u;  // r = P - X, u = 1/|r|
 };

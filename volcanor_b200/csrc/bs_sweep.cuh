@@ -26,7 +26,11 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
                 int want)
 {
   if (flag != nullptr && *flag != want) return;
+#if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/kernels_emul.cpp), see bs_lattice.cuh
+  alignas(128) static unsigned char smem_raw[(size_t)STAGES * TILE * kSrcBytes + STAGES * 8];
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   double* buf = reinterpret_cast<double*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * kSrcBytes);
 
@@ -38,13 +42,13 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
   const double* gsrc = src + s_begin * kSrcDoubles;
   constexpr uint32_t kTileBytes = TILE * kSrcBytes;
 
-  if (tid == 0) {
+  if (VLC_PRODUCER(tid)) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
+  if (VLC_PRODUCER(tid)) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s)
       if (s < ntiles) {
@@ -79,7 +83,7 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
       for (int k = 0; k < T; ++k) pair_accumulate<FAST>(s, px[k], py[k], pz[k], vx[k], vy[k], vz[k]);
     }
     __syncthreads();  // every warp is done with this stage before it is refilled
-    if (tid == 0 && tile + STAGES < ntiles) {
+    if (VLC_PRODUCER(tid) && tile + STAGES < ntiles) {
       mbar_expect_tx(&bars[stage], kTileBytes);
       tma_bulk_g2s(buf + (size_t)stage * TILE * kSrcDoubles, gsrc + (size_t)(tile + STAGES) * TILE * kSrcDoubles,
                    kTileBytes, &bars[stage]);

@@ -152,6 +152,12 @@ __device__ __forceinline__ void pair_accumulate(const Src& s, double px, double 
 }
 
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----
+// the thread that issues the bulk copies of a CTA (host build of the tests: every emulated thread stages its own tiles)
+#if defined(__CUDA_EMUL__)
+#define VLC_PRODUCER(tid) true
+#else
+#define VLC_PRODUCER(tid) ((tid) == 0)
+#endif
 #if !defined(__CUDA_EMUL__)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
