@@ -12,6 +12,10 @@ if [ "${2:-}" != "skip-tests" ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > $OUT/pytest_gpu_$TAG.log 2>&1
   echo "pytest rc=$?" >> $OUT/pytest_gpu_$TAG.log
   tail -25 $OUT/pytest_gpu_$TAG.log
+  # the tests that had not run on a GPU when they were written, once more WITHOUT -x and verbosely: every outcome is kept
+  timeout 600 python -m pytest tests/test_zzz_gpu_first_run.py tests/test_zz_probes.py -m gpu -q -rA -s > $OUT/pytest_gpu_first_run_$TAG.log 2>&1
+  echo "pytest rc=$?" >> $OUT/pytest_gpu_first_run_$TAG.log
+  grep -E "PASSED|FAILED|ERROR|max rel err" $OUT/pytest_gpu_first_run_$TAG.log | tail -30
 fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
