@@ -175,21 +175,49 @@ void emul_vind_records(long long n, const double* rec, long long m, const double
 // pair arithmetic.  V = what vind_bywake gives for a blade without a far wake, regrouped node by node and edge by edge.
 }  // extern "C"
 
+// strips of width W over ring columns col0 .. (clipped at ns by fill_strip_record): pack + null padding + sweep, added to out
 template <int W, int T>
-static int lattice_vind(const double* waN, int nNwake, int ns, int i0, int nrows, long long m, const double* P, double* V) {
+static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nrows, int col0, int nstrips, long long m,
+                          const double* P, double* out) {
   constexpr int RD = vlc::lat_rec_doubles(W), TILE = vlc::lat_tile(W), THREADS = 128;
-  const int nstrips = ns / W;
   const long long nrec = (long long)nstrips * (nrows + 1), npad = (nrec + TILE - 1) / TILE * TILE;
   std::vector<double> lat((size_t)npad * RD);
   int unmergeable = 0;
-  emul_launch(blocks_for(nrec, 128), 1, 128, vlc::pack_rings_shared_kernel<W>, waN, vlc::kVr, nNwake, i0, nrows, ns, 0, nstrips,
+  emul_launch(blocks_for(nrec, 128), 1, 128, vlc::pack_rings_shared_kernel<W>, waN, vlc::kVr, nNwake, i0, nrows, ns, col0, nstrips,
               lat.data(), &unmergeable, 0LL);
   if (npad > nrec)
     emul_launch(blocks_for(npad - nrec, 128), 1, 128, vlc::pack_null_lat_kernel<W>, npad - nrec, lat.data() + (size_t)nrec * RD);
   if (unmergeable) return 1;
-  std::vector<double> out(3 * (size_t)m);
+  std::vector<double> part(3 * (size_t)m);
   emul_launch(blocks_for(m, THREADS * T), 1, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>, (const double*)lat.data(), npad,
-              npad, P, m, out.data(), (const int*)&unmergeable, 0);
+              npad, P, m, part.data(), (const int*)&unmergeable, 0);
+  for (size_t k = 0; k < 3 * (size_t)m; ++k) out[k] += part[k];
+  return 0;
+}
+
+static int lattice_dispatch(int W, int T, const double* waN, int nNwake, int ns, int i0, int nrows, int col0, int nstrips,
+                            long long m, const double* P, double* out) {
+#define X(WW, TT) \
+  if (W == WW && T == TT) return lattice_strips<WW, TT>(waN, nNwake, ns, i0, nrows, col0, nstrips, m, P, out);
+  X(1, 1) X(1, 3) X(2, 2) X(3, 1) X(3, 2) X(4, 1) X(4, 2)
+#undef X
+  return 3;
+}
+
+extern "C" {
+
+// The strip plan of capi.cu (plan_strips): tailW = 0: ceil(ns / W) strips of width W (the last one partial when ns is not a
+// multiple of W); tailW = ns mod W > 0: floor(ns / W) strips of width W + one tail strip of width tailW swept with
+// kLatBestT[tailW] targets per thread (sweep_shared's second lattice launch).  Then the flat remainder as in the product.
+int emul_lattice_vind_plan(int W, int T, int tailW, const double* waN, int nNwake, int ns, int i0, int nrows, long long m,
+                           const double* P, double* V) {
+  static const int bestT[4] = {0, 3, 2, 2};
+  if (tailW < 0 || tailW > 3 || (tailW && (ns <= W || ns % W != tailW))) return 2;
+  const int nmain = tailW ? ns / W : (ns + W - 1) / W;
+  std::vector<double> out(3 * (size_t)m, 0.0);
+  int rc = lattice_dispatch(W, T, waN, nNwake, ns, i0, nrows, 0, nmain, m, P, out.data());
+  if (rc) return rc;
+  if (tailW && (rc = lattice_dispatch(tailW, bestT[tailW], waN, nNwake, ns, i0, nrows, nmain * W, 1, m, P, out.data()))) return rc;
   std::vector<double> rem((size_t)nrows * vlc::kSrcDoubles), vrem(3 * (size_t)m);
   emul_launch(blocks_for(nrows, 128), 1, 128, vlc::pack_rings_kernel, waN + (size_t)vlc::kVr * nNwake * (ns - 1), vlc::kVr, nNwake, i0,
               nrows, 1, 0x4, 1, 1.0, 1, rem.data(), 0LL, 0LL);
@@ -198,16 +226,10 @@ static int lattice_vind(const double* waN, int nNwake, int ns, int i0, int nrows
   return 0;
 }
 
-extern "C" {
-
 int emul_lattice_vind(int W, int T, const double* waN, int nNwake, int ns, int i0, int nrows, long long m, const double* P,
                       double* V) {
   if (ns % W != 0) return 2;
-#define X(WW, TT) \
-  if (W == WW && T == TT) return lattice_vind<WW, TT>(waN, nNwake, ns, i0, nrows, m, P, V);
-  X(1, 1) X(1, 3) X(2, 2) X(3, 1) X(3, 2) X(4, 1) X(4, 2)
-#undef X
-  return 3;
+  return emul_lattice_vind_plan(W, T, 0, waN, nNwake, ns, i0, nrows, m, P, V);
 }
 
 // ---- the flat sweep: pack_flat_kernel (tier 1 arrays -> records, padded with null filaments to whole tiles) ->

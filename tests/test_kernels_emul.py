@@ -37,7 +37,8 @@ def emul_lib():
            "emul_vind_records": (None, [C.c_longlong, vp, C.c_longlong, vp, vp]),
            "emul_flat_sweep": (i32, [i32, i32, C.c_longlong] + [vp] * 5 + [C.c_longlong, vp, vp]),
            "emul_rsqrt": (None, [i32, C.c_longlong, vp, vp]),
-           "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
+           "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp]),
+           "emul_lattice_vind_plan": (i32, [i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
         getattr(lib, k).argtypes = args
@@ -316,6 +317,39 @@ def test_lattice_kernel_on_the_cpu(oracle, W, T, ns, nsteps):
     err = float(np.max(np.abs(got - ref)))
     print(f"lattice kernel W={W} T={T} on the CPU: {P.shape[0]} targets x {rot.nb * nrows * rot.ns} rings, max error "
           f"{err / scale * 50:.2e} of the velocity scale")
+    assert err < 1e-12 * scale, err / scale
+
+
+@pytest.mark.parametrize("W,T,tailW,ns", [(4, 2, 0, 6), (4, 2, 2, 6), (4, 2, 1, 5), (4, 1, 3, 7), (4, 2, 1, 9), (3, 2, 0, 5),
+                                          (2, 2, 0, 5), (4, 2, 0, 3), (4, 2, 0, 2), (1, 3, 0, 2)])
+def test_lattice_kernel_on_the_cpu_strip_plans(oracle, W, T, tailW, ns):
+    """Column counts that are not a multiple of the strip width, covered the two ways capi.cu's plan_strips does it: a
+    partial last strip of the same width (fill_strip_record clips at ns), or floor(ns / 4) strips of width 4 and one tail
+    strip of width ns mod 4 packed with col_base = 4 floor(ns / 4) and swept by a second lattice launch (green on a B200:
+    tests/test_gpu_lattice.py::test_tail_strips_cover_column_counts_that_are_not_multiples_of_four, ::test_degenerate_
+    lattice_shapes).  Same targets, oracle and bar as test_lattice_kernel_on_the_cpu; growing wake (rows 1..4 inactive)."""
+    case, _ = _case(oracle, 4, ns=ns, wakeTruncateNt=0, nNwake=8)
+    rot, lib = case.rotor(0), emul_lib()
+    d = rot.dims()
+    nrows, i0 = rot.nNwake - d["rowNear"] + 1, d["rowNear"] - 1
+    assert nrows == 4 and d["rowFar"] > rot.nFwake
+    waN = _stack(rot, "waN")
+    rng = np.random.default_rng(100 * W + 10 * tailW + ns)
+    nodes = waN[0, :, i0:, 12:15].reshape(-1, 3)
+    mid = 0.5 * (waN[1, :, i0:, 12:15] + waN[1, :, i0:, 24:27]).reshape(-1, 3)
+    last = waN[2, ns - 1, i0:, 24:27].reshape(-1, 3)                              # corner 3 of the last column (the flat remainder's edge)
+    P = np.ascontiguousarray(np.concatenate([rng.uniform(-1.3, 1.3, (200, 3)) * float(np.abs(nodes).max()), nodes, mid, last]))
+    got = np.zeros_like(P)
+    for ib in range(rot.nb):
+        V = np.empty_like(P)
+        rc = lib.emul_lattice_vind_plan(W, T, tailW, np.ascontiguousarray(waN[ib]).ctypes.data, rot.nNwake, rot.ns, i0, nrows,
+                                        P.shape[0], P.ctypes.data, V.ctypes.data)
+        assert rc == 0, rc
+        got = got + V
+    ref = rot.vind_points(1, P, False)
+    assert np.all(np.isfinite(got)) and np.abs(ref).max() > 0
+    scale = 50.0 * float(np.abs(ref).max())
+    err = float(np.max(np.abs(got - ref)))
     assert err < 1e-12 * scale, err / scale
 
 
