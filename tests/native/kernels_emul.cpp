@@ -175,30 +175,34 @@ void emul_vind_records(long long n, const double* rec, long long m, const double
 // pair arithmetic.  V = what vind_bywake gives for a blade without a far wake, regrouped node by node and edge by edge.
 }  // extern "C"
 
-// strips of width W over ring columns col0 .. (clipped at ns by fill_strip_record): pack + null padding + sweep, added to out
+// strips of width W over ring columns col0 .. (clipped at ns by fill_strip_record): pack + null padding + sweep with nsplit
+// source splits (grid y, chunks of whole tiles as sweep_shared cuts them); the partial slots are appended to parts
 template <int W, int T>
-static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nrows, int col0, int nstrips, long long m,
-                          const double* P, double* out) {
+static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nrows, int col0, int nstrips, int nsplit, long long m,
+                          const double* P, int* unmergeable, std::vector<double>& parts, int* nslots) {
   constexpr int RD = vlc::lat_rec_doubles(W), TILE = vlc::lat_tile(W), THREADS = 128;
   const long long nrec = (long long)nstrips * (nrows + 1), npad = (nrec + TILE - 1) / TILE * TILE;
   std::vector<double> lat((size_t)npad * RD);
-  int unmergeable = 0;
   emul_launch(blocks_for(nrec, 128), 1, 128, vlc::pack_rings_shared_kernel<W>, waN, vlc::kVr, nNwake, i0, nrows, ns, col0, nstrips,
-              lat.data(), &unmergeable, 0LL);
+              lat.data(), unmergeable, 0LL);
   if (npad > nrec)
     emul_launch(blocks_for(npad - nrec, 128), 1, 128, vlc::pack_null_lat_kernel<W>, npad - nrec, lat.data() + (size_t)nrec * RD);
-  if (unmergeable) return 1;
-  std::vector<double> part(3 * (size_t)m);
-  emul_launch(blocks_for(m, THREADS * T), 1, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>, (const double*)lat.data(), npad,
-              npad, P, m, part.data(), (const int*)&unmergeable, 0);
-  for (size_t k = 0; k < 3 * (size_t)m; ++k) out[k] += part[k];
+  if (*unmergeable) return 1;
+  const long long tiles = npad / TILE, chunk_tiles = (tiles + nsplit - 1) / nsplit;
+  const int real_split = (int)((tiles + chunk_tiles - 1) / chunk_tiles);
+  const size_t len = 3 * (size_t)m, at = parts.size();
+  parts.resize(at + (size_t)real_split * len, 0.0);
+  emul_launch(blocks_for(m, THREADS * T), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>,
+              (const double*)lat.data(), chunk_tiles * TILE, npad, P, m, parts.data() + at, (const int*)unmergeable, 0);
+  *nslots += real_split;
   return 0;
 }
 
 static int lattice_dispatch(int W, int T, const double* waN, int nNwake, int ns, int i0, int nrows, int col0, int nstrips,
-                            long long m, const double* P, double* out) {
+                            int nsplit, long long m, const double* P, int* unmergeable, std::vector<double>& parts, int* nslots) {
 #define X(WW, TT) \
-  if (W == WW && T == TT) return lattice_strips<WW, TT>(waN, nNwake, ns, i0, nrows, col0, nstrips, m, P, out);
+  if (W == WW && T == TT) \
+    return lattice_strips<WW, TT>(waN, nNwake, ns, i0, nrows, col0, nstrips, nsplit, m, P, unmergeable, parts, nslots);
   X(1, 1) X(1, 3) X(2, 2) X(3, 1) X(3, 2) X(4, 1) X(4, 2)
 #undef X
   return 3;
@@ -208,22 +212,38 @@ extern "C" {
 
 // The strip plan of capi.cu (plan_strips): tailW = 0: ceil(ns / W) strips of width W (the last one partial when ns is not a
 // multiple of W); tailW = ns mod W > 0: floor(ns / W) strips of width W + one tail strip of width tailW swept with
-// kLatBestT[tailW] targets per thread (sweep_shared's second lattice launch).  Then the flat remainder as in the product.
-int emul_lattice_vind_plan(int W, int T, int tailW, const double* waN, int nNwake, int ns, int i0, int nrows, long long m,
-                           const double* P, double* V) {
+// kLatBestT[tailW] targets per thread (sweep_shared's second lattice launch).  Launch sequence of pack_rotor_sources /
+// sweep_shared for one blade: check_rings_kernel, the strip packs, the lattice launches with nsplit source splits, the flat
+// remainder (one slot), bs_reduce_select_kernel over the slots of the mergeable path.  1 = not a lattice (flag raised).
+int emul_lattice_vind_split(int W, int T, int tailW, int nsplit, const double* waN, int nNwake, int ns, int i0, int nrows,
+                            long long m, const double* P, double* V) {
   static const int bestT[4] = {0, 3, 2, 2};
-  if (tailW < 0 || tailW > 3 || (tailW && (ns <= W || ns % W != tailW))) return 2;
+  if (tailW < 0 || tailW > 3 || (tailW && (ns <= W || ns % W != tailW)) || nsplit < 1) return 2;
   const int nmain = tailW ? ns / W : (ns + W - 1) / W;
-  std::vector<double> out(3 * (size_t)m, 0.0);
-  int rc = lattice_dispatch(W, T, waN, nNwake, ns, i0, nrows, 0, nmain, m, P, out.data());
+  int unmergeable = 0, nslots = 0;
+  emul_launch(blocks_for((long long)nrows * ns, 256), 1, 256, vlc::check_rings_kernel, waN, vlc::kVr, nNwake, i0, nrows, ns,
+              &unmergeable, 0LL);
+  std::vector<double> parts;
+  int rc = lattice_dispatch(W, T, waN, nNwake, ns, i0, nrows, 0, nmain, nsplit, m, P, &unmergeable, parts, &nslots);
   if (rc) return rc;
-  if (tailW && (rc = lattice_dispatch(tailW, bestT[tailW], waN, nNwake, ns, i0, nrows, nmain * W, 1, m, P, out.data()))) return rc;
-  std::vector<double> rem((size_t)nrows * vlc::kSrcDoubles), vrem(3 * (size_t)m);
+  if (tailW && (rc = lattice_dispatch(tailW, bestT[tailW], waN, nNwake, ns, i0, nrows, nmain * W, 1, 1, m, P, &unmergeable, parts,
+                                      &nslots)))
+    return rc;
+  const size_t len = 3 * (size_t)m;
+  std::vector<double> rem((size_t)nrows * vlc::kSrcDoubles);
   emul_launch(blocks_for(nrows, 128), 1, 128, vlc::pack_rings_kernel, waN + (size_t)vlc::kVr * nNwake * (ns - 1), vlc::kVr, nNwake, i0,
               nrows, 1, 0x4, 1, 1.0, 1, rem.data(), 0LL, 0LL);
-  emul_vind_records(nrows, rem.data(), m, P, vrem.data());
-  for (size_t k = 0; k < 3 * (size_t)m; ++k) V[k] = out[k] + vrem[k];
+  parts.resize(parts.size() + len);
+  emul_vind_records(nrows, rem.data(), m, P, parts.data() + (size_t)nslots * len);
+  ++nslots;
+  emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)parts.data(),
+              (const int*)&unmergeable, nslots, 0, (long long)len, V);
   return 0;
+}
+
+int emul_lattice_vind_plan(int W, int T, int tailW, const double* waN, int nNwake, int ns, int i0, int nrows, long long m,
+                           const double* P, double* V) {
+  return emul_lattice_vind_split(W, T, tailW, 1, waN, nNwake, ns, i0, nrows, m, P, V);
 }
 
 int emul_lattice_vind(int W, int T, const double* waN, int nNwake, int ns, int i0, int nrows, long long m, const double* P,

@@ -38,7 +38,8 @@ def emul_lib():
            "emul_flat_sweep": (i32, [i32, i32, C.c_longlong] + [vp] * 5 + [C.c_longlong, vp, vp]),
            "emul_rsqrt": (None, [i32, C.c_longlong, vp, vp]),
            "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp]),
-           "emul_lattice_vind_plan": (i32, [i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
+           "emul_lattice_vind_plan": (i32, [i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp]),
+           "emul_lattice_vind_split": (i32, [i32, i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
         getattr(lib, k).argtypes = args
@@ -344,6 +345,37 @@ def test_lattice_kernel_on_the_cpu_strip_plans(oracle, W, T, tailW, ns):
         V = np.empty_like(P)
         rc = lib.emul_lattice_vind_plan(W, T, tailW, np.ascontiguousarray(waN[ib]).ctypes.data, rot.nNwake, rot.ns, i0, nrows,
                                         P.shape[0], P.ctypes.data, V.ctypes.data)
+        assert rc == 0, rc
+        got = got + V
+    ref = rot.vind_points(1, P, False)
+    assert np.all(np.isfinite(got)) and np.abs(ref).max() > 0
+    scale = 50.0 * float(np.abs(ref).max())
+    err = float(np.max(np.abs(got - ref)))
+    assert err < 1e-12 * scale, err / scale
+
+
+@pytest.mark.parametrize("W,T,tailW,nsplit,ns", [(1, 1, 0, 1, 8), (1, 3, 0, 2, 8), (1, 3, 0, 4, 8), (2, 2, 0, 3, 8), (4, 2, 0, 1, 8),
+                                                 (4, 2, 0, 2, 8), (4, 1, 0, 3, 8), (3, 2, 0, 2, 6), (4, 2, 2, 2, 6)])
+def test_lattice_kernel_on_the_cpu_source_splits_and_tile_ring(oracle, W, T, tailW, nsplit, ns):
+    """Long near wake (30 active rows): the strip records fill several shared-memory tiles, so one CTA walks more tiles than
+    the ring has stages (3) and the sweep is cut into source splits of whole tiles (grid y, sweep_shared's chunks); then
+    check_rings_kernel and bs_reduce_select_kernel close the launch sequence of the mergeable path.  Oracle and bar as above;
+    more than 128 T targets, so several CTAs in x as well."""
+    case, _ = _case(oracle, 30, ns=ns, wakeTruncateNt=0, nNwake=32)
+    rot, lib = case.rotor(0), emul_lib()
+    d = rot.dims()
+    nrows, i0 = rot.nNwake - d["rowNear"] + 1, d["rowNear"] - 1
+    assert nrows == 30 and d["rowFar"] > rot.nFwake
+    waN = _stack(rot, "waN")
+    rng = np.random.default_rng(1000 * W + 100 * T + nsplit)
+    nodes = waN[0, :, i0:, 12:15].reshape(-1, 3)
+    P = np.ascontiguousarray(np.concatenate([rng.uniform(-1.3, 1.3, (190, 3)) * float(np.abs(nodes).max()), nodes]))
+    assert P.shape[0] > 128 * T
+    got = np.zeros_like(P)
+    for ib in range(rot.nb):
+        V = np.empty_like(P)
+        rc = lib.emul_lattice_vind_split(W, T, tailW, nsplit, np.ascontiguousarray(waN[ib]).ctypes.data, rot.nNwake, rot.ns, i0,
+                                         nrows, P.shape[0], P.ctypes.data, V.ctypes.data)
         assert rc == 0, rc
         got = got + V
     ref = rot.vind_points(1, P, False)
