@@ -5,6 +5,7 @@
 // hold the kernels against the oracle bit for bit without a GPU (cos / sin / atan2 / acos are then libm's on both
 // sides).  Nothing in the product links or loads this file.  Build: tests/native/Makefile (g++ -O2 -ffp-contract=off).
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "../../volcanor_b200/csrc/wake_records.cuh"
@@ -244,6 +245,52 @@ int emul_lattice_vind_split(int W, int T, int tailW, int nsplit, const double* w
 int emul_lattice_vind_plan(int W, int T, int tailW, const double* waN, int nNwake, int ns, int i0, int nrows, long long m,
                            const double* P, double* V) {
   return emul_lattice_vind_split(W, T, tailW, 1, waN, nNwake, ns, i0, nrows, m, P, V);
+}
+
+// Device-side dispatch of sweep_shared for one blade, every launch made whatever the flag says (as on the device, where the
+// host never reads it): check_rings + strip pack raise *flag_out when the records are not a lattice; the W = 4 lattice launch
+// and the flat remainder run with want = 0, the flat enumeration (pack_rings_kernel, 4 filaments per ring, wake rule) with
+// want = 1 and nsplit_flat source splits; bs_reduce_select_kernel sums the slots of the path that ran.  The partial buffer
+// starts as NaN: a selected slot that nobody wrote shows up in V.
+int emul_lattice_vind_dispatch(int nsplit_flat, const double* waN, int nNwake, int ns, int i0, int nrows, long long m,
+                               const double* P, double* V, int* flag_out) {
+  constexpr int W = 4, T = 2, THREADS = 128, FT = 4, FTILE = 128;
+  constexpr int RD = vlc::lat_rec_doubles(W), TILE = vlc::lat_tile(W);
+  if (nsplit_flat < 1 || m <= 0) return 2;
+  int flag = 0;
+  emul_launch(blocks_for((long long)nrows * ns, 256), 1, 256, vlc::check_rings_kernel, waN, vlc::kVr, nNwake, i0, nrows, ns, &flag, 0LL);
+  const int nstrips = (ns + W - 1) / W;
+  const long long nrec = (long long)nstrips * (nrows + 1), npad = (nrec + TILE - 1) / TILE * TILE;
+  std::vector<double> lat((size_t)npad * RD);
+  emul_launch(blocks_for(nrec, 128), 1, 128, vlc::pack_rings_shared_kernel<W>, waN, vlc::kVr, nNwake, i0, nrows, ns, 0, nstrips,
+              lat.data(), &flag, 0LL);
+  if (npad > nrec)
+    emul_launch(blocks_for(npad - nrec, 128), 1, 128, vlc::pack_null_lat_kernel<W>, npad - nrec, lat.data() + (size_t)nrec * RD);
+  auto flat_records = [&](const double* base, int cols, int mask, int per_ring, std::vector<double>& rec) -> long long {
+    const long long n = (long long)per_ring * nrows * cols, pad = std::max(1LL, (n + FTILE - 1) / FTILE) * FTILE;
+    rec.assign((size_t)pad * vlc::kSrcDoubles, 0.0);
+    emul_launch(blocks_for(n, 256), 1, 256, vlc::pack_rings_kernel, base, vlc::kVr, nNwake, i0, nrows, cols, mask, per_ring, 1.0, 1,
+                rec.data(), 0LL, 0LL);
+    if (pad > n) emul_launch(blocks_for(pad - n, 256), 1, 256, vlc::pack_null_kernel, pad - n, rec.data() + (size_t)n * vlc::kSrcDoubles);
+    return pad;
+  };
+  std::vector<double> rem, flat;
+  const long long rem_pad = flat_records(waN + (size_t)vlc::kVr * nNwake * (ns - 1), 1, 0x4, 1, rem);
+  const long long flat_pad = flat_records(waN, ns, 0xF, 4, flat);
+  const long long ftiles = flat_pad / FTILE, fchunk_tiles = (ftiles + nsplit_flat - 1) / nsplit_flat;
+  const int nb = (int)((ftiles + fchunk_tiles - 1) / fchunk_tiles), na = 2;
+  const size_t len = 3 * (size_t)m;
+  std::vector<double> parts((size_t)(na + nb) * len, std::nan(""));
+  emul_launch(blocks_for(m, THREADS * T), 1, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>, (const double*)lat.data(), npad, npad,
+              P, m, parts.data(), (const int*)&flag, 0);
+  emul_launch(blocks_for(m, THREADS * FT), 1, THREADS, vlc::bs_sweep_kernel<FT, THREADS, FTILE, 3, 1, false>, (const double*)rem.data(),
+              rem_pad, rem_pad, P, m, parts.data() + len, (const int*)&flag, 0);
+  emul_launch(blocks_for(m, THREADS * FT), (unsigned)nb, THREADS, vlc::bs_sweep_kernel<FT, THREADS, FTILE, 3, 1, false>,
+              (const double*)flat.data(), fchunk_tiles * FTILE, flat_pad, P, m, parts.data() + (size_t)na * len, (const int*)&flag, 1);
+  emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)parts.data(), (const int*)&flag, na,
+              nb, (long long)len, V);
+  *flag_out = flag;
+  return 0;
 }
 
 int emul_lattice_vind(int W, int T, const double* waN, int nNwake, int ns, int i0, int nrows, long long m, const double* P,

@@ -39,7 +39,8 @@ def emul_lib():
            "emul_rsqrt": (None, [i32, C.c_longlong, vp, vp]),
            "emul_lattice_vind": (i32, [i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp]),
            "emul_lattice_vind_plan": (i32, [i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp]),
-           "emul_lattice_vind_split": (i32, [i32, i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp])}
+           "emul_lattice_vind_split": (i32, [i32, i32, i32, i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp]),
+           "emul_lattice_vind_dispatch": (i32, [i32, vp, i32, i32, i32, i32, C.c_longlong, vp, vp, vp])}
     for k, (res, args) in sig.items():
         getattr(lib, k).restype = res
         getattr(lib, k).argtypes = args
@@ -380,6 +381,35 @@ def test_lattice_kernel_on_the_cpu_source_splits_and_tile_ring(oracle, W, T, tai
         got = got + V
     ref = rot.vind_points(1, P, False)
     assert np.all(np.isfinite(got)) and np.abs(ref).max() > 0
+    scale = 50.0 * float(np.abs(ref).max())
+    err = float(np.max(np.abs(got - ref)))
+    assert err < 1e-12 * scale, err / scale
+
+
+@pytest.mark.parametrize("predicted,nsplit_flat", [(False, 1), (False, 3), (True, 2)])
+def test_device_side_dispatch_between_lattice_and_flat_enumeration(oracle, predicted, nsplit_flat):
+    """sweep_shared never reads the mergeability flag on the host: the lattice launch and the flat remainder run when it is 0,
+    the flat enumeration when it is 1, and bs_reduce_select_kernel sums the slots of the path that ran.  End of a step with
+    every row shed: the CURRENT records are mid-update (newest row's vf(4)%rVc, classdef.f90:4386-4392) -> flag 1, flat path;
+    the PREDICTED records are a lattice -> flag 0.  Both against rotor%vind_bywake of the oracle, partial buffer pre-filled
+    with NaN.  (On a B200: tests/test_gpu_lattice.py::test_unmergeable_core_radii_fall_back_to_flat_enumeration.)"""
+    case, _ = _case(oracle, 8, ns=6, wakeTruncateNt=0, nNwake=8)
+    rot, lib = case.rotor(0), emul_lib()
+    d = rot.dims()
+    assert d["rowNear"] == 1 and d["rowFar"] > rot.nFwake
+    waN = _stack(rot, "waN", predicted)
+    rng = np.random.default_rng(7 + nsplit_flat)
+    nodes = waN[0, :, :, 12:15].reshape(-1, 3)
+    P = np.ascontiguousarray(np.concatenate([rng.uniform(-1.3, 1.3, (530, 3)) * float(np.abs(nodes).max()), nodes]))
+    got = np.zeros_like(P)
+    for ib in range(rot.nb):
+        V, flag = np.empty_like(P), C.c_int(-1)
+        rc = lib.emul_lattice_vind_dispatch(nsplit_flat, np.ascontiguousarray(waN[ib]).ctypes.data, rot.nNwake, rot.ns, 0,
+                                            rot.nNwake, P.shape[0], P.ctypes.data, V.ctypes.data, C.byref(flag))
+        assert rc == 0 and flag.value == (0 if predicted else 1), (rc, flag.value)
+        got = got + V
+    ref = rot.vind_points(1, P, predicted)
+    assert np.all(np.isfinite(got))
     scale = 50.0 * float(np.abs(ref).max())
     err = float(np.max(np.abs(got - ref)))
     assert err < 1e-12 * scale, err / scale
