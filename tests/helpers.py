@@ -27,5 +27,18 @@ def lattice_to_rotor(lat, rotor, ib, predicted=False):
 
 
 def scaled_err(V, Vref, Vabs):
-    """max |V - Vref| / max(sum |terms|): the per-call parity measure."""
+    """PER-TARGET parity measure: max_t ( max_k |V_tk - Vref_tk| / max_k sum_i |term_i,tk| ).
+
+    Every target is measured against ITS OWN velocity scale sum|terms|, so a target far from the wake --
+    whose scale is orders of magnitude below the batch maximum -- cannot hide a dropped edge or a wrong merged
+    strength behind the large targets of the batch (round-1 review: the batch-scaled form could)."""
+    V, Vref, Vabs = (np.asarray(a, dtype=np.float64).reshape(-1, 3) for a in (V, Vref, Vabs))
+    if V.shape[0] == 0:
+        return 0.0
+    scale = np.maximum(Vabs.max(axis=1), 1e-300)
+    return float(np.max(np.abs(V - Vref).max(axis=1) / scale))
+
+
+def scaled_err_batch(V, Vref, Vabs):
+    """Batch-scaled form (round 1): max |V - Vref| / max sum|terms| -- kept as a diagnostic next to scaled_err."""
     return float(np.max(np.abs(V - Vref)) / max(np.max(Vabs), 1e-300))

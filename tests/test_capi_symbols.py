@@ -55,3 +55,62 @@ def test_product_does_not_reference_oracle():
             if p.is_file() and p.suffix in (".py", ".sh", ".h", ".hpp", ".f90", ".cu", ".c", ".cpp"):
                 txt = p.read_text()
                 assert "pyoracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, p
+
+
+class _RecordingLib:
+    """Stand-in for the CDLL: every vlc_* call forces a garbage collection, churns the allocator, and then reads the
+    doubles its pointer arguments address -- what the C side would see.  A binding that passes the address of a temporary
+    (round 1: `_ptr(_f64(list))`) hands over freed, reused memory and is caught here without a GPU."""
+
+    def __init__(self, sizes):
+        self.sizes, self.seen = sizes, {}
+
+    def __getattr__(self, name):
+        if not name.startswith("vlc_"):
+            raise AttributeError(name)
+
+        def call(h, *args):
+            import gc
+
+            import numpy as np
+            gc.collect()
+            junk = [np.full(n, -7.0) for n in (2, 3, 3, 3, 16, 104, 650) for _ in range(8)]   # reuse freed blocks
+            ptrs = [a for a in args if isinstance(a, int) and a > 4096]
+            self.seen[name] = [np.ctypeslib.as_array((ctypes.c_double * n).from_address(p)).copy()
+                               for p, n in zip(ptrs, self.sizes[name])]
+            del junk
+            return 0
+        return call
+
+
+def test_binding_keeps_converted_arrays_alive_across_the_call():
+    """list / non-contiguous / non-float64 arguments are converted to temporaries; every one of them
+    must outlive the foreign call (vlc_rotor_set_frame got shaftAxis == hubCoords; classdef.f90:1010-1012 reads both)."""
+    import numpy as np
+    sizes = {"vlc_rotor_set_frame": [3, 3], "vlc_rotor_put_wing": [208], "vlc_rotor_put_wing_gam": [6],
+             "vlc_rotor_put_nwake": [100], "vlc_rotor_put_fwake": [26], "vlc_rotor_put_pfwake": [39],
+             "vlc_rotor_put_pfwake_helix": [2], "vlc_rotor_put_sections": [16], "vlc_rotor_put_wakevel": [9, 6]}
+    c = object.__new__(vb.Context)
+    c.lib, c.h = _RecordingLib(sizes), None
+    c.rotor_set_frame(0, [0.0, 0.6, 0.8], [1.0, 2.0, 3.0])
+    sa, hc = c.lib.seen["vlc_rotor_set_frame"]
+    assert sa.tolist() == [0.0, 0.6, 0.8] and hc.tolist() == [1.0, 2.0, 3.0]
+    c.rotor_set_frame(0, (0, 0, 1), np.array([4, 5, 6], dtype=np.int32))       # tuple + wrong dtype
+    sa, hc = c.lib.seen["vlc_rotor_set_frame"]
+    assert sa.tolist() == [0.0, 0.0, 1.0] and hc.tolist() == [4.0, 5.0, 6.0]
+    rng = np.random.default_rng(0)
+    for meth, name, n, pre in [("rotor_put_wing", "vlc_rotor_put_wing", 208, (0, 0)),
+                               ("rotor_put_wing_gam", "vlc_rotor_put_wing_gam", 6, (0, 0)),
+                               ("rotor_put_nwake", "vlc_rotor_put_nwake", 100, (0, 0)),
+                               ("rotor_put_fwake", "vlc_rotor_put_fwake", 26, (0, 0)),
+                               ("rotor_put_pfwake", "vlc_rotor_put_pfwake", 39, (0, 0)),
+                               ("rotor_put_pfwake_helix", "vlc_rotor_put_pfwake_helix", 2, (0, 0)),
+                               ("rotor_put_sections", "vlc_rotor_put_sections", 16, (0, 0))]:
+        want = rng.uniform(-1, 1, n)
+        for arg in (want.tolist(), want.astype(np.float32).astype(np.float64)[::-1][::-1], np.asfortranarray(want)):
+            getattr(c, meth)(*pre, arg)
+            assert np.array_equal(c.lib.seen[name][0], np.asarray(arg, dtype=np.float64)), (meth, type(arg))
+    vn, vf = rng.uniform(size=9), rng.uniform(size=6)
+    c.rotor_put_wakevel(0, 0, 0, vn.tolist(), vf.tolist())
+    assert np.array_equal(c.lib.seen["vlc_rotor_put_wakevel"][0], vn)
+    assert np.array_equal(c.lib.seen["vlc_rotor_put_wakevel"][1], vf)

@@ -101,6 +101,26 @@ def test_strip_widths_and_targets_per_thread(ctx, oracle, W, T):
         ctx.set_lattice_tuning(0, 0)
 
 
+def test_far_field_targets_per_target_tolerance(ctx, oracle):
+    """Targets 100 rotor radii away from the wake, mixed into a batch with wake-node targets: their own velocity scale
+    sum|terms| is ~1e-6 of the batch maximum, so only the PER-TARGET measure (tests/helpers.py:scaled_err) can see an
+    error there -- a dropped edge or a wrong merged strength on a low-influence target (round-1 review, item 6)."""
+    from tests.helpers import scaled_err_batch
+    lats = synth.multirotor(20000, seed=31, n_rotor=4, nb=2, S=8, F=16, with_wing=True)
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=(600, 3))
+    far = 100.0 * d / np.linalg.norm(d, axis=1)[:, None] * rng.uniform(0.8, 1.5, size=(600, 1))
+    P = np.concatenate([synth.targets_all(lats)[::7], far, 1e4 * far[:50]])
+    Vs, Vf, Vo, Vabs = _check(ctx, oracle, lats, P)
+    nfar = far.shape[0] + 50
+    scale_far, scale_near = Vabs[-nfar:].max(), Vabs[:-nfar].max()
+    assert scale_far < 1e-4 * scale_near                      # the far targets ARE invisible to the batch measure
+    e_far = scaled_err(Vs[-nfar:], Vo[-nfar:], Vabs[-nfar:])
+    print(f"far field: per-target scaled error {e_far:.3e} (batch form would report "
+          f"{scaled_err_batch(Vs[-nfar:], Vo[-nfar:], Vabs):.3e})")
+    assert e_far < TOL
+
+
 @pytest.mark.parametrize("R,S,F", [(1, 1, 0), (1, 1, 3), (2, 1, 0), (1, 5, 2), (130, 2, 1), (3, 70, 0)])
 def test_degenerate_lattice_shapes(ctx, oracle, R, S, F):
     rng = np.random.Generator(np.random.PCG64(R * 100 + S))

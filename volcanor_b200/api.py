@@ -309,19 +309,24 @@ class Context:
         self._ck(self.lib.vlc_rotor_set_rows(self.h, ir, rowNear, rowFar))
 
     def rotor_put_wing(self, ir, ib, wiP):
-        self._ck(self.lib.vlc_rotor_put_wing(self.h, ir, ib, _ptr(_f64(wiP))))
+        a = _f64(wiP)  # bound to a local: the converted array must outlive the foreign call
+        self._ck(self.lib.vlc_rotor_put_wing(self.h, ir, ib, _ptr(a)))
 
     def rotor_put_wing_gam(self, ir, ib, gam):
-        self._ck(self.lib.vlc_rotor_put_wing_gam(self.h, ir, ib, _ptr(_f64(gam))))
+        a = _f64(gam)
+        self._ck(self.lib.vlc_rotor_put_wing_gam(self.h, ir, ib, _ptr(a)))
 
     def rotor_put_nwake(self, ir, ib, waN, predicted=False):
-        self._ck(self.lib.vlc_rotor_put_nwake(self.h, ir, ib, int(predicted), _ptr(_f64(waN))))
+        a = _f64(waN)
+        self._ck(self.lib.vlc_rotor_put_nwake(self.h, ir, ib, int(predicted), _ptr(a)))
 
     def rotor_put_fwake(self, ir, ib, waF, predicted=False):
-        self._ck(self.lib.vlc_rotor_put_fwake(self.h, ir, ib, int(predicted), _ptr(_f64(waF))))
+        a = _f64(waF)
+        self._ck(self.lib.vlc_rotor_put_fwake(self.h, ir, ib, int(predicted), _ptr(a)))
 
     def rotor_put_pfwake(self, ir, ib, wapF, predicted=False):
-        self._ck(self.lib.vlc_rotor_put_pfwake(self.h, ir, ib, int(predicted), _ptr(_f64(wapF))))
+        a = _f64(wapF)
+        self._ck(self.lib.vlc_rotor_put_pfwake(self.h, ir, ib, int(predicted), _ptr(a)))
 
     def _points(self, fn, P, *pre):
         P = _f64(P)
@@ -398,7 +403,8 @@ class Context:
                                                     apparentViscCoeff, decayCoeff, initWakeVel))
 
     def rotor_set_frame(self, ir, shaftAxis, hubCoords):
-        self._ck(self.lib.vlc_rotor_set_frame(self.h, ir, _ptr(_f64(shaftAxis, (3,))), _ptr(_f64(hubCoords, (3,)))))
+        sa, hc = _f64(shaftAxis, (3,)), _f64(hubCoords, (3,))  # both alive across the call (lists are converted copies)
+        self._ck(self.lib.vlc_rotor_set_frame(self.h, ir, _ptr(sa), _ptr(hc)))
 
     def rotor_assignshed(self, ir, edge: str):
         self._ck(self.lib.vlc_rotor_assignshed(self.h, ir, {"LE": 0, "TE": 1}[edge]))
@@ -431,7 +437,8 @@ class Context:
         self._ck(self.lib.vlc_rotor_updatePrescribedWake(self.h, ir, deltaPsi, prescWakeGenNt, {"C": 0, "P": 1}[wakeType]))
 
     def rotor_put_pfwake_helix(self, ir, ib, helix, predicted=False):
-        self._ck(self.lib.vlc_rotor_put_pfwake_helix(self.h, ir, ib, int(predicted), _ptr(_f64(helix, (2,)))))
+        hx = _f64(helix, (2,))
+        self._ck(self.lib.vlc_rotor_put_pfwake_helix(self.h, ir, ib, int(predicted), _ptr(hx)))
 
     def rotor_get_pfwake(self, ir, ib, predicted=False):
         """-> (wapF (240, 13), (helixPitch, helixRadius)) of one blade."""
@@ -512,7 +519,8 @@ class Context:
                                                          zAxisAziFlap)])
 
     def rotor_put_sections(self, ir, ib, sec):
-        self._ck(self.lib.vlc_rotor_put_sections(self.h, ir, ib, _ptr(_f64(sec))))
+        a = _f64(sec)
+        self._ck(self.lib.vlc_rotor_put_sections(self.h, ir, ib, _ptr(a)))
 
     def rotor_calc_velCPTotal(self, ir):
         self._ck(self.lib.vlc_rotor_calc_velCPTotal(self.h, ir))
