@@ -66,9 +66,10 @@ int vlc_device_info(vlc_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, i
 int vlc_set_tuning(vlc_ctx* ctx, int targets_per_thread, int nsplit);
 /* Arithmetic of the two reciprocal square roots per pair (everything else is identical):
  *   0 = full: MUFU.RSQ64H seed + third-order Newton step, pair error ~1e-16 (default);
- *   1 = fast: second-order step, relative error of a pair <= 6.4e-13 (2 FP64 instructions fewer per pair,
- *       ~6 % faster): inside the 1e-12 per-call tolerance but with little margin -> opt-in only
- *       (DESIGN.md "Precision modes"). */
+ *   1 = fast: second-order step, rsqrt error <= 6.4e-13 (2 FP64 instructions fewer per pair, ~6 % faster).
+ *       OUTSIDE the 1e-12 per-target tolerance: the error enters the two end-point terms of a pair separately and
+ *       their difference cancels away from the filament (measured 1.4e-12 of a target's own scale) -> opt-in only,
+ *       never used for a parity or benchmark claim (DESIGN.md "Precision modes"). */
 int vlc_set_precision(vlc_ctx* ctx, int mode);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 int64_t vlc_launch_count(const vlc_ctx* ctx);

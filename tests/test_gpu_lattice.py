@@ -102,23 +102,46 @@ def test_strip_widths_and_targets_per_thread(ctx, oracle, W, T):
 
 
 def test_far_field_targets_per_target_tolerance(ctx, oracle):
-    """Targets 100 rotor radii away from the wake, mixed into a batch with wake-node targets: their own velocity scale
-    sum|terms| is ~1e-6 of the batch maximum, so only the PER-TARGET measure (tests/helpers.py:scaled_err) can see an
-    error there -- a dropped edge or a wrong merged strength on a low-influence target (round-1 review, item 6)."""
+    """Targets 10 / 100 / 1000 rotor radii away from the wake, mixed into a batch with wake-node targets: their own
+    velocity scale sum|terms| is 1e-2 ... 1e-6 of the batch maximum, so only the PER-TARGET measure
+    (tests/helpers.py:scaled_err) can see an error there -- a dropped edge or a wrong merged strength on a
+    low-influence target (round-1 review, item 6).  The pair formula r0.(r1/|r1| - r2/|r2|) loses log2(r/L) bits to
+    cancellation IN THE REFERENCE TOO (classdef.f90:499): its own double sum is 5e-15 from the exact sum at 100 R and
+    2e-11 at 1e6 R (measured with the long-double oracle).  Hence: 1e-12 per target out to 1000 R, and for the 1e6 R
+    group -- where the reference itself is not reproducible to 1e-12 -- no further from the exact sum than the
+    reference-order double sum is (factor 5, the bar the other tests use)."""
     from tests.helpers import scaled_err_batch
     lats = synth.multirotor(20000, seed=31, n_rotor=4, nb=2, S=8, F=16, with_wing=True)
     rng = np.random.default_rng(5)
     d = rng.normal(size=(600, 3))
     far = 100.0 * d / np.linalg.norm(d, axis=1)[:, None] * rng.uniform(0.8, 1.5, size=(600, 1))
-    P = np.concatenate([synth.targets_all(lats)[::7], far, 1e4 * far[:50]])
-    Vs, Vf, Vo, Vabs = _check(ctx, oracle, lats, P)
-    nfar = far.shape[0] + 50
-    scale_far, scale_near = Vabs[-nfar:].max(), Vabs[:-nfar].max()
-    assert scale_far < 1e-4 * scale_near                      # the far targets ARE invisible to the batch measure
-    e_far = scaled_err(Vs[-nfar:], Vo[-nfar:], Vabs[-nfar:])
-    print(f"far field: per-target scaled error {e_far:.3e} (batch form would report "
-          f"{scaled_err_batch(Vs[-nfar:], Vo[-nfar:], Vabs):.3e})")
-    assert e_far < TOL
+    groups = [("wake nodes", synth.targets_all(lats)[::7]), ("10 R", 0.1 * far[:200]), ("100 R", far),
+              ("1000 R", 10.0 * far[:200])]
+    P = np.concatenate([g[1] for g in groups])
+    Vs, Vf, Vo, Vabs = _check(ctx, oracle, lats, P)          # asserts 1e-12 PER TARGET on the whole batch, both kernels
+    off = 0
+    for name, Pg in groups:
+        sl = slice(off, off + Pg.shape[0])
+        off += Pg.shape[0]
+        print(f"{name:>10}: scale {Vabs[sl].max():.2e}  per-target error lattice {scaled_err(Vs[sl], Vo[sl], Vabs[sl]):.2e} "
+              f"flat {scaled_err(Vf[sl], Vo[sl], Vabs[sl]):.2e}  (batch-scaled form: "
+              f"{scaled_err_batch(Vs[sl], Vo[sl], Vabs):.1e})")
+    assert Vabs[-200:].max() < 1e-5 * Vabs[:groups[0][1].shape[0]].max()   # the far targets ARE invisible to the batch form
+    # 1e6 R: cancellation of ~26 bits in the reference's own formula
+    Px = 1e4 * far[:100]
+    keep = _upload(ctx, lats)
+    p1, p2, rvc, gam, flag = synth.flatten_all(lats)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, flag, Px)
+    Vl, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, flag, Px)
+    ref_err = scaled_err(Vo, Vl, Vabs)
+    for shared in (True, False):
+        ctx.set_shared_nodes(shared)
+        try:
+            e = scaled_err(_sweep(ctx, Px), Vl, Vabs)
+        finally:
+            ctx.set_shared_nodes(True)
+        print(f"     1e6 R: vs exact sum: {'lattice' if shared else 'flat'} kernel {e:.2e}, reference-order double sum {ref_err:.2e}")
+        assert e < 5 * ref_err
 
 
 @pytest.mark.parametrize("R,S,F", [(1, 1, 0), (1, 1, 3), (2, 1, 0), (1, 5, 2), (130, 2, 1), (3, 70, 0)])

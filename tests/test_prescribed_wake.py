@@ -366,7 +366,8 @@ def check_calc_skew(ctx, oracle, axisym):
     oracle.load().orc_rotor_calc_skew(rot.h)
     for ib in range(rot.nb):
         got, ref = ctx.rotor_get_nwake(0, ib, rot.nNwake, rot.ns), rot.waN(ib)
-        assert np.array_equal(got, ref), ib
+        # rows rowNear.. only: vlc_rotor_put_nwake transfers the active rows, the device's rows 1, 2 were never written
+        assert np.array_equal(got[:, 2:, :], ref[:, 2:, :]), (ib, np.argwhere(got[:, 2:, :] != ref[:, 2:, :])[:4])
         sk = ref[:, 2:, 49]
         assert np.all((sk >= 0) & (sk <= 1)) and np.any(sk > 0)
         assert np.all((sk > 0) | (np.abs(ref[:, 2:, 48]) <= np.finfo(float).eps) | (sk == 0))
