@@ -41,6 +41,14 @@ static inline long long __double_as_longlong(double a) {
   std::memcpy(&r, &a, sizeof r);
   return r;
 }
+static inline int __double2hiint(double a) { return (int)(__double_as_longlong(a) >> 32); }
+static inline int __double2loint(double a) { return (int)(__double_as_longlong(a) & 0xFFFFFFFFLL); }
+static inline double __hiloint2double(int hi, int lo) {
+  const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double r;
+  std::memcpy(&r, &b, sizeof r);
+  return r;
+}
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 
 // run kernel(args...) for every thread of a 1-D / 2-D grid, serially, in reverse order (the kernels must not depend on

@@ -59,7 +59,7 @@ __device__ __forceinline__ void edge_accumulate(const NodeQ& a, const NodeQ& b, 
   const double c2 = fma(cz, cz, fma(cy, cy, cx * cx));
   const double a1 = fma(gz, a.rz, fma(gy, a.ry, gx * a.rx));  // g r0.rU
   const double a2 = a1 - L2g;                                  // g r0.rV
-  const double w = rsqrt_fp64<false>(fma(c2, c2, K));
+  const double w = rsqrt_edge(fma(c2, c2, K));  // 3 FP64 instructions + an FP32 seed off the pipe (vlc_device.cuh)
   double sc = fma(-a2, b.u, a1 * a.u) * w;
   // classdef.f90:498 `if (r1Xr2Abs2 > eps*eps)`: c2 >= 0 orders like its bit pattern, eps^2 = 2^-104 =
   // 0x3970000000000000: one 64-bit integer compare + a select of sc's high word (guard_scale), nothing extra on the FP64 pipe.  (Predicating the three

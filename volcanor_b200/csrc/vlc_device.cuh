@@ -68,6 +68,66 @@ __device__ __forceinline__ double rsqrt_fp64(double x) {
   return fma(y, ep, y);
 }
 
+// Reciprocal square root for the EDGE term w = rsqrt(K + |c|^4) of the shared-node kernel (bs_lattice.cuh): its relative
+// error enters a pair's contribution as it is (no cancellation follows it -- unlike the node quantity u = 1/|r|, whose
+// error is amplified by r/L in r0.(r1 u1 - r2 u2) and therefore keeps the full refinement above), so 5e-14 is enough
+// for the 1e-12 per-target bar with a factor 20 to spare.  That allows ONE second-order Newton step if the seed carries
+// ~22.7 bits instead of MUFU.RSQ64H's 20, and such a seed is available off the FP64 pipe (round-1 review, item 3; ncu
+// r01j: 46 % of the issue slots idle, the ALU / XU pipes almost unused):
+//   x = 2^(2k+p) * 1.f, p in {-1, 0}  ->  m = 2^p * 1.f in [0.5, 2) as an FP32 number, built with two integer instructions
+//       from the top 23 fraction bits of x and the low bit of its exponent;
+//   ym = MUFU.RSQ(m) (FP32, error 2^-22.9; the truncation of x adds <= 2^-24);
+//   y = ym * 2^-k assembled bitwise as an FP64 number (three shifts, one add), yh = y/2 by an exponent decrement;
+//   result = y + yh*(1 - x y^2): THREE FP64 instructions (DMUL, DFMA with an immediate, DFMA) instead of five.
+// Measured over 2e6 log-uniform x in [1e-62, 1e60] (numpy model, tests/test_kernels_emul.py on the same source): seed
+// error <= 2^-22.7, result error <= 3.2e-14.  x must be a positive normal number (the callers' c2 guard discards every
+// other case: K + c2^2 >= 2^-208 whenever the result is used).
+// VLC_EDGE_RSQRT: 0 = rsqrt_fp64<false> (round 1; DEFAULT), 1 = this.
+// MEASURED (r02b, profiles/r02b_edge_rsqrt.md): 1 is SLOWER on B200 -- 274.2 ms instead of 259.6 ms per sweep at 1e6
+// filaments although the loop holds 956 instead of 1020 FP64 instructions: the 8 integer / shift instructions per seed
+// (557 instead of 266 non-FP64 instructions per loop iteration) cost about one issue cycle each, i.e. 0.44 of an FP64
+// instruction, more than the two FP64 instructions they save.  The "idle" 46 % of the issue slots are not free: with two
+// warps per scheduler the FP64 unit is fed only while nothing else competes for the dispatch port.  Kept as an option
+// for the record; every non-FP64 instruction REMOVED from the loop is worth the same 0.44.
+#ifndef VLC_EDGE_RSQRT
+#define VLC_EDGE_RSQRT 0
+#endif
+__device__ __forceinline__ double rsqrt_edge(double x) {
+#if VLC_EDGE_RSQRT == 0
+  return rsqrt_fp64<false>(x);
+#else
+  const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+#if defined(__CUDA_EMUL__)
+  const unsigned v = (hi << 3) | (lo >> 29);
+#else
+  const unsigned v = __funnelshift_l(lo, hi, 3);                 // [e8..e0 | fraction bits 51..29]
+#endif
+  const unsigned fb = (v & 0x00FFFFFFu) | 0x3F000000u;            // exponent field 126 + e0: m in [0.5, 2)
+  float ym;
+#if defined(__CUDA_EMUL__)
+  {
+    float m;
+    std::memcpy(&m, &fb, sizeof m);
+    ym = 1.0f / std::sqrt(m);
+  }
+  unsigned yb;
+  std::memcpy(&yb, &ym, sizeof yb);
+#else
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ym) : "f"(__uint_as_float(fb)));
+  const unsigned yb = __float_as_uint(ym);
+#endif
+  // k = ((e11 | 1) - 1023)/2;  high word of ym as FP64 = (yb >> 3) + (896 << 20);  minus k << 20:
+  const unsigned B = (hi & 0x7FF00000u) | 0x00100000u;
+  const unsigned hy = (yb >> 3) + 0x57F80000u - (B >> 1);
+  const unsigned ly = yb << 29;
+  const double y = __hiloint2double((int)hy, (int)ly);
+  const double yh = __hiloint2double((int)(hy - 0x00100000u), (int)ly);
+  const double t = y * y;
+  const double e = fma(-x, t, 1.0);
+  return fma(yh, e, y);
+#endif
+}
+
 // sc <- (c2 > eps^2) ? sc : 0 without touching the FP64 pipe.  VLC_GUARD_HI (default): only the HIGH word of sc is
 // selected (one SEL instead of two): a guarded sc becomes {lo, 0} = a denormal < 2^-1042 (whatever sc was, NaN and
 // Inf included), and every |c_i| <= 2^-52 there (c2 <= 2^-104), so |c_i * sc| < 2^-1094 rounds to zero in the three
