@@ -52,6 +52,32 @@ enum {
 /* ---- context ---------------------------------------------------------------------------- */
 int vlc_create(int device, vlc_ctx** out);
 int vlc_destroy(vlc_ctx* ctx);
+/*
+ * Several GPUs of one box behind ONE handle (SURVEY 8b "library owns ... NCCL communicators", 8e).  The reference is a
+ * single process whose wake loops call vind_onNwake_byRotor target by target (main.f90:814-841 ->
+ * libCommon.f90:114-171); its call sites cannot hand out slices.  vlc_create_multi returns a context that LOOKS like a
+ * single-GPU one: every entry point that changes state is replicated on all n_devices members (each holds the whole
+ * wake; the O(N) mutators run redundantly), every host-pointer sweep (vlc_vind, vlc_rotor_vind_*,
+ * vlc_vind_on{N,F}wake_byRotor, vlc_gridgen) gives each member a contiguous slice of the targets against ALL sources,
+ * and vlc_wake_sweep of the resident path all-gathers the velocity slices -- ncclAllGather over NVLink, 24 bytes per
+ * target, once per predictor and once per corrector stage -- so that the replicas stay bit-identical.  Readers
+ * (vlc_rotor_get_*, ..._out arguments) are served by the first member.  Entry points that take DEVICE pointers address
+ * one device and return VLC_ERR_STATE on such a handle.  devices == NULL means 0..n_devices-1.  A list that repeats a
+ * device (group logic on a single-GPU box) and VLC_GROUP_NCCL=0 exchange the slices with peer copies instead of NCCL.
+ * One worker thread per member issues its launches, so the caller stays single-threaded.
+ */
+int vlc_create_multi(int n_devices, const int* devices, vlc_ctx** out);
+/*
+ * The same partition with ONE PROCESS PER GPU (torchrun, or an MPI build of the driver): rank 0 obtains a 128-byte id
+ * (ncclGetUniqueId), the launcher distributes it, every rank joins with its own single-GPU context.  From then on
+ * vlc_wake_sweep and the host-pointer sweeps are COLLECTIVE: every rank calls them with the same arguments, sweeps its
+ * slice, and all ranks end up with the complete result (ncclAllGather inside the library).  world = 1 leaves the
+ * context as it is.  The communicator is destroyed by vlc_destroy.
+ */
+int vlc_comm_unique_id(void* id128);
+int vlc_comm_init_rank(vlc_ctx* ctx, int world, int rank, const void* id128);
+/* world, rank of this handle in the target partition; transport: 0 = single GPU, 1 = NCCL, 2 = peer copies */
+int vlc_comm_info(const vlc_ctx* ctx, int* world, int* rank, int* transport);
 const char* vlc_last_error(const vlc_ctx* ctx); /* ctx may be NULL: error of the last failed vlc_create */
 const char* vlc_version(void);
 /* Run on the caller's cudaStream_t (cuda_stream == NULL is the legacy default stream, which is what

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--short-caradonna", action="store_true", help="nt 40, nNwake 12 (roll-up inside a short window)")
     ap.add_argument("--cp", action="store_true",
                     help="also run the collocation-point stage (RHS, solve, map_gam, loads: C ABI tier 2c) on every rank's device")
+    ap.add_argument("--lib-comm", action="store_true",
+                    help="the LIBRARY owns the communicator (vlc_comm_init_rank): the driver calls plain vlc_wake_sweep, which "
+                         "shards the targets and all-gathers the velocity slices itself (ncclAllGather); needs one GPU per rank")
     args = ap.parse_args()
 
     import torch
@@ -100,7 +103,14 @@ def main():
 
     CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_long)
     cb = CB(exchange)
-    if world > 1:
+    if world > 1 and args.lib_comm:
+        if not own_gpu:
+            raise SystemExit("--lib-comm needs one GPU per rank (NCCL)")
+        uid = [vb.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_rank(world, rank, uid[0])
+        assert ctx.comm_info() == {"world": world, "rank": rank, "transport": "nccl"}
+    elif world > 1:
         lib.case_gpu_hooks_set_sharding(h, world, rank, xbuf.data_ptr(), world * per_max, C.cast(cb, C.c_void_p), None)
 
     c.init()
@@ -128,10 +138,10 @@ def main():
         gathered = [(hist.tobytes(), wall, errors)]
     if rank == 0:
         identical = all(g[0] == gathered[0][0] for g in gathered)
-        out = {"case": args.case, "world": world, "exchange": ("nccl" if own_gpu else "gloo via host") if world > 1 else "none",
+        out = {"case": args.case, "world": world, "exchange": ("nccl inside the library" if args.lib_comm else "nccl" if own_gpu else "gloo via host") if world > 1 else "none",
                "steps": len(hist) - 1, "wall_s": max(g[1] for g in gathered), "ok": ok and not any(g[2] for g in gathered),
                "errors": [e for g in gathered for e in g[2]][:3], "ranks_identical": identical,
-               "exchanges": int(lib.case_gpu_hooks_exchanges(h)), "final_CT_or_CL": float(hist[-1, 0]),
+               "exchanges": int(lib.case_gpu_hooks_exchanges(h)) if not args.lib_comm else None, "final_CT_or_CL": float(hist[-1, 0]),
                "cp_stage_on_device": bool(args.cp)}
         out["timesteps_per_s"] = out["steps"] / out["wall_s"] if out["wall_s"] > 0 else 0.0
         if "ref_ForceNonDim" in fx and not args.short_caradonna:

@@ -68,6 +68,26 @@ _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
 
+def _preload_torch_nccl():
+    """The library binds NCCL at run time by soname (csrc/group.hpp).  In a Python process that will also import torch,
+    the copy that ships with torch (nvidia/nccl/lib, newer than the system's) must be the one in the process -- a system
+    libnccl.so.2 loaded first would be picked up by torch's own DT_NEEDED and break its import.  Load torch's copy first
+    when there is one; a plain C / Fortran driver never gets here and uses the system library."""
+    if "torch" in sys.modules:
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            for d in spec.submodule_search_locations:
+                so = Path(d) / "lib" / "libnccl.so.2"
+                if so.exists():
+                    C.CDLL(str(so), mode=C.RTLD_GLOBAL)
+                    return
+    except Exception:
+        pass
+
+
 def load_library() -> C.CDLL:
     """Load the CUDA library.  Fails loudly if it has not been built (no fallback)."""
     global _LIB
@@ -82,6 +102,10 @@ def load_library() -> C.CDLL:
     sig = {
         "vlc_create": (i32, [i32, C.POINTER(_vp)]),
         "vlc_destroy": (i32, [_vp]),
+        "vlc_create_multi": (i32, [i32, C.POINTER(i32), C.POINTER(_vp)]),
+        "vlc_comm_unique_id": (i32, [_vp]),
+        "vlc_comm_init_rank": (i32, [_vp, i32, i32, _vp]),
+        "vlc_comm_info": (i32, [_vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "vlc_last_error": (C.c_char_p, [_vp]),
         "vlc_version": (C.c_char_p, []),
         "vlc_set_stream": (i32, [_vp, _vp, i32]),
@@ -202,14 +226,47 @@ def _ptr(a) -> int | None:
 class Context:
     """One library context = one GPU.  Mirrors the reference call sites (see the header)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
+        """device: one GPU.  devices = [d0, d1, ...]: ONE handle over several GPUs of the box (vlc_create_multi): state is
+        replicated, sweeps are target-sharded, the wake sweep all-gathers inside the library."""
         self.lib = load_library()
         h = _vp()
-        rc = self.lib.vlc_create(device, C.byref(h))
+        if devices is not None:
+            _preload_torch_nccl()
+            devs = [int(d) for d in devices]
+            arr = (C.c_int * len(devs))(*devs)
+            rc = self.lib.vlc_create_multi(len(devs), arr, C.byref(h))
+            device = devs[0]
+        else:
+            rc = self.lib.vlc_create(device, C.byref(h))
         if rc != 0:
             raise VlcError(f"vlc_create failed ({rc}): {self.lib.vlc_last_error(None).decode()}")
         self.h = h
         self.device = device
+
+    # -- multi-GPU data plane behind the ABI ----------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id made by rank 0; the launcher hands it to every rank (comm_init_rank)."""
+        _preload_torch_nccl()
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.vlc_comm_unique_id(buf)
+        if rc != 0:
+            raise VlcError(f"vlc_comm_unique_id failed ({rc}): {lib.vlc_last_error(None).decode()}")
+        return buf.raw
+
+    def comm_init_rank(self, world: int, rank: int, unique_id: bytes | None):
+        """One process per GPU: join the library-owned communicator; wake_sweep and the host-pointer sweeps become
+        collective (same arguments on every rank)."""
+        _preload_torch_nccl()
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._ck(self.lib.vlc_comm_init_rank(self.h, world, rank, buf))
+
+    def comm_info(self) -> dict:
+        w, r, t = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.vlc_comm_info(self.h, C.byref(w), C.byref(r), C.byref(t)))
+        return {"world": w.value, "rank": r.value, "transport": {0: "single", 1: "nccl", 2: "peer"}[t.value]}
 
     # -- plumbing ---------------------------------------------------------------------------
     def _ck(self, rc: int):

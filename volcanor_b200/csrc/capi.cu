@@ -22,6 +22,7 @@
 #include "wake_state.cuh"
 #include "wake_records.cuh"
 #include "cp_stage.cuh"
+#include "group.hpp"
 
 namespace {
 
@@ -138,6 +139,21 @@ struct vlc_ctx {
   cusolverDnHandle_t solver = nullptr;
   DevBuf solver_work;
   int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
+  // multi-GPU data plane (group.hpp): this context's place in the target partition, its NCCL communicator (library-owned),
+  // and -- for the members of an in-process group made by vlc_create_multi -- the group
+  int rank = 0, world = 1;
+  vlc::grp::NcclComm comm = nullptr;
+  struct vlc_group* group = nullptr;
+  bool is_leader = false;
+};
+
+// One process, several GPUs: members[0] is the context the caller holds (the leader), members[1..] are replicas on the
+// other devices, each driven by its own worker thread.
+struct vlc_group {
+  std::vector<vlc_ctx*> members;
+  vlc::grp::Workers* workers = nullptr;
+  vlc::grp::Barrier* barrier = nullptr;
+  bool nccl = false;
 };
 
 namespace {
@@ -146,6 +162,40 @@ int fail(vlc_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
   return code;
 }
+
+// true while this thread executes ONE member's share of a replicated call (always on the worker threads): nested entry
+// points then act on that member alone
+thread_local bool t_in_member = false;
+
+// Run fn on every member of the leader's group, each on its own thread and device.  First failure (in member order) is
+// returned with that member's message.
+int group_all(vlc_ctx* L, const std::function<int(vlc_ctx*)>& fn) {
+  vlc_group* g = L->group;
+  const int rc = g->workers->run([&](int k) -> int {
+    const bool prev = t_in_member;
+    t_in_member = true;
+    vlc_ctx* m = g->members[k];
+    int r = (cudaSetDevice(m->device) == cudaSuccess) ? fn(m) : fail(m, VLC_ERR_CUDA, "cudaSetDevice failed");
+    t_in_member = prev;
+    return r;
+  });
+  if (rc)
+    for (size_t k = 1; k < g->members.size(); ++k)
+      if (g->workers->results[k] && !g->workers->results[0]) {
+        L->err = "[member " + std::to_string(k) + ", device " + std::to_string(g->members[k]->device) + "] " + g->members[k]->err;
+        break;
+      }
+  return rc;
+}
+// Replicated entry point: on a group's leader, run CALL (an expression in `m`) on every member.
+#define VLC_GROUP(c, CALL)                                  \
+  if ((c)->group && (c)->is_leader && !t_in_member)         \
+  return group_all((c), [&](vlc_ctx* m) -> int { return CALL; })
+// Entry points that take DEVICE pointers address one device: not available on a group handle.
+#define VLC_NO_GROUP(c)                                                                                           \
+  if ((c)->group && !t_in_member)                                                                                 \
+  return fail((c), VLC_ERR_STATE, std::string(__func__) + ": device-pointer entry points address ONE device; a context made by " \
+                                  "vlc_create_multi spans several -- use the host-pointer / resident entry points")
 
 #define CUDA_OK(c, expr)                                                                        \
   do {                                                                                          \
@@ -496,19 +546,67 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   return VLC_OK;
 }
 
-// host-buffer sweep: H2D targets, sweep, D2H velocities (synchronous)
+// In-place all-gather of equal slots on the context's stream: slot k = doubles [k*cnt, (k+1)*cnt) of `buf`, this rank's
+// slot is filled.  NCCL when the context has a communicator (vlc_comm_init_rank; vlc_create_multi on distinct devices).
+// `peer_buf(member)` names the same buffer in another member of an in-process group for the fallback without NCCL: every
+// member waits until all slots are complete, pulls the other slots with peer copies, and waits again before anybody may
+// overwrite its slot.
+int allgather_slots(vlc_ctx* c, double* buf, size_t cnt, const std::function<double*(vlc_ctx*)>& peer_buf) {
+  if (c->world <= 1 || cnt == 0) return VLC_OK;
+  if (c->comm) {
+    vlc::grp::Nccl& n = vlc::grp::Nccl::get();
+    const int r = n.AllGather(buf + (size_t)c->rank * cnt, buf, cnt, vlc::grp::kNcclFloat64, c->comm, (void*)c->stream);
+    if (r != 0) return fail(c, VLC_ERR_CUDA, std::string("ncclAllGather: ") + (n.GetErrorString ? n.GetErrorString(r) : "?"));
+    c->launches++;
+    return VLC_OK;
+  }
+  if (c->group && t_in_member) {
+    vlc_group* g = c->group;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    g->barrier->wait();
+    for (vlc_ctx* o : g->members) {
+      if (o == c) continue;
+      CUDA_OK(c, cudaMemcpyPeerAsync(buf + (size_t)o->rank * cnt, c->device, peer_buf(o) + (size_t)o->rank * cnt, o->device,
+                                     cnt * sizeof(double), c->stream));
+    }
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    g->barrier->wait();
+    return VLC_OK;
+  }
+  return fail(c, VLC_ERR_STATE, "world > 1 without a communicator (vlc_comm_init_rank) or a group (vlc_create_multi)");
+}
+
+// host-buffer sweep: H2D targets, sweep, D2H velocities (synchronous).  With world > 1 the call is COLLECTIVE (every
+// member / rank makes it with the same arguments) and each takes its contiguous slice of the targets against all
+// sources (libCommon.f90:132-139 is a parallel loop over targets): the members of an in-process group write their
+// slices of V straight into the caller's array; one process per GPU all-gathers the slices so that every rank returns
+// the whole V.
 int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, const double* P, double* V,
                const SourceSet* shared = nullptr) {
   if (m <= 0) return VLC_OK;
   if (!P || !V) return fail(c, VLC_ERR_ARG, "null target / output pointer");
-  int rc = reserve(c, c->stage_P, 3 * (size_t)m);
+  vlc::grp::Shard sh;
+  sh.per = m;
+  sh.hi = m;
+  if (c->world > 1) sh = vlc::grp::shard_range(m, c->world, c->rank);
+  const long long ml = sh.count();
+  const bool gather = c->world > 1 && !c->group;
+  int rc = reserve(c, c->stage_P, 3 * (size_t)std::max(ml, 1LL));
   if (rc) return rc;
-  rc = reserve(c, c->stage_V, 3 * (size_t)m);
+  rc = reserve(c, c->stage_V, gather ? 3 * (size_t)sh.per * c->world : 3 * (size_t)std::max(ml, 1LL));
   if (rc) return rc;
-  CUDA_OK(c, cudaMemcpyAsync(c->stage_P.p, P, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
-  rc = shared ? sweep_shared(c, *shared, m, c->stage_P.p, c->stage_V.p) : sweep(c, src, n_pad, m, c->stage_P.p, c->stage_V.p);
-  if (rc) return rc;
-  CUDA_OK(c, cudaMemcpyAsync(V, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  double* dV = c->stage_V.p + (gather ? 3 * (size_t)sh.per * c->rank : 0);
+  if (ml > 0) {
+    CUDA_OK(c, cudaMemcpyAsync(c->stage_P.p, P + 3 * sh.lo, sizeof(double) * 3 * (size_t)ml, cudaMemcpyHostToDevice, c->stream));
+    rc = shared ? sweep_shared(c, *shared, ml, c->stage_P.p, dV) : sweep(c, src, n_pad, ml, c->stage_P.p, dV);
+    if (rc) return rc;
+  }
+  if (gather) {
+    if ((rc = allgather_slots(c, c->stage_V.p, 3 * (size_t)sh.per, nullptr))) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(V, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  } else if (ml > 0) {
+    CUDA_OK(c, cudaMemcpyAsync(V + 3 * sh.lo, dV, sizeof(double) * 3 * (size_t)ml, cudaMemcpyDeviceToHost, c->stream));
+  }
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }
@@ -865,7 +963,22 @@ extern "C" int vlc_create(int device, vlc_ctx** out) {
 
 extern "C" int vlc_destroy(vlc_ctx* c) {
   if (!c) return VLC_OK;
+  if (c->group && c->is_leader) {  // a group handle: stop the workers, then destroy every member (the leader last)
+    vlc_group* g = c->group;
+    delete g->workers;  // joins the threads
+    g->workers = nullptr;
+    for (vlc_ctx* m : g->members) m->group = nullptr;
+    for (size_t k = 1; k < g->members.size(); ++k) vlc_destroy(g->members[k]);
+    delete g->barrier;
+    delete g;
+    c->is_leader = false;
+  }
   cudaSetDevice(c->device);
+  if (c->comm) {
+    cudaStreamSynchronize(c->stream);
+    vlc::grp::Nccl::get().CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
   cudaStreamSynchronize(c->stream);
   for (auto& s : c->sets) {
     release(s.rec);
@@ -931,10 +1044,144 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   return VLC_OK;
 }
 
+extern "C" int vlc_create_multi(int n_devices, const int* devices, vlc_ctx** out) {
+  if (!out) return VLC_ERR_ARG;
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > 64) {
+    g_create_error = "vlc_create_multi: n_devices outside 1..64";
+    return VLC_ERR_ARG;
+  }
+  std::vector<int> dev(n_devices);
+  for (int k = 0; k < n_devices; ++k) dev[k] = devices ? devices[k] : k;
+  vlc_group* g = new vlc_group();
+  auto undo = [&](int rc) {
+    for (vlc_ctx* m : g->members) {
+      m->group = nullptr;
+      m->is_leader = false;
+      vlc_destroy(m);
+    }
+    delete g;
+    return rc;
+  };
+  for (int k = 0; k < n_devices; ++k) {
+    vlc_ctx* m = nullptr;
+    const int rc = vlc_create(dev[k], &m);
+    if (rc) return undo(rc);  // g_create_error is set by vlc_create
+    m->rank = k;
+    m->world = n_devices;
+    g->members.push_back(m);
+  }
+  if (n_devices == 1) {  // a group of one is a plain context
+    vlc_ctx* m = g->members[0];
+    delete g;
+    *out = m;
+    return VLC_OK;
+  }
+  // NCCL serves a device list without repetitions (one rank per GPU).  A list that names a device twice -- the way the
+  // group path is exercised on a single-GPU box -- and VLC_GROUP_NCCL=0 use peer copies instead.
+  bool distinct = true;
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = a + 1; b < n_devices; ++b) distinct = distinct && dev[a] != dev[b];
+  const char* env = std::getenv("VLC_GROUP_NCCL");
+  const bool want_nccl = distinct && !(env && env[0] == '0');
+  if (want_nccl) {
+    vlc::grp::Nccl& n = vlc::grp::Nccl::get();
+    if (n.ok) {
+      std::vector<vlc::grp::NcclComm> comms(n_devices, nullptr);
+      const int r = n.CommInitAll(comms.data(), n_devices, dev.data());
+      if (r == 0) {
+        for (int k = 0; k < n_devices; ++k) g->members[k]->comm = comms[k];
+        g->nccl = true;
+      } else {
+        g_create_error = std::string("ncclCommInitAll failed: ") + (n.GetErrorString ? n.GetErrorString(r) : "?");
+        return undo(VLC_ERR_CUDA);
+      }
+    } else if (env && env[0] == '1') {
+      g_create_error = "VLC_GROUP_NCCL=1 but " + n.why;
+      return undo(VLC_ERR_CUDA);
+    }
+  }
+  if (!g->nccl)  // peer copies between the members' buffers (cudaMemcpyPeerAsync stages through the host without it)
+    for (int a = 0; a < n_devices; ++a)
+      for (int b = 0; b < n_devices; ++b)
+        if (dev[a] != dev[b]) {
+          int can = 0;
+          cudaDeviceCanAccessPeer(&can, dev[a], dev[b]);
+          if (can) {
+            cudaSetDevice(dev[a]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(dev[b], 0);
+            if (e != cudaSuccess) cudaGetLastError();  // already enabled: fine
+          }
+        }
+  cudaSetDevice(dev[0]);
+  g->barrier = new vlc::grp::Barrier(n_devices);
+  g->workers = new vlc::grp::Workers(n_devices);
+  for (vlc_ctx* m : g->members) m->group = g;
+  g->members[0]->is_leader = true;
+  *out = g->members[0];
+  return VLC_OK;
+}
+
+extern "C" int vlc_comm_unique_id(void* id128) {
+  if (!id128) return VLC_ERR_ARG;
+  vlc::grp::Nccl& n = vlc::grp::Nccl::get();
+  if (!n.ok) {
+    g_create_error = n.why;
+    return VLC_ERR_STATE;
+  }
+  vlc::grp::NcclUniqueId id;
+  const int r = n.GetUniqueId(&id);
+  if (r != 0) {
+    g_create_error = std::string("ncclGetUniqueId: ") + (n.GetErrorString ? n.GetErrorString(r) : "?");
+    return VLC_ERR_CUDA;
+  }
+  std::memcpy(id128, &id, sizeof id);
+  return VLC_OK;
+}
+
+extern "C" int vlc_comm_init_rank(vlc_ctx* c, int world, int rank, const void* id128) {
+  CHECK_CTX(c);
+  if (c->group) return fail(c, VLC_ERR_STATE, "vlc_comm_init_rank on a context made by vlc_create_multi");
+  if (world < 1 || rank < 0 || rank >= world) return fail(c, VLC_ERR_ARG, "bad world / rank");
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (c->comm) {
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    vlc::grp::Nccl::get().CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  c->world = 1;
+  c->rank = 0;
+  if (world == 1) return VLC_OK;
+  if (!id128) return fail(c, VLC_ERR_ARG, "null unique id");
+  vlc::grp::Nccl& n = vlc::grp::Nccl::get();
+  if (!n.ok) return fail(c, VLC_ERR_STATE, n.why);
+  vlc::grp::NcclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  const int r = n.CommInitRank(&c->comm, world, id, rank);
+  if (r != 0) {
+    c->comm = nullptr;
+    return fail(c, VLC_ERR_CUDA, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(r) : "?"));
+  }
+  c->world = world;
+  c->rank = rank;
+  return VLC_OK;
+}
+
+extern "C" int vlc_comm_info(const vlc_ctx* c, int* world, int* rank, int* transport) {
+  if (!c) return VLC_ERR_ARG;
+  if (world) *world = c->world;
+  if (rank) *rank = c->rank;
+  if (transport) *transport = c->world <= 1 ? 0 : (c->comm ? 1 : 2);  // 0 = single, 1 = NCCL, 2 = peer copies
+  return VLC_OK;
+}
+
 extern "C" const char* vlc_last_error(const vlc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int vlc_set_stream(vlc_ctx* c, void* s, int use_own) {
   CHECK_CTX(c);
+  if (c->group && !use_own) return fail(c, VLC_ERR_STATE, "a caller's stream belongs to one device: a group runs on its members' own streams");
+  VLC_GROUP(c, vlc_set_stream(m, nullptr, 1));
   c->stream = use_own ? c->own_stream : (cudaStream_t)s;  // s == NULL is the legacy default stream
   if (c->solver) cusolverDnSetStream(c->solver, c->stream);
   return VLC_OK;
@@ -942,6 +1189,7 @@ extern "C" int vlc_set_stream(vlc_ctx* c, void* s, int use_own) {
 
 extern "C" int vlc_sync(vlc_ctx* c) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_sync(m));
   int rc = bind_device(c);
   if (rc) return rc;
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -959,6 +1207,7 @@ extern "C" int vlc_device_info(vlc_ctx* c, int* sm, int* maj, int* min, int64_t*
 
 extern "C" int vlc_set_tuning(vlc_ctx* c, int T, int nsplit) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_set_tuning(m, T, nsplit));
   if (T < 0 || T > 4 || nsplit < 0) return fail(c, VLC_ERR_ARG, "targets_per_thread in 0..4, nsplit >= 0");
   c->tune_T = T;
   c->tune_nsplit = nsplit;
@@ -967,12 +1216,21 @@ extern "C" int vlc_set_tuning(vlc_ctx* c, int T, int nsplit) {
 
 extern "C" int vlc_set_precision(vlc_ctx* c, int mode) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_set_precision(m, mode));
   if (mode != 0 && mode != 1) return fail(c, VLC_ERR_ARG, "precision mode must be 0 (full) or 1 (fast)");
   c->fast = (mode == 1);
   return VLC_OK;
 }
 
-extern "C" int64_t vlc_launch_count(const vlc_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t vlc_launch_count(const vlc_ctx* c) {
+  if (!c) return 0;
+  if (c->group && c->is_leader) {  // all members' kernels
+    long long n = 0;
+    for (const vlc_ctx* m : c->group->members) n += m->launches;
+    return n;
+  }
+  return c->launches;
+}
 
 extern "C" int vlc_source_tile(void) { return kTile; }
 
@@ -981,6 +1239,7 @@ extern "C" int vlc_source_tile(void) { return kTile; }
 extern "C" int vlc_set_sources_dev(vlc_ctx* c, int set, int64_t n, const double* p1, const double* p2,
                                    const double* rvc, const double* gam, const uint8_t* flag) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
@@ -1004,6 +1263,7 @@ extern "C" int vlc_set_sources_dev(vlc_ctx* c, int set, int64_t n, const double*
 extern "C" int vlc_set_sources(vlc_ctx* c, int set, int64_t n, const double* p1, const double* p2, const double* rvc,
                                const double* gam, const uint8_t* flag) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_set_sources(m, set, n, p1, p2, rvc, gam, flag));
   int rc = bind_device(c);
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
@@ -1044,6 +1304,7 @@ extern "C" int64_t vlc_num_sources(const vlc_ctx* c, int set) {
 
 extern "C" int vlc_vind_dev(vlc_ctx* c, int set, int64_t m, const double* dP, double* dV) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
@@ -1057,6 +1318,7 @@ extern "C" int vlc_vind_dev(vlc_ctx* c, int set, int64_t m, const double* dP, do
 extern "C" int vlc_vind_range_dev(vlc_ctx* c, int set, int64_t first, int64_t count, int64_t m, const double* dP,
                                   double* dV) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
@@ -1073,6 +1335,7 @@ extern "C" int vlc_vind_range_dev(vlc_ctx* c, int set, int64_t first, int64_t co
 
 extern "C" int vlc_vind(vlc_ctx* c, int set, int64_t m, const double* P, double* V) {
   CHECK_CTX(c);
+  if (c->group && c->is_leader && !t_in_member) return group_all(c, [&](vlc_ctx* g_) -> int { return vlc_vind(g_, set, m, P, V); });
   int rc = bind_device(c);
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
@@ -1086,6 +1349,7 @@ extern "C" int vlc_vind(vlc_ctx* c, int set, int64_t m, const double* P, double*
 
 extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int nNwake, int nFwake, int surfaceType) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_define(m, ir, nb, nc, ns, nNwake, nFwake, surfaceType));
   if (ir < 0 || ir > 1023) return fail(c, VLC_ERR_ARG, "rotor index out of range");
   if (nb < 1 || nc < 1 || ns < 1 || nNwake < 0 || nFwake < 0) return fail(c, VLC_ERR_ARG, "bad rotor sizes");
   if ((int)c->rotors.size() <= ir) c->rotors.resize(ir + 1);
@@ -1172,6 +1436,7 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
 
 extern "C" int vlc_rotor_set_rows(vlc_ctx* c, int ir, int rowNear, int rowFar) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_set_rows(m, ir, rowNear, rowFar));
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
   if (rowNear < 1 || rowNear > r->nNwake + 1 || rowFar < 1 || rowFar > r->nFwake + 1)
@@ -1184,6 +1449,7 @@ extern "C" int vlc_rotor_set_rows(vlc_ctx* c, int ir, int rowNear, int rowFar) {
 
 extern "C" int vlc_rotor_put_wing(vlc_ctx* c, int ir, int ib, const double* wiP) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_wing(m, ir, ib, wiP));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1198,6 +1464,7 @@ extern "C" int vlc_rotor_put_wing(vlc_ctx* c, int ir, int ib, const double* wiP)
 
 extern "C" int vlc_rotor_put_wing_gam(vlc_ctx* c, int ir, int ib, const double* gam) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_wing_gam(m, ir, ib, gam));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1213,6 +1480,7 @@ extern "C" int vlc_rotor_put_wing_gam(vlc_ctx* c, int ir, int ib, const double* 
 
 extern "C" int vlc_rotor_put_nwake(vlc_ctx* c, int ir, int ib, int predicted, const double* waN) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_nwake(m, ir, ib, predicted, waN));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1236,6 +1504,7 @@ extern "C" int vlc_rotor_put_nwake(vlc_ctx* c, int ir, int ib, int predicted, co
 
 extern "C" int vlc_rotor_put_fwake(vlc_ctx* c, int ir, int ib, int predicted, const double* waF) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_fwake(m, ir, ib, predicted, waF));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1255,6 +1524,7 @@ extern "C" int vlc_rotor_put_fwake(vlc_ctx* c, int ir, int ib, int predicted, co
 
 extern "C" int vlc_rotor_put_pfwake(vlc_ctx* c, int ir, int ib, int predicted, const double* wapF) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_pfwake(m, ir, ib, predicted, wapF));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1269,6 +1539,7 @@ extern "C" int vlc_rotor_put_pfwake(vlc_ctx* c, int ir, int ib, int predicted, c
 
 extern "C" int vlc_rotor_vind_bywing(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
   CHECK_CTX(c);
+  if (c->group && c->is_leader && !t_in_member) return group_all(c, [&](vlc_ctx* g_) -> int { return vlc_rotor_vind_bywing(g_, ir, m, P, V); });
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1279,6 +1550,7 @@ extern "C" int vlc_rotor_vind_bywing(vlc_ctx* c, int ir, int64_t m, const double
 
 extern "C" int vlc_rotor_vind_bywake(vlc_ctx* c, int ir, int predicted, int64_t m, const double* P, double* V) {
   CHECK_CTX(c);
+  if (c->group && c->is_leader && !t_in_member) return group_all(c, [&](vlc_ctx* g_) -> int { return vlc_rotor_vind_bywake(g_, ir, predicted, m, P, V); });
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1291,6 +1563,7 @@ extern "C" int vlc_rotor_vind_bywake(vlc_ctx* c, int ir, int predicted, int64_t 
 
 extern "C" int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
   CHECK_CTX(c);
+  if (c->group && c->is_leader && !t_in_member) return group_all(c, [&](vlc_ctx* g_) -> int { return vlc_rotor_vind_bywing_boundVortices(g_, ir, m, P, V); });
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1301,6 +1574,7 @@ extern "C" int vlc_rotor_vind_bywing_boundVortices(vlc_ctx* c, int ir, int64_t m
 
 extern "C" int vlc_rotor_vind_bywing_chordwiseVortices(vlc_ctx* c, int ir, int64_t m, const double* P, double* V) {
   CHECK_CTX(c);
+  if (c->group && c->is_leader && !t_in_member) return group_all(c, [&](vlc_ctx* g_) -> int { return vlc_rotor_vind_bywing_chordwiseVortices(g_, ir, m, P, V); });
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1311,6 +1585,7 @@ extern "C" int vlc_rotor_vind_bywing_chordwiseVortices(vlc_ctx* c, int ir, int64
 
 extern "C" int vlc_rotor_vind(vlc_ctx* c, int ir, int predicted, int64_t m, const double* P, double* V) {
   CHECK_CTX(c);
+  if (c->group && c->is_leader && !t_in_member) return group_all(c, [&](vlc_ctx* g_) -> int { return vlc_rotor_vind(g_, ir, predicted, m, P, V); });
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1324,6 +1599,7 @@ extern "C" int vlc_rotor_vind(vlc_ctx* c, int ir, int predicted, int64_t m, cons
 extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake, int rows, int cols, int ld,
                                         int predicted, double* vindArray) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_vind_onNwake_byRotor(m, ir, Nwake, rows, cols, ld, predicted, vindArray));
   if (rows < 0 || cols < 1 || ld < rows) return fail(c, VLC_ERR_ARG, "bad Nwake slice shape");
   if (rows == 0) return VLC_OK;
   if (!Nwake || !vindArray) return fail(c, VLC_ERR_ARG, "null pointer");
@@ -1345,6 +1621,7 @@ extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake,
 extern "C" int vlc_vind_onFwake_byRotor(vlc_ctx* c, int ir, const double* Fwake, int rows, int predicted,
                                         double* vindArray) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_vind_onFwake_byRotor(m, ir, Fwake, rows, predicted, vindArray));
   if (rows < 0) return fail(c, VLC_ERR_ARG, "rows < 0");
   if (rows == 0) return VLC_OK;
   if (!Fwake || !vindArray) return fail(c, VLC_ERR_ARG, "null pointer");
@@ -1367,6 +1644,7 @@ int ensure_solver(vlc_ctx* c) {
 
 extern "C" int vlc_rotor_calcAIC(vlc_ctx* c, int ir, double* AIC_out) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_calcAIC(m, ir, m->rank == 0 ? AIC_out : nullptr));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1487,6 +1765,7 @@ extern "C" int vlc_rotor_set_wake_params(vlc_ctx* c, int ir, int nbConvect, int 
                                          int suppressFwakeSwitch, int rollupStart, int rollupEnd, double rollupSign,
                                          double apparentViscCoeff, double decayCoeff, double initWakeVel) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_set_wake_params(m, ir, nbConvect, axisymmetrySwitch, ductSwitch, suppressFwakeSwitch, rollupStart, rollupEnd, rollupSign, apparentViscCoeff, decayCoeff, initWakeVel));
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
   if (nbConvect < 1 || nbConvect > r->nb) return fail(c, VLC_ERR_ARG, "nbConvect out of range");
@@ -1506,6 +1785,7 @@ extern "C" int vlc_rotor_set_wake_params(vlc_ctx* c, int ir, int nbConvect, int 
 
 extern "C" int vlc_rotor_set_frame(vlc_ctx* c, int ir, const double* shaftAxis, const double* hubCoords) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_set_frame(m, ir, shaftAxis, hubCoords));
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
   if (!shaftAxis || !hubCoords) return fail(c, VLC_ERR_ARG, "null pointer");
@@ -1518,6 +1798,7 @@ extern "C" int vlc_rotor_set_frame(vlc_ctx* c, int ir, const double* shaftAxis, 
 
 extern "C" int vlc_rotor_assignshed(vlc_ctx* c, int ir, int edge) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_assignshed(m, ir, edge));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1536,6 +1817,7 @@ extern "C" int vlc_rotor_assignshed(vlc_ctx* c, int ir, int edge) {
 
 extern "C" int vlc_rotor_age_wake(vlc_ctx* c, int ir, double dt, double omegaSlow) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_age_wake(m, ir, dt, omegaSlow));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1553,6 +1835,7 @@ extern "C" int vlc_rotor_age_wake(vlc_ctx* c, int ir, double dt, double omegaSlo
 
 extern "C" int vlc_rotor_dissipate_wake(vlc_ctx* c, int ir, double dt, double kinematicVisc) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_dissipate_wake(m, ir, dt, kinematicVisc));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1579,6 +1862,7 @@ extern "C" int vlc_rotor_dissipate_wake(vlc_ctx* c, int ir, double dt, double ki
 
 extern "C" int vlc_rotor_strain_wake(vlc_ctx* c, int ir) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_strain_wake(m, ir));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1594,6 +1878,7 @@ extern "C" int vlc_rotor_strain_wake(vlc_ctx* c, int ir) {
 
 extern "C" int vlc_rotor_wake_to_predicted(vlc_ctx* c, int ir) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_wake_to_predicted(m, ir));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1639,6 +1924,7 @@ int upload_blade_rotations(vlc_ctx* c, Rotor& r) {
 
 extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicted) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_convectwake(m, ir, dt, predicted));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1683,6 +1969,7 @@ extern "C" int vlc_rotor_convectwake(vlc_ctx* c, int ir, double dt, int predicte
 
 extern "C" int vlc_rotor_calc_skew(vlc_ctx* c, int ir) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_calc_skew(m, ir));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1698,6 +1985,7 @@ extern "C" int vlc_rotor_calc_skew(vlc_ctx* c, int ir) {
 
 extern "C" int vlc_rotor_burst_wake(vlc_ctx* c, int ir, double skewLimit, double largeCoreRadius) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_burst_wake(m, ir, skewLimit, largeCoreRadius));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1714,6 +2002,7 @@ extern "C" int vlc_rotor_burst_wake(vlc_ctx* c, int ir, double skewLimit, double
 
 extern "C" int vlc_rotor_updatePrescribedWake(vlc_ctx* c, int ir, double deltaPsi, int prescWakeGenNt, int predicted) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_updatePrescribedWake(m, ir, deltaPsi, prescWakeGenNt, predicted));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1742,6 +2031,7 @@ extern "C" int vlc_rotor_updatePrescribedWake(vlc_ctx* c, int ir, double deltaPs
 
 extern "C" int vlc_rotor_put_pfwake_helix(vlc_ctx* c, int ir, int ib, int predicted, const double* helix) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_pfwake_helix(m, ir, ib, predicted, helix));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1767,6 +2057,7 @@ extern "C" int vlc_rotor_get_pfwake(vlc_ctx* c, int ir, int ib, int predicted, d
 
 extern "C" int vlc_rotor_rollup(vlc_ctx* c, int ir) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_rollup(m, ir));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1817,6 +2108,7 @@ extern "C" int vlc_wake_sweep_count(vlc_ctx* c, int64_t* M_out) {
 // libCommon.f90:132-139 is a parallel loop over them); count = M on one GPU.
 extern "C" int vlc_wake_sweep_slice(vlc_ctx* c, int predicted, int64_t first, int64_t count, double* d_vel) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   const int s = predicted ? 1 : 0;
@@ -1862,6 +2154,7 @@ extern "C" int vlc_wake_sweep_slice(vlc_ctx* c, int predicted, int64_t first, in
 
 extern "C" int vlc_wake_sweep_scatter(vlc_ctx* c, int predicted, int addInitWakeVel, const double* d_vel) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   const int s = predicted ? 1 : 0;
@@ -1883,6 +2176,7 @@ extern "C" int vlc_wake_sweep_scatter(vlc_ctx* c, int predicted, int addInitWake
 
 extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_wake_sweep(m, predicted, addInitWakeVel));
   int64_t M = 0;
   int rc = vlc_wake_sweep_count(c, &M);
   if (rc || M <= 0) return rc;
@@ -1890,13 +2184,24 @@ extern "C" int vlc_wake_sweep(vlc_ctx* c, int predicted, int addInitWakeVel) {
   for (auto& r : c->rotors)
     if (r.defined && r.nNwake > 0) Mmax += ((long long)r.nNwake * (r.ns + 1) + r.nFwake) * r.nbConvect;
   if ((rc = bind_device(c))) return rc;
-  if ((rc = reserve(c, c->ws_acc, 3 * (size_t)Mmax))) return rc;
-  if ((rc = vlc_wake_sweep_slice(c, predicted, 0, M, c->ws_acc.p))) return rc;
+  // world > 1: this member sweeps its contiguous slice of the target list against ALL sources, then the
+  // velocity slices are all-gathered (24 bytes per target, once per predictor and once per corrector stage) and every
+  // member scatters the complete list into its own copy of the velocity arrays.
+  vlc::grp::Shard sh;
+  sh.per = M;
+  sh.hi = M;
+  if (c->world > 1) sh = vlc::grp::shard_range(M, c->world, c->rank);
+  if ((rc = reserve(c, c->ws_acc, 3 * ((size_t)Mmax + (size_t)c->world)))) return rc;  // per*world <= M + world - 1
+  if ((rc = vlc_wake_sweep_slice(c, predicted, sh.lo, sh.count(), c->ws_acc.p))) return rc;
+  if (c->world > 1 &&
+      (rc = allgather_slots(c, c->ws_acc.p, 3 * (size_t)sh.per, [](vlc_ctx* o) -> double* { return o->ws_acc.p; })))
+    return rc;
   return vlc_wake_sweep_scatter(c, predicted, addInitWakeVel, c->ws_acc.p);
 }
 
 extern "C" int vlc_rotor_wakevel_op(vlc_ctx* c, int ir, int op) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_wakevel_op(m, ir, op));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1979,6 +2284,7 @@ int ensure_histories(vlc_ctx* c, Rotor& r) {
 
 extern "C" int vlc_rotor_wakevel_copy(vlc_ctx* c, int ir, int dst, int src) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_wakevel_copy(m, ir, dst, src));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -1997,6 +2303,7 @@ extern "C" int vlc_rotor_wakevel_copy(vlc_ctx* c, int ir, int dst, int src) {
 extern "C" int vlc_rotor_wakevel_lincomb(vlc_ctx* c, int ir, int dst, int nterms, const int* src, const double* coef,
                                          double divisor) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_wakevel_lincomb(m, ir, dst, nterms, src, coef, divisor));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2059,6 +2366,7 @@ extern "C" int vlc_rotor_get_fwake(vlc_ctx* c, int ir, int ib, int predicted, do
 
 extern "C" int vlc_rotor_put_wakevel(vlc_ctx* c, int ir, int ib, int which, const double* velN, const double* velF) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_wakevel(m, ir, ib, which, velN, velF));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2117,6 +2425,7 @@ int cp_targets(vlc_ctx* c, Rotor* r, long long m) {
 
 extern "C" int vlc_rotor_calc_RHS(vlc_ctx* c, int ir, double* velCP_out, double* RHS_out) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_calc_RHS(m, ir, m->rank == 0 ? velCP_out : nullptr, m->rank == 0 ? RHS_out : nullptr));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2152,6 +2461,7 @@ extern "C" int vlc_rotor_calc_RHS(vlc_ctx* c, int ir, double* velCP_out, double*
 
 extern "C" int vlc_rotor_solve_map_gam(vlc_ctx* c, int ir, double* gamVec_out) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_solve_map_gam(m, ir, m->rank == 0 ? gamVec_out : nullptr));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2174,6 +2484,7 @@ extern "C" int vlc_rotor_solve_map_gam(vlc_ctx* c, int ir, double* gamVec_out) {
 
 extern "C" int vlc_rotor_put_sections(vlc_ctx* c, int ir, int ib, const double* sec) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_put_sections(m, ir, ib, sec));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2186,6 +2497,7 @@ extern "C" int vlc_rotor_put_sections(vlc_ctx* c, int ir, int ib, const double* 
 
 extern "C" int vlc_rotor_calc_velCPTotal(vlc_ctx* c, int ir) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_calc_velCPTotal(m, ir));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2216,6 +2528,7 @@ extern "C" int vlc_rotor_calc_velCPTotal(vlc_ctx* c, int ir) {
 
 extern "C" int vlc_rotor_calc_force(vlc_ctx* c, int ir, double density, double dt, double Omega, int spanwiseLiftSwitch) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_calc_force(m, ir, density, dt, Omega, spanwiseLiftSwitch));
   int rc = bind_device(c);
   if (rc) return rc;
   Rotor* r = get_rotor(c, ir);
@@ -2271,6 +2584,7 @@ extern "C" int vlc_rotor_get_wing(vlc_ctx* c, int ir, int ib, double* wiP) {
 
 extern "C" int vlc_convect_dev(vlc_ctx* c, int64_t n, double* x, const double* v, double dt) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!x || !v))) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2280,6 +2594,7 @@ extern "C" int vlc_convect_dev(vlc_ctx* c, int64_t n, double* x, const double* v
 
 extern "C" int vlc_ab2_dev(vlc_ctx* c, int64_t n, const double* v, const double* v1, double* out) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!v || !v1 || !out))) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2289,6 +2604,7 @@ extern "C" int vlc_ab2_dev(vlc_ctx* c, int64_t n, const double* v, const double*
 
 extern "C" int vlc_am2_dev(vlc_ctx* c, int64_t n, const double* vp, const double* vs, double* out) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!vp || !vs || !out))) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2298,6 +2614,7 @@ extern "C" int vlc_am2_dev(vlc_ctx* c, int64_t n, const double* vp, const double
 
 extern "C" int vlc_vel_order2_dev(vlc_ctx* c, int rows, int cols, const double* vn, const double* vnp1, double* out) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (rows < 0 || cols < 0 || (rows > 0 && cols > 0 && (!vn || !vnp1 || !out)) || out == vn || out == vnp1)
@@ -2310,6 +2627,7 @@ extern "C" int vlc_vel_order2_dev(vlc_ctx* c, int rows, int cols, const double* 
 extern "C" int vlc_dissipate_dev(vlc_ctx* c, int64_t n_rvc, double* rvc, int64_t n_gam, double* gam,
                                  double apparentViscCoeff, double nu, double decayCoeff, double dt) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (n_rvc < 0 || n_gam < 0) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2321,6 +2639,7 @@ extern "C" int vlc_dissipate_dev(vlc_ctx* c, int64_t n_rvc, double* rvc, int64_t
 extern "C" int vlc_dissipate_lattice_dev(vlc_ctx* c, int nrows, int ns, double* rvc4, double* gam,
                                          double apparentViscCoeff, double nu, double decayCoeff, double dt) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (nrows < 0 || ns < 0 || !rvc4 || !gam) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2333,6 +2652,7 @@ extern "C" int vlc_dissipate_lattice_dev(vlc_ctx* c, int nrows, int ns, double* 
 extern "C" int vlc_strain_dev(vlc_ctx* c, int64_t n, const double* p1, const double* p2, const double* l0,
                               const double* rvc0, double* rvc) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!p1 || !p2 || !l0 || !rvc0 || !rvc))) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2344,6 +2664,7 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
                                     const double* gam, const double* rvc4, int nfar, const double* far_nodes,
                                     const double* gamF, const double* rvcF) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if ((rc = check_set(c, set))) return rc;
@@ -2458,6 +2779,7 @@ extern "C" int vlc_pack_lattice(vlc_ctx* c, int set, int append, int nrows, int 
                                 const double* gam, const double* rvc4, int nfar, const double* far_nodes,
                                 const double* gamF, const double* rvcF) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_pack_lattice(m, set, append, nrows, ns, nodes, gam, rvc4, nfar, far_nodes, gamF, rvcF));
   int rc = bind_device(c);
   if (rc) return rc;
   if (nrows < 0 || ns < 1 || nfar < 0) return fail(c, VLC_ERR_ARG, "bad lattice shape");
@@ -2550,6 +2872,7 @@ extern "C" int vlc_last_sweep_ms(vlc_ctx* c, double* ms_kernel, double* ms_total
 
 extern "C" int vlc_set_lattice_tuning(vlc_ctx* c, int strip_width, int targets_per_thread) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_set_lattice_tuning(m, strip_width, targets_per_thread));
   const int W = strip_width, T = targets_per_thread;
   if (W < 0 || W > 4 || T < 0 || T > 3) return fail(c, VLC_ERR_ARG, "strip_width in 1..4, targets_per_thread in 1..3 (0 = automatic)");
   c->lat_W = W;
@@ -2560,6 +2883,7 @@ extern "C" int vlc_set_lattice_tuning(vlc_ctx* c, int strip_width, int targets_p
 
 extern "C" int vlc_set_shared_nodes(vlc_ctx* c, int on) {
   CHECK_CTX(c);
+  VLC_GROUP(c, vlc_set_shared_nodes(m, on));
   c->shared_nodes = (on != 0);
   for (auto& r : c->rotors) r.dirty[0] = r.dirty[1] = true;
   return VLC_OK;
@@ -2567,6 +2891,7 @@ extern "C" int vlc_set_shared_nodes(vlc_ctx* c, int on) {
 
 extern "C" int vlc_lattice_targets_dev(vlc_ctx* c, int nrows, int ns, const double* nodes, double* P) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (nrows < 0 || ns < 0 || !nodes || !P) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2577,6 +2902,7 @@ extern "C" int vlc_lattice_targets_dev(vlc_ctx* c, int nrows, int ns, const doub
 
 extern "C" int vlc_lattice_scatter_dev(vlc_ctx* c, int nrows, int ns, double* nodes, const double* P) {
   CHECK_CTX(c);
+  VLC_NO_GROUP(c);
   int rc = bind_device(c);
   if (rc) return rc;
   if (nrows < 0 || ns < 0 || !nodes || !P) return fail(c, VLC_ERR_ARG, "bad arguments");
@@ -2687,7 +3013,17 @@ extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyz
                            const double* vrNwake, int64_t nVfNwakeTE, const double* vfNwakeTE, const double* gamNwakeTE,
                            int64_t nVfFwake, const double* vfFwake, const double* gamFwake, double* gridCentre,
                            double* velCentre) {
+  CHECK_CTX(c);
   if (nx < 2 || ny < 2 || nz < 2) return fail(c, VLC_ERR_ARG, "bad grid arguments");
+  if (c->group && c->is_leader && !t_in_member) {  // every member takes a contiguous slice of the cell list (gridgen.f90:116-139)
+    const long long cells = (long long)(nx - 1) * (ny - 1) * (nz - 1);
+    return group_all(c, [&](vlc_ctx* g_) -> int {
+      const vlc::grp::Shard sh = vlc::grp::shard_range(cells, g_->world, g_->rank);
+      return vlc_gridgen_slice(g_, nx, ny, nz, xyzMin, xyzMax, vel, nVrWing, vrWing, nVrNwake, vrNwake, nVfNwakeTE, vfNwakeTE,
+                               gamNwakeTE, nVfFwake, vfFwake, gamFwake, sh.lo, sh.count(),
+                               gridCentre ? gridCentre + 3 * sh.lo : nullptr, velCentre ? velCentre + 3 * sh.lo : nullptr);
+    });
+  }
   return vlc_gridgen_slice(c, nx, ny, nz, xyzMin, xyzMax, vel, nVrWing, vrWing, nVrNwake, vrNwake, nVfNwakeTE, vfNwakeTE,
                            gamNwakeTE, nVfFwake, vfFwake, gamFwake, 0, (int64_t)(nx - 1) * (ny - 1) * (nz - 1), gridCentre,
                            velCentre);
