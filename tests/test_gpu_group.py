@@ -95,6 +95,7 @@ def test_group_rotor_call_sites(ctx, gctx, oracle):
         for c in (ctx, gctx):
             c.set_tuning(0, 0)
     A = gctx.rotor_calcAIC(0, ro.N)
+    assert ro.calcAIC() == 0
     assert np.max(np.abs(A - ro.AIC())) < 1e-12 * np.max(np.abs(A))
     assert np.array_equal(A, ctx.rotor_calcAIC(0, ro.N))
     rhs = np.random.default_rng(1).uniform(-1, 1, ro.N)
