@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- Biot-Savart pair-interactions/s on the synthetic multirotor wake (BASELINE.json).
+"""bench.py -- Biot-Savart pair-interactions/s on the synthetic multirotor wake (BASELINE.json configs[4]).
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+  python bench.py --gpus N --single-process                # the same step, ONE process driving N GPUs (vlc_create_multi)
   python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference OpenMP path
 
-One "step" = one wake-convection stage of the hot path at the named size: re-pack the filament set from
-the device-resident wake lattices, sweep every convected wake node (targets) against every filament
-(sources) with the sm_100a kernel, convect the nodes, and (N > 1) all-gather the updated node slices
-over NCCL and scatter them back into the lattices.  Work is fixed as N grows (targets are sharded):
-strong scaling.  `value` = total pair interactions of all ranks / max-over-ranks device time.
-Prints ONE JSON line on rank 0.
+Everything goes through the entry points the Fortran shim binds (include/volcanor_b200.h, tiers 2 / 2b): the wake is
+handed over as the reference's own records (Nwake_class / Fwake_class, classdef.f90:181-220).
+
+One "step" = one wake time step of the reference's fdScheme 3 (main.f90:1002-1115) with the wake resident on the
+device(s): rotor%dissipate_wake, the wake sweep on the current wake (every convected wake node against every filament of
+every rotor: libCommon.f90:114-211), Adams-Bashforth predictor + convectwake('P'), the sweep on the predicted wake,
+Adams-Moulton corrector + convectwake('C').  With N > 1 the LIBRARY shards the targets of both sweeps and all-gathers
+the velocity slices (ncclAllGather inside vlc_wake_sweep); work is fixed as N grows: strong scaling.
+`value` = pair interactions of all GPUs / max-over-ranks device time.  `e2e` = the per-sweep hand-over the unmodified
+call sites make: vlc_rotor_put_nwake / _put_fwake of every blade + vlc_vind_onNwake_byRotor / _onFwake_byRotor per
+(target blade, source rotor) with pinned HOST buffers.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -29,9 +35,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FLOPS_PER_PAIR = 76        # algorithmic flops of vf_vind as written + gam scale/accumulate
-PIPE_INSTR_PER_PAIR = {0: 43, 1: 41}   # FP64-pipe instructions per pair in bs_sweep_kernel (SASS count; full / fast)
-def pipe_instr_per_record(W):           # ... per (target, strip record of width W) in bs_lattice_kernel: W+1 nodes, 2W edges
-    return 11 * (W + 1) + 50 * W
+NU, VISC_COEFF = 1.8e-5, 5.0
+DT_STEP = 1e-4             # s: wake nodes move by <= ~4e-3 rotor radii per step (induced velocities <= ~40 m/s)
 
 
 def parse():
@@ -40,19 +45,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--filaments", type=int, default=1_000_000)
+    ap.add_argument("--filaments", type=int, default=int(os.environ.get("VLC_BENCH_FILAMENTS", "1000000")),
+                    help="size of the synthetic wake (default 1e6; VLC_BENCH_FILAMENTS sets it for a driver-run 1e7 line)")
     ap.add_argument("--seed", type=int, default=12345)
-    ap.add_argument("--T", type=int, default=0, help="targets per thread (0 = auto)")
+    ap.add_argument("--T", type=int, default=0, help="targets per thread of the flat kernel (0 = auto)")
     ap.add_argument("--nsplit", type=int, default=0, help="source splits (0 = auto)")
-    ap.add_argument("--precision", type=int, default=0, choices=[0, 1],
-                    help="0 = full (third-order rsqrt, default), 1 = fast (second order, pair error <= 6.4e-13)")
     ap.add_argument("--lat-w", type=int, default=0, help="strip width of the shared-node kernel, 1..4 (0 = default)")
     ap.add_argument("--lat-t", type=int, default=0, help="targets per thread of the shared-node kernel, 1..3 (0 = default)")
     ap.add_argument("--flat", action="store_true",
                     help="force the flat kernel on the reference's enumeration (default: shared-node lattice kernel)")
-    ap.add_argument("--graph", action="store_true",
-                    help="1 GPU only: capture the time step in a CUDA graph and replay it (launch-bound small wakes: ~215 "
-                         "launches per step); the per-kernel roofline is then taken from one eager step after the timed region")
+    ap.add_argument("--single-process", action="store_true",
+                    help="ONE process, --gpus N devices behind one handle (vlc_create_multi): what a single-process Fortran "
+                         "driver gets; the default for N > 1 is one process per GPU under torchrun (vlc_comm_init_rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -67,6 +71,16 @@ def workload(args):
     name = (f"synthetic 4-rotor(2 blades)+wing wake, {n_src} filaments x {m} wake-node targets, "
             f"seed {args.seed} (BASELINE.json configs[4] at ~1e{int(round(np.log10(max(n_src, 1))))})")
     return lats, n_src, m, name
+
+
+def config_of(args, name, n_src, m):
+    """The `config` object: identical in our arm and in --impl reference (the driver compares them)."""
+    return {"workload": name, "filaments": int(n_src), "targets": int(m), "seed": args.seed,
+            "step": "one wake time step of fdScheme 3 (main.f90:1002-1115), wake resident on the device(s): dissipate_wake, "
+                    "wake sweep on the current wake (all wake-node targets x all filaments), AB2 predictor + convectwake('P'), "
+                    "wake sweep on the predicted wake, AM2 corrector + convectwake('C'); 2 sweeps = 2 x targets x filaments "
+                    f"pair interactions; dt = {DT_STEP:g} s (the wake moves; no shedding / roll-up: fixed size)",
+            "l2": "flushed every step by a 256 MiB memset inside the timed region (vlc_l2_flush)"}
 
 
 class ClockSampler:
@@ -124,8 +138,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(args, p1, p2, rvc, gam, flag, P, seconds: float):
-    """C restatement of the reference OpenMP path (oracle, 'port') on the host cores, bounded sample."""
+    """C restatement of the reference OpenMP path (oracle, 'port') on the host cores, bounded sample.  Also returns
+    the velocities of the sampled targets: bench.py's in-run parity check compares the GPU's against them."""
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must use the host's cores whatever launched it
+    # (round 1: the reference arm ran on one core at N >= 2).  Set before libgomp is loaded by the oracle library.
+    if os.environ.get("OMP_NUM_THREADS") == "1" and ("WORLD_SIZE" in os.environ or "TORCHELASTIC_RUN_ID" in os.environ):
+        os.environ["OMP_NUM_THREADS"] = str(host_threads())
     from oracle import pyoracle
     pyoracle.build()
     lib = None
@@ -152,16 +178,17 @@ def cpu_baseline(args, p1, p2, rvc, gam, flag, P, seconds: float):
     idx = np.linspace(0, P.shape[0] - 1, m_s).astype(np.int64)
     Ps = np.ascontiguousarray(P[idx])
     t0 = time.perf_counter()
-    pyoracle.vind_flat(p1, p2, rvc, gam, flag, Ps, lib=lib)
+    Vs = pyoracle.vind_flat(p1, p2, rvc, gam, flag, Ps, lib=lib)
     dt = time.perf_counter() - t0
     return {"value": m_s * n / dt, "unit": "pair-interactions/s", "cores": int(cores), "kind": "port",
             "sample": f"{m_s} evenly spaced targets x all {n} filaments of the same workload, "
                       f"{dt:.1f} s, gcc {flags}, OMP_SCHEDULE={os.environ.get('OMP_SCHEDULE')}",
-            "lib": lib, "m_sample": m_s}
+            "lib": lib, "m_sample": m_s, "idx": idx, "V": Vs}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path (C restatement; no Fortran compiler exists here)."""
+    """--impl reference: the reference's own CPU path (C restatement; no Fortran compiler exists here), all host
+    threads, bounded sample per step.  Under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -171,6 +198,8 @@ def run_reference(args):
     P = synth.targets_all(lats)
     base = cpu_baseline(args, p1, p2, rvc, gam, flag, P, seconds=3.0)
     lib, m_s = base.pop("lib"), base.pop("m_sample")
+    base.pop("idx")
+    base.pop("V")
     from oracle import pyoracle
     idx = np.linspace(0, P.shape[0] - 1, m_s).astype(np.int64)
     Ps = np.ascontiguousarray(P[idx])
@@ -183,14 +212,58 @@ def run_reference(args):
     val = args.steps * m_s * n_src / dt
     base["value"] = val
     base["sample"] = (f"each step = {m_s} evenly spaced targets x all {n_src} filaments (bounded sample of the "
-                      f"workload), C restatement of the reference OpenMP loops (libCommon.f90:132-146)")
+                      f"workload), C restatement of the reference OpenMP loops (libCommon.f90:132-146), {base['cores']} threads")
     out = {"impl": "reference", "metric": "biot_savart_pair_interactions_per_s", "value": val,
            "unit": "pair-interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic", "config": {"workload": name, "filaments": n_src, "targets": m},
+           "dtype": "f64", "data": "synthetic", "config": config_of(args, name, n_src, m),
            "cpu_baseline": base,
            "e2e": {"value": val, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def define_rotors(ctx, rotors):
+    """vlc_rotor_define + the rotor_class members the wake mutators read.  surfaceType = 2: the synthetic workload has
+    wake filaments only (a non-lifting surface contributes no wing sources, classdef.f90:4437-4441)."""
+    for ir, r in enumerate(rotors):
+        ctx.rotor_define(ir, r["nb"], 1, r["ns"], r["nNwake"], r["nFwake"], 2)
+        ctx.rotor_set_wake_params(ir, r["nb"], 0, 0, 0, 1, r["ns"], 1.0, VISC_COEFF, 0.0, 0.0)
+        ctx.rotor_set_rows(ir, 1, 1)
+
+
+def upload_wake(ctx, rotors, predicted=False):
+    for ir, r in enumerate(rotors):
+        for ib in range(r["nb"]):
+            ctx.rotor_put_nwake(ir, ib, r["waN"][ib], predicted)
+            if r["nFwake"]:
+                ctx.rotor_put_fwake(ir, ib, r["waF"][ib], predicted)
+
+
+def resident_step(ctx, nr, first):
+    """main.f90:466-506 (dissipation) + :1002-1115 (fdScheme 3) with the library's device twins; tests/native/
+    case_gpu_hooks.c:g_convect is the same sequence inside the reference driver."""
+    C = type(ctx)
+    ctx.l2_flush()
+    for ir in range(nr):
+        ctx.rotor_dissipate_wake(ir, DT_STEP, NU)
+    ctx.wake_sweep(False)                                   # stage 1: sources 'C', targets = every convected wake node
+    if first:                                               # iter == 1 (main.f90:1003-1020)
+        for ir in range(nr):
+            ctx.rotor_convectwake(ir, DT_STEP, "C")
+            ctx.rotor_wakevel_op(ir, C.VEL_FIRST_STEP)
+        ctx.wake_sweep(False)                               # keep two sweeps per step in every step of the bench
+        return
+    for ir in range(nr):
+        ctx.rotor_wake_to_predicted(ir)
+        ctx.rotor_wakevel_op(ir, C.VEL_AB2)                 # velStep = vel; vel = 0.5*(3 vel - vel1)
+        ctx.rotor_convectwake(ir, DT_STEP, "P")
+    ctx.wake_sweep(True)                                    # stage 2 on the predicted wake
+    for ir in range(nr):
+        ctx.rotor_wakevel_op(ir, C.VEL_AM2)                 # vel = (velPredicted + velStep)*0.5
+        ctx.rotor_convectwake(ir, DT_STEP, "C")
+        ctx.rotor_wakevel_op(ir, C.VEL_SHIFT_HISTORY)
 
 
 def main():
@@ -214,6 +287,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (volcanor_b200 has no CPU fallback)")
+    single = bool(args.single_process and world == 1 and args.gpus > 1)
+    n_gpus = args.gpus if single else world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -221,292 +296,239 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     lats, n_src, m, name = workload(args)
-    ctx = vb.Context(local)
+    rotors = synth.rotors_from_lattices(lats)
+    nr = len(rotors)
+    if single:
+        ctx = vb.Context(devices=list(range(args.gpus)))   # one handle, N GPUs: the library owns threads + communicators
+    else:
+        ctx = vb.Context(local)
+        if world > 1:                                      # one process per GPU: the library still owns the communicator
+            uid = [vb.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init_rank(world, rank, uid[0])
+    comm = ctx.comm_info()
     ctx.set_tuning(args.T, args.nsplit)
-    ctx.set_precision(args.precision)
     ctx.set_shared_nodes(not args.flat)
     ctx.set_lattice_tuning(args.lat_w, args.lat_t)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
-
-    # ---- device-resident wake state (node-indexed SoA per lattice): current ('C') and predicted ('P') node sets ----
-    d = []
-    for l in lats:
-        nodes = torch.from_numpy(l.nodes).to(dev)
-        far = torch.from_numpy(l.far_nodes).to(dev) if l.F > 0 else None
-        d.append({"R": l.R, "S": l.S, "F": l.F, "nodes": nodes, "nodesP": nodes.clone(),
-                  "gam": torch.from_numpy(l.gam).to(dev), "rvc4": torch.from_numpy(l.rvc4).to(dev),
-                  "far": far, "farP": far.clone() if far is not None else None,
-                  "gamF": torch.from_numpy(l.gamF).to(dev) if l.F > 0 else None,
-                  "rvcF": torch.from_numpy(l.rvcF).to(dev) if l.F > 0 else None})
-    # target list = convected nodes of every lattice (+ far-chain nodes), padded to world * per
-    from volcanor_b200.sharding import TargetShard, allgather_slices
-    shard = TargetShard(m, world, rank)
-    per, lo, hi, m_loc = shard.per, shard.lo, shard.hi, shard.count
-    f64 = dict(dtype=torch.float64, device=dev)
-    P_all, Pp_all = torch.zeros(shard.padded, 3, **f64), torch.zeros(shard.padded, 3, **f64)
-    V, Vp, V1, Vw = (torch.zeros(max(per, 1), 3, **f64) for _ in range(4))   # this rank's slice: vel, predicted, previous, work
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    dt_step, nu, visc_coeff = 1e-9, 1.8e-5, 5.0
-    state = {"first": True}
-
-    def gather_targets(key, far_key, dst):
-        off = 0
-        for L in d:
-            k = L["R"] * (L["S"] + 1)
-            ctx.lattice_targets_dev(L["R"], L["S"], L[key], dst[off:off + k])
-            off += k
-            if L["F"] > 0:
-                dst[off:off + L["F"]].copy_(L[far_key][1:])
-                off += L["F"]
-
-    def scatter_targets(key, far_key, src):
-        off = 0
-        for L in d:
-            k = L["R"] * (L["S"] + 1)
-            ctx.lattice_scatter_dev(L["R"], L["S"], L[key], src[off:off + k])
-            off += k
-            if L["F"] > 0:
-                L[far_key][1:].copy_(src[off:off + L["F"]])
-                off += L["F"]
-
-    def pack(set_=0, key="nodes", far_key="far"):
-        for i, L in enumerate(d):
-            ctx.pack_lattice_dev(set_, i > 0, L["R"], L["S"], L[key], L["gam"], L["rvc4"], L["F"], L[far_key],
-                                 L["gamF"], L["rvcF"])
-
-    ev_k0, ev_k1 = [], []
-
-    def sweep(set_, P, out, record):
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        if m_loc > 0:
-            ctx.vind_dev(set_, m_loc, P[lo:hi], out)       # THE sweep: m_loc targets x n_src filaments
-        if record:
-            e1.record(stream)
-            ev_k0.append(e0)
-            ev_k1.append(e1)
-
-    def step(record=False):
-        """One wake time step of the reference's fdScheme 3 (main.f90:1002-1115) on device-resident state:
-        core growth, sweep on the current wake, Adams-Bashforth predictor, sweep on the predicted wake,
-        Adams-Moulton corrector; one all-gather of node positions per stage."""
-        flush.zero_()                                      # L2 flush (inside the timed region, ~0.05 ms)
-        for L in d:                                        # rotor_dissipate_wake (classdef.f90:4356-4408)
-            ctx.dissipate_lattice_dev(L["R"], L["S"], L["rvc4"], L["gam"], visc_coeff, nu, 0.0, dt_step)
-        pack(0, "nodes", "far")                            # sources 'C' from the current lattices
-        gather_targets("nodes", "far", P_all)
-        sweep(0, P_all, V, record)                         # stage 1
-        if state["first"]:
-            V1.copy_(V)                                    # iter == 1: plain convection (main.f90:1003-1020)
-            state["first"] = False
-        if m_loc > 0:
-            ctx.ab2_dev(m_loc, V, V1, Vw)                  # vel = 0.5*(3 vel - vel1)      (main.f90:1032-1034)
-            Pp_all[lo:hi].copy_(P_all[lo:hi])
-            ctx.convect_dev(m_loc, Pp_all[lo:hi], Vw, dt_step)   # convectwake('P')
-        allgather_slices(Pp_all, shard)                    # exchange 1: predicted node positions (NCCL)
-        scatter_targets("nodesP", "farP", Pp_all)
-        pack(1, "nodesP", "farP")                          # sources 'P'
-        sweep(1, Pp_all, Vp, record)                       # stage 2 on the predicted wake
-        if m_loc > 0:
-            ctx.am2_dev(m_loc, Vp, V, Vw)                  # vel = (velPredicted + velStep)*0.5  (main.f90:1094-1096)
-            ctx.convect_dev(m_loc, P_all[lo:hi], Vw, dt_step)    # convectwake('C')
-        allgather_slices(P_all, shard)                     # exchange 2: corrected node positions
-        scatter_targets("nodes", "far", P_all)
-        V1.copy_(V)                                        # vel1 = velStep                  (main.f90:1105-1106)
 
     def barrier():
+        ctx.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    pack()
-    assert ctx.num_sources(0) == n_src, (ctx.num_sources(0), n_src)
-    info = ctx.set_info(0)
-    shared = info["shared_active"] == 1
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- resident wake: uploaded once in the reference's record layout -----------------------------------------
+    define_rotors(ctx, rotors)
+    upload_wake(ctx, rotors)
+    assert ctx.wake_sweep_count() == m, (ctx.wake_sweep_count(), m)
+    info = [ctx.rotor_info(ir) for ir in range(nr)]
+    assert sum(i["filaments"] for i in info) == n_src, (info, n_src)
+    shared = all(i["shared_active"] == 1 for i in info)
     fp64_peak, _ = ctx.measure_fp64_peak(20000)
     fp64_rate3, _ = ctx.measure_fp64_rate(1, 20000)    # DFMA rate with three changing register operands (informational)
 
+    first = True
     for _ in range(max(args.warmup, 3)):
-        step()
+        resident_step(ctx, nr, first)
+        first = False
     barrier()
-    use_graph = bool(args.graph and world == 1)
-    graph = None
-    if use_graph:
-        # The whole step (library launches on the context's stream, its side-stream fork/join, torch copies) is captured
-        # once and replayed: one cudaGraphLaunch per time step instead of ~215 kernel launches.
-        gstream = torch.cuda.Stream()
-        gstream.wait_stream(stream)
-        ctx.set_stream(gstream.cuda_stream)
-        launches_before = ctx.launch_count
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=gstream):
-            step()
-        launches_per_step = ctx.launch_count - launches_before
-        stream = gstream
-        with torch.cuda.stream(gstream):
-            graph.replay()                                   # warm replay
-        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.sweep_stats(reset=1)
     barrier()
-    t0.record(stream)
-    if use_graph:
-        with torch.cuda.stream(stream):
-            for _ in range(args.steps):
-                graph.replay()
-    else:
-        for _ in range(args.steps):
-            step(record=True)
-    t1.record(stream)
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        resident_step(ctx, nr, False)
+    ctx.event_record(1)
     barrier()
-    elapsed_ms = t0.elapsed_time(t1)
-    launches = (launches_per_step * args.steps) if use_graph else (ctx.launch_count - launches0)
+    elapsed_ms = reduce_max(ctx.event_elapsed_ms(0, 1))
+    stats = ctx.sweep_stats(reset=-1)
+    launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if use_graph:                                            # per-kernel timings for the roofline: one eager step
-        with torch.cuda.stream(stream):
-            step(record=True)
-        torch.cuda.synchronize()
-    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)])) if ev_k0 else 0.0
-    # dominant kernel alone (CUDA events recorded by the library on the launching stream around that launch, last step)
-    main_ms, total_ms = ctx.last_sweep_ms() if m_loc > 0 else (0.0, 0.0)
-    kern_ms = sweep_ms * (main_ms / total_ms) if total_ms > 0 else sweep_ms
-    tt = torch.tensor([elapsed_ms, kern_ms, sweep_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed_ms, kern_ms_max, sweep_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
-    # every rank must hold the same wake after the last all-gather (bitwise): max - min over ranks of a position checksum
-    chk = P_all[:m].sum(dim=0)
+    pairs_step = 2.0 * float(m) * float(n_src)             # two sweeps per time step
+    value = pairs_step * args.steps / (elapsed_ms * 1e-3)
+
+    # every rank / member must hold the same wake after the last all-gather, and it must be finite: blade 0 of rotor 0
+    w0 = ctx.rotor_get_nwake(0, 0, rotors[0]["nNwake"], rotors[0]["ns"])
+    wake_finite = bool(np.isfinite(w0).all())
+    moved = float(np.max(np.abs(w0[:, :, 0:3] - rotors[0]["waN"][0][:, :, 0:3])))
     ranks_consistent = True
     if world > 1:
+        chk = torch.tensor([float(w0[:, :, 12:15].sum())], dtype=torch.float64, device=dev)
         hi_, lo_ = chk.clone(), chk.clone()
         dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
         ranks_consistent = bool(torch.equal(hi_, lo_))
-    wake_finite = bool(torch.isfinite(chk).all())
-    pairs_step = 2.0 * float(m) * float(n_src)             # two sweeps per time step
-    value = pairs_step * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D + D2H inside the timed region) ----
-    e2e = None
+    # ---- same-work figure: ONE sweep of the flat kernel on the reference's enumeration, after the timed region ----
+    same_work = None
+    if shared:
+        ctx.set_shared_nodes(False)
+        ctx.wake_sweep(False)                              # packs the flat enumeration, warm
+        ctx.sweep_stats(reset=1)
+        ctx.wake_sweep(False)
+        sf = ctx.sweep_stats(reset=-1)["bs_sweep_kernel"]
+        ctx.set_shared_nodes(True)
+        if sf["ms"] > 0:
+            same_work = {"kernel": "bs_sweep_kernel", "launches": sf["launches"], "ms": sf["ms"],
+                         "achieved": sf["pairs"] * FLOPS_PER_PAIR / (sf["ms"] * 1e-3) / 1e12,
+                         "frac": sf["pairs"] * FLOPS_PER_PAIR / (sf["ms"] * 1e-3) / fp64_peak,
+                         "pipe_frac": sf["fp64_instr"] * 2 / (sf["ms"] * 1e-3) / fp64_peak}
+
+    # ---- e2e: the per-sweep hand-over of the unmodified call sites, HOST buffers (H2D + D2H inside the timed region) ----
+    e2e, e2e_V, e2e_off = None, None, None
     if not args.no_e2e:
-        P_host = synth.targets_all(lats)
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        hl = [{"R": l.R, "S": l.S, "F": l.F, "nodes": pin(l.nodes), "gam": pin(l.gam), "rvc4": pin(l.rvc4),
-               "far": pin(l.far_nodes) if l.F > 0 else None, "gamF": pin(l.gamF) if l.F > 0 else None,
-               "rvcF": pin(l.rvcF) if l.F > 0 else None} for l in lats]
-        h2d = sum(8 * (L["nodes"].numel() + L["gam"].numel() + L["rvc4"].numel()
-                       + (L["far"].numel() + 2 * L["F"] if L["F"] > 0 else 0)) for L in hl)
-        hP = pin(P_host[lo:hi]) if m_loc > 0 else None
-        hV = torch.empty(max(m_loc, 1), 3, dtype=torch.float64).pin_memory()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        hrot = [{**r, "waN": [pin(w) for w in r["waN"]], "waF": [pin(w) for w in r["waF"]]} for r in rotors]
+        ectx = ctx
+        # a second set of rotors (indices nr..2nr-1) so that the resident wake above stays untouched
+        for k, r in enumerate(hrot):
+            ectx.rotor_define(nr + k, r["nb"], 1, r["ns"], r["nNwake"], r["nFwake"], 2)
+            ectx.rotor_set_rows(nr + k, 1, 1)
+        h2d = sum(8 * sum(w.size for w in r["waN"]) + 8 * sum(w.size for w in r["waF"]) for r in hrot)
+        tgt_bytes = 0
+        out_near = [[np.zeros((r["ns"] + 1, r["nNwake"], 3)) for _ in range(r["nb"])] for r in hrot]
+        out_far = [[np.zeros((r["nFwake"], 3)) for _ in range(r["nb"])] for r in hrot]
+
+        def e2e_sweep():
+            """main.f90:814-841 as the shim executes it: refresh the device copies of every blade's records, then per
+            target blade and source rotor one vind_onNwake_byRotor and one vind_onFwake_byRotor, summed on the host."""
+            nonlocal tgt_bytes
+            tgt_bytes = 0
+            for k, r in enumerate(hrot):
+                for ib in range(r["nb"]):
+                    ectx.rotor_put_nwake(nr + k, ib, r["waN"][ib])
+                    if r["nFwake"]:
+                        ectx.rotor_put_fwake(nr + k, ib, r["waF"][ib])
+            for k, r in enumerate(hrot):
+                for ib in range(r["nb"]):
+                    vn, vf = out_near[k][ib], out_far[k][ib]
+                    vn[...] = 0.0
+                    vf[...] = 0.0
+                    for j in range(nr):
+                        vn += ectx.vind_onNwake_byRotor(nr + j, r["waN"][ib], r["nNwake"], r["ns"], r["nNwake"])
+                        tgt_bytes += 24 * r["nNwake"] * (r["ns"] + 1)
+                        if r["nFwake"]:
+                            vf += ectx.vind_onFwake_byRotor(nr + j, r["waF"][ib], r["nFwake"])
+                            tgt_bytes += 24 * r["nFwake"]
 
         def e2e_step():
-            # the caller-facing C-ABI calls with HOST buffers, twice per time step (current and predicted wake):
-            # wake lattices in, velocities of this rank's targets out
-            for stage in range(2):
-                for i, L in enumerate(hl):
-                    ctx.pack_lattice(2, i > 0, L["R"], L["S"], L["nodes"], L["gam"], L["rvc4"], L["F"], L["far"],
-                                     L["gamF"], L["rvcF"])
-                if m_loc > 0:
-                    ctx.vind_into(2, m_loc, hP, hV)
+            e2e_sweep()        # current wake
+            e2e_sweep()        # predicted wake (the same records stand in for it: same sizes, same work)
 
-        for _ in range(2):
-            e2e_step()
+        e2e_step()
         barrier()
-        w0 = time.perf_counter()
+        w0_ = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         barrier()
-        w = time.perf_counter() - w0
-        tw = torch.tensor([w], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        e2e = {"value": pairs_step * args.steps / float(tw[0]), "unit": "pair-interactions/s",
-               "h2d_bytes_per_step": int(2 * (h2d + 24 * m_loc)), "d2h_bytes_per_step": int(2 * 24 * m_loc),
-               "call": "per time step 2 x [vlc_pack_lattice (host wake lattices of all blades) + vlc_vind (host targets -> "
-                       "host velocities)], pinned buffers, per rank: all sources, its target slice",
-               "ms_per_step": 1e3 * float(tw[0]) / args.steps}
+        w = reduce_max(time.perf_counter() - w0_)
+        e2e = {"value": pairs_step * args.steps / w, "unit": "pair-interactions/s",
+               "h2d_bytes_per_step": int(2 * (h2d + tgt_bytes)), "d2h_bytes_per_step": int(2 * tgt_bytes),
+               "call": "per wake sweep (2 per time step): vlc_rotor_put_nwake + vlc_rotor_put_fwake of every blade (the reference's "
+                       "400-byte Nwake_class / 104-byte Fwake_class records, pinned host memory), then per (target blade, source "
+                       "rotor) vlc_vind_onNwake_byRotor + vlc_vind_onFwake_byRotor (libCommon.f90:114-211) with host target records "
+                       "in and host velocity arrays out, summed over source rotors on the host like main.f90:817-826",
+               "calls_per_step": int(2 * sum(r["nb"] for r in hrot) * nr * 2), "ms_per_step": 1e3 * w / args.steps}
+        # velocities of all targets in the order of synth.targets_all (per blade: near nodes, then far nodes)
+        e2e_V = np.concatenate([np.concatenate([out_near[k][ib].reshape(-1, 3), out_far[k][ib]])
+                                for k, r in enumerate(hrot) for ib in range(r["nb"])])
 
     if rank != 0:
         if world > 1:
+            ctx.close()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
+    # ---- roofline of the dominant kernel: one CUDA-event pair per launch on the launching stream, over the timed region ----
     peak = fp64_peak / 1e12
-    if shared:
-        # bs_lattice_kernel covers the 4 ring filaments of every near-wake ring; the remainder kernel the rest
-        kernel = "bs_lattice_kernel"
-        pairs_launch = float(m_loc) * 4.0 * float(sum(l.R * l.S for l in lats))
-        issued = float(m_loc) * float(info["lattice_records"]) * pipe_instr_per_record(info["strip_width"])
-        note = ("shared-node lattice kernel: every lattice node evaluated once per target and every interior edge once "
-                "with the merged strength of its two rings -- the reference's ring-by-ring sum regrouped, so frac counts "
-                "the reference's 76 flop x 4 filaments per ring while the kernel issues (11(W+1)+50W)/W = "
-                "72 / 66.5 / 64.7 / 63.75 FP64 instructions per (target, ring) for strip width W = 1..4: frac may exceed 1; pipe_frac = issued FP64 instructions vs the pipe's peak")
-    else:
-        kernel = "bs_sweep_kernel"
-        pairs_launch = float(m_loc) * float(n_src)
-        issued = pairs_launch * PIPE_INSTR_PER_PAIR[args.precision]
-        note = ("flat kernel on the reference's enumeration: frac = algorithmic 76 flop/pair, pipe_frac = issued FP64 "
-                "instr/pair (43 full, 41 fast)")
-    achieved = pairs_launch * FLOPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12 if kern_ms_max > 0 else 0.0
-    # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture of this same command
-    # (profiles/r01i_bs_sweep_full.md: dram__bytes_read.sum 37.57 MB + dram__bytes_write.sum 29.13 MB; the strip records
-    # are 28.0 MB, targets 6.2 MB, the 12 source-split partial sums 74 MB, more than half of them absorbed by L2): no
-    # wasted re-reads -- 0.003 % of the HBM peak.  Only quoted for the workload and launch shape the capture was taken on.
-    traffic = 66.70e6 if (shared and world == 1 and args.filaments == 1_000_000 and args.lat_w in (0, 4)
-                          and args.lat_t in (0, 2) and args.nsplit == 0) else None
+    kernel = "bs_lattice_kernel" if shared else "bs_sweep_kernel"
+    st = stats[kernel]
+    kern_ms_total, n_launch = st["ms"], max(st["launches"], 1)
+    achieved = st["pairs"] * FLOPS_PER_PAIR / (kern_ms_total * 1e-3) / 1e12 if kern_ms_total > 0 else 0.0
+    note = ("shared-node lattice kernel: every lattice node evaluated once per target and every interior edge once with the "
+            "merged strength of its two rings -- the reference's ring-by-ring sum regrouped, so `frac` (the reference's 76 flop x "
+            "4 filaments per ring) exceeds what the kernel executes ((11(W+1)+50W)/W = 63.75 FP64 instructions per (target, ring) "
+            "at W = 4) and may exceed 1; `pipe_frac` = issued FP64 instructions x 2 / peak is the hardware utilisation; "
+            "`same_work` = the flat kernel on the reference's own enumeration, one sweep after the timed region"
+            if shared else "flat kernel on the reference's enumeration: frac = algorithmic 76 flop/pair, pipe_frac = 43 issued FP64 instr/pair")
+    prof = ROOT / "profiles" / "r02_bs_lattice_full.md"
+    traffic, traffic_source = None, None
+    if shared and n_gpus == 1 and args.filaments == 1_000_000 and prof.exists():
+        import re
+        txt = prof.read_text()
+        mm = re.search(r"traffic per launch[^0-9]*([0-9.]+)\s*MB", txt)
+        if mm:
+            traffic = float(mm.group(1)) * 1e6
+            traffic_source = ("profiles/r02_bs_lattice_full.md: ncu --set full of this command, dram__bytes_read.sum + "
+                              "dram__bytes_write.sum of one bs_lattice_kernel launch (one source rotor); not re-measured in this run")
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "kernel": kernel, "kernel_ms": kern_ms_max, "sweep_ms": sweep_ms_max,
-                "pairs_per_launch": pairs_launch, "flops_per_pair": FLOPS_PER_PAIR,
-                "pipe_frac": issued * 2 / (kern_ms_max * 1e-3) / fp64_peak if kern_ms_max > 0 else 0.0,
+                "traffic": traffic, "traffic_source": traffic_source,
+                "kernel": kernel, "launches": st["launches"], "kernel_ms": kern_ms_total / n_launch,
+                "kernel_ms_per_step": kern_ms_total / args.steps,
+                "kernel_share_of_step": kern_ms_total / elapsed_ms if elapsed_ms > 0 else None,
+                "pairs_per_launch": st["pairs"] / n_launch, "flops_per_pair": FLOPS_PER_PAIR,
+                "pipe_frac": st["fp64_instr"] * 2 / (kern_ms_total * 1e-3) / fp64_peak if kern_ms_total > 0 else 0.0,
+                "same_work": same_work, "frac_same_work": same_work["frac"] if same_work else None,
                 "dfma_3reg_tflops": fp64_rate3 / 1e12,
-                "pipe_frac_of_3reg_rate": issued * 2 / (kern_ms_max * 1e-3) / fp64_rate3 if kern_ms_max > 0 else 0.0,
-                "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); "
-                               "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2; dfma_3reg_tflops = the same "
-                               "measurement with three distinct changing register operands per DFMA (vlc_measure_fp64_rate "
-                               "pattern 1), the practical ceiling of register-fed FP64 code",
+                "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); MEASURED_PEAKS.json has no "
+                               "FP64 entry; nominal 148*64*2*1.965 GHz = 37.2; dfma_3reg_tflops = the same measurement with three "
+                               "distinct changing register operands per DFMA, the practical ceiling of register-fed FP64 code",
+                "timing": "one CUDA event pair per launch on the launching stream (vlc_sweep_stats), summed over the timed region; "
+                          "per GPU (rank 0's slice of the targets)",
                 "note": "compute-bound pairwise N-body on the FP64 pipe (no tensor cores by construction); " + note}
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    cpu, checks = None, {"ranks_hold_identical_wake": ranks_consistent, "wake_finite": wake_finite,
+                         "wake_moved_max_abs": moved}
+    if n_gpus == 1 and not args.no_cpu_baseline:
         p1, p2, rvc, gam, flag = synth.flatten_all(lats)
         cpu = cpu_baseline(args, p1, p2, rvc, gam, flag, synth.targets_all(lats), args.cpu_seconds)
         cpu.pop("lib")
         cpu.pop("m_sample")
+        idx, Vs = cpu.pop("idx"), cpu.pop("V")
+        if e2e_V is not None:
+            # in-run parity: the host-path velocities of the sampled targets against the CPU restatement, per target,
+            # relative to the target's own velocity magnitude budget max|V| of the sample (no long-double pass here)
+            err = np.abs(e2e_V[idx] - Vs).max(axis=1)
+            scale = np.maximum(np.abs(Vs).max(axis=1), 1e-300)
+            checks["sampled_oracle"] = {"targets": int(idx.size), "max_abs_err": float(err.max()),
+                                        "max_err_over_own_velocity": float((err / scale).max()),
+                                        "max_err_over_sample_velocity_scale": float(err.max() / np.abs(Vs).max()),
+                                        "note": "e2e (host-path) velocities of the CPU baseline's sampled targets vs the C restatement "
+                                                "of the reference; tests/ measure against sum|terms| per target (1e-12)"}
 
     out = {"metric": "biot_savart_pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
-           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+           "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": name, "filaments": n_src, "targets": m, "targets_per_rank": per,
-                      "step": "one wake time step of fdScheme 3 on device-resident state: core growth, pack, sweep on the "
-                              "current wake (targets slice x all filaments), AB2 predictor + all-gather, pack, sweep on the "
-                              "predicted wake, AM2 corrector + all-gather",
-                      "l2": "flushed every step by a 256 MiB memset inside the timed region",
-                      "parallelism": f"target-sharded x{world}, sources replicated, 1 NCCL all-gather per stage (2 per step)",
-                      "launch": ("the step is captured once in a CUDA graph and replayed (one graph launch per time step); "
-                                 "roofline kernel times from one eager step after the timed region") if use_graph
-                                else "eager: one stream, every kernel launched per step",
+           "config": {**config_of(args, name, n_src, m),
+                      "parallelism": (f"target-sharded x{n_gpus} behind the C ABI, sources replicated, 1 all-gather of velocity slices per "
+                                      f"wake sweep (2 per step) inside vlc_wake_sweep; transport {comm['transport']}; "
+                                      + ("ONE process, one worker thread per GPU (vlc_create_multi)" if single else
+                                         "one process per GPU, library-owned communicator (vlc_comm_init_rank)" if world > 1 else
+                                         "single GPU")),
+                      "launch": "eager: every kernel launched per step on the library's stream(s)",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
-                      "sources": ({"form": "shared-node lattice", "strip_width": int(info["strip_width"]),
-                                   "strip_records": int(info["lattice_records"]),
-                                   "remainder_filaments": int(info["remainder_filaments"])} if shared
-                                  else {"form": "flat reference enumeration"}),
-                      "precision": ["full: third-order rsqrt refinement, pair error ~1e-16",
-                                    "fast: second-order rsqrt refinement, pair error <= 6.4e-13"][args.precision]},
+                      "sources": ({"form": "shared-node lattice", "strip_width": int(info[0]["strip_width"]),
+                                   "strip_records": int(sum(i["lattice_records"] for i in info)),
+                                   "remainder_filaments": int(sum(i["remainder_filaments"] for i in info)),
+                                   "source_rotors": nr} if shared else {"form": "flat reference enumeration", "source_rotors": nr})},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-           "timesteps_per_s": args.steps / (elapsed_ms * 1e-3), "sweeps_per_step": 2,
-           "checks": {"ranks_hold_identical_wake": ranks_consistent, "wake_finite": wake_finite},
+           "timesteps_per_s": args.steps / (elapsed_ms * 1e-3), "sweeps_per_step": 2, "checks": checks,
            "fp64_peak_measured_tflops": peak}
     sys.stdout.flush()
     os.dup2(stdout_fd, 1)
     print(json.dumps(out), flush=True)
+    os.dup2(2, 1)          # NCCL teardown messages, if any
+    ctx.close()
     if world > 1:
-        os.dup2(2, 1)          # NCCL teardown messages, if any
         dist.destroy_process_group()
 
 

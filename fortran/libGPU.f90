@@ -55,6 +55,12 @@ module libGPU
       integer(c_int), value :: device
       type(c_ptr), intent(out) :: out
     end function
+    integer(c_int) function vlc_create_multi(n_devices, devices, out) bind(C, name='vlc_create_multi')
+      import :: c_int, c_ptr
+      integer(c_int), value :: n_devices
+      integer(c_int), intent(in) :: devices(*)
+      type(c_ptr), intent(out) :: out
+    end function
     integer(c_int) function vlc_destroy(c) bind(C, name='vlc_destroy')
       import :: c_int, c_ptr
       type(c_ptr), value :: c
@@ -360,10 +366,25 @@ contains
 
   subroutine gpu_init(rotor, device)
     !! Once, after rotor%init (main.f90:31-40): declare every rotor's sizes.
+    !! VOLCANOR_GPUS=n in the environment (n > 1) makes the ONE handle span the GPUs 0 .. n-1 of the box
+    !! (vlc_create_multi): the library replicates the wake, shards the targets of every sweep and all-gathers the
+    !! velocity slices with NCCL; no call site below changes (main.f90:814-841 keeps calling vind_onNwake_byRotor).
     type(rotor_class), intent(in) :: rotor(:)
     integer, intent(in) :: device
-    integer :: ir
-    call check(vlc_create(int(device, c_int), ctx))
+    integer :: ir, ngpu, stat
+    integer(c_int), allocatable :: devlist(:)
+    character(len=16) :: env
+    ngpu = 1
+    call get_environment_variable('VOLCANOR_GPUS', env, status=stat)
+    if (stat == 0) read (env, *, iostat=stat) ngpu
+    if (stat /= 0) ngpu = 1
+    if (ngpu > 1) then
+      allocate (devlist(ngpu))
+      devlist = [(int(ir - 1, c_int), ir=1, ngpu)]
+      call check(vlc_create_multi(int(ngpu, c_int), devlist, ctx))
+    else
+      call check(vlc_create(int(device, c_int), ctx))
+    endif
     allocate (stale(3, size(rotor)))
     stale = .true.
     do ir = 1, size(rotor)

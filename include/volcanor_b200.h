@@ -413,6 +413,21 @@ int vlc_gridgen_slice(vlc_ctx* ctx, int nx, int ny, int nz, const double* xyzMin
                       const double* gamFwake, int64_t first, int64_t count, double* gridCentre, double* velCentre);
 
 /* ---- measurement helper ------------------------------------------------------------------ */
+/* Device-side timing across the library's own stream(s): vlc_event_record(slot) records a CUDA event (slot 0..7) on the
+ * stream of the context -- of every member for a handle made by vlc_create_multi; vlc_event_elapsed_ms waits for slot_b
+ * and returns the time from slot_a to slot_b, the LARGEST over the members of a group (the step is over when the slowest
+ * device is done). */
+int vlc_event_record(vlc_ctx* ctx, int slot);
+int vlc_event_elapsed_ms(vlc_ctx* ctx, int slot_a, int slot_b, double* ms);
+/* Roofline bookkeeping of the dominant kernels, measured with one CUDA event pair per launch on the launching stream:
+ * reset > 0 starts collecting (and clears), reset < 0 stops; the four output arrays (any may be NULL) receive, for
+ * [0] bs_lattice_kernel and [1] bs_sweep_kernel, the launches since the last reset, their summed device time in ms, the
+ * reference pair interactions they stand for (lattice: targets x 4 filaments x rings; flat: targets x filaments) and the
+ * FP64-pipe instructions they issued (lattice: (11(W+1) + 50W) per (target, strip record); flat: 43 per pair).  Reads
+ * the first member of a group handle (its slice of the targets). */
+int vlc_sweep_stats(vlc_ctx* ctx, int reset, int64_t* launches, double* ms, double* pairs, double* fp64_instr);
+/* memset of a 256 MiB scratch buffer on the context's stream(s): evicts the previous step's data from the 126 MB L2. */
+int vlc_l2_flush(vlc_ctx* ctx);
 /* Register-resident DFMA chains on every SM: returns sustained FP64 FMA rate in flop/s (DFMA = 2)
  * and the elapsed milliseconds; used by bench.py as the measured FP64 roofline denominator
  * (MEASURED_PEAKS.json has no FP64 entry). */

@@ -44,3 +44,15 @@ def test_own_arm_fails_loudly_without_a_gpu():
     r = _run("--steps", "1", "--warmup", "0", "--filaments", "20000", "--no-cpu-baseline", "--no-e2e")
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]      # no number without the CUDA path
+
+
+def test_reference_arm_under_torchrun_uses_all_host_threads(oracle):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still run on the host's cores (round 1: the
+    N >= 2 reference lines ran on one core and the driver's ratios at N = 2, 4, 8 were void)."""
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--filaments", "20000", "--gpus", "2",
+             env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    want = len(os.sched_getaffinity(0))
+    assert out["cpu_baseline"]["cores"] == want, (out["cpu_baseline"]["cores"], want)
+    assert out["n_gpus"] == 2 and set(out["config"]) >= {"workload", "filaments", "targets", "step", "l2"}

@@ -190,6 +190,10 @@ def load_library() -> C.CDLL:
         "vlc_gridgen": (i32, [_vp, i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, _vp, _vp]),
         "vlc_gridgen_slice": (i32, [_vp, i32, i32, i32, _vp, _vp, _vp, i64, _vp, i64, _vp, i64, _vp, _vp, i64, _vp, _vp, i64, i64,
                                     _vp, _vp]),
+        "vlc_event_record": (i32, [_vp, i32]),
+        "vlc_event_elapsed_ms": (i32, [_vp, i32, i32, _dp]),
+        "vlc_l2_flush": (i32, [_vp]),
+        "vlc_sweep_stats": (i32, [_vp, i32, C.POINTER(i64), _dp, _dp, _dp]),
         "vlc_measure_fp64_peak": (i32, [_vp, i32, _dp, _dp]),
         "vlc_measure_fp64_rate": (i32, [_vp, i32, i32, _dp, _dp]),
         "vlc_probe_rsqrt": (i32, [_vp, i64, _vp, _vp, _vp, _vp]),
@@ -306,6 +310,26 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.vlc_launch_count(self.h))
+
+    def event_record(self, slot: int):
+        """CUDA event on the library's stream (every member's for a multi-GPU handle)."""
+        self._ck(self.lib.vlc_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, slot_a: int, slot_b: int) -> float:
+        """Device time between two recorded events; the largest over the members of a multi-GPU handle."""
+        ms = C.c_double()
+        self._ck(self.lib.vlc_event_elapsed_ms(self.h, slot_a, slot_b, C.byref(ms)))
+        return ms.value
+
+    def sweep_stats(self, reset: int = 0) -> dict:
+        """Per-launch device times of the dominant kernels since the last reset (reset=1 starts collecting)."""
+        n, ms, pr, ins = (C.c_int64 * 2)(), (C.c_double * 2)(), (C.c_double * 2)(), (C.c_double * 2)()
+        self._ck(self.lib.vlc_sweep_stats(self.h, reset, n, ms, pr, ins))
+        return {k: {"launches": int(n[i]), "ms": ms[i], "pairs": pr[i], "fp64_instr": ins[i]}
+                for i, k in enumerate(("bs_lattice_kernel", "bs_sweep_kernel"))}
+
+    def l2_flush(self):
+        self._ck(self.lib.vlc_l2_flush(self.h))
 
     def measure_fp64_peak(self, iters: int = 20000) -> tuple[float, float]:
         f, ms = C.c_double(), C.c_double()

@@ -63,6 +63,14 @@ struct SourceSet {
   long long n_rem = 0, n_rem_pad = 0;  // filaments no strip covers (last column, horseshoe, far chain)
   int* d_unmergeable = nullptr;        // device flag raised by the pack kernels
   bool has_shared = false;
+  long long n_rings_main = 0;          // vortex rings covered by the strips of `lat` (4 reference filaments each)
+};
+
+// one dominant-kernel launch of a sweep, for vlc_sweep_stats
+struct SweepStat {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int kind = 0;  // 0 = bs_lattice_kernel, 1 = bs_sweep_kernel
+  double pairs = 0.0, instr = 0.0;
 };
 
 struct Rotor {
@@ -141,6 +149,11 @@ struct vlc_ctx {
   int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
   // multi-GPU data plane (group.hpp): this context's place in the target partition, its NCCL communicator (library-owned),
   // and -- for the members of an in-process group made by vlc_create_multi -- the group
+  bool stats_on = false;         // vlc_sweep_stats: per-launch events of the dominant kernels
+  std::vector<SweepStat> stats;
+  size_t stats_n = 0;
+  cudaEvent_t user_ev[8] = {};   // vlc_event_record slots
+  unsigned char* d_flush = nullptr;  // vlc_l2_flush scratch (256 MiB, allocated on first use)
   int rank = 0, world = 1;
   vlc::grp::NcclComm comm = nullptr;
   struct vlc_group* group = nullptr;
@@ -161,6 +174,27 @@ namespace {
 int fail(vlc_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
   return code;
+}
+
+// vlc_sweep_stats: an event pair around a dominant-kernel launch (events are created once and reused)
+SweepStat* stat_begin(vlc_ctx* c) {
+  if (!c->stats_on) return nullptr;
+  if (c->stats_n == c->stats.size()) {
+    SweepStat st;
+    if (cudaEventCreate(&st.e0) != cudaSuccess || cudaEventCreate(&st.e1) != cudaSuccess) return nullptr;
+    c->stats.push_back(st);
+  }
+  SweepStat* st = &c->stats[c->stats_n];
+  cudaEventRecord(st->e0, c->stream);
+  return st;
+}
+void stat_end(vlc_ctx* c, SweepStat* st, int kind, double pairs, double instr) {
+  if (!st) return;
+  cudaEventRecord(st->e1, c->stream);
+  st->kind = kind;
+  st->pairs = pairs;
+  st->instr = instr;
+  c->stats_n++;
 }
 
 // true while this thread executes ONE member's share of a replicated call (always on the worker threads): nested entry
@@ -350,8 +384,10 @@ int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const dou
     out = c->part.p;
   }
   cudaEventRecord(c->ev[0], c->stream);
+  SweepStat* st = stat_begin(c);
   int rc = launch_flat(c, src, n_pad, p, m, dP, out, nullptr, 0);
   if (rc) return rc;
+  stat_end(c, st, 1, (double)m * (double)n_pad, (double)m * (double)n_pad * (c->fast ? 41.0 : 43.0));
   cudaEventRecord(c->ev[1], c->stream);
   if (p.nsplit > 1) {
     const long long len = 3 * m;
@@ -495,6 +531,7 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   const bool side = (c->aux != nullptr);
   if (side) CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));  // inputs (records, targets, partial buffer) are ready here
   cudaEventRecord(c->ev[0], c->stream);
+  SweepStat* st = stat_begin(c);
   {
     dim3 grid(blocks_for(m, kLatThreads * LT), (unsigned)ns_l, 1);
     const long long lat_chunk = lat_chunk_tiles * lat_tile_of(LW);
@@ -507,6 +544,8 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
     CUDA_OK(c, cudaGetLastError());
     c->launches++;
   }
+  // reference pairs = 4 filaments per ring; issued FP64 instructions = (11 (W+1) + 50 W) per (target, strip record)
+  stat_end(c, st, 0, (double)m * 4.0 * (double)s.n_rings_main, (double)m * (double)s.n_lat_pad * (11.0 * (LW + 1) + 50.0 * LW));
   cudaEventRecord(c->ev[1], c->stream);
   // The flat remainder (and the fallback, which exits at once when the set is mergeable) go to a low-priority side
   // stream launched AFTER the lattice kernel: their CTAs fill the SMs that the lattice kernel's last wave leaves idle.
@@ -801,6 +840,7 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     CUDA_OK(c, cudaGetLastError());
     cs.n_lat = lat_n;
     cs.n_lat_pad = lat_pad;
+    cs.n_rings_main = (long long)r.nb * nrows * std::min(r.ns, nstrips * LW);
     cs.n_lat2 = lat2_n;
     cs.n_lat2_pad = lat2_pad;
     cs.lat2_W = TW;
@@ -1034,6 +1074,13 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     if (r.d_info) cudaFree(r.d_info);
   }
   if (c->solver) cusolverDnDestroy(c->solver);
+  for (auto& e : c->user_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& st : c->stats) {
+    if (st.e0) cudaEventDestroy(st.e0);
+    if (st.e1) cudaEventDestroy(st.e1);
+  }
+  if (c->d_flush) cudaFree(c->d_flush);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -2709,6 +2756,7 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
 
   // ---- shared-node form of the same lattice: strip records + flat remainder (bs_lattice.cuh) ----
   if (!append) {
+    s.n_rings_main = 0;
     s.n_lat = s.n_rem = s.n_lat2 = s.n_lat2_pad = 0;
     s.has_shared = true;
     s.lat_W = auto_strip_width(c, ns);  // lattices appended later share the record width of the first one
@@ -2770,6 +2818,7 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
     LAUNCH1D(c, vlc::pack_null_kernel, rem_pad - rem_new, rem_pad - rem_new, s.rem.p + (size_t)rem_new * vlc::kSrcDoubles);
   s.n_lat = lat_new;
   s.n_lat_pad = lat_pad;
+  s.n_rings_main += (long long)nrows * ns;
   s.n_rem = rem_new;
   s.n_rem_pad = rem_pad;
   return VLC_OK;
@@ -3030,6 +3079,86 @@ extern "C" int vlc_gridgen(vlc_ctx* c, int nx, int ny, int nz, const double* xyz
 }
 
 // ============================================================================ measurement
+
+// Device-side timing of whatever the caller brackets: the library runs on its own stream(s) -- several devices for a
+// group handle -- which no event of the caller's can see.
+extern "C" int vlc_event_record(vlc_ctx* c, int slot) {
+  CHECK_CTX(c);
+  VLC_GROUP(c, vlc_event_record(m, slot));
+  if (slot < 0 || slot >= 8) return fail(c, VLC_ERR_ARG, "event slot outside 0..7");
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (!c->user_ev[slot]) CUDA_OK(c, cudaEventCreate(&c->user_ev[slot]));
+  CUDA_OK(c, cudaEventRecord(c->user_ev[slot], c->stream));
+  return VLC_OK;
+}
+
+extern "C" int vlc_event_elapsed_ms(vlc_ctx* c, int slot_a, int slot_b, double* ms) {
+  CHECK_CTX(c);
+  if (!ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return fail(c, VLC_ERR_ARG, "bad event slots / null pointer");
+  if (c->group && c->is_leader && !t_in_member) {  // the slowest member
+    std::vector<double> each(c->group->members.size(), 0.0);
+    const int rc = group_all(c, [&](vlc_ctx* g_) -> int { return vlc_event_elapsed_ms(g_, slot_a, slot_b, &each[g_->rank]); });
+    if (rc) return rc;
+    *ms = *std::max_element(each.begin(), each.end());
+    return VLC_OK;
+  }
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (!c->user_ev[slot_a] || !c->user_ev[slot_b]) return fail(c, VLC_ERR_STATE, "event slot was never recorded");
+  CUDA_OK(c, cudaEventSynchronize(c->user_ev[slot_b]));
+  float f = 0.f;
+  CUDA_OK(c, cudaEventElapsedTime(&f, c->user_ev[slot_a], c->user_ev[slot_b]));
+  *ms = f;
+  return VLC_OK;
+}
+
+// Per-launch device times of the dominant kernels since the last reset, summed by kernel: [0] bs_lattice_kernel,
+// [1] bs_sweep_kernel (the launches that cover a set's main part; remainder / tail-strip launches are not counted).
+extern "C" int vlc_sweep_stats(vlc_ctx* c, int reset, int64_t* launches, double* ms, double* pairs, double* fp64_instr) {
+  CHECK_CTX(c);
+  int rc = bind_device(c);
+  if (rc) return rc;
+  if (launches || ms || pairs || fp64_instr) {
+    int64_t n[2] = {0, 0};
+    double t[2] = {0.0, 0.0}, pr[2] = {0.0, 0.0}, in[2] = {0.0, 0.0};
+    for (size_t k = 0; k < c->stats_n; ++k) {
+      SweepStat& st = c->stats[k];
+      CUDA_OK(c, cudaEventSynchronize(st.e1));
+      float f = 0.f;
+      CUDA_OK(c, cudaEventElapsedTime(&f, st.e0, st.e1));
+      n[st.kind]++;
+      t[st.kind] += f;
+      pr[st.kind] += st.pairs;
+      in[st.kind] += st.instr;
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (launches) launches[k] = n[k];
+      if (ms) ms[k] = t[k];
+      if (pairs) pairs[k] = pr[k];
+      if (fp64_instr) fp64_instr[k] = in[k];
+    }
+  }
+  if (reset) {
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->stats_n = 0;
+    c->stats_on = reset > 0;
+  }
+  return VLC_OK;
+}
+
+// Writes a 256 MiB scratch buffer (twice the 126 MB L2 of a B200) on the context's stream: bench.py calls it between
+// timed steps so that no step starts with the previous step's sources in L2.
+extern "C" int vlc_l2_flush(vlc_ctx* c) {
+  CHECK_CTX(c);
+  VLC_GROUP(c, vlc_l2_flush(m));
+  int rc = bind_device(c);
+  if (rc) return rc;
+  constexpr size_t kBytes = (size_t)256 << 20;
+  if (!c->d_flush) CUDA_OK(c, cudaMalloc(&c->d_flush, kBytes));
+  CUDA_OK(c, cudaMemsetAsync(c->d_flush, 0, kBytes, c->stream));
+  return VLC_OK;
+}
 
 static int measure_fp64(vlc_ctx* c, int iters, int pattern, double* flops_per_s, double* ms_out);
 extern "C" int vlc_measure_fp64_peak(vlc_ctx* c, int iters, double* flops_per_s, double* ms_out) {

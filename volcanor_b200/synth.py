@@ -182,3 +182,58 @@ def random_filaments(n: int, m: int, seed: int = 0, scale: float = 1.0):
         if m > 3 * k:
             P[2 * k:3 * k] = 0.5 * (p1[:k] + p2[:k])  # on the filament itself
     return p1, p2, rvc, gam, flag, P
+
+
+# ---- the same wakes in the reference's own record layout (what the Fortran driver holds and the shim hands over) ----
+
+VF, VR, FW = 12, 50, 13   # doubles per vf_class / vr_class (= Nwake_class) / Fwake_class record (classdef.f90:57-104, :181-220)
+
+
+def lattice_records(lat: Lattice):
+    """One blade's wake as the reference stores it: waN (S, R, 50) = Fortran waN(R, S) of Nwake_class records (ring corners
+    per vr_assignP, classdef.f90:569-592: filament k runs corner k -> k+1; rVc0 = rVc; gam at member 48) and waF (F, 13)
+    Fwake_class records (fc(:,1) = downstream end, fc(:,2) = upstream end; gam at member 12)."""
+    S, R = lat.S, lat.R
+    nd = lat.nodes
+    c = [nd[:-1, :-1], nd[:-1, 1:], nd[1:, 1:], nd[1:, :-1]]
+    waN = np.zeros((S, R, VR))
+    for f in range(4):
+        a, b = c[f], c[(f + 1) % 4]
+        waN[:, :, VF * f + 0:VF * f + 3] = a
+        waN[:, :, VF * f + 3:VF * f + 6] = b
+        ln = np.linalg.norm(b - a, axis=2)
+        waN[:, :, VF * f + 6] = ln          # l0
+        waN[:, :, VF * f + 7] = ln          # lc
+        waN[:, :, VF * f + 8] = lat.rvc4[:, :, f]
+        waN[:, :, VF * f + 9] = lat.rvc4[:, :, f]
+    waN[:, :, 48] = lat.gam
+    waF = np.zeros((lat.F, FW))
+    if lat.F > 0:
+        waF[:, 0:3] = lat.far_nodes[1:]
+        waF[:, 3:6] = lat.far_nodes[:-1]
+        ln = np.linalg.norm(lat.far_nodes[1:] - lat.far_nodes[:-1], axis=1)
+        waF[:, 6] = ln
+        waF[:, 7] = ln
+        waF[:, 8] = lat.rvcF
+        waF[:, 9] = lat.rvcF
+        waF[:, 12] = lat.gamF
+    return waN, waF
+
+
+def rotors_from_lattices(lattices: list[Lattice]) -> list[dict]:
+    """Group the blades' lattices into rotors (blades of one hub; the fixed wing is a one-bladed rotor without far wake):
+    [{nb, ns, nNwake, nFwake, waN: [per blade (ns, nNwake, 50)], waF: [per blade (nFwake, 13)], lattices}] in the order
+    of flatten_all / targets_all, so that source and target counts are those of the flat enumeration."""
+    rotors, key_of = [], {}
+    for l in lattices:
+        key = (l.meta.get("kind"), tuple(l.meta.get("hub", ())), l.R, l.S, l.F)
+        if l.meta.get("kind") != "rotor-blade" or key not in key_of:
+            key_of[key] = len(rotors)
+            rotors.append({"nb": 0, "ns": l.S, "nNwake": l.R, "nFwake": l.F, "waN": [], "waF": [], "lattices": []})
+        r = rotors[key_of[key]]
+        waN, waF = lattice_records(l)
+        r["nb"] += 1
+        r["waN"].append(waN)
+        r["waF"].append(waF)
+        r["lattices"].append(l)
+    return rotors
