@@ -140,6 +140,9 @@ struct vlc_ctx {
   DevBuf stage_V;
   DevBuf scratch;  // packing inputs for host-API set_sources
   DevBuf ws_P, ws_V, ws_acc;  // vlc_wake_sweep: targets of every convected blade, one source rotor's result, the sum
+  SourceSet ws_comb[2];       // vlc_wake_sweep: the packed sets of ALL source rotors side by side (one launch per sweep)
+  int* ws_flags = nullptr;    // device array of the addresses of the source rotors' mergeability flags (or_flags_kernel)
+  std::vector<const int*> ws_flags_host[2];  // what ws_flags holds for set s (re-uploaded only when the list changes)
   DevBuf cp_P, cp_V;          // tier 2c: collocation points of one rotor, one source rotor's velocities there
   unsigned char* d_flag = nullptr;
   size_t flag_cap = 0;
@@ -923,6 +926,114 @@ int pack_chord(vlc_ctx* c, Rotor& r) {
   return VLC_OK;
 }
 
+// out = OR of up to 64 device flags
+__global__ void or_flags_kernel(int n, const int* const* __restrict__ flags, int* __restrict__ out) {
+  int f = 0;
+  for (int k = 0; k < n; ++k) f |= *flags[k];
+  *out = f;
+}
+
+// The wake sweep sums over ALL source rotors (main.f90:817-826: vel = vel + vind_on?wake_byRotor(rotor(jr), ...)).  One
+// sweep per source rotor costs a wave tail, a pipeline fill per CTA and four launches each (measured r02e: 3.3 % of the
+// sweep at 1e6 filaments with 5 source rotors); instead the rotors' packed sets -- every one already padded with null
+// records to whole tiles -- are laid side by side with device-to-device copies (O(N), < 0.1 % of a sweep) and swept as
+// ONE set: strip records of all near wakes | flat remainders (wings, last columns, far wakes) | the flat enumeration
+// for the fallback, with the OR of the rotors' mergeability flags.  Possible when every lattice uses the same strip
+// width and none needs tail strips; *ok = false otherwise (the caller then sweeps rotor by rotor).  A strip record that
+// starts a rotor's block starts a strip (streamwise strengths 0), so the nodes of the record before it are never used.
+int build_ws_combined(vlc_ctx* c, int s, bool* ok) {
+  *ok = false;
+  std::vector<Rotor*> src;
+  for (auto& r : c->rotors)
+    if (r.defined) {
+      int rc = pack_rotor(c, r, s);
+      if (rc) return rc;
+      if (r.comb[s].n_pad > 0) src.push_back(&r);
+    }
+  if (src.size() < 2 || src.size() > 64) return VLC_OK;  // one source rotor: its own set is the combined set
+  int W = 0;
+  bool any_shared = false;
+  for (Rotor* r : src) {
+    const SourceSet& v = r->comb[s];
+    if (!(v.has_shared && c->shared_nodes && v.n_lat_pad > 0)) continue;
+    if (v.n_lat2_pad > 0) return VLC_OK;
+    if (W && v.lat_W != W) return VLC_OK;
+    W = v.lat_W;
+    any_shared = true;
+  }
+  SourceSet& w = c->ws_comb[s];
+  long long n = 0, n_pad = 0, lat_n = 0, lat_pad = 0, rem_n = 0, rem_pad = 0, rings = 0;
+  for (Rotor* r : src) {
+    const SourceSet& v = r->comb[s];
+    const bool sh = any_shared && v.has_shared && v.n_lat_pad > 0;
+    n += v.n;
+    n_pad += v.n_pad;
+    if (sh) {
+      lat_n += v.n_lat;
+      lat_pad += v.n_lat_pad;
+      rings += v.n_rings_main;
+    }
+    rem_n += sh ? v.n_rem : v.n;  // a rotor without a lattice (no wake row yet) goes to the remainder whole
+    rem_pad += sh ? v.n_rem_pad : v.n_pad;
+  }
+  int rc;
+  if ((rc = reserve(c, w.rec, (size_t)n_pad * vlc::kSrcDoubles))) return rc;
+  const int RD = W ? lat_rd_of(W) : 0;
+  if (any_shared) {
+    if ((rc = reserve(c, w.lat, (size_t)lat_pad * RD)) || (rc = reserve(c, w.rem, (size_t)rem_pad * vlc::kSrcDoubles))) return rc;
+    if (!w.d_unmergeable) CUDA_OK(c, cudaMalloc(&w.d_unmergeable, sizeof(int)));
+    if (!c->ws_flags) CUDA_OK(c, cudaMalloc(&c->ws_flags, sizeof(int*) * 128));  // 64 per record set
+  }
+  cudaStream_t st = c->stream;
+  auto d2d = [&](double* dst, const double* from, size_t doubles) -> int {
+    if (doubles) CUDA_OK(c, cudaMemcpyAsync(dst, from, doubles * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return VLC_OK;
+  };
+  size_t o_rec = 0, o_lat = 0, o_rem = 0;
+  std::vector<const int*> flags;
+  for (Rotor* r : src) {
+    const SourceSet& v = r->comb[s];
+    const bool sh = any_shared && v.has_shared && v.n_lat_pad > 0;
+    if ((rc = d2d(w.rec.p + o_rec, v.rec.p, (size_t)v.n_pad * vlc::kSrcDoubles))) return rc;
+    o_rec += (size_t)v.n_pad * vlc::kSrcDoubles;
+    if (!any_shared) continue;
+    if (sh) {
+      if ((rc = d2d(w.lat.p + o_lat, v.lat.p, (size_t)v.n_lat_pad * RD))) return rc;
+      o_lat += (size_t)v.n_lat_pad * RD;
+      if ((rc = d2d(w.rem.p + o_rem, v.rem.p, (size_t)v.n_rem_pad * vlc::kSrcDoubles))) return rc;
+      o_rem += (size_t)v.n_rem_pad * vlc::kSrcDoubles;
+      flags.push_back(v.d_unmergeable);
+    } else {
+      if ((rc = d2d(w.rem.p + o_rem, v.rec.p, (size_t)v.n_pad * vlc::kSrcDoubles))) return rc;
+      o_rem += (size_t)v.n_pad * vlc::kSrcDoubles;
+    }
+  }
+  if (any_shared) {
+    const int* const* d_list = reinterpret_cast<const int* const*>(c->ws_flags) + 64 * s;
+    if (c->ws_flags_host[s] != flags) {  // the addresses are stable: uploaded once per record set
+      CUDA_OK(c, cudaStreamSynchronize(st));
+      c->ws_flags_host[s] = flags;
+      CUDA_OK(c, cudaMemcpy((void*)d_list, c->ws_flags_host[s].data(), sizeof(int*) * flags.size(), cudaMemcpyHostToDevice));
+    }
+    or_flags_kernel<<<1, 1, 0, st>>>((int)flags.size(), d_list, w.d_unmergeable);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+  }
+  w.n = n;
+  w.n_pad = n_pad;
+  w.has_shared = any_shared;
+  w.lat_W = W ? W : 1;
+  w.n_lat = lat_n;
+  w.n_lat_pad = any_shared ? lat_pad : 0;
+  w.n_lat2 = w.n_lat2_pad = 0;
+  w.lat2_W = 0;
+  w.n_rem = rem_n;
+  w.n_rem_pad = any_shared ? rem_pad : 0;
+  w.n_rings_main = rings;
+  *ok = true;
+  return VLC_OK;
+}
+
 int upload(vlc_ctx* c, DevBuf& b, size_t total, size_t offset, const double* host, size_t count) {
   int rc = reserve(c, b, total);
   if (rc) return rc;
@@ -1031,6 +1142,13 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   release(c->stage_P);
   release(c->stage_V);
   release(c->scratch);
+  for (auto& w : c->ws_comb) {
+    release(w.rec);
+    release(w.lat);
+    release(w.rem);
+    if (w.d_unmergeable) cudaFree(w.d_unmergeable);
+  }
+  if (c->ws_flags) cudaFree(c->ws_flags);
   release(c->ws_P);
   release(c->ws_V);
   release(c->ws_acc);
@@ -2182,6 +2300,14 @@ extern "C" int vlc_wake_sweep_slice(vlc_ctx* c, int predicted, int64_t first, in
   CUDA_OK(c, cudaGetLastError());
   const double* P = c->ws_P.p + 3 * first;
   double* acc = d_vel + 3 * first;
+  {  // all source rotors as ONE set (build_ws_combined); rotor by rotor below when their strip shapes differ
+    bool ok = false;
+    if ((rc = build_ws_combined(c, s, &ok))) return rc;
+    if (ok) {
+      const SourceSet& v = c->ws_comb[s];
+      return (v.has_shared && c->shared_nodes) ? sweep_shared(c, v, count, P, acc) : sweep(c, v.rec.p, v.n_pad, count, P, acc);
+    }
+  }
   bool first_src = true;
   for (auto& src : c->rotors) {  // jr = 1..nr in order (main.f90:817)
     if (!src.defined) continue;
