@@ -478,6 +478,11 @@ def main():
                 "kernel_share_of_step": kern_ms_total / elapsed_ms if elapsed_ms > 0 else None,
                 "pairs_per_launch": st["pairs"] / n_launch, "flops_per_pair": FLOPS_PER_PAIR,
                 "pipe_frac": st["fp64_instr"] * 2 / (kern_ms_total * 1e-3) / fp64_peak if kern_ms_total > 0 else 0.0,
+                "sweep": {"ms": st["sweep_ms"] / n_launch, "pairs": st["sweep_pairs"] / n_launch,
+                          "pipe_frac": st["sweep_fp64_instr"] * 2 / (st["sweep_ms"] * 1e-3) / fp64_peak if st["sweep_ms"] > 0 else 0.0,
+                          "note": "whole sweep = dominant kernel + flat remainder (last columns, horseshoe corrections, far wakes; "
+                                  "low-priority side stream: its CTAs share SMs with the dominant kernel inside that kernel's window) "
+                                  "+ fixed-order reduce of the source-split partial sums"},
                 "same_work": same_work, "frac_same_work": same_work["frac"] if same_work else None,
                 "dfma_3reg_tflops": fp64_rate3 / 1e12,
                 "peak_source": "measured live: vlc_measure_fp64_peak (register-resident DFMA chains, all SMs); MEASURED_PEAKS.json has no "

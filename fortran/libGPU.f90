@@ -61,6 +61,10 @@ module libGPU
       integer(c_int), intent(in) :: devices(*)
       type(c_ptr), intent(out) :: out
     end function
+    integer(c_int) function vlc_rotors_clear(c) bind(C, name='vlc_rotors_clear')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+    end function
     integer(c_int) function vlc_destroy(c) bind(C, name='vlc_destroy')
       import :: c_int, c_ptr
       type(c_ptr), value :: c
@@ -385,6 +389,7 @@ contains
     else
       call check(vlc_create(int(device, c_int), ctx))
     endif
+    call check(vlc_rotors_clear(ctx))
     allocate (stale(3, size(rotor)))
     stale = .true.
     do ir = 1, size(rotor)

@@ -130,6 +130,10 @@ int vlc_source_tile(void);
  * panels, nNwake near-wake rows, nFwake far-wake rows; surfaceType as rotor%surfaceType (+-1 lifting,
  * +-2 non-lifting: vind_bywing returns 0, classdef.f90:4437-4441 + :544-554). */
 int vlc_rotor_define(vlc_ctx* ctx, int ir, int nb, int nc, int ns, int nNwake, int nFwake, int surfaceType);
+/* Forget every rotor declared so far (their device buffers are kept for re-use).  The sweeps of tiers 2b / 2c sum over
+ * ALL declared rotors, like the reference's loops over rotor(1:nr): a context that is re-used for another configuration
+ * starts from here (the shim's gpu_init calls it before declaring the rotors of config.nml). */
+int vlc_rotors_clear(vlc_ctx* ctx);
 /* rotor%rowNear, rotor%rowFar (1-based, as in the reference, main.f90:412-417). */
 int vlc_rotor_set_rows(vlc_ctx* ctx, int ir, int rowNear, int rowFar);
 /* Upload blade ib (0-based) state in reference record layout. predicted != 0 -> waNPredicted etc.
@@ -420,10 +424,13 @@ int vlc_gridgen_slice(vlc_ctx* ctx, int nx, int ny, int nz, const double* xyzMin
 int vlc_event_record(vlc_ctx* ctx, int slot);
 int vlc_event_elapsed_ms(vlc_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* Roofline bookkeeping of the dominant kernels, measured with one CUDA event pair per launch on the launching stream:
- * reset > 0 starts collecting (and clears), reset < 0 stops; the four output arrays (any may be NULL) receive, for
- * [0] bs_lattice_kernel and [1] bs_sweep_kernel, the launches since the last reset, their summed device time in ms, the
- * reference pair interactions they stand for (lattice: targets x 4 filaments x rings; flat: targets x filaments) and the
- * FP64-pipe instructions they issued (lattice: (11(W+1) + 50W) per (target, strip record); flat: 43 per pair).  Reads
+ * reset > 0 starts collecting (and clears), reset < 0 stops.  Output arrays (any may be NULL): launches[2]; ms[4],
+ * pairs[4], fp64_instr[4].  Entries [0] bs_lattice_kernel and [1] bs_sweep_kernel: the dominant launches since the last
+ * reset, their summed device time in ms, the reference pair interactions they stand for (lattice: targets x 4 filaments x
+ * rings; flat: targets x filaments) and the FP64-pipe instructions they issued (lattice: (11(W+1) + 50W) per (target, strip
+ * record); flat: 43 per pair).  Entries [2], [3]: the same for the WHOLE sweeps those launches belong to (dominant kernel
+ * + tail strips + flat remainder + reduce, window = first launch to end of the reduce): the remainder runs on a
+ * low-priority side stream and its CTAs may share SMs with the dominant kernel, inside that kernel's own window.  Reads
  * the first member of a group handle (its slice of the targets). */
 int vlc_sweep_stats(vlc_ctx* ctx, int reset, int64_t* launches, double* ms, double* pairs, double* fp64_instr);
 /* memset of a 256 MiB scratch buffer on the context's stream(s): evicts the previous step's data from the 126 MB L2. */

@@ -669,6 +669,7 @@ void *case_gpu_hooks_install(orc_case_t *cas, vlc_ctx *ctx, int nr) {
   u->cas = cas;
   u->ctx = ctx;
   u->nr = nr;
+  vlc_rotors_clear(ctx); /* the context may have served another case: its rotors would be sources of this one's sweeps */
   for (int ir = 0; ir < nr; ++ir) {
     int d[10];
     orc_rotor_dims(orc_case_rotor(cas, ir), d);

@@ -122,6 +122,7 @@ def load_library() -> C.CDLL:
         "vlc_vind_range_dev": (i32, [_vp, i32, i64, i64, i64, _vp, _vp]),
         "vlc_source_tile": (i32, []),
         "vlc_rotor_define": (i32, [_vp, i32, i32, i32, i32, i32, i32, i32]),
+        "vlc_rotors_clear": (i32, [_vp]),
         "vlc_rotor_set_rows": (i32, [_vp, i32, i32, i32]),
         "vlc_rotor_put_wing": (i32, [_vp, i32, i32, _vp]),
         "vlc_rotor_put_nwake": (i32, [_vp, i32, i32, i32, _vp]),
@@ -323,9 +324,10 @@ class Context:
 
     def sweep_stats(self, reset: int = 0) -> dict:
         """Per-launch device times of the dominant kernels since the last reset (reset=1 starts collecting)."""
-        n, ms, pr, ins = (C.c_int64 * 2)(), (C.c_double * 2)(), (C.c_double * 2)(), (C.c_double * 2)()
+        n, ms, pr, ins = (C.c_int64 * 2)(), (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)()
         self._ck(self.lib.vlc_sweep_stats(self.h, reset, n, ms, pr, ins))
-        return {k: {"launches": int(n[i]), "ms": ms[i], "pairs": pr[i], "fp64_instr": ins[i]}
+        return {k: {"launches": int(n[i]), "ms": ms[i], "pairs": pr[i], "fp64_instr": ins[i],
+                    "sweep_ms": ms[2 + i], "sweep_pairs": pr[2 + i], "sweep_fp64_instr": ins[2 + i]}
                 for i, k in enumerate(("bs_lattice_kernel", "bs_sweep_kernel"))}
 
     def l2_flush(self):
@@ -385,6 +387,10 @@ class Context:
     # -- tier 2 -----------------------------------------------------------------------------
     def rotor_define(self, ir, nb, nc, ns, nNwake, nFwake, surfaceType=1):
         self._ck(self.lib.vlc_rotor_define(self.h, ir, nb, nc, ns, nNwake, nFwake, surfaceType))
+
+    def rotors_clear(self):
+        """Forget every declared rotor (the resident sweeps sum over all of them)."""
+        self._ck(self.lib.vlc_rotors_clear(self.h))
 
     def rotor_set_rows(self, ir, rowNear, rowFar):
         self._ck(self.lib.vlc_rotor_set_rows(self.h, ir, rowNear, rowFar))

@@ -68,9 +68,10 @@ struct SourceSet {
 
 // one dominant-kernel launch of a sweep, for vlc_sweep_stats
 struct SweepStat {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;  // before / after the dominant kernel, after the whole sweep
   int kind = 0;  // 0 = bs_lattice_kernel, 1 = bs_sweep_kernel
-  double pairs = 0.0, instr = 0.0;
+  double pairs = 0.0, instr = 0.0;            // of the dominant kernel
+  double pairs_all = 0.0, instr_all = 0.0;    // of every kernel of the sweep (+ tail strips, flat remainder)
 };
 
 struct Rotor {
@@ -184,7 +185,8 @@ SweepStat* stat_begin(vlc_ctx* c) {
   if (!c->stats_on) return nullptr;
   if (c->stats_n == c->stats.size()) {
     SweepStat st;
-    if (cudaEventCreate(&st.e0) != cudaSuccess || cudaEventCreate(&st.e1) != cudaSuccess) return nullptr;
+    if (cudaEventCreate(&st.e0) != cudaSuccess || cudaEventCreate(&st.e1) != cudaSuccess || cudaEventCreate(&st.e2) != cudaSuccess)
+      return nullptr;
     c->stats.push_back(st);
   }
   SweepStat* st = &c->stats[c->stats_n];
@@ -195,8 +197,15 @@ void stat_end(vlc_ctx* c, SweepStat* st, int kind, double pairs, double instr) {
   if (!st) return;
   cudaEventRecord(st->e1, c->stream);
   st->kind = kind;
-  st->pairs = pairs;
-  st->instr = instr;
+  st->pairs = st->pairs_all = pairs;
+  st->instr = st->instr_all = instr;
+}
+// after the last kernel of the sweep (the reduce): closes the record
+void stat_close(vlc_ctx* c, SweepStat* st, double pairs_extra, double instr_extra) {
+  if (!st) return;
+  cudaEventRecord(st->e2, c->stream);
+  st->pairs_all += pairs_extra;
+  st->instr_all += instr_extra;
   c->stats_n++;
 }
 
@@ -399,6 +408,7 @@ int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const dou
     c->launches++;
   }
   cudaEventRecord(c->ev[2], c->stream);
+  stat_close(c, st, 0.0, 0.0);
   c->ev_valid = true;
   return VLC_OK;
 }
@@ -584,6 +594,11 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   cudaEventRecord(c->ev[2], c->stream);
+  {  // the sweep's other kernels: tail strips (lattice form) and the flat remainder
+    const double in2 = LW2 ? (double)m * (double)s.n_lat2_pad * (11.0 * (LW2 + 1) + 50.0 * LW2) : 0.0;
+    const double inr = (double)m * (double)s.n_rem_pad * (c->fast ? 41.0 : 43.0);
+    stat_close(c, st, (double)m * (double)s.n_pad - (double)m * 4.0 * (double)s.n_rings_main, in2 + inr);
+  }
   c->ev_valid = true;
   return VLC_OK;
 }
@@ -1197,6 +1212,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
   for (auto& st : c->stats) {
     if (st.e0) cudaEventDestroy(st.e0);
     if (st.e1) cudaEventDestroy(st.e1);
+    if (st.e2) cudaEventDestroy(st.e2);
   }
   if (c->d_flush) cudaFree(c->d_flush);
   for (auto& e : c->ev)
@@ -1596,6 +1612,13 @@ extern "C" int vlc_rotor_define(vlc_ctx* c, int ir, int nb, int nc, int ns, int 
     CUDA_OK(c, cudaMemsetAsync(r.pfHelix[s].p, 0, r.pfHelix[s].cap * sizeof(double), c->stream));
   }
   if ((rc = reserve(c, r.pfFits, (size_t)nb * (sizeof(vlc::pf::Fit) / sizeof(double))))) return rc;
+  return VLC_OK;
+}
+
+extern "C" int vlc_rotors_clear(vlc_ctx* c) {
+  CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotors_clear(m));
+  for (auto& r : c->rotors) r.defined = false;  // buffers are kept for the next definition
   return VLC_OK;
 }
 
@@ -3247,19 +3270,24 @@ extern "C" int vlc_sweep_stats(vlc_ctx* c, int reset, int64_t* launches, double*
   if (rc) return rc;
   if (launches || ms || pairs || fp64_instr) {
     int64_t n[2] = {0, 0};
-    double t[2] = {0.0, 0.0}, pr[2] = {0.0, 0.0}, in[2] = {0.0, 0.0};
+    double t[4] = {0.0, 0.0, 0.0, 0.0}, pr[4] = {0.0, 0.0, 0.0, 0.0}, in[4] = {0.0, 0.0, 0.0, 0.0};
     for (size_t k = 0; k < c->stats_n; ++k) {
       SweepStat& st = c->stats[k];
-      CUDA_OK(c, cudaEventSynchronize(st.e1));
-      float f = 0.f;
+      CUDA_OK(c, cudaEventSynchronize(st.e2));
+      float f = 0.f, g = 0.f;
       CUDA_OK(c, cudaEventElapsedTime(&f, st.e0, st.e1));
+      CUDA_OK(c, cudaEventElapsedTime(&g, st.e0, st.e2));
       n[st.kind]++;
       t[st.kind] += f;
       pr[st.kind] += st.pairs;
       in[st.kind] += st.instr;
+      t[2 + st.kind] += g;
+      pr[2 + st.kind] += st.pairs_all;
+      in[2 + st.kind] += st.instr_all;
     }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 2; ++k)
       if (launches) launches[k] = n[k];
+    for (int k = 0; k < 4; ++k) {
       if (ms) ms[k] = t[k];
       if (pairs) pairs[k] = pr[k];
       if (fp64_instr) fp64_instr[k] = in[k];
