@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--single-process", action="store_true",
                     help="ONE process, --gpus N devices behind one handle (vlc_create_multi): what a single-process Fortran "
                          "driver gets; the default for N > 1 is one process per GPU under torchrun (vlc_comm_init_rank)")
+    ap.add_argument("--core-slope", type=float, default=0.0,
+                    help="non-uniform streamwiseCoreVec: vf(1)/vf(3) core radii of column j scaled by (1 + slope*j), so that the two "
+                         "copies of every interior streamwise edge differ (SURVEY C2) and the sweeps use the DUAL form of the lattice "
+                         "kernel; 0 = the BASELINE workload (uniform)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -298,6 +302,12 @@ def main():
     lats, n_src, m, name = workload(args)
     rotors = synth.rotors_from_lattices(lats)
     nr = len(rotors)
+    if args.core_slope:
+        for r in rotors:
+            for w in r["waN"]:
+                f = 1.0 + args.core_slope * np.arange(r["ns"])[:, None]
+                for k in (8, 9, 24 + 8, 24 + 9):
+                    w[:, :, k] *= f
     if single:
         ctx = vb.Context(devices=list(range(args.gpus)))   # one handle, N GPUs: the library owns threads + communicators
     else:
@@ -330,7 +340,8 @@ def main():
     assert ctx.wake_sweep_count() == m, (ctx.wake_sweep_count(), m)
     info = [ctx.rotor_info(ir) for ir in range(nr)]
     assert sum(i["filaments"] for i in info) == n_src, (info, n_src)
-    shared = all(i["shared_active"] == 1 for i in info)
+    shared = all(i["shared_active"] in (1, 2) for i in info)
+    dual = any(i["shared_active"] == 2 for i in info)
     fp64_peak, _ = ctx.measure_fp64_peak(20000)
     fp64_rate3, _ = ctx.measure_fp64_rate(1, 20000)    # DFMA rate with three changing register operands (informational)
 
@@ -452,7 +463,12 @@ def main():
     # ---- roofline of the dominant kernel: one CUDA-event pair per launch on the launching stream, over the timed region ----
     peak = fp64_peak / 1e12
     kernel = "bs_lattice_kernel" if shared else "bs_sweep_kernel"
-    st = stats[kernel]
+    st = dict(stats[kernel])
+    if shared and dual:     # the library counts the merged form's instructions (the host never reads the flag): 58 W instead of 50 W
+        W_ = int(info[0]["strip_width"])
+        extra = st["fp64_instr"] * ((11 * (W_ + 1) + 58 * W_) / (11 * (W_ + 1) + 50 * W_) - 1.0)
+        st["fp64_instr"] += extra
+        st["sweep_fp64_instr"] += extra
     kern_ms_total, n_launch = st["ms"], max(st["launches"], 1)
     achieved = st["pairs"] * FLOPS_PER_PAIR / (kern_ms_total * 1e-3) / 1e12 if kern_ms_total > 0 else 0.0
     note = ("shared-node lattice kernel: every lattice node evaluated once per target and every interior edge once with the "
@@ -521,7 +537,8 @@ def main():
                                          "single GPU")),
                       "launch": "eager: every kernel launched per step on the library's stream(s)",
                       "tuning": {"T": args.T, "nsplit": args.nsplit},
-                      "sources": ({"form": "shared-node lattice", "strip_width": int(info[0]["strip_width"]),
+                      "sources": ({"form": "shared-node lattice" + (", DUAL form (two core radii per streamwise edge)" if dual else ""),
+                                   "core_slope": args.core_slope, "strip_width": int(info[0]["strip_width"]),
                                    "strip_records": int(sum(i["lattice_records"] for i in info)),
                                    "remainder_filaments": int(sum(i["remainder_filaments"] for i in info)),
                                    "source_rotors": nr} if shared else {"form": "flat reference enumeration", "source_rotors": nr})},

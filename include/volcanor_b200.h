@@ -375,8 +375,10 @@ int vlc_set_shared_nodes(vlc_ctx* ctx, int on);
  * 0 = default.  Takes effect at the next pack.  Only speed and summation order change. */
 int vlc_set_lattice_tuning(vlc_ctx* ctx, int strip_width, int targets_per_thread);
 /* out[0..5]: out[0] = filaments in the reference's enumeration, out[1] = strip records and out[2] = remainder filaments of
- * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel, 0 if
- * the flat one (reads the device flag: synchronises), -1 for a flat-only set, out[4] = strip width of the records,
+ * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel with merged
+ * edge strengths, 2 if its dual form (rotor records whose streamwise edge copies carry different core radii: a non-uniform
+ * streamwiseCoreVec, classdef.f90:3841, :4371-4372), 0 if the flat kernel on the reference's enumeration (reads the device
+ * flag: synchronises), -1 for a flat-only set, out[4] = strip width of the records,
  * out[5] = width of the tail strips (0 = none): a rotor's lattice with ns columns, ns not a multiple of 4, is covered by
  * floor(ns/4) strips of width 4 plus one strip of width ns mod 4 when that is cheaper than padding the last strip. */
 int vlc_set_info(vlc_ctx* ctx, int set, int64_t* out);

@@ -49,6 +49,11 @@ static inline double __hiloint2double(int hi, int lo) {
   std::memcpy(&r, &b, sizeof r);
   return r;
 }
+static inline int atomicOr(int* p, int v) {  // one emulated thread at a time
+  const int old = *p;
+  *p = old | v;
+  return old;
+}
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 
 // run kernel(args...) for every thread of a 1-D / 2-D grid, serially, in reverse order (the kernels must not depend on

@@ -188,13 +188,22 @@ static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nro
               lat.data(), unmergeable, 0LL);
   if (npad > nrec)
     emul_launch(blocks_for(npad - nrec, 128), 1, 128, vlc::pack_null_lat_kernel<W>, npad - nrec, lat.data() + (size_t)nrec * RD);
-  if (*unmergeable) return 1;
+  if (*unmergeable & 1) return 1;
   const long long tiles = npad / TILE, chunk_tiles = (tiles + nsplit - 1) / nsplit;
   const int real_split = (int)((tiles + chunk_tiles - 1) / chunk_tiles);
   const size_t len = 3 * (size_t)m, at = parts.size();
   parts.resize(at + (size_t)real_split * len, 0.0);
+  // both forms are launched, as on the device; the set's flag (0 merged / 2 dual) decides which one does the work
+  std::vector<double> other((size_t)real_split * len, std::nan(""));
+  const bool dual = (*unmergeable == 2);
   emul_launch(blocks_for(m, THREADS * T), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>,
-              (const double*)lat.data(), chunk_tiles * TILE, npad, P, m, parts.data() + at, (const int*)unmergeable, 0);
+              (const double*)lat.data(), chunk_tiles * TILE, npad, P, m, dual ? other.data() : parts.data() + at,
+              (const int*)unmergeable, 3, 0);
+  emul_launch(blocks_for(m, THREADS), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, 1, THREADS, 3, 1, true>,
+              (const double*)lat.data(), chunk_tiles * TILE, npad, P, m, dual ? parts.data() + at : other.data(),
+              (const int*)unmergeable, 3, 2);
+  for (double v : other)
+    if (v == v) return 4;  // the form that must not run wrote something
   *nslots += real_split;
   return 0;
 }
@@ -234,12 +243,22 @@ int emul_lattice_vind_split(int W, int T, int tailW, int nsplit, const double* w
   std::vector<double> rem((size_t)nrows * vlc::kSrcDoubles);
   emul_launch(blocks_for(nrows, 128), 1, 128, vlc::pack_rings_kernel, waN + (size_t)vlc::kVr * nNwake * (ns - 1), vlc::kVr, nNwake, i0,
               nrows, 1, 0x4, 1, 1.0, 1, rem.data(), 0LL, 0LL);
-  parts.resize(parts.size() + len);
-  emul_vind_records(nrows, rem.data(), m, P, parts.data() + (size_t)nslots * len);
-  ++nslots;
-  emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)parts.data(),
-              (const int*)&unmergeable, nslots, 0, (long long)len, V);
-  return 0;
+  std::vector<double> remv(len);
+  emul_vind_records(nrows, rem.data(), m, P, remv.data());
+  // slot layout of sweep_shared: [merged | remainder | dual | flat]; the lattice slots above belong to the form the flag names
+  std::vector<double> all;
+  if (unmergeable == 2) {
+    all = remv;
+    all.insert(all.end(), parts.begin(), parts.end());
+    emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)all.data(),
+                (const int*)&unmergeable, 0, 1, nslots, 0, (long long)len, V);
+  } else {
+    all = parts;
+    all.insert(all.end(), remv.begin(), remv.end());
+    emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)all.data(),
+                (const int*)&unmergeable, nslots, 1, 0, 0, (long long)len, V);
+  }
+  return unmergeable == 2 ? -2 : 0;  // -2: done, by the dual form
 }
 
 int emul_lattice_vind_plan(int W, int T, int tailW, const double* waN, int nNwake, int ns, int i0, int nrows, long long m,
@@ -278,17 +297,20 @@ int emul_lattice_vind_dispatch(int nsplit_flat, const double* waN, int nNwake, i
   const long long rem_pad = flat_records(waN + (size_t)vlc::kVr * nNwake * (ns - 1), 1, 0x4, 1, rem);
   const long long flat_pad = flat_records(waN, ns, 0xF, 4, flat);
   const long long ftiles = flat_pad / FTILE, fchunk_tiles = (ftiles + nsplit_flat - 1) / nsplit_flat;
-  const int nb = (int)((ftiles + fchunk_tiles - 1) / fchunk_tiles), na = 2;
+  const int nb = (int)((ftiles + fchunk_tiles - 1) / fchunk_tiles);
   const size_t len = 3 * (size_t)m;
-  std::vector<double> parts((size_t)(na + nb) * len, std::nan(""));
+  // slots: [0] merged lattice, [1] flat remainder, [2] dual lattice, [3 ..] flat enumeration
+  std::vector<double> parts((size_t)(3 + nb) * len, std::nan(""));
   emul_launch(blocks_for(m, THREADS * T), 1, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>, (const double*)lat.data(), npad, npad,
-              P, m, parts.data(), (const int*)&flag, 0);
+              P, m, parts.data(), (const int*)&flag, 3, 0);
+  emul_launch(blocks_for(m, THREADS), 1, THREADS, vlc::bs_lattice_kernel<W, 1, THREADS, 3, 1, true>, (const double*)lat.data(), npad,
+              npad, P, m, parts.data() + 2 * len, (const int*)&flag, 3, 2);
   emul_launch(blocks_for(m, THREADS * FT), 1, THREADS, vlc::bs_sweep_kernel<FT, THREADS, FTILE, 3, 1, false>, (const double*)rem.data(),
-              rem_pad, rem_pad, P, m, parts.data() + len, (const int*)&flag, 0);
+              rem_pad, rem_pad, P, m, parts.data() + len, (const int*)&flag, 1, 0);
   emul_launch(blocks_for(m, THREADS * FT), (unsigned)nb, THREADS, vlc::bs_sweep_kernel<FT, THREADS, FTILE, 3, 1, false>,
-              (const double*)flat.data(), fchunk_tiles * FTILE, flat_pad, P, m, parts.data() + (size_t)na * len, (const int*)&flag, 1);
-  emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)parts.data(), (const int*)&flag, na,
-              nb, (long long)len, V);
+              (const double*)flat.data(), fchunk_tiles * FTILE, flat_pad, P, m, parts.data() + 3 * len, (const int*)&flag, 1, 1);
+  emul_launch(blocks_for((long long)len, 256), 1, 256, vlc::bs_reduce_select_kernel, (const double*)parts.data(), (const int*)&flag, 1,
+              1, 1, nb, (long long)len, V);
   *flag_out = flag;
   return 0;
 }
@@ -312,10 +334,10 @@ int emul_flat_sweep(int fast, int nsplit, long long n, const double* p1, const d
   std::vector<double> part((size_t)nsplit * 3 * (size_t)m);
   if (fast)
     emul_launch(blocks_for(m, THREADS * T), (unsigned)nsplit, THREADS, vlc::bs_sweep_kernel<T, THREADS, TILE, 3, 1, true>,
-                (const double*)rec.data(), chunk, npad, P, m, part.data(), (const int*)nullptr, 0);
+                (const double*)rec.data(), chunk, npad, P, m, part.data(), (const int*)nullptr, 0, 0);
   else
     emul_launch(blocks_for(m, THREADS * T), (unsigned)nsplit, THREADS, vlc::bs_sweep_kernel<T, THREADS, TILE, 3, 1, false>,
-                (const double*)rec.data(), chunk, npad, P, m, part.data(), (const int*)nullptr, 0);
+                (const double*)rec.data(), chunk, npad, P, m, part.data(), (const int*)nullptr, 0, 0);
   emul_launch(blocks_for(3 * m, 256), 1, 256, vlc::bs_reduce_kernel, (const double*)part.data(), nsplit, 3 * m, V);
   return 0;
 }

@@ -189,6 +189,54 @@ def test_unmergeable_core_radii_fall_back_to_flat_enumeration(ctx, oracle):
     assert not np.array_equal(Vs2, Vf2) and scaled_err(Vs2, Vf2, Vabs2) < TOL
 
 
+@pytest.mark.parametrize("ns,nNwake,W", [(8, 12, 0), (6, 9, 0), (5, 7, 0), (7, 10, 2)])
+def test_nonuniform_streamwise_cores_use_the_dual_form(ctx, oracle, ns, nNwake, W):
+    """Rotor records shed with a non-uniform streamwiseCoreVec (classdef.f90:3841; dissipate_wake keeps vf(3)%rVc = vf(1)%rVc
+    of the same ring, :4371-4372): the two copies of every interior streamwise edge differ.  Round 1 abandoned the lattice
+    kernel for the whole set; now check_rings_kernel selects the DUAL form (rotor_info: shared_active == 2): same nodes, same
+    spanwise edges, 33-instruction streamwise edges with both core radii.  Per-call parity against the oracle's ring-by-ring
+    sum, for every source loop that contains the wake, with tail strips (ns = 5, 6, 7) and a forced strip width."""
+    from tests.test_gpu_parity import _make_rotor_pair, _tol_scale
+    ctx.rotors_clear()
+    ctx.set_lattice_tuning(W, 0)
+    try:
+        ro = _make_rotor_pair(ctx, oracle, seed=13, ns=ns, nNwake=nNwake, nFwake=4, rowNear=2, rowFar=2)
+        for pred in (False, True):
+            for ib in range(ro.nb):
+                w = ro.waN(ib, pred)
+                for j in range(ns):
+                    w[j, :, 9] *= 1.0 + 0.25 * j             # vf(1)%rVc by column
+                    w[j, :, 24 + 9] = w[j, :, 9]              # vf(3)%rVc = vf(1)%rVc of the same ring
+                ctx.rotor_put_nwake(0, ib, w, pred)
+        assert ctx.rotor_info(0)["shared_active"] == 2 and ctx.rotor_info(0, True)["shared_active"] == 2
+        rng = np.random.default_rng(3)
+        nodes = ro.waN(0)[:, 1:, 12:15].reshape(-1, 3)
+        P = np.concatenate([rng.uniform(-1.5, 1.5, size=(300, 3)), nodes,
+                            0.5 * (ro.waN(1)[:, 1:, 0:3] + ro.waN(1)[:, 1:, 12:15]).reshape(-1, 3)])
+        s = _tol_scale(ro, P) * 50
+        got = ctx.rotor_vind_bywake(0, P)
+        assert np.max(np.abs(got - ro.vind_points(1, P))) < TOL * s
+        assert np.max(np.abs(ctx.rotor_vind_bywake(0, P, True) - ro.vind_points(1, P, True))) < TOL * s
+        assert np.max(np.abs(ctx.rotor_vind(0, P) - ro.vind_points(2, P))) < TOL * s
+        # the flat enumeration of the same records agrees to rounding, and is a different summation (not bitwise)
+        ctx.set_shared_nodes(False)
+        try:
+            flat = ctx.rotor_vind_bywake(0, P)
+        finally:
+            ctx.set_shared_nodes(True)
+        assert np.max(np.abs(flat - got)) < TOL * s and not np.array_equal(flat, got)
+        # one spanwise copy out of step (the transient between shiftwake and dissipate_wake): the whole set goes flat
+        w = ro.waN(0).copy()
+        w[2, 3, 36 + 9] *= 1.5
+        ctx.rotor_put_nwake(0, 0, w)
+        assert ctx.rotor_info(0)["shared_active"] == 0
+        ro.waN(0)[...] = w
+        assert np.max(np.abs(ctx.rotor_vind_bywake(0, P) - ro.vind_points(1, P))) < TOL * s
+    finally:
+        ctx.set_lattice_tuning(0, 0)
+        ctx.rotors_clear()
+
+
 def test_lattice_state_kernels_vs_oracle(ctx, oracle):
     """dissipate (classdef.f90:4364-4393), convect (:1531), AB2/AM2 (main.f90:1032-1034, :1094-1096) on device arrays."""
     import torch

@@ -355,6 +355,66 @@ def test_lattice_kernel_on_the_cpu_strip_plans(oracle, W, T, tailW, ns):
     assert err < 1e-12 * scale, err / scale
 
 
+@pytest.mark.parametrize("W,tailW,ns,nsplit", [(4, 0, 8, 1), (4, 0, 8, 3), (4, 2, 6, 2), (4, 1, 5, 1), (2, 0, 6, 2), (1, 0, 5, 1),
+                                               (3, 0, 6, 1)])
+def test_dual_core_streamwise_edges_on_the_cpu(oracle, W, tailW, ns, nsplit):
+    """A wake shed with a NON-UNIFORM streamwiseCoreVec (classdef.f90:3841: vf(1) of ring (i, j) gets streamwiseCoreVec(j),
+    vf(3) gets streamwiseCoreVec(j+1); rotor_dissipate_wake then copies vf(1)%rVc into vf(3)%rVc, :4371-4372):
+    the two copies of every interior streamwise edge carry different core radii.  check_rings_kernel classifies the set as
+    DUAL (flag 2), pack_rings_shared_kernel writes the dual records, the dual form of bs_lattice_kernel (33-instruction
+    edge: one cross product, two reciprocal square roots) runs and the merged form does not; the result is the reference's
+    ring-by-ring sum at the per-call bar.  Round 1 sent such a set to the flat enumeration whole (2.6x slower)."""
+    case, _ = _case(oracle, 6, ns=ns, wakeTruncateNt=0, nNwake=8)
+    rot, lib = case.rotor(0), emul_lib()
+    d = rot.dims()
+    nrows, i0 = rot.nNwake - d["rowNear"] + 1, d["rowNear"] - 1
+    assert nrows >= 4 and d["rowFar"] > rot.nFwake
+    # what the reference's records look like after shedding with streamwiseCoreVec(j) = base*(1 + 0.3 j) and one dissipation
+    # step: vf(1) and vf(3) of ring (i, j) hold the SAME radius (the left edge's), so ring j's vf(3) differs from ring j+1's vf(1)
+    for ib in range(rot.nb):
+        w = rot.waN(ib)
+        for j in range(ns):
+            w[j, :, 9] *= 1.0 + 0.3 * j
+            w[j, :, 24 + 9] = w[j, :, 9]
+    waN = _stack(rot, "waN")
+    rng = np.random.default_rng(7 * W + ns)
+    nodes = waN[0, :, i0:, 12:15].reshape(-1, 3)
+    mid = 0.5 * (waN[1, :, i0:, 12:15] + waN[1, :, i0:, 0:3]).reshape(-1, 3)       # on the streamwise (dual) edges of blade 2
+    P = np.ascontiguousarray(np.concatenate([rng.uniform(-1.3, 1.3, (250, 3)) * float(np.abs(nodes).max()), nodes, mid]))
+    got = np.zeros_like(P)
+    for ib in range(rot.nb):
+        V = np.empty_like(P)
+        rc = lib.emul_lattice_vind_split(W, {1: 1, 2: 2, 3: 1, 4: 1}[W], tailW, nsplit, np.ascontiguousarray(waN[ib]).ctypes.data,
+                                         rot.nNwake, rot.ns, i0, nrows, P.shape[0], P.ctypes.data, V.ctypes.data)
+        assert rc == -2, rc                                                         # done, by the dual form
+        got = got + V
+    ref = rot.vind_points(1, P, False)
+    assert np.all(np.isfinite(got))
+    scale = 50.0 * float(np.abs(ref).max())
+    err = float(np.max(np.abs(got - ref)))
+    print(f"dual form W={W} tail={tailW} on the CPU: max error {err / scale * 50:.2e} of the velocity scale")
+    assert err < 1e-12 * scale, err / scale
+    # and the merged form on the same records would be WRONG by far more than the bar (the test has teeth)
+    for ib in range(rot.nb):
+        w = rot.waN(ib)
+        w[:, :, 24 + 9] = np.roll(w[:, :, 9], -1, axis=0)                           # make the copies agree: a different wake
+    assert np.max(np.abs(rot.vind_points(1, P, False) - ref)) > 1e-8 * scale
+    # device-side dispatch with every launch made: flag 2 -> the dual slots are the ones summed
+    for ib in range(rot.nb):
+        w = rot.waN(ib)
+        w[:, :, 24 + 9] = w[:, :, 9]
+    if W == 4 and tailW == 0:
+        waN = _stack(rot, "waN")
+        got = np.zeros_like(P)
+        for ib in range(rot.nb):
+            V, flag = np.empty_like(P), C.c_int(-1)
+            assert lib.emul_lattice_vind_dispatch(2, np.ascontiguousarray(waN[ib]).ctypes.data, rot.nNwake, rot.ns, i0, nrows, P.shape[0],
+                                                  P.ctypes.data, V.ctypes.data, C.byref(flag)) == 0
+            assert flag.value == 2
+            got = got + V
+        assert np.all(np.isfinite(got)) and np.max(np.abs(got - ref)) < 1e-12 * scale
+
+
 @pytest.mark.parametrize("W,T,tailW,nsplit,ns", [(1, 1, 0, 1, 8), (1, 3, 0, 2, 8), (1, 3, 0, 4, 8), (2, 2, 0, 3, 8), (4, 2, 0, 1, 8),
                                                  (4, 2, 0, 2, 8), (4, 1, 0, 3, 8), (3, 2, 0, 2, 6), (4, 2, 2, 2, 6)])
 def test_lattice_kernel_on_the_cpu_source_splits_and_tile_ring(oracle, W, T, tailW, nsplit, ns):

@@ -33,8 +33,10 @@ def _usage(res, name):
     return int(m.group(1)), int(m.group(2))
 
 
-@pytest.mark.parametrize("kernel,rings,regs_max", [("bs_lattice_kernelILi4ELi1E", 8, 168), ("bs_lattice_kernelILi4ELi2E", 16, 255),
-                                                   ("bs_lattice_kernelILi2ELi2E", 8, 168), ("bs_lattice_kernelILi1ELi3E", 6, 168)])
+@pytest.mark.parametrize("kernel,rings,regs_max", [("bs_lattice_kernelILi4ELi1ELi128ELi3ELi2ELb0E", 8, 168),
+                                                   ("bs_lattice_kernelILi4ELi2ELi128ELi3ELi2ELb0E", 16, 255),
+                                                   ("bs_lattice_kernelILi2ELi2ELi128ELi3ELi2ELb0E", 8, 168),
+                                                   ("bs_lattice_kernelILi1ELi3ELi128ELi3ELi2ELb0E", 6, 168)])
 def test_lattice_kernel_instruction_budget(sass, kernel, rings, regs_max):
     import sass_fp64_cost as sc
     path, res = sass
@@ -50,6 +52,21 @@ def test_lattice_kernel_instruction_budget(sass, kernel, rings, regs_max):
     assert stack == 0 and regs <= regs_max, (regs, stack)
 
 
+def test_dual_lattice_kernel_instruction_budget(sass):
+    """The dual form (streamwise edges whose two copies carry different core radii): 33 instead of 25 FP64 instructions on
+    the streamwise edge, nodes and spanwise edges unchanged -> (11 (W+1) + 58 W) / W = 71.75 per ring at W = 4 (the flat
+    enumeration such a set used to fall back to: 172)."""
+    import sass_fp64_cost as sc
+    path, res = sass
+    kernel = "bs_lattice_kernelILi4ELi1ELi128ELi3ELi2ELb1E"
+    a = sc.analyse(str(path), kernel)
+    assert a["n_fp64"] == (11 * 5 + 58 * 4) * 2, a["n_fp64"]        # 2 records unrolled, 1 target per thread
+    assert a["other"]["MUFU"] == (5 + 4 + 8) * 2                    # nodes + spanwise + two per streamwise edge
+    assert a["bound"] >= 0.86, a["bound"]
+    regs, stack = _usage(res, kernel)
+    assert stack == 0 and regs <= 168, (regs, stack)
+
+
 def test_flat_kernel_instruction_budget(sass):
     import sass_fp64_cost as sc
     path, res = sass
@@ -63,7 +80,7 @@ def test_flat_kernel_instruction_budget(sass):
 def test_tma_bulk_copy_and_no_local_memory_in_hot_kernels(sass):
     path, res = sass
     text = path.read_text()
-    for kernel in ("bs_lattice_kernelILi4ELi2E", "bs_sweep_kernelILi4E"):
+    for kernel in ("bs_lattice_kernelILi4ELi2ELi128ELi3ELi2ELb0E", "bs_lattice_kernelILi4ELi1ELi128ELi3ELi2ELb1E", "bs_sweep_kernelILi4E"):
         start = text.index(kernel)
         body = text[start:text.index("Function :", start + 10)] if "Function :" in text[start + 10:] else text[start:]
         assert "UBLKCP" in body, kernel                          # cp.async.bulk (1-D TMA) staging of the source tiles

@@ -15,9 +15,9 @@
 // per (target, ring) = 4 reference pair interactions = 18 per pair (the flat kernel needs 43); W = 2..4 bring it
 // to 66.5 / 64.7 / 63.75.
 //
-// Merging needs both copies of an edge to carry the same core radius; pack_lattice_shared_kernel checks this
-// bitwise and raises a device flag otherwise, in which case this kernel returns immediately and the flat kernel
-// runs on the reference enumeration instead (capi.cu: sweep_shared) -- results never depend on the assumption.
+// Merging needs both copies of an edge to carry the same core radius; the pack kernels check this bitwise and raise a
+// device flag otherwise: streamwise copies that differ select the DUAL form of this kernel (below), anything else the
+// flat kernel on the reference enumeration (capi.cu: sweep_shared) -- results never depend on the assumption.
 #pragma once
 #include "vlc_device.cuh"
 
@@ -27,10 +27,23 @@ namespace vlc {
 //   [0 .. 3(W+1))            nodes N_0 .. N_W of this row                     (padded to an even count)
 //   then for k = 0 .. W-1    spanwise edge N_k -> N_{k+1}:  g*(r0)[3], g*|r0|^2, K       (5)
 //                            streamwise edge Nprev_k -> N_k: g*(r0)[3], g*|r0|^2, K      (5)
-// W = 1: 16 doubles (A, B, edge A->B, edge A_prev->A).  Wider strips amortise the node work over more edges:
+//   then for k = 0 .. W-1    4 more doubles, used by the DUAL form only (below)
+// W = 1: 16 + 4 doubles (A, B, edge A->B, edge A_prev->A).  Wider strips amortise the node work over more edges:
 // FP64 instructions per ring = (11 (W+1) + 50 W) / W = 72, 66.5, 64.7, 63.75 for W = 1..4.
+//
+// DUAL form (round-1 review, task 5): the two copies of a shared STREAMWISE edge -- vf(1) of ring (r, j) and vf(3) of
+// ring (r, j-1) -- carry different core radii whenever streamwiseCoreVec is not uniform (the reference keeps both:
+// classdef.f90:3841, and rotor_dissipate_wake's vf(3)%rVc <- vf(1)%rVc, :4371-4372).  Such an edge cannot be
+// merged into one strength, but it still shares its two nodes, its cross product and the end-point term:
+//     v += c * (r0.rU uU - r0.rV uV) * (gA / sqrt(KA + |c|^4) + gB / sqrt(KB + |c|^4))
+// = 33 instead of 25 FP64 instructions (two reciprocal square roots); nodes and spanwise edges are unchanged, so a ring
+// costs (11 (W+1) + 58 W) / W = 71.75 at W = 4 -- against 172 on the flat enumeration the whole set fell back to in
+// round 1.  The streamwise slot then holds r0[3], |r0|^2, gA and the extra four doubles KA, gB, KB, 0 (gB carries the
+// sign of the reversed copy).  Which form a buffer holds is decided ON THE DEVICE by the set's flag (pack.cuh:
+// check_rings_kernel): 0 = merged, 2 = dual, odd = not a lattice / spanwise copies differ -> flat enumeration.
 __host__ __device__ constexpr int lat_nodes_pad(int W) { return (3 * (W + 1) + 1) / 2 * 2; }
-__host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_nodes_pad(W) + 10 * W; }
+__host__ __device__ constexpr int lat_core_doubles(int W) { return lat_nodes_pad(W) + 10 * W; }  // what the merged form reads
+__host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_core_doubles(W) + 4 * W; }  // record stride
 #ifndef VLC_LAT_TILE_DIV
 #define VLC_LAT_TILE_DIV 1
 #endif
@@ -71,16 +84,38 @@ __device__ __forceinline__ void edge_accumulate(const NodeQ& a, const NodeQ& b, 
   vz = fma(cz, sc, vz);
 }
 
-template <int W, int T, int THREADS, int STAGES, int MINB>
+// One (target, streamwise edge U->V) interaction whose two copies carry different core radii: 33 FP64-pipe instructions.
+__device__ __forceinline__ void edge_accumulate_dual(const NodeQ& a, const NodeQ& b, double ex, double ey, double ez, double L2,
+                                                     double gA, double KA, double gB, double KB, double& vx, double& vy,
+                                                     double& vz) {
+  const double cx = fma(a.ry, b.rz, -(a.rz * b.ry));
+  const double cy = fma(a.rz, b.rx, -(a.rx * b.rz));
+  const double cz = fma(a.rx, b.ry, -(a.ry * b.rx));
+  const double c2 = fma(cz, cz, fma(cy, cy, cx * cx));
+  const double a1 = fma(ez, a.rz, fma(ey, a.ry, ex * a.rx));  // r0.rU
+  const double a2 = a1 - L2;                                   // r0.rV
+  const double wA = rsqrt_fp64<false>(fma(c2, c2, KA));
+  const double wB = rsqrt_fp64<false>(fma(c2, c2, KB));
+  const double t = fma(-a2, b.u, a1 * a.u);
+  double sc = t * fma(gB, wB, gA * wA);
+  guard_scale(sc, c2);
+  vx = fma(cx, sc, vx);
+  vy = fma(cy, sc, vy);
+  vz = fma(cz, sc, vz);
+}
+
+// flag dispatch: the kernel runs when (*flag & mask) == want (flag == nullptr: always)
+template <int W, int T, int THREADS, int STAGES, int MINB, bool DUAL = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, padded to a multiple of lat_tile(W)
                   long long chunk,                 // records per split (multiple of the tile)
                   long long n_pad,                 // total padded records
                   const double* __restrict__ P, long long m,
                   double* __restrict__ out,        // [gridDim.y][3 m]
-                  const int* __restrict__ flag, int want) {
-  if (flag != nullptr && *flag != want) return;  // uniform: the set is not mergeable -> the flat kernel does the work
+                  const int* __restrict__ flag, int mask, int want) {
+  if (flag != nullptr && (*flag & mask) != want) return;  // uniform: another form of the set does the work
   constexpr int RD = lat_rec_doubles(W), NP = lat_nodes_pad(W), TILE = lat_tile(W);
+  constexpr int RL = DUAL ? RD : lat_core_doubles(W);  // doubles of a record this form reads
 #if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/kernels_emul.cpp): one emulated thread at a time, which
   // stages its own tiles (VLC_PRODUCER) into a static buffer with memcpy standing in for the bulk copy
   alignas(128) static unsigned char smem_raw[(size_t)STAGES * TILE * RD * 8 + STAGES * 8];
@@ -139,9 +174,9 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
 #pragma unroll 2
     for (int j = 0; j < TILE; ++j) {
       const double2* sb = reinterpret_cast<const double2*>(sbase + (size_t)j * RD);
-      double q[RD];  // the record, in registers (constant indices after unrolling)
+      double q[RL];  // the record, in registers (constant indices after unrolling)
 #pragma unroll
-      for (int i = 0; i < RD / 2; ++i) {
+      for (int i = 0; i < RL / 2; ++i) {
         const double2 v = sb[i];
         q[2 * i] = v.x;
         q[2 * i + 1] = v.y;
@@ -154,7 +189,12 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
         for (int i = 0; i < W; ++i) {
           const NodeQ nxt = node_eval(px[k], py[k], pz[k], q[3 * i + 3], q[3 * i + 4], q[3 * i + 5]);
           const double* e = &q[NP + 10 * i];
-          edge_accumulate(prev[k][i], cur, e[5], e[6], e[7], e[8], e[9], vx[k], vy[k], vz[k]);  // streamwise Nprev_i -> N_i
+          if (DUAL) {  // streamwise Nprev_i -> N_i with the core radii of both copies
+            const double* x = &q[NP + 10 * W + 4 * i];
+            edge_accumulate_dual(prev[k][i], cur, e[5], e[6], e[7], e[8], e[9], x[0], x[1], x[2], vx[k], vy[k], vz[k]);
+          } else {
+            edge_accumulate(prev[k][i], cur, e[5], e[6], e[7], e[8], e[9], vx[k], vy[k], vz[k]);  // streamwise Nprev_i -> N_i
+          }
           edge_accumulate(cur, nxt, e[0], e[1], e[2], e[3], e[4], vx[k], vy[k], vz[k]);         // spanwise   N_i -> N_{i+1}
           prev[k][i] = cur;
           cur = nxt;
@@ -180,14 +220,17 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
   }
 }
 
-// Fixed-order sum of partial slots, selecting the slots of the path that actually ran:
-//   *flag == 0 -> slots [0, na)   (lattice + remainder kernels)      *flag != 0 -> slots [na, na+nb)  (flat fallback)
-__global__ void bs_reduce_select_kernel(const double* __restrict__ part, const int* __restrict__ flag, int na, int nb,
-                                        long long len, double* __restrict__ V) {
+// Fixed-order sum of partial slots, selecting the slots of the form that actually ran.  Slot layout:
+//   [0, na) merged lattice (+ tail strips) | [na, na+nr) flat remainder | [na+nr, na+nr+nd) dual lattice (+ tail strips) |
+//   [na+nr+nd, na+nr+nd+nf) flat fallback
+//   *flag == 0 -> [0, na+nr)     *flag == 2 -> [na, na+nr+nd)     *flag odd -> the last nf slots
+__global__ void bs_reduce_select_kernel(const double* __restrict__ part, const int* __restrict__ flag, int na, int nr, int nd,
+                                        int nf, long long len, double* __restrict__ V) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= len) return;
-  const int first = (*flag == 0) ? 0 : na;
-  const int count = (*flag == 0) ? na : nb;
+  const int f = *flag;
+  const int first = (f & 1) ? na + nr + nd : (f == 2 ? na : 0);
+  const int count = (f & 1) ? nf : (f == 2 ? nr + nd : na + nr);
   double a = 0.0;
   for (int s = 0; s < count; ++s) a += part[(size_t)(first + s) * len + i];
   V[i] = a;

@@ -22,10 +22,10 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
                 const double* __restrict__ P,     // targets (3, m) interleaved
                 long long m,
                 double* __restrict__ out,         // [gridDim.y][3 m]
-                const int* __restrict__ flag,     // optional device flag: run only when *flag == want (capi.cu: sweep_shared)
-                int want)
+                const int* __restrict__ flag,     // optional device flag: run only when (*flag & mask) == want (capi.cu: sweep_shared)
+                int mask, int want)
 {
-  if (flag != nullptr && *flag != want) return;
+  if (flag != nullptr && (*flag & mask) != want) return;
 #if defined(__CUDA_EMUL__)  // host build of the tests (tests/native/kernels_emul.cpp), see bs_lattice.cuh
   alignas(128) static unsigned char smem_raw[(size_t)STAGES * TILE * kSrcBytes + STAGES * 8];
 #else

@@ -64,6 +64,7 @@ struct SourceSet {
   int* d_unmergeable = nullptr;        // device flag raised by the pack kernels
   bool has_shared = false;
   long long n_rings_main = 0;          // vortex rings covered by the strips of `lat` (4 reference filaments each)
+  bool may_dual = false;               // the flag can take the value 2 (records classified by check_rings_kernel: tier 2)
 };
 
 // one dominant-kernel launch of a sweep, for vlc_sweep_stats
@@ -133,6 +134,7 @@ struct vlc_ctx {
   bool ev_valid = false;
   int lat_W = 0, lat_T = 0;          // lattice kernel shape (vlc_set_lattice_tuning), 0 = automatic
   int occ_lat[5][4] = {};            // resident CTAs/SM of the lattice kernel [W][T]
+  int occ_dual[5] = {};              // ... of its dual form [W] (T = 1)
   bool fast = false;  // rsqrt refinement: false = third order (~1e-16), true = second order (~4e-14)
   long long launches = 0;
   SourceSet sets[VLC_MAX_SETS];
@@ -289,10 +291,10 @@ constexpr size_t kSweepSmem = (size_t)kStages * kTile * vlc::kSrcBytes + kStages
 
 template <int T, int MINB, bool FAST>
 int launch_sweep_T(vlc_ctx* c, const double* src, long long n_pad, long long chunk, int nsplit, long long m,
-                   const double* dP, double* out, const int* flag, int want) {
+                   const double* dP, double* out, const int* flag, int mask, int want) {
   auto kern = vlc::bs_sweep_kernel<T, kThreads, kTile, kStages, MINB, FAST>;
   dim3 grid(blocks_for(m, kThreads * T), (unsigned)nsplit, 1);
-  kern<<<grid, kThreads, kSweepSmem, c->stream>>>(src, chunk, n_pad, dP, m, out, flag, want);
+  kern<<<grid, kThreads, kSweepSmem, c->stream>>>(src, chunk, n_pad, dP, m, out, flag, mask, want);
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   return VLC_OK;
@@ -365,13 +367,13 @@ FlatPlan plan_flat(const vlc_ctx* c, long long m, long long n_pad) {
   return p;
 }
 
-// out: [plan.nsplit][3 m] partial slots.  flag/want: optional device-side dispatch (see sweep_shared).
+// out: [plan.nsplit][3 m] partial slots.  flag/mask/want: optional device-side dispatch (see sweep_shared).
 int launch_flat(vlc_ctx* c, const double* src, long long n_pad, const FlatPlan& p, long long m, const double* dP,
-                double* out, const int* flag, int want) {
+                double* out, const int* flag, int mask, int want) {
   int rc;
-#define VLC_SWEEP(TT, MB)                                                                                    \
-  rc = c->fast ? launch_sweep_T<TT, MB, true>(c, src, n_pad, p.chunk, p.nsplit, m, dP, out, flag, want)      \
-               : launch_sweep_T<TT, MB, false>(c, src, n_pad, p.chunk, p.nsplit, m, dP, out, flag, want)
+#define VLC_SWEEP(TT, MB)                                                                                         \
+  rc = c->fast ? launch_sweep_T<TT, MB, true>(c, src, n_pad, p.chunk, p.nsplit, m, dP, out, flag, mask, want)      \
+               : launch_sweep_T<TT, MB, false>(c, src, n_pad, p.chunk, p.nsplit, m, dP, out, flag, mask, want)
   switch (p.T) {
     case 1: VLC_SWEEP(1, 5); break;
     case 2: VLC_SWEEP(2, 4); break;
@@ -397,7 +399,7 @@ int sweep(vlc_ctx* c, const double* src, long long n_pad, long long m, const dou
   }
   cudaEventRecord(c->ev[0], c->stream);
   SweepStat* st = stat_begin(c);
-  int rc = launch_flat(c, src, n_pad, p, m, dP, out, nullptr, 0);
+  int rc = launch_flat(c, src, n_pad, p, m, dP, out, nullptr, 0, 0);
   if (rc) return rc;
   stat_end(c, st, 1, (double)m * (double)n_pad, (double)m * (double)n_pad * (c->fast ? 41.0 : 43.0));
   cudaEventRecord(c->ev[1], c->stream);
@@ -461,6 +463,8 @@ inline long long pad_lat(long long n, int W) { return (n + lat_tile_of(W) - 1) /
 #ifndef VLC_LAT_MINB42
 #define VLC_LAT_MINB42 2
 #endif
+// the dual form (streamwise edges with two core radii, bs_lattice.cuh): one target per thread
+#define VLC_DUAL_SHAPES(X) X(1, 5) X(2, 3) X(3, 3) X(4, 2)
 #define VLC_LAT_SHAPES(X) X(1, 1, 6) X(1, 2, 4) X(1, 3, 2) X(2, 1, 4) X(2, 2, 2) X(2, 3, 2) X(3, 1, 3) X(3, 2, 2) X(4, 1, VLC_LAT_MINB41) X(4, 2, VLC_LAT_MINB42)
 
 int query_occ_lat_all(vlc_ctx* c) {
@@ -471,6 +475,14 @@ int query_occ_lat_all(vlc_ctx* c) {
     CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lat[WW][TT], kern, kLatThreads, lat_smem_of(WW))); \
   }
   VLC_LAT_SHAPES(X)
+#undef X
+#define X(WW, MB)                                                                                                \
+  {                                                                                                              \
+    auto kern = vlc::bs_lattice_kernel<WW, 1, kLatThreads, kStages, MB, true>;                                     \
+    CUDA_OK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lat_smem_of(WW)));   \
+    CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_dual[WW], kern, kLatThreads, lat_smem_of(WW))); \
+  }
+  VLC_DUAL_SHAPES(X)
 #undef X
   return VLC_OK;
 }
@@ -483,11 +495,12 @@ bool lat_shape_exists(int W, int T) {
 }
 
 // Source splits of the lattice kernel: whole waves of (SMs x resident CTAs), chunks of >= 4 tiles when possible.
-int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad) {
+int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad, bool dual = false) {
   if (c->tune_nsplit > 0) return c->tune_nsplit;
   const long long tiles = n_lat_pad / lat_tile_of(W);
   const long long ttiles = (m + (long long)kLatThreads * T - 1) / ((long long)kLatThreads * T);
-  const long long slots = (long long)c->sm_count * (c->occ_lat[W][T] > 0 ? c->occ_lat[W][T] : 2);
+  const int occ = dual ? c->occ_dual[W] : c->occ_lat[W][T];
+  const long long slots = (long long)c->sm_count * (occ > 0 ? occ : 2);
   long long max_split = tiles / 4;
   if (max_split < 1) max_split = 1;
   if (max_split > 256) max_split = 256;
@@ -508,94 +521,101 @@ int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_
   return best_s;
 }
 
-// Sweep over a set that also holds the shared-node form.  Three launches, dispatched ON THE DEVICE by the set's
-// mergeability flag so that no host synchronisation is needed: lattice strips + flat remainder run when the flag
-// is 0, the flat kernel over the reference enumeration runs when it is 1; bs_reduce_select_kernel sums the slots
-// of whichever path ran, in fixed order.
+// Sweep over a set that also holds the shared-node form.  The launches are dispatched ON THE DEVICE by the set's flag so
+// that no host synchronisation is needed: 0 = merged strips + flat remainder; 2 = DUAL strips (streamwise edges whose two
+// copies carry different core radii, bs_lattice.cuh) + the same flat remainder; odd = the flat kernel over the reference
+// enumeration.  bs_reduce_select_kernel sums the slots of whichever form ran, in fixed order.
 int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, double* dV) {
   if (m <= 0) return VLC_OK;
-  const int LW = s.lat_W;
-  const long long lat_tiles = s.n_lat_pad / lat_tile_of(LW);
-  int LT = (c->lat_T >= 1 && c->lat_T <= 3) ? c->lat_T : kLatBestT[LW];
-  if (m <= kLatThreads) LT = 1;
-  while (LT > 1 && !lat_shape_exists(LW, LT)) --LT;
-  int ns_l = plan_lattice_split(c, LW, LT, m, s.n_lat_pad);
-  const long long lat_chunk_tiles = (lat_tiles + ns_l - 1) / ns_l;
-  ns_l = (int)((lat_tiles + lat_chunk_tiles - 1) / lat_chunk_tiles);
+  struct LatPlan {
+    int W = 0, T = 1, ns = 0;
+    long long chunk = 0;
+  };
+  auto plan = [&](int W, long long n_pad, bool dual) {
+    LatPlan p;
+    if (n_pad <= 0 || W < 1) return p;
+    p.W = W;
+    p.T = dual ? 1 : ((c->lat_T >= 1 && c->lat_T <= 3) ? c->lat_T : kLatBestT[W]);
+    if (m <= kLatThreads) p.T = 1;
+    while (p.T > 1 && !lat_shape_exists(W, p.T)) --p.T;
+    const long long tiles = n_pad / lat_tile_of(W);
+    p.ns = plan_lattice_split(c, W, p.T, m, n_pad, dual);
+    const long long chunk_tiles = (tiles + p.ns - 1) / p.ns;
+    p.ns = (int)((tiles + chunk_tiles - 1) / chunk_tiles);
+    p.chunk = chunk_tiles * lat_tile_of(W);
+    return p;
+  };
+  const bool dual = s.may_dual;
+  const LatPlan pm = plan(s.lat_W, s.n_lat_pad, false), pm2 = plan(s.lat2_W, s.n_lat2_pad, false);  // merged: main + tail strips
+  const LatPlan pd = dual ? plan(s.lat_W, s.n_lat_pad, true) : LatPlan(), pd2 = dual ? plan(s.lat2_W, s.n_lat2_pad, true) : LatPlan();
   const FlatPlan pr = s.n_rem_pad > 0 ? plan_flat(c, m, s.n_rem_pad) : FlatPlan();
   const FlatPlan pf = plan_flat(c, m, s.n_pad);
   const int ns_r = s.n_rem_pad > 0 ? pr.nsplit : 0;
-  // tail strips of another width (plan_strips): a second, small lattice launch with its own split
-  const int LW2 = s.n_lat2_pad > 0 ? s.lat2_W : 0;
-  int LT2 = LW2 ? kLatBestT[LW2] : 1, ns_l2 = 0;
-  long long lat2_chunk_tiles = 0;
-  if (LW2) {
-    if (m <= kLatThreads) LT2 = 1;
-    while (LT2 > 1 && !lat_shape_exists(LW2, LT2)) --LT2;
-    const long long tiles2 = s.n_lat2_pad / lat_tile_of(LW2);
-    ns_l2 = plan_lattice_split(c, LW2, LT2, m, s.n_lat2_pad);
-    lat2_chunk_tiles = (tiles2 + ns_l2 - 1) / ns_l2;
-    ns_l2 = (int)((tiles2 + lat2_chunk_tiles - 1) / lat2_chunk_tiles);
-  }
+  const int na = pm.ns + pm2.ns, nd = pd.ns + pd2.ns;
   const size_t len = 3 * (size_t)m;
-  int rc = reserve(c, c->part, (size_t)(ns_l + ns_l2 + ns_r + pf.nsplit) * len);
+  int rc = reserve(c, c->part, (size_t)(na + ns_r + nd + pf.nsplit) * len);
   if (rc) return rc;
   double* part = c->part.p;
+  double* part_rem = part + (size_t)na * len;
+  double* part_dual = part_rem + (size_t)ns_r * len;
+  double* part_flat = part_dual + (size_t)nd * len;
+  auto launch_lat = [&](const LatPlan& p, bool dual_form, const double* rec, long long n_pad, double* out) -> int {
+    if (p.ns <= 0) return VLC_OK;
+    dim3 grid(blocks_for(m, kLatThreads * p.T), (unsigned)p.ns, 1);
+    if (!dual_form) {
+#define X(WW, TT, MB)                                                                                            \
+  if (p.W == WW && p.T == TT)                                                                                    \
+    vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>( \
+        rec, p.chunk, n_pad, dP, m, out, s.d_unmergeable, 3, 0);
+      VLC_LAT_SHAPES(X)
+#undef X
+    } else {
+#define X(WW, MB)                                                                                                     \
+  if (p.W == WW)                                                                                                      \
+    vlc::bs_lattice_kernel<WW, 1, kLatThreads, kStages, MB, true><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>( \
+        rec, p.chunk, n_pad, dP, m, out, s.d_unmergeable, 3, 2);
+      VLC_DUAL_SHAPES(X)
+#undef X
+    }
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+    return VLC_OK;
+  };
   const bool side = (c->aux != nullptr);
   if (side) CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));  // inputs (records, targets, partial buffer) are ready here
   cudaEventRecord(c->ev[0], c->stream);
   SweepStat* st = stat_begin(c);
-  {
-    dim3 grid(blocks_for(m, kLatThreads * LT), (unsigned)ns_l, 1);
-    const long long lat_chunk = lat_chunk_tiles * lat_tile_of(LW);
-#define X(WW, TT, MB)                                                                                              \
-  if (LW == WW && LT == TT)                                                                                        \
-    vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>(          \
-        s.lat.p, lat_chunk, s.n_lat_pad, dP, m, part, s.d_unmergeable, 0);
-    VLC_LAT_SHAPES(X)
-#undef X
-    CUDA_OK(c, cudaGetLastError());
-    c->launches++;
-  }
-  // reference pairs = 4 filaments per ring; issued FP64 instructions = (11 (W+1) + 50 W) per (target, strip record)
-  stat_end(c, st, 0, (double)m * 4.0 * (double)s.n_rings_main, (double)m * (double)s.n_lat_pad * (11.0 * (LW + 1) + 50.0 * LW));
+  if ((rc = launch_lat(pm, false, s.lat.p, s.n_lat_pad, part))) return rc;
+  if ((rc = launch_lat(pd, true, s.lat.p, s.n_lat_pad, part_dual))) return rc;  // exits at once unless the flag is 2
+  // reference pairs = 4 filaments per ring; issued FP64 instructions = (11 (W+1) + 50 W) per (target, strip record) of
+  // the merged form (the host does not know which form ran: a dual set issues 58 W)
+  stat_end(c, st, 0, (double)m * 4.0 * (double)s.n_rings_main,
+           (double)m * (double)s.n_lat_pad * (11.0 * (pm.W + 1) + 50.0 * pm.W));
   cudaEventRecord(c->ev[1], c->stream);
-  // The flat remainder (and the fallback, which exits at once when the set is mergeable) go to a low-priority side
-  // stream launched AFTER the lattice kernel: their CTAs fill the SMs that the lattice kernel's last wave leaves idle.
+  // Tail strips, the flat remainder and the fallback (which exits at once unless the flag is odd) go to a low-priority
+  // side stream launched AFTER the lattice kernel: their CTAs fill the SMs that the lattice kernel's last wave leaves idle.
   cudaStream_t main_stream = c->stream;
   if (side) {
     CUDA_OK(c, cudaStreamWaitEvent(c->aux, c->ev_fork, 0));  // ev_fork was recorded BEFORE the lattice kernel
     c->stream = c->aux;
   }
-  if (LW2) {
-    dim3 grid(blocks_for(m, kLatThreads * LT2), (unsigned)ns_l2, 1);
-    const long long chunk2 = lat2_chunk_tiles * lat_tile_of(LW2);
-#define X(WW, TT, MB)                                                                                       \
-  if (LW2 == WW && LT2 == TT)                                                                               \
-    vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>( \
-        s.lat2.p, chunk2, s.n_lat2_pad, dP, m, part + (size_t)ns_l * len, s.d_unmergeable, 0);
-    VLC_LAT_SHAPES(X)
-#undef X
-    CUDA_OK(c, cudaGetLastError());
-    c->launches++;
-  }
-  if (ns_r > 0)
-    rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part + (size_t)(ns_l + ns_l2) * len, s.d_unmergeable, 0);
-  if (!rc)
-    rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part + (size_t)(ns_l + ns_l2 + ns_r) * len, s.d_unmergeable, 1);
-  c->stream = main_stream;
+  rc = launch_lat(pm2, false, s.lat2.p, s.n_lat2_pad, part + (size_t)pm.ns * len);
+  if (!rc) rc = launch_lat(pd2, true, s.lat2.p, s.n_lat2_pad, part_dual + (size_t)pd.ns * len);
+  if (!rc && ns_r > 0) rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part_rem, s.d_unmergeable, 1, 0);
+  if (!rc) rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part_flat, s.d_unmergeable, 1, 1);
+  c->stream = main_stream;  // restored before any early return below
   if (rc) return rc;
   if (side) {
     CUDA_OK(c, cudaEventRecord(c->ev_join, c->aux));
     CUDA_OK(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));
   }
-  vlc::bs_reduce_select_kernel<<<blocks_for((long long)len, 256), 256, 0, c->stream>>>(
-      part, s.d_unmergeable, ns_l + ns_l2 + ns_r, pf.nsplit, (long long)len, dV);
+  vlc::bs_reduce_select_kernel<<<blocks_for((long long)len, 256), 256, 0, c->stream>>>(part, s.d_unmergeable, na, ns_r, nd,
+                                                                                      pf.nsplit, (long long)len, dV);
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   cudaEventRecord(c->ev[2], c->stream);
   {  // the sweep's other kernels: tail strips (lattice form) and the flat remainder
-    const double in2 = LW2 ? (double)m * (double)s.n_lat2_pad * (11.0 * (LW2 + 1) + 50.0 * LW2) : 0.0;
+    const double in2 = pm2.ns ? (double)m * (double)s.n_lat2_pad * (11.0 * (pm2.W + 1) + 50.0 * pm2.W) : 0.0;
     const double inr = (double)m * (double)s.n_rem_pad * (c->fast ? 41.0 : 43.0);
     stat_close(c, st, (double)m * (double)s.n_pad - (double)m * 4.0 * (double)s.n_rings_main, in2 + inr);
   }
@@ -859,6 +879,7 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     cs.n_lat = lat_n;
     cs.n_lat_pad = lat_pad;
     cs.n_rings_main = (long long)r.nb * nrows * std::min(r.ns, nstrips * LW);
+    cs.may_dual = true;
     cs.n_lat2 = lat2_n;
     cs.n_lat2_pad = lat2_pad;
     cs.lat2_W = TW;
@@ -941,11 +962,13 @@ int pack_chord(vlc_ctx* c, Rotor& r) {
   return VLC_OK;
 }
 
-// out = OR of up to 64 device flags
+// Form of a set made of several rotors' records laid side by side: the rotors' common form when they agree, the flat
+// enumeration (1) when one of them needs it or when they disagree (merged and dual records cannot share a launch).
 __global__ void or_flags_kernel(int n, const int* const* __restrict__ flags, int* __restrict__ out) {
-  int f = 0;
-  for (int k = 0; k < n; ++k) f |= *flags[k];
-  *out = f;
+  int f = *flags[0];
+  for (int k = 1; k < n; ++k)
+    if (*flags[k] != f) f = 1;
+  *out = (f & 1) ? 1 : f;
 }
 
 // The wake sweep sums over ALL source rotors (main.f90:817-826: vel = vel + vind_on?wake_byRotor(rotor(jr), ...)).  One
@@ -1045,6 +1068,7 @@ int build_ws_combined(vlc_ctx* c, int s, bool* ok) {
   w.n_rem = rem_n;
   w.n_rem_pad = any_shared ? rem_pad : 0;
   w.n_rings_main = rings;
+  w.may_dual = any_shared;
   *ok = true;
   return VLC_OK;
 }
@@ -2906,6 +2930,7 @@ extern "C" int vlc_pack_lattice_dev(vlc_ctx* c, int set, int append, int nrows, 
   // ---- shared-node form of the same lattice: strip records + flat remainder (bs_lattice.cuh) ----
   if (!append) {
     s.n_rings_main = 0;
+    s.may_dual = false;
     s.n_lat = s.n_rem = s.n_lat2 = s.n_lat2_pad = 0;
     s.has_shared = true;
     s.lat_W = auto_strip_width(c, ns);  // lattices appended later share the record width of the first one
@@ -3024,7 +3049,7 @@ extern "C" int vlc_set_info(vlc_ctx* c, int set, int64_t* out) {
     int f = 0;
     CUDA_OK(c, cudaMemcpyAsync(&f, s.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    out[3] = (f == 0 && c->shared_nodes) ? 1 : 0;
+    out[3] = !c->shared_nodes ? 0 : (f == 0 ? 1 : (f == 2 && s.may_dual ? 2 : 0));
   }
   return VLC_OK;
 }
@@ -3049,7 +3074,7 @@ extern "C" int vlc_rotor_info(vlc_ctx* c, int ir, int predicted, int64_t* out) {
     int f = 0;
     CUDA_OK(c, cudaMemcpyAsync(&f, cs.d_unmergeable, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    out[3] = (f == 0 && c->shared_nodes) ? 1 : 0;
+    out[3] = !c->shared_nodes ? 0 : (f == 0 ? 1 : (f == 2 ? 2 : 0));
   }
   return VLC_OK;
 }

@@ -193,9 +193,15 @@ __global__ void pack_chain_kernel(int nfar, const double* __restrict__ p, const 
 //   spanwise   (rr,c)->(rr,c+1): Gamma'(rr-1,c) - Gamma'(rr,c)     [f2 of ring (rr-1,c), reversed f4 of ring (rr,c)]
 //   streamwise (rr-1,c)->(rr,c): Gamma'(rr-1,c) - Gamma'(rr-1,c-1) [f1 of ring (rr-1,c), reversed f3 of ring (rr-1,c-1)]
 // The streamwise edges of the LAST node column (c = ns) are left to the flat remainder (pack_lastcol / fil_mask 0x4).
-// *unmergeable is raised when the two copies of a shared edge carry different core radii (possible with a
-// non-uniform streamwiseCoreVec): the sweep then uses the flat records instead.
+// Core radii: the two copies of a shared edge may differ (non-uniform streamwiseCoreVec).  `fmt` says what to
+// do about it:
+//   kFmtDetect (tier 3, node-indexed lattices): write the merged form and raise *flag (bit 0) on ANY difference -- the
+//              sweep then uses the flat records instead;
+//   kFmtMerged / kFmtDual (tier 2, after check_rings_kernel has classified the set): write that form, never touch the flag.
+//              Dual: the streamwise slot holds r0[3], |r0|^2, gA and the record's extra doubles KA, gB, KB (bs_lattice.cuh).
 // Acc supplies node(rr, c, out[3]), gam(r, j) (raw circulation) and rvc(r, j, f).
+constexpr int kFmtDetect = -1, kFmtMerged = 0, kFmtDual = 2;
+
 __device__ __forceinline__ void write_edge(double* __restrict__ e, const double* U, const double* V, double g, double rvc) {
   const double x = V[0] - U[0], y = V[1] - U[1], z = V[2] - U[2];
   const double L = fma(z, z, fma(y, y, x * x));
@@ -206,10 +212,26 @@ __device__ __forceinline__ void write_edge(double* __restrict__ e, const double*
   e[3] = g * L;
   e[4] = q * q;
 }
+// the dual form of a streamwise edge: e[0..4] = r0, |r0|^2, gA; x[0..3] = KA, gB, KB, 0
+__device__ __forceinline__ void write_edge_dual(double* __restrict__ e, double* __restrict__ x, const double* U, const double* V,
+                                                double gA, double rvcA, double gB, double rvcB) {
+  const double rx = V[0] - U[0], ry = V[1] - U[1], rz = V[2] - U[2];
+  const double L = fma(rz, rz, fma(ry, ry, rx * rx));
+  const double qA = rvcA * rvcA * L, qB = rvcB * rvcB * L;
+  e[0] = rx;
+  e[1] = ry;
+  e[2] = rz;
+  e[3] = L;
+  e[4] = gA;
+  x[0] = qA * qA;
+  x[1] = gB;
+  x[2] = qB * qB;
+  x[3] = 0.0;
+}
 
 template <int W, class Acc>
 __device__ __forceinline__ void fill_strip_record(const Acc& acc, int nrows, int ns, int c0, int rr,
-                                                  double* __restrict__ rec, int* __restrict__ unmergeable) {
+                                                  double* __restrict__ rec, int* __restrict__ unmergeable, int fmt) {
   constexpr int NP = (3 * (W + 1) + 1) / 2 * 2;  // c0 = first ring column of the strip (global column index)
   auto G = [&](int r, int j) -> double {
     return (r >= 0 && r < nrows && j >= 0 && j < ns) ? strength(acc.gam(r, j), true) : 0.0;
@@ -245,33 +267,45 @@ __device__ __forceinline__ void fill_strip_record(const Acc& acc, int nrows, int
   for (int k = 0; k < W; ++k) {
     const int c = c0 + k;
     double* e = rec + NP + 10 * k;
+    double* x = rec + NP + 10 * W + 4 * k;
     // spanwise edge (rr, c) -> (rr, c+1), real when c + 1 <= ns
     double gp = 0.0, rvcp = 0.0;
     if (c + 1 <= ns) {
       gp = G(rr - 1, c) - G(rr, c);
       if (rr >= 1) {
         rvcp = acc.rvc(rr - 1, c, 1);
-        if (rr < nrows && acc.rvc(rr, c, 3) != rvcp) *unmergeable = 1;
+        if (fmt == kFmtDetect && rr < nrows && acc.rvc(rr, c, 3) != rvcp) *unmergeable = 1;
       } else {
         rvcp = acc.rvc(0, c, 3);
       }
     }
     write_edge(e, N[k], N[k + 1], gp, rvcp);
-    // streamwise edge (rr-1, c) -> (rr, c), real when rr >= 1 and c <= ns - 1
-    double gs = 0.0, rvcs = 0.0;
+    // streamwise edge (rr-1, c) -> (rr, c), real when rr >= 1 and c <= ns - 1: vf(1) of ring (rr-1, c) and the reversed
+    // vf(3) of ring (rr-1, c-1)
+    double gA = 0.0, gB = 0.0, rvcA = 0.0, rvcB = 0.0;
     if (rr >= 1 && c <= ns - 1) {
-      gs = G(rr - 1, c) - G(rr - 1, c - 1);
-      rvcs = acc.rvc(rr - 1, c, 0);
-      if (c >= 1 && acc.rvc(rr - 1, c - 1, 2) != rvcs) *unmergeable = 1;
+      gA = G(rr - 1, c);
+      rvcA = acc.rvc(rr - 1, c, 0);
+      rvcB = rvcA;
+      if (c >= 1) {
+        gB = -G(rr - 1, c - 1);
+        rvcB = acc.rvc(rr - 1, c - 1, 2);
+        if (fmt == kFmtDetect && rvcB != rvcA) *unmergeable = 1;
+      }
     }
-    write_edge(e + 5, Np[k], N[k], gs, rvcs);
+    if (fmt == kFmtDual) {
+      write_edge_dual(e + 5, x, Np[k], N[k], gA, rvcA, gB, rvcB);
+    } else {
+      write_edge(e + 5, Np[k], N[k], gA + gB, rvcA);  // = Gamma'(rr-1, c) - Gamma'(rr-1, c-1)
+      x[0] = x[1] = x[2] = x[3] = 0.0;
+    }
   }
 }
 
 // null strip records (padding): distinct finite nodes, zero strengths
 template <int W>
 __global__ void pack_null_lat_kernel(long long count, double* __restrict__ rec) {
-  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2, RD = NP + 10 * W;
+  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2, RD = NP + 14 * W;  // = lat_rec_doubles(W); zero strengths in both forms
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   double* r = rec + i * RD;
@@ -299,12 +333,12 @@ template <int W>
 __global__ void pack_lattice_shared_kernel(int nrows, int ns, const double* __restrict__ nodes,
                                            const double* __restrict__ gam, const double* __restrict__ rvc4,
                                            double* __restrict__ rec, int* __restrict__ unmergeable) {
-  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 10 * W;
+  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 14 * W;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nr1 = nrows + 1, nstrips = (ns + W - 1) / W;
   if (q >= (long long)nstrips * nr1) return;
   const LatticeAcc acc{nodes, gam, rvc4, nrows, ns};
-  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable);
+  fill_strip_record<W>(acc, nrows, ns, (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable, kFmtDetect);
 }
 
 // Streamwise edges of the last column (f3 of ring (r, ns-1): corner 3 -> corner 4), which no strip covers.
@@ -359,7 +393,13 @@ __global__ void check_rings_kernel(const double* __restrict__ base, int stride, 
     const double* lf = ring_ptr(base, stride, ld, i0, r, j - 1);
     ok = ok && same3(g, lf + kVf * 3) && same3(g + kVf * 1, lf + kVf * 2);  // corner 1 == left.corner4, corner 2 == left.corner3
   }
-  if (!ok) *unmergeable = 1;
+  if (!ok) atomicOr(unmergeable, 1);
+  // core radii of the two copies of the shared edges (bitwise): spanwise copies that differ -- vf(4) of this ring against
+  // vf(2) of the ring upstream; only transiently, between shiftwake and the next dissipate_wake (classdef.f90:4386-4392) --
+  // send the set to the flat enumeration (bit 0); streamwise copies that differ -- vf(1) of this ring against vf(3) of its
+  // left neighbour: every interior edge of a wake shed with a non-uniform streamwiseCoreVec -- select the dual form (bit 1)
+  if (r >= 1 && g[kVf * 3 + kVfRvc] != ring_ptr(base, stride, ld, i0, r - 1, j)[kVf * 1 + kVfRvc]) atomicOr(unmergeable, 1);
+  if (j >= 1 && g[kVfRvc] != ring_ptr(base, stride, ld, i0, r, j - 1)[kVf * 2 + kVfRvc]) atomicOr(unmergeable, 2);
 }
 
 // tier 2: reference records (vr_class) of one blade's near wake
@@ -388,14 +428,17 @@ template <int W>
 __global__ void pack_rings_shared_kernel(const double* __restrict__ base, int stride, int ld, int i0, int nrows,
                                          int ns, int col_base, int nstrips, double* __restrict__ rec,
                                          int* __restrict__ unmergeable, long long src_blade = 0) {
-  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 10 * W;
+  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 14 * W;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nr1 = nrows + 1;
   if (q >= (long long)nstrips * nr1) return;
   base += (size_t)blockIdx.y * src_blade;          // blade blockIdx.y: its records follow the previous blade's
   rec += (size_t)blockIdx.y * nstrips * nr1 * RD;
   const RingsAcc acc{base, stride, ld, i0, nrows, ns};
-  fill_strip_record<W>(acc, nrows, ns, col_base + (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable);
+  // the form check_rings_kernel chose for the whole set (launched before this kernel on the same stream); a set that goes
+  // to the flat enumeration (odd flag) gets merged-form records nobody reads
+  const int fmt = (*unmergeable == kFmtDual) ? kFmtDual : kFmtMerged;
+  fill_strip_record<W>(acc, nrows, ns, col_base + (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable, fmt);
 }
 
 
