@@ -155,6 +155,10 @@ struct vlc_ctx {
   int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
   // multi-GPU data plane (group.hpp): this context's place in the target partition, its NCCL communicator (library-owned),
   // and -- for the members of an in-process group made by vlc_create_multi -- the group
+  static constexpr size_t kStageBytes = (size_t)1 << 20;
+  void* stage_h[2] = {nullptr, nullptr};  // pinned staging of small uploads (upload())
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  int stage_next = 0;
   bool stats_on = false;         // vlc_sweep_stats: per-launch events of the dominant kernels
   std::vector<SweepStat> stats;
   size_t stats_n = 0;
@@ -434,12 +438,15 @@ inline int auto_strip_width(const vlc_ctx* c, int ns) {
 struct StripPlan {
   int W = 1, tailW = 0, nmain = 0;  // nmain strips of width W, then (tailW > 0) one strip of width tailW
 };
-inline StripPlan plan_strips(const vlc_ctx* c, int ns) {
+inline StripPlan plan_strips(const vlc_ctx* c, int ns, long long rings_max = -1) {
   StripPlan p;
   p.W = auto_strip_width(c, ns);
   p.nmain = (ns + p.W - 1) / p.W;
   if (c->lat_W >= 1 && c->lat_W <= 4) return p;
   const int t = ns % 4;
+  // a tail strip is two more launches per sweep (merged + dual form): not worth it while the whole wake is small enough
+  // for a sweep to be launch-bound (< ~2e4 rings: a few hundred microseconds)
+  if (rings_max >= 0 && rings_max < 20000) return p;
   if (ns > 4 && t != 0) {
     const double single = kLatCost[p.W] * (double)(p.nmain * p.W) / (double)ns;
     const double mixed = (kLatCost[4] * (double)(ns - t) + kLatCost[t] * (double)t) / (double)ns + 0.005;
@@ -701,7 +708,93 @@ Rotor* get_rotor(vlc_ctx* c, int ir) {
   return &c->rotors[ir];
 }
 
-// (Re)build the packed [wing | wake] set of a rotor in the reference's enumeration order.
+// Builder of the segment table of pack_table_kernel (pack.cuh): every segment of a packed set in ONE launch.
+struct PackBuilder {
+  vlc::PackTable t;
+  long long total = 0;
+  PackBuilder() {
+    t.n = 0;
+    t.start[0] = 0;
+  }
+  vlc::PackSeg& add(int kind, long long count, int nb) {
+    vlc::PackSeg& g = t.seg[t.n];
+    std::memset(&g, 0, sizeof g);
+    g.kind = kind;
+    g.count = count;
+    g.nb = nb;
+    g.W = 4;
+    total += count * nb;
+    t.start[++t.n] = total;
+    return g;
+  }
+  bool full() const { return t.n >= vlc::kPackSegs - 1; }
+  // ring filaments: rings (i0 .. i0+ni-1, 0 .. nj-1) of `base`, the filaments of `mask`, per blade
+  void rings(const double* base, int stride, int ld, int i0, int ni, int nj, int mask, int nfil, double sign, int wake, double* dst,
+             int nb, long long src_blade, long long dst_blade) {
+    if ((long long)ni * nj * nfil <= 0) return;
+    vlc::PackSeg& g = add(0, (long long)ni * nj * nfil, nb);
+    g.src = base;
+    g.dst = dst;
+    g.src_blade = src_blade;
+    g.dst_blade = dst_blade;
+    g.stride = stride;
+    g.ld = ld;
+    g.i0 = i0;
+    g.ni = ni;
+    g.mask = mask;
+    g.nfil = nfil;
+    g.sign = sign;
+    g.wake = wake;
+  }
+  void fwake(const double* base, int i0, int ni, double* dst, int nb, long long src_blade, long long dst_blade) {
+    if (ni <= 0) return;
+    vlc::PackSeg& g = add(1, ni, nb);
+    g.src = base;
+    g.dst = dst;
+    g.src_blade = src_blade;
+    g.dst_blade = dst_blade;
+    g.i0 = i0;
+  }
+  void nulls(double* dst, long long count) {
+    if (count <= 0) return;
+    vlc::PackSeg& g = add(2, count, 1);
+    g.dst = dst;
+  }
+  void strips(int W, const double* base, int stride, int ld, int i0, int nrows, int ns, int col_base, int nstrips, double* dst, int* flag,
+              int nb, long long src_blade) {
+    vlc::PackSeg& g = add(3, (long long)nstrips * (nrows + 1), nb);
+    g.W = W;
+    g.src = base;
+    g.dst = dst;
+    g.src_blade = src_blade;
+    g.stride = stride;
+    g.ld = ld;
+    g.i0 = i0;
+    g.nrows = nrows;
+    g.ns = ns;
+    g.col_base = col_base;
+    g.nstrips = nstrips;
+    g.flag = flag;
+  }
+  void null_strips(int W, double* dst, long long count) {
+    if (count <= 0) return;
+    vlc::PackSeg& g = add(4, count, 1);
+    g.W = W;
+    g.dst = dst;
+  }
+  int launch(vlc_ctx* c) {
+    if (total <= 0) return VLC_OK;
+    vlc::pack_table_kernel<<<blocks_for(total, 128), 128, 0, c->stream>>>(t);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+    return VLC_OK;
+  }
+};
+
+// (Re)build the packed [wing | wake] set of a rotor in the reference's enumeration order -- and, for a near wake, its
+// shared-node form: strip records per blade + the flat remainder [wing | last column, horseshoe corrections, far wakes].
+// Three launches whatever the rotor looks like: clear the flag, classify the records (check_rings_kernel), pack every
+// segment (pack_table_kernel).
 int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   if (!r.dirty[s]) return VLC_OK;
   for (int ib = 0; ib < r.nb; ++ib)
@@ -717,63 +810,50 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   long long wake_per_blade = 4LL * nrows * r.ns;
   if (has_far) wake_per_blade += r.ns + nfar + (r.have_pf[s] ? VLC_NPFWAKE : 0);
   const long long wake_n = wake_per_blade * r.nb;
-  const long long total_pad = wing_pad + pad_tile(wake_n);
+  const long long wake_pad = pad_tile(wake_n);
+  const long long total_pad = wing_pad + wake_pad;
   int rc = reserve(c, r.comb[s].rec, (size_t)total_pad * vlc::kSrcDoubles);
   if (rc) return rc;
   double* rec = r.comb[s].rec.p;
   cudaStream_t st = c->stream;
-  // one launch per kernel type for ALL blades (blockIdx.y = blade): their arrays and record blocks are equally spaced
-  auto grid2 = [&](long long n, int t) { return dim3(blocks_for(n, t), (unsigned)r.nb, 1); };
   const long long wiP_blade = (long long)r.nc * r.ns * vlc::kWp, waN_blade = (long long)r.nNwake * r.ns * vlc::kVr;
   const long long waF_blade = (long long)r.nFwake * vlc::kFw, wapF_blade = (long long)VLC_NPFWAKE * vlc::kFw;
-  if (wing_n > 0) {
-    const long long cnt = 4LL * r.nc * r.ns;
-    vlc::pack_rings_kernel<<<grid2(cnt, 256), 256, 0, st>>>(r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0, rec,
-                                                            wiP_blade, cnt);
-    c->launches++;
-  }
-  if (wing_pad > wing_n) {
-    vlc::pack_null_kernel<<<blocks_for(wing_pad - wing_n, 256), 256, 0, st>>>(wing_pad - wing_n,
-                                                                               rec + (size_t)wing_n * vlc::kSrcDoubles);
-    c->launches++;
-  }
-  double* wrec = rec + (size_t)wing_pad * vlc::kSrcDoubles;
-  long long off = 0;  // records of one blade's block written so far; the blocks are wake_per_blade apart
-  if (r.nNwake > 0) {
-    if (nrows > 0) {
-      const long long cnt = 4LL * nrows * r.ns;
-      vlc::pack_rings_kernel<<<grid2(cnt, 256), 256, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, 0xF, 4,
-                                                              1.0, 1, wrec, waN_blade, wake_per_blade);
-      c->launches++;
-      off += cnt;
+  PackBuilder pb;
+  // ---- the flat enumeration: [wing | padding | per blade: rings, horseshoe correction, far wake, prescribed wake | padding]
+  auto flat_segments = [&](double* dst, bool rings_all) {
+    if (wing_n > 0) pb.rings(r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0, dst, r.nb, wiP_blade, 4LL * r.nc * r.ns);
+    pb.nulls(dst + (size_t)wing_n * vlc::kSrcDoubles, wing_pad - wing_n);
+    double* w = dst + (size_t)wing_pad * vlc::kSrcDoubles;
+    // rings_all: 4 filaments of every ring (reference enumeration); otherwise only what no strip covers: f3 of the last column
+    const long long per_blade = rings_all ? wake_per_blade : (long long)nrows + (has_far ? r.ns + nfar + (r.have_pf[s] ? VLC_NPFWAKE : 0) : 0);
+    long long off = 0;
+    if (r.nNwake > 0 && nrows > 0) {
+      if (rings_all) {
+        pb.rings(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, 0xF, 4, 1.0, 1, w, r.nb, waN_blade, per_blade);
+        off += 4LL * nrows * r.ns;
+      } else {  // last column: f3 of ring (i, ns-1), wake rule applies (classdef.f90:1452)
+        pb.rings(r.waN[s].p + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr, r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1, w,
+                 r.nb, waN_blade, per_blade);
+        off += nrows;
+      }
     }
     if (has_far) {
       // horseshoe correction: -vf(2) of the last near row, no gam rule (classdef.f90:1460-1463)
-      vlc::pack_rings_kernel<<<grid2(r.ns, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2, 1,
-                                                               -1.0, 0, wrec + (size_t)off * vlc::kSrcDoubles, waN_blade,
-                                                               wake_per_blade);
+      pb.rings(r.waN[s].p, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2, 1, -1.0, 0, w + (size_t)off * vlc::kSrcDoubles, r.nb, waN_blade,
+               per_blade);
       off += r.ns;
-      vlc::pack_fwake_kernel<<<grid2(nfar, 128), 128, 0, st>>>(r.waF[s].p, r.rowFar - 1, nfar,
-                                                               wrec + (size_t)off * vlc::kSrcDoubles, waF_blade, wake_per_blade);
+      pb.fwake(r.waF[s].p, r.rowFar - 1, nfar, w + (size_t)off * vlc::kSrcDoubles, r.nb, waF_blade, per_blade);
       off += nfar;
-      c->launches += 2;
       if (r.have_pf[s]) {
-        vlc::pack_fwake_kernel<<<grid2(VLC_NPFWAKE, 128), 128, 0, st>>>(r.wapF[s].p, 0, VLC_NPFWAKE,
-                                                                        wrec + (size_t)off * vlc::kSrcDoubles, wapF_blade,
-                                                                        wake_per_blade);
-        c->launches++;
+        pb.fwake(r.wapF[s].p, 0, VLC_NPFWAKE, w + (size_t)off * vlc::kSrcDoubles, r.nb, wapF_blade, per_blade);
         off += VLC_NPFWAKE;
       }
     }
-    off = wake_per_blade * r.nb;  // all blades' blocks are written
-  }
-  const long long wake_pad = pad_tile(wake_n);
-  if (wake_pad > off) {
-    vlc::pack_null_kernel<<<blocks_for(wake_pad - off, 256), 256, 0, st>>>(wake_pad - off,
-                                                                            wrec + (size_t)off * vlc::kSrcDoubles);
-    c->launches++;
-  }
-  CUDA_OK(c, cudaGetLastError());
+    const long long n = per_blade * r.nb;
+    pb.nulls(w + (size_t)n * vlc::kSrcDoubles, pad_tile(n) - n);
+    return n;
+  };
+  flat_segments(rec, true);
   r.comb[s].n = wing_n + wake_n;
   r.comb[s].n_pad = total_pad;
   r.wing_pad[s] = wing_pad;
@@ -786,7 +866,7 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   cs.n_lat = cs.n_lat_pad = cs.n_rem = cs.n_rem_pad = cs.n_lat2 = cs.n_lat2_pad = 0;
   cs.lat2_W = 0;
   if (nrows > 0 && c->shared_nodes) {
-    const StripPlan sp = plan_strips(c, r.ns);
+    const StripPlan sp = plan_strips(c, r.ns, (long long)r.nb * r.nNwake * r.ns);
     const int LW = sp.W, RD = lat_rd_of(LW), nstrips = sp.nmain;
     const long long lat_n = (long long)r.nb * nstrips * (nrows + 1);
     const long long lat_pad = pad_lat(lat_n, LW);
@@ -802,80 +882,19 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     if ((rc = reserve(c, cs.rem, (size_t)rem_pad * vlc::kSrcDoubles))) return rc;
     if (!cs.d_unmergeable) CUDA_OK(c, cudaMalloc(&cs.d_unmergeable, sizeof(int)));
     CUDA_OK(c, cudaMemsetAsync(cs.d_unmergeable, 0, sizeof(int), st));
-    if (wing_pad > 0)
-      CUDA_OK(c, cudaMemcpyAsync(cs.rem.p, rec, sizeof(double) * (size_t)wing_pad * vlc::kSrcDoubles,
-                                 cudaMemcpyDeviceToDevice, st));
-    double* rrec = cs.rem.p + (size_t)wing_pad * vlc::kSrcDoubles;
-    long long roff = 0;  // within one blade's block of the remainder; blocks are rem_per_blade apart
     {
-      const long long nring = (long long)nrows * r.ns, nrec = (long long)nstrips * (nrows + 1);
-      vlc::check_rings_kernel<<<grid2(nring, 256), 256, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns,
-                                                                 cs.d_unmergeable, waN_blade);
-#define X(WW)                                                                                                       \
-  if (LW == WW)                                                                                                     \
-    vlc::pack_rings_shared_kernel<WW><<<grid2(nrec, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, \
-                                                                        r.ns, 0, nstrips, cs.lat.p, cs.d_unmergeable, waN_blade);
-      X(1) X(2) X(3) X(4)
-#undef X
-      if (TW) {  // the tail strip: columns nstrips*LW .. ns-1
-#define X(WW)                                                                                                         \
-  if (TW == WW)                                                                                                       \
-    vlc::pack_rings_shared_kernel<WW><<<grid2(nrows + 1, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1,    \
-                                                                             nrows, r.ns, nstrips * LW, 1, cs.lat2.p,         \
-                                                                             cs.d_unmergeable, waN_blade);
-        X(1) X(2) X(3)
-#undef X
-        c->launches++;
-      }
-      // last column: f3 of ring (i, ns-1), wake rule applies (classdef.f90:1452)
-      vlc::pack_rings_kernel<<<grid2(nrows, 128), 128, 0, st>>>(r.waN[s].p + (size_t)vlc::kVr * r.nNwake * (r.ns - 1), vlc::kVr,
-                                                                r.nNwake, r.rowNear - 1, nrows, 1, 0x4, 1, 1.0, 1, rrec, waN_blade,
-                                                                rem_per_blade);
-      roff += nrows;
-      c->launches += 3;
-      if (has_far) {
-        vlc::pack_rings_kernel<<<grid2(r.ns, 128), 128, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.nNwake - 1, 1, r.ns, 0x2, 1,
-                                                                 -1.0, 0, rrec + (size_t)roff * vlc::kSrcDoubles, waN_blade,
-                                                                 rem_per_blade);
-        roff += r.ns;
-        vlc::pack_fwake_kernel<<<grid2(nfar, 128), 128, 0, st>>>(r.waF[s].p, r.rowFar - 1, nfar,
-                                                                 rrec + (size_t)roff * vlc::kSrcDoubles, waF_blade, rem_per_blade);
-        roff += nfar;
-        c->launches += 2;
-        if (r.have_pf[s]) {
-          vlc::pack_fwake_kernel<<<grid2(VLC_NPFWAKE, 128), 128, 0, st>>>(r.wapF[s].p, 0, VLC_NPFWAKE,
-                                                                          rrec + (size_t)roff * vlc::kSrcDoubles, wapF_blade,
-                                                                          rem_per_blade);
-          roff += VLC_NPFWAKE;
-          c->launches++;
-        }
-      }
-      roff = rem_per_blade * r.nb;
-    }
-    if (lat_pad > lat_n) {
-#define X(WW)                                                                                        \
-  if (LW == WW)                                                                                      \
-    vlc::pack_null_lat_kernel<WW><<<blocks_for(lat_pad - lat_n, 128), 128, 0, st>>>(lat_pad - lat_n, \
-                                                                                     cs.lat.p + (size_t)lat_n * RD);
-      X(1) X(2) X(3) X(4)
-#undef X
+      const long long nring = (long long)nrows * r.ns;
+      vlc::check_rings_kernel<<<dim3(blocks_for(nring, 256), (unsigned)r.nb, 1), 256, 0, st>>>(r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1,
+                                                                                           nrows, r.ns, cs.d_unmergeable, waN_blade);
       c->launches++;
     }
-    if (lat2_pad > lat2_n) {
-#define X(WW)                                                                                           \
-  if (TW == WW)                                                                                         \
-    vlc::pack_null_lat_kernel<WW><<<blocks_for(lat2_pad - lat2_n, 128), 128, 0, st>>>(lat2_pad - lat2_n, \
-                                                                                       cs.lat2.p + (size_t)lat2_n * RD2);
-      X(1) X(2) X(3)
-#undef X
-      c->launches++;
+    flat_segments(cs.rem.p, false);
+    pb.strips(LW, r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, 0, nstrips, cs.lat.p, cs.d_unmergeable, r.nb, waN_blade);
+    pb.null_strips(LW, cs.lat.p + (size_t)lat_n * RD, lat_pad - lat_n);
+    if (TW) {  // the tail strip: columns nstrips*LW .. ns-1
+      pb.strips(TW, r.waN[s].p, vlc::kVr, r.nNwake, r.rowNear - 1, nrows, r.ns, nstrips * LW, 1, cs.lat2.p, cs.d_unmergeable, r.nb, waN_blade);
+      pb.null_strips(TW, cs.lat2.p + (size_t)lat2_n * RD2, lat2_pad - lat2_n);
     }
-    if (pad_tile(rem_wake) > roff) {
-      vlc::pack_null_kernel<<<blocks_for(pad_tile(rem_wake) - roff, 256), 256, 0, st>>>(
-          pad_tile(rem_wake) - roff, rrec + (size_t)roff * vlc::kSrcDoubles);
-      c->launches++;
-    }
-    CUDA_OK(c, cudaGetLastError());
     cs.n_lat = lat_n;
     cs.n_lat_pad = lat_pad;
     cs.n_rings_main = (long long)r.nb * nrows * std::min(r.ns, nstrips * LW);
@@ -887,7 +906,7 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
     cs.n_rem_pad = rem_pad;
     cs.has_shared = true;
   }
-  return VLC_OK;
+  return pb.launch(c);
 }
 
 // View of a rotor's packed set without its wing segment (vind_bywake).
@@ -903,64 +922,30 @@ SourceSet wake_view(const Rotor& r, int s) {
   return v;
 }
 
-// bound-vortex set (classdef.f90:1376-1396): (vf2 + vf4)*gam of every ring, minus vf2*gam of row nc.
-int pack_bound(vlc_ctx* c, Rotor& r) {
-  if (!r.bound_dirty) return VLC_OK;
+// bound-vortex set (classdef.f90:1376-1396): (vf2 + vf4)*gam of every ring, minus vf2*gam of row nc; chordwise-vortex set
+// (classdef.f90:1398-1418): (vf1 + vf3)*gam of every ring, plus vf2*gam of row nc -- the same layout with the other two
+// filaments and the opposite sign on the trailing-edge row.  One launch each (pack_table_kernel).
+int pack_wing_subset(vlc_ctx* c, Rotor& r, SourceSet& set, bool& dirty, int mask, double te_sign) {
+  if (!dirty) return VLC_OK;
   const long long per_blade = 2LL * r.nc * r.ns + r.ns;
   const long long n = per_blade * r.nb;
   const long long n_pad = pad_tile(n);
-  int rc = reserve(c, r.bound.rec, (size_t)n_pad * vlc::kSrcDoubles);
+  int rc = reserve(c, set.rec, (size_t)n_pad * vlc::kSrcDoubles);
   if (rc) return rc;
-  double* rec = r.bound.rec.p;
-  {  // one launch per kernel type for all blades (blockIdx.y = blade), blocks of per_blade records
-    const long long cnt = 2LL * r.nc * r.ns, wiP_blade = (long long)r.nc * r.ns * vlc::kWp;
-    vlc::pack_rings_kernel<<<dim3(blocks_for(cnt, 256), (unsigned)r.nb, 1), 256, 0, c->stream>>>(
-        r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xA, 2, 1.0, 0, rec, wiP_blade, per_blade);
-    vlc::pack_rings_kernel<<<dim3(blocks_for(r.ns, 128), (unsigned)r.nb, 1), 128, 0, c->stream>>>(
-        r.wiP.p, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2, 1, -1.0, 0, rec + (size_t)cnt * vlc::kSrcDoubles, wiP_blade, per_blade);
-    c->launches += 2;
-  }
-  if (n_pad > n) {
-    vlc::pack_null_kernel<<<blocks_for(n_pad - n, 256), 256, 0, c->stream>>>(n_pad - n,
-                                                                              rec + (size_t)n * vlc::kSrcDoubles);
-    c->launches++;
-  }
-  CUDA_OK(c, cudaGetLastError());
-  r.bound.n = n;
-  r.bound.n_pad = n_pad;
-  r.bound_dirty = false;
+  double* rec = set.rec.p;
+  const long long cnt = 2LL * r.nc * r.ns, wiP_blade = (long long)r.nc * r.ns * vlc::kWp;
+  PackBuilder pb;
+  pb.rings(r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, mask, 2, 1.0, 0, rec, r.nb, wiP_blade, per_blade);
+  pb.rings(r.wiP.p, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2, 1, te_sign, 0, rec + (size_t)cnt * vlc::kSrcDoubles, r.nb, wiP_blade, per_blade);
+  pb.nulls(rec + (size_t)n * vlc::kSrcDoubles, n_pad - n);
+  if ((rc = pb.launch(c))) return rc;
+  set.n = n;
+  set.n_pad = n_pad;
+  dirty = false;
   return VLC_OK;
 }
-
-// chordwise-vortex set (classdef.f90:1398-1418): (vf1 + vf3)*gam of every ring, plus vf2*gam of row nc -- the same
-// layout and kernels as pack_bound with the other two filaments and the opposite sign on the trailing-edge row.
-int pack_chord(vlc_ctx* c, Rotor& r) {
-  if (!r.chord_dirty) return VLC_OK;
-  const long long per_blade = 2LL * r.nc * r.ns + r.ns;
-  const long long n = per_blade * r.nb;
-  const long long n_pad = pad_tile(n);
-  int rc = reserve(c, r.chord.rec, (size_t)n_pad * vlc::kSrcDoubles);
-  if (rc) return rc;
-  double* rec = r.chord.rec.p;
-  {
-    const long long cnt = 2LL * r.nc * r.ns, wiP_blade = (long long)r.nc * r.ns * vlc::kWp;
-    vlc::pack_rings_kernel<<<dim3(blocks_for(cnt, 256), (unsigned)r.nb, 1), 256, 0, c->stream>>>(
-        r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0x5, 2, 1.0, 0, rec, wiP_blade, per_blade);
-    vlc::pack_rings_kernel<<<dim3(blocks_for(r.ns, 128), (unsigned)r.nb, 1), 128, 0, c->stream>>>(
-        r.wiP.p, vlc::kWp, r.nc, r.nc - 1, 1, r.ns, 0x2, 1, 1.0, 0, rec + (size_t)cnt * vlc::kSrcDoubles, wiP_blade, per_blade);
-    c->launches += 2;
-  }
-  if (n_pad > n) {
-    vlc::pack_null_kernel<<<blocks_for(n_pad - n, 256), 256, 0, c->stream>>>(n_pad - n,
-                                                                              rec + (size_t)n * vlc::kSrcDoubles);
-    c->launches++;
-  }
-  CUDA_OK(c, cudaGetLastError());
-  r.chord.n = n;
-  r.chord.n_pad = n_pad;
-  r.chord_dirty = false;
-  return VLC_OK;
-}
+int pack_bound(vlc_ctx* c, Rotor& r) { return pack_wing_subset(c, r, r.bound, r.bound_dirty, 0xA, -1.0); }
+int pack_chord(vlc_ctx* c, Rotor& r) { return pack_wing_subset(c, r, r.chord, r.chord_dirty, 0x5, 1.0); }
 
 // Form of a set made of several rotors' records laid side by side: the rotors' common form when they agree, the flat
 // enumeration (1) when one of them needs it or when they disagree (merged and dual records cannot share a launch).
@@ -1073,11 +1058,30 @@ int build_ws_combined(vlc_ctx* c, int s, bool* ok) {
   return VLC_OK;
 }
 
+// Host -> device copy of a caller's array.  The caller may reuse its buffer as soon as the call returns.  Small arrays
+// (the moved wing of every time step, section frames: < 1 MiB) go through one of two pinned staging buffers and the copy
+// is left in flight -- no synchronisation, the stream keeps running ahead (a synchronous hand-over costs ~20 us of idle
+// device per call, several per time step of a small case); large arrays are copied from the caller's memory and waited for.
 int upload(vlc_ctx* c, DevBuf& b, size_t total, size_t offset, const double* host, size_t count) {
   int rc = reserve(c, b, total);
   if (rc) return rc;
-  CUDA_OK(c, cudaMemcpyAsync(b.p + offset, host, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer right away
+  const size_t bytes = count * sizeof(double);
+  if (bytes > 0 && bytes <= vlc_ctx::kStageBytes) {
+    const int k = c->stage_next;
+    c->stage_next ^= 1;
+    if (!c->stage_h[k]) {
+      CUDA_OK(c, cudaMallocHost(&c->stage_h[k], vlc_ctx::kStageBytes));
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+    } else {
+      CUDA_OK(c, cudaEventSynchronize(c->stage_ev[k]));  // the copy that last used this buffer (two uploads ago) is done
+    }
+    std::memcpy(c->stage_h[k], host, bytes);
+    CUDA_OK(c, cudaMemcpyAsync(b.p + offset, c->stage_h[k], bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaEventRecord(c->stage_ev[k], c->stream));
+    return VLC_OK;
+  }
+  CUDA_OK(c, cudaMemcpyAsync(b.p + offset, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }
 
@@ -1231,6 +1235,10 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     if (r.d_info) cudaFree(r.d_info);
   }
   if (c->solver) cusolverDnDestroy(c->solver);
+  for (int k = 0; k < 2; ++k) {
+    if (c->stage_h[k]) cudaFreeHost(c->stage_h[k]);
+    if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
+  }
   for (auto& e : c->user_ev)
     if (e) cudaEventDestroy(e);
   for (auto& st : c->stats) {
@@ -2433,24 +2441,31 @@ extern "C" int vlc_rotor_wakevel_op(vlc_ctx* c, int ir, int op) {
     CUDA_OK(c, cudaMemcpyAsync(dst.p, src.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return VLC_OK;
   };
+  const vlc::VelArrays va{r->velN[0].p, r->velN[1].p, r->velN[2].p, r->velN[3].p, r->velF[0].p, r->velF[1].p, r->velF[2].p, r->velF[3].p};
+  auto fused = [&](int fop, int dst, int src) -> int {  // near and far arrays in one launch (wake_state.cuh)
+    const long long tot = (long long)(nn + nf);
+    if (tot <= 0) return VLC_OK;
+    vlc::wakevel_fused_kernel<<<blocks_for(tot, 256), 256, 0, c->stream>>>(fop, (long long)nn, (long long)nf, va, dst, src);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches++;
+    return VLC_OK;
+  };
+  (void)copy;
   switch (op) {
     case VLC_VEL_FIRST_STEP:  // main.f90:1013-1020: vel1 = vel
-      if ((rc = copy(r->velN[1], r->velN[0], nn)) || (rc = copy(r->velF[1], r->velF[0], nf))) return rc;
+      if ((rc = fused(2, 1, 0))) return rc;
       break;
     case VLC_VEL_AB2:  // main.f90:1031-1041: velStep = vel; vel = 0.5*(3*vel - vel1), whole arrays
-      if ((rc = copy(r->velN[3], r->velN[0], nn)) || (rc = copy(r->velF[3], r->velF[0], nf))) return rc;
-      LAUNCH1D(c, vlc::ab2_kernel, (long long)nn, (long long)nn, r->velN[3].p, r->velN[1].p, r->velN[0].p);
-      LAUNCH1D(c, vlc::ab2_kernel, (long long)nf, (long long)nf, r->velF[3].p, r->velF[1].p, r->velF[0].p);
+      if ((rc = fused(0, 0, 0))) return rc;
       break;
     case VLC_VEL_AM2:  // main.f90:1094-1099: vel = (velPredicted + velStep)*0.5
-      LAUNCH1D(c, vlc::am2_kernel, (long long)nn, (long long)nn, r->velN[2].p, r->velN[3].p, r->velN[0].p);
-      LAUNCH1D(c, vlc::am2_kernel, (long long)nf, (long long)nf, r->velF[2].p, r->velF[3].p, r->velF[0].p);
+      if ((rc = fused(1, 0, 0))) return rc;
       break;
     case VLC_VEL_SHIFT_HISTORY:  // main.f90:1103-1107: vel1 = velStep
-      if ((rc = copy(r->velN[1], r->velN[3], nn)) || (rc = copy(r->velF[1], r->velF[3], nf))) return rc;
+      if ((rc = fused(2, 1, 3))) return rc;
       break;
     case VLC_VEL_COPY_TO_STEP:  // velStep = vel (fdScheme 2, main.f90:975-988 together with AB2 and FIRST_STEP)
-      if ((rc = copy(r->velN[3], r->velN[0], nn)) || (rc = copy(r->velF[3], r->velF[0], nf))) return rc;
+      if ((rc = fused(2, 3, 0))) return rc;
       break;
     case VLC_VEL_ORDER2: {  // main.f90:927-940: vel(active) = vel_order2(vel(active), velPredicted(active))
       const int rowsN = r->nNwake - r->rowNear + 1, rowsF = r->nFwake - r->rowFar + 1;

@@ -72,14 +72,8 @@ __global__ void pack_null_kernel(long long count, double* __restrict__ rec) {
 //   fil_mask selects filaments (bit f), sign scales gam.
 //   blockIdx.y = blade: source arrays and record blocks of the blades of a rotor are equally shaped and equally spaced
 //   (src_blade doubles, dst_blade records apart), so one launch packs them all (gridDim.y = 1 and 0, 0 otherwise).
-__global__ void pack_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int ni, int nj,
-                                  int fil_mask, int nfil, double sign, int wake, double* __restrict__ rec,
-                                  long long src_blade = 0, long long dst_blade = 0) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)ni * nj * nfil;
-  if (q >= total) return;
-  base += (size_t)blockIdx.y * src_blade;
-  rec += (size_t)blockIdx.y * dst_blade * kSrcDoubles;
+__device__ __forceinline__ void pack_rings_body(const double* __restrict__ base, int stride, int ld, int i0, int ni, int nfil,
+                                                int fil_mask, double sign, int wake, double* __restrict__ rec, long long q) {
   const int fsel = (int)(q % nfil);
   const long long ring = q / nfil;
   const int i = (int)(ring % ni) + i0;
@@ -97,16 +91,31 @@ __global__ void pack_rings_kernel(const double* __restrict__ base, int stride, i
             strength(sign * vr[kVrGam], wake != 0));
 }
 
+__global__ void pack_rings_kernel(const double* __restrict__ base, int stride, int ld, int i0, int ni, int nj,
+                                  int fil_mask, int nfil, double sign, int wake, double* __restrict__ rec,
+                                  long long src_blade = 0, long long dst_blade = 0) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)ni * nj * nfil;
+  if (q >= total) return;
+  base += (size_t)blockIdx.y * src_blade;
+  rec += (size_t)blockIdx.y * dst_blade * kSrcDoubles;
+  pack_rings_body(base, stride, ld, i0, ni, nfil, fil_mask, sign, wake, rec, q);
+}
+
 // Far-wake / prescribed-wake filaments stored as Fwake_class records (13 doubles), i in [i0, i0+ni).
+__device__ __forceinline__ void pack_fwake_body(const double* __restrict__ base, int i0, double* __restrict__ rec, long long q) {
+  const double* fw = base + (size_t)kFw * (i0 + q);
+  write_rec(rec + (size_t)q * kSrcDoubles, fw[0], fw[1], fw[2], fw[3], fw[4], fw[5], fw[kVfRvc],
+            strength(fw[kFwGam], true));
+}
+
 __global__ void pack_fwake_kernel(const double* __restrict__ base, int i0, int ni, double* __restrict__ rec,
                                   long long src_blade = 0, long long dst_blade = 0) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= ni) return;
   base += (size_t)blockIdx.y * src_blade;
   rec += (size_t)blockIdx.y * dst_blade * kSrcDoubles;
-  const double* fw = base + (size_t)kFw * (i0 + q);
-  write_rec(rec + (size_t)q * kSrcDoubles, fw[0], fw[1], fw[2], fw[3], fw[4], fw[5], fw[kVfRvc],
-            strength(fw[kFwGam], true));
+  pack_fwake_body(base, i0, rec, q);
 }
 
 // AIC(row, col) = vr(col)%vind(CP(row)) . nCap(row)   classdef.f90:4159-4176 (serial 6-deep loop there).
@@ -441,6 +450,83 @@ __global__ void pack_rings_shared_kernel(const double* __restrict__ base, int st
   fill_strip_record<W>(acc, nrows, ns, col_base + (int)(q / nr1) * W, (int)(q % nr1), rec + q * RD, unmergeable, fmt);
 }
 
+
+// ---- one launch for everything a rotor's packed set consists of ------------------------------------------------------
+// A packed set is a handful of SEGMENTS (wing rings | padding | wake rings of every blade | horseshoe corrections | far wake
+// | prescribed wake | padding; the same again for the flat remainder of the shared-node form; strip records of one or two
+// widths | padding).  One kernel per segment made ~14 launches per pack and ~40 per time step of a small case, where a
+// launch costs more than the work (K&P: 0.95 ms per step for 0.15 ms of sweeps).  The table below names the segments; one
+// thread packs one record, found by its global index.  Segment kinds: 0 ring filaments (pack_rings_body), 1 far-wake
+// records (pack_fwake_body), 2 null flat records, 3 strip records of width W (fill_strip_record), 4 null strip records.
+struct PackSeg {
+  int kind, W;
+  const double* src;   // blade 0
+  double* dst;         // blade 0
+  long long src_blade; // doubles between the blades' source arrays
+  long long dst_blade; // records between the blades' destination blocks
+  long long count;     // records per blade
+  int nb;
+  int stride, ld, i0, ni, mask, nfil, wake;  // ring segments
+  double sign;
+  int nrows, ns, col_base, nstrips;          // strip segments
+  int* flag;
+};
+constexpr int kPackSegs = 20;
+__host__ __device__ constexpr int strip_rd(int W) { return (3 * (W + 1) + 1) / 2 * 2 + 14 * W; }  // = lat_rec_doubles(W), bs_lattice.cuh
+struct PackTable {
+  int n;
+  long long start[kPackSegs + 1];  // first global index of every segment; start[n] = total
+  PackSeg seg[kPackSegs];
+};
+
+template <int W>
+__device__ __forceinline__ void pack_strip_seg(const PackSeg& g, const double* src, double* dst, long long idx) {
+  constexpr int RD = (3 * (W + 1) + 1) / 2 * 2 + 14 * W;
+  const int nr1 = g.nrows + 1;
+  const RingsAcc acc{src, g.stride, g.ld, g.i0, g.nrows, g.ns};
+  const int fmt = (*g.flag == kFmtDual) ? kFmtDual : kFmtMerged;
+  fill_strip_record<W>(acc, g.nrows, g.ns, g.col_base + (int)(idx / nr1) * W, (int)(idx % nr1), dst + idx * RD, g.flag, fmt);
+}
+template <int W>
+__device__ __forceinline__ void pack_null_strip(double* dst, long long idx) {
+  constexpr int NP = (3 * (W + 1) + 1) / 2 * 2, RD = NP + 14 * W;
+  double* r = dst + idx * RD;
+  for (int k = 0; k < RD; ++k) r[k] = 0.0;
+  for (int k = 0; k <= W; ++k) r[3 * k] = (double)k;
+}
+
+__global__ void pack_table_kernel(const PackTable t) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= t.start[t.n]) return;
+  int k = 0;
+  while (q >= t.start[k + 1]) ++k;
+  const PackSeg& g = t.seg[k];
+  const long long local = q - t.start[k];
+  const int blade = (int)(local / g.count);
+  const long long idx = local % g.count;
+  const double* src = g.src + (size_t)blade * g.src_blade;
+  switch (g.kind) {
+    case 0: pack_rings_body(src, g.stride, g.ld, g.i0, g.ni, g.nfil, g.mask, g.sign, g.wake, g.dst + (size_t)blade * g.dst_blade * kSrcDoubles, idx); break;
+    case 1: pack_fwake_body(src, g.i0, g.dst + (size_t)blade * g.dst_blade * kSrcDoubles, idx); break;
+    case 2: write_null_rec(g.dst + (size_t)idx * kSrcDoubles); break;
+    case 3: {
+      const long long per = (long long)g.nstrips * (g.nrows + 1);
+      switch (g.W) {
+        case 1: pack_strip_seg<1>(g, src, g.dst + (size_t)blade * per * strip_rd(1), idx); break;
+        case 2: pack_strip_seg<2>(g, src, g.dst + (size_t)blade * per * strip_rd(2), idx); break;
+        case 3: pack_strip_seg<3>(g, src, g.dst + (size_t)blade * per * strip_rd(3), idx); break;
+        default: pack_strip_seg<4>(g, src, g.dst + (size_t)blade * per * strip_rd(4), idx); break;
+      }
+    } break;
+    default:
+      switch (g.W) {
+        case 1: pack_null_strip<1>(g.dst, idx); break;
+        case 2: pack_null_strip<2>(g.dst, idx); break;
+        case 3: pack_null_strip<3>(g.dst, idx); break;
+        default: pack_null_strip<4>(g.dst, idx); break;
+      }
+  }
+}
 
 // ---- gridgen (src/gridgen.f90) ---------------------------------------------------------------------------
 // vf_class records (12 doubles) with a separate circulation array; no |gam| > eps rule (gridgen.f90:129-135).

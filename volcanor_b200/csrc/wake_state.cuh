@@ -18,6 +18,31 @@ __global__ void ab2_kernel(long long n, const double* __restrict__ v, const doub
   if (i < n) out[i] = __dmul_rn(0.5, __dadd_rn(__dmul_rn(3.0, v[i]), -v1[i]));
 }
 
+// The velocity bookkeeping of a predictor / corrector stage on the near- and far-wake arrays of a rotor in ONE launch
+// (near array = elements [0, nn), far array = [nn, nn + nf)); same arithmetic as ab2_kernel / am2_kernel.
+//   op 0: main.f90:1031-1041  velStep = vel; vel = 0.5*(3*vel - vel1)
+//   op 1: main.f90:1094-1099  vel = (velPredicted + velStep)*0.5
+//   op 2: dst = src (vel1 = vel, vel1 = velStep, velStep = vel)
+struct VelArrays {
+  double *n0, *n1, *n2, *n3, *f0, *f1, *f2, *f3;  // vel, vel1, velPredicted, velStep: near / far
+};
+__global__ void wakevel_fused_kernel(int op, long long nn, long long nf, VelArrays a, int dst, int src) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nn + nf) return;
+  const bool far = q >= nn;
+  const long long i = far ? q - nn : q;
+  double* v[4] = {far ? a.f0 : a.n0, far ? a.f1 : a.n1, far ? a.f2 : a.n2, far ? a.f3 : a.n3};
+  if (op == 0) {
+    const double s = v[0][i];
+    v[3][i] = s;
+    v[0][i] = __dmul_rn(0.5, __dadd_rn(__dmul_rn(3.0, s), -v[1][i]));
+  } else if (op == 1) {
+    v[0][i] = __dmul_rn(__dadd_rn(v[2][i], v[3][i]), 0.5);
+  } else {
+    v[dst][i] = v[src][i];
+  }
+}
+
 // main.f90:1094-1096  velNwake = (velNwakePredicted + velNwakeStep)*0.5   (Adams-Moulton corrector)
 __global__ void am2_kernel(long long n, const double* __restrict__ vp, const double* __restrict__ vs,
                            double* __restrict__ out) {
