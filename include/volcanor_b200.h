@@ -372,7 +372,9 @@ int vlc_pack_lattice(vlc_ctx* ctx, int set, int append, int nrows, int ns, const
 int vlc_set_shared_nodes(vlc_ctx* ctx, int on);
 /* Launch shape of the shared-node kernel: strip_width W in 1..4 ring columns per strip record (wider strips
  * amortise the node work: 72 / 66.5 / 64.7 / 63.75 FP64 instructions per ring), targets_per_thread in 1..3;
- * 0 = default.  Takes effect at the next pack.  Only speed and summation order change. */
+ * 0 = default.  Takes effect at the next pack.  Only speed and summation order change.  A rotor's lattice whose column
+ * count is not a multiple of 4 is covered by width-4 strips plus one narrower tail strip when the wake is large (>= 2e4
+ * rings: the tail's extra launches then cost less than padded columns); strip_width = 5 asks for that cover at any size. */
 int vlc_set_lattice_tuning(vlc_ctx* ctx, int strip_width, int targets_per_thread);
 /* out[0..5]: out[0] = filaments in the reference's enumeration, out[1] = strip records and out[2] = remainder filaments of
  * the shared-node form (0 if the set has none), out[3] = 1 if the next sweep will use the shared-node kernel with merged

@@ -50,9 +50,10 @@ def test_katzNplotkin_50_steps_CL_and_circulation(ctx, oracle):
     assert err[:, 0].max() < TOL_HISTORY and err[:, 1].max() < TOL_HISTORY
     # the reference's own wake records describe a lattice: the shared-node kernel did the work (no silent fallback)
     info = ctx.rotor_info(0)
-    # ns = 26 columns = 6 strips of width 4 + one tail strip of width 2, 50 rows (+1 record per strip)
-    assert info["shared_active"] == 1 and info["strip_width"] == 4 and info["tail_strip_width"] == 2, info
-    assert info["lattice_records"] == (6 + 1) * 51, info
+    # ns = 26 columns, a small wake (4160 rings at most): one strip width without padding, 13 strips of width 2, 50 rows
+    # (+1 record per strip); from 2e4 rings on the cover would be 6 strips of width 4 + one tail strip of width 2
+    assert info["shared_active"] == 1 and info["strip_width"] == 2 and info["tail_strip_width"] == 0, info
+    assert info["lattice_records"] == 13 * 51, info
     # and the GPU-driven run still reproduces the reference's golden file to its 7 printed digits
     fx = json.loads((GOLDEN / "katzNplotkin_AR04.json").read_text())
     ref50 = fx["ref_ForceNonDim"]["rows"][50][1]

@@ -401,6 +401,7 @@ def test_tail_strips_cover_column_counts_that_are_not_multiples_of_four(ctx, ora
     enumeration: compared with the oracle on random targets and on the wake's own nodes (guarded pairs), for the current
     and the predicted set; forcing one width with vlc_set_lattice_tuning gives the same velocities."""
     from tests.test_gpu_parity import _make_rotor_pair, _tol_scale
+    ctx.set_lattice_tuning(5, 0)       # the tail-strip cover also for a wake this small (default: only from 2e4 rings on)
     ro = _make_rotor_pair(ctx, oracle, seed=40 + ns, ns=ns, nNwake=9, nFwake=4, rowNear=2, rowFar=2)
     rng = np.random.default_rng(ns)
     nodes = np.concatenate([ro.waN(ib)[:, 1:, 12:15].reshape(-1, 3) for ib in range(ro.nb)])     # corner 2 of the active rings

@@ -446,7 +446,7 @@ inline StripPlan plan_strips(const vlc_ctx* c, int ns, long long rings_max = -1)
   const int t = ns % 4;
   // a tail strip is two more launches per sweep (merged + dual form): not worth it while the whole wake is small enough
   // for a sweep to be launch-bound (< ~2e4 rings: a few hundred microseconds)
-  if (rings_max >= 0 && rings_max < 20000) return p;
+  if (rings_max >= 0 && rings_max < 20000 && c->lat_W != 5) return p;  // lat_W == 5: tail strips whatever the size (tests)
   if (ns > 4 && t != 0) {
     const double single = kLatCost[p.W] * (double)(p.nmain * p.W) / (double)ns;
     const double mixed = (kLatCost[4] * (double)(ns - t) + kLatCost[t] * (double)t) / (double)ns + 0.005;
@@ -3112,7 +3112,8 @@ extern "C" int vlc_set_lattice_tuning(vlc_ctx* c, int strip_width, int targets_p
   CHECK_CTX(c);
   VLC_GROUP(c, vlc_set_lattice_tuning(m, strip_width, targets_per_thread));
   const int W = strip_width, T = targets_per_thread;
-  if (W < 0 || W > 4 || T < 0 || T > 3) return fail(c, VLC_ERR_ARG, "strip_width in 1..4, targets_per_thread in 1..3 (0 = automatic)");
+  if (W < 0 || W > 5 || T < 0 || T > 3)
+    return fail(c, VLC_ERR_ARG, "strip_width in 1..4 (0 = automatic, 5 = automatic with tail strips for small wakes too), targets_per_thread in 1..3");
   c->lat_W = W;
   c->lat_T = T;
   for (auto& r : c->rotors) r.dirty[0] = r.dirty[1] = true;  // tier-3 sets are re-packed by their owner
