@@ -477,16 +477,21 @@ def main():
             "at W = 4) and may exceed 1; `pipe_frac` = issued FP64 instructions x 2 / peak is the hardware utilisation; "
             "`same_work` = the flat kernel on the reference's own enumeration, one sweep after the timed region"
             if shared else "flat kernel on the reference's enumeration: frac = algorithmic 76 flop/pair, pipe_frac = 43 issued FP64 instr/pair")
-    prof = ROOT / "profiles" / "r02_bs_lattice_full.md"
+    # DRAM traffic of the dominant kernel: not measurable outside a profiler; quoted from the committed ncu --set full capture
+    # of THIS command (profiles/r02m_bs_sweep_full.md), and only for the workload and launch shape it was taken on
+    prof = ROOT / "profiles" / "r02m_bs_sweep_full.md"
     traffic, traffic_source = None, None
-    if shared and n_gpus == 1 and args.filaments == 1_000_000 and prof.exists():
+    if shared and not dual and n_gpus == 1 and n_src == 1000192 and args.lat_w in (0, 4) and args.lat_t in (0, 2) and prof.exists():
         import re
         txt = prof.read_text()
-        mm = re.search(r"traffic per launch[^0-9]*([0-9.]+)\s*MB", txt)
-        if mm:
-            traffic = float(mm.group(1)) * 1e6
-            traffic_source = ("profiles/r02_bs_lattice_full.md: ncu --set full of this command, dram__bytes_read.sum + "
-                              "dram__bytes_write.sum of one bs_lattice_kernel launch (one source rotor); not re-measured in this run")
+        rd = re.search(r"dram__bytes_read\.sum \| ([0-9.]+) \| Mbyte", txt)
+        wr = re.search(r"dram__bytes_write\.sum \| ([0-9.]+) \| Mbyte", txt)
+        if rd and wr:
+            traffic = (float(rd.group(1)) + float(wr.group(1))) * 1e6
+            traffic_source = ("profiles/r02m_bs_sweep_full.md: ncu --set full of this command (same workload, same launch shape), "
+                              "dram__bytes_read.sum + dram__bytes_write.sum of one bs_lattice_kernel launch; not re-measured in this "
+                              "run. Algorithmic bytes per launch: 36.0 MB of strip records (62 536 x 576 B) + 6.2 MB of targets "
+                              "read + 74 MB of source-split partial sums written (12 x 6.2 MB), most of which stay in L2")
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_source,
                 "kernel": kernel, "launches": st["launches"], "kernel_ms": kern_ms_total / n_launch,
