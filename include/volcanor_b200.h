@@ -302,6 +302,12 @@ int vlc_rotor_get_wakevel(vlc_ctx* ctx, int ir, int ib, int which, double* velN 
  * rotor.  velCP stays in the device records, RHS on the device for vlc_rotor_solve_map_gam.  Optional host copies:
  * velCP_out (3, nbConvect*nc*ns) in wiP order, RHS_out (nc*ns*nb); either may be NULL. */
 int vlc_rotor_calc_RHS(vlc_ctx* ctx, int ir, double* velCP_out, double* RHS_out);
+/* Sub-iterations (switches%ntSub > 0, main.f90:522-615): every pass of ntSubLoop starts velCP again from its kinematic
+ * part (:528-547), which the records keep in velCPm (:545-546).  Pass i >= 1 of the loop is
+ *   vlc_rotor_reset_velCP of every rotor; vlc_rotor_calc_RHS of every rotor; vlc_rotor_solve_map_gam of every rotor
+ * (the wings of the other rotors then carry the circulation of pass i-1, as in the reference); the driver compares
+ * gamVec with the previous pass (:606-613). */
+int vlc_rotor_reset_velCP(vlc_ctx* ctx, int ir);
 /* gamVec = matmulAX(AIC_inv, RHS) (main.f90:596; getrs with the factors of vlc_rotor_calcAIC) followed by
  * rotor%map_gam() (classdef.f90:4181-4196) on the device records.  gamVec_out (nc*ns*nb) may be NULL. */
 int vlc_rotor_solve_map_gam(vlc_ctx* ctx, int ir, double* gamVec_out);

@@ -56,6 +56,29 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+def case_lib_path() -> Path:
+    return _HERE / "libvolcanor_case.so"
+
+
+def build_case_driver(force: bool = False) -> Path:
+    """g++ -> volcanor_b200/libvolcanor_case.so: the product-side driver of an unmodified .case directory
+    (csrc/case_driver.cpp; host code only -- every stage of the hot path is a call into libvolcanor_b200.so, which it links).
+    -ffp-contract=off: the reference's statement order without FMA contraction, like its own -O2 build on x86-64."""
+    out = case_lib_path()
+    src = _HERE / "csrc" / "case_driver.cpp"
+    deps = [src, _ROOT / "include" / "volcanor_b200.h"]
+    if out.exists() and not force and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return out
+    build_library()
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    cmd = [cxx, "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", str(out), str(src),
+           f"-L{_HERE}", "-lvolcanor_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise VlcError("g++ failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def _declared_symbols() -> list[str]:
     hdr = (_ROOT / "include" / "volcanor_b200.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
@@ -166,6 +189,7 @@ def load_library() -> C.CDLL:
         "vlc_rotor_put_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_rotor_get_wakevel": (i32, [_vp, i32, i32, i32, _vp, _vp]),
         "vlc_rotor_calc_RHS": (i32, [_vp, i32, _vp, _vp]),
+        "vlc_rotor_reset_velCP": (i32, [_vp, i32]),
         "vlc_rotor_solve_map_gam": (i32, [_vp, i32, _vp]),
         "vlc_rotor_put_sections": (i32, [_vp, i32, i32, _vp]),
         "vlc_rotor_calc_velCPTotal": (i32, [_vp, i32]),
@@ -593,6 +617,10 @@ class Context:
         r = np.empty(N, dtype=np.float64) if want_RHS else None
         self._ck(self.lib.vlc_rotor_calc_RHS(self.h, ir, _ptr(v), _ptr(r)))
         return v, r
+
+    def rotor_reset_velCP(self, ir):
+        """velCP <- velCPm (its kinematic part) on the device records: head of a sub-iteration pass (main.f90:528-547)."""
+        self._ck(self.lib.vlc_rotor_reset_velCP(self.h, ir))
 
     def rotor_solve_map_gam(self, ir, N, want_gamVec=True):
         g = np.empty(N, dtype=np.float64) if want_gamVec else None

@@ -2025,7 +2025,10 @@ extern "C" int vlc_rotor_assignshed(vlc_ctx* c, int ir, int edge) {
   if (!r) return VLC_ERR_STATE;
   if (edge != 0 && edge != 1) return fail(c, VLC_ERR_ARG, "edge: 0 = 'LE', 1 = 'TE' (classdef.f90:4303, :4313)");
   if (r->nNwake <= 0) return VLC_OK;
-  if (r->rowNear < 1 || r->rowNear > r->nNwake) return fail(c, VLC_ERR_STATE, "assignshed: rowNear outside 1..nNwake");
+  // 'LE' writes row rowNear; 'TE' writes row max(rowNear - 1, 1): also legal with rowNear = nNwake + 1, which is how the
+  // reference pre-sheds the first row before the time loop (main.f90:227-234)
+  if (r->rowNear < 1 || r->rowNear > r->nNwake + (edge == 1 ? 1 : 0))
+    return fail(c, VLC_ERR_STATE, "assignshed: rowNear outside 1..nNwake");
   const int n = r->nb * r->ns;
   vlc::rec_assignshed_kernel<<<blocks_for(n, 128), 128, 0, c->stream>>>(edge, r->nb, r->nc, r->ns, r->nNwake, r->rowNear,
                                                                         r->wiP.p, r->waN[0].p);
@@ -2691,6 +2694,23 @@ extern "C" int vlc_rotor_calc_RHS(vlc_ctx* c, int ir, double* velCP_out, double*
                                  3 * sizeof(double), (size_t)m, cudaMemcpyDeviceToHost, c->stream));
   if (RHS_out) CUDA_OK(c, cudaMemcpyAsync(RHS_out, r->rhs.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
   if (velCP_out || RHS_out) CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+// main.f90:528-547 at the head of EVERY sub-iteration of ntSubLoop (:522): velCP starts again from its kinematic part,
+// which the driver keeps in velCPm (:545-546).  vlc_rotor_calc_RHS adds the induced velocities to velCP, so a second
+// pass over the same wing records (ntSub > 0) calls this first.
+extern "C" int vlc_rotor_reset_velCP(vlc_ctx* c, int ir) {
+  CHECK_CTX(c);
+  VLC_GROUP(c, vlc_rotor_reset_velCP(m, ir));
+  int rc = bind_device(c);
+  if (rc) return rc;
+  Rotor* r = get_rotor(c, ir);
+  if (!r) return VLC_ERR_STATE;
+  const long long m = (long long)r->nbConvect * r->nc * r->ns;
+  vlc::cp_copy_field_kernel<<<blocks_for(3 * m, 256), 256, 0, c->stream>>>(m, vlc::cp::kVelCPm, vlc::cp::kVelCP, r->wiP.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
   return VLC_OK;
 }
 

@@ -28,7 +28,7 @@ namespace cp {
 // delDiConstant delDiUnsteady | meanChord meanSpan panelArea rHinge alpha
 constexpr int kRec = 104;
 constexpr int kGam = 48, kGamPrev = 50, kGamTrapz = 51, kPC1 = 52, kCP = 64, kNcap = 67, kTauChord = 70, kTauSpan = 73;
-constexpr int kVelCP = 76, kVelCPTotal = 79, kNormalForce = 85, kNormalForceUnsteady = 88, kChordwiseResVel = 91;
+constexpr int kVelCP = 76, kVelCPTotal = 79, kVelCPm = 82, kNormalForce = 85, kNormalForceUnsteady = 88, kChordwiseResVel = 91;
 constexpr int kDelP = 95, kDelPUnsteady = 96, kMeanChord = 99, kMeanSpan = 100, kPanelArea = 101;
 
 // Section frames of one blade as the driver holds them after moving the wing (blade_class, classdef.f90:238-358):
