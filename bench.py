@@ -534,8 +534,8 @@ def main():
     out = {"metric": "biot_savart_pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
            "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {**config_of(args, name, n_src, m),
-                      "parallelism": (f"target-sharded x{n_gpus} behind the C ABI, sources replicated, 1 all-gather of velocity slices per "
+           "config": config_of(args, name, n_src, m),     # the same object in both arms (the driver compares them)
+           "run": {"parallelism": (f"target-sharded x{n_gpus} behind the C ABI, sources replicated, 1 all-gather of velocity slices per "
                                       f"wake sweep (2 per step) inside vlc_wake_sweep; transport {comm['transport']}; "
                                       + ("ONE process, one worker thread per GPU (vlc_create_multi)" if single else
                                          "one process per GPU, library-owned communicator (vlc_comm_init_rank)" if world > 1 else

@@ -105,9 +105,17 @@ class CaseDriver:
             pass
 
 
-def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False) -> dict:
-    case = casefile.read_case(case_dir)
+def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False, nsplit: int = 0) -> dict:
+    if isinstance(case_dir, dict):          # an already parsed case ({"name", "config", "geom"}: what read_case returns)
+        case, case_dir = case_dir, Path(".")
+    elif str(case_dir).endswith(".json"):   # the same, stored as JSON (tests/golden/*.json: the shipped cases, parsed once)
+        import json
+        case, case_dir = json.loads(Path(case_dir).read_text()), Path(case_dir).parent
+    else:
+        case = casefile.read_case(case_dir)
     ctx = api.Context(devices=list(range(gpus))) if gpus > 1 else api.Context(0)
+    if nsplit:
+        ctx.set_tuning(0, nsplit)   # a fixed source split: a target's summation order no longer depends on the launch it is in
     drv = CaseDriver(case, ctx)
     t0 = time.perf_counter()
     drv.init()
@@ -137,12 +145,15 @@ def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False) -> 
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
-    ap.add_argument("case_dir")
+    ap.add_argument("case_dir", help="a .case directory (config.nml, geomNN.nml[, PLOT3D grid]) or a JSON dump of read_case()")
     ap.add_argument("--nt", type=int, default=0, help="stop after this many steps (default: the case's nt)")
     ap.add_argument("--out", default=None, help="results directory (default: <case_dir>/Results)")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs behind the one library handle (vlc_create_multi)")
+    ap.add_argument("--nsplit", type=int, default=0,
+                    help="fixed number of source splits per sweep (default: chosen per launch): makes the history independent of "
+                         "--gpus bit for bit")
     args = ap.parse_args(argv)
-    run(args.case_dir, args.nt, args.out, args.gpus)
+    run(args.case_dir, args.nt, args.out, args.gpus, nsplit=args.nsplit)
     return 0
 
 
