@@ -148,6 +148,47 @@ def test_sub_iterations_on_the_device(ctx, oracle, ntSub):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("two_rotors", [False, True])
+def test_nonuniform_streamwiseCoreVec_case_runs_on_the_dual_form(ctx, oracle, two_rotors):
+    """A case file with a NON-UNIFORM streamwiseCoreVec (classdef.f90:2722-2726, :3841) and wake dissipation on: after the
+    first rotor_dissipate_wake (vf(3)%rVc <- vf(1)%rVc, :4371-4372) the two copies of every interior streamwise edge of the
+    wake carry different core radii.  The whole time loop then runs on the dual form of the lattice kernel
+    (rotor_info: shared_active == 2) and reproduces the CPU driver's histories within the north-star's 1e-8; round 1 ran such
+    a case on the flat enumeration.  With a second rotor whose cores ARE uniform the combined wake sweep sees two forms and
+    goes to the flat enumeration for that launch (or_flags_kernel) -- same answer."""
+    from tests.test_oracle_case import two_body_case
+    if two_rotors:
+        fx = two_body_case()
+        g = fx["geom"][1]
+    else:
+        fx = _fixture("caradonna")
+        _short_caradonna(fx)
+        g = fx["geom"][0]
+    g["streamwiseCoreVec"] = [0.03 + 0.002 * j for j in range(int(g["ns"]) + 1)]
+    fx["config"]["wakeDissipation"] = 1
+    a = oracle.Case(fx)
+    a.init()
+    from volcanor_b200.run_case import CaseDriver
+    d = CaseDriver(fx, ctx)
+    d.init()
+    ir = 1 if two_rotors else 0
+    worst, forms = 0.0, set()
+    for it in range(14 if two_rotors else 25):
+        a.step()
+        d.step()
+        for k in range(d.nr):
+            fa, fb = a.force_nondim(k), d.force_nondim(k)
+            ga, gb = a.rotor(k).vec(0), d.gamvec(k)
+            worst = max(worst, abs(fb[0] / fa[0] - 1.0), float(np.max(np.abs(gb - ga)) / np.max(np.abs(ga))))
+        forms.add(ctx.rotor_info(ir, True)["shared_active"])
+    print(f"non-uniform streamwiseCoreVec ({'wing + rotor' if two_rotors else 'caradonna'}): max rel err {worst:.2e}, forms seen {sorted(forms)}")
+    assert worst < 1e-8
+    assert 2 in forms                                   # the dual form did the rotor's sweeps
+    if two_rotors:
+        assert ctx.rotor_info(0, True)["shared_active"] == 1    # the wing's wake: merged form
+
+
+@pytest.mark.gpu
 def test_product_driver_through_a_multi_gpu_handle(ctx, oracle):
     """The same driver, the same calls, a handle made by vlc_create_multi: bit-identical history under a fixed source split."""
     import torch

@@ -155,6 +155,8 @@ struct vlc_ctx {
   int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
   // multi-GPU data plane (group.hpp): this context's place in the target partition, its NCCL communicator (library-owned),
   // and -- for the members of an in-process group made by vlc_create_multi -- the group
+  double* host_P = nullptr;  // pinned scratch for target lists gathered from the caller's records (vlc_vind_on?wake_byRotor)
+  size_t host_P_cap = 0;
   static constexpr size_t kStageBytes = (size_t)1 << 20;
   void* stage_h[2] = {nullptr, nullptr};  // pinned staging of small uploads (upload())
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -692,6 +694,20 @@ int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, cons
     CUDA_OK(c, cudaMemcpyAsync(V + 3 * sh.lo, dV, sizeof(double) * 3 * (size_t)ml, cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VLC_OK;
+}
+
+// pinned host scratch of at least n doubles (the previous sweep_host has synchronised, so it is free to overwrite)
+int host_targets(vlc_ctx* c, size_t n, double** out) {
+  if (n > c->host_P_cap) {
+    if (c->host_P) cudaFreeHost(c->host_P);
+    c->host_P = nullptr;
+    c->host_P_cap = 0;
+    const size_t want = n + n / 4 + 1024;
+    CUDA_OK(c, cudaMallocHost(&c->host_P, want * sizeof(double)));
+    c->host_P_cap = want;
+  }
+  *out = c->host_P;
   return VLC_OK;
 }
 
@@ -1235,6 +1251,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     if (r.d_info) cudaFree(r.d_info);
   }
   if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->host_P) cudaFreeHost(c->host_P);
   for (int k = 0; k < 2; ++k) {
     if (c->stage_h[k]) cudaFreeHost(c->stage_h[k]);
     if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
@@ -1825,7 +1842,12 @@ extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake,
   if (!Nwake || !vindArray) return fail(c, VLC_ERR_ARG, "null pointer");
   // targets in the reference's order (libCommon.f90:133-145): corner 2 of ring (i,j) = vf(2)%fc(:,1),
   // then corner 3 of the last column = vf(3)%fc(:,1)
-  std::vector<double> P((size_t)3 * rows * (cols + 1));
+  double* P = nullptr;  // pinned, grow-only: no allocation, no page faults and an asynchronous H2D per call
+  {
+    int rc0 = bind_device(c);
+    if (rc0) return rc0;
+    if ((rc0 = host_targets(c, (size_t)3 * rows * (cols + 1), &P))) return rc0;
+  }
   for (int j = 0; j < cols; ++j)
     for (int i = 0; i < rows; ++i) {
       const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * j);
@@ -1835,7 +1857,7 @@ extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake,
     const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * (cols - 1));
     std::memcpy(&P[3 * ((size_t)i + (size_t)rows * cols)], rec + VLC_VF_DOUBLES * 2, 3 * sizeof(double));
   }
-  return vlc_rotor_vind(c, ir, predicted, (int64_t)rows * (cols + 1), P.data(), vindArray);
+  return vlc_rotor_vind(c, ir, predicted, (int64_t)rows * (cols + 1), P, vindArray);
 }
 
 extern "C" int vlc_vind_onFwake_byRotor(vlc_ctx* c, int ir, const double* Fwake, int rows, int predicted,
@@ -1845,9 +1867,14 @@ extern "C" int vlc_vind_onFwake_byRotor(vlc_ctx* c, int ir, const double* Fwake,
   if (rows < 0) return fail(c, VLC_ERR_ARG, "rows < 0");
   if (rows == 0) return VLC_OK;
   if (!Fwake || !vindArray) return fail(c, VLC_ERR_ARG, "null pointer");
-  std::vector<double> P((size_t)3 * rows);
+  double* P = nullptr;
+  {
+    int rc0 = bind_device(c);
+    if (rc0) return rc0;
+    if ((rc0 = host_targets(c, (size_t)3 * rows, &P))) return rc0;
+  }
   for (int i = 0; i < rows; ++i) std::memcpy(&P[3 * (size_t)i], Fwake + (size_t)VLC_FWAKE_DOUBLES * i, 3 * sizeof(double));
-  return vlc_rotor_vind(c, ir, predicted, rows, P.data(), vindArray);
+  return vlc_rotor_vind(c, ir, predicted, rows, P, vindArray);
 }
 
 // ---------------------------------------------------------------------------- AIC
