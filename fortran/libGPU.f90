@@ -306,6 +306,11 @@ module libGPU
       real(c_double), value :: divisor
     end function
     ! tier 2c
+    integer(c_int) function vlc_rotor_reset_velCP(c, ir) bind(C, name='vlc_rotor_reset_velCP')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: c
+      integer(c_int), value :: ir
+    end function
     integer(c_int) function vlc_rotor_calc_RHS(c, ir, velCP_out, RHS_out) bind(C, name='vlc_rotor_calc_RHS')
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: c
@@ -780,16 +785,25 @@ contains
 
   ! ------------------------------------------------------------------ collocation-point stage (tier 2c)
 
-  subroutine gpu_cp_rhs_solve(rotor)
-    !! Replaces main.f90:548-603 for every rotor inside the time loop (ntSub = 0).  The driver keeps :528-547 -- it writes
+  subroutine gpu_cp_rhs_solve(rotor, subIter)
+    !! Replaces main.f90:548-603 for every rotor inside ONE pass of ntSubLoop (:522).  The driver keeps :528-547 -- it writes
     !! the kinematic part into wiP%velCP / velCPm -- saves gamVecPrev, calls gpu_touch(ir, GPU_WING) and then this routine;
     !! velCP, RHS, gamVec come back, the wing circulation is mapped on both sides (rotor%map_gam() here, map_gam on the
-    !! device), so the wing is NOT stale afterwards.
+    !! device), so the wing is NOT stale afterwards.  subIter (optional) = the loop index i of ntSubLoop: for i >= 1 the
+    !! wing did not move, so nothing is uploaded and the device restarts velCP from velCPm (vlc_rotor_reset_velCP) before
+    !! it adds the induced velocities again -- with the other rotors' circulations of pass i-1, as in the reference.
     type(rotor_class), intent(inout) :: rotor(:)
-    integer :: ir, ib, ic, is, q
+    integer, intent(in), optional :: subIter
+    integer :: ir, ib, ic, is, q, pass
     real(c_double), allocatable :: velCP(:, :)
+    pass = 0
+    if (present(subIter)) pass = subIter
     do ir = 1, size(rotor)
-      call gpu_sync_rotor(rotor(ir), ir, .false.)
+      if (pass == 0) then
+        call gpu_sync_rotor(rotor(ir), ir, .false.)
+      else
+        call check(vlc_rotor_reset_velCP(ctx, ir - 1))
+      endif
     enddo
     do ir = 1, size(rotor)
       allocate (velCP(3, rotor(ir)%nbConvect*rotor(ir)%nc*rotor(ir)%ns))

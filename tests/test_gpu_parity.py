@@ -26,6 +26,31 @@ def _check_flat(ctx, oracle, p1, p2, rvc, gam, flag, P, tol=TOL):
     return V, Vo, Vl, Vabs
 
 
+def test_targets_within_eps_of_a_node_of_a_long_filament(ctx, oracle):
+    """libMath.f90:249-262: unitVec(r) returns the ZERO vector when |r| <= eps = 2.2e-16.  A target that close to an end
+    point of a filament longer than ~1 -- but not bitwise on it -- passes the reference's c2 > eps^2 test, and the reference
+    then drops the r1/|r1| piece of r0.(r1/|r1| - r2/|r2|), while the kernels (u = 1/|r| from a reciprocal square root, no
+    zeroing) keep it: the continuous value.  The difference is |c| |r0.r1/|r1|| / sqrt(K + |c|^4) <= eps L^2 / (rVc^2 L^2) =
+    eps / rVc^2 in absolute terms: measured here on 2-unit filaments with rVc = 0.05 and asserted against the 1e-12 bar of
+    the target's velocity scale (documented deviation; a target bitwise ON the node is skipped exactly)."""
+    rng = np.random.default_rng(12)
+    n = 40
+    p1 = rng.uniform(-1, 1, (n, 3))
+    d = rng.normal(size=(n, 3))
+    p2 = p1 + 2.0 * d / np.linalg.norm(d, axis=1)[:, None]
+    rvc, gam = np.full(n, 0.05), rng.uniform(0.5, 1.0, n)
+    off = rng.normal(size=(n, 3))
+    P = np.concatenate([p1 + 1.5e-16 * off / np.linalg.norm(off, axis=1)[:, None], p1 * (1 + 2.0 ** -52), p1])
+    Vl, Vabs = oracle.vind_flat_ld(p1, p2, rvc, gam, None, P)
+    Vo = oracle.vind_flat(p1, p2, rvc, gam, None, P)
+    ctx.set_sources(0, p1, p2, rvc, gam, None)
+    V = ctx.vind(0, P)
+    assert np.all(np.isfinite(V))
+    e = scaled_err(V, Vo, Vabs)
+    print(f"targets within eps of a node: per-target error vs the reference-order sum {e:.2e} (vs long double {scaled_err(V, Vl, Vabs):.2e})")
+    assert e < TOL
+
+
 @pytest.mark.parametrize("n,m", [(1, 1), (7, 3), (127, 129), (128, 512), (129, 513), (1000, 77), (5000, 2049)])
 def test_flat_random_vs_oracle(ctx, oracle, n, m):
     ctx.set_tuning(0, 0)

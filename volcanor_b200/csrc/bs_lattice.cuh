@@ -59,7 +59,11 @@ __device__ __forceinline__ NodeQ node_eval(double px, double py, double pz, doub
   n.ry = py - ay;
   n.rz = pz - az;
   const double d = fma(n.rz, n.rz, fma(n.ry, n.ry, n.rx * n.rx));
-  n.u = rsqrt_fp64<false>(d);  // d == 0 (target on the node) gives NaN; every edge that uses it has c == 0 and is guarded
+  // d == 0 (target on the node) gives NaN; every edge that uses it has c == 0 and is guarded.  Unlike libMath.f90:257
+  // (unitVec = 0 when |r| <= eps) u is NOT zeroed for 0 < |r| <= 2.2e-16: for a filament longer than ~1 such a target
+  // passes c2 > eps^2 and keeps the r/|r| piece the reference drops; the difference is <= eps/rVc^2 in absolute terms
+  // (tests/test_gpu_parity.py::test_targets_within_eps_of_a_node_of_a_long_filament)
+  n.u = rsqrt_fp64<false>(d);
   return n;
 }
 
