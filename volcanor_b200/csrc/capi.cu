@@ -314,6 +314,31 @@ int query_occ(vlc_ctx* c, int* out) {
   return VLC_OK;
 }
 
+// Source split of a SMALL sweep: one that cannot fill the machine for two waves with chunks of >= 4 tiles.  Parallelism
+// then matters more than the per-CTA prologue: chunks go down to ONE tile, and the split is the one with the least estimated
+// time ceil(waves) * (chunk_tiles + c0), c0 ~ prologue + epilogue in units of a tile (ncu launch list of K&P, r02s: the
+// wake sweeps of a 4 000-node wake ran 7 splits x 15 target tiles = 105 CTAs on 296 slots for 106 us; 5e7 pairs are 53 us
+// of the whole machine).  Returns 0 when the sweep is not small (the caller's search for whole waves applies).
+int plan_small_split(long long target_tiles, long long src_tiles, long long slots) {
+  const long long by4 = std::max(1LL, src_tiles / 4);
+  if (target_tiles * by4 >= 2 * slots || src_tiles <= 1) return 0;
+  const double c0 = 0.3;
+  double best = 1e300;
+  int best_s = 1;
+  const long long max_split = std::min(src_tiles, 256LL);
+  for (long long s = 1; s <= max_split; ++s) {
+    const long long chunk = (src_tiles + s - 1) / s, real = (src_tiles + chunk - 1) / chunk;
+    if (real != s) continue;
+    const double waves = (double)target_tiles * (double)real / (double)slots;
+    const double cost = std::ceil(waves - 1e-9) * ((double)chunk + c0);
+    if (cost < best * (1.0 - 1e-9)) {
+      best = cost;
+      best_s = (int)s;
+    }
+  }
+  return best_s;
+}
+
 // Launch shape: T targets per thread and nsplit source splits.
 void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, int* nsplit_out) {
   const long long src_tiles = n_pad / kTile;
@@ -324,6 +349,11 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
     const long long tiles4 = (m + kThreads * 4 - 1) / (kThreads * 4);
     T = (tiles4 * src_tiles >= 4 * slots4 || tiles4 >= slots4) ? 4 : 2;
     if (m <= kThreads) T = 1;
+    if (T == 2) {  // still too small at two targets per thread: one per thread, twice the CTAs
+      const long long slots2 = (long long)c->sm_count * (c->occ[2] > 0 ? c->occ[2] : 3);
+      const long long tiles2 = (m + kThreads * 2 - 1) / (kThreads * 2);
+      if (plan_small_split(tiles2, src_tiles, slots2) > 0) T = 1;
+    }
   }
   int nsplit = c->tune_nsplit;
   if (nsplit < 1) {
@@ -336,8 +366,8 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
     const long long cap_by_mem = (long long)((size_t)1 << 31) / (3 * (m > 0 ? m : 1) * 8) + 1;  // <= 2 GiB partials
     if (max_split > cap_by_mem) max_split = cap_by_mem;
     double best = -1.0;
-    int best_s = 1;
-    for (long long s = 1; s <= max_split; ++s) {
+    int best_s = plan_small_split(tiles, src_tiles, slots);
+    for (long long s = 1; s <= max_split && best_s == 0; ++s) {
       const long long chunk_tiles = (src_tiles + s - 1) / s;
       const long long real_s = (src_tiles + chunk_tiles - 1) / chunk_tiles;
       const double ctas = (double)tiles * (double)real_s;
@@ -351,7 +381,7 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
       }
       if (waves >= 8.0 && eff > 0.995) break;  // whole waves matter: equal-work CTAs leave a (1 - eff) tail idle
     }
-    nsplit = best_s;
+    nsplit = best_s > 0 ? best_s : 1;
   }
   if (nsplit > src_tiles) nsplit = (int)(src_tiles > 0 ? src_tiles : 1);
   *T_out = T;
@@ -510,6 +540,8 @@ int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_
   const long long ttiles = (m + (long long)kLatThreads * T - 1) / ((long long)kLatThreads * T);
   const int occ = dual ? c->occ_dual[W] : c->occ_lat[W][T];
   const long long slots = (long long)c->sm_count * (occ > 0 ? occ : 2);
+  const int small = plan_small_split(ttiles, tiles, slots);
+  if (small > 0) return small;
   long long max_split = tiles / 4;
   if (max_split < 1) max_split = 1;
   if (max_split > 256) max_split = 256;
@@ -548,6 +580,12 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
     if (m <= kLatThreads) p.T = 1;
     while (p.T > 1 && !lat_shape_exists(W, p.T)) --p.T;
     const long long tiles = n_pad / lat_tile_of(W);
+    if (p.T > 1 && !dual && c->lat_T < 1) {
+      // a sweep too small to fill the machine at T targets per thread: one target per thread, T times the CTAs
+      const long long tt = (m + (long long)kLatThreads * p.T - 1) / ((long long)kLatThreads * p.T);
+      const long long slots = (long long)c->sm_count * (c->occ_lat[W][p.T] > 0 ? c->occ_lat[W][p.T] : 2);
+      if (plan_small_split(tt, tiles, slots) > 0) p.T = 1;
+    }
     p.ns = plan_lattice_split(c, W, p.T, m, n_pad, dual);
     const long long chunk_tiles = (tiles + p.ns - 1) / p.ns;
     p.ns = (int)((tiles + chunk_tiles - 1) / chunk_tiles);

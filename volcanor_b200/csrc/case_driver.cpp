@@ -21,6 +21,7 @@
 //
 // Built by volcanor_b200/api.py:build_case_driver with g++ -O2 -ffp-contract=off (the reference's statement order,
 // no FMA contraction) into volcanor_b200/libvolcanor_case.so, which links libvolcanor_b200.so.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -370,6 +371,7 @@ struct vcase {
   vlc_ctx* ctx = nullptr;
   std::string err;
   long wing_uploads = 0;
+  double stage_s[6] = {0, 0, 0, 0, 0, 0};  // host wall time per stage: motion, upload + prestep, RHS + solve, forces, wake stage, (unused)
 };
 
 namespace {
@@ -1088,6 +1090,13 @@ int vcase_step(vcase* c) {
   c->iter += 1;
   c->t = c->t + dt;
   const int iter = c->iter;
+  using clk = std::chrono::steady_clock;
+  auto t0 = clk::now();
+  auto lap = [&](int k) {
+    const auto t1 = clk::now();
+    c->stage_s[k] += std::chrono::duration<double>(t1 - t0).count();
+    t0 = t1;
+  };
   for (Rotor& r : c->rotor) {  // :412-417
     r.rowNear = r.rowNear - 1 > 1 ? r.rowNear - 1 : 1;
     if (iter > r.nNwake) r.rowFar = r.rowFar - 1 > 1 ? r.rowFar - 1 : 1;
@@ -1112,10 +1121,10 @@ int vcase_step(vcase* c) {
     rotor_rot_advance(r, r.omegaSlow * dt, false);
   }
   // the moved wing goes up ONCE per step, with the kinematic velCP (:528-547) already in its records
-  for (int ir = 0; ir < c->nr; ++ir) {
-    kinematic_velCP(c->rotor[ir]);
+  for (int ir = 0; ir < c->nr; ++ir) kinematic_velCP(c->rotor[ir]);
+  lap(0);
+  for (int ir = 0; ir < c->nr; ++ir)
     if (int rc = sync_wing(c, ir)) return rc;
-  }
   if (cfg.wakeSuppress == 0) {  // :466-506
     for (int ir = 0; ir < c->nr; ++ir)
       if (c->rotor[ir].nNwake > 0) VK(c, vlc_rotor_assignshed(c->ctx, ir, 0));
@@ -1126,13 +1135,22 @@ int vcase_step(vcase* c) {
       for (int ir = 0; ir < c->nr; ++ir)
         if (c->rotor[ir].nNwake > 0) VK(c, vlc_rotor_burst_wake(c->ctx, ir, c->rotor[ir].skewLimit, c->rotor[ir].chord));
   }
+  lap(1);
   if (int rc = rhs_solve(c, cfg.ntSub)) return rc;  // :522-615
+  lap(2);
   if (cfg.rotorForcePlot != 0 && iter % cfg.rotorForcePlot == 0)  // :624-722
     if (int rc = compute_forces(c)) return rc;
+  lap(3);
   if (cfg.wakeSuppress == 0)  // :800-1440
     if (int rc = wake_convect(c, iter)) return rc;
+  lap(4);
   return 0;
 }
+
+// host wall time spent in the stages of vcase_step so far: motion | wing upload + wake pre-step | RHS + solve | forces |
+// wake stage.  The stages end in a device read-back (gamVec; wing + loads) or run asynchronously (wake stage), so the
+// numbers say where the HOST waits, which for a small case is where the time goes.
+void vcase_stage_seconds(const vcase* c, double out[5]) { std::memcpy(out, c->stage_s, 5 * sizeof(double)); }
 
 int vcase_iter(const vcase* c) { return c->iter; }
 // nt, dt as rotor%init left them (chords / revolutions resolved), per-rotor sizes and row counters

@@ -37,7 +37,8 @@ class CaseDriver:
                            "vcase_attach": [C.c_void_p, C.c_void_p], "vcase_init": [C.c_void_p], "vcase_step": [C.c_void_p],
                            "vcase_iter": [C.c_void_p], "vcase_info": [C.c_void_p, C.c_int, C.c_void_p],
                            "vcase_force_nondim": [C.c_void_p, C.c_int, C.c_void_p], "vcase_get_gamvec": [C.c_void_p, C.c_int, C.c_void_p],
-                           "vcase_get_loads": [C.c_void_p, C.c_int, C.c_int, C.c_void_p]}.items():
+                           "vcase_get_loads": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+                           "vcase_stage_seconds": [C.c_void_p, C.c_void_p]}.items():
             getattr(L, name).argtypes = args
         self.nr = int(case["config"].get("nr", len(case["geom"])))
         self.h = L.vcase_new(self.nr)
@@ -93,6 +94,11 @@ class CaseDriver:
         self.lib.vcase_get_loads(self.h, ir, ib, a.ctypes.data)
         return a
 
+    def stage_seconds(self) -> dict:
+        a = np.zeros(5)
+        self.lib.vcase_stage_seconds(self.h, a.ctypes.data)
+        return dict(zip(("motion", "upload+prestep", "rhs+solve", "forces", "wake"), a.tolist()))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.vcase_free(self.h)
@@ -134,10 +140,12 @@ def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False, nsp
         (outdir / f"r{ir + 1:02d}ForceNonDim.csv").write_text("\n".join(lines[ir]) + "\n")
     res = {"case": case["name"], "steps": n, "init_s": t1 - t0, "loop_s": t2 - t1, "timesteps_per_s": n / (t2 - t1) if t2 > t1 else 0.0,
            "launches": ctx.launch_count, "gpus": gpus, "out": str(outdir), "ignored_keys": drv.ignored,
+           "stage_seconds": drv.stage_seconds(),
            "final": [drv.force_nondim(ir).tolist() for ir in range(drv.nr)]}
     if not quiet:
         print(f"{case['name']}: {n} steps in {t2 - t1:.2f} s ({res['timesteps_per_s']:.1f} timesteps/s, {ctx.launch_count / max(n, 1):.0f} "
               f"kernel launches per step) on {gpus} GPU(s); wrote {outdir}/rNNForceNonDim.csv")
+        print("  host time per stage [s]: " + ", ".join(f"{k} {v:.3f}" for k, v in res["stage_seconds"].items()))
     drv.close()
     ctx.close()
     return res
