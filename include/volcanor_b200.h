@@ -171,11 +171,11 @@ int vlc_vind_onFwake_byRotor(vlc_ctx* ctx, int ir, const double* Fwake, int rows
                              double* vindArray);
 
 /* = rotor%calcAIC() classdef.f90:4151-4179: assembles AIC on the device from the uploaded wing
- * (CP, nCap, vortex rings) and LU-factors it (cuSOLVER getrf; the reference's explicit inverse
- * inv2 = DGETRF+DGETRI, libMath.f90:48-83, is replaced by factor-once / getrs-per-step).
+ * (CP, nCap, vortex rings), LU-factors it (cuSOLVER getrf) and forms AIC_inv once (getrs on the identity: the
+ * reference's inv2 = DGETRF+DGETRI, libMath.f90:48-83, classdef.f90:4178).
  * AIC_out (N x N column-major, N = nc*ns*nb) may be NULL. */
 int vlc_rotor_calcAIC(vlc_ctx* ctx, int ir, double* AIC_out);
-/* gamVec = AIC^-1 * RHS, replaces matmulAX(AIC_inv, RHS) (main.f90:190, :596). */
+/* gamVec = matmulAX(AIC_inv, RHS) (main.f90:190, :596; libMath.f90:105-122): one GEMV with the stored inverse. */
 int vlc_rotor_solve(vlc_ctx* ctx, int ir, const double* RHS, double* gamVec);
 /* AIC_inv (N x N) if the caller wants the explicit inverse the reference stores. */
 int vlc_rotor_get_AIC_inv(vlc_ctx* ctx, int ir, double* AIC_inv);
@@ -308,7 +308,7 @@ int vlc_rotor_calc_RHS(vlc_ctx* ctx, int ir, double* velCP_out, double* RHS_out)
  * (the wings of the other rotors then carry the circulation of pass i-1, as in the reference); the driver compares
  * gamVec with the previous pass (:606-613). */
 int vlc_rotor_reset_velCP(vlc_ctx* ctx, int ir);
-/* gamVec = matmulAX(AIC_inv, RHS) (main.f90:596; getrs with the factors of vlc_rotor_calcAIC) followed by
+/* gamVec = matmulAX(AIC_inv, RHS) (main.f90:596; one GEMV with the inverse of vlc_rotor_calcAIC) followed by
  * rotor%map_gam() (classdef.f90:4181-4196) on the device records.  gamVec_out (nc*ns*nb) may be NULL. */
 int vlc_rotor_solve_map_gam(vlc_ctx* ctx, int ir, double* gamVec_out);
 /* Section frames of blade ib as the driver holds them after moving the wing, one block of 10*ns + 6 doubles:

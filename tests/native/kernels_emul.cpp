@@ -177,7 +177,7 @@ void emul_vind_records(long long n, const double* rec, long long m, const double
 }  // extern "C"
 
 // strips of width W over ring columns col0 .. (clipped at ns by fill_strip_record): pack + null padding + sweep with nsplit
-// source splits (grid y, chunks of whole tiles as sweep_shared cuts them); the partial slots are appended to parts
+// source splits (grid y, chunks of whole granules as sweep_shared cuts them); the partial slots are appended to parts
 template <int W, int T>
 static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nrows, int col0, int nstrips, int nsplit, long long m,
                           const double* P, int* unmergeable, std::vector<double>& parts, int* nslots) {
@@ -189,18 +189,21 @@ static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nro
   if (npad > nrec)
     emul_launch(blocks_for(npad - nrec, 128), 1, 128, vlc::pack_null_lat_kernel<W>, npad - nrec, lat.data() + (size_t)nrec * RD);
   if (*unmergeable & 1) return 1;
-  const long long tiles = npad / TILE, chunk_tiles = (tiles + nsplit - 1) / nsplit;
-  const int real_split = (int)((tiles + chunk_tiles - 1) / chunk_tiles);
+  // chunks are multiples of the granule (a quarter tile), as sweep_shared cuts a tuned or a small sweep: with nsplit that does
+  // not divide the tiles the last tile of a chunk is partial
+  constexpr int GRAN = vlc::lat_granule(W);
+  const long long units = npad / GRAN, per = (units + nsplit - 1) / nsplit, chunk = per * GRAN;
+  const int real_split = (int)((units + per - 1) / per);
   const size_t len = 3 * (size_t)m, at = parts.size();
   parts.resize(at + (size_t)real_split * len, 0.0);
   // both forms are launched, as on the device; the set's flag (0 merged / 2 dual) decides which one does the work
   std::vector<double> other((size_t)real_split * len, std::nan(""));
   const bool dual = (*unmergeable == 2);
   emul_launch(blocks_for(m, THREADS * T), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>,
-              (const double*)lat.data(), chunk_tiles * TILE, npad, P, m, dual ? other.data() : parts.data() + at,
+              (const double*)lat.data(), chunk, npad, P, m, dual ? other.data() : parts.data() + at,
               (const int*)unmergeable, 3, 0);
   emul_launch(blocks_for(m, THREADS), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, 1, THREADS, 3, 1, true>,
-              (const double*)lat.data(), chunk_tiles * TILE, npad, P, m, dual ? parts.data() + at : other.data(),
+              (const double*)lat.data(), chunk, npad, P, m, dual ? parts.data() + at : other.data(),
               (const int*)unmergeable, 3, 2);
   for (double v : other)
     if (v == v) return 4;  // the form that must not run wrote something

@@ -416,10 +416,12 @@ def test_dual_core_streamwise_edges_on_the_cpu(oracle, W, tailW, ns, nsplit):
 
 
 @pytest.mark.parametrize("W,T,tailW,nsplit,ns", [(1, 1, 0, 1, 8), (1, 3, 0, 2, 8), (1, 3, 0, 4, 8), (2, 2, 0, 3, 8), (4, 2, 0, 1, 8),
-                                                 (4, 2, 0, 2, 8), (4, 1, 0, 3, 8), (3, 2, 0, 2, 6), (4, 2, 2, 2, 6)])
+                                                 (4, 2, 0, 2, 8), (4, 1, 0, 3, 8), (3, 2, 0, 2, 6), (4, 2, 2, 2, 6),
+                                                 (1, 3, 0, 3, 8), (2, 2, 0, 5, 8), (4, 2, 0, 7, 8)])
 def test_lattice_kernel_on_the_cpu_source_splits_and_tile_ring(oracle, W, T, tailW, nsplit, ns):
     """Long near wake (30 active rows): the strip records fill several shared-memory tiles, so one CTA walks more tiles than
-    the ring has stages (3) and the sweep is cut into source splits of whole tiles (grid y, sweep_shared's chunks); then
+    the ring has stages (3) and the sweep is cut into source splits of whole granules (grid y, sweep_shared's chunks: the last
+    three cases end a chunk in a partial tile -- 1.5 tiles, half a tile, half a tile); then
     check_rings_kernel and bs_reduce_select_kernel close the launch sequence of the mergeable path.  Oracle and bar as above;
     more than 128 T targets, so several CTAs in x as well."""
     case, _ = _case(oracle, 30, ns=ns, wakeTruncateNt=0, nNwake=32)

@@ -48,6 +48,9 @@ __host__ __device__ constexpr int lat_rec_doubles(int W) { return lat_core_doubl
 #define VLC_LAT_TILE_DIV 1
 #endif
 __host__ __device__ constexpr int lat_tile(int W) { return (W <= 2 ? 64 : 32) / VLC_LAT_TILE_DIV; }  // records per shared-memory tile
+// A source split (chunk) is a multiple of the GRANULE, a quarter of a tile: the last tile of a chunk may be partial.  Small
+// sweeps (a few thousand targets x a few hundred records: the reference's own test cases) need more CTAs than whole tiles give.
+__host__ __device__ constexpr int lat_granule(int W) { return lat_tile(W) / 4; }
 
 struct NodeQ {
   double rx, ry, rz, u;  // r = P - X, u = 1/|r|
@@ -112,7 +115,7 @@ __device__ __forceinline__ void edge_accumulate_dual(const NodeQ& a, const NodeQ
 template <int W, int T, int THREADS, int STAGES, int MINB, bool DUAL = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, padded to a multiple of lat_tile(W)
-                  long long chunk,                 // records per split (multiple of the tile)
+                  long long chunk,                 // records per split (multiple of the granule)
                   long long n_pad,                 // total padded records
                   const double* __restrict__ P, long long m,
                   double* __restrict__ out,        // [gridDim.y][3 m]
@@ -133,9 +136,13 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
   const long long s_begin = (long long)blockIdx.y * chunk;
   long long s_end = s_begin + chunk;
   if (s_end > n_pad) s_end = n_pad;
-  const int ntiles = (s_end > s_begin) ? (int)((s_end - s_begin) / TILE) : 0;
+  const long long len = s_end > s_begin ? s_end - s_begin : 0;  // a multiple of the granule (even)
+  const int ntiles = (int)((len + TILE - 1) / TILE);
   const double* gsrc = lat + s_begin * RD;
-  constexpr uint32_t kTileBytes = TILE * RD * 8;
+  auto tile_records = [&](int t) -> int {  // TILE, except for the last tile of a chunk that is not a whole number of tiles
+    const long long left = len - (long long)t * TILE;
+    return left < TILE ? (int)left : TILE;
+  };
 
   if (VLC_PRODUCER(tid)) {
 #pragma unroll
@@ -147,8 +154,9 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
 #pragma unroll
     for (int s = 0; s < STAGES; ++s)
       if (s < ntiles) {
-        mbar_expect_tx(&bars[s], kTileBytes);
-        tma_bulk_g2s(buf + (size_t)s * TILE * RD, gsrc + (size_t)s * TILE * RD, kTileBytes, &bars[s]);
+        const uint32_t bytes = (uint32_t)tile_records(s) * (RD * 8);
+        mbar_expect_tx(&bars[s], bytes);
+        tma_bulk_g2s(buf + (size_t)s * TILE * RD, gsrc + (size_t)s * TILE * RD, bytes, &bars[s]);
       }
   }
 
@@ -175,8 +183,12 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
     const uint32_t phase = (uint32_t)(tile / STAGES) & 1u;
     mbar_wait(&bars[stage], phase);
     const double* sbase = buf + (size_t)stage * TILE * RD;
-#pragma unroll 2
-    for (int j = 0; j < TILE; ++j) {
+    const int jn = tile_records(tile);
+#pragma unroll 1
+    for (int j2 = 0; j2 < jn; j2 += 2)  // two records per trip (jn is even): the unroll the fixed-length loop had
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = j2 + jj;
       const double2* sb = reinterpret_cast<const double2*>(sbase + (size_t)j * RD);
       double q[RL];  // the record, in registers (constant indices after unrolling)
 #pragma unroll
@@ -207,8 +219,9 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
     }
     __syncthreads();
     if (VLC_PRODUCER(tid) && tile + STAGES < ntiles) {
-      mbar_expect_tx(&bars[stage], kTileBytes);
-      tma_bulk_g2s(buf + (size_t)stage * TILE * RD, gsrc + (size_t)(tile + STAGES) * TILE * RD, kTileBytes, &bars[stage]);
+      const uint32_t bytes = (uint32_t)tile_records(tile + STAGES) * (RD * 8);
+      mbar_expect_tx(&bars[stage], bytes);
+      tma_bulk_g2s(buf + (size_t)stage * TILE * RD, gsrc + (size_t)(tile + STAGES) * TILE * RD, bytes, &bars[stage]);
     }
   }
 

@@ -39,6 +39,7 @@ constexpr int kStages = 3;     // TMA ring depth
 // (sweeps with at most one CTA of targets use T=1, sweep_shared).
 constexpr double kLatCost[5] = {0.0, 1.000, 0.919, 0.932, 0.885};
 constexpr int kLatBestT[5] = {0, 3, 2, 2, 2};
+constexpr double kSmallC0 = 0.3;  // fixed cost of a CTA of a small sweep, in source tiles (plan_small_split)
 
 std::string g_create_error;
 
@@ -111,7 +112,7 @@ struct Rotor {
   std::vector<char> have_sec;  // per blade: vlc_rotor_put_sections seen
   // AIC
   int N = 0;
-  DevBuf LU;
+  DevBuf LU, Ainv;  // LU factors (cuSOLVER getrf) and the inverse the reference multiplies by every step (classdef.f90:4178)
   int* d_ipiv = nullptr;
   int* d_info = nullptr;
   bool factored = false;
@@ -315,19 +316,21 @@ int query_occ(vlc_ctx* c, int* out) {
 }
 
 // Source split of a SMALL sweep: one that cannot fill the machine for two waves with chunks of >= 4 tiles.  Parallelism
-// then matters more than the per-CTA prologue: chunks go down to ONE tile, and the split is the one with the least estimated
-// time ceil(waves) * (chunk_tiles + c0), c0 ~ prologue + epilogue in units of a tile (ncu launch list of K&P, r02s: the
+// then matters more than the per-CTA prologue: the split is the one with the least estimated time
+// ceil(waves) * (chunk + c0), chunk in UNITS of `per_tile` to a tile (1 for the flat kernel; 4 for the lattice kernel, whose
+// chunks are multiples of a quarter tile), c0 ~ prologue + epilogue of a CTA in tiles (ncu launch list of K&P, r02s: the
 // wake sweeps of a 4 000-node wake ran 7 splits x 15 target tiles = 105 CTAs on 296 slots for 106 us; 5e7 pairs are 53 us
 // of the whole machine).  Returns 0 when the sweep is not small (the caller's search for whole waves applies).
-int plan_small_split(long long target_tiles, long long src_tiles, long long slots) {
+int plan_small_split(long long target_tiles, long long src_tiles, long long slots, int per_tile = 1) {
   const long long by4 = std::max(1LL, src_tiles / 4);
-  if (target_tiles * by4 >= 2 * slots || src_tiles <= 1) return 0;
-  const double c0 = 0.3;
+  if (target_tiles * by4 >= 2 * slots || src_tiles * per_tile <= 1) return 0;
+  const double c0 = kSmallC0 * per_tile;
+  const long long units = src_tiles * per_tile;
   double best = 1e300;
   int best_s = 1;
-  const long long max_split = std::min(src_tiles, 256LL);
+  const long long max_split = std::min(units, 256LL);
   for (long long s = 1; s <= max_split; ++s) {
-    const long long chunk = (src_tiles + s - 1) / s, real = (src_tiles + chunk - 1) / chunk;
+    const long long chunk = (units + s - 1) / s, real = (units + chunk - 1) / chunk;
     if (real != s) continue;
     const double waves = (double)target_tiles * (double)real / (double)slots;
     const double cost = std::ceil(waves - 1e-9) * ((double)chunk + c0);
@@ -534,14 +537,17 @@ bool lat_shape_exists(int W, int T) {
 }
 
 // Source splits of the lattice kernel: whole waves of (SMs x resident CTAs), chunks of >= 4 tiles when possible.
-int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad, bool dual = false) {
+// *unit = the records a chunk is a multiple of: the granule for a small sweep or a tuned split, else the tile
+int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad, bool dual, int* unit) {
+  *unit = vlc::lat_granule(W);
   if (c->tune_nsplit > 0) return c->tune_nsplit;
   const long long tiles = n_lat_pad / lat_tile_of(W);
   const long long ttiles = (m + (long long)kLatThreads * T - 1) / ((long long)kLatThreads * T);
   const int occ = dual ? c->occ_dual[W] : c->occ_lat[W][T];
   const long long slots = (long long)c->sm_count * (occ > 0 ? occ : 2);
-  const int small = plan_small_split(ttiles, tiles, slots);
+  const int small = plan_small_split(ttiles, tiles, slots, lat_tile_of(W) / vlc::lat_granule(W));
   if (small > 0) return small;
+  *unit = lat_tile_of(W);
   long long max_split = tiles / 4;
   if (max_split < 1) max_split = 1;
   if (max_split > 256) max_split = 256;
@@ -586,10 +592,11 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
       const long long slots = (long long)c->sm_count * (c->occ_lat[W][p.T] > 0 ? c->occ_lat[W][p.T] : 2);
       if (plan_small_split(tt, tiles, slots) > 0) p.T = 1;
     }
-    p.ns = plan_lattice_split(c, W, p.T, m, n_pad, dual);
-    const long long chunk_tiles = (tiles + p.ns - 1) / p.ns;
-    p.ns = (int)((tiles + chunk_tiles - 1) / chunk_tiles);
-    p.chunk = chunk_tiles * lat_tile_of(W);
+    int unit = 0;
+    p.ns = plan_lattice_split(c, W, p.T, m, n_pad, dual, &unit);
+    const long long units = n_pad / unit, per = (units + p.ns - 1) / p.ns;
+    p.ns = (int)((units + per - 1) / per);
+    p.chunk = per * unit;
     return p;
   };
   const bool dual = s.may_dual;
@@ -1285,6 +1292,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     release(r.sec);
     release(r.loads);
     release(r.LU);
+    release(r.Ainv);
     if (r.d_ipiv) cudaFree(r.d_ipiv);
     if (r.d_info) cudaFree(r.d_info);
   }
@@ -1958,14 +1966,25 @@ extern "C" int vlc_rotor_calcAIC(vlc_ctx* c, int ir, double* AIC_out) {
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   c->launches++;
   if (info != 0) return fail(c, VLC_ERR_SINGULAR, "Matrix is numerically singular!");  // libMath.f90:73
+  // AIC_inv = inv2(AIC) once (classdef.f90:4178, libMath.f90:48-83: getrf + getri); here getrs on the identity
+  const size_t NN = (size_t)N * N;
+  if ((rc = reserve(c, r->Ainv, NN))) return rc;
+  vlc::identity_kernel<<<blocks_for((long long)NN, 256), 256, 0, c->stream>>>(N, r->Ainv.p);
+  CUDA_OK(c, cudaGetLastError());
+  c->launches++;
+  st = cusolverDnDgetrs(c->solver, CUBLAS_OP_N, N, N, r->LU.p, N, r->d_ipiv, r->Ainv.p, N, r->d_info);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(c, VLC_ERR_CUDA, "cusolverDnDgetrs failed: " + std::to_string((int)st));
+  c->launches++;
   r->factored = true;
   return VLC_OK;
 }
 
 namespace {
-int solve_dev(vlc_ctx* c, Rotor* r, double* dB, int nrhs) {
-  cusolverStatus_t st = cusolverDnDgetrs(c->solver, CUBLAS_OP_N, r->N, nrhs, r->LU.p, r->N, r->d_ipiv, dB, r->N, r->d_info);
-  if (st != CUSOLVER_STATUS_SUCCESS) return fail(c, VLC_ERR_CUDA, "cusolverDnDgetrs failed: " + std::to_string((int)st));
+// gamVec = AIC_inv . RHS: the reference's per-step operation (main.f90:190, :596), one launch
+int solve_dev(vlc_ctx* c, Rotor* r, const double* d_rhs, double* d_gam) {
+  dim3 block(vlc::kGemvRows, vlc::kGemvSlices, 1);
+  vlc::ainv_gemv_kernel<<<blocks_for(r->N, vlc::kGemvRows), block, 0, c->stream>>>(r->N, r->Ainv.p, d_rhs, d_gam);
+  CUDA_OK(c, cudaGetLastError());
   c->launches++;
   return VLC_OK;
 }
@@ -1979,10 +1998,10 @@ extern "C" int vlc_rotor_solve(vlc_ctx* c, int ir, const double* RHS, double* ga
   if (!r) return VLC_ERR_STATE;
   if (!r->factored) return fail(c, VLC_ERR_STATE, "vlc_rotor_solve before vlc_rotor_calcAIC");
   if (!RHS || !gamVec) return fail(c, VLC_ERR_ARG, "null pointer");
-  if ((rc = reserve(c, c->stage_V, (size_t)r->N))) return rc;
+  if ((rc = reserve(c, c->stage_V, 2 * (size_t)r->N))) return rc;
   CUDA_OK(c, cudaMemcpyAsync(c->stage_V.p, RHS, sizeof(double) * r->N, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = solve_dev(c, r, c->stage_V.p, 1))) return rc;
-  CUDA_OK(c, cudaMemcpyAsync(gamVec, c->stage_V.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = solve_dev(c, r, c->stage_V.p, c->stage_V.p + r->N))) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(gamVec, c->stage_V.p + r->N, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }
@@ -1996,12 +2015,7 @@ extern "C" int vlc_rotor_get_AIC_inv(vlc_ctx* c, int ir, double* AIC_inv) {
   if (!r->factored) return fail(c, VLC_ERR_STATE, "vlc_rotor_get_AIC_inv before vlc_rotor_calcAIC");
   if (!AIC_inv) return fail(c, VLC_ERR_ARG, "null pointer");
   const size_t NN = (size_t)r->N * r->N;
-  if ((rc = reserve(c, c->scratch, NN))) return rc;
-  vlc::identity_kernel<<<blocks_for((long long)NN, 256), 256, 0, c->stream>>>(r->N, c->scratch.p);
-  CUDA_OK(c, cudaGetLastError());
-  c->launches++;
-  if ((rc = solve_dev(c, r, c->scratch.p, r->N))) return rc;
-  CUDA_OK(c, cudaMemcpyAsync(AIC_inv, c->scratch.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(AIC_inv, r->Ainv.p, sizeof(double) * NN, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VLC_OK;
 }
@@ -2788,8 +2802,7 @@ extern "C" int vlc_rotor_solve_map_gam(vlc_ctx* c, int ir, double* gamVec_out) {
   if (!r) return VLC_ERR_STATE;
   if (!r->factored) return fail(c, VLC_ERR_STATE, "vlc_rotor_solve_map_gam before vlc_rotor_calcAIC");
   if (!r->have_rhs) return fail(c, VLC_ERR_STATE, "vlc_rotor_solve_map_gam before vlc_rotor_calc_RHS");
-  CUDA_OK(c, cudaMemcpyAsync(r->gamvec.p, r->rhs.p, sizeof(double) * r->N, cudaMemcpyDeviceToDevice, c->stream));
-  if ((rc = solve_dev(c, r, r->gamvec.p, 1))) return rc;
+  if ((rc = solve_dev(c, r, r->rhs.p, r->gamvec.p))) return rc;
   vlc::cp_map_gam_kernel<<<blocks_for(r->N, 128), 128, 0, c->stream>>>(r->nb, r->nc * r->ns, r->nbConvect, r->axisym, r->gamvec.p, r->wiP.p);
   CUDA_OK(c, cudaGetLastError());
   c->launches++;

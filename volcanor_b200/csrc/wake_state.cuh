@@ -135,6 +135,30 @@ __global__ void identity_kernel(int N, double* __restrict__ A) {
   A[i] = ((i % N) == (i / N)) ? 1.0 : 0.0;
 }
 
+// gamVec = AIC_inv . RHS (main.f90:190, :596: matmulAX = DGEMV 'N', libMath.f90:105-122), A column-major N x N.
+// One thread per (row, column slice): kGemvSlices partial sums over contiguous column ranges, each accumulated in column
+// order like DGEMV's axpy sweep, combined in slice order -- a fixed order, independent of the launch.
+constexpr int kGemvRows = 32;
+constexpr int kGemvSlices = 8;
+__global__ void __launch_bounds__(kGemvRows* kGemvSlices)
+    ainv_gemv_kernel(int N, const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ double part[kGemvSlices][kGemvRows];
+  const int i = blockIdx.x * kGemvRows + threadIdx.x, s = threadIdx.y;
+  const int per = (N + kGemvSlices - 1) / kGemvSlices;
+  const int j0 = s * per, j1 = min(N, j0 + per);
+  double acc = 0.0;
+  if (i < N)
+    for (int j = j0; j < j1; ++j) acc = fma(A[(size_t)j * N + i], x[j], acc);
+  part[s][threadIdx.x] = acc;
+  __syncthreads();
+  if (s == 0 && i < N) {
+    double t = part[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < kGemvSlices; ++k) t += part[k][threadIdx.x];
+    y[i] = t;
+  }
+}
+
 // FP64 roofline denominator: kPeakChains independent register-resident DFMA chains per thread.
 constexpr int kPeakChains = 8;
 constexpr int kPeakUnroll = 16;

@@ -111,7 +111,7 @@ class CaseDriver:
             pass
 
 
-def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False, nsplit: int = 0) -> dict:
+def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False, nsplit: int = 0, stats: bool = False) -> dict:
     if isinstance(case_dir, dict):          # an already parsed case ({"name", "config", "geom"}: what read_case returns)
         case, case_dir = case_dir, Path(".")
     elif str(case_dir).endswith(".json"):   # the same, stored as JSON (tests/golden/*.json: the shipped cases, parsed once)
@@ -123,6 +123,8 @@ def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False, nsp
     if nsplit:
         ctx.set_tuning(0, nsplit)   # a fixed source split: a target's summation order no longer depends on the launch it is in
     drv = CaseDriver(case, ctx)
+    if stats:
+        ctx.sweep_stats(1)
     t0 = time.perf_counter()
     drv.init()
     n = drv.info()["nt"] if nt <= 0 else min(nt, drv.info()["nt"])
@@ -142,10 +144,18 @@ def run(case_dir, nt: int = 0, out=None, gpus: int = 1, quiet: bool = False, nsp
            "launches": ctx.launch_count, "gpus": gpus, "out": str(outdir), "ignored_keys": drv.ignored,
            "stage_seconds": drv.stage_seconds(),
            "final": [drv.force_nondim(ir).tolist() for ir in range(drv.nr)]}
+    if stats:   # device time and FP64-pipe use of the sweeps (vlc_sweep_stats: one event pair per launch)
+        st, (peak, _) = ctx.sweep_stats(-1), ctx.measure_fp64_peak()
+        res["sweeps"] = {k: {"launches": v["launches"], "ms": v["sweep_ms"], "pairs": v["sweep_pairs"],
+                             "pipe_frac": (v["sweep_fp64_instr"] * 2 / (v["sweep_ms"] * 1e-3) / peak) if v["sweep_ms"] > 0 else 0.0}
+                         for k, v in st.items()}
     if not quiet:
         print(f"{case['name']}: {n} steps in {t2 - t1:.2f} s ({res['timesteps_per_s']:.1f} timesteps/s, {ctx.launch_count / max(n, 1):.0f} "
               f"kernel launches per step) on {gpus} GPU(s); wrote {outdir}/rNNForceNonDim.csv")
         print("  host time per stage [s]: " + ", ".join(f"{k} {v:.3f}" for k, v in res["stage_seconds"].items()))
+        for k, v in res.get("sweeps", {}).items():
+            print(f"  sweeps led by {k}: {v['launches']} launches, {v['ms'] * 1e-3:.3f} s on the device, {v['pairs']:.3e} pair "
+                  f"interactions, FP64 pipe {100 * v['pipe_frac']:.1f} %")
     drv.close()
     ctx.close()
     return res
@@ -160,8 +170,9 @@ def main(argv=None):
     ap.add_argument("--nsplit", type=int, default=0,
                     help="fixed number of source splits per sweep (default: chosen per launch): makes the history independent of "
                          "--gpus bit for bit")
+    ap.add_argument("--stats", action="store_true", help="time every sweep on the device (vlc_sweep_stats) and print the totals")
     args = ap.parse_args(argv)
-    run(args.case_dir, args.nt, args.out, args.gpus, nsplit=args.nsplit)
+    run(args.case_dir, args.nt, args.out, args.gpus, nsplit=args.nsplit, stats=args.stats)
     return 0
 
 
