@@ -409,28 +409,38 @@ def main():
         tgt_bytes = 0
         out_near = [[np.zeros((r["ns"] + 1, r["nNwake"], 3)) for _ in range(r["nb"])] for r in hrot]
         out_far = [[np.zeros((r["nFwake"], 3)) for _ in range(r["nb"])] for r in hrot]
+        # the function result of one call (libCommon.f90:124, :186): one array per shape, reused like the caller's temporary
+        tmp_near = {(r["ns"], r["nNwake"]): np.zeros((r["ns"] + 1, r["nNwake"], 3)) for r in hrot}
+        tmp_far = {r["nFwake"]: np.zeros((r["nFwake"], 3)) for r in hrot}
+
+        e2e_host = {"put_s": 0.0, "vind_s": 0.0}
 
         def e2e_sweep():
             """main.f90:814-841 as the shim executes it: refresh the device copies of every blade's records, then per
             target blade and source rotor one vind_onNwake_byRotor and one vind_onFwake_byRotor, summed on the host."""
             nonlocal tgt_bytes
             tgt_bytes = 0
+            tp = time.perf_counter()
             for k, r in enumerate(hrot):
                 for ib in range(r["nb"]):
                     ectx.rotor_put_nwake(nr + k, ib, r["waN"][ib])
                     if r["nFwake"]:
                         ectx.rotor_put_fwake(nr + k, ib, r["waF"][ib])
+            tv = time.perf_counter()
+            e2e_host["put_s"] += tv - tp
             for k, r in enumerate(hrot):
                 for ib in range(r["nb"]):
                     vn, vf = out_near[k][ib], out_far[k][ib]
                     vn[...] = 0.0
                     vf[...] = 0.0
                     for j in range(nr):
-                        vn += ectx.vind_onNwake_byRotor(nr + j, r["waN"][ib], r["nNwake"], r["ns"], r["nNwake"])
+                        vn += ectx.vind_onNwake_byRotor(nr + j, r["waN"][ib], r["nNwake"], r["ns"], r["nNwake"],
+                                                        out=tmp_near[(r["ns"], r["nNwake"])])
                         tgt_bytes += 24 * r["nNwake"] * (r["ns"] + 1)
                         if r["nFwake"]:
-                            vf += ectx.vind_onFwake_byRotor(nr + j, r["waF"][ib], r["nFwake"])
+                            vf += ectx.vind_onFwake_byRotor(nr + j, r["waF"][ib], r["nFwake"], out=tmp_far[r["nFwake"]])
                             tgt_bytes += 24 * r["nFwake"]
+            e2e_host["vind_s"] += time.perf_counter() - tv
 
         def e2e_step():
             e2e_sweep()        # current wake
@@ -438,18 +448,25 @@ def main():
 
         e2e_step()
         barrier()
+        e2e_host["put_s"] = e2e_host["vind_s"] = 0.0
+        ectx.sweep_stats(1)
         w0_ = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         barrier()
         w = reduce_max(time.perf_counter() - w0_)
+        est = ectx.sweep_stats(-1)
         e2e = {"value": pairs_step * args.steps / w, "unit": "pair-interactions/s",
                "h2d_bytes_per_step": int(2 * (h2d + tgt_bytes)), "d2h_bytes_per_step": int(2 * tgt_bytes),
                "call": "per wake sweep (2 per time step): vlc_rotor_put_nwake + vlc_rotor_put_fwake of every blade (the reference's "
                        "400-byte Nwake_class / 104-byte Fwake_class records, pinned host memory), then per (target blade, source "
                        "rotor) vlc_vind_onNwake_byRotor + vlc_vind_onFwake_byRotor (libCommon.f90:114-211) with host target records "
                        "in and host velocity arrays out, summed over source rotors on the host like main.f90:817-826",
-               "calls_per_step": int(2 * sum(r["nb"] for r in hrot) * nr * 2), "ms_per_step": 1e3 * w / args.steps}
+               "calls_per_step": int(2 * sum(r["nb"] for r in hrot) * nr * 2), "ms_per_step": 1e3 * w / args.steps,
+               "breakdown_ms_per_step": {"host_in_put_calls": 1e3 * e2e_host["put_s"] / args.steps,
+                                         "host_in_vind_calls": 1e3 * e2e_host["vind_s"] / args.steps,
+                                         "device_in_sweeps": sum(v["sweep_ms"] for v in est.values()) / args.steps,
+                                         "sweeps": int(sum(v["launches"] for v in est.values()) / args.steps)}}
         # velocities of all targets in the order of synth.targets_all (per blade: near nodes, then far nodes)
         e2e_V = np.concatenate([np.concatenate([out_near[k][ib].reshape(-1, 3), out_far[k][ib]])
                                 for k, r in enumerate(hrot) for ib in range(r["nb"])])

@@ -461,18 +461,22 @@ class Context:
     def rotor_vind(self, ir, P, predicted=False):
         return self._points(self.lib.vlc_rotor_vind, P, ir, int(predicted))
 
-    def vind_onNwake_byRotor(self, ir, Nwake, rows, cols, ld, predicted=False, offset_records=0):
+    def vind_onNwake_byRotor(self, ir, Nwake, rows, cols, ld, predicted=False, offset_records=0, out=None):
         """Nwake: the parent record array (ld*cols*50 doubles); slice starts `offset_records` records in.
-        Returns (cols+1, rows, 3) = Fortran (3, rows, cols+1)."""
+        Returns (cols+1, rows, 3) = Fortran (3, rows, cols+1); `out`: a C-contiguous float64 array of that shape to fill."""
         Nwake = _f64(Nwake)
-        out = np.empty((cols + 1, rows, 3), dtype=np.float64)
+        if out is None:
+            out = np.empty((cols + 1, rows, 3), dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == 3 * rows * (cols + 1)
         self._ck(self.lib.vlc_vind_onNwake_byRotor(self.h, ir, Nwake.ctypes.data + 8 * VR_DOUBLES * offset_records,
                                                    rows, cols, ld, int(predicted), _ptr(out)))
         return out
 
-    def vind_onFwake_byRotor(self, ir, Fwake, rows, predicted=False, offset_records=0):
+    def vind_onFwake_byRotor(self, ir, Fwake, rows, predicted=False, offset_records=0, out=None):
         Fwake = _f64(Fwake)
-        out = np.empty((rows, 3), dtype=np.float64)
+        if out is None:
+            out = np.empty((rows, 3), dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == 3 * rows
         self._ck(self.lib.vlc_vind_onFwake_byRotor(self.h, ir, Fwake.ctypes.data + 8 * FWAKE_DOUBLES * offset_records,
                                                    rows, int(predicted), _ptr(out)))
         return out

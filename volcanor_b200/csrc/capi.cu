@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -152,6 +153,7 @@ struct vlc_ctx {
   size_t flag_cap = 0;
   std::vector<Rotor> rotors;
   cusolverDnHandle_t solver = nullptr;
+  vlc::grp::Workers* host_pool = nullptr;  // host_parallel
   DevBuf solver_work;
   int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
   // multi-GPU data plane (group.hpp): this context's place in the target partition, its NCCL communicator (library-owned),
@@ -707,6 +709,35 @@ int allgather_slots(vlc_ctx* c, double* buf, size_t cnt, const std::function<dou
   return fail(c, VLC_ERR_STATE, "world > 1 without a communicator (vlc_comm_init_rank) or a group (vlc_create_multi)");
 }
 
+void host_parallel(vlc_ctx* c, long long n, const std::function<void(long long, long long)>& fn);
+
+// VLC_TIMERS=1: host wall time of the phases of the host-buffer calls, printed at vlc_destroy (a debugging aid: where the
+// time of a synchronous per-sweep hand-over goes besides the sweep itself)
+struct HostTimers {
+  bool on = std::getenv("VLC_TIMERS") != nullptr;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  long long n[6] = {0, 0, 0, 0, 0, 0};
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  ~HostTimers() {
+    if (!on) return;
+    static const char* name[6] = {"gather targets", "pack (enqueue)", "h2d + sweep (enqueue)", "d2h + wait", "(unused)", "put (upload)"};
+    for (int k = 0; k < 6; ++k)
+      if (n[k]) std::fprintf(stderr, "[vlc timers] %-22s %8lld calls %10.3f ms total %8.1f us each\n", name[k], n[k], 1e3 * s[k], 1e6 * s[k] / n[k]);
+  }
+};
+HostTimers g_timers;
+struct TimerScope {
+  int k;
+  double t0;
+  explicit TimerScope(int k_) : k(k_), t0(g_timers.on ? HostTimers::now() : 0.0) {}
+  ~TimerScope() {
+    if (g_timers.on) {
+      g_timers.s[k] += HostTimers::now() - t0;
+      g_timers.n[k]++;
+    }
+  }
+};
+
 // host-buffer sweep: H2D targets, sweep, D2H velocities (synchronous).  With world > 1 the call is COLLECTIVE (every
 // member / rank makes it with the same arguments) and each takes its contiguous slice of the targets against all
 // sources (libCommon.f90:132-139 is a parallel loop over targets): the members of an in-process group write their
@@ -728,14 +759,18 @@ int sweep_host(vlc_ctx* c, const double* src, long long n_pad, long long m, cons
   if (rc) return rc;
   double* dV = c->stage_V.p + (gather ? 3 * (size_t)sh.per * c->rank : 0);
   if (ml > 0) {
+    TimerScope ts(2);
     CUDA_OK(c, cudaMemcpyAsync(c->stage_P.p, P + 3 * sh.lo, sizeof(double) * 3 * (size_t)ml, cudaMemcpyHostToDevice, c->stream));
     rc = shared ? sweep_shared(c, *shared, ml, c->stage_P.p, dV) : sweep(c, src, n_pad, ml, c->stage_P.p, dV);
     if (rc) return rc;
   }
+  TimerScope ts(3);
   if (gather) {
     if ((rc = allgather_slots(c, c->stage_V.p, 3 * (size_t)sh.per, nullptr))) return rc;
     CUDA_OK(c, cudaMemcpyAsync(V, c->stage_V.p, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
   } else if (ml > 0) {
+    // straight into the caller's (pageable) array: staging through pinned scratch + a threaded copy was measured and is
+    // no faster at 0.7 MB per call (r02z)
     CUDA_OK(c, cudaMemcpyAsync(V + 3 * sh.lo, dV, sizeof(double) * 3 * (size_t)ml, cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -754,6 +789,33 @@ int host_targets(vlc_ctx* c, size_t n, double** out) {
   }
   *out = c->host_P;
   return VLC_OK;
+}
+
+// Host loops over the caller's records (one 24-byte read per 400-byte record: a cache line per target) on a few
+// persistent threads: at 3e4 targets per call the single-threaded gather was 0.27 ms of GPU idle time per call
+// (bench.py e2e breakdown, r02w).  fn(lo, hi) over [0, n).
+void host_parallel(vlc_ctx* c, long long n, const std::function<void(long long, long long)>& fn) {
+  if (n < 8192) {
+    fn(0, n);
+    return;
+  }
+  if (!c->host_pool) {
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    const unsigned members = c->world > 1 && c->group ? (unsigned)c->world : 1u;  // members of a group gather concurrently
+    int nt = (int)(hc / (2 * members));
+    nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+    c->host_pool = new vlc::grp::Workers(nt);
+  }
+  const int nt = c->host_pool->size();
+  if (nt <= 1) {
+    fn(0, n);
+    return;
+  }
+  c->host_pool->run([&](int k) {
+    fn(n * k / nt, n * (k + 1) / nt);
+    return 0;
+  });
 }
 
 int check_set(vlc_ctx* c, int set) {
@@ -1297,6 +1359,8 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     if (r.d_info) cudaFree(r.d_info);
   }
   if (c->solver) cusolverDnDestroy(c->solver);
+  delete c->host_pool;
+  c->host_pool = nullptr;
   if (c->host_P) cudaFreeHost(c->host_P);
   for (int k = 0; k < 2; ++k) {
     if (c->stage_h[k]) cudaFreeHost(c->stage_h[k]);
@@ -1778,6 +1842,7 @@ extern "C" int vlc_rotor_put_nwake(vlc_ctx* c, int ir, int ib, int predicted, co
   r->stale_near[s][ib] = r->rowNear;
   if (nact <= 0) return VLC_OK;
   if ((rc = reserve(c, r->waN[s], per * r->nb))) return rc;
+  TimerScope ts(5);
   const size_t pitch = (size_t)r->nNwake * vlc::kVr * sizeof(double);
   CUDA_OK(c, cudaMemcpy2DAsync(r->waN[s].p + per * ib + (size_t)first * vlc::kVr, pitch, waN + (size_t)first * vlc::kVr, pitch,
                                (size_t)nact * vlc::kVr * sizeof(double), (size_t)r->ns, cudaMemcpyHostToDevice, c->stream));
@@ -1874,7 +1939,10 @@ extern "C" int vlc_rotor_vind(vlc_ctx* c, int ir, int predicted, int64_t m, cons
   Rotor* r = get_rotor(c, ir);
   if (!r) return VLC_ERR_STATE;
   const int s = predicted ? 1 : 0;
-  if ((rc = pack_rotor(c, *r, s))) return rc;
+  {
+    TimerScope ts(1);
+    if ((rc = pack_rotor(c, *r, s))) return rc;
+  }
   const SourceSet& v = r->comb[s];
   return sweep_host(c, v.rec.p, v.n_pad, m, P, V, (v.has_shared && c->shared_nodes) ? &v : nullptr);
 }
@@ -1894,14 +1962,16 @@ extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake,
     if (rc0) return rc0;
     if ((rc0 = host_targets(c, (size_t)3 * rows * (cols + 1), &P))) return rc0;
   }
-  for (int j = 0; j < cols; ++j)
-    for (int i = 0; i < rows; ++i) {
-      const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * j);
-      std::memcpy(&P[3 * ((size_t)i + (size_t)rows * j)], rec + VLC_VF_DOUBLES * 1, 3 * sizeof(double));
-    }
-  for (int i = 0; i < rows; ++i) {
-    const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * (cols - 1));
-    std::memcpy(&P[3 * ((size_t)i + (size_t)rows * cols)], rec + VLC_VF_DOUBLES * 2, 3 * sizeof(double));
+  {
+    TimerScope ts(0);
+    host_parallel(c, (long long)rows * (cols + 1), [&](long long lo, long long hi) {
+      for (long long q = lo; q < hi; ++q) {
+        const long long j = q / rows, i = q - j * rows;
+        const bool last = j == cols;  // corner 3 of the last column
+        const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * (last ? cols - 1 : j));
+        std::memcpy(&P[3 * (size_t)q], rec + VLC_VF_DOUBLES * (last ? 2 : 1), 3 * sizeof(double));
+      }
+    });
   }
   return vlc_rotor_vind(c, ir, predicted, (int64_t)rows * (cols + 1), P, vindArray);
 }
@@ -1919,7 +1989,9 @@ extern "C" int vlc_vind_onFwake_byRotor(vlc_ctx* c, int ir, const double* Fwake,
     if (rc0) return rc0;
     if ((rc0 = host_targets(c, (size_t)3 * rows, &P))) return rc0;
   }
-  for (int i = 0; i < rows; ++i) std::memcpy(&P[3 * (size_t)i], Fwake + (size_t)VLC_FWAKE_DOUBLES * i, 3 * sizeof(double));
+  host_parallel(c, rows, [&](long long lo, long long hi) {
+    for (long long i = lo; i < hi; ++i) std::memcpy(&P[3 * (size_t)i], Fwake + (size_t)VLC_FWAKE_DOUBLES * i, 3 * sizeof(double));
+  });
   return vlc_rotor_vind(c, ir, predicted, rows, P, vindArray);
 }
 
