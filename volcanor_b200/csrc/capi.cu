@@ -24,6 +24,7 @@
 #include "wake_records.cuh"
 #include "cp_stage.cuh"
 #include "group.hpp"
+#include "plan.hpp"
 
 namespace {
 
@@ -40,7 +41,6 @@ constexpr int kStages = 3;     // TMA ring depth
 // (sweeps with at most one CTA of targets use T=1, sweep_shared).
 constexpr double kLatCost[5] = {0.0, 1.000, 0.919, 0.932, 0.885};
 constexpr int kLatBestT[5] = {0, 3, 2, 2, 2};
-constexpr double kSmallC0 = 0.3;  // fixed cost of a CTA of a small sweep, in source tiles (plan_small_split)
 
 std::string g_create_error;
 
@@ -317,33 +317,6 @@ int query_occ(vlc_ctx* c, int* out) {
   return VLC_OK;
 }
 
-// Source split of a SMALL sweep: one that cannot fill the machine for two waves with chunks of >= 4 tiles.  Parallelism
-// then matters more than the per-CTA prologue: the split is the one with the least estimated time
-// ceil(waves) * (chunk + c0), chunk in UNITS of `per_tile` to a tile (1 for the flat kernel; 4 for the lattice kernel, whose
-// chunks are multiples of a quarter tile), c0 ~ prologue + epilogue of a CTA in tiles (ncu launch list of K&P, r02s: the
-// wake sweeps of a 4 000-node wake ran 7 splits x 15 target tiles = 105 CTAs on 296 slots for 106 us; 5e7 pairs are 53 us
-// of the whole machine).  Returns 0 when the sweep is not small (the caller's search for whole waves applies).
-int plan_small_split(long long target_tiles, long long src_tiles, long long slots, int per_tile = 1) {
-  const long long by4 = std::max(1LL, src_tiles / 4);
-  if (target_tiles * by4 >= 2 * slots || src_tiles * per_tile <= 1) return 0;
-  const double c0 = kSmallC0 * per_tile;
-  const long long units = src_tiles * per_tile;
-  double best = 1e300;
-  int best_s = 1;
-  const long long max_split = std::min(units, 256LL);
-  for (long long s = 1; s <= max_split; ++s) {
-    const long long chunk = (units + s - 1) / s, real = (units + chunk - 1) / chunk;
-    if (real != s) continue;
-    const double waves = (double)target_tiles * (double)real / (double)slots;
-    const double cost = std::ceil(waves - 1e-9) * ((double)chunk + c0);
-    if (cost < best * (1.0 - 1e-9)) {
-      best = cost;
-      best_s = (int)s;
-    }
-  }
-  return best_s;
-}
-
 // Launch shape: T targets per thread and nsplit source splits.
 void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, int* nsplit_out) {
   const long long src_tiles = n_pad / kTile;
@@ -357,35 +330,16 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
     if (T == 2) {  // still too small at two targets per thread: one per thread, twice the CTAs
       const long long slots2 = (long long)c->sm_count * (c->occ[2] > 0 ? c->occ[2] : 3);
       const long long tiles2 = (m + kThreads * 2 - 1) / (kThreads * 2);
-      if (plan_small_split(tiles2, src_tiles, slots2) > 0) T = 1;
+      if (vlc::plan::small_split(tiles2, src_tiles, slots2) > 0) T = 1;
     }
   }
   int nsplit = c->tune_nsplit;
   if (nsplit < 1) {
     const long long slots = (long long)c->sm_count * (c->occ[T] > 0 ? c->occ[T] : 3);
     const long long tiles = (m + (long long)kThreads * T - 1) / ((long long)kThreads * T);
-    // candidates: keep chunks >= 4 tiles when possible, cap the partial buffer
-    long long max_split = src_tiles / 4;
-    if (max_split < 1) max_split = 1;
-    if (max_split > 256) max_split = 256;
     const long long cap_by_mem = (long long)((size_t)1 << 31) / (3 * (m > 0 ? m : 1) * 8) + 1;  // <= 2 GiB partials
-    if (max_split > cap_by_mem) max_split = cap_by_mem;
-    double best = -1.0;
-    int best_s = plan_small_split(tiles, src_tiles, slots);
-    for (long long s = 1; s <= max_split && best_s == 0; ++s) {
-      const long long chunk_tiles = (src_tiles + s - 1) / s;
-      const long long real_s = (src_tiles + chunk_tiles - 1) / chunk_tiles;
-      const double ctas = (double)tiles * (double)real_s;
-      const double waves = ctas / (double)slots;
-      const double eff = waves / (double)(long long)(waves + 0.999999);
-      // mild preference for more, smaller CTAs once efficiency saturates (better tail), and for fewer splits
-      const double score = eff - 1e-4 * (double)s;
-      if (waves >= 1.0 ? (score > best + 1e-9) : (eff > best + 1e-9)) {
-        best = (waves >= 1.0) ? score : eff;
-        best_s = (int)s;
-      }
-      if (waves >= 8.0 && eff > 0.995) break;  // whole waves matter: equal-work CTAs leave a (1 - eff) tail idle
-    }
+    int best_s = vlc::plan::small_split(tiles, src_tiles, slots);
+    if (best_s == 0) best_s = vlc::plan::wave_split(tiles, src_tiles, slots, cap_by_mem);
     nsplit = best_s > 0 ? best_s : 1;
   }
   if (nsplit > src_tiles) nsplit = (int)(src_tiles > 0 ? src_tiles : 1);
@@ -401,10 +355,9 @@ struct FlatPlan {
 FlatPlan plan_flat(const vlc_ctx* c, long long m, long long n_pad) {
   FlatPlan p;
   choose_shape(c, m, n_pad, &p.T, &p.nsplit);
-  const long long src_tiles = n_pad / kTile;
-  const long long chunk_tiles = (src_tiles + p.nsplit - 1) / p.nsplit;
-  p.nsplit = (int)((src_tiles + chunk_tiles - 1) / chunk_tiles);
-  p.chunk = chunk_tiles * kTile;
+  const vlc::plan::Cut ct = vlc::plan::cut(n_pad, kTile, p.nsplit);
+  p.nsplit = ct.nsplit;
+  p.chunk = ct.chunk;
   return p;
 }
 
@@ -547,27 +500,11 @@ int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_
   const long long ttiles = (m + (long long)kLatThreads * T - 1) / ((long long)kLatThreads * T);
   const int occ = dual ? c->occ_dual[W] : c->occ_lat[W][T];
   const long long slots = (long long)c->sm_count * (occ > 0 ? occ : 2);
-  const int small = plan_small_split(ttiles, tiles, slots, lat_tile_of(W) / vlc::lat_granule(W));
+  const int small = vlc::plan::small_split(ttiles, tiles, slots, lat_tile_of(W) / vlc::lat_granule(W));
   if (small > 0) return small;
   *unit = lat_tile_of(W);
-  long long max_split = tiles / 4;
-  if (max_split < 1) max_split = 1;
-  if (max_split > 256) max_split = 256;
-  double best = -1.0;
-  int best_s = 1;
-  for (long long s = 1; s <= max_split; ++s) {
-    const long long chunk_tiles = (tiles + s - 1) / s;
-    const long long real_s = (tiles + chunk_tiles - 1) / chunk_tiles;
-    const double waves = (double)ttiles * (double)real_s / (double)slots;
-    const double eff = waves / (double)(long long)(waves + 0.999999);
-    const double score = (waves >= 1.0) ? eff - 1e-4 * (double)s : eff;
-    if (score > best + 1e-9) {
-      best = score;
-      best_s = (int)s;
-    }
-    if (waves >= 8.0 && eff > 0.995) break;  // whole waves matter: equal-work CTAs leave a (1 - eff) tail idle
-  }
-  return best_s;
+  const long long cap_by_mem = (long long)((size_t)1 << 31) / (3 * (m > 0 ? m : 1) * 8) + 1;  // <= 2 GiB partials
+  return vlc::plan::wave_split(ttiles, tiles, slots, cap_by_mem);
 }
 
 // Sweep over a set that also holds the shared-node form.  The launches are dispatched ON THE DEVICE by the set's flag so
@@ -592,13 +529,13 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
       // a sweep too small to fill the machine at T targets per thread: one target per thread, T times the CTAs
       const long long tt = (m + (long long)kLatThreads * p.T - 1) / ((long long)kLatThreads * p.T);
       const long long slots = (long long)c->sm_count * (c->occ_lat[W][p.T] > 0 ? c->occ_lat[W][p.T] : 2);
-      if (plan_small_split(tt, tiles, slots) > 0) p.T = 1;
+      if (vlc::plan::small_split(tt, tiles, slots) > 0) p.T = 1;
     }
     int unit = 0;
     p.ns = plan_lattice_split(c, W, p.T, m, n_pad, dual, &unit);
-    const long long units = n_pad / unit, per = (units + p.ns - 1) / p.ns;
-    p.ns = (int)((units + per - 1) / per);
-    p.chunk = per * unit;
+    const vlc::plan::Cut ct = vlc::plan::cut(n_pad, unit, p.ns);
+    p.ns = ct.nsplit;
+    p.chunk = ct.chunk;
     return p;
   };
   const bool dual = s.may_dual;
@@ -1964,8 +1901,11 @@ extern "C" int vlc_vind_onNwake_byRotor(vlc_ctx* c, int ir, const double* Nwake,
   }
   {
     TimerScope ts(0);
-    host_parallel(c, (long long)rows * (cols + 1), [&](long long lo, long long hi) {
-      for (long long q = lo; q < hi; ++q) {
+    // a member of a group / a rank of a communicator sweeps only its slice of the targets (sweep_host): gather that slice
+    const long long mt = (long long)rows * (cols + 1);
+    const vlc::grp::Shard sh = c->world > 1 ? vlc::grp::shard_range(mt, c->world, c->rank) : vlc::grp::shard_range(mt, 1, 0);
+    host_parallel(c, sh.count(), [&](long long lo, long long hi) {
+      for (long long q = sh.lo + lo; q < sh.lo + hi; ++q) {
         const long long j = q / rows, i = q - j * rows;
         const bool last = j == cols;  // corner 3 of the last column
         const double* rec = Nwake + (size_t)VLC_VR_DOUBLES * ((size_t)i + (size_t)ld * (last ? cols - 1 : j));
@@ -1989,8 +1929,10 @@ extern "C" int vlc_vind_onFwake_byRotor(vlc_ctx* c, int ir, const double* Fwake,
     if (rc0) return rc0;
     if ((rc0 = host_targets(c, (size_t)3 * rows, &P))) return rc0;
   }
-  host_parallel(c, rows, [&](long long lo, long long hi) {
-    for (long long i = lo; i < hi; ++i) std::memcpy(&P[3 * (size_t)i], Fwake + (size_t)VLC_FWAKE_DOUBLES * i, 3 * sizeof(double));
+  const vlc::grp::Shard shf = c->world > 1 ? vlc::grp::shard_range(rows, c->world, c->rank) : vlc::grp::shard_range(rows, 1, 0);
+  host_parallel(c, shf.count(), [&](long long lo, long long hi) {
+    for (long long i = shf.lo + lo; i < shf.lo + hi; ++i)
+      std::memcpy(&P[3 * (size_t)i], Fwake + (size_t)VLC_FWAKE_DOUBLES * i, 3 * sizeof(double));
   });
   return vlc_rotor_vind(c, ir, predicted, rows, P, vindArray);
 }
