@@ -61,6 +61,17 @@ def test_small_sweeps_are_split_for_parallelism(plib, ttiles, tiles, slots, per_
     assert ttiles * ns <= 2 * slots or chunk == unit or ns == 256
 
 
+def test_flat_sweep_of_the_headline_size_is_split_into_whole_waves(plib):
+    """The same-work sweep of bench.py (flat kernel, T = 4: 505 target tiles of 512, 7 815 source tiles of 128, 3 CTAs per
+    SM): 7 splits = 7.96 waves.  (A planner bug of r02t left such sweeps at ONE split = 1.14 waves: 806 instead of 678 ms.)"""
+    slots = 148 * 3
+    assert plib.plan_small_split(505, 7815, slots, 1) == 0
+    s = plib.plan_wave_split(505, 7815, slots, 347)
+    assert s == 7
+    waves = 505 * s / slots
+    assert waves / -(-waves // 1) > 0.99
+
+
 def test_a_sweep_that_fills_the_machine_is_not_small(plib):
     for ttiles, tiles in [(1009, 1955), (113, 391), (95, 175), (600, 8)]:
         assert plib.plan_small_split(ttiles, tiles, SLOTS, 4) == 0, (ttiles, tiles)
