@@ -652,13 +652,13 @@ void host_parallel(vlc_ctx* c, long long n, const std::function<void(long long, 
 // time of a synchronous per-sweep hand-over goes besides the sweep itself)
 struct HostTimers {
   bool on = std::getenv("VLC_TIMERS") != nullptr;
-  double s[6] = {0, 0, 0, 0, 0, 0};
-  long long n[6] = {0, 0, 0, 0, 0, 0};
+  double s[5] = {0, 0, 0, 0, 0};
+  long long n[5] = {0, 0, 0, 0, 0};
   static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   ~HostTimers() {
     if (!on) return;
-    static const char* name[6] = {"gather targets", "pack (enqueue)", "h2d + sweep (enqueue)", "d2h + wait", "(unused)", "put (upload)"};
-    for (int k = 0; k < 6; ++k)
+    static const char* name[5] = {"gather targets", "pack (enqueue)", "h2d + sweep (enqueue)", "d2h + wait", "put (upload)"};
+    for (int k = 0; k < 5; ++k)
       if (n[k]) std::fprintf(stderr, "[vlc timers] %-22s %8lld calls %10.3f ms total %8.1f us each\n", name[k], n[k], 1e3 * s[k], 1e6 * s[k] / n[k]);
   }
 };
@@ -1779,7 +1779,7 @@ extern "C" int vlc_rotor_put_nwake(vlc_ctx* c, int ir, int ib, int predicted, co
   r->stale_near[s][ib] = r->rowNear;
   if (nact <= 0) return VLC_OK;
   if ((rc = reserve(c, r->waN[s], per * r->nb))) return rc;
-  TimerScope ts(5);
+  TimerScope ts(4);
   const size_t pitch = (size_t)r->nNwake * vlc::kVr * sizeof(double);
   CUDA_OK(c, cudaMemcpy2DAsync(r->waN[s].p + per * ib + (size_t)first * vlc::kVr, pitch, waN + (size_t)first * vlc::kVr, pitch,
                                (size_t)nact * vlc::kVr * sizeof(double), (size_t)r->ns, cudaMemcpyHostToDevice, c->stream));
