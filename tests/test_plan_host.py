@@ -18,7 +18,7 @@ def plib():
     lib = C.CDLL(str(HERE / "libplan_host.so"))
     LL = C.c_longlong
     lib.plan_small_split.argtypes = [LL, LL, LL, C.c_int]
-    lib.plan_wave_split.argtypes = [LL, LL, LL, LL]
+    lib.plan_wave_split.argtypes = [LL, LL, LL, LL, C.c_int]
     lib.plan_cut.argtypes = [LL, LL, C.c_int, C.POINTER(C.c_int), C.POINTER(LL)]
     return lib
 
@@ -34,10 +34,10 @@ def test_headline_sweep_keeps_its_launch_shape(plib):
     of 256: not a small sweep; 12 splits = 40.9 waves, the shape of every profile of the round."""
     ttiles, tiles = (258176 + 255) // 256, 62560 // 32
     assert plib.plan_small_split(ttiles, tiles, SLOTS, 4) == 0
-    s = plib.plan_wave_split(ttiles, tiles, SLOTS, 347)
-    assert s == 12
-    ns, chunk = _cut(plib, 62560, 32, s)
-    assert ns == 12 and chunk % 32 == 0 and (ns - 1) * chunk < 62560 <= ns * chunk
+    s = plib.plan_wave_split(ttiles, tiles, SLOTS, 347, 4)
+    assert s == 12 and plib.plan_wave_split(ttiles, tiles, SLOTS, 347, 1) == 12
+    ns, chunk = _cut(plib, 62560, 8, s)
+    assert ns == 12 and chunk % 8 == 0 and (ns - 1) * chunk < 62560 <= ns * chunk
     waves = ttiles * ns / SLOTS
     assert waves / -(-waves // 1) > 0.99
 
@@ -66,10 +66,22 @@ def test_flat_sweep_of_the_headline_size_is_split_into_whole_waves(plib):
     SM): 7 splits = 7.96 waves.  (A planner bug of r02t left such sweeps at ONE split = 1.14 waves: 806 instead of 678 ms.)"""
     slots = 148 * 3
     assert plib.plan_small_split(505, 7815, slots, 1) == 0
-    s = plib.plan_wave_split(505, 7815, slots, 347)
+    s = plib.plan_wave_split(505, 7815, slots, 347, 1)
     assert s == 7
     waves = 505 * s / slots
     assert waves / -(-waves // 1) > 0.99
+
+
+def test_quarter_tile_units_reach_whole_waves_where_tiles_cannot(plib):
+    """A late caradonna step: 95 target tiles x 175 strip-record tiles on 296 slots.  In whole tiles the best fit is 3 splits
+    (285 CTAs, 0.963 of one wave); in quarter tiles 28 splits (2 660 CTAs = 8.99 waves) -- measured 1.5 % faster over the case
+    (profiles/r02v_small_cases.md, scan of fixed splits)."""
+    assert plib.plan_wave_split(95, 175, SLOTS, 256, 1) == 3
+    s = plib.plan_wave_split(95, 175, SLOTS, 256, 4)
+    waves = 95 * s / SLOTS
+    assert waves >= 8 and waves / -(-waves // 1) > 0.995
+    ns, chunk = _cut(plib, 175 * 32, 8, s)
+    assert ns == s and chunk >= 4 * 32
 
 
 def test_a_sweep_that_fills_the_machine_is_not_small(plib):
@@ -78,11 +90,12 @@ def test_a_sweep_that_fills_the_machine_is_not_small(plib):
 
 
 def test_wave_search_respects_the_partial_buffer_cap_and_chunk_floor(plib):
-    assert plib.plan_wave_split(1009, 1955, SLOTS, 5) <= 5          # caller's cap (2 GiB of partial sums)
-    assert plib.plan_wave_split(1009, 7, SLOTS, 256) == 1            # fewer than 8 tiles: one chunk
+    assert plib.plan_wave_split(1009, 1955, SLOTS, 5, 4) <= 5          # caller's cap (2 GiB of partial sums)
+    assert plib.plan_wave_split(1009, 7, SLOTS, 256, 4) == 1            # fewer than 8 tiles: one chunk
     for tiles in (16, 64, 391, 1955, 100000):
-        s = plib.plan_wave_split(113, tiles, SLOTS, 256)
-        assert 1 <= s <= min(256, max(1, tiles // 4))
+        for per_tile in (1, 4):
+            s = plib.plan_wave_split(113, tiles, SLOTS, 256, per_tile)
+            assert 1 <= s <= min(256, max(1, tiles // 4))
 
 
 @pytest.mark.parametrize("n_pad,unit,nsplit", [(62560, 32, 12), (62560, 8, 12), (128, 16, 5), (64, 64, 3), (4096, 128, 7), (32, 8, 100)])

@@ -492,7 +492,7 @@ bool lat_shape_exists(int W, int T) {
 }
 
 // Source splits of the lattice kernel: whole waves of (SMs x resident CTAs), chunks of >= 4 tiles when possible.
-// *unit = the records a chunk is a multiple of: the granule for a small sweep or a tuned split, else the tile
+// *unit = the records a chunk is a multiple of: the granule (a quarter tile)
 int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_lat_pad, bool dual, int* unit) {
   *unit = vlc::lat_granule(W);
   if (c->tune_nsplit > 0) return c->tune_nsplit;
@@ -500,11 +500,11 @@ int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_
   const long long ttiles = (m + (long long)kLatThreads * T - 1) / ((long long)kLatThreads * T);
   const int occ = dual ? c->occ_dual[W] : c->occ_lat[W][T];
   const long long slots = (long long)c->sm_count * (occ > 0 ? occ : 2);
-  const int small = vlc::plan::small_split(ttiles, tiles, slots, lat_tile_of(W) / vlc::lat_granule(W));
+  const int per_tile = lat_tile_of(W) / vlc::lat_granule(W);
+  const int small = vlc::plan::small_split(ttiles, tiles, slots, per_tile);
   if (small > 0) return small;
-  *unit = lat_tile_of(W);
   const long long cap_by_mem = (long long)((size_t)1 << 31) / (3 * (m > 0 ? m : 1) * 8) + 1;  // <= 2 GiB partials
-  return vlc::plan::wave_split(ttiles, tiles, slots, cap_by_mem);
+  return vlc::plan::wave_split(ttiles, tiles, slots, cap_by_mem, per_tile);
 }
 
 // Sweep over a set that also holds the shared-node form.  The launches are dispatched ON THE DEVICE by the set's flag so

@@ -44,17 +44,21 @@ inline int small_split(long long target_tiles, long long src_tiles, long long sl
   return best_s;
 }
 
-// Source split of a sweep that fills the machine: chunks of >= 4 tiles, at most `max_split` splits (the caller's cap on the
-// partial-sum buffer), the split whose CTA count is closest below a whole number of waves -- equal-work CTAs leave a
-// (1 - eff) tail idle -- with a mild preference for fewer splits.
-inline int wave_split(long long target_tiles, long long src_tiles, long long slots, long long max_split = 256) {
+// Source split of a sweep that fills the machine: chunks of >= 4 tiles (cut in units of `per_tile` to a tile, like
+// small_split), at most `max_split` splits (the caller's cap on the partial-sum buffer), the split whose CTA count is closest
+// below a whole number of waves -- equal-work CTAs leave a (1 - eff) tail idle -- with a mild preference for fewer splits.
+// Finer units reach more CTA counts: 95 target tiles x 175 source tiles (a late caradonna step) fit 296 slots as 3 splits
+// (0.963 of a wave) in tiles, as 28 splits (8.99 waves) in quarter tiles.
+inline int wave_split(long long target_tiles, long long src_tiles, long long slots, long long max_split = 256, int per_tile = 1) {
   long long cap = src_tiles / 4;
   cap = std::max(1LL, std::min(cap, std::min(max_split, 256LL)));
+  const long long units = src_tiles * per_tile;
   double best = -1.0;
   int best_s = 1;
   for (long long s = 1; s <= cap; ++s) {
-    const long long chunk_tiles = (src_tiles + s - 1) / s;
-    const long long real_s = (src_tiles + chunk_tiles - 1) / chunk_tiles;
+    const long long chunk = (units + s - 1) / s;
+    const long long real_s = (units + chunk - 1) / chunk;
+    if (real_s != s) continue;
     const double waves = (double)target_tiles * (double)real_s / (double)slots;
     const double eff = waves / (double)(long long)(waves + 0.999999);
     const double score = (waves >= 1.0) ? eff - 1e-4 * (double)s : eff;
