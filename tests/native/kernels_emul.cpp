@@ -201,10 +201,10 @@ static int lattice_strips(const double* waN, int nNwake, int ns, int i0, int nro
   const bool dual = (*unmergeable == 2);
   emul_launch(blocks_for(m, THREADS * T), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>,
               (const double*)lat.data(), chunk, npad, P, m, dual ? other.data() : parts.data() + at,
-              (const int*)unmergeable, 3, 0);
+              (const int*)unmergeable, 3, 0, 0);
   emul_launch(blocks_for(m, THREADS), (unsigned)real_split, THREADS, vlc::bs_lattice_kernel<W, 1, THREADS, 3, 1, true>,
               (const double*)lat.data(), chunk, npad, P, m, dual ? parts.data() + at : other.data(),
-              (const int*)unmergeable, 3, 2);
+              (const int*)unmergeable, 3, 2, 0);
   for (double v : other)
     if (v == v) return 4;  // the form that must not run wrote something
   *nslots += real_split;
@@ -305,9 +305,9 @@ int emul_lattice_vind_dispatch(int nsplit_flat, const double* waN, int nNwake, i
   // slots: [0] merged lattice, [1] flat remainder, [2] dual lattice, [3 ..] flat enumeration
   std::vector<double> parts((size_t)(3 + nb) * len, std::nan(""));
   emul_launch(blocks_for(m, THREADS * T), 1, THREADS, vlc::bs_lattice_kernel<W, T, THREADS, 3, 1>, (const double*)lat.data(), npad, npad,
-              P, m, parts.data(), (const int*)&flag, 3, 0);
+              P, m, parts.data(), (const int*)&flag, 3, 0, 0);
   emul_launch(blocks_for(m, THREADS), 1, THREADS, vlc::bs_lattice_kernel<W, 1, THREADS, 3, 1, true>, (const double*)lat.data(), npad,
-              npad, P, m, parts.data() + 2 * len, (const int*)&flag, 3, 2);
+              npad, P, m, parts.data() + 2 * len, (const int*)&flag, 3, 2, 0);
   emul_launch(blocks_for(m, THREADS * FT), 1, THREADS, vlc::bs_sweep_kernel<FT, THREADS, FTILE, 3, 1, false>, (const double*)rem.data(),
               rem_pad, rem_pad, P, m, parts.data() + len, (const int*)&flag, 1, 0);
   emul_launch(blocks_for(m, THREADS * FT), (unsigned)nb, THREADS, vlc::bs_sweep_kernel<FT, THREADS, FTILE, 3, 1, false>,

@@ -142,6 +142,52 @@ def test_group_resident_case_is_bit_identical_to_one_gpu(ctx, gctx, oracle, name
         assert dev.max() <= 1.0
 
 
+def test_group_shares_source_splits_of_the_collocation_point_stage(ctx, oracle, monkeypatch):
+    """SURVEY 8e, "RHS: shard sources and sum partials": with NCCL between distinct devices the collocation-point sweeps of a
+    group share their SOURCE splits out (each member a part of every slot range, all-reduce of the partial buffer, the same
+    fixed-order reduce) -- here forced for every sweep by VLC_RHS_SHARE_MIN_PAIRS=0.  The all-reduce adds zeros to the one
+    contribution of each slot, so the force history of a case is bit-identical to the one-GPU run and to a group that does
+    not share (the wake sweeps, sharded by targets, need the fixed split for that)."""
+    import torch
+    import volcanor_b200 as vb
+    from tests.test_gpu_resident import _resident_hooks, _step
+    import ctypes as C
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs NCCL between two devices")
+    fx = json.loads((GOLDEN / "elevateTest.json").read_text())
+
+    def run(c, nsteps=40):
+        c.set_tuning(0, 4)
+        try:
+            case = oracle.Case(fx)
+            lib, h = _resident_hooks(case, c)
+            lib.case_hooks_enable_cp.argtypes = [C.c_void_p]
+            assert lib.case_hooks_enable_cp(h) == 0, c.lib.vlc_last_error(c.h)
+            case.init()
+            n0 = c.launch_count
+            f = [case.force_nondim(0).copy()]
+            for it in range(nsteps):
+                _step(case, lib, h, c, it + 1)
+                f.append(case.force_nondim(0).copy())
+            lib.case_gpu_hooks_free(h)
+            return np.array(f), c.launch_count - n0
+        finally:
+            c.set_tuning(0, 0)
+
+    ref, _ = run(ctx)
+    out = {}
+    for share in ("0", "-1"):
+        monkeypatch.setenv("VLC_RHS_SHARE_MIN_PAIRS", share)
+        g = vb.Context(devices=[0, 1])
+        try:
+            assert g.comm_info()["transport"] == "nccl"
+            out[share] = run(g)
+        finally:
+            g.close()
+    assert np.array_equal(out["0"][0], ref) and np.array_equal(out["-1"][0], ref)
+    assert out["0"][1] > out["-1"][1], "no all-reduce was launched: the source splits were not shared"
+
+
 def test_group_refuses_device_pointer_entry_points(gctx):
     """A device pointer belongs to one device: the tier-3 / _dev entry points return VLC_ERR_STATE on a group handle."""
     import torch

@@ -118,8 +118,10 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
                   long long chunk,                 // records per split (multiple of the granule)
                   long long n_pad,                 // total padded records
                   const double* __restrict__ P, long long m,
-                  double* __restrict__ out,        // [gridDim.y][3 m]
-                  const int* __restrict__ flag, int mask, int want) {
+                  double* __restrict__ out,        // [y0 + gridDim.y][3 m]: this launch fills slots y0 .. y0 + gridDim.y - 1
+                  const int* __restrict__ flag, int mask, int want,
+                  int y0) {                        // first source split of this launch (0 unless the splits are shared out
+                                                   // between devices: collocation-point stage of a group, capi.cu)
   if (flag != nullptr && (*flag & mask) != want) return;  // uniform: another form of the set does the work
   constexpr int RD = lat_rec_doubles(W), NP = lat_nodes_pad(W), TILE = lat_tile(W);
   constexpr int RL = DUAL ? RD : lat_core_doubles(W);  // doubles of a record this form reads
@@ -133,7 +135,7 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * RD * 8);
 
   const int tid = threadIdx.x;
-  const long long s_begin = (long long)blockIdx.y * chunk;
+  const long long s_begin = ((long long)blockIdx.y + y0) * chunk;
   long long s_end = s_begin + chunk;
   if (s_end > n_pad) s_end = n_pad;
   const long long len = s_end > s_begin ? s_end - s_begin : 0;  // a multiple of the granule (even)
@@ -225,7 +227,7 @@ bs_lattice_kernel(const double* __restrict__ lat,  // strip records of width W, 
     }
   }
 
-  double* o = out + (size_t)blockIdx.y * 3 * (size_t)m;
+  double* o = out + ((size_t)blockIdx.y + (size_t)y0) * 3 * (size_t)m;
 #pragma unroll
   for (int k = 0; k < T; ++k) {
     const long long t = t0 + (long long)k * THREADS;

@@ -154,6 +154,9 @@ struct vlc_ctx {
   std::vector<Rotor> rotors;
   cusolverDnHandle_t solver = nullptr;
   vlc::grp::Workers* host_pool = nullptr;  // host_parallel
+  // collocation-point sweeps of a group share their source splits from this many pair interactions on (cp_sweep);
+  // VLC_RHS_SHARE_MIN_PAIRS overrides (0 = always, negative = never)
+  double rhs_share_min = std::getenv("VLC_RHS_SHARE_MIN_PAIRS") ? std::atof(std::getenv("VLC_RHS_SHARE_MIN_PAIRS")) : 2e8;
   DevBuf solver_work;
   int occ[5] = {0, 0, 0, 0, 0};  // resident CTAs/SM of the sweep kernel for T = 1..4
   // multi-GPU data plane (group.hpp): this context's place in the target partition, its NCCL communicator (library-owned),
@@ -511,8 +514,18 @@ int plan_lattice_split(const vlc_ctx* c, int W, int T, long long m, long long n_
 // that no host synchronisation is needed: 0 = merged strips + flat remainder; 2 = DUAL strips (streamwise edges whose two
 // copies carry different core radii, bs_lattice.cuh) + the same flat remainder; odd = the flat kernel over the reference
 // enumeration.  bs_reduce_select_kernel sums the slots of whichever form ran, in fixed order.
-int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, double* dV) {
+//
+// share_sources (collocation-point stage of a group / communicator, SURVEY 8e "RHS: shard sources and sum partials"): the
+// targets are few and every member has them all, so the SOURCE SPLITS are shared out instead -- member k launches the
+// k-th part of every slot range into a zeroed partial buffer, an all-reduce (sum) over NVLink completes the buffer on every
+// member (each slot has exactly one non-zero contributor, so the sum is exact whatever NCCL's order), and the same
+// fixed-order reduce follows: the result is bit-identical to one GPU's, for any number of members.
+int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, double* dV, bool share_sources = false) {
   if (m <= 0) return VLC_OK;
+  if (share_sources && !(c->world > 1 && c->comm)) share_sources = false;
+  const int W_ = share_sources ? c->world : 1, k_ = share_sources ? c->rank : 0;
+  auto my_lo = [&](int ns) { return (int)((long long)ns * k_ / W_); };
+  auto my_hi = [&](int ns) { return (int)((long long)ns * (k_ + 1) / W_); };
   struct LatPlan {
     int W = 0, T = 1, ns = 0;
     long long chunk = 0;
@@ -552,21 +565,24 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   double* part_rem = part + (size_t)na * len;
   double* part_dual = part_rem + (size_t)ns_r * len;
   double* part_flat = part_dual + (size_t)nd * len;
+  if (share_sources) CUDA_OK(c, cudaMemsetAsync(part, 0, (size_t)(na + ns_r + nd + pf.nsplit) * len * sizeof(double), c->stream));
   auto launch_lat = [&](const LatPlan& p, bool dual_form, const double* rec, long long n_pad, double* out) -> int {
     if (p.ns <= 0) return VLC_OK;
-    dim3 grid(blocks_for(m, kLatThreads * p.T), (unsigned)p.ns, 1);
+    const int y0 = my_lo(p.ns), yn = my_hi(p.ns) - y0;  // this member's source splits (all of them without sharing)
+    if (yn <= 0) return VLC_OK;
+    dim3 grid(blocks_for(m, kLatThreads * p.T), (unsigned)yn, 1);
     if (!dual_form) {
 #define X(WW, TT, MB)                                                                                            \
   if (p.W == WW && p.T == TT)                                                                                    \
     vlc::bs_lattice_kernel<WW, TT, kLatThreads, kStages, MB><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>( \
-        rec, p.chunk, n_pad, dP, m, out, s.d_unmergeable, 3, 0);
+        rec, p.chunk, n_pad, dP, m, out, s.d_unmergeable, 3, 0, y0);
       VLC_LAT_SHAPES(X)
 #undef X
     } else {
 #define X(WW, MB)                                                                                                     \
   if (p.W == WW)                                                                                                      \
     vlc::bs_lattice_kernel<WW, 1, kLatThreads, kStages, MB, true><<<grid, kLatThreads, lat_smem_of(WW), c->stream>>>( \
-        rec, p.chunk, n_pad, dP, m, out, s.d_unmergeable, 3, 2);
+        rec, p.chunk, n_pad, dP, m, out, s.d_unmergeable, 3, 2, y0);
       VLC_DUAL_SHAPES(X)
 #undef X
     }
@@ -594,13 +610,29 @@ int sweep_shared(vlc_ctx* c, const SourceSet& s, long long m, const double* dP, 
   }
   rc = launch_lat(pm2, false, s.lat2.p, s.n_lat2_pad, part + (size_t)pm.ns * len);
   if (!rc) rc = launch_lat(pd2, true, s.lat2.p, s.n_lat2_pad, part_dual + (size_t)pd.ns * len);
-  if (!rc && ns_r > 0) rc = launch_flat(c, s.rem.p, s.n_rem_pad, pr, m, dP, part_rem, s.d_unmergeable, 1, 0);
-  if (!rc) rc = launch_flat(c, s.rec.p, s.n_pad, pf, m, dP, part_flat, s.d_unmergeable, 1, 1);
+  // the flat kernel needs no record before its chunk: a member's splits are a launch on the tail of the set
+  auto launch_flat_part = [&](const double* src, long long n_pad, const FlatPlan& p, double* out, int want) -> int {
+    const int y0 = my_lo(p.nsplit), yn = my_hi(p.nsplit) - y0;
+    if (yn <= 0) return VLC_OK;
+    FlatPlan q = p;
+    q.nsplit = yn;
+    return launch_flat(c, src + (size_t)y0 * p.chunk * vlc::kSrcDoubles, n_pad - (long long)y0 * p.chunk, q, m, dP,
+                       out + (size_t)y0 * len, s.d_unmergeable, 1, want);
+  };
+  if (!rc && ns_r > 0) rc = launch_flat_part(s.rem.p, s.n_rem_pad, pr, part_rem, 0);
+  if (!rc) rc = launch_flat_part(s.rec.p, s.n_pad, pf, part_flat, 1);
   c->stream = main_stream;  // restored before any early return below
   if (rc) return rc;
   if (side) {
     CUDA_OK(c, cudaEventRecord(c->ev_join, c->aux));
     CUDA_OK(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+  }
+  if (share_sources) {
+    vlc::grp::Nccl& n = vlc::grp::Nccl::get();
+    const int r = n.AllReduce(part, part, (size_t)(na + ns_r + nd + pf.nsplit) * len, vlc::grp::kNcclFloat64, vlc::grp::kNcclSum, c->comm,
+                              (void*)c->stream);
+    if (r != 0) return fail(c, VLC_ERR_CUDA, std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(r) : "?"));
+    c->launches++;
   }
   vlc::bs_reduce_select_kernel<<<blocks_for((long long)len, 256), 256, 0, c->stream>>>(part, s.d_unmergeable, na, ns_r, nd,
                                                                                       pf.nsplit, (long long)len, dV);
@@ -2732,8 +2764,13 @@ extern "C" int vlc_rotor_get_wakevel(vlc_ctx* c, int ir, int ib, int which, doub
 namespace {
 
 // one source set swept at the collocation points held in c->cp_P, result in c->cp_V
+// Collocation points against one packed set.  In a group / communicator a sweep of at least rhs_share_min pair interactions
+// shares its source splits out between the members (sweep_shared: share_sources); below that an all-reduce costs more than
+// the sweep (a caradonna-sized sweep is 70 us on one GPU).
 int cp_sweep(vlc_ctx* c, const double* rec, long long n_pad, long long m, const SourceSet* shared) {
-  return shared ? sweep_shared(c, *shared, m, c->cp_P.p, c->cp_V.p) : sweep(c, rec, n_pad, m, c->cp_P.p, c->cp_V.p);
+  if (!shared) return sweep(c, rec, n_pad, m, c->cp_P.p, c->cp_V.p);
+  const bool share = c->world > 1 && c->comm && c->rhs_share_min >= 0.0 && (double)m * (double)shared->n_pad >= c->rhs_share_min;
+  return sweep_shared(c, *shared, m, c->cp_P.p, c->cp_V.p, share);
 }
 
 int cp_accumulate(vlc_ctx* c, Rotor* r, long long m, int field, int sign) {

@@ -145,6 +145,7 @@ struct NcclUniqueId {
 };
 typedef void* NcclComm;
 constexpr int kNcclFloat64 = 8;  // ncclDataType_t: ncclFloat64 / ncclDouble
+constexpr int kNcclSum = 0;      // ncclRedOp_t: ncclSum
 
 struct Nccl {
   bool ok = false;
@@ -154,6 +155,7 @@ struct Nccl {
   int (*CommInitAll)(NcclComm*, int, const int*) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, NcclComm, void* /*cudaStream_t*/) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int /*ncclRedOp_t*/, NcclComm, void* /*cudaStream_t*/) = nullptr;
   int (*GetVersion)(int*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 
@@ -183,6 +185,7 @@ struct Nccl {
     CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
     AllGather = reinterpret_cast<decltype(AllGather)>(sym("ncclAllGather"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
     GetVersion = reinterpret_cast<decltype(GetVersion)>(sym("ncclGetVersion"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
     ok = why.empty();
