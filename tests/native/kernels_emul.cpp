@@ -333,7 +333,11 @@ int emul_flat_sweep(int fast, int nsplit, long long n, const double* p1, const d
   const long long npad = std::max(1LL, (n + TILE - 1) / TILE) * TILE;
   std::vector<double> rec((size_t)npad * vlc::kSrcDoubles);
   emul_launch(blocks_for(npad, 256), 1, 256, vlc::pack_flat_kernel, n, npad, p1, p2, rvc, gam, wake_flag, rec.data());
-  const long long tiles = npad / TILE, chunk = (tiles + nsplit - 1) / nsplit * TILE;
+  // chunks are multiples of the granule (a quarter tile), as plan_flat cuts a tuned or a small sweep: the last tile of a chunk
+  // may be partial
+  constexpr int GRAN = TILE / 4;
+  const long long units = npad / GRAN, per = (units + nsplit - 1) / nsplit, chunk = per * GRAN;
+  nsplit = (int)((units + per - 1) / per);
   std::vector<double> part((size_t)nsplit * 3 * (size_t)m);
   if (fast)
     emul_launch(blocks_for(m, THREADS * T), (unsigned)nsplit, THREADS, vlc::bs_sweep_kernel<T, THREADS, TILE, 3, 1, true>,

@@ -495,12 +495,13 @@ def test_rsqrt_refinement_with_a_seed_as_coarse_as_the_devices():
 
 
 @pytest.mark.parametrize("n,m,nsplit,fast", [(1, 1, 1, 0), (7, 3, 1, 0), (127, 129, 1, 0), (129, 513, 2, 0), (1000, 77, 3, 0),
-                                             (2000, 520, 4, 0), (1000, 77, 2, 1)])
+                                             (2000, 520, 4, 0), (1000, 77, 2, 1), (234, 104, 8, 0), (600, 130, 7, 0)])
 def test_flat_sweep_kernel_on_the_cpu(oracle, n, m, nsplit, fast):
     """pack_flat_kernel -> bs_sweep_kernel<4, 128, 128, 3> (tile ring, T = 4 targets per thread, source splits) ->
     bs_reduce_kernel on the random sets of tests/test_gpu_parity.py::test_flat_random_vs_oracle (targets on end points and
     on filaments, gam = 0 and |gam| <= eps with and without the wake rule): the same measure and the same bar as on the GPU,
-    err = max|V - V_oracle| / max sum|terms| < 1e-12; second-order precision mode included."""
+    err = max|V - V_oracle| / max sum|terms| < 1e-12; second-order precision mode included.  Chunks are cut in quarter
+    tiles like plan_flat's (the last two cases: 8 chunks of 32 sources; 7 chunks of 96 = three quarters of a tile)."""
     from tests.helpers import scaled_err
     from volcanor_b200 import synth
     p1, p2, rvc, gam, flag, P = synth.random_filaments(n, m, seed=n + m)

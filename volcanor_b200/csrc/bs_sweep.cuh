@@ -17,7 +17,7 @@ namespace vlc {
 template <int T, int THREADS, int TILE, int STAGES, int MINB, bool FAST>
 __global__ void __launch_bounds__(THREADS, MINB)
 bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a multiple of TILE
-                long long chunk,                  // sources per split (multiple of TILE)
+                long long chunk,                  // sources per split (multiple of TILE / 4: the last tile of a chunk may be partial)
                 long long n_src_padded,           // total padded sources (multiple of TILE)
                 const double* __restrict__ P,     // targets (3, m) interleaved
                 long long m,
@@ -38,9 +38,13 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
   const long long s_begin = (long long)blockIdx.y * chunk;
   long long s_end = s_begin + chunk;
   if (s_end > n_src_padded) s_end = n_src_padded;
-  const int ntiles = (s_end > s_begin) ? (int)((s_end - s_begin) / TILE) : 0;
+  const long long len = s_end > s_begin ? s_end - s_begin : 0;  // a multiple of the granule TILE / 4 (even)
+  const int ntiles = (int)((len + TILE - 1) / TILE);
   const double* gsrc = src + s_begin * kSrcDoubles;
-  constexpr uint32_t kTileBytes = TILE * kSrcBytes;
+  auto tile_records = [&](int t) -> int {  // TILE, except for the last tile of a chunk that is not a whole number of tiles
+    const long long left = len - (long long)t * TILE;
+    return left < TILE ? (int)left : TILE;
+  };
 
   if (VLC_PRODUCER(tid)) {
 #pragma unroll
@@ -52,9 +56,9 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
 #pragma unroll
     for (int s = 0; s < STAGES; ++s)
       if (s < ntiles) {
-        mbar_expect_tx(&bars[s], kTileBytes);
-        tma_bulk_g2s(buf + (size_t)s * TILE * kSrcDoubles, gsrc + (size_t)s * TILE * kSrcDoubles, kTileBytes,
-                     &bars[s]);
+        const uint32_t bytes = (uint32_t)tile_records(s) * kSrcBytes;
+        mbar_expect_tx(&bars[s], bytes);
+        tma_bulk_g2s(buf + (size_t)s * TILE * kSrcDoubles, gsrc + (size_t)s * TILE * kSrcDoubles, bytes, &bars[s]);
       }
   }
 
@@ -76,17 +80,22 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
     const uint32_t phase = (uint32_t)(tile / STAGES) & 1u;
     mbar_wait(&bars[stage], phase);
     const double* sb = buf + (size_t)stage * TILE * kSrcDoubles;
-#pragma unroll 2
-    for (int j = 0; j < TILE; ++j) {
+    const int jn = tile_records(tile);
+#pragma unroll 1
+    for (int j2 = 0; j2 < jn; j2 += 2)  // two sources per trip (jn is even): the unroll the fixed-length loop had
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = j2 + jj;
       const Src s = load_src(sb + j * kSrcDoubles);
 #pragma unroll
       for (int k = 0; k < T; ++k) pair_accumulate<FAST>(s, px[k], py[k], pz[k], vx[k], vy[k], vz[k]);
     }
     __syncthreads();  // every warp is done with this stage before it is refilled
     if (VLC_PRODUCER(tid) && tile + STAGES < ntiles) {
-      mbar_expect_tx(&bars[stage], kTileBytes);
-      tma_bulk_g2s(buf + (size_t)stage * TILE * kSrcDoubles, gsrc + (size_t)(tile + STAGES) * TILE * kSrcDoubles,
-                   kTileBytes, &bars[stage]);
+      const uint32_t bytes = (uint32_t)tile_records(tile + STAGES) * kSrcBytes;
+      mbar_expect_tx(&bars[stage], bytes);
+      tma_bulk_g2s(buf + (size_t)stage * TILE * kSrcDoubles, gsrc + (size_t)(tile + STAGES) * TILE * kSrcDoubles, bytes,
+                   &bars[stage]);
     }
   }
 

@@ -321,7 +321,11 @@ int query_occ(vlc_ctx* c, int* out) {
 }
 
 // Launch shape: T targets per thread and nsplit source splits.
-void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, int* nsplit_out) {
+constexpr int kFlatPerTile = 4;                   // a flat chunk is a multiple of a quarter tile (bs_sweep.cuh)
+constexpr int kFlatGranule = kTile / kFlatPerTile;
+// *unit_out = the records a chunk is a multiple of: the granule for a small sweep or a tuned split, else the tile
+void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, int* nsplit_out, int* unit_out) {
+  *unit_out = kFlatGranule;
   const long long src_tiles = n_pad / kTile;
   int T = c->tune_T;
   if (T < 1 || T > 4) {
@@ -333,7 +337,7 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
     if (T == 2) {  // still too small at two targets per thread: one per thread, twice the CTAs
       const long long slots2 = (long long)c->sm_count * (c->occ[2] > 0 ? c->occ[2] : 3);
       const long long tiles2 = (m + kThreads * 2 - 1) / (kThreads * 2);
-      if (vlc::plan::small_split(tiles2, src_tiles, slots2) > 0) T = 1;
+      if (vlc::plan::small_split(tiles2, src_tiles, slots2, kFlatPerTile) > 0) T = 1;
     }
   }
   int nsplit = c->tune_nsplit;
@@ -341,11 +345,15 @@ void choose_shape(const vlc_ctx* c, long long m, long long n_pad, int* T_out, in
     const long long slots = (long long)c->sm_count * (c->occ[T] > 0 ? c->occ[T] : 3);
     const long long tiles = (m + (long long)kThreads * T - 1) / ((long long)kThreads * T);
     const long long cap_by_mem = (long long)((size_t)1 << 31) / (3 * (m > 0 ? m : 1) * 8) + 1;  // <= 2 GiB partials
-    int best_s = vlc::plan::small_split(tiles, src_tiles, slots);
-    if (best_s == 0) best_s = vlc::plan::wave_split(tiles, src_tiles, slots, cap_by_mem);
+    int best_s = vlc::plan::small_split(tiles, src_tiles, slots, kFlatPerTile);
+    if (best_s == 0) {
+      best_s = vlc::plan::wave_split(tiles, src_tiles, slots, cap_by_mem);
+      *unit_out = kTile;
+    }
     nsplit = best_s > 0 ? best_s : 1;
   }
-  if (nsplit > src_tiles) nsplit = (int)(src_tiles > 0 ? src_tiles : 1);
+  const long long units = n_pad / *unit_out;
+  if (nsplit > units) nsplit = (int)(units > 0 ? units : 1);
   *T_out = T;
   *nsplit_out = nsplit;
 }
@@ -357,8 +365,9 @@ struct FlatPlan {
 
 FlatPlan plan_flat(const vlc_ctx* c, long long m, long long n_pad) {
   FlatPlan p;
-  choose_shape(c, m, n_pad, &p.T, &p.nsplit);
-  const vlc::plan::Cut ct = vlc::plan::cut(n_pad, kTile, p.nsplit);
+  int unit = kTile;
+  choose_shape(c, m, n_pad, &p.T, &p.nsplit, &unit);
+  const vlc::plan::Cut ct = vlc::plan::cut(n_pad, unit, p.nsplit);
   p.nsplit = ct.nsplit;
   p.chunk = ct.chunk;
   return p;
