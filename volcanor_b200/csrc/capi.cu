@@ -90,7 +90,9 @@ struct Rotor {
   long long wing_pad[2] = {0, 0};  // padded wing segment length inside comb[s]
   long long wing_n = 0;
   SourceSet bound;
-  bool dirty[2] = {true, true};
+  // packed set s needs (re)building: 0 = no; 1 = all of it (every `dirty[s] = true`); 2 = only its wing segments -- the
+  // wing's records changed (moved wing, new circulation) while the wake records and rows did not (mark_wing_dirty)
+  int dirty[2] = {1, 1};
   bool bound_dirty = true;
   SourceSet chord;  // chordwise-vortex set (classdef.f90:1398-1418), same shape as `bound`
   bool chord_dirty = true;
@@ -896,6 +898,12 @@ struct PackBuilder {
 // shared-node form: strip records per blade + the flat remainder [wing | last column, horseshoe corrections, far wakes].
 // Three launches whatever the rotor looks like: clear the flag, classify the records (check_rings_kernel), pack every
 // segment (pack_table_kernel).
+void mark_wing_dirty(Rotor& r) {
+  for (int s = 0; s < 2; ++s)
+    if (r.dirty[s] == 0) r.dirty[s] = 2;
+  r.bound_dirty = r.chord_dirty = true;
+}
+
 int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   if (!r.dirty[s]) return VLC_OK;
   for (int ib = 0; ib < r.nb; ++ib)
@@ -919,6 +927,17 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   cudaStream_t st = c->stream;
   const long long wiP_blade = (long long)r.nc * r.ns * vlc::kWp, waN_blade = (long long)r.nNwake * r.ns * vlc::kVr;
   const long long waF_blade = (long long)r.nFwake * vlc::kFw, wapF_blade = (long long)VLC_NPFWAKE * vlc::kFw;
+  if (r.dirty[s] == 2 && r.comb[s].n_pad == total_pad && r.wing_pad[s] == wing_pad) {
+    // only the wing changed since the last pack (a solve, a moved wing): its rings again, into the flat enumeration and
+    // into the flat remainder of the shared-node form; the wake's records, strips, flag and padding stand
+    PackBuilder pw;
+    if (wing_n > 0) {
+      pw.rings(r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0, rec, r.nb, wiP_blade, 4LL * r.nc * r.ns);
+      if (r.comb[s].has_shared) pw.rings(r.wiP.p, vlc::kWp, r.nc, 0, r.nc, r.ns, 0xF, 4, 1.0, 0, r.comb[s].rem.p, r.nb, wiP_blade, 4LL * r.nc * r.ns);
+    }
+    r.dirty[s] = 0;
+    return pw.launch(c);
+  }
   PackBuilder pb;
   // ---- the flat enumeration: [wing | padding | per blade: rings, horseshoe correction, far wake, prescribed wake | padding]
   auto flat_segments = [&](double* dst, bool rings_all) {
@@ -959,7 +978,7 @@ int pack_rotor(vlc_ctx* c, Rotor& r, int s) {
   r.comb[s].n_pad = total_pad;
   r.wing_pad[s] = wing_pad;
   r.wing_n = wing_n;
-  r.dirty[s] = false;
+  r.dirty[s] = 0;
 
   // ---- shared-node form of the near wake (bs_lattice.cuh): strips per blade + [wing | remainder] flat ----
   SourceSet& cs = r.comb[s];
@@ -1781,7 +1800,7 @@ extern "C" int vlc_rotor_put_wing(vlc_ctx* c, int ir, int ib, const double* wiP)
   if (!r) return VLC_ERR_STATE;
   if (ib < 0 || ib >= r->nb || !wiP) return fail(c, VLC_ERR_ARG, "bad blade index / null pointer");
   const size_t per = (size_t)r->nc * r->ns * vlc::kWp;
-  r->dirty[0] = r->dirty[1] = r->bound_dirty = r->chord_dirty = true;
+  mark_wing_dirty(*r);
   // The LU factors stay valid: the reference computes AIC once, before the time loop, and keeps using it while the
   // wing moves rigidly (main.f90:65-81); only vlc_rotor_calcAIC replaces them.
   return upload(c, r->wiP, per * r->nb, per * ib, wiP, per);
@@ -1799,7 +1818,7 @@ extern "C" int vlc_rotor_put_wing_gam(vlc_ctx* c, int ir, int ib, const double* 
   CUDA_OK(c, cudaMemcpy2DAsync(r->wiP.p + (size_t)ib * np * vlc::kWp + vlc::kVrGam, vlc::kWp * sizeof(double), gam,
                                sizeof(double), sizeof(double), np, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  r->dirty[0] = r->dirty[1] = r->bound_dirty = r->chord_dirty = true;
+  mark_wing_dirty(*r);
   return VLC_OK;
 }
 
@@ -2867,7 +2886,7 @@ extern "C" int vlc_rotor_solve_map_gam(vlc_ctx* c, int ir, double* gamVec_out) {
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   r->have_rhs = false;  // one solve per right-hand side
-  r->dirty[0] = r->dirty[1] = r->bound_dirty = r->chord_dirty = true;  // the wing's circulation changed
+  mark_wing_dirty(*r);  // the wing's circulation changed
   if (gamVec_out) {
     CUDA_OK(c, cudaMemcpyAsync(gamVec_out, r->gamvec.p, sizeof(double) * r->N, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
