@@ -118,8 +118,16 @@ bs_sweep_kernel(const double* __restrict__ src,   // packed sources, padded to a
 __global__ void bs_reduce_kernel(const double* __restrict__ part, int nsplit, long long len, double* __restrict__ V) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= len) return;
-  double a = part[i];
-  for (int s = 1; s < nsplit; ++s) a += part[(size_t)s * len + i];
+  double a = part[i];  // slots added in order; loads of eight slots in flight (see bs_reduce_select_kernel)
+  int s = 1;
+  for (; s + 8 <= nsplit; s += 8) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = part[(size_t)(s + k) * len + i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += v[k];
+  }
+  for (; s < nsplit; ++s) a += part[(size_t)s * len + i];
   V[i] = a;
 }
 
