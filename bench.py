@@ -495,8 +495,8 @@ def main():
             "`same_work` = the flat kernel on the reference's own enumeration, one sweep after the timed region"
             if shared else "flat kernel on the reference's enumeration: frac = algorithmic 76 flop/pair, pipe_frac = 43 issued FP64 instr/pair")
     # DRAM traffic of the dominant kernel: not measurable outside a profiler; quoted from the committed ncu --set full capture
-    # of THIS command (profiles/r03c_bs_sweep_full.md), and only for the workload and launch shape it was taken on
-    prof = ROOT / "profiles" / "r03c_bs_sweep_full.md"
+    # of THIS command (profiles/r03z_bs_sweep_full.md), and only for the workload and launch shape it was taken on
+    prof = ROOT / "profiles" / "r03z_bs_sweep_full.md"
     traffic, traffic_source = None, None
     if shared and not dual and n_gpus == 1 and n_src == 1000192 and args.lat_w in (0, 4) and args.lat_t in (0, 2) and prof.exists():
         import re
@@ -505,7 +505,7 @@ def main():
         wr = re.search(r"dram__bytes_write\.sum \| ([0-9.]+) \| Mbyte", txt)
         if rd and wr:
             traffic = (float(rd.group(1)) + float(wr.group(1))) * 1e6
-            traffic_source = ("profiles/r03c_bs_sweep_full.md: ncu --set full of this command (same workload, same launch shape), "
+            traffic_source = ("profiles/r03z_bs_sweep_full.md: ncu --set full of this command (same workload, same launch shape), "
                               "dram__bytes_read.sum + dram__bytes_write.sum of one bs_lattice_kernel launch; not re-measured in this "
                               "run. Algorithmic bytes per launch: 36.0 MB of strip records (62 536 x 576 B) + 6.2 MB of targets "
                               "read + 74 MB of source-split partial sums written (12 x 6.2 MB), most of which stay in L2")
