@@ -9,6 +9,8 @@ run() {  # name, tool, timeout, pytest args...
     python -m pytest -m gpu -q -x "$@" > "gpurun_out/sanitizer_${name}.pytest.log" 2>&1
   echo "$name ($tool): rc=$? | $(tail -n 1 gpurun_out/sanitizer_${name}.pytest.log) | $(grep -c 'ERROR SUMMARY: 0 errors\|RACECHECK SUMMARY: 0 hazards' gpurun_out/sanitizer_${name}.log) clean summaries | $(grep -h 'SUMMARY' gpurun_out/sanitizer_${name}.log | sort | uniq -c | tr '\n' ';')"
 }
+run mem_parity   memcheck  900 tests/test_gpu_parity.py -k "not full_size"
+run race_parity  racecheck 900 tests/test_gpu_parity.py -k "flat_random or empty or skipped"
 run mem_lattice  memcheck  900 tests/test_gpu_lattice.py tests/test_gpu_wake_sweep.py -k "not full_size"
 run mem_resident memcheck  900 tests/test_gpu_resident.py tests/test_zz_gpu_cp_stage.py tests/test_gpu_group.py
 run mem_case     memcheck  900 tests/test_case_driver.py -k "golden_history or sub_iterations or dual_form"
