@@ -155,9 +155,15 @@ VLC_HD void section_loads(int nc, int ns, int is, double* wiP, const double* sec
   // ---- chordwise resultant velocity of the section (:2197-2232)
   const double* PC1 = panel(wiP, nc, 1, is) + kPC1;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, r1[3] = {0, 0, 0}, r2[3] = {0, 0, 0}, r3[3] = {0, 0, 0};
+  // Values that are written to the records or the loads block and used again are kept in locals (rv, dd, ld, fi, sl, slu,
+  // nf, nfu below): the same numbers without reading them back from global memory.  (The kernel stays at ~29 us for a
+  // 4 x 26 wing, r03n: ONE warp walking ~3 000 dependent FP64 instructions -- IEEE divisions, atan2, square roots -- per
+  // section; only spreading a section over several threads would shorten it.)
   for (int ic = 1; ic <= nc; ++ic) {
     double* p = panel(wiP, nc, ic, is);
-    noproj3(p + kVelCPTotal, p + kTauSpan, p + kChordwiseResVel);  // wingpanel_calc_chordwiseResVel :917-923
+    double crv[3];
+    noproj3(p + kVelCPTotal, p + kTauSpan, crv);  // wingpanel_calc_chordwiseResVel :917-923
+    for (int i = 0; i < 3; ++i) p[kChordwiseResVel + i] = crv[i];
     const double d[3] = {sub(p[kCP], PC1[0]), sub(p[kCP + 1], PC1[1]), sub(p[kCP + 2], PC1[2])};
     const double x = dot3(d, tauChord);
     const double xx = mul(x, x);
@@ -166,34 +172,42 @@ VLC_HD void section_loads(int nc, int ns, int is, double* wiP, const double* sec
     s3 = add(s3, mul(xx, x));
     s4 = add(s4, mul(mul(xx, x), x));
     for (int i = 0; i < 3; ++i) {
-      const double y = p[kChordwiseResVel + i];
+      const double y = crv[i];
       r1[i] = add(r1[i], y);
       r2[i] = add(r2[i], mul(y, x));
       r3[i] = add(r3[i], mul(y, xx));
     }
   }
+  double rv[3];
   if (nc >= 3) {
     const double d[3] = {sub(secCP[0], PC1[0]), sub(secCP[1], PC1[1]), sub(secCP[2], PC1[2])};
     const double xq = dot3(d, tauChord);
-    for (int i = 0; i < 3; ++i) resVel[i] = lsq2_from_moments(xq, nc, s1, s2, s3, s4, r1[i], r2[i], r3[i]);
+    for (int i = 0; i < 3; ++i) rv[i] = lsq2_from_moments(xq, nc, s1, s2, s3, s4, r1[i], r2[i], r3[i]);
   } else {
-    for (int i = 0; i < 3; ++i) resVel[i] = quo(r1[i], (double)nc);
+    for (int i = 0; i < 3; ++i) rv[i] = quo(r1[i], (double)nc);
   }
-  sec1[ns * kLdAlpha + (is - 1)] = atan2(dot3(resVel, normalVec), dot3(resVel, tauChord));  // :2250-2252
+  for (int i = 0; i < 3; ++i) resVel[i] = rv[i];
+  sec1[ns * kLdAlpha + (is - 1)] = atan2(dot3(rv, normalVec), dot3(rv, tauChord));  // :2250-2252
 
   // ---- lift and drag directions (:2355-2366)
+  double dd[3], ld[3];
   {
     double c[3], u[3];
-    unit3(resVel, dragDir);
-    cross3(dragDir, yAxisAziFlap, c);
+    unit3(rv, dd);
+    cross3(dd, yAxisAziFlap, c);
     unit3(c, u);
     const double sg = sign1(Omega);
-    for (int k = 0; k < 3; ++k) liftDir[k] = mul(sg, u[k]);
+    for (int k = 0; k < 3; ++k) ld[k] = mul(sg, u[k]);
+    for (int k = 0; k < 3; ++k) {
+      dragDir[k] = dd[k];
+      liftDir[k] = ld[k];
+    }
   }
 
   // ---- panel pressures and forces of the section (:1726-1850)
   const double inv = mul(-1.0, sign1(Omega));  // invertGammaSign :1726
-  for (int k = 0; k < 3; ++k) secForceInertial[k] = secLift[k] = secDrag[k] = secLiftUnsteady[k] = 0.0;
+  double fi[3] = {0.0, 0.0, 0.0}, sl[3] = {0.0, 0.0, 0.0}, slu[3] = {0.0, 0.0, 0.0};
+  for (int k = 0; k < 3; ++k) secDrag[k] = 0.0;
   for (int ic = 1; ic <= nc; ++ic) {
     double* p = panel(wiP, nc, ic, is);
     const double gam = p[kGam];
@@ -212,31 +226,39 @@ VLC_HD void section_loads(int nc, int ns, int is, double* wiP, const double* sec
     p[kDelPUnsteady] = delPUnsteady;
     p[kDelP] = delP;
     p[kGamPrev] = gamTrapz;
-    double pl[3], plu[3];
+    double pl[3], plu[3], nf[3], nfu[3];
     for (int k = 0; k < 3; ++k) {
-      p[kNormalForce + k] = mul(mul(delP, p[kPanelArea]), p[kNcap + k]);                          // :1813
-      p[kNormalForceUnsteady + k] = mul(mul(delPUnsteady, p[kPanelArea]), p[kNcap + k]);          // :1816
-      secForceInertial[k] = add(secForceInertial[k], p[kNormalForce + k]);
+      nf[k] = mul(mul(delP, p[kPanelArea]), p[kNcap + k]);            // :1813
+      nfu[k] = mul(mul(delPUnsteady, p[kPanelArea]), p[kNcap + k]);   // :1816
+      p[kNormalForce + k] = nf[k];
+      p[kNormalForceUnsteady + k] = nfu[k];
+      fi[k] = add(fi[k], nf[k]);
     }
-    proj3(p + kNormalForce, liftDir, pl);
-    proj3(p + kNormalForceUnsteady, liftDir, plu);
+    proj3(nf, ld, pl);
+    proj3(nfu, ld, plu);
     for (int k = 0; k < 3; ++k) {
-      secLift[k] = add(secLift[k], pl[k]);
-      secLiftUnsteady[k] = add(secLiftUnsteady[k], plu[k]);
+      sl[k] = add(sl[k], pl[k]);
+      slu[k] = add(slu[k], plu[k]);
     }
+  }
+  for (int k = 0; k < 3; ++k) {
+    secForceInertial[k] = fi[k];
+    secLift[k] = sl[k];
+    secLiftUnsteady[k] = slu[k];
   }
 
   // ---- sectional coefficients (:1861-1892; the drag terms are zero in the reference)
   {
-    const double mag = norm3(resVel);
+    const double mag = norm3(rv);
     const double q = mul(mul(0.5, density), mul(mag, mag));  // getSecDynamicPressure :2058-2069
     double cl = 0.0, cd = 0.0, clu = 0.0;
     if (fabs(q) > kEps) {
-      const double s = sign1(dot3(secLift, zAxisAziFlap));
+      const double zero3[3] = {0.0, 0.0, 0.0};  // secDrag: zero in the reference
+      const double s = sign1(dot3(sl, zAxisAziFlap));
       const double den = mul(q, secArea);
-      cl = quo(mul(norm3(secLift), s), den);
-      cd = quo(norm3(secDrag), den);
-      clu = quo(mul(norm3(secLiftUnsteady), s), den);
+      cl = quo(mul(norm3(sl), s), den);
+      cd = quo(norm3(zero3), den);
+      clu = quo(mul(norm3(slu), s), den);
     }
     sec1[ns * kLdCL + (is - 1)] = cl;
     sec1[ns * kLdCD + (is - 1)] = cd;
