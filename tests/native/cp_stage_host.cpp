@@ -3,6 +3,9 @@
 // (one "thread" per section / entry), so tests/test_cp_stage_host.py can check the arithmetic and the index logic against
 // the oracle bit for bit without a GPU.  Nothing in the product links or loads this file.
 // Build: tests/native/Makefile (g++ -O2 -ffp-contract=off).
+#include <cmath>
+#include <vector>
+
 #include "../../volcanor_b200/csrc/cp_stage.cuh"
 
 extern "C" {
@@ -14,8 +17,14 @@ void cp_host_loads(int nbConvect, int nc, int ns, double density, double dt, dou
     double* w = wiP + (size_t)vlc::cp::kRec * nc * ns * ib;
     const double* s = sec + (size_t)vlc::cp::sec_doubles(ns) * ib;
     double* l = loads + (size_t)vlc::cp::loads_doubles(ns) * ib;
-    for (int is = ns; is >= 1; --is)  // any order: sections are independent
-      vlc::cp::section_loads(nc, ns, is, w, s, density, dt, Omega, spanwiseLiftSwitch, l);
+    // the four phases of cp_loads_kernel, each over its panels / sections in REVERSE order (any order within a phase: a
+    // phase reads only what an earlier phase wrote)
+    std::vector<double> scr((size_t)vlc::cp::kScr * nc * ns, std::nan(""));
+    for (int q = nc * ns - 1; q >= 0; --q) vlc::cp::loads_panel_resvel(nc, ns, q % nc + 1, q / nc + 1, w, s, scr.data());
+    for (int is = ns; is >= 1; --is) vlc::cp::loads_section_dirs(nc, ns, is, w, s, Omega, l, scr.data());
+    for (int q = nc * ns - 1; q >= 0; --q)
+      vlc::cp::loads_panel_forces(nc, ns, q % nc + 1, q / nc + 1, w, density, dt, Omega, spanwiseLiftSwitch, l, scr.data());
+    for (int is = ns; is >= 1; --is) vlc::cp::loads_section_sums(nc, ns, is, s, density, l, scr.data());
     vlc::cp::blade_sum_loads(ns, l);
   }
 }

@@ -110,7 +110,7 @@ struct Rotor {
   vlc::AxiT* d_axi = nullptr;
   std::vector<vlc::AxiT> h_axi;
   // tier 2c (collocation-point stage on the device): right-hand side, circulation vector, section frames, loads
-  DevBuf rhs, gamvec, sec, loads;
+  DevBuf rhs, gamvec, sec, loads, loads_scr;  // loads_scr: per-panel scratch of the loads phases (cp_stage.cuh: kScr)
   bool have_rhs = false;
   std::vector<char> have_sec;  // per blade: vlc_rotor_put_sections seen
   // AIC
@@ -1350,6 +1350,7 @@ extern "C" int vlc_destroy(vlc_ctx* c) {
     release(r.gamvec);
     release(r.sec);
     release(r.loads);
+    release(r.loads_scr);
     release(r.LU);
     release(r.Ainv);
     if (r.d_ipiv) cudaFree(r.d_ipiv);
@@ -2949,8 +2950,10 @@ extern "C" int vlc_rotor_calc_force(vlc_ctx* c, int ir, double density, double d
   for (int ib = 0; ib < r->nbConvect; ++ib)
     if (!r->have_sec[ib]) return fail(c, VLC_ERR_STATE, "vlc_rotor_calc_force before vlc_rotor_put_sections of every convected blade");
   const int npb = r->nc * r->ns, nld = vlc::cp::loads_doubles(r->ns);
-  vlc::cp_loads_kernel<<<r->nbConvect, 64, 0, c->stream>>>(r->nc, r->ns, density, dt, Omega, spanwiseLiftSwitch, r->wiP.p,
-                                                           r->sec.p, r->loads.p);
+  if ((rc = reserve(c, r->loads_scr, (size_t)r->nbConvect * npb * vlc::cp::kScr))) return rc;
+  const int threads = npb >= 256 ? 256 : (npb + 31) / 32 * 32;  // a thread per panel of the blade (strided beyond 256)
+  vlc::cp_loads_kernel<<<r->nbConvect, threads, 0, c->stream>>>(r->nc, r->ns, density, dt, Omega, spanwiseLiftSwitch, r->wiP.p,
+                                                                r->sec.p, r->loads.p, r->loads_scr.p);
   CUDA_OK(c, cudaGetLastError());
   c->launches++;
   if (r->axisym == 1 && r->nb > 1) {  // classdef.f90:4623-4650: blades 2..nb take blade 1's pressures, forces and loads

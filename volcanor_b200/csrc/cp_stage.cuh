@@ -131,48 +131,76 @@ VLC_HD double* panel(double* wiP, int nc, int ic, int is) {  // wiP(ic, is), 1-b
   return wiP + (size_t)kRec * ((size_t)(ic - 1) + (size_t)nc * (is - 1));
 }
 
-// One spanwise section `is` (1-based) of one blade: blade_calc_secChordwiseResVel + secAlpha (classdef.f90:2197-2265),
-// blade_dirLiftDrag (:2355-2366), the section's share of blade_calc_force (:1726-1892).  Reads gam of section is-1
-// (never written here), writes only records of section `is` and slot `is` of the loads block: sections are independent.
-VLC_HD void section_loads(int nc, int ns, int is, double* wiP, const double* sec, double density, double dt, double Omega,
-                          int spanwiseLiftSwitch, double* loads) {
-  const double* tauChord = sec + 3 * (is - 1);
-  const double* normalVec = sec + 3 * ns + 3 * (is - 1);
-  const double* secCP = sec + 6 * ns + 3 * (is - 1);
-  const double secArea = sec[9 * ns + (is - 1)];
-  const double* yAxisAziFlap = sec + 10 * ns;
-  const double* zAxisAziFlap = sec + 10 * ns + 3;
-  double* sec3 = loads + 12;            // (3, ns) blocks
-  double* sec1 = loads + 12 + 21 * ns;  // (ns) blocks
-  double* resVel = sec3 + 3 * ns * kLdResVel + 3 * (is - 1);
-  double* dragDir = sec3 + 3 * ns * kLdDragDir + 3 * (is - 1);
-  double* liftDir = sec3 + 3 * ns * kLdLiftDir + 3 * (is - 1);
-  double* secForceInertial = sec3 + 3 * ns * kLdForceInertial + 3 * (is - 1);
-  double* secLift = sec3 + 3 * ns * kLdLift + 3 * (is - 1);
-  double* secDrag = sec3 + 3 * ns * kLdDrag + 3 * (is - 1);
-  double* secLiftUnsteady = sec3 + 3 * ns * kLdLiftUnsteady + 3 * (is - 1);
+// ---- loads of one blade (blade_calc_secChordwiseResVel + secAlpha classdef.f90:2197-2265, blade_dirLiftDrag :2355-2366,
+// blade_calc_force :1726-1892) in four phases, so that the device gives every PANEL a thread where the work is per panel
+// and every SECTION a thread where the reference adds panels in order:
+//   1 loads_panel_resvel   per panel   chordwise resultant velocity of the panel, its abscissa along the chord
+//   2 loads_section_dirs   per section moments added in panel order, least-squares value at the section point, alpha,
+//                                      drag and lift directions
+//   3 loads_panel_forces   per panel   pressures, normal forces, their components along the section's lift direction
+//   4 loads_section_sums   per section forces added in panel order, sectional coefficients
+// Panel results that a section phase adds travel through a scratch block of kScr doubles per panel.  A phase reads only
+// what an EARLIER phase (or nobody) writes: panels and sections are independent within a phase.  Before r03t one thread per
+// section walked everything (29 us for a 4 x 26 wing: ~3 000 dependent FP64 instructions in one warp); the arithmetic and
+// its order are unchanged (tests/test_cp_stage_host.py: bit for bit against the oracle).
+constexpr int kScr = 16;  // x | chordwiseResVel(3) | lift part of normalForce(3) | of normalForceUnsteady(3) | normalForce(3)
 
-  // ---- chordwise resultant velocity of the section (:2197-2232)
+struct SecPtr {
+  const double *tauChord, *normalVec, *secCP, *yAxisAziFlap, *zAxisAziFlap;
+  double secArea;
+  double *resVel, *dragDir, *liftDir, *secForceInertial, *secLift, *secDrag, *secLiftUnsteady, *sec1;
+};
+VLC_HD SecPtr sec_ptr(int ns, int is, const double* sec, double* loads) {
+  SecPtr q;
+  q.tauChord = sec + 3 * (is - 1);
+  q.normalVec = sec + 3 * ns + 3 * (is - 1);
+  q.secCP = sec + 6 * ns + 3 * (is - 1);
+  q.secArea = sec[9 * ns + (is - 1)];
+  q.yAxisAziFlap = sec + 10 * ns;
+  q.zAxisAziFlap = sec + 10 * ns + 3;
+  double* sec3 = loads + 12;    // (3, ns) blocks
+  q.sec1 = loads + 12 + 21 * ns;  // (ns) blocks
+  q.resVel = sec3 + 3 * ns * kLdResVel + 3 * (is - 1);
+  q.dragDir = sec3 + 3 * ns * kLdDragDir + 3 * (is - 1);
+  q.liftDir = sec3 + 3 * ns * kLdLiftDir + 3 * (is - 1);
+  q.secForceInertial = sec3 + 3 * ns * kLdForceInertial + 3 * (is - 1);
+  q.secLift = sec3 + 3 * ns * kLdLift + 3 * (is - 1);
+  q.secDrag = sec3 + 3 * ns * kLdDrag + 3 * (is - 1);
+  q.secLiftUnsteady = sec3 + 3 * ns * kLdLiftUnsteady + 3 * (is - 1);
+  return q;
+}
+VLC_HD double* scr_of(double* scr, int nc, int ic, int is) { return scr + (size_t)kScr * ((size_t)(ic - 1) + (size_t)nc * (is - 1)); }
+
+// phase 1 (:2197-2232, wingpanel_calc_chordwiseResVel :917-923)
+VLC_HD void loads_panel_resvel(int nc, int ns, int ic, int is, double* wiP, const double* sec, double* scr) {
+  double* p = panel(wiP, nc, ic, is);
+  const double* PC1 = panel(wiP, nc, 1, is) + kPC1;
+  const double* tauChord = sec + 3 * (is - 1);
+  double* o = scr_of(scr, nc, ic, is);
+  double crv[3];
+  noproj3(p + kVelCPTotal, p + kTauSpan, crv);
+  for (int i = 0; i < 3; ++i) p[kChordwiseResVel + i] = crv[i];
+  const double d[3] = {sub(p[kCP], PC1[0]), sub(p[kCP + 1], PC1[1]), sub(p[kCP + 2], PC1[2])};
+  o[0] = dot3(d, tauChord);
+  for (int i = 0; i < 3; ++i) o[1 + i] = crv[i];
+  (void)ns;
+}
+
+// phase 2 (:2197-2265, :2355-2366)
+VLC_HD void loads_section_dirs(int nc, int ns, int is, double* wiP, const double* sec, double Omega, double* loads, double* scr) {
+  const SecPtr q = sec_ptr(ns, is, sec, loads);
   const double* PC1 = panel(wiP, nc, 1, is) + kPC1;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, r1[3] = {0, 0, 0}, r2[3] = {0, 0, 0}, r3[3] = {0, 0, 0};
-  // Values that are written to the records or the loads block and used again are kept in locals (rv, dd, ld, fi, sl, slu,
-  // nf, nfu below): the same numbers without reading them back from global memory.  (The kernel stays at ~29 us for a
-  // 4 x 26 wing, r03n: ONE warp walking ~3 000 dependent FP64 instructions -- IEEE divisions, atan2, square roots -- per
-  // section; only spreading a section over several threads would shorten it.)
   for (int ic = 1; ic <= nc; ++ic) {
-    double* p = panel(wiP, nc, ic, is);
-    double crv[3];
-    noproj3(p + kVelCPTotal, p + kTauSpan, crv);  // wingpanel_calc_chordwiseResVel :917-923
-    for (int i = 0; i < 3; ++i) p[kChordwiseResVel + i] = crv[i];
-    const double d[3] = {sub(p[kCP], PC1[0]), sub(p[kCP + 1], PC1[1]), sub(p[kCP + 2], PC1[2])};
-    const double x = dot3(d, tauChord);
+    const double* o = scr_of(scr, nc, ic, is);
+    const double x = o[0];
     const double xx = mul(x, x);
     s1 = add(s1, x);
     s2 = add(s2, xx);
     s3 = add(s3, mul(xx, x));
     s4 = add(s4, mul(mul(xx, x), x));
     for (int i = 0; i < 3; ++i) {
-      const double y = crv[i];
+      const double y = o[1 + i];
       r1[i] = add(r1[i], y);
       r2[i] = add(r2[i], mul(y, x));
       r3[i] = add(r3[i], mul(y, xx));
@@ -180,90 +208,93 @@ VLC_HD void section_loads(int nc, int ns, int is, double* wiP, const double* sec
   }
   double rv[3];
   if (nc >= 3) {
-    const double d[3] = {sub(secCP[0], PC1[0]), sub(secCP[1], PC1[1]), sub(secCP[2], PC1[2])};
-    const double xq = dot3(d, tauChord);
+    const double d[3] = {sub(q.secCP[0], PC1[0]), sub(q.secCP[1], PC1[1]), sub(q.secCP[2], PC1[2])};
+    const double xq = dot3(d, q.tauChord);
     for (int i = 0; i < 3; ++i) rv[i] = lsq2_from_moments(xq, nc, s1, s2, s3, s4, r1[i], r2[i], r3[i]);
   } else {
     for (int i = 0; i < 3; ++i) rv[i] = quo(r1[i], (double)nc);
   }
-  for (int i = 0; i < 3; ++i) resVel[i] = rv[i];
-  sec1[ns * kLdAlpha + (is - 1)] = atan2(dot3(rv, normalVec), dot3(rv, tauChord));  // :2250-2252
-
-  // ---- lift and drag directions (:2355-2366)
-  double dd[3], ld[3];
-  {
-    double c[3], u[3];
-    unit3(rv, dd);
-    cross3(dd, yAxisAziFlap, c);
-    unit3(c, u);
-    const double sg = sign1(Omega);
-    for (int k = 0; k < 3; ++k) ld[k] = mul(sg, u[k]);
-    for (int k = 0; k < 3; ++k) {
-      dragDir[k] = dd[k];
-      liftDir[k] = ld[k];
-    }
+  for (int i = 0; i < 3; ++i) q.resVel[i] = rv[i];
+  q.sec1[ns * kLdAlpha + (is - 1)] = atan2(dot3(rv, q.normalVec), dot3(rv, q.tauChord));  // :2250-2252
+  double dd[3], c[3], u[3];
+  unit3(rv, dd);
+  cross3(dd, q.yAxisAziFlap, c);
+  unit3(c, u);
+  const double sg = sign1(Omega);
+  for (int k = 0; k < 3; ++k) {
+    q.dragDir[k] = dd[k];
+    q.liftDir[k] = mul(sg, u[k]);
   }
+}
 
-  // ---- panel pressures and forces of the section (:1726-1850)
+// phase 3 (:1726-1850)
+VLC_HD void loads_panel_forces(int nc, int ns, int ic, int is, double* wiP, double density, double dt, double Omega,
+                               int spanwiseLiftSwitch, const double* loads, double* scr) {
+  const double* liftDir = loads + 12 + 3 * ns * kLdLiftDir + 3 * (is - 1);
+  double* o = scr_of(scr, nc, ic, is);
   const double inv = mul(-1.0, sign1(Omega));  // invertGammaSign :1726
+  double* p = panel(wiP, nc, ic, is);
+  const double gam = p[kGam];
+  const double velTangentialChord = dot3(p + kVelCP, p + kTauChord);
+  const double velTangentialSpan = dot3(p + kVelCP, p + kTauSpan);
+  const double gamChordPrev = ic > 1 ? panel(wiP, nc, ic - 1, is)[kGam] : 0.0;
+  double gamElementChord = ic == 1 ? gam : sub(gam, gamChordPrev);
+  double gamElementSpan = is == 1 ? gam : sub(gam, panel(wiP, nc, ic, is - 1)[kGam]);
+  gamElementChord = mul(inv, gamElementChord);
+  gamElementSpan = mul(inv, gamElementSpan);
+  const double gamTrapz = ic > 1 ? mul(mul(inv, 0.5), add(gam, gamChordPrev)) : mul(mul(inv, 0.5), gam);  // :1774-1780
+  p[kGamTrapz] = gamTrapz;
+  const double delPUnsteady = quo(mul(density, sub(gamTrapz, p[kGamPrev])), dt);  // :1786
+  double delP = add(delPUnsteady, quo(mul(mul(density, velTangentialChord), gamElementChord), p[kMeanChord]));  // :1789
+  if (spanwiseLiftSwitch != 0) delP = add(delP, quo(mul(mul(density, velTangentialSpan), gamElementSpan), p[kMeanSpan]));
+  p[kDelPUnsteady] = delPUnsteady;
+  p[kDelP] = delP;
+  p[kGamPrev] = gamTrapz;
+  double nf[3], nfu[3];
+  for (int k = 0; k < 3; ++k) {
+    nf[k] = mul(mul(delP, p[kPanelArea]), p[kNcap + k]);            // :1813
+    nfu[k] = mul(mul(delPUnsteady, p[kPanelArea]), p[kNcap + k]);   // :1816
+    p[kNormalForce + k] = nf[k];
+    p[kNormalForceUnsteady + k] = nfu[k];
+    o[10 + k] = nf[k];
+  }
+  proj3(nf, liftDir, o + 4);
+  proj3(nfu, liftDir, o + 7);
+}
+
+// phase 4 (:1813-1892; the drag terms are zero in the reference)
+VLC_HD void loads_section_sums(int nc, int ns, int is, const double* sec, double density, double* loads, double* scr) {
+  const SecPtr q = sec_ptr(ns, is, sec, loads);
   double fi[3] = {0.0, 0.0, 0.0}, sl[3] = {0.0, 0.0, 0.0}, slu[3] = {0.0, 0.0, 0.0};
-  for (int k = 0; k < 3; ++k) secDrag[k] = 0.0;
   for (int ic = 1; ic <= nc; ++ic) {
-    double* p = panel(wiP, nc, ic, is);
-    const double gam = p[kGam];
-    const double velTangentialChord = dot3(p + kVelCP, p + kTauChord);
-    const double velTangentialSpan = dot3(p + kVelCP, p + kTauSpan);
-    const double gamChordPrev = ic > 1 ? panel(wiP, nc, ic - 1, is)[kGam] : 0.0;
-    double gamElementChord = ic == 1 ? gam : sub(gam, gamChordPrev);
-    double gamElementSpan = is == 1 ? gam : sub(gam, panel(wiP, nc, ic, is - 1)[kGam]);
-    gamElementChord = mul(inv, gamElementChord);
-    gamElementSpan = mul(inv, gamElementSpan);
-    const double gamTrapz = ic > 1 ? mul(mul(inv, 0.5), add(gam, gamChordPrev)) : mul(mul(inv, 0.5), gam);  // :1774-1780
-    p[kGamTrapz] = gamTrapz;
-    const double delPUnsteady = quo(mul(density, sub(gamTrapz, p[kGamPrev])), dt);  // :1786
-    double delP = add(delPUnsteady, quo(mul(mul(density, velTangentialChord), gamElementChord), p[kMeanChord]));  // :1789
-    if (spanwiseLiftSwitch != 0) delP = add(delP, quo(mul(mul(density, velTangentialSpan), gamElementSpan), p[kMeanSpan]));
-    p[kDelPUnsteady] = delPUnsteady;
-    p[kDelP] = delP;
-    p[kGamPrev] = gamTrapz;
-    double pl[3], plu[3], nf[3], nfu[3];
+    const double* o = scr_of(scr, nc, ic, is);
+    for (int k = 0; k < 3; ++k) fi[k] = add(fi[k], o[10 + k]);
     for (int k = 0; k < 3; ++k) {
-      nf[k] = mul(mul(delP, p[kPanelArea]), p[kNcap + k]);            // :1813
-      nfu[k] = mul(mul(delPUnsteady, p[kPanelArea]), p[kNcap + k]);   // :1816
-      p[kNormalForce + k] = nf[k];
-      p[kNormalForceUnsteady + k] = nfu[k];
-      fi[k] = add(fi[k], nf[k]);
-    }
-    proj3(nf, ld, pl);
-    proj3(nfu, ld, plu);
-    for (int k = 0; k < 3; ++k) {
-      sl[k] = add(sl[k], pl[k]);
-      slu[k] = add(slu[k], plu[k]);
+      sl[k] = add(sl[k], o[4 + k]);
+      slu[k] = add(slu[k], o[7 + k]);
     }
   }
   for (int k = 0; k < 3; ++k) {
-    secForceInertial[k] = fi[k];
-    secLift[k] = sl[k];
-    secLiftUnsteady[k] = slu[k];
+    q.secForceInertial[k] = fi[k];
+    q.secLift[k] = sl[k];
+    q.secDrag[k] = 0.0;
+    q.secLiftUnsteady[k] = slu[k];
   }
-
-  // ---- sectional coefficients (:1861-1892; the drag terms are zero in the reference)
-  {
-    const double mag = norm3(rv);
-    const double q = mul(mul(0.5, density), mul(mag, mag));  // getSecDynamicPressure :2058-2069
-    double cl = 0.0, cd = 0.0, clu = 0.0;
-    if (fabs(q) > kEps) {
-      const double zero3[3] = {0.0, 0.0, 0.0};  // secDrag: zero in the reference
-      const double s = sign1(dot3(sl, zAxisAziFlap));
-      const double den = mul(q, secArea);
-      cl = quo(mul(norm3(sl), s), den);
-      cd = quo(norm3(zero3), den);
-      clu = quo(mul(norm3(slu), s), den);
-    }
-    sec1[ns * kLdCL + (is - 1)] = cl;
-    sec1[ns * kLdCD + (is - 1)] = cd;
-    sec1[ns * kLdCLu + (is - 1)] = clu;
+  const double rv[3] = {q.resVel[0], q.resVel[1], q.resVel[2]};
+  const double mag = norm3(rv);
+  const double qd = mul(mul(0.5, density), mul(mag, mag));  // getSecDynamicPressure :2058-2069
+  double cl = 0.0, cd = 0.0, clu = 0.0;
+  if (fabs(qd) > kEps) {
+    const double zero3[3] = {0.0, 0.0, 0.0};  // secDrag
+    const double s = sign1(dot3(sl, q.zAxisAziFlap));
+    const double den = mul(qd, q.secArea);
+    cl = quo(mul(norm3(sl), s), den);
+    cd = quo(norm3(zero3), den);
+    clu = quo(mul(norm3(slu), s), den);
   }
+  q.sec1[ns * kLdCL + (is - 1)] = cl;
+  q.sec1[ns * kLdCD + (is - 1)] = cd;
+  q.sec1[ns * kLdCLu + (is - 1)] = clu;
 }
 
 // sumSecToNetForces (classdef.f90:2368-2380): sections added in order is = 1..ns
@@ -346,15 +377,25 @@ __global__ void cp_map_gam_kernel(int nb, int npb, int nbConvect, int axisym, co
   if (src >= 0) wiP[(size_t)cp::kRec * i + cp::kGam] = gamVec[src];
 }
 
-// One CTA per convected blade, one thread per spanwise section (strided); thread 0 then adds the sections in order.
+// One CTA per convected blade; the four phases of the loads (cp::loads_*) with the CTA's threads over panels, sections,
+// panels, sections (strided), a barrier between phases (the scratch block and the loads block are global memory: writes of
+// a phase are visible to the CTA after __syncthreads); thread 0 then adds the sections in order.
 __global__ void cp_loads_kernel(int nc, int ns, double density, double dt, double Omega, int spanwiseLiftSwitch,
-                                double* __restrict__ wiP, const double* __restrict__ sec, double* __restrict__ loads) {
-  const int ib = blockIdx.x;
-  double* w = wiP + (size_t)cp::kRec * nc * ns * ib;
+                                double* __restrict__ wiP, const double* __restrict__ sec, double* __restrict__ loads,
+                                double* __restrict__ scratch) {
+  const int ib = blockIdx.x, np = nc * ns;
+  double* w = wiP + (size_t)cp::kRec * np * ib;
   const double* s = sec + (size_t)cp::sec_doubles(ns) * ib;
   double* l = loads + (size_t)cp::loads_doubles(ns) * ib;
-  for (int is = 1 + threadIdx.x; is <= ns; is += blockDim.x)
-    cp::section_loads(nc, ns, is, w, s, density, dt, Omega, spanwiseLiftSwitch, l);
+  double* scr = scratch + (size_t)cp::kScr * np * ib;
+  for (int q = threadIdx.x; q < np; q += blockDim.x) cp::loads_panel_resvel(nc, ns, q % nc + 1, q / nc + 1, w, s, scr);
+  __syncthreads();
+  for (int is = 1 + threadIdx.x; is <= ns; is += blockDim.x) cp::loads_section_dirs(nc, ns, is, w, s, Omega, l, scr);
+  __syncthreads();
+  for (int q = threadIdx.x; q < np; q += blockDim.x)
+    cp::loads_panel_forces(nc, ns, q % nc + 1, q / nc + 1, w, density, dt, Omega, spanwiseLiftSwitch, l, scr);
+  __syncthreads();
+  for (int is = 1 + threadIdx.x; is <= ns; is += blockDim.x) cp::loads_section_sums(nc, ns, is, s, density, l, scr);
   __syncthreads();
   if (threadIdx.x == 0) cp::blade_sum_loads(ns, l);
 }
