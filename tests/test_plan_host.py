@@ -103,3 +103,29 @@ def test_cut_covers_all_records_in_unit_multiples(plib, n_pad, unit, nsplit):
     ns, chunk = _cut(plib, n_pad, unit, nsplit)
     assert 1 <= ns <= nsplit and chunk % unit == 0
     assert (ns - 1) * chunk < n_pad <= ns * chunk
+
+
+def test_planner_invariants_on_random_shapes(plib):
+    """Whatever the sweep looks like: 1 <= splits <= 256, the cut covers every record exactly once in multiples of the unit,
+    a wave split never cuts below 4 tiles per chunk, a small split never asks for more splits than there are units."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=400, deadline=None)
+    @given(ttiles=st.integers(1, 20000), tiles=st.integers(1, 200000), occ=st.integers(1, 6), per_tile=st.sampled_from([1, 4]),
+           cap=st.integers(1, 4096))
+    def check(ttiles, tiles, occ, per_tile, cap):
+        slots = 148 * occ
+        unit = 32 // per_tile if per_tile == 4 else 32
+        n_pad = tiles * 32
+        s = plib.plan_small_split(ttiles, tiles, slots, per_tile)
+        if s:
+            assert 1 <= s <= min(256, tiles * per_tile)
+            ns, chunk = _cut(plib, n_pad, 32 // per_tile, s)
+            assert ns == s and chunk % (32 // per_tile) == 0 and (ns - 1) * chunk < n_pad <= ns * chunk
+        w = plib.plan_wave_split(ttiles, tiles, slots, cap, per_tile)
+        assert 1 <= w <= max(1, min(256, cap, tiles // 4))
+        ns, chunk = _cut(plib, n_pad, unit, w)
+        assert ns == w and chunk % unit == 0 and (ns - 1) * chunk < n_pad <= ns * chunk
+        assert chunk >= min(n_pad, 4 * 32) - 32 or w == 1
+
+    check()
